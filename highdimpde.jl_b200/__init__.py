@@ -1,0 +1,20 @@
+"""hdpde_b200 — B200-native (sm_100a) Monte-Carlo hot path of SciML/HighDimPDE.jl.
+
+Host-side mirror of the reference interface for the accelerated path
+(`PIDEProblem` / `ParabolicPDEProblem`, `MLP`, `solve`, the samplers, `_reflect`,
+`sde_loop!`) over the C ABI of libhdpde_b200.so (include/hdpde.h).  The directory
+is named `highdimpde.jl_b200`; import it through the `hdpde_b200` shim at the
+repo root.  There is no CPU fallback: without the CUDA library and a B200 the
+calls raise.
+"""
+from . import _capi as capi
+from ._capi import Handle, HdpError, StartOutsideDomain, default_handle, load_library, set_default_handle
+from . import kinds
+from .kinds import (ConstCoef, LinearCoef, SumSq, InvSumSq, ExpSumSq, MinCoord, GaussDensity, FZero, FLinear,
+                    FAllenCahn, FDefaultRisk, FFisherKPP, FNLAllenCahnDiff, FNLFisher, FNLReplicatorMutator)
+from .sampling import UniformSampling, NormalSampling, NoSampling, _integrate
+from .problems import PIDEProblem, ParabolicPDEProblem, PIDESolution
+from .mlp import MLP, solve, mlp_counts, _ml_picard_batch
+from .sde import _reflect, sde_loop
+
+__all__ = [n for n in dir() if not n.startswith("__")]

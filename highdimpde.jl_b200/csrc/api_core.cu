@@ -1,0 +1,367 @@
+// api_core.cu — handle lifecycle, error reporting, NCCL plumbing (dlopen),
+// random-tape materialisation and the FP32/FP64 pipe-peak microbenchmark.
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <string.h>
+#include "hdp_context.h"
+#include "hdp_device.cuh"
+
+using namespace hdp;
+
+static thread_local std::string g_create_err;
+
+namespace hdp {
+
+int set_err(hdp_context* h, int code, const char* fmt, ...)
+{
+    char tmp[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(tmp, sizeof(tmp), fmt, ap);
+    va_end(ap);
+    if (h) h->err = tmp;
+    else g_create_err = tmp;
+    return code;
+}
+
+void* ensure(hdp_context* h, int which, size_t bytes)
+{
+    DevBuf& b = h->buf[which];
+    if (bytes == 0) bytes = 16;
+    if (b.cap >= bytes) return b.p;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 4;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        want = bytes;
+        e = cudaMalloc(&b.p, want);
+    }
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        set_err(h, HDP_ERR_ALLOC, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        b.p = nullptr;
+        return nullptr;
+    }
+    b.cap = want;
+    return b.p;
+}
+
+} // namespace hdp
+
+extern "C" int hdp_version(void) { return HDP_VERSION; }
+
+extern "C" const char* hdp_last_error(hdp_handle h)
+{
+    return h ? h->err.c_str() : g_create_err.c_str();
+}
+
+extern "C" int hdp_create(hdp_handle* out, int device)
+{
+    if (!out) return set_err(nullptr, HDP_ERR_BAD_ARG, "hdp_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        (void)cudaGetLastError();
+        return set_err(nullptr, HDP_ERR_NO_DEVICE,
+                       "no usable CUDA device (%s); libhdpde_b200 has no CPU fallback",
+                       e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+    }
+    if (device >= n) return set_err(nullptr, HDP_ERR_BAD_ARG, "device %d out of range (count %d)", device, n);
+    hdp_context* h = new hdp_context();
+    h->device = device;
+    DeviceGuard g(device);
+    if (cudaGetDeviceProperties(&h->prop, device) != cudaSuccess) {
+        delete h;
+        return set_err(nullptr, HDP_ERR_CUDA, "cudaGetDeviceProperties failed");
+    }
+    if (h->prop.major < 10) {
+        int maj = h->prop.major, min = h->prop.minor;
+        delete h;
+        return set_err(nullptr, HDP_ERR_NO_DEVICE,
+                       "device %d is sm_%d%d; libhdpde_b200 carries sm_100a code only", device, maj, min);
+    }
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
+        cudaMalloc(&h->d_flags, 64 * sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&h->d_ctr, 64 * sizeof(unsigned long long)) != cudaSuccess) {
+        const char* m = cudaGetErrorString(cudaGetLastError());
+        delete h;
+        return set_err(nullptr, HDP_ERR_CUDA, "handle setup failed: %s", m);
+    }
+    cudaMemset(h->d_flags, 0, 64 * sizeof(int));
+    cudaMemset(h->d_ctr, 0, 64 * sizeof(unsigned long long));
+    *out = h;
+    return HDP_OK;
+}
+
+extern "C" int hdp_comm_destroy(hdp_handle h);
+
+extern "C" int hdp_destroy(hdp_handle h)
+{
+    if (!h) return HDP_OK;
+    {
+        DeviceGuard g(h->device);
+        cudaStreamSynchronize(h->stream);
+        hdp_comm_destroy(h);
+        h->plans.clear();
+        for (auto& b : h->buf)
+            if (b.p) cudaFree(b.p);
+        if (h->d_flags) cudaFree(h->d_flags);
+        if (h->d_ctr) cudaFree(h->d_ctr);
+        if (h->ev0) cudaEventDestroy(h->ev0);
+        if (h->ev1) cudaEventDestroy(h->ev1);
+        if (h->stream) cudaStreamDestroy(h->stream);
+    }
+    delete h;
+    return HDP_OK;
+}
+
+extern "C" int hdp_sync(hdp_handle h)
+{
+    if (!h) return HDP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    HDP_CUDA(h, cudaStreamSynchronize(h->stream));
+    return HDP_OK;
+}
+
+extern "C" int hdp_device_info(hdp_handle h, hdp_devinfo* out)
+{
+    if (!h || !out) return HDP_ERR_BAD_ARG;
+    memset(out, 0, sizeof(*out));
+    out->device = h->device;
+    out->sm_count = h->prop.multiProcessorCount;
+    out->cc_major = h->prop.major;
+    out->cc_minor = h->prop.minor;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device);
+    out->clock_khz = khz;
+    out->nccl_rank = h->nccl_rank;
+    out->nccl_nranks = h->nccl_nranks;
+    out->total_mem = h->prop.totalGlobalMem;
+    strncpy(out->name, h->prop.name, sizeof(out->name) - 1);
+    return HDP_OK;
+}
+
+// ---------------------------------------------------------------------
+// NCCL via dlopen: no link-time dependency, and when the host process has
+// already loaded a libnccl.so.2 (e.g. torch's) that one is reused.
+// ---------------------------------------------------------------------
+namespace {
+typedef struct { char internal[128]; } nccl_uid;
+typedef int (*fn_GetUniqueId)(nccl_uid*);
+typedef int (*fn_CommInitRank)(void**, int, nccl_uid, int);
+typedef int (*fn_CommDestroy)(void*);
+typedef int (*fn_AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef const char* (*fn_GetErrorString)(int);
+struct NcclApi {
+    void* lib = nullptr;
+    fn_GetUniqueId GetUniqueId = nullptr;
+    fn_CommInitRank CommInitRank = nullptr;
+    fn_CommDestroy CommDestroy = nullptr;
+    fn_AllReduce AllReduce = nullptr;
+    fn_GetErrorString GetErrorString = nullptr;
+    std::string err;
+};
+NcclApi* nccl_api()
+{
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (api.lib) break;
+        }
+        if (!api.lib) { api.err = std::string("dlopen libnccl.so.2 failed: ") + dlerror(); return; }
+        api.GetUniqueId = (fn_GetUniqueId)dlsym(api.lib, "ncclGetUniqueId");
+        api.CommInitRank = (fn_CommInitRank)dlsym(api.lib, "ncclCommInitRank");
+        api.CommDestroy = (fn_CommDestroy)dlsym(api.lib, "ncclCommDestroy");
+        api.AllReduce = (fn_AllReduce)dlsym(api.lib, "ncclAllReduce");
+        api.GetErrorString = (fn_GetErrorString)dlsym(api.lib, "ncclGetErrorString");
+        if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce)
+            api.err = "libnccl.so.2 lacks required symbols";
+    });
+    return &api;
+}
+const int kNcclFloat64 = 8; // ncclDouble
+const int kNcclSum = 0;     // ncclSum
+} // namespace
+
+extern "C" int hdp_nccl_unique_id(uint8_t id_out[128])
+{
+    NcclApi* a = nccl_api();
+    if (!a->err.empty()) return set_err(nullptr, HDP_ERR_NCCL, "%s", a->err.c_str());
+    nccl_uid id;
+    int rc = a->GetUniqueId(&id);
+    if (rc != 0) return set_err(nullptr, HDP_ERR_NCCL, "ncclGetUniqueId: %s", a->GetErrorString ? a->GetErrorString(rc) : "?");
+    memcpy(id_out, id.internal, 128);
+    return HDP_OK;
+}
+
+extern "C" int hdp_comm_init_rank(hdp_handle h, const uint8_t id[128], int nranks, int rank)
+{
+    if (!h || !id || nranks < 1 || rank < 0 || rank >= nranks) return HDP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    NcclApi* a = nccl_api();
+    if (!a->err.empty()) return set_err(h, HDP_ERR_NCCL, "%s", a->err.c_str());
+    DeviceGuard g(h->device);
+    if (h->nccl_comm) { a->CommDestroy(h->nccl_comm); h->nccl_comm = nullptr; }
+    nccl_uid uid;
+    memcpy(uid.internal, id, 128);
+    int rc = a->CommInitRank(&h->nccl_comm, nranks, uid, rank);
+    if (rc != 0) {
+        h->nccl_comm = nullptr;
+        return set_err(h, HDP_ERR_NCCL, "ncclCommInitRank: %s", a->GetErrorString ? a->GetErrorString(rc) : "?");
+    }
+    h->nccl_rank = rank;
+    h->nccl_nranks = nranks;
+    return HDP_OK;
+}
+
+extern "C" int hdp_comm_destroy(hdp_handle h)
+{
+    if (!h) return HDP_ERR_BAD_ARG;
+    if (h->nccl_comm) {
+        NcclApi* a = nccl_api();
+        if (a->CommDestroy) a->CommDestroy(h->nccl_comm);
+        h->nccl_comm = nullptr;
+    }
+    h->nccl_rank = 0;
+    h->nccl_nranks = 1;
+    return HDP_OK;
+}
+
+namespace hdp {
+int nccl_allreduce_f64_device(hdp_context* h, double* dbuf, size_t n)
+{
+    if (!h->nccl_comm || h->nccl_nranks <= 1) return HDP_OK;
+    NcclApi* a = nccl_api();
+    int rc = a->AllReduce(dbuf, dbuf, n, kNcclFloat64, kNcclSum, h->nccl_comm, h->stream);
+    if (rc != 0) return set_err(h, HDP_ERR_NCCL, "ncclAllReduce: %s", a->GetErrorString ? a->GetErrorString(rc) : "?");
+    return HDP_OK;
+}
+} // namespace hdp
+
+extern "C" int hdp_comm_allreduce_f64(hdp_handle h, double* buf, size_t n)
+{
+    if (!h || !buf) return HDP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    double* d = (double*)ensure(h, hdp_context::B_A, n * sizeof(double));
+    if (!d) return HDP_ERR_ALLOC;
+    HDP_CUDA(h, cudaMemcpyAsync(d, buf, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    int rc = nccl_allreduce_f64_device(h, d, n);
+    if (rc != HDP_OK) return rc;
+    HDP_CUDA(h, cudaMemcpyAsync(buf, d, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    HDP_CUDA(h, cudaStreamSynchronize(h->stream));
+    return HDP_OK;
+}
+
+// ---------------------------------------------------------------------
+// tape materialisation: out[o*width + i] = draw(stream, ordinal0+o, i)
+// ---------------------------------------------------------------------
+template <typename T>
+__global__ void tape_fill_kernel(T* __restrict__ out, int stream, int want_normal, u64 seed, u64 ord0,
+                                 u64 n_ord, int width)
+{
+    constexpr int VEC = Tr<T>::VEC;
+    const u64 ngroups = ((u64)width + VEC - 1) / VEC;
+    const u64 total = n_ord * ngroups;
+    for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (u64)gridDim.x * blockDim.x) {
+        u64 o = w / ngroups;
+        uint32_t grp = (uint32_t)(w % ngroups);
+        Vec<T> v = draw_vec<T>(seed, stream, ord0 + o, grp, want_normal != 0);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            u64 i = (u64)grp * VEC + e;
+            if (i < (u64)width) out[o * (u64)width + i] = v.v[e];
+        }
+    }
+}
+
+template <typename T>
+static int tape_fill_impl(hdp_handle h, T* out, int stream, int want_normal, int normal_mode, u64 seed,
+                          u64 ord0, u64 n_ord, int width)
+{
+    if (!h || !out || width <= 0) return HDP_ERR_BAD_ARG;
+    if (normal_mode != HDP_NORMAL_DEFAULT &&
+        normal_mode != (sizeof(T) == 8 ? HDP_NORMAL_BM64 : HDP_NORMAL_BM32))
+        return set_err(h, HDP_ERR_UNSUPPORTED, "normal_mode %d not supported for this element type", normal_mode);
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    size_t n = (size_t)n_ord * (size_t)width;
+    if (n == 0) return HDP_OK;
+    T* d = (T*)ensure(h, hdp_context::B_A, n * sizeof(T));
+    if (!d) return HDP_ERR_ALLOC;
+    int blocks = h->prop.multiProcessorCount * 8;
+    tape_fill_kernel<T><<<blocks, 256, 0, h->stream>>>(d, stream, want_normal, seed, ord0, n_ord, width);
+    HDP_CUDA(h, cudaGetLastError());
+    HDP_CUDA(h, cudaMemcpyAsync(out, d, n * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+    HDP_CUDA(h, cudaStreamSynchronize(h->stream));
+    return HDP_OK;
+}
+
+extern "C" int hdp_tape_fill_f64(hdp_handle h, double* out, int stream, int want_normal, int normal_mode,
+                                 uint64_t seed, uint64_t ordinal0, uint64_t n_ord, int width)
+{
+    return tape_fill_impl<double>(h, out, stream, want_normal, normal_mode, seed, ordinal0, n_ord, width);
+}
+extern "C" int hdp_tape_fill_f32(hdp_handle h, float* out, int stream, int want_normal, int normal_mode,
+                                 uint64_t seed, uint64_t ordinal0, uint64_t n_ord, int width)
+{
+    return tape_fill_impl<float>(h, out, stream, want_normal, normal_mode, seed, ordinal0, n_ord, width);
+}
+
+// ---------------------------------------------------------------------
+// pipe-peak microbenchmark: 8 independent FMA chains per thread
+// ---------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ T fma_t(T a, T b, T c);
+template <> __device__ __forceinline__ double fma_t<double>(double a, double b, double c) { return fma(a, b, c); }
+template <> __device__ __forceinline__ float fma_t<float>(float a, float b, float c) { return fmaf(a, b, c); }
+
+template <typename T> __global__ void __launch_bounds__(256) peak_kernel(T* out, int iters, T m, T c)
+{
+    T a0 = (T)threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            a0 = fma_t<T>(a0, m, c); a1 = fma_t<T>(a1, m, c); a2 = fma_t<T>(a2, m, c); a3 = fma_t<T>(a3, m, c);
+            a4 = fma_t<T>(a4, m, c); a5 = fma_t<T>(a5, m, c); a6 = fma_t<T>(a6, m, c); a7 = fma_t<T>(a7, m, c);
+        }
+    }
+    T s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == (T)123456789) out[0] = s; // never true in practice; keeps the chains alive
+}
+
+extern "C" int hdp_measure_pipe_peak(hdp_handle h, int which, double* lane_instr_per_s)
+{
+    if (!h || !lane_instr_per_s || (which != 32 && which != 64)) return HDP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    void* d = ensure(h, hdp_context::B_A, 64);
+    if (!d) return HDP_ERR_ALLOC;
+    const int blocks = h->prop.multiProcessorCount * 8, threads = 256;
+    const int iters = which == 64 ? 2048 : 4096;
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        HDP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+        if (which == 64) peak_kernel<double><<<blocks, threads, 0, h->stream>>>((double*)d, iters, 0.999999, 1e-9);
+        else peak_kernel<float><<<blocks, threads, 0, h->stream>>>((float*)d, iters, 0.99999f, 1e-6f);
+        HDP_CUDA(h, cudaGetLastError());
+        HDP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+        HDP_CUDA(h, cudaEventSynchronize(h->ev1));
+        float ms = 0;
+        HDP_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        double instr = (double)blocks * threads * (double)iters * 16.0 * 8.0;
+        double rate = instr / (ms * 1e-3);
+        if (rep > 0 && rate > best) best = rate;
+    }
+    *lane_instr_per_s = best;
+    return HDP_OK;
+}

@@ -1,0 +1,68 @@
+// hdp_context.h — host-side handle of libhdpde_b200.so: stream, scratch,
+// error reporting, optional NCCL communicator (dlopen'ed), MLP plan cache.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "../../include/hdpde.h"
+
+namespace hdp {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct MlpPlan; // mlp_plan.h
+
+} // namespace hdp
+
+struct hdp_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaDeviceProp prop{};
+    std::mutex mu;
+    std::string err;
+    // grow-only scratch, indexed by role
+    enum { B_A = 0, B_B, B_C, B_D, B_E, B_F, B_G, B_H, B_I, B_J, B_K, B_L, B_N };
+    hdp::DevBuf buf[B_N];
+    int* d_flags = nullptr;          // [0] error flag, [1..] spare
+    unsigned long long* d_ctr = nullptr; // [0] work counter, [1] bounce counter
+    // NCCL (optional)
+    void* nccl_comm = nullptr;
+    int nccl_rank = 0, nccl_nranks = 1;
+    // MLP plan cache
+    std::map<std::string, std::shared_ptr<hdp::MlpPlan>> plans;
+    int launches = 0;
+};
+
+namespace hdp {
+
+int set_err(hdp_context* h, int code, const char* fmt, ...);
+// grow-only device buffer; returns nullptr (and sets h->err) on failure
+void* ensure(hdp_context* h, int which, size_t bytes);
+
+#define HDP_CUDA(h, call)                                                                      \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return hdp::set_err((h), HDP_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, \
+                                cudaGetErrorString(e__));                                      \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// NCCL through dlopen (no link-time dependency; reuses an already-loaded libnccl.so.2)
+int nccl_allreduce_f64_device(hdp_context* h, double* dbuf, size_t n);
+
+} // namespace hdp

@@ -1,0 +1,432 @@
+// k_elementwise.cu — K1 (reflected Euler–Maruyama loop), K2 (samplers),
+// K4 (reflection operator).  One thread owns VEC consecutive elements of the
+// column-major d×B state (one 128-bit load/store, one Philox call) and keeps
+// them in registers across all N steps; nothing but y0, y1 (and z) is written.
+//
+// Replaces: sde_loop! (src/DeepSplitting.jl:153-166), _reflect
+// (src/reflect.jl:8-82), UniformSampling/NormalSampling call operators
+// (src/MCSample.jl:28-33, 63-71).
+#include "hdp_host_util.h"
+
+using namespace hdp;
+
+namespace {
+
+template <typename T, bool ALIGNED>
+__device__ __forceinline__ Vec<T> load_el(const T* p, size_t q0, size_t n)
+{
+    constexpr int VEC = Tr<T>::VEC;
+    if constexpr (ALIGNED) return ldv<T>(p + q0);
+    Vec<T> r;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) r.v[e] = (q0 + e < n) ? p[q0 + e] : (T)0;
+    return r;
+}
+template <typename T, bool ALIGNED>
+__device__ __forceinline__ void store_el(T* p, size_t q0, size_t n, const Vec<T>& r)
+{
+    constexpr int VEC = Tr<T>::VEC;
+    if constexpr (ALIGNED) { stv<T>(p + q0, r); return; }
+#pragma unroll
+    for (int e = 0; e < VEC; ++e)
+        if (q0 + e < n) p[q0 + e] = r.v[e];
+}
+
+template <typename T> struct Bounds {
+    int scalar;
+    T lo_s, hi_s;
+    const T* lo;
+    const T* hi;
+    __device__ __forceinline__ T lo_at(int i) const { return scalar ? lo_s : lo[i]; }
+    __device__ __forceinline__ T hi_at(int i) const { return scalar ? hi_s : hi[i]; }
+};
+
+// ------------------------------ K4 -----------------------------------
+template <typename T, bool ALIGNED>
+__global__ void __launch_bounds__(256)
+reflect_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out,
+               int32_t* __restrict__ cnt, size_t n_el, int d, Bounds<T> bd, int* flags)
+{
+    constexpr int VEC = Tr<T>::VEC;
+    const size_t nv = (n_el + VEC - 1) / VEC;
+    bool bad = false;
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (size_t)gridDim.x * blockDim.x) {
+        const size_t q0 = v * VEC;
+        Vec<T> av = load_el<T, ALIGNED>(a, q0, n_el);
+        Vec<T> bv = load_el<T, ALIGNED>(b, q0, n_el);
+        int i = (int)(q0 % (size_t)d);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            if (q0 + e < n_el) {
+                T lo = bd.lo_at(i), hi = bd.hi_at(i);
+                if (!(av.v[e] >= lo && av.v[e] <= hi)) bad = true; // src/reflect.jl:12, :59
+                int nb = 0;
+                bv.v[e] = reflect_coord<T>(bv.v[e], lo, hi, nb);
+                if (cnt) cnt[q0 + e] = nb;
+            }
+            if (++i == d) i = 0;
+        }
+        store_el<T, ALIGNED>(out, q0, n_el, bv);
+    }
+    if (bad) atomicExch(&flags[0], 1);
+}
+
+// ------------------------------ K2 -----------------------------------
+template <typename T>
+__device__ __forceinline__ T sample_one(const DevSampler<T>& sm, T raw, int i, T xref)
+{
+    if (sm.kind == HDP_SAMPLER_UNIFORM) {
+        T a = sm.scalar ? sm.a_s : sm.a[i];
+        T b = sm.scalar ? sm.b_s : sm.b[i];
+        return uniform_map<T>(raw, a, b);
+    }
+    return normal_map<T>(raw, sm.sigma, sm.shifted != 0, xref);
+}
+
+template <typename T, bool ALIGNED>
+__global__ void __launch_bounds__(256)
+mc_sample_kernel(T* __restrict__ z, const T* __restrict__ y1, const T* __restrict__ inject,
+                 size_t n_el, int d, int K, DevSampler<T> sm, u64 seed, int stream)
+{
+    constexpr int VEC = Tr<T>::VEC;
+    const size_t nv = (n_el + VEC - 1) / VEC;
+    const bool normal = sm.kind == HDP_SAMPLER_NORMAL;
+    const bool use_ref = normal && sm.shifted && y1 != nullptr;
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (size_t)gridDim.x * blockDim.x) {
+        const size_t q0 = v * VEC;
+        Vec<T> ref;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) ref.v[e] = (T)0;
+        if (use_ref) ref = load_el<T, ALIGNED>(y1, q0, n_el);
+        const int i0 = (int)(q0 % (size_t)d);
+        for (int k = 0; k < K; ++k) {
+            Vec<T> raw = inject ? load_el<T, ALIGNED>(inject + (size_t)k * n_el, q0, n_el)
+                                : draw_vec<T>(seed, stream, (u64)k, (uint32_t)v, normal);
+            int i = i0;
+            Vec<T> o;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                o.v[e] = (use_ref || !normal) ? sample_one<T>(sm, raw.v[e], i, ref.v[e])
+                                              : normal_map<T>(raw.v[e], sm.sigma, false, (T)0);
+                if (++i == d) i = 0;
+            }
+            store_el<T, ALIGNED>(z + (size_t)k * n_el, q0, n_el, o);
+        }
+    }
+}
+
+// ------------------------------ K1 -----------------------------------
+// N reflected EM steps per element; normals from dWall (INJECT) or Philox in
+// registers.  draw addressing: dWall[q + n_el*step] == draw(SDE, ordinal=step, i=q).
+template <typename T, bool ALIGNED, bool INJECT>
+__global__ void __launch_bounds__(256)
+sde_loop_kernel(DevProblem<T> pb, T* __restrict__ y0, T* __restrict__ y1, size_t n_el, int nsteps, T dt,
+                DevSampler<T> x0s, const T* __restrict__ x0_inject, u64 seed, const T* __restrict__ dW,
+                DevSampler<T> mc, T* __restrict__ z, int K, int* flags, unsigned long long* bounce_ctr)
+{
+    constexpr int VEC = Tr<T>::VEC;
+    const int d = pb.d;
+    const size_t nv = (n_el + VEC - 1) / VEC;
+    const T sq = sqrt_rn(dt);
+    Bounds<T> bd{pb.bc_is_scalar, pb.lo_s, pb.hi_s, pb.lo, pb.hi};
+    bool bad = false;
+    int nb_total = 0;
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (size_t)gridDim.x * blockDim.x) {
+        const size_t q0 = v * VEC;
+        const int i0 = (int)(q0 % (size_t)d);
+        Vec<T> cur = load_el<T, ALIGNED>(y1, q0, n_el);
+        // x0_sample!(y1), 1-argument sampler form (src/DeepSplitting.jl:155)
+        if (x0s.kind != HDP_SAMPLER_NONE) {
+            Vec<T> raw = x0_inject ? load_el<T, ALIGNED>(x0_inject, q0, n_el)
+                                   : draw_vec<T>(seed, HDP_STREAM_X0, 0, (uint32_t)v, x0s.kind == HDP_SAMPLER_NORMAL);
+            int i = i0;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                if (x0s.kind == HDP_SAMPLER_UNIFORM) cur.v[e] = sample_one<T>(x0s, raw.v[e], i, (T)0);
+                else cur.v[e] = normal_map<T>(raw.v[e], x0s.sigma, false, (T)0);
+                if (++i == d) i = 0;
+            }
+        }
+        Vec<T> prev = cur;
+        for (int st = 0; st < nsteps; ++st) {
+            Vec<T> xi;
+            if constexpr (INJECT) xi = load_el<T, ALIGNED>(dW + (size_t)st * n_el, q0, n_el);
+            else xi = draw_vec<T>(seed, HDP_STREAM_SDE, (u64)st, (uint32_t)v, true);
+            prev = cur; // y0 .= y1 (:159)
+            int i = i0;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                T x = prev.v[e];
+                T mu = coef<T>(pb.mu_kind, pb.mu_c, x);
+                T sg = coef<T>(pb.sigma_kind, pb.sigma_c, x);
+                T nx = em_ds<T>(x, mu, sg, dt, sq, xi.v[e]); // :160
+                if (pb.has_bc) {
+                    T lo = bd.lo_at(i), hi = bd.hi_at(i);
+                    if (st == 0 && q0 + e < n_el && !(x >= lo && x <= hi)) bad = true; // :59
+                    nx = reflect_coord<T>(nx, lo, hi, nb_total);                      // :161-163
+                }
+                cur.v[e] = nx;
+                if (++i == d) i = 0;
+            }
+        }
+        store_el<T, ALIGNED>(y0, q0, n_el, prev);
+        store_el<T, ALIGNED>(y1, q0, n_el, cur);
+        // fused epilogue mc_sample!(z, y1) (src/DeepSplitting.jl:186-189)
+        if (z != nullptr && mc.kind != HDP_SAMPLER_NONE) {
+            const bool normal = mc.kind == HDP_SAMPLER_NORMAL;
+            for (int k = 0; k < K; ++k) {
+                Vec<T> raw = draw_vec<T>(seed, HDP_STREAM_MC, (u64)k, (uint32_t)v, normal);
+                int i = i0;
+                Vec<T> o;
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    o.v[e] = sample_one<T>(mc, raw.v[e], i, cur.v[e]);
+                    if (++i == d) i = 0;
+                }
+                store_el<T, ALIGNED>(z + (size_t)k * n_el, q0, n_el, o);
+            }
+        }
+    }
+    if (bad) atomicExch(&flags[0], 1);
+    if (bounce_ctr && nb_total) atomicAdd(bounce_ctr, (unsigned long long)nb_total);
+}
+
+inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+inline int grid_for(hdp_context* h, size_t nv, int threads, int per_sm)
+{
+    size_t blocks = (nv + threads - 1) / threads;
+    size_t cap = (size_t)h->prop.multiProcessorCount * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+// stage a caller array on the device (HOST flag) or pass it through (DEVICE flag)
+template <typename T>
+int stage_in(hdp_context* h, const T* src, size_t n, unsigned mem_flags, int which, const T** dptr)
+{
+    if (!src) { *dptr = nullptr; return HDP_OK; }
+    if (mem_flags & HDP_MEM_DEVICE) { *dptr = src; return HDP_OK; }
+    T* d = (T*)ensure(h, which, n * sizeof(T));
+    if (!d) return HDP_ERR_ALLOC;
+    HDP_CUDA(h, cudaMemcpyAsync(d, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    *dptr = d;
+    return HDP_OK;
+}
+template <typename T>
+int stage_out(hdp_context* h, T* dst, size_t n, unsigned mem_flags, int which, T** dptr)
+{
+    if (!dst) { *dptr = nullptr; return HDP_OK; }
+    if (mem_flags & HDP_MEM_DEVICE) { *dptr = dst; return HDP_OK; }
+    T* d = (T*)ensure(h, which, n * sizeof(T));
+    if (!d) return HDP_ERR_ALLOC;
+    *dptr = d;
+    return HDP_OK;
+}
+template <typename T>
+int copy_back(hdp_context* h, T* dst, const T* d, size_t n, unsigned mem_flags)
+{
+    if (!dst || (mem_flags & HDP_MEM_DEVICE)) return HDP_OK;
+    HDP_CUDA(h, cudaMemcpyAsync(dst, d, n * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+    return HDP_OK;
+}
+
+int check_flag(hdp_context* h, const char* what)
+{
+    int f = 0;
+    HDP_CUDA(h, cudaMemcpyAsync(&f, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    HDP_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (f) {
+        cudaMemsetAsync(h->d_flags, 0, sizeof(int), h->stream);
+        return set_err(h, HDP_ERR_START_OUTSIDE_DOMAIN, "%s: start point not in hypercube", what);
+    }
+    return HDP_OK;
+}
+
+// ------------------------------ K4 host ------------------------------
+template <typename T>
+int reflect_impl(hdp_handle h, const T* a, const T* b, T* out, int d, int B, const T* lo, const T* hi,
+                 int bounds_are_scalar, int32_t* cnt, unsigned mem_flags)
+{
+    if (!h || !a || !b || !out || !lo || !hi || d <= 0 || B < 0) return HDP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    const size_t n_el = (size_t)d * (size_t)B;
+    if (n_el == 0) return HDP_OK;
+    const T *da, *db, *dlo = nullptr, *dhi = nullptr;
+    T* dout;
+    int32_t* dcnt = nullptr;
+    int rc;
+    if ((rc = stage_in(h, a, n_el, mem_flags, hdp_context::B_A, &da)) != HDP_OK) return rc;
+    if ((rc = stage_in(h, b, n_el, mem_flags, hdp_context::B_B, &db)) != HDP_OK) return rc;
+    if ((rc = stage_out(h, out, n_el, mem_flags, hdp_context::B_C, &dout)) != HDP_OK) return rc;
+    if ((rc = stage_out(h, cnt, n_el, mem_flags, hdp_context::B_D, &dcnt)) != HDP_OK) return rc;
+    Bounds<T> bd{};
+    bd.scalar = bounds_are_scalar;
+    if (bounds_are_scalar) {
+        T l, u;
+        if (mem_flags & HDP_MEM_DEVICE) {
+            HDP_CUDA(h, cudaMemcpyAsync(&l, lo, sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+            HDP_CUDA(h, cudaMemcpyAsync(&u, hi, sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+            HDP_CUDA(h, cudaStreamSynchronize(h->stream));
+        } else { l = lo[0]; u = hi[0]; }
+        bd.lo_s = l; bd.hi_s = u;
+    } else {
+        if ((rc = stage_in(h, lo, (size_t)d, mem_flags, hdp_context::B_E, &dlo)) != HDP_OK) return rc;
+        if ((rc = stage_in(h, hi, (size_t)d, mem_flags, hdp_context::B_F, &dhi)) != HDP_OK) return rc;
+        bd.lo = dlo; bd.hi = dhi;
+    }
+    constexpr int VEC = Tr<T>::VEC;
+    const size_t nv = (n_el + VEC - 1) / VEC;
+    const bool al = (n_el % VEC == 0) && aligned16(da) && aligned16(db) && aligned16(dout);
+    const int grid = grid_for(h, nv, 256, 16);
+    if (al) reflect_kernel<T, true><<<grid, 256, 0, h->stream>>>(da, db, dout, dcnt, n_el, d, bd, h->d_flags);
+    else reflect_kernel<T, false><<<grid, 256, 0, h->stream>>>(da, db, dout, dcnt, n_el, d, bd, h->d_flags);
+    h->launches++;
+    HDP_CUDA(h, cudaGetLastError());
+    if ((rc = copy_back(h, out, dout, n_el, mem_flags)) != HDP_OK) return rc;
+    if ((rc = copy_back(h, cnt, dcnt, n_el, mem_flags)) != HDP_OK) return rc;
+    return check_flag(h, "_reflect");
+}
+
+// ------------------------------ K2 host ------------------------------
+template <typename T>
+int mc_sample_impl(hdp_handle h, T* z, const T* y1, int d, int B, int K, const hdp_sampler* sampler,
+                   uint64_t seed, const T* inject, unsigned mem_flags)
+{
+    if (!h || !z || !sampler || d <= 0 || B < 0 || K < 0) return HDP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    if (sampler->kind == HDP_SAMPLER_NONE) return HDP_OK; // NoSampling()(x...) = nothing (src/MCSample.jl:86)
+    const size_t n_el = (size_t)d * (size_t)B;
+    if (n_el == 0 || K == 0) return HDP_OK;
+    DevSampler<T> sm;
+    int rc = make_dev_sampler<T>(h, sampler, d, hdp_context::B_E, &sm);
+    if (rc != HDP_OK) return rc;
+    const T *dy1 = nullptr, *dinj = nullptr;
+    T* dz;
+    if (sampler->kind == HDP_SAMPLER_NORMAL && sampler->shifted && y1)
+        if ((rc = stage_in(h, y1, n_el, mem_flags, hdp_context::B_A, &dy1)) != HDP_OK) return rc;
+    if ((rc = stage_in(h, inject, n_el * (size_t)K, mem_flags, hdp_context::B_B, &dinj)) != HDP_OK) return rc;
+    if ((rc = stage_out(h, z, n_el * (size_t)K, mem_flags, hdp_context::B_C, &dz)) != HDP_OK) return rc;
+    constexpr int VEC = Tr<T>::VEC;
+    const size_t nv = (n_el + VEC - 1) / VEC;
+    const bool al = (n_el % VEC == 0) && aligned16(dz) && aligned16(dy1) && aligned16(dinj);
+    const int grid = grid_for(h, nv, 256, 16);
+    if (al) mc_sample_kernel<T, true><<<grid, 256, 0, h->stream>>>(dz, dy1, dinj, n_el, d, K, sm, seed, HDP_STREAM_MC);
+    else mc_sample_kernel<T, false><<<grid, 256, 0, h->stream>>>(dz, dy1, dinj, n_el, d, K, sm, seed, HDP_STREAM_MC);
+    h->launches++;
+    HDP_CUDA(h, cudaGetLastError());
+    if ((rc = copy_back(h, z, dz, n_el * (size_t)K, mem_flags)) != HDP_OK) return rc;
+    if (!(mem_flags & HDP_MEM_DEVICE)) HDP_CUDA(h, cudaStreamSynchronize(h->stream));
+    return HDP_OK;
+}
+
+// ------------------------------ K1 host ------------------------------
+template <typename T>
+int sde_loop_impl(hdp_handle h, const hdp_problem* prob, T* y0, T* y1, int B, int nsteps, T dt, const T* ts,
+                  const hdp_sampler* x0_sampler, uint64_t seed, const T* dWall_inject,
+                  const hdp_sampler* mc, T* z, int K, int normal_mode, unsigned mem_flags)
+{
+    (void)ts; // every supported coefficient kind is time-independent
+    if (!h || !prob || !y0 || !y1 || B < 0 || nsteps < 0) return HDP_ERR_BAD_ARG;
+    if (normal_mode != HDP_NORMAL_DEFAULT && normal_mode != (sizeof(T) == 8 ? HDP_NORMAL_BM64 : HDP_NORMAL_BM32))
+        return set_err(h, HDP_ERR_UNSUPPORTED, "normal_mode %d not supported for this element type", normal_mode);
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    DevProblem<T> pb;
+    int rc = make_dev_problem<T>(h, prob, hdp_context::B_E, &pb);
+    if (rc != HDP_OK) return rc;
+    const int d = prob->d;
+    const size_t n_el = (size_t)d * (size_t)B;
+    if (n_el == 0) return HDP_OK;
+    DevSampler<T> x0s, mcs;
+    if ((rc = make_dev_sampler<T>(h, x0_sampler, d, hdp_context::B_F, &x0s)) != HDP_OK) return rc;
+    if ((rc = make_dev_sampler<T>(h, mc, d, hdp_context::B_G, &mcs)) != HDP_OK) return rc;
+    const bool want_z = z != nullptr && mcs.kind != HDP_SAMPLER_NONE && K > 0;
+    T *dy0, *dy1, *dz = nullptr;
+    const T* ddw = nullptr;
+    if (mem_flags & HDP_MEM_DEVICE) { dy0 = y0; dy1 = y1; dz = z; ddw = dWall_inject; }
+    else {
+        dy0 = (T*)ensure(h, hdp_context::B_A, n_el * sizeof(T));
+        dy1 = (T*)ensure(h, hdp_context::B_B, n_el * sizeof(T));
+        if (!dy0 || !dy1) return HDP_ERR_ALLOC;
+        HDP_CUDA(h, cudaMemcpyAsync(dy1, y1, n_el * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+        if (dWall_inject) {
+            T* t = (T*)ensure(h, hdp_context::B_C, n_el * (size_t)nsteps * sizeof(T));
+            if (!t) return HDP_ERR_ALLOC;
+            HDP_CUDA(h, cudaMemcpyAsync(t, dWall_inject, n_el * (size_t)nsteps * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+            ddw = t;
+        }
+        if (want_z) {
+            dz = (T*)ensure(h, hdp_context::B_D, n_el * (size_t)K * sizeof(T));
+            if (!dz) return HDP_ERR_ALLOC;
+        }
+    }
+    if (!want_z) dz = nullptr;
+    constexpr int VEC = Tr<T>::VEC;
+    const size_t nv = (n_el + VEC - 1) / VEC;
+    const bool al = (n_el % VEC == 0) && aligned16(dy0) && aligned16(dy1) && aligned16(dz) && aligned16(ddw);
+    const int threads = 128;
+    const int grid = grid_for(h, nv, threads, 64);
+#define LAUNCH(AL, INJ)                                                                                  \
+    sde_loop_kernel<T, AL, INJ><<<grid, threads, 0, h->stream>>>(pb, dy0, dy1, n_el, nsteps, dt, x0s,    \
+                                                                 nullptr, seed, ddw, mcs, dz, K,          \
+                                                                 h->d_flags, h->d_ctr + 1)
+    if (al && ddw) LAUNCH(true, true);
+    else if (al) LAUNCH(true, false);
+    else if (ddw) LAUNCH(false, true);
+    else LAUNCH(false, false);
+#undef LAUNCH
+    h->launches++;
+    HDP_CUDA(h, cudaGetLastError());
+    if (!(mem_flags & HDP_MEM_DEVICE)) {
+        HDP_CUDA(h, cudaMemcpyAsync(y0, dy0, n_el * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+        HDP_CUDA(h, cudaMemcpyAsync(y1, dy1, n_el * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+        if (want_z) HDP_CUDA(h, cudaMemcpyAsync(z, dz, n_el * (size_t)K * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (prob->has_bc || !(mem_flags & HDP_MEM_DEVICE)) return check_flag(h, "sde_loop!");
+    return HDP_OK;
+}
+
+} // namespace
+
+extern "C" int hdp_reflect_f64(hdp_handle h, const double* a, const double* b, double* out, int d, int B,
+                               const double* lo, const double* hi, int bounds_are_scalar,
+                               int32_t* bounce_count_out, unsigned mem_flags)
+{
+    return reflect_impl<double>(h, a, b, out, d, B, lo, hi, bounds_are_scalar, bounce_count_out, mem_flags);
+}
+extern "C" int hdp_reflect_f32(hdp_handle h, const float* a, const float* b, float* out, int d, int B,
+                               const float* lo, const float* hi, int bounds_are_scalar,
+                               int32_t* bounce_count_out, unsigned mem_flags)
+{
+    return reflect_impl<float>(h, a, b, out, d, B, lo, hi, bounds_are_scalar, bounce_count_out, mem_flags);
+}
+extern "C" int hdp_mc_sample_f64(hdp_handle h, double* z, const double* y1, int d, int B, int K,
+                                 const hdp_sampler* sampler, uint64_t seed, const double* inject, unsigned mem_flags)
+{
+    return mc_sample_impl<double>(h, z, y1, d, B, K, sampler, seed, inject, mem_flags);
+}
+extern "C" int hdp_mc_sample_f32(hdp_handle h, float* z, const float* y1, int d, int B, int K,
+                                 const hdp_sampler* sampler, uint64_t seed, const float* inject, unsigned mem_flags)
+{
+    return mc_sample_impl<float>(h, z, y1, d, B, K, sampler, seed, inject, mem_flags);
+}
+extern "C" int hdp_sde_loop_f64(hdp_handle h, const hdp_problem* prob, double* y0, double* y1, int B, int nsteps,
+                                double dt, const double* ts, const hdp_sampler* x0_sampler, uint64_t seed,
+                                const double* dWall_inject, const hdp_sampler* mc, double* z, int K,
+                                int normal_mode, unsigned mem_flags)
+{
+    return sde_loop_impl<double>(h, prob, y0, y1, B, nsteps, dt, ts, x0_sampler, seed, dWall_inject, mc, z, K,
+                                 normal_mode, mem_flags);
+}
+extern "C" int hdp_sde_loop_f32(hdp_handle h, const hdp_problem* prob, float* y0, float* y1, int B, int nsteps,
+                                float dt, const float* ts, const hdp_sampler* x0_sampler, uint64_t seed,
+                                const float* dWall_inject, const hdp_sampler* mc, float* z, int K,
+                                int normal_mode, unsigned mem_flags)
+{
+    return sde_loop_impl<float>(h, prob, y0, y1, B, nsteps, dt, ts, x0_sampler, seed, dWall_inject, mc, z, K,
+                                normal_mode, mem_flags);
+}

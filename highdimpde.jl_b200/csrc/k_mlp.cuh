@@ -1,0 +1,555 @@
+// k_mlp.cuh — K3: the multilevel-Picard tree on the GPU.
+//
+// Replaces `_ml_picard` / `_ml_picard_mlt` / `_ml_picard_call`
+// (src/MLP.jl:102-388), `_mlt_sde_loop!` (:406-421), the Vector `_reflect`
+// (src/reflect.jl:8-55) and the sampler calls inside the recursion.
+//
+// Mapping.  A group of G lanes (G = 1..32, a power of two) owns one work unit;
+// lane g holds vec-groups g, g+G, g+2G, … of every point (one vec-group = VEC
+// coordinates = one Philox call = one 128-bit load/store).  The recursion is
+// the compile-time family Call<LV>/eval_site<l>; the points x2, x3 of the
+// active site of level l live in scratch slot 2l / 2l+1, laid out
+// [slot][vec-group j][thread] so every access is a coalesced 128-bit
+// transaction (SoA).  All draws are addressed by the reference's consumption
+// ordinal, so results do not depend on G, on the cut, or on the GPU count.
+#pragma once
+#include "hdp_device.cuh"
+#include "mlp_plan.h"
+
+namespace hdp {
+
+template <typename T> struct MlpParams {
+    DevProblem<T> pb;
+    DevSampler<T> sm;
+    int M, K, L, Kp;
+    int nvec, npl, dpad;
+    u64 C[kMaxL + 1], R[kMaxL + 1], S[kMaxL + 1];
+    u64 cs[kMaxL + 1], rs[kMaxL + 1], ss[kMaxL + 1];
+    u64 Mpow[kMaxL + 2];
+    const T *r_tape, *n_tape, *s_tape;
+    u64 seed0;
+    int n_solves, n_x0;
+    const PlanUnit* units;
+    const int32_t* exec;
+    const PlanNode* nodes;
+    const PlanSite* sites;
+    const int32_t* children;
+    const int32_t* sites_by_depth;
+    const int32_t* nodes_by_depth;
+    int n_units, n_nodes, n_sites, n_points;
+    T* points;       // [n_solves][n_points][dpad]
+    T* feat;         // [n_solves][n_points]  sum(x^2)
+    T* site_r;       // [n_solves][n_sites]   sampled time of each explicit site
+    double* partial; // [n_solves][n_units]
+    T* value;        // [n_solves][n_nodes]
+    T* scratch;
+    u64 total_threads;
+    int rank, nranks;
+    unsigned long long* work_ctr;
+    unsigned long long* bounce_ctr;
+    int* flags;
+};
+
+template <typename T> struct XAcc {
+    T* base;
+    u64 vstride, voff;
+    __device__ __forceinline__ T* at(int j) const { return base + ((u64)j * vstride + voff) * Tr<T>::VEC; }
+};
+
+template <typename T, int G> struct Ctx {
+    const MlpParams<T>* P;
+    u64 seed;
+    u64 tid;
+    int lane;
+    unsigned gmask;
+    int nb;
+    int bad;
+    __device__ __forceinline__ XAcc<T> slot(int k) const
+    {
+        XAcc<T> a;
+        a.base = P->scratch + (u64)k * (u64)P->npl * P->total_threads * Tr<T>::VEC;
+        a.vstride = P->total_threads;
+        a.voff = tid;
+        return a;
+    }
+    __device__ __forceinline__ XAcc<T> point(int solve, int pt) const
+    {
+        XAcc<T> a;
+        a.base = P->points + ((u64)solve * (u64)P->n_points + (u64)pt) * (u64)P->dpad;
+        a.vstride = G;
+        a.voff = (u64)lane;
+        return a;
+    }
+};
+
+template <typename T, int G> __device__ __forceinline__ T gsum(T v, unsigned mask)
+{
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) v += __shfl_xor_sync(mask, v, off);
+    return v;
+}
+template <typename T, int G> __device__ __forceinline__ T gmin(T v, unsigned mask)
+{
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) {
+        T o = __shfl_xor_sync(mask, v, off);
+        v = o < v ? o : v;
+    }
+    return v;
+}
+template <int G> __device__ __forceinline__ int gsumi(int v, unsigned mask)
+{
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) v += __shfl_xor_sync(mask, v, off);
+    return v;
+}
+
+template <typename T> __device__ __forceinline__ T big() { return (T)3.0e38; }
+
+// rand(tType)  (src/MLP.jl:132)
+template <typename T, int G> __device__ __forceinline__ T time_uniform(const Ctx<T, G>& c, u64 ro)
+{
+    const MlpParams<T>& P = *c.P;
+    if (P.r_tape) return P.r_tape[ro];
+    return draw_vec<T>(c.seed, HDP_STREAM_TIME, ro, 0u, false).v[0];
+}
+
+// `_mlt_sde_loop!(x2, x, s, t, prob, neumann_bc)`  (src/MLP.jl:406-421):
+// one Euler–Maruyama step s -> tend from the point `src`, then reflection.
+// Writes x2 to `dst` when non-null; returns sum(x2^2) and min(x2).
+template <typename T, int G>
+__device__ HDP_NOINLINE Feat<T> em_step(Ctx<T, G>& c, const XAcc<T>& src, const XAcc<T>* dst, T s, T tend, u64 ord)
+{
+    constexpr int VEC = Tr<T>::VEC;
+    const MlpParams<T>& P = *c.P;
+    const DevProblem<T>& pb = P.pb;
+    const int d = pb.d;
+    const T dt = sub_rn(tend, s);  // :415
+    const T sq = sqrt_rn(dt);
+    Feat<T> f;
+    f.ssq = (T)0;
+    f.mn = big<T>();
+    for (int j = 0; j < P.npl; ++j) {
+        const int p = c.lane + G * j;
+        if (p < P.nvec) {
+            Vec<T> xi;
+            if (P.n_tape) {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    int i = p * VEC + e;
+                    xi.v[e] = i < d ? P.n_tape[ord * (u64)d + (u64)i] : (T)0;
+                }
+            } else xi = draw_vec<T>(c.seed, HDP_STREAM_STEP, ord, (uint32_t)p, true); // :416 randn!(x2)
+            const Vec<T> xv = ldv<T>(src.at(j));
+            Vec<T> o;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                const int i = p * VEC + e;
+                T nx = (T)0;
+                if (i < d) {
+                    const T x = xv.v[e];
+                    const T mu = coef<T>(pb.mu_kind, pb.mu_c, x);
+                    const T sg = coef<T>(pb.sigma_kind, pb.sigma_c, x);
+                    nx = em_mlp<T>(x, mu, sg, dt, sq, xi.v[e]); // :417
+                    if (pb.has_bc) {                             // :418-420
+                        const T lo = pb.bc_is_scalar ? pb.lo_s : pb.lo[i];
+                        const T hi = pb.bc_is_scalar ? pb.hi_s : pb.hi[i];
+                        if (!(x >= lo && x <= hi)) c.bad = 1;     // src/reflect.jl:12
+                        nx = reflect_coord<T>(nx, lo, hi, c.nb);
+                    }
+                    f.ssq += nx * nx;
+                    f.mn = nx < f.mn ? nx : f.mn;
+                }
+                o.v[e] = nx;
+            }
+            if (dst) stv<T>(dst->at(j), o);
+        }
+    }
+    f.ssq = gsum<T, G>(f.ssq, c.gmask);
+    if (pb.g_kind == HDP_G_MIN) f.mn = gmin<T, G>(f.mn, c.gmask);
+    return f;
+}
+
+// mc_sample!(x3, x2)  (src/MLP.jl:139,177; src/MCSample.jl:28-33, 63-71)
+template <typename T, int G>
+__device__ HDP_NOINLINE Feat<T> sample_step(Ctx<T, G>& c, const XAcc<T>* dst, const XAcc<T>& x2, u64 ord)
+{
+    constexpr int VEC = Tr<T>::VEC;
+    const MlpParams<T>& P = *c.P;
+    const DevSampler<T>& sm = P.sm;
+    const int d = P.pb.d;
+    const bool normal = sm.kind == HDP_SAMPLER_NORMAL;
+    const bool shifted = normal && sm.shifted;
+    Feat<T> f;
+    f.ssq = (T)0;
+    f.mn = big<T>();
+    for (int j = 0; j < P.npl; ++j) {
+        const int p = c.lane + G * j;
+        if (p < P.nvec) {
+            Vec<T> raw;
+            if (P.s_tape) {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    int i = p * VEC + e;
+                    raw.v[e] = i < d ? P.s_tape[ord * (u64)d + (u64)i] : (T)0;
+                }
+            } else raw = draw_vec<T>(c.seed, HDP_STREAM_SAMPLER, ord, (uint32_t)p, normal);
+            Vec<T> ref;
+            if (shifted) ref = ldv<T>(x2.at(j));
+            Vec<T> o;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                const int i = p * VEC + e;
+                T v = (T)0;
+                if (i < d) {
+                    if (normal) v = normal_map<T>(raw.v[e], sm.sigma, shifted, shifted ? ref.v[e] : (T)0);
+                    else v = uniform_map<T>(raw.v[e], sm.scalar ? sm.a_s : sm.a[i], sm.scalar ? sm.b_s : sm.b[i]);
+                    f.ssq += v * v;
+                }
+                o.v[e] = v;
+            }
+            if (dst) stv<T>(dst->at(j), o);
+        }
+    }
+    f.ssq = gsum<T, G>(f.ssq, c.gmask);
+    return f;
+}
+
+template <typename T, int G, int LV> struct Call;
+
+// One (l,k) iteration of the level loops: src/MLP.jl:132-148 (l<=1), :157-194 (l>=2).
+// Returns b3 / K.  (co, ro, so): consumption ordinals at the start of the site.
+template <typename T, int G, int l>
+__device__ __forceinline__ T eval_site(Ctx<T, G>& c, const XAcc<T>& xp, T s, u64 co, u64 ro, u64 so)
+{
+    const MlpParams<T>& P = *c.P;
+    const DevProblem<T>& pb = P.pb;
+    const T t1 = pb.t1;
+    const T u = time_uniform<T, G>(c, ro);
+    const T r = add_rn(s, mul_rn(sub_rn(t1, s), u)); // :132
+    const XAcc<T> x2 = c.slot(2 * l);
+    const XAcc<T> x3 = c.slot(2 * l + 1);
+    const bool shifted = P.sm.kind == HDP_SAMPLER_NORMAL && P.sm.shifted;
+    const bool keep_x2 = (l >= 1) || shifted;
+    const Feat<T> f2 = em_step<T, G>(c, xp, keep_x2 ? &x2 : nullptr, s, r, co); // :133
+    u64 cc = co + 1, rr = ro + 1, qq = so;
+    T b2 = (T)0, b4 = (T)0;
+    if constexpr (l >= 1) {
+        b2 = Call<T, G, l>::run(c, x2, r, cc, rr, qq); // :134
+        cc += P.C[l]; rr += P.R[l]; qq += P.S[l];
+    }
+    if constexpr (l >= 2) {
+        b4 = Call<T, G, l - 1>::run(c, x2, r, cc, rr, qq); // :160-173
+        cc += P.C[l - 1]; rr += P.R[l - 1]; qq += P.S[l - 1];
+    }
+    T b3 = (T)0;
+    if (P.Kp > 0) {
+        for (int h = 0; h < P.K; ++h) { // :137, :176
+            const Feat<T> f3 = sample_step<T, G>(c, l >= 1 ? &x3 : nullptr, x2, qq); // :139, :177
+            qq += 1;
+            T v = (T)0;
+            if constexpr (l >= 1) {
+                v = Call<T, G, l>::run(c, x3, r, cc, rr, qq);
+                cc += P.C[l]; rr += P.R[l]; qq += P.S[l];
+            }
+            T term = f_eval<T>(pb, f2.ssq, f3.ssq, b2, v); // :140-146
+            if constexpr (l >= 2) {
+                const T w = Call<T, G, l - 1>::run(c, x3, r, cc, rr, qq);
+                cc += P.C[l - 1]; rr += P.R[l - 1]; qq += P.S[l - 1];
+                term = term - f_eval<T>(pb, f2.ssq, f3.ssq, b4, w); // :178-191
+            }
+            b3 += term;
+        }
+    } else {
+        // NoSampling: the K-loop re-evaluates f on identical arguments (:137-147, :210-216)
+        T term = f_eval<T>(pb, f2.ssq, (T)0, b2, (T)0);
+        if constexpr (l >= 2) term = term - f_eval<T>(pb, f2.ssq, (T)0, b4, (T)0);
+        for (int h = 0; h < P.K; ++h) b3 += term;
+    }
+    return b3 / (T)P.K; // :148
+}
+
+// sum of g over `n` plain steps s -> t1 (src/MLP.jl:198-205), ordinals co..co+n-1
+template <typename T, int G>
+__device__ __forceinline__ T g_sum(Ctx<T, G>& c, const XAcc<T>& xp, T s, u64 co, u64 n)
+{
+    const DevProblem<T>& pb = c.P->pb;
+    T a2 = (T)0;
+    for (u64 k = 0; k < n; ++k) {
+        const Feat<T> f = em_step<T, G>(c, xp, nullptr, s, pb.t1, co + k); // :202
+        a2 += g_eval<T>(pb, f);                                            // :203
+    }
+    return a2;
+}
+
+template <typename T, int G, int LV, int l> struct LevelLoop {
+    static __device__ __forceinline__ void run(Ctx<T, G>& c, const XAcc<T>& xp, T s, u64& co, u64& ro, u64& so, T& a)
+    {
+        const MlpParams<T>& P = *c.P;
+        const u64 num = P.Mpow[LV - l];
+        T b = (T)0;
+        for (u64 k = 0; k < num; ++k) {
+            b += eval_site<T, G, l>(c, xp, s, co, ro, so);
+            co += P.cs[l]; ro += P.rs[l]; so += P.ss[l];
+        }
+        a += ((P.pb.t1 - s) * b) / (T)num; // :150, :195
+        LevelLoop<T, G, LV, l + 1>::run(c, xp, s, co, ro, so, a);
+    }
+};
+template <typename T, int G, int LV> struct LevelLoop<T, G, LV, LV> {
+    static __device__ __forceinline__ void run(Ctx<T, G>&, const XAcc<T>&, T, u64&, u64&, u64&, T&) {}
+};
+
+// `_ml_picard(M, LV, K, x, s, t, ...)`  (src/MLP.jl:102-208)
+template <typename T, int G, int LV> struct Call {
+    static __device__ HDP_NOINLINE T run(Ctx<T, G>& c, XAcc<T> xp, T s, u64 co, u64 ro, u64 so)
+    {
+        T a = (T)0;
+        LevelLoop<T, G, LV, 0>::run(c, xp, s, co, ro, so, a);
+        const u64 num = c.P->Mpow[LV];
+        T a2 = g_sum<T, G>(c, xp, s, co, num);
+        a2 /= (T)num;   // :205
+        return a + a2;  // :207
+    }
+};
+template <typename T, int G> struct Call<T, G, 0> {
+    static __device__ __forceinline__ T run(Ctx<T, G>&, XAcc<T>, T, u64, u64, u64) { return (T)0; } // :117-119
+};
+
+template <typename T, int G, int l>
+__device__ HDP_NOINLINE T level_slice(Ctx<T, G>& c, XAcc<T> xp, T s, u64 co, u64 ro, u64 so, u64 n)
+{
+    const MlpParams<T>& P = *c.P;
+    T b = (T)0;
+    for (u64 k = 0; k < n; ++k) {
+        b += eval_site<T, G, l>(c, xp, s, co, ro, so);
+        co += P.cs[l]; ro += P.rs[l]; so += P.ss[l];
+    }
+    return b;
+}
+
+template <typename T, int G>
+__device__ __forceinline__ T run_unit(Ctx<T, G>& c, const PlanUnit& u, const PlanNode& nd, const XAcc<T>& xp, T s)
+{
+    const u64 n = (u64)(u.k1 - u.k0);
+    if (u.kind == UNIT_WHOLE) {
+        switch (nd.lv) {
+        case 1: return Call<T, G, 1>::run(c, xp, s, u.c, u.r, u.s);
+        case 2: return Call<T, G, 2>::run(c, xp, s, u.c, u.r, u.s);
+        case 3: return Call<T, G, 3>::run(c, xp, s, u.c, u.r, u.s);
+        case 4: return Call<T, G, 4>::run(c, xp, s, u.c, u.r, u.s);
+        case 5: return Call<T, G, 5>::run(c, xp, s, u.c, u.r, u.s);
+        case 6: return Call<T, G, 6>::run(c, xp, s, u.c, u.r, u.s);
+        }
+        return (T)0;
+    }
+    if (u.kind == UNIT_G) return g_sum<T, G>(c, xp, s, u.c, n);
+    switch (u.l) {
+    case 0: return level_slice<T, G, 0>(c, xp, s, u.c, u.r, u.s, n);
+    case 1: return level_slice<T, G, 1>(c, xp, s, u.c, u.r, u.s, n);
+    case 2: return level_slice<T, G, 2>(c, xp, s, u.c, u.r, u.s, n);
+    case 3: return level_slice<T, G, 3>(c, xp, s, u.c, u.r, u.s, n);
+    case 4: return level_slice<T, G, 4>(c, xp, s, u.c, u.r, u.s, n);
+    case 5: return level_slice<T, G, 5>(c, xp, s, u.c, u.r, u.s, n);
+    }
+    return (T)0;
+}
+
+template <typename T, int G>
+__device__ __forceinline__ void ctx_init(Ctx<T, G>& c, const MlpParams<T>& P, u64 tid, int lane_w)
+{
+    c.P = &P;
+    c.tid = tid;
+    c.lane = lane_w % G;
+    c.gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane_w - c.lane));
+    c.nb = 0;
+    c.bad = 0;
+    c.seed = 0;
+}
+
+// ---------------------------------------------------------------------
+// per-item bodies (shared by the kernels and by the test-only host emulation)
+// ---------------------------------------------------------------------
+// geometry of one explicit site: r, x2, x3_h
+template <typename T, int G>
+__device__ __forceinline__ void expand_item(Ctx<T, G>& c, const MlpParams<T>& P, int off, u64 item)
+{
+    const int solve = (int)(item % (u64)P.n_solves);
+    const int sidx = P.sites_by_depth[off + (int)(item / (u64)P.n_solves)];
+    const PlanSite st = P.sites[sidx];
+    const PlanNode nd = P.nodes[st.node];
+    c.seed = P.seed0 + (u64)solve;
+    const T s = nd.time_site < 0 ? P.pb.t0 : P.site_r[(u64)solve * P.n_sites + nd.time_site];
+    const XAcc<T> xp = c.point(solve, nd.point);
+    const T u = time_uniform<T, G>(c, st.r);
+    const T r = add_rn(s, mul_rn(sub_rn(P.pb.t1, s), u));
+    const XAcc<T> x2 = c.point(solve, st.x2_point);
+    const Feat<T> f2 = em_step<T, G>(c, xp, &x2, s, r, st.c);
+    if (c.lane == 0) {
+        P.site_r[(u64)solve * P.n_sites + sidx] = r;
+        P.feat[(u64)solve * P.n_points + st.x2_point] = f2.ssq;
+    }
+    if (P.Kp > 0) {
+        const int l = st.l;
+        const u64 sub = P.S[l] + (l >= 2 ? P.S[l - 1] : 0);
+        u64 qq = st.s + sub;
+        for (int h = 0; h < P.Kp; ++h) {
+            const XAcc<T> x3 = c.point(solve, st.x3_point0 + h);
+            const Feat<T> f3 = sample_step<T, G>(c, &x3, x2, qq);
+            if (c.lane == 0) P.feat[(u64)solve * P.n_points + st.x3_point0 + h] = f3.ssq;
+            qq += 1 + sub;
+        }
+    }
+    const int nb = gsumi<G>(c.nb, c.gmask);
+    const int bad = gsumi<G>(c.bad, c.gmask);
+    if (c.lane == 0) {
+        if (nb) atomicAdd(P.bounce_ctr, (unsigned long long)nb);
+        if (bad) atomicExch(&P.flags[0], 1);
+    }
+}
+
+// one work item w = (unit, solve): evaluate and store the partial sum
+template <typename T, int G>
+__device__ __forceinline__ void unit_item(Ctx<T, G>& c, const MlpParams<T>& P, u64 w)
+{
+    const int solve = (int)(w % (u64)P.n_solves);
+    const int uid = P.exec[w / (u64)P.n_solves];
+    const PlanUnit un = P.units[uid];
+    const PlanNode nd = P.nodes[un.node];
+    c.seed = P.seed0 + (u64)solve;
+    c.nb = 0;
+    const T s = nd.time_site < 0 ? P.pb.t0 : P.site_r[(u64)solve * P.n_sites + nd.time_site];
+    const XAcc<T> xp = c.point(solve, nd.point);
+    const T v = run_unit<T, G>(c, un, nd, xp, s);
+    const int nb = gsumi<G>(c.nb, c.gmask);
+    if (c.lane == 0) {
+        P.partial[(u64)solve * P.n_units + uid] = (double)v;
+        if (nb) atomicAdd(P.bounce_ctr, (unsigned long long)nb);
+    }
+}
+
+// value of one explicit node from its units' partial sums and its explicit sites
+template <typename T>
+__device__ __forceinline__ void combine_item(const MlpParams<T>& P, int off, u64 item)
+{
+    const int solve = (int)(item % (u64)P.n_solves);
+    const int nidx = P.nodes_by_depth[off + (int)(item / (u64)P.n_solves)];
+    const PlanNode nd = P.nodes[nidx];
+    const DevProblem<T>& pb = P.pb;
+    const double* part = P.partial + (u64)solve * P.n_units;
+    const T* val = P.value + (u64)solve * P.n_nodes;
+    const T* feat = P.feat + (u64)solve * P.n_points;
+    T result;
+    if (nd.unit_end - nd.unit_begin == 1 && P.units[nd.unit_begin].kind == UNIT_WHOLE) {
+        result = (T)part[nd.unit_begin];
+    } else {
+        const T s = nd.time_site < 0 ? pb.t0 : P.site_r[(u64)solve * P.n_sites + nd.time_site];
+        T Bl[kMaxL];
+#pragma unroll
+        for (int l = 0; l < kMaxL; ++l) Bl[l] = (T)0;
+        T Gs = (T)0;
+        for (int u = nd.unit_begin; u < nd.unit_end; ++u) {
+            const int kind = P.units[u].kind;
+            const T v = (T)part[u];
+            if (kind == UNIT_G) Gs += v;
+            else Bl[P.units[u].l] += v;
+        }
+        for (int si = nd.site_begin; si < nd.site_end; ++si) {
+            const PlanSite st = P.sites[si];
+            const int l = st.l;
+            const int32_t* ch = P.children + st.child0;
+            const T f2 = feat[st.x2_point];
+            const T b2 = ch[0] >= 0 ? val[ch[0]] : (T)0;
+            const T b4 = ch[1] >= 0 ? val[ch[1]] : (T)0;
+            T b3 = (T)0;
+            if (P.Kp > 0) {
+                for (int h = 0; h < P.K; ++h) {
+                    const T f3 = feat[st.x3_point0 + h];
+                    const T v = ch[2 + 2 * h] >= 0 ? val[ch[2 + 2 * h]] : (T)0;
+                    T term = f_eval<T>(pb, f2, f3, b2, v);
+                    if (l >= 2) {
+                        const T w = ch[3 + 2 * h] >= 0 ? val[ch[3 + 2 * h]] : (T)0;
+                        term = term - f_eval<T>(pb, f2, f3, b4, w);
+                    }
+                    b3 += term;
+                }
+            } else {
+                T term = f_eval<T>(pb, f2, (T)0, b2, (T)0);
+                if (l >= 2) term = term - f_eval<T>(pb, f2, (T)0, b4, (T)0);
+                for (int h = 0; h < P.K; ++h) b3 += term;
+            }
+            Bl[l] += b3 / (T)P.K;
+        }
+        T a = (T)0;
+        for (int l = 0; l < nd.lv; ++l) a += ((pb.t1 - s) * Bl[l]) / (T)P.Mpow[nd.lv - l];
+        const T a2 = Gs / (T)P.Mpow[nd.lv];
+        result = a + a2;
+    }
+    P.value[(u64)solve * P.n_nodes + nidx] = result;
+}
+
+// points[solve][0] <- x0 (padded with zeros)
+template <typename T>
+__device__ __forceinline__ void init_item(const MlpParams<T>& P, const T* x0, u64 q)
+{
+    const u64 solve = q / (u64)P.dpad;
+    const int i = (int)(q % (u64)P.dpad);
+    const u64 src = (P.n_x0 == 1 ? 0 : solve) * (u64)P.pb.d;
+    P.points[solve * (u64)P.n_points * (u64)P.dpad + i] = i < P.pb.d ? x0[src + i] : (T)0;
+}
+
+#ifndef HDP_HOST_EMU
+// ---------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------
+template <typename T>
+__global__ void mlp_init_kernel(const __grid_constant__ MlpParams<T> P, const T* __restrict__ x0)
+{
+    const u64 total = (u64)P.n_solves * (u64)P.dpad;
+    for (u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (u64)gridDim.x * blockDim.x)
+        init_item<T>(P, x0, q);
+}
+
+template <typename T, int G>
+__global__ void __launch_bounds__(128) mlp_expand_kernel(const __grid_constant__ MlpParams<T> P, int off, int count)
+{
+    Ctx<T, G> c;
+    ctx_init<T, G>(c, P, (u64)blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31);
+    const u64 gid = c.tid / G;
+    if (gid >= (u64)count * (u64)P.n_solves) return;
+    expand_item<T, G>(c, P, off, gid);
+}
+
+// the work units: dynamic fetch, one warp takes 32/G consecutive work items at a time
+// (lane groups of a warp then run equal-shaped units in lockstep)
+template <typename T, int G>
+__global__ void __launch_bounds__(128, 3) mlp_units_kernel(const __grid_constant__ MlpParams<T> P)
+{
+    constexpr int GPW = 32 / G;
+    Ctx<T, G> c;
+    const int lane_w = threadIdx.x & 31;
+    ctx_init<T, G>(c, P, (u64)blockIdx.x * blockDim.x + threadIdx.x, lane_w);
+    const int sub = lane_w / G;
+    const u64 n_work = (u64)P.n_units * (u64)P.n_solves;
+    const u64 n_local = n_work > (u64)P.rank ? (n_work - (u64)P.rank + (u64)P.nranks - 1) / (u64)P.nranks : 0;
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane_w == 0) base = atomicAdd(P.work_ctr, (unsigned long long)GPW);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n_local) break;
+        const u64 wl = base + (u64)sub;
+        if (wl < n_local) unit_item<T, G>(c, P, wl * (u64)P.nranks + (u64)P.rank);
+    }
+    if (c.bad) atomicExch(&P.flags[0], 1);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) mlp_combine_kernel(const __grid_constant__ MlpParams<T> P, int off, int count)
+{
+    const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (u64)count * (u64)P.n_solves) return;
+    combine_item<T>(P, off, gid);
+}
+#endif // HDP_HOST_EMU
+
+} // namespace hdp

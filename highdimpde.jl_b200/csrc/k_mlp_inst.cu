@@ -1,0 +1,45 @@
+// k_mlp_inst.cu — one (T, G) instantiation of the MLP unit / expand kernels.
+// Build: nvcc ... -DHDP_INST_T=double -DHDP_INST_TN=f64 -DHDP_INST_G=8 -c k_mlp_inst.cu
+#include "k_mlp_launch.h"
+
+namespace hdp {
+
+#define HDP_CAT4_(a, b, c, d) a##b##c##d
+#define HDP_CAT4(a, b, c, d) HDP_CAT4_(a, b, c, d)
+#define HDP_INST_NAME HDP_CAT4(mlp_launchers_, HDP_INST_TN, _g, HDP_INST_G)
+
+namespace {
+typedef HDP_INST_T T_;
+constexpr int G_ = HDP_INST_G;
+
+int inst_max_blocks(int block)
+{
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mlp_units_kernel<T_, G_>, block, 0) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return nb;
+}
+cudaError_t inst_units(const MlpParams<T_>& P, int grid, int block, cudaStream_t st)
+{
+    mlp_units_kernel<T_, G_><<<grid, block, 0, st>>>(P);
+    return cudaGetLastError();
+}
+cudaError_t inst_expand(const MlpParams<T_>& P, int off, int count, int grid, int block, cudaStream_t st)
+{
+    mlp_expand_kernel<T_, G_><<<grid, block, 0, st>>>(P, off, count);
+    return cudaGetLastError();
+}
+} // namespace
+
+MlpLaunchers<HDP_INST_T> HDP_INST_NAME()
+{
+    MlpLaunchers<HDP_INST_T> l;
+    l.max_blocks_per_sm = inst_max_blocks;
+    l.units = inst_units;
+    l.expand = inst_expand;
+    return l;
+}
+
+} // namespace hdp

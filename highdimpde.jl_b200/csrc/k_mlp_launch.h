@@ -1,0 +1,20 @@
+// k_mlp_launch.h — per-(element type, group size) launch table of the MLP kernels.
+// Each (T, G) pair is compiled in its own translation unit (k_mlp_inst.cu with
+// -DHDP_INST_T / -DHDP_INST_G) so the build parallelises.
+#pragma once
+#include "k_mlp.cuh"
+
+namespace hdp {
+
+template <typename T> struct MlpLaunchers {
+    int (*max_blocks_per_sm)(int block);
+    cudaError_t (*units)(const MlpParams<T>& P, int grid, int block, cudaStream_t st);
+    cudaError_t (*expand)(const MlpParams<T>& P, int off, int count, int grid, int block, cudaStream_t st);
+};
+
+#define HDP_DECL_INST(T, TN, G) MlpLaunchers<T> mlp_launchers_##TN##_g##G();
+#define HDP_FOR_ALL_G(X, T, TN) X(T, TN, 1) X(T, TN, 2) X(T, TN, 4) X(T, TN, 8) X(T, TN, 16) X(T, TN, 32)
+HDP_FOR_ALL_G(HDP_DECL_INST, double, f64)
+HDP_FOR_ALL_G(HDP_DECL_INST, float, f32)
+
+} // namespace hdp

@@ -1,0 +1,215 @@
+// mlp_plan.cu — host-only planner (see mlp_plan.h).  Work-count recurrences:
+//   C(0)=0;  C(L) = Σ_{l<L} M^{L-l}·(1 + (1+K')·(C(l) + [l≥2]·C(l-1))) + M^L
+// and the analogous R (time uniforms) and S (sampler calls), which give the
+// closed-form consumption ordinal of every node of the reference's recursion.
+#include "mlp_plan.h"
+#include <math.h>
+#include <algorithm>
+#include <numeric>
+
+namespace hdp {
+
+void mlp_count_tables(int M, int L, int K, bool nonlocal, MlpCountTables* t)
+{
+    t->M = M; t->L = L; t->K = K; t->Kp = nonlocal ? K : 0;
+    const uint64_t Kp = (uint64_t)t->Kp;
+    t->Mpow[0] = 1;
+    for (int i = 1; i <= kMaxL + 1; ++i) t->Mpow[i] = t->Mpow[i - 1] * (uint64_t)M;
+    for (int i = 0; i <= kMaxL; ++i) {
+        t->C[i] = t->R[i] = t->S[i] = t->F[i] = t->G[i] = 0;
+        t->cs[i] = t->rs[i] = t->ss[i] = 0;
+        t->W[i] = t->Ws[i] = 0;
+    }
+    for (int lv = 0; lv <= L && lv <= kMaxL; ++lv) {
+        // per-site consumption at level lv (needs C[lv], C[lv-1], filled below for lv>=1)
+        if (lv >= 1) {
+            uint64_t c = 0, r = 0, s = 0, f = 0, g = 0;
+            for (int l = 0; l < lv; ++l) {
+                uint64_t num = t->Mpow[lv - l];
+                c += num * t->cs[l];
+                r += num * t->rs[l];
+                s += num * t->ss[l];
+                uint64_t ff = t->F[l] + (l >= 2 ? t->F[l - 1] : 0);
+                uint64_t gg = t->G[l] + (l >= 2 ? t->G[l - 1] : 0);
+                f += num * ((uint64_t)K * (l >= 2 ? 2 : 1) + (1 + Kp) * ff);
+                g += num * ((1 + Kp) * gg);
+            }
+            t->C[lv] = c + t->Mpow[lv];
+            t->R[lv] = r;
+            t->S[lv] = s;
+            t->F[lv] = f;
+            t->G[lv] = g + t->Mpow[lv];
+        }
+        uint64_t cc = t->C[lv] + (lv >= 2 ? t->C[lv - 1] : 0);
+        uint64_t rr = t->R[lv] + (lv >= 2 ? t->R[lv - 1] : 0);
+        uint64_t sc = t->S[lv] + (lv >= 2 ? t->S[lv - 1] : 0);
+        t->cs[lv] = 1 + (1 + Kp) * cc;
+        t->rs[lv] = 1 + (1 + Kp) * rr;
+        t->ss[lv] = Kp + (1 + Kp) * sc;
+        t->W[lv] = (double)t->C[lv] + 0.5 * (double)t->S[lv];
+        t->Ws[lv] = (double)t->cs[lv] + 0.5 * (double)t->ss[lv];
+    }
+}
+
+// `_get_loop_num(M, num, thread_id, NUM_THREADS)`  (src/MLP.jl:391-404); `1:loop_num`
+// with a Float64 loop_num iterates floor(loop_num) times.
+int64_t mlp_get_loop_num(int M, int64_t num, int thread_id, int nthreads)
+{
+    if (num < nthreads) return thread_id > num ? 0 : 1;
+    int64_t remainder = (int64_t)M % num;
+    double ln = (double)num / (double)nthreads;
+    if (remainder > 0 && thread_id <= remainder) ln += 1.0;
+    return (int64_t)floor(ln);
+}
+
+namespace {
+struct Builder {
+    MlpPlan* p;
+    const MlpCountTables& t;
+    double thresh;
+    int compat;
+    std::vector<double> unit_cost;
+
+    void add_unit(int node, int kind, int l, int64_t k0, int64_t k1, uint64_t c, uint64_t r, uint64_t s, double cost)
+    {
+        PlanUnit u{};
+        u.node = node; u.kind = kind; u.l = l; u.k0 = k0; u.k1 = k1; u.c = c; u.r = r; u.s = s;
+        p->units.push_back(u);
+        unit_cost.push_back(cost);
+    }
+
+    // one run of `nsites` consecutive level-l sites of node `id`, starting at (c,r,s)
+    void do_level(int id, int depth, int l, int64_t nsites, uint64_t& c, uint64_t& r, uint64_t& s)
+    {
+        if (nsites <= 0) return;
+        if (l >= 1 && t.W[l] > thresh) {
+            for (int64_t k = 0; k < nsites; ++k) {
+                PlanSite st{};
+                st.node = id; st.l = l; st.depth = depth;
+                st.c = c; st.r = r; st.s = s;
+                st.x2_point = p->n_points++;
+                st.x3_point0 = -1;
+                if (t.Kp > 0) { st.x3_point0 = p->n_points; p->n_points += t.Kp; }
+                st.child0 = (int32_t)p->children.size();
+                p->children.resize(p->children.size() + 2 * (size_t)(1 + t.Kp), -1);
+                p->sites.push_back(st);
+                c += t.cs[l]; r += t.rs[l]; s += t.ss[l];
+            }
+        } else {
+            int64_t chunk = (int64_t)floor(thresh / t.Ws[l]);
+            if (chunk < 1) chunk = 1;
+            for (int64_t k0 = 0; k0 < nsites; k0 += chunk) {
+                int64_t k1 = std::min(nsites, k0 + chunk);
+                add_unit(id, UNIT_LEVEL, l, k0, k1, c, r, s, (double)(k1 - k0) * t.Ws[l]);
+                c += (uint64_t)(k1 - k0) * t.cs[l];
+                r += (uint64_t)(k1 - k0) * t.rs[l];
+                s += (uint64_t)(k1 - k0) * t.ss[l];
+            }
+        }
+    }
+
+    int build_node(int lv, int point, int time_site, int depth, uint64_t c0, uint64_t r0, uint64_t s0, bool root)
+    {
+        const int id = (int)p->nodes.size();
+        {
+            PlanNode n{};
+            n.lv = lv; n.point = point; n.time_site = time_site; n.depth = depth;
+            p->nodes.push_back(n);
+        }
+        p->max_depth = std::max(p->max_depth, depth);
+        const int unit_begin = (int)p->units.size();
+        const int site_begin = (int)p->sites.size();
+        const bool compat_root = root && compat > 0;
+        if (t.W[lv] <= thresh && !compat_root) {
+            add_unit(id, UNIT_WHOLE, lv, 0, 1, c0, r0, s0, t.W[lv]);
+        } else {
+            uint64_t c = c0, r = r0, s = s0;
+            if (!compat_root) {
+                for (int l = 0; l < lv; ++l) do_level(id, depth, l, (int64_t)t.Mpow[lv - l], c, r, s);
+            } else {
+                // `_ml_picard_mlt`: tasks tid = 1..NT in turn, each its levels (src/MLP.jl:235-243, 262-388)
+                for (int tid = 1; tid <= compat; ++tid)
+                    for (int l = 0; l < lv; ++l)
+                        do_level(id, depth, l, mlp_get_loop_num(t.M, (int64_t)t.Mpow[lv - l], tid, compat), c, r, s);
+            }
+            // g-term: M^lv plain steps (src/MLP.jl:198-205 / :246-254)
+            int64_t ng = (int64_t)t.Mpow[lv];
+            int64_t chunk = (int64_t)floor(thresh);
+            if (chunk < 1) chunk = 1;
+            for (int64_t k0 = 0; k0 < ng; k0 += chunk) {
+                int64_t k1 = std::min(ng, k0 + chunk);
+                add_unit(id, UNIT_G, 0, k0, k1, c, r, s, (double)(k1 - k0));
+                c += (uint64_t)(k1 - k0);
+            }
+        }
+        const int unit_end = (int)p->units.size();
+        const int site_end = (int)p->sites.size();
+        p->nodes[id].unit_begin = unit_begin; p->nodes[id].unit_end = unit_end;
+        p->nodes[id].site_begin = site_begin; p->nodes[id].site_end = site_end;
+        // children of the explicit sites (consumption order inside a site:
+        // r, step, U_l(x2), [U_{l-1}(x2)], then per h: sample, U_l(x3), [U_{l-1}(x3)])
+        for (int si = site_begin; si < site_end; ++si) {
+            const PlanSite st = p->sites[si];
+            const int l = st.l;
+            uint64_t c = st.c + 1, r = st.r + 1, s = st.s;
+            int ch = st.child0;
+            int id0 = build_node(l, st.x2_point, si, depth + 1, c, r, s, false);
+            p->children[ch++] = id0;
+            c += t.C[l]; r += t.R[l]; s += t.S[l];
+            if (l >= 2) {
+                int id1 = build_node(l - 1, st.x2_point, si, depth + 1, c, r, s, false);
+                p->children[ch++] = id1;
+                c += t.C[l - 1]; r += t.R[l - 1]; s += t.S[l - 1];
+            } else ch++;
+            for (int h = 0; h < t.Kp; ++h) {
+                s += 1; // the sampler call itself
+                int idh = build_node(l, st.x3_point0 + h, si, depth + 1, c, r, s, false);
+                p->children[ch++] = idh;
+                c += t.C[l]; r += t.R[l]; s += t.S[l];
+                if (l >= 2) {
+                    int idh1 = build_node(l - 1, st.x3_point0 + h, si, depth + 1, c, r, s, false);
+                    p->children[ch++] = idh1;
+                    c += t.C[l - 1]; r += t.R[l - 1]; s += t.S[l - 1];
+                } else ch++;
+            }
+        }
+        return id;
+    }
+};
+} // namespace
+
+void mlp_build_plan(int M, int L, int K, bool nonlocal, double thresh, int compat_threads, MlpPlan* plan)
+{
+    mlp_count_tables(M, L, K, nonlocal, &plan->tab);
+    plan->thresh = thresh;
+    plan->compat_threads = compat_threads;
+    plan->nodes.clear(); plan->sites.clear(); plan->units.clear(); plan->children.clear();
+    plan->n_points = 1;
+    plan->max_depth = 0;
+    Builder b{plan, plan->tab, thresh, compat_threads, {}};
+    b.build_node(L, 0, -1, 0, 0, 0, 0, true);
+    // execution order: most expensive first (LPT); ties keep creation order so that
+    // equal-shaped units stay adjacent (lane groups of one warp run in lockstep)
+    plan->exec_order.resize(plan->units.size());
+    std::iota(plan->exec_order.begin(), plan->exec_order.end(), 0);
+    std::stable_sort(plan->exec_order.begin(), plan->exec_order.end(),
+                     [&](int a, int c) { return b.unit_cost[a] > b.unit_cost[c]; });
+    // depth buckets
+    const int nd = plan->max_depth + 1;
+    plan->site_depth_off.assign(nd + 1, 0);
+    plan->node_depth_off.assign(nd + 1, 0);
+    for (auto& s : plan->sites) plan->site_depth_off[s.depth + 1]++;
+    for (auto& n : plan->nodes) plan->node_depth_off[n.depth + 1]++;
+    for (int i = 0; i < nd; ++i) {
+        plan->site_depth_off[i + 1] += plan->site_depth_off[i];
+        plan->node_depth_off[i + 1] += plan->node_depth_off[i];
+    }
+    plan->sites_by_depth.resize(plan->sites.size());
+    plan->nodes_by_depth.resize(plan->nodes.size());
+    std::vector<int32_t> so(plan->site_depth_off.begin(), plan->site_depth_off.end() - 1);
+    std::vector<int32_t> no(plan->node_depth_off.begin(), plan->node_depth_off.end() - 1);
+    for (size_t i = 0; i < plan->sites.size(); ++i) plan->sites_by_depth[so[plan->sites[i].depth]++] = (int32_t)i;
+    for (size_t i = 0; i < plan->nodes.size(); ++i) plan->nodes_by_depth[no[plan->nodes[i].depth]++] = (int32_t)i;
+}
+
+} // namespace hdp

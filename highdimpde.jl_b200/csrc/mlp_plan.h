@@ -1,0 +1,97 @@
+// mlp_plan.h — host-side planner that cuts the multilevel-Picard recursion
+// tree (src/MLP.jl:102-208) into GPU work units.
+//
+// The geometry of the tree (sample times, points) never depends on a value of
+// u — only the f(...) combinations do — and every random draw is addressed by
+// its consumption ordinal in the reference's depth-first order.  So the tree
+// can be cut anywhere: the top is expanded into explicit *nodes* (calls
+// U_lv(x,s)) and *sites* (one (l,k) iteration of the level loops); everything
+// below the cut is evaluated on-chip, depth-first, by one lane group per
+// *unit*.  A call's value is a plain sum over its sites, so a unit is a slice
+// of one node's site list (or a whole small call); the nonlinearity f is
+// applied where complete child values meet, in the bottom-up combine.
+#pragma once
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+namespace hdp {
+
+constexpr int kMaxL = 6;
+
+enum { UNIT_LEVEL = 0, UNIT_G = 1, UNIT_WHOLE = 2 };
+
+struct PlanUnit {
+    int32_t node;
+    int32_t kind;     // UNIT_*
+    int32_t l;        // level of the sites in the slice (UNIT_LEVEL)
+    int32_t _pad;
+    int64_t k0, k1;   // site range [k0,k1) within the level (or g-term range)
+    uint64_t c, r, s; // consumption ordinals at the first site: path-step / time / sampler
+};
+
+struct PlanNode {
+    int32_t lv;        // call level: this node is U_lv(x, s)
+    int32_t point;     // index of x in the per-solve point table
+    int32_t time_site; // site whose r is this node's start time s (-1: root, s = t0)
+    int32_t depth;
+    int32_t unit_begin, unit_end; // units of this node (creation order)
+    int32_t site_begin, site_end; // explicit sites of this node
+};
+
+struct PlanSite {
+    int32_t node;      // parent call
+    int32_t l;         // level of this site
+    int32_t x2_point;  // point index of x2
+    int32_t x3_point0; // first of K' consecutive x3 points (-1 if local)
+    int32_t child0;    // index into children[]: [U_l(x2), U_{l-1}(x2), {U_l(x3_h), U_{l-1}(x3_h)}_h], -1 = identically 0
+    int32_t depth;     // depth of the parent node
+    uint64_t c, r, s;  // ordinals at the start of the site
+};
+
+struct MlpCountTables {
+    int M, L, K, Kp; // Kp = K if a sampler integrates, else 0
+    uint64_t C[kMaxL + 1], R[kMaxL + 1], S[kMaxL + 1]; // per call U_l
+    uint64_t F[kMaxL + 1], G[kMaxL + 1];
+    uint64_t cs[kMaxL + 1], rs[kMaxL + 1], ss[kMaxL + 1]; // per level-l site
+    uint64_t Mpow[kMaxL + 2];
+    double W[kMaxL + 1];  // work model of a call
+    double Ws[kMaxL + 1]; // work model of a level-l site
+};
+
+void mlp_count_tables(int M, int L, int K, bool nonlocal, MlpCountTables* t);
+
+struct MlpPlan {
+    MlpCountTables tab;
+    double thresh = 0;
+    int compat_threads = 0;
+    std::vector<PlanNode> nodes;
+    std::vector<PlanSite> sites;
+    std::vector<PlanUnit> units;
+    std::vector<int32_t> children;
+    std::vector<int32_t> exec_order;    // unit ids, most expensive first
+    std::vector<int32_t> sites_by_depth;  // site ids grouped by depth
+    std::vector<int32_t> site_depth_off;  // size max_depth+2
+    std::vector<int32_t> nodes_by_depth;
+    std::vector<int32_t> node_depth_off;
+    int n_points = 1;
+    int max_depth = 0;
+    // device copies (owned; freed in destructor)
+    void* d_nodes = nullptr;
+    void* d_sites = nullptr;
+    void* d_units = nullptr;
+    void* d_children = nullptr;
+    void* d_exec = nullptr;
+    void* d_sites_by_depth = nullptr;
+    void* d_nodes_by_depth = nullptr;
+    ~MlpPlan();
+};
+
+// thresh: maximum work (path-steps + sampler calls) of one unit.
+// compat_threads > 0 reproduces the `_ml_picard_mlt` / `_get_loop_num`
+// enumeration of the root call (src/MLP.jl:218-404).
+void mlp_build_plan(int M, int L, int K, bool nonlocal, double thresh, int compat_threads, MlpPlan* plan);
+
+int64_t mlp_get_loop_num(int M, int64_t num, int thread_id, int nthreads);
+
+} // namespace hdp

@@ -1,0 +1,81 @@
+"""`_reflect` and the DeepSplitting `sde_loop!` — mirrors of src/reflect.jl:8-82
+and src/DeepSplitting.jl:153-166, served by the K4 / K1 kernels."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi as capi
+from .sampling import NoSampling
+
+
+def _reflect(a, b, s, e, *, return_bounces=False, handle=None):
+    """_reflect(a, b, s, e): reflection of the segment a→b on the hypercube [s, e]
+    (src/reflect.jl).  a, b: d-vectors (Vector method, :8-55) or d×B column-major
+    matrices (AbstractArray method, :58-82); s, e scalars or length-d vectors.
+    Raises StartOutsideDomain when a is not inside (:12, :59)."""
+    h = handle or capi.default_handle()
+    a = np.asarray(a)
+    dt = a.dtype if a.dtype in (np.float32, np.float64) else np.dtype(np.float64)
+    a = np.asarray(a, dtype=dt, order="F")
+    b = np.asarray(b, dtype=dt, order="F")
+    if a.shape != b.shape:
+        raise ValueError("a not same dim as b")  # :13, :60
+    d = a.shape[0]
+    B = 1 if a.ndim == 1 else int(np.prod(a.shape[1:]))
+    scalar = np.ndim(s) == 0 and np.ndim(e) == 0
+    if scalar:
+        lo = np.array([s], dtype=dt)
+        hi = np.array([e], dtype=dt)
+    else:
+        lo = np.ascontiguousarray(np.broadcast_to(np.asarray(s, dtype=dt), (d,)))
+        hi = np.ascontiguousarray(np.broadcast_to(np.asarray(e, dtype=dt), (d,)))
+    out = np.empty_like(a, order="F")
+    cnt = np.empty(a.shape, dtype=np.int32, order="F") if return_bounces else None
+    fn = h.lib.hdp_reflect_f64 if dt == np.float64 else h.lib.hdp_reflect_f32
+    capi.check(h.h, fn(h.h, capi.np_ptr(a), capi.np_ptr(b), capi.np_ptr(out), d, B, capi.np_ptr(lo),
+                       capi.np_ptr(hi), int(scalar), capi.np_ptr(cnt), capi.HDP_MEM_HOST))
+    return (out, cnt) if return_bounces else out
+
+
+def sde_loop(prob, y0, y1, nsteps, dt, *, ts=None, dWall=None, seed=0, mc_sample=None, z=None, handle=None):
+    """sde_loop!(y0, y1, dWall) (src/DeepSplitting.jl:153-166): `nsteps` reflected
+    Euler–Maruyama steps of the d×B batch.  y1 holds x0_batch on entry (:182); on
+    return y0 is the state before the last step and y1 the final state.
+    dWall: optional injected d×B×nsteps standard normals (the reference's array after
+    randn!, :154); by default the normals are Philox draws generated in registers.
+    mc_sample / z: optional fused `mc_sample!(z, y1)` (:186-189), z is d×B×K."""
+    h = handle or capi.default_handle()
+    dtp = y1.dtype
+    if dtp not in (np.float32, np.float64) or y0.dtype != dtp:
+        raise TypeError("y0, y1 must both be float32 or float64")
+    for arr in (y0, y1):
+        if arr.ndim != 2 or not arr.flags.f_contiguous:
+            raise ValueError("y0, y1 must be d×B column-major (order='F') matrices")
+    d, B = y1.shape
+    if d != prob.d or y0.shape != y1.shape:
+        raise ValueError("shape mismatch")
+    pb, keep = prob.to_c()
+    x0s, keep2 = prob.x0_sample._descriptor(d)
+    mcs, keep3 = (mc_sample or NoSampling())._descriptor(d)
+    K = 0
+    if z is not None:
+        if z.dtype != dtp or not z.flags.f_contiguous or z.shape[:2] != (d, B):
+            raise ValueError("z must be d×B×K column-major of the same element type")
+        K = int(np.prod(z.shape[2:]))
+    dw = None
+    if dWall is not None:
+        dw = np.asarray(dWall, dtype=dtp, order="F")
+        if dw.shape != (d, B, nsteps):
+            raise ValueError("dWall must be d×B×nsteps")
+    tsa = None if ts is None else np.ascontiguousarray(ts, dtype=dtp)
+    if dtp == np.float64:
+        fn, dtc = h.lib.hdp_sde_loop_f64, C.c_double(dt)
+    else:
+        fn, dtc = h.lib.hdp_sde_loop_f32, C.c_float(dt)
+    capi.check(h.h, fn(h.h, C.byref(pb), capi.np_ptr(y0), capi.np_ptr(y1), B, int(nsteps), dtc,
+                       capi.np_ptr(tsa), C.byref(x0s), int(seed), capi.np_ptr(dw), C.byref(mcs),
+                       capi.np_ptr(z), K, capi.HDP_NORMAL_DEFAULT, capi.HDP_MEM_HOST))
+    del keep, keep2, keep3
+    return y0, y1

@@ -1,0 +1,51 @@
+// hdp_host_emu_shim.h — TEST INFRASTRUCTURE ONLY.
+// Lets g++ compile the product's device code (hdp_device.cuh, k_mlp.cuh) for the
+// host with a single-lane group (G = 1), so the tree planner, the consumption-
+// ordinal arithmetic and the combine logic can be checked against the oracle on
+// a machine without a GPU.  Never compiled into libhdpde_b200.so.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#define __device__
+#define __host__
+#define __global__
+#define __forceinline__ inline
+#define __restrict__
+#define __grid_constant__
+#define __launch_bounds__(...)
+
+struct alignas(16) double2 { double x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+
+// IEEE round-to-nearest primitives (the emulation is built with -ffp-contract=off)
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline double __ddiv_rn(double a, double b) { return a / b; }
+static inline double __dsqrt_rn(double a) { return sqrt(a); }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline float __fsqrt_rn(float a) { return sqrtf(a); }
+static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+static inline void sincospi(double x, double* s, double* c) { *s = sin(M_PI * x); *c = cos(M_PI * x); }
+#define __log2f(x) log2f(x)
+#define __cosf(x) cosf(x)
+#define __sinf(x) sinf(x)
+template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int) { return v; }
+template <typename T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v)
+{
+    unsigned long long o = *p;
+    *p += v;
+    return o;
+}
+static inline int atomicExch(int* p, int v)
+{
+    int o = *p;
+    *p = v;
+    return o;
+}

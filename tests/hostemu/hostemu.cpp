@@ -1,0 +1,131 @@
+// hostemu.cpp — TEST INFRASTRUCTURE ONLY: runs the product's MLP device code
+// (k_mlp.cuh, compiled for the host through hdp_host_emu_shim.h with G = 1) and
+// the product's planner (mlp_plan.cu) on the CPU.  Used by tests/ to check the
+// tree cut / ordinal / combine logic against the oracle without a GPU.
+// It is NOT a fallback: libhdpde_b200.so never contains or calls it.
+#define HDP_HOST_EMU 1
+#include <vector>
+#include <algorithm>
+#include "k_mlp.cuh"
+#include "hdp_convert.h"
+
+using namespace hdp;
+
+namespace hdp {
+MlpPlan::~MlpPlan() {} // no device copies in the emulation
+}
+
+template <typename T>
+static int emu_solve(const hdp_problem* prob, const hdp_mlp_cfg* cfg, const T* x0, T* u_out, hdp_mlp_stats* stats)
+{
+    const int M = cfg->M, L = cfg->L, K = cfg->K, n_solves = cfg->n_solves;
+    if (M < 1 || K < 1 || L < 1 || L > kMaxL || n_solves < 1) return HDP_ERR_BAD_ARG;
+    const bool nonlocal = cfg->sampler.kind != HDP_SAMPLER_NONE;
+    constexpr int VEC = Tr<T>::VEC;
+    constexpr int G = 1;
+    MlpParams<T> P;
+    memset(&P, 0, sizeof(P));
+    fill_dev_problem<T>(prob, &P.pb);
+    fill_dev_sampler<T>(&cfg->sampler, &P.sm);
+    const int d = prob->d;
+    std::vector<T> lohi, ab;
+    if (prob->has_bc && !prob->bc_is_scalar) {
+        lohi.resize(2 * d);
+        for (int i = 0; i < d; ++i) { lohi[i] = (T)prob->lo[i]; lohi[d + i] = (T)prob->hi[i]; }
+        P.pb.lo = lohi.data(); P.pb.hi = lohi.data() + d;
+    }
+    if (cfg->sampler.kind == HDP_SAMPLER_UNIFORM && !cfg->sampler.bounds_are_scalar) {
+        ab.resize(2 * d);
+        for (int i = 0; i < d; ++i) { ab[i] = (T)cfg->sampler.a[i]; ab[d + i] = (T)cfg->sampler.b[i]; }
+        P.sm.a = ab.data(); P.sm.b = ab.data() + d;
+    }
+    MlpCountTables tab;
+    mlp_count_tables(M, L, K, nonlocal, &tab);
+    const int compat = cfg->compat_mlt_threads > 0 ? cfg->compat_mlt_threads : 0;
+    double thresh = tab.W[L];
+    if (cfg->target_units > 0) thresh = std::max(1.0, tab.W[L] * n_solves / (double)cfg->target_units);
+    if (thresh > tab.W[L]) thresh = tab.W[L];
+    MlpPlan plan;
+    mlp_build_plan(M, L, K, nonlocal, thresh, compat, &plan);
+
+    const int nvec = (d + VEC - 1) / VEC;
+    P.M = M; P.K = K; P.L = L; P.Kp = tab.Kp;
+    P.nvec = nvec; P.npl = nvec; P.dpad = nvec * VEC;
+    for (int i = 0; i <= kMaxL; ++i) {
+        P.C[i] = tab.C[i]; P.R[i] = tab.R[i]; P.S[i] = tab.S[i];
+        P.cs[i] = tab.cs[i]; P.rs[i] = tab.rs[i]; P.ss[i] = tab.ss[i];
+    }
+    for (int i = 0; i <= kMaxL + 1; ++i) P.Mpow[i] = tab.Mpow[i];
+    P.seed0 = cfg->seed; P.n_solves = n_solves; P.n_x0 = cfg->n_x0;
+    P.units = plan.units.data(); P.exec = plan.exec_order.data(); P.nodes = plan.nodes.data();
+    P.sites = plan.sites.data(); P.children = plan.children.data();
+    P.sites_by_depth = plan.sites_by_depth.data(); P.nodes_by_depth = plan.nodes_by_depth.data();
+    P.n_units = (int)plan.units.size(); P.n_nodes = (int)plan.nodes.size();
+    P.n_sites = (int)plan.sites.size(); P.n_points = plan.n_points;
+    P.rank = 0; P.nranks = 1;
+    P.r_tape = (const T*)cfg->r_tape; P.n_tape = (const T*)cfg->n_tape; P.s_tape = (const T*)cfg->s_tape;
+    std::vector<T> points((size_t)n_solves * P.n_points * P.dpad + VEC), feat((size_t)n_solves * P.n_points);
+    std::vector<T> site_r((size_t)n_solves * std::max(P.n_sites, 1)), value((size_t)n_solves * P.n_nodes);
+    std::vector<double> partial((size_t)n_solves * P.n_units);
+    // 16-byte aligned scratch
+    std::vector<double2> scratch_raw((size_t)(2 * L) * P.npl * VEC * sizeof(T) / sizeof(double2) + 2);
+    unsigned long long ctr[2] = {0, 0};
+    int flags[2] = {0, 0};
+    // align points to 16 B
+    std::vector<double2> points_raw(((size_t)n_solves * P.n_points * P.dpad * sizeof(T)) / sizeof(double2) + 2);
+    P.points = (T*)points_raw.data(); P.feat = feat.data(); P.site_r = site_r.data();
+    P.partial = partial.data(); P.value = value.data(); P.scratch = (T*)scratch_raw.data();
+    P.total_threads = 1; P.work_ctr = &ctr[0]; P.bounce_ctr = &ctr[1]; P.flags = flags;
+
+    for (u64 q = 0; q < (u64)n_solves * P.dpad; ++q) init_item<T>(P, x0, q);
+    Ctx<T, G> c;
+    ctx_init<T, G>(c, P, 0, 0);
+    for (int dep = 0; dep <= plan.max_depth; ++dep) {
+        int off = plan.site_depth_off[dep], cnt = plan.site_depth_off[dep + 1] - off;
+        for (u64 it = 0; it < (u64)cnt * n_solves; ++it) { c.nb = 0; expand_item<T, G>(c, P, off, it); }
+    }
+    for (u64 w = 0; w < (u64)P.n_units * n_solves; ++w) unit_item<T, G>(c, P, w);
+    if (c.bad) flags[0] = 1;
+    for (int dep = plan.max_depth; dep >= 0; --dep) {
+        int off = plan.node_depth_off[dep], cnt = plan.node_depth_off[dep + 1] - off;
+        for (u64 it = 0; it < (u64)cnt * n_solves; ++it) combine_item<T>(P, off, it);
+    }
+    for (int i = 0; i < n_solves; ++i) u_out[i] = value[(size_t)i * P.n_nodes];
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->per_solve.path_steps = tab.C[L];
+        stats->per_solve.time_uniforms = tab.R[L];
+        stats->per_solve.sampler_calls = tab.S[L];
+        stats->per_solve.f_evals = tab.F[L];
+        stats->per_solve.g_evals = tab.G[L];
+        stats->bounces = ctr[1];
+        stats->n_units = P.n_units; stats->n_nodes = P.n_nodes; stats->n_sites = P.n_sites;
+        stats->group_size = 1;
+    }
+    return flags[0] ? HDP_ERR_START_OUTSIDE_DOMAIN : HDP_OK;
+}
+
+extern "C" int hdp_emu_mlp_solve_f64(const hdp_problem* prob, const hdp_mlp_cfg* cfg, const double* x0,
+                                     double* u_out, hdp_mlp_stats* stats)
+{
+    return emu_solve<double>(prob, cfg, x0, u_out, stats);
+}
+extern "C" int hdp_emu_mlp_solve_f32(const hdp_problem* prob, const hdp_mlp_cfg* cfg, const float* x0,
+                                     float* u_out, hdp_mlp_stats* stats)
+{
+    return emu_solve<float>(prob, cfg, x0, u_out, stats);
+}
+// raw draw of the emulated generator (libm transcendentals): for generator sanity tests
+extern "C" void hdp_emu_draw_f64(uint64_t seed, int stream, uint64_t ord, uint32_t group, int normal, double out[2])
+{
+    Vec<double> v = draw_vec<double>(seed, stream, ord, group, normal != 0);
+    out[0] = v.v[0]; out[1] = v.v[1];
+}
+extern "C" void hdp_emu_plan_summary(int M, int L, int K, int nonlocal, double thresh, int compat, int64_t out[8])
+{
+    MlpPlan plan;
+    mlp_build_plan(M, L, K, nonlocal != 0, thresh, compat, &plan);
+    out[0] = (int64_t)plan.nodes.size(); out[1] = (int64_t)plan.sites.size(); out[2] = (int64_t)plan.units.size();
+    out[3] = plan.n_points; out[4] = plan.max_depth;
+    out[5] = (int64_t)plan.tab.C[L]; out[6] = (int64_t)plan.tab.R[L]; out[7] = (int64_t)plan.tab.S[L];
+}
