@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native HighDimPDE.jl Monte-Carlo hot path.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    (N>1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N … bench.py --gpus N …)
+
+Workload (BASELINE.json configs[1] = SURVEY.md C2): MLP Allen–Cahn d=100 with Neumann
+reflection on [-1/2,1/2]^d, M=4, L=4, K=10, fp64.  One *step* = one pass of the hot path
+over one batch of independent solves (4096 per GPU, seeds seed..seed+n-1).
+metric = MLP solves/s (whole job); the same line carries reflected SDE path-steps/s
+(= solves/s × 4916) and, under "extra", the batched reflected Euler–Maruyama loop of
+configs[2] (C3: B=8192, d=100, N=10, fp32).
+
+`value`  : device time (CUDA events on the library's stream around init/expand/units/combine),
+           inputs already resident, max over ranks.
+`e2e`    : the same metric through the public API `_ml_picard_batch` (the call `solve` makes):
+           host buffers in, host→device copy of x0 and device→host read of u inside the timed
+           region, wall clock around each call with a stream sync on both sides.
+`--impl reference`: the reference's algorithm on the host cores (the C oracle port — Julia is
+           not in this image), every host thread busy with independent serial solves.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+D, M, L, K = 100, 4, 4, 10
+SOLVES_PER_GPU = 4096
+PATH_STEPS_PER_SOLVE = 4916          # C(4) for M=4 local
+I64_PER_COORD_STEP = 39              # fp64 pipe-instr budget per reflected coordinate-step
+F_ALG_PER_COORD_STEP = 11            # algorithmic FLOP per reflected coordinate-step
+METRIC = "mlp_solves_per_sec"
+UNIT = "solves/s"
+WORKLOAD = "C2: MLP Allen-Cahn d=100, Neumann reflection [-1/2,1/2]^d, M=4 L=4 K=10, fp64, x0=0, tspan=(0,0.5)"
+
+
+def make_problem(H):
+    prob = H.ParabolicPDEProblem(0.0, 1.0, np.zeros(D), (0.0, 0.5), g=H.ExpSumSq(0.25), f=H.FAllenCahn(1.0),
+                                 neumann_bc=(np.full(D, -0.5), np.full(D, 0.5)))
+    return prob, H.MLP(M=M, L=L, K=K)
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock / throttle reasons DURING the timed region (NVML, else nvidia-smi)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._t = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._dev, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nvml = None
+
+    _REASONS = {0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+                0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
+                0x100: "display_clock_setting"}
+
+    def _loop(self):
+        p = self._nvml
+        while not self._stop.is_set():
+            try:
+                if p is not None:
+                    self.samples.append(p.nvmlDeviceGetClockInfo(self._dev, p.NVML_CLOCK_SM))
+                    try:
+                        r = p.nvmlDeviceGetCurrentClocksEventReasons(self._dev)
+                    except Exception:
+                        r = p.nvmlDeviceGetCurrentClocksThrottleReasons(self._dev)
+                    for bit, name in self._REASONS.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                else:
+                    import subprocess
+                    out = subprocess.run(
+                        ["nvidia-smi", "-i", str(self.index),
+                         "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+                         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                         "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits"],
+                        capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                    self.samples.append(int(out[0]))
+                    self.max_mhz = int(out[1])
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), out[2:]):
+                        if "Active" in v and "Not" not in v:
+                            self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        self._t = threading.Thread(target=self._loop, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# --------------------------------------------------------------------------- reference arm
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path (oracle port), all host threads."""
+    if rank != 0:
+        return
+    import hdpde_b200 as H
+    from oracle import oracle as O
+    prob, alg = make_problem(H)
+    pb, _k = prob.to_c()
+    sm, _k2 = alg.mc_sample._descriptor(D)
+    cores = os.cpu_count() or 1
+    n_sample = max(cores * 4, 32)  # bounded sample of the same workload per step
+    for w in range(args.warmup):
+        O.bench_solves(pb, sm, M, L, K, prob.x, cores, cores, seed=w)
+    tot = 0.0
+    us = []
+    for s in range(args.steps):
+        u, sec = O.bench_solves(pb, sm, M, L, K, prob.x, n_sample, cores, seed=1000 + s * n_sample)
+        tot += sec
+        us.append(u.mean())
+    value = n_sample * args.steps / tot
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "solves_per_step": n_sample,
+                   "note": "reference algorithm restated in C (oracle/), Julia unavailable in this image"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n_sample} independent serial _ml_picard solves per step on {cores} host threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "reflected_path_steps_per_sec": value * PATH_STEPS_PER_SOLVE,
+        "u_mean": float(np.mean(us)),
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- our arm
+def flush_l2(torch, buf):
+    buf.add_(1.0)
+    torch.cuda.synchronize()
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import hdpde_b200 as H
+    from hdpde_b200 import dist as HD
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device visible; the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    h = H.Handle(local_rank)
+    prob, alg = make_problem(H)
+    n_local = SOLVES_PER_GPU
+    n_total = n_local * world
+    seed0 = 20261019
+    flush_buf = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device="cuda")  # 256 MB > 126 MB L2
+
+    def step(i):
+        # solve index is global: rank r owns solves [r*n_local, (r+1)*n_local) of this step's batch
+        seed = seed0 + i * n_total + rank * n_local
+        t0 = time.perf_counter()
+        u, st = H._ml_picard_batch(prob, alg, n_solves=n_local, seed=seed, handle=h)
+        t1 = time.perf_counter()
+        return u, st, t1 - t0
+
+    for w in range(args.warmup):
+        step(-1 - w)
+    clk = ClockSampler(local_rank)
+    barrier()
+    clk.start()
+    dev_ms, e2e_s, launches, bounces = 0.0, 0.0, 0, 0
+    means = []
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush_l2(torch, flush_buf)
+        u, st, sec = step(i)
+        dev_ms += st["device_ms"]
+        e2e_s += sec
+        launches += st["n_launches"]
+        bounces += st["bounces"]
+        means.append(float(u.mean()))
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = clk.stop()
+
+    # ---- C3 extra: batched reflected EM loop, fp32, device-resident state (configs[2]) ----
+    extra = {}
+    try:
+        extra = bench_sde_loop(torch, H, h, local_rank)
+    except Exception as e:  # pragma: no cover
+        extra = {"sde_loop_error": repr(e)}
+
+    peak64 = h.measure_pipe_peak(64)
+    peak32 = h.measure_pipe_peak(32)
+
+    if dist is not None:
+        dev_ms = HD.max_over_ranks(dev_ms)
+        e2e_s = HD.max_over_ranks(e2e_s)
+        t = torch.tensor([launches, bounces], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        launches, bounces = int(t[0].item()), int(t[1].item())
+
+    if rank == 0:
+        value = n_total * args.steps / (dev_ms * 1e-3)
+        e2e = n_total * args.steps / e2e_s
+        coord_steps_per_s_gpu = (n_local * args.steps * PATH_STEPS_PER_SOLVE * D) / (dev_ms * 1e-3)
+        achieved = coord_steps_per_s_gpu * I64_PER_COORD_STEP
+        cpu = cpu_baseline(H, prob, alg)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "solves_per_gpu_per_step": n_local, "global_solves_per_step": n_total,
+                       "parallelism": f"solves sharded over {world} rank(s), no data-path collective",
+                       "l2": "256 MB flush between steps (untimed); the path is compute-bound, inputs are d doubles",
+                       "rng": "Philox4x32-10 + fp64 Box-Muller generated in registers"},
+            "reflected_path_steps_per_sec": value * PATH_STEPS_PER_SOLVE,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": D * 8, "d2h_bytes_per_step": n_local * 8,
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "api": "hdpde_b200._ml_picard_batch -> hdp_mlp_solve_f64 (host buffers)"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "fp64", "achieved": achieved / 1e12, "peak": peak64 / 1e12, "unit": "Tlane-instr/s",
+                         "frac": achieved / peak64, "traffic": None,
+                         "kernel": "mlp_units_kernel<double,G>",
+                         "algorithmic": f"{I64_PER_COORD_STEP} fp64 pipe-instr per reflected coordinate-step x "
+                                        f"{PATH_STEPS_PER_SOLVE * D} coordinate-steps per solve (SURVEY.md 8d)",
+                         "peak_source": "hdp_measure_pipe_peak(64): DFMA saturation microbenchmark, measured live",
+                         "flop_form": {"achieved_tflops": coord_steps_per_s_gpu * F_ALG_PER_COORD_STEP / 1e12,
+                                       "peak_tflops": 2 * peak64 / 1e12},
+                         "fp32_peak_tlane_instr": peak32 / 1e12},
+            "cpu_baseline": cpu,
+            "wall_s_timed_region": wall,
+            "u_mean": float(np.mean(means)), "bounces_per_path_step": bounces / (n_total * args.steps * PATH_STEPS_PER_SOLVE),
+            "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    h.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def bench_sde_loop(torch, H, h, local_rank):
+    """C3: `sde_loop!` with reflection, fp32, B=8192 (the config) and B=1,048,576 (saturating)."""
+    import ctypes as C
+    out = {}
+    d, N = 100, 10
+    prob = H.ParabolicPDEProblem(0.0, 1.0, np.zeros(d, dtype=np.float32), (0.0, 1.0), g=H.SumSq(), f=H.FZero(),
+                                 neumann_bc=(-1.0, 1.0))
+    pb, _k = prob.to_c()
+    none, _k2 = H.NoSampling()._descriptor(d)
+    for B in (8192, 1 << 20):
+        y1 = torch.zeros(d * B, dtype=torch.float32, device="cuda")
+        y0 = torch.empty_like(y1)
+        torch.cuda.synchronize()
+        flags = H.capi.HDP_MEM_DEVICE | H.capi.HDP_ASYNC
+        reps = 20
+        best = None
+        for r in range(reps + 3):
+            y1.zero_()
+            torch.cuda.synchronize()
+            rc = h.lib.hdp_sde_loop_f32(h.h, C.byref(pb), C.c_void_p(y0.data_ptr()), C.c_void_p(y1.data_ptr()), B, N,
+                                        C.c_float(0.1), None, C.byref(none), 7 + r, None, C.byref(none), None, 0,
+                                        H.capi.HDP_NORMAL_DEFAULT, flags)
+            H.capi.check(h.h, rc)
+            ms = h.last_device_ms()
+            if r >= 3:
+                best = ms if best is None else min(best, ms)
+        h.sync()
+        ps = B * N / (best * 1e-3)
+        out[f"sde_loop_f32_B{B}"] = {"path_steps_per_sec": ps, "coord_steps_per_sec": ps * d, "kernel_ms": best,
+                                     "bytes_written": 2 * d * B * 4}
+    return out
+
+
+def cpu_baseline(H, prob, alg):
+    """Oracle port on the box's host cores, bounded sample (rank 0, N=1 only in spirit; cheap)."""
+    from oracle import oracle as O
+    pb, _k = prob.to_c()
+    sm, _k2 = alg.mc_sample._descriptor(D)
+    cores = os.cpu_count() or 1
+    O.bench_solves(pb, sm, M, L, K, prob.x, cores, cores, seed=1)
+    n = cores * 16
+    u, sec = O.bench_solves(pb, sm, M, L, K, prob.x, n, cores, seed=99)
+    if sec < 8.0:
+        n2 = int(n * 12.0 / max(sec, 1e-3))
+        u, sec = O.bench_solves(pb, sm, M, L, K, prob.x, n2, cores, seed=199)
+        n = n2
+    return {"value": n / sec, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} independent serial _ml_picard solves of the same workload on {cores} host threads "
+                      f"({sec:.1f} s), C restatement of the reference (oracle/), Julia unavailable",
+            "u_mean": float(u.mean())}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3  # timing rule: W >= 3
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -29,6 +29,7 @@ HDP_ERR_UNSUPPORTED = -8
 
 HDP_MEM_HOST = 0
 HDP_MEM_DEVICE = 1
+HDP_ASYNC = 2
 
 HDP_COEF_CONST, HDP_COEF_LINEAR = 0, 1
 HDP_G_SUMSQ, HDP_G_INV_SUMSQ, HDP_G_EXP_SUMSQ, HDP_G_MIN, HDP_G_GAUSS = 0, 1, 2, 3, 4
@@ -114,6 +115,7 @@ SYMBOLS = {
     "hdp_tape_fill_f64": (_i, [_H, _VP, _i, _i, _i, _u64, _u64, _u64, _i]),
     "hdp_tape_fill_f32": (_i, [_H, _VP, _i, _i, _i, _u64, _u64, _u64, _i]),
     "hdp_measure_pipe_peak": (_i, [_H, _i, C.POINTER(C.c_double)]),
+    "hdp_last_device_ms": (_i, [_H, C.POINTER(C.c_double)]),
 }
 
 
@@ -227,6 +229,11 @@ class Handle:
     def measure_pipe_peak(self, which: int) -> float:
         out = C.c_double()
         check(self.h, self.lib.hdp_measure_pipe_peak(self.h, which, C.byref(out)))
+        return out.value
+
+    def last_device_ms(self) -> float:
+        out = C.c_double()
+        check(self.h, self.lib.hdp_last_device_ms(self.h, C.byref(out)))
         return out.value
 
     def tape_fill(self, dtype, stream: int, want_normal: bool, seed: int, ordinal0: int, n_ord: int,

@@ -93,6 +93,8 @@ extern "C" int hdp_create(hdp_handle* out, int device)
         delete h;
         return set_err(nullptr, HDP_ERR_CUDA, "handle setup failed: %s", m);
     }
+    cudaEventRecord(h->ev0, h->stream);
+    cudaEventRecord(h->ev1, h->stream);
     cudaMemset(h->d_flags, 0, 64 * sizeof(int));
     cudaMemset(h->d_ctr, 0, 64 * sizeof(unsigned long long));
     *out = h;
@@ -126,7 +128,25 @@ extern "C" int hdp_sync(hdp_handle h)
     if (!h) return HDP_ERR_BAD_ARG;
     std::lock_guard<std::mutex> lk(h->mu);
     DeviceGuard g(h->device);
+    int f = 0;
+    HDP_CUDA(h, cudaMemcpyAsync(&f, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     HDP_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (f) {
+        cudaMemsetAsync(h->d_flags, 0, sizeof(int), h->stream);
+        return set_err(h, HDP_ERR_START_OUTSIDE_DOMAIN, "an asynchronous call found a start point outside the hypercube");
+    }
+    return HDP_OK;
+}
+
+extern "C" int hdp_last_device_ms(hdp_handle h, double* ms)
+{
+    if (!h || !ms) return HDP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    HDP_CUDA(h, cudaEventSynchronize(h->ev1));
+    float f = 0;
+    HDP_CUDA(h, cudaEventElapsedTime(&f, h->ev0, h->ev1));
+    *ms = f;
     return HDP_OK;
 }
 

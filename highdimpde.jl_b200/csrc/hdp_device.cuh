@@ -12,7 +12,7 @@
 // only where written explicitly (inside the normal generator).
 #pragma once
 #ifdef HDP_HOST_EMU
-// test-only: compile the device code for the host (tests/hostemu/); never part of the product build
+// test-only hook: lets the tests compile this device code for the host; never defined in the product build
 #include "hdp_host_emu_shim.h"
 #define HDP_NOINLINE __attribute__((noinline))
 #else

@@ -281,8 +281,10 @@ int reflect_impl(hdp_handle h, const T* a, const T* b, T* out, int d, int B, con
     const size_t nv = (n_el + VEC - 1) / VEC;
     const bool al = (n_el % VEC == 0) && aligned16(da) && aligned16(db) && aligned16(dout);
     const int grid = grid_for(h, nv, 256, 16);
+    HDP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     if (al) reflect_kernel<T, true><<<grid, 256, 0, h->stream>>>(da, db, dout, dcnt, n_el, d, bd, h->d_flags);
     else reflect_kernel<T, false><<<grid, 256, 0, h->stream>>>(da, db, dout, dcnt, n_el, d, bd, h->d_flags);
+    HDP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     h->launches++;
     HDP_CUDA(h, cudaGetLastError());
     if ((rc = copy_back(h, out, dout, n_el, mem_flags)) != HDP_OK) return rc;
@@ -314,8 +316,10 @@ int mc_sample_impl(hdp_handle h, T* z, const T* y1, int d, int B, int K, const h
     const size_t nv = (n_el + VEC - 1) / VEC;
     const bool al = (n_el % VEC == 0) && aligned16(dz) && aligned16(dy1) && aligned16(dinj);
     const int grid = grid_for(h, nv, 256, 16);
+    HDP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     if (al) mc_sample_kernel<T, true><<<grid, 256, 0, h->stream>>>(dz, dy1, dinj, n_el, d, K, sm, seed, HDP_STREAM_MC);
     else mc_sample_kernel<T, false><<<grid, 256, 0, h->stream>>>(dz, dy1, dinj, n_el, d, K, sm, seed, HDP_STREAM_MC);
+    HDP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     h->launches++;
     HDP_CUDA(h, cudaGetLastError());
     if ((rc = copy_back(h, z, dz, n_el * (size_t)K, mem_flags)) != HDP_OK) return rc;
@@ -374,11 +378,13 @@ int sde_loop_impl(hdp_handle h, const hdp_problem* prob, T* y0, T* y1, int B, in
     sde_loop_kernel<T, AL, INJ><<<grid, threads, 0, h->stream>>>(pb, dy0, dy1, n_el, nsteps, dt, x0s,    \
                                                                  nullptr, seed, ddw, mcs, dz, K,          \
                                                                  h->d_flags, h->d_ctr + 1)
+    HDP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     if (al && ddw) LAUNCH(true, true);
     else if (al) LAUNCH(true, false);
     else if (ddw) LAUNCH(false, true);
     else LAUNCH(false, false);
 #undef LAUNCH
+    HDP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     h->launches++;
     HDP_CUDA(h, cudaGetLastError());
     if (!(mem_flags & HDP_MEM_DEVICE)) {
@@ -386,6 +392,7 @@ int sde_loop_impl(hdp_handle h, const hdp_problem* prob, T* y0, T* y1, int B, in
         HDP_CUDA(h, cudaMemcpyAsync(y1, dy1, n_el * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
         if (want_z) HDP_CUDA(h, cudaMemcpyAsync(z, dz, n_el * (size_t)K * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
     }
+    if ((mem_flags & HDP_MEM_DEVICE) && (mem_flags & HDP_ASYNC)) return HDP_OK;
     if (prob->has_bc || !(mem_flags & HDP_MEM_DEVICE)) return check_flag(h, "sde_loop!");
     return HDP_OK;
 }

@@ -1,0 +1,77 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), `torch.distributed` only for
+rendezvous-level exchanges (NCCL unique id, result gathering, timing reductions).
+
+How the path shards:
+ * independent solves (different seeds / start points): contiguous shards of the solve
+   index, NO data-path collective — `shard_range`, `gather_solves`;
+ * one large solve: every rank evaluates a slice of the tree's work units and the
+   per-unit partial sums are all-reduced by NCCL inside libhdpde_b200
+   (`attach_nccl` → hdp_comm_init_rank; the reference's analogue is the
+   `Threads.@spawn`/`fetch`/`sum` of src/MLP.jl:235-259).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous, balanced [lo, hi) of n items for `rank` of `world`."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    return lo, hi
+
+
+def local_seed(seed: int, rank: int, world: int, n: int) -> int:
+    """Solve i always uses seed+i, whatever the number of ranks."""
+    return seed + shard_range(n, rank, world)[0]
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def all_gather_object(obj):
+    dist = _dist()
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, obj)
+    return out
+
+
+def broadcast_bytes(data: bytes | None, n: int, src: int = 0) -> bytes:
+    import torch
+    dist = _dist()
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.zeros(n, dtype=torch.uint8, device=dev)
+    if dist.get_rank() == src:
+        t.copy_(torch.tensor(list(data), dtype=torch.uint8))
+    dist.broadcast(t, src)
+    return bytes(t.cpu().tolist())
+
+
+def gather_solves(local: np.ndarray, n: int) -> np.ndarray:
+    """All ranks' per-solve results, concatenated in solve order."""
+    parts = all_gather_object(np.asarray(local))
+    full = np.concatenate(parts) if parts else np.zeros(0)
+    assert full.shape[0] == n
+    return full
+
+
+def max_over_ranks(x: float) -> float:
+    import torch
+    dist = _dist()
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def attach_nccl(handle):
+    """Join this rank's handle to an NCCL communicator over all ranks."""
+    dist = _dist()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    uid = handle.nccl_unique_id() if rank == 0 else None
+    uid = broadcast_bytes(uid, 128)
+    handle.comm_init_rank(uid, world, rank)
+    return rank, world

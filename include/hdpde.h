@@ -59,7 +59,10 @@ enum {
 /* ------------------------------------------------------------------ */
 enum {
     HDP_MEM_HOST = 0,   /* plain host pointers (Julia Array)            */
-    HDP_MEM_DEVICE = 1  /* device pointers (Julia CuArray / CuPtr)      */
+    HDP_MEM_DEVICE = 1, /* device pointers (Julia CuArray / CuPtr)      */
+    HDP_ASYNC = 2       /* with HDP_MEM_DEVICE: enqueue only, do not wait;
+                           a start-outside-domain error is then reported by the
+                           next hdp_sync (overlap with Flux)     */
 };
 
 /* ------------------------------------------------------------------ */
@@ -326,6 +329,9 @@ int hdp_tape_fill_f32(hdp_handle h, float* out, int stream, int want_normal, int
 /* Saturating DFMA (which=64) / FFMA (which=32) microbenchmark: returns the
  * measured vector-pipe peak in lane-instructions per second.           */
 int hdp_measure_pipe_peak(hdp_handle h, int which, double* lane_instr_per_s);
+/* CUDA-event time (ms) of the kernels launched by the last entry-point call on this
+ * handle (K1/K2/K3/K4); synchronises the handle's stream. */
+int hdp_last_device_ms(hdp_handle h, double* ms);
 
 #ifdef __cplusplus
 }

@@ -359,3 +359,61 @@ void hdp_oracle_mlp_counts(int M, int L, int K, int nonlocal, int64_t out[5])
 #include "hdp_oracle_impl.h"
 #undef REAL
 #undef SUFFIX
+
+/* ================================================================ */
+/* CPU baseline helper (bench.py `cpu_baseline` / `--impl reference`):  */
+/* n_solves independent serial `_ml_picard` solves spread over          */
+/* `nthreads` host threads, each with its own xoshiro256++ stream.      */
+/* This uses every host core (the reference's own threaded variant,     */
+/* `_ml_picard_mlt`, is capped by its 4 heavy top-level samples).       */
+/* ================================================================ */
+#include <time.h>
+typedef struct bench_job {
+    const hdp_problem* pb;
+    const hdp_sampler* sm;
+    int M, L, K, n_solves, nthreads, tid;
+    const double* x;
+    uint64_t seed;
+    double* u_out;
+    int rc;
+} bench_job;
+
+static void* bench_main(void* arg)
+{
+    bench_job* j = (bench_job*)arg;
+    for (int i = j->tid; i < j->n_solves; i += j->nthreads) {
+        hdp_oracle_rng* g = hdp_oracle_rng_xoshiro(j->seed + (uint64_t)i, 0,
+                                                   j->sm && j->sm->kind == HDP_SAMPLER_NORMAL);
+        double u = 0;
+        int rc = hdp_oracle_ml_picard_f64(j->pb, j->sm, j->M, j->L, j->K, j->x, g, &u, NULL);
+        if (rc) j->rc = rc;
+        j->u_out[i] = u;
+        hdp_oracle_rng_free(g);
+    }
+    return NULL;
+}
+
+int hdp_oracle_bench_solves_f64(const hdp_problem* pb, const hdp_sampler* sm, int M, int L, int K,
+                                const double* x, int n_solves, int nthreads, uint64_t seed,
+                                double* u_out, double* seconds)
+{
+    if (nthreads < 1) nthreads = 1;
+    bench_job* jobs = (bench_job*)calloc((size_t)nthreads, sizeof(bench_job));
+    pthread_t* th = (pthread_t*)calloc((size_t)nthreads, sizeof(pthread_t));
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int t = 0; t < nthreads; ++t) {
+        jobs[t] = (bench_job){pb, sm, M, L, K, n_solves, nthreads, t, x, seed, u_out, 0};
+        pthread_create(&th[t], NULL, bench_main, &jobs[t]);
+    }
+    int rc = 0;
+    for (int t = 0; t < nthreads; ++t) {
+        pthread_join(th[t], NULL);
+        if (jobs[t].rc) rc = jobs[t].rc;
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    *seconds = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+    free(jobs);
+    free(th);
+    return rc;
+}

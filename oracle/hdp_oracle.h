@@ -57,6 +57,10 @@ void hdp_oracle_mlp_counts(int M, int L, int K, int nonlocal, int64_t out[5]);
 HDP_ORACLE_DECL(double, _f64)
 HDP_ORACLE_DECL(float, _f32)
 
+int hdp_oracle_bench_solves_f64(const hdp_problem* pb, const hdp_sampler* sm, int M, int L, int K,
+                                const double* x, int n_solves, int nthreads, uint64_t seed,
+                                double* u_out, double* seconds);
+
 #ifdef __cplusplus
 }
 #endif

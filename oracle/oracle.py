@@ -64,6 +64,7 @@ def lib():
             getattr(L, "hdp_oracle_ml_picard" + sfx).argtypes = [vp, vp, i, i, i, vp, vp, vp, i64p]
             getattr(L, "hdp_oracle_ml_picard_mlt" + sfx).argtypes = [vp, vp, i, i, i, vp, i, C.POINTER(vp), i, vp, i64p]
             getattr(L, "hdp_oracle_sde_loop" + sfx).argtypes = [vp, vp, vp, i, i, real, vp, vp, vp, vp, vp]
+        L.hdp_oracle_bench_solves_f64.argtypes = [vp, vp, i, i, i, vp, i, i, u64, vp, C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
@@ -259,3 +260,16 @@ def sde_loop(pb_struct, y1, nsteps, dt, dWall, x0_sampler_struct=None, x0_raw=No
     if rc != 0:
         raise ValueError(f"oracle sde_loop rc={rc}")
     return y0, y1, its
+
+
+def bench_solves(pb_struct, sampler_struct, M, L, K, x, n_solves, nthreads, seed=0):
+    """n_solves independent serial `_ml_picard` solves on nthreads host threads.
+    Returns (u[n_solves], seconds)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    u = np.zeros(n_solves, dtype=np.float64)
+    sec = C.c_double(0)
+    rc = lib().hdp_oracle_bench_solves_f64(C.byref(pb_struct), C.byref(sampler_struct), M, L, K, _p(x), n_solves,
+                                           nthreads, seed, _p(u), C.byref(sec))
+    if rc != 0:
+        raise ValueError(f"oracle bench_solves rc={rc}")
+    return u, sec.value

@@ -1,0 +1,90 @@
+"""GPU, independent RNG: u(T,x0) agrees with the oracle within the Monte-Carlo confidence
+interval (north_star's second correctness criterion), with the reference's closed forms,
+and — at BASELINE.json's full sizes — through size-independent properties."""
+import math
+
+import numpy as np
+import pytest
+
+from helpers import zoo
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_many(H, O, prob, alg, dt, seeds):
+    pb, keep = prob.to_c()
+    sm, k2 = alg.mc_sample._descriptor(prob.d)
+    normal = isinstance(alg.mc_sample, H.NormalSampling)
+    return np.array([O.ml_picard(pb, sm, alg.M, alg.L, alg.K, np.asarray(prob.x, dtype=dt),
+                                 O.Rng.xoshiro(s, dt, normal))[0] for s in seeds])
+
+
+@pytest.mark.parametrize("name", ["heat_d10", "allen_cahn_neumann_d5", "black_scholes_d20", "nonlocal_ac_neumann_d5",
+                                  "replicator_d2", "allen_cahn_d10"])
+def test_agrees_with_oracle_within_mc_interval(H, O, handle, name):
+    prob, alg, dt = zoo(H)[name]
+    n_gpu, n_cpu = 512, 48
+    ug, st = H._ml_picard_batch(prob, alg, n_solves=n_gpu, seed=1000, handle=handle, dtype=dt)
+    uc = _oracle_many(H, O, prob, alg, dt, range(n_cpu))
+    se = math.sqrt(ug.var(ddof=1) / n_gpu + uc.var(ddof=1) / n_cpu)
+    assert abs(ug.mean() - uc.mean()) <= 4.5 * se + 1e-14, (name, ug.mean(), uc.mean(), se)
+    # and the spread of single solves is the same distribution (F-test-ish, loose)
+    if uc.std() > 0:
+        assert 0.6 < ug.std(ddof=1) / uc.std(ddof=1) < 1.6
+
+
+def test_closed_forms_full_size(H, handle):
+    """BASELINE C1 (heat d=10, L=4): exact 0.05 at x0=0 and 40.05 at x0=2 (test/MLP.jl:27)."""
+    n = 4096
+    prob = H.ParabolicPDEProblem(0.0, 0.1, np.zeros(10), (0.0, 0.5), g=H.SumSq(), f=H.FZero())
+    u, st = H._ml_picard_batch(prob, H.MLP(), n_solves=n, seed=5, handle=handle)
+    assert abs(u.mean() - 0.05) <= 4.5 * u.std(ddof=1) / math.sqrt(n)
+    x0 = np.full(10, 2.0)
+    u, st = H._ml_picard_batch(prob, H.MLP(), n_solves=n, x0=x0, seed=6, handle=handle)
+    assert abs(u.mean() - 40.05) <= 4.5 * u.std(ddof=1) / math.sqrt(n)
+    # exponential growth g*exp(rT) (test/MLP.jl:117): a biased-at-finite-L estimator, 1e-3 is its level
+    prob = H.ParabolicPDEProblem(0.0, 0.0, np.zeros(3), (0.0, 0.5), g=H.SumSq(2.0), f=H.FLinear(0.1))
+    u, st = H._ml_picard_batch(prob, H.MLP(), n_solves=256, seed=7, handle=handle)
+    assert abs(u.mean() - 2.0 * math.exp(0.05)) < 2e-3
+
+
+def test_full_size_properties_c2(H, handle):
+    """BASELINE C2 (Allen–Cahn d=100, Neumann ±1/2, L=4, fp64) at full size:
+    - determinism: same seed -> same bits, whatever the tree cut and batch composition;
+    - the batch is a set of independent solves: solve i of a batch == a batch of one with seed+i;
+    - the value sits at the survey's sanity level 0.2037 ± 0.0042 (App. C)."""
+    d = 100
+    prob = H.ParabolicPDEProblem(0.0, 1.0, np.zeros(d), (0.0, 0.5), g=H.ExpSumSq(0.25), f=H.FAllenCahn(1.0),
+                                 neumann_bc=(np.full(d, -0.5), np.full(d, 0.5)))
+    alg = H.MLP(M=4, L=4, K=10)
+    u1, st1 = H._ml_picard_batch(prob, alg, n_solves=256, seed=77, handle=handle)
+    u2, st2 = H._ml_picard_batch(prob, alg, n_solves=256, seed=77, handle=handle)
+    assert np.array_equal(u1, u2) and st1["bounces"] == st2["bounces"]
+    u3, st3 = H._ml_picard_batch(prob, alg, n_solves=1, seed=77 + 5, handle=handle)          # deep cut
+    u4, st4 = H._ml_picard_batch(prob, alg, n_solves=1, seed=77 + 5, target_units=1, handle=handle)  # no cut
+    assert st3["n_units"] > st4["n_units"] == 1
+    assert abs(u3[0] - u1[5]) <= 1e-12 * abs(u1[5]) and abs(u4[0] - u1[5]) <= 1e-12 * abs(u1[5])
+    assert st1["path_steps"] == 4916
+    assert abs(u1.mean() - 0.2037) < 0.01
+    # roughly 45 wall hits per reflected step at this sigma*sqrt(dt) (41-54)
+    per_step = st1["bounces"] / (256 * 4916)
+    assert 20 < per_step < 70
+
+
+def test_full_size_c4_nonlocal_fisher_smaller_levels(H, O, handle):
+    """BASELINE C4 shape (non-local Fisher–KPP d=10, UniformSampling) at L=4 (0.93 M path-steps +
+    4.7 M sampler calls per solve): one solve cut into many units equals the uncut solve."""
+    d = 10
+    prob = H.PIDEProblem(0.0, 0.1, np.zeros(d), (0.0, 0.5), H.ExpSumSq(1.0), H.FNLFisher(),
+                         neumann_bc=(np.full(d, -0.5), np.full(d, 0.5)))
+    alg = H.MLP(M=4, L=4, K=10, mc_sample=H.UniformSampling(np.full(d, -0.5), np.full(d, 0.5)))
+    ua, sa = H._ml_picard_batch(prob, alg, n_solves=1, seed=3, handle=handle)
+    ub, sb = H._ml_picard_batch(prob, alg, n_solves=1, seed=3, target_units=64, handle=handle)
+    assert sa["path_steps"] == 928116 and sa["sampler_calls"] == 4688520
+    assert sa["n_units"] > sb["n_units"]
+    assert abs(ua[0] - ub[0]) <= 1e-12 * abs(ub[0]) and sa["bounces"] == sb["bounces"]
+    # CPU oracle on the same Philox ordinals (libm transcendentals): agreement far inside MC noise
+    pb, keep = prob.to_c()
+    sm, k2 = alg.mc_sample._descriptor(d)
+    uo, info = O.ml_picard(pb, sm, alg.M, alg.L, alg.K, prob.x, O.Rng.philox(3, np.float64, False))
+    assert abs(ua[0] - uo) <= 1e-9 * abs(uo)

@@ -1,0 +1,104 @@
+"""CPU-only check of the PRODUCT's MLP device code and tree planner: k_mlp.cuh and
+mlp_plan.cu are compiled for the host (tests/hostemu, single-lane group) and compared
+with the oracle on identical injected tapes.  This validates, without a GPU, the
+consumption-ordinal arithmetic ("bit-exact indexing"), the tree cut at any threshold,
+the bottom-up combine, the kinds, and the per-coordinate reflection."""
+import numpy as np
+import pytest
+
+from helpers import emu_solve, oracle_solve, random_tapes, rel_err, zoo
+
+TOL = {np.float64: 1e-12, np.float32: 1e-5}
+
+
+def _names():
+    import hdpde_b200 as H
+    return list(zoo(H).keys())
+
+
+@pytest.mark.parametrize("name", _names())
+def test_emulated_device_code_matches_oracle(H, O, emu, name):
+    prob, alg, dt = zoo(H)[name]
+    tapes = random_tapes(H, prob, alg, dt, seed=11)
+    uo, info = oracle_solve(H, O, prob, alg, dt, tapes)
+    assert info["rc"] == 0 and not info["tape_pos"]["overrun"]
+    # the oracle consumed exactly the closed-form counts
+    assert info["tape_pos"]["r"] == tapes[0].size and info["tape_pos"]["n"] == tapes[1].size
+    seen_units = set()
+    for target in (0, 8, 64, 1000, 100000):
+        u, rc, st = emu_solve(H, emu, prob, alg, dt, tapes=tapes, target_units=target)
+        assert rc == 0
+        assert rel_err(float(u[0]), uo) <= TOL[dt], (name, target, u[0], uo)
+        # reflection decisions are exact: identical number of wall hits
+        assert st.bounces == info["bounces"], (name, target)
+        seen_units.add(int(st.n_units))
+        if target == 0:
+            assert st.n_units == 1 and float(u[0]) == uo  # no cut, same summation order: bit-equal
+    assert len(seen_units) >= 3  # the thresholds really produced different cuts
+
+
+def test_cut_plans_cover_the_tree(H, emu):
+    """Every plan consumes exactly the closed-form number of ordinals (no gaps, no overlap):
+    with a tape of the exact length any mis-indexing would read zeros or overrun."""
+    import ctypes as C
+    out = (C.c_int64 * 8)()
+    for (M, L, K, nl) in ((4, 4, 10, 0), (4, 5, 10, 0), (3, 4, 3, 1), (2, 6, 2, 1)):
+        c = H.mlp_counts(M, L, K, bool(nl))
+        for thresh in (1.0, 24.0, 100.0, 1e4, 1e9):
+            emu.hdp_emu_plan_summary(M, L, K, nl, C.c_double(thresh), 0, out)
+            assert out[5] == c["path_steps"] and out[6] == c["time_uniforms"] and out[7] == c["sampler_calls"]
+            assert out[0] >= 1 and out[2] >= 1
+
+
+@pytest.mark.parametrize("nt", [1, 3, 8])
+def test_compat_mlt_partition(H, O, emu, nt):
+    """`_ml_picard_mlt` + `_get_loop_num` (src/MLP.jl:218-404, quirk Q4) reproduced behind
+    compat_mlt_threads, on one shared tape consumed task by task."""
+    prob, alg, dt = zoo(H)["allen_cahn_neumann_d5"]
+    tapes = random_tapes(H, prob, alg, dt, seed=5, compat=nt)
+    pb, keep = prob.to_c()
+    sm, k2 = alg.mc_sample._descriptor(prob.d)
+    rng = O.Rng.tape(dt, *tapes)
+    uo, info = O.ml_picard_mlt(pb, sm, alg.M, alg.L, alg.K, prob.x, nt, [rng] * (nt + 1), parallel=False)
+    pos = rng.tape_pos()
+    assert info["rc"] == 0 and not pos["overrun"] and pos["r"] == tapes[0].size and pos["n"] == tapes[1].size
+    for target in (0, 64, 5000):
+        u, rc, st = emu_solve(H, emu, prob, alg, dt, tapes=tapes, target_units=target, compat=nt)
+        assert rc == 0 and rel_err(float(u[0]), uo) <= 1e-12
+        assert st.bounces == info["bounces"]
+
+
+def test_philox_mode_matches_oracle_philox(H, O, emu):
+    """RNG mode is tape mode with the tape generated on the fly: the emulated generator and
+    the oracle's Philox-by-ordinal stream address the same draws."""
+    prob, alg, dt = zoo(H)["nonlocal_ac_neumann_d5"]
+    pb, keep = prob.to_c()
+    sm, k2 = alg.mc_sample._descriptor(prob.d)
+    for seed in (0, 77):
+        uo, info = O.ml_picard(pb, sm, alg.M, alg.L, alg.K, prob.x, O.Rng.philox(seed, dt, False))
+        for target in (0, 1000):
+            u, rc, st = emu_solve(H, emu, prob, alg, dt, seed=seed, target_units=target)
+            assert rc == 0 and rel_err(float(u[0]), uo) <= 1e-11
+
+
+def test_batch_of_solves_uses_consecutive_seeds(H, O, emu):
+    prob, alg, dt = zoo(H)["heat_neumann_d5"]
+    pb, keep = prob.to_c()
+    sm, k2 = alg.mc_sample._descriptor(prob.d)
+    u, rc, st = emu_solve(H, emu, prob, alg, dt, seed=40, n_solves=3, target_units=50)
+    for i in range(3):
+        uo, _ = O.ml_picard(pb, sm, alg.M, alg.L, alg.K, prob.x, O.Rng.philox(40 + i, dt, False))
+        assert rel_err(float(u[i]), uo) <= 1e-11
+
+
+def test_start_outside_domain_is_reported(H, O, emu):
+    """Q5: NormalSampling + neumann_bc can leave the box; the reference errors in `_reflect`."""
+    d = 3
+    prob = H.PIDEProblem(0.0, 0.1, np.zeros(d), (0.0, 0.5), H.ExpSumSq(1.0), H.FNLFisher(),
+                         neumann_bc=(np.full(d, -0.5), np.full(d, 0.5)))
+    alg = H.MLP(M=2, L=3, K=2, mc_sample=H.NormalSampling(5.0))
+    tapes = random_tapes(H, prob, alg, np.float64, seed=2)
+    uo, info = oracle_solve(H, O, prob, alg, np.float64, tapes)
+    assert info["rc"] == H.capi.HDP_ERR_START_OUTSIDE_DOMAIN
+    u, rc, st = emu_solve(H, emu, prob, alg, np.float64, tapes=tapes)
+    assert rc == H.capi.HDP_ERR_START_OUTSIDE_DOMAIN

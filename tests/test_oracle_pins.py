@@ -1,0 +1,272 @@
+"""Pins the CPU oracle (oracle/hdp_oracle.c) against every closed-form answer and
+predicate the reference's own tests hold for the path:
+test/MLP.jl, test/reflect.jl, test/MCSample.jl.  CPU only."""
+import math
+
+import numpy as np
+import pytest
+
+from helpers import zoo
+
+
+def rel_error_l2(u, uanal):  # test/MLP.jl:10-16
+    return math.sqrt((u - uanal) ** 2 / u ** 2) if abs(uanal) >= 10 * np.finfo(float).eps else abs(u - uanal)
+
+
+def _solve(H, O, prob, alg, seed, dtype=np.float64, fast=True):
+    pb, keep = prob.to_c()
+    sm, k2 = alg.mc_sample._descriptor(prob.d)
+    normal = isinstance(alg.mc_sample, H.NormalSampling)
+    rng = (O.Rng.xoshiro if fast else O.Rng.philox)(seed, dtype, normal)
+    u, info = O.ml_picard(pb, sm, alg.M, alg.L, alg.K, np.asarray(prob.x, dtype=dtype), rng)
+    assert info["rc"] == 0
+    return u, info
+
+
+def test_philox_known_answers(O):
+    # Random123 kat_vectors: philox4x32_10
+    kat = [([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+           ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+           ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+            [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1])]
+    for ctr, key, want in kat:
+        assert [int(v) for v in O.philox4x32_10(ctr, key)] == want
+
+
+@pytest.mark.parametrize("kind", ["xoshiro", "philox"])
+def test_generators_are_standard(O, kind):
+    rng = getattr(O.Rng, kind)(7)
+    z = rng.fill(1, 200000)
+    u = np.array([rng.fill(0, 1)[0] for _ in range(20000)])
+    assert abs(z.mean()) < 0.01 and abs(z.var() - 1) < 0.02
+    assert abs(np.mean(z ** 4) - 3) < 0.1
+    assert 0 <= u.min() and u.max() < 1 and abs(u.mean() - 0.5) < 0.01
+
+
+@pytest.mark.parametrize("M,L,K,nl,want", [
+    (4, 4, 10, False, (4916, 26480, 2304)),
+    (4, 5, 10, False, (41652, 224400, 19520)),
+    (4, 4, 10, True, (928116, None, None)),
+    (4, 5, 10, True, (45384692, 229363600, 22457920)),
+    (8, 5, 10, False, (1184968, None, None)),
+])
+def test_work_counts(O, H, M, L, K, nl, want):
+    c = O.mlp_counts(M, L, K, nl)
+    assert c["path_steps"] == want[0]
+    if want[1] is not None:
+        assert c["f_evals"] == want[1] and c["g_evals"] == want[2]
+    # the product's planner tables agree with the oracle's recurrences
+    assert H.mlp_counts(M, L, K, nl) == c
+
+
+def test_counts_match_actual_consumption(O, H):
+    for name, (prob, alg, dt) in zoo(H).items():
+        u, info = _solve(H, O, prob, alg, 3, dt)
+        c = O.mlp_counts(alg.M, alg.L, alg.K, H._integrate(alg.mc_sample))
+        for k in ("path_steps", "time_uniforms", "sampler_calls", "f_evals", "g_evals"):
+            assert info[k] == c[k], (name, k)
+
+
+def test_get_loop_num_quirk(O):
+    # M=4, L=4, NT=8 runs 260/256, 68/64, 20/16, 4/4 samples for l=0..3
+    tot = [sum(O.get_loop_num(4, 4 ** (4 - l), t, 8) for t in range(1, 9)) for l in range(4)]
+    assert tot == [260, 68, 20, 4]
+    tot1 = [O.get_loop_num(4, 4 ** (4 - l), 1, 1) for l in range(4)]
+    assert tot1 == [257, 65, 17, 4]
+    assert sum(O.get_loop_num(4, 16, t, 3) for t in range(1, 4)) == 18
+
+
+# ---- closed-form pins of test/MLP.jl --------------------------------------------
+@pytest.mark.parametrize("d", [1, 10, 50])
+def test_heat_equation(O, H, d):  # test/MLP.jl:19-47
+    prob = H.ParabolicPDEProblem(0.0, 0.1, np.full(d, 2.0), (0.0, 0.5), g=H.SumSq(), f=H.FZero())
+    u, _ = _solve(H, O, prob, H.MLP(), 100)
+    assert rel_error_l2(u, 4.0 * d + d * 0.1 ** 2 * 0.5) < 0.1
+    # averaged over seeds the estimator is unbiased: much tighter than the reference's 10 %
+    us = [_solve(H, O, prob, H.MLP(), s)[0] for s in range(32)]
+    assert abs(np.mean(us) - (4.0 * d + d * 0.005)) < 4 * np.std(us) / math.sqrt(32) + 1e-12
+
+
+def test_heat_equation_x0_zero(O, H):  # BASELINE config C1
+    prob = H.ParabolicPDEProblem(0.0, 0.1, np.zeros(10), (0.0, 0.5), g=H.SumSq(), f=H.FZero())
+    us = [_solve(H, O, prob, H.MLP(), s)[0] for s in range(64)]
+    assert abs(np.mean(us) - 0.05) < 4 * np.std(us) / 8
+
+
+@pytest.mark.parametrize("d", [1, 3, 10])
+def test_exponential(O, H, d):  # test/MLP.jl:107-134
+    prob = H.ParabolicPDEProblem(0.0, 0.0, np.zeros(d), (0.0, 0.5), g=H.SumSq(2.0), f=H.FLinear(0.1))
+    u, _ = _solve(H, O, prob, H.MLP(), 100)
+    assert rel_error_l2(u, 2.0 * math.exp(0.1 * 0.5)) < 0.1
+    assert abs(u - 2.10254) < 0.01  # 2.1027 ± 0.0005
+
+
+def test_allen_cahn_literature(O, H):  # test/MLP.jl:136-160 (tolerance 0.5 in the reference)
+    prob = zoo(H)["allen_cahn_d10"][0]
+    us = [_solve(H, O, prob, H.MLP(), s)[0] for s in range(8)]
+    assert rel_error_l2(float(np.mean(us)), 0.30879) < 0.5
+    assert abs(np.mean(us) - 0.241) < 0.02  # SURVEY.md App. C restatement value
+
+
+@pytest.mark.parametrize("d", [1, 2, 5])
+def test_allen_cahn_neumann_not_nan(O, H, d):  # test/MLP.jl:162-186
+    prob = H.ParabolicPDEProblem(0.0, 1.0, np.zeros(d), (0.0, 0.5), g=H.ExpSumSq(0.25), f=H.FAllenCahn(1.0),
+                                 neumann_bc=(np.full(d, -0.5), np.full(d, 0.5)))
+    u, info = _solve(H, O, prob, H.MLP(), 100)
+    assert not math.isnan(u) and info["bounces"] > 0
+
+
+@pytest.mark.parametrize("d", [1, 2, 5])
+def test_heat_neumann_two_runs_agree(O, H, d):  # test/MLP.jl:80-105
+    prob = H.ParabolicPDEProblem(0.0, 0.1, np.full(d, 0.3), (0.0, 0.5), g=H.SumSq(), f=H.FZero(),
+                                 neumann_bc=(np.full(d, -0.5), np.full(d, 0.5)))
+    u1, _ = _solve(H, O, prob, H.MLP(), 1)
+    u2, _ = _solve(H, O, prob, H.MLP(), 2)
+    assert rel_error_l2(u1, u2) < 0.1
+
+
+def test_black_scholes_default_risk(O, H):  # test/MLP.jl:188-230
+    prob, alg, _ = zoo(H)["black_scholes_d20"]
+    u, _ = _solve(H, O, prob, alg, 100)
+    assert rel_error_l2(u, 60.781) < 0.1
+
+
+@pytest.mark.parametrize("d", [1, 2])
+def test_replicator_mutator(O, H, d):  # test/MLP.jl:236-286
+    ss0, sig, t = 1e-2, 0.1, 0.5
+    MM = sig
+    SSt = MM * ((MM * math.sinh(MM * t) + ss0 * math.cosh(MM * t)) / (MM * math.cosh(MM * t) + ss0 * math.sinh(MM * t)))
+    uanal = (2 * math.pi) ** (-d / 2) * SSt ** (-d / 2)
+    prob = H.PIDEProblem(0.0, sig, np.zeros(d), (0.0, t), H.GaussDensity(ss0), H.FNLReplicatorMutator(1.0))
+    alg = H.MLP(M=4, K=10, L=3 if d > 1 else 4, mc_sample=H.NormalSampling(1.0))
+    us = [_solve(H, O, prob, alg, s)[0] for s in range(3)]
+    assert rel_error_l2(float(np.mean(us)), uanal) < 0.2
+
+
+def test_nonlocal_allen_cahn_neumann_two_runs(O, H):  # test/MLP.jl:288-317
+    d = 2
+    bc = (np.full(d, -0.5), np.full(d, 0.5))
+    prob = H.PIDEProblem(0.0, 0.1, np.zeros(d), (0.0, 0.5), H.ExpSumSq(0.25), H.FNLAllenCahnDiff(), neumann_bc=bc)
+    alg = H.MLP(M=4, K=10, L=3, mc_sample=H.UniformSampling(*bc))
+    u1, _ = _solve(H, O, prob, alg, 1)
+    u2, _ = _solve(H, O, prob, alg, 2)
+    assert rel_error_l2(u1, u2) < 0.1
+
+
+def test_threaded_variant_matches_serial_statistically(O, H):
+    """`_ml_picard_mlt` (src/MLP.jl:218-260): f = 0 makes the `_get_loop_num` bias vanish."""
+    prob = H.ParabolicPDEProblem(0.0, 0.1, np.full(10, 2.0), (0.0, 0.5), g=H.SumSq(), f=H.FZero())
+    pb, keep = prob.to_c()
+    sm, k2 = H.NoSampling()._descriptor(10)
+    for nt, par in ((1, False), (8, False), (8, True)):
+        rngs = [O.Rng.xoshiro(1000 + i) for i in range(nt + 1)]
+        u, info = O.ml_picard_mlt(pb, sm, 4, 4, 10, prob.x, nt, rngs, parallel=par)
+        assert info["rc"] == 0 and abs(u - 40.05) / 40.05 < 0.1
+    # and with f != 0 the threaded estimator is the biased one (Q4): 260/256 samples at l=0
+    c1 = H.mlp_counts(4, 4, 10, False, 8)
+    assert c1["path_steps"] == 5264 and c1["time_uniforms"] == 2800
+
+
+# ---- test/reflect.jl ------------------------------------------------------------
+def test_reflect_vector_inside_and_no_nan(O):  # test/reflect.jl:8-30
+    rng = np.random.default_rng(0)
+    d = 10
+    X0 = np.zeros(d)
+    X1 = X0 + rng.standard_normal(d)
+    X11 = O.reflect_vector(X0, X1, np.full(d, -1.0), np.full(d, 1.0))
+    assert np.all((X11 < 1) & (X11 > -1))
+    y1 = X0.copy()
+    dW = rng.standard_normal((d, 1000)).astype(np.float32)
+    for i in range(1000):
+        y0 = y1.copy()
+        y1 = y0 + dW[:, i]
+        y1 = O.reflect_vector(y0, y1, np.full(d, -1.0), np.full(d, 1.0))
+    assert not np.any(np.isnan(y1))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_reflect_array_equals_vector(O, dtype):  # test/reflect.jl:36-53
+    rng = np.random.default_rng(1)
+    d, B = 10, 200
+    a = np.zeros((d, B), dtype=dtype, order="F")
+    b = np.asfortranarray((a + 2 * rng.standard_normal((d, B))).astype(dtype))
+    out, cnt, col, it = O.reflect_array(a, b, dtype(-1.0), dtype(1.0), return_info=True)
+    assert np.all((out < 1) & (out > -1))
+    tol = 1e-12 if dtype == np.float64 else 2e-6
+    for j in range(0, B, 7):
+        v, cv = O.reflect_vector(a[:, j].copy(), b[:, j].copy(), dtype(-1.0), dtype(1.0), return_bounces=True)
+        assert np.max(np.abs(v - out[:, j])) <= tol
+        assert np.array_equal(cv, cnt[:, j])  # same wall hits per coordinate (no exact ties in random data)
+    assert it == col.max()
+
+
+def test_reflect_array_chain_no_nan(O):  # test/reflect.jl:55-69
+    rng = np.random.default_rng(2)
+    d, B = 10, 500
+    y1 = np.zeros((d, B), dtype=np.float32, order="F")
+    for i in range(30):
+        y0 = y1.copy(order="F")
+        y1 = np.asfortranarray(y0 + rng.standard_normal((d, B)).astype(np.float32))
+        y1 = O.reflect_array(y0, y1, np.float32(-1.0), np.float32(1.0))
+    assert not np.any(np.isnan(y1)) and np.all(np.abs(y1) <= 1)
+
+
+def test_reflect_start_outside_errors(O):  # src/reflect.jl:12, :59
+    with pytest.raises(ValueError):
+        O.reflect_vector(np.array([2.0, 0.0]), np.array([0.0, 0.0]), -1.0, 1.0)
+    with pytest.raises(ValueError):
+        O.reflect_array(np.array([[2.0], [0.0]]), np.array([[0.0], [0.0]]), -1.0, 1.0)
+
+
+def test_reflect_matches_per_coordinate_mirror(O):
+    """The survey's claim (App. C): in an axis-aligned box the sequential billiard equals the
+    per-coordinate iterated mirror b <- b - 2(b - wall)."""
+    rng = np.random.default_rng(3)
+    for d, sc in ((10, 0.071), (100, 0.5), (100, 0.707), (300, 0.5)):
+        a = rng.uniform(-0.5, 0.5, d)
+        b = a + sc * rng.standard_normal(d)
+        out, cnt = O.reflect_vector(a, b, -0.5, 0.5, return_bounces=True)
+        m = b.copy()
+        n = np.zeros(d, dtype=int)
+        for i in range(d):
+            while m[i] < -0.5 or m[i] > 0.5:
+                w = -0.5 if m[i] < -0.5 else 0.5
+                m[i] = m[i] - 2 * (m[i] - w)
+                n[i] += 1
+        assert np.array_equal(n, cnt)
+        assert np.max(np.abs(m - out)) <= 1e-15
+
+
+# ---- test/MCSample.jl -----------------------------------------------------------
+def test_samplers_shape_type_range(O, H):  # test/MCSample.jl:25-42
+    rng = np.random.default_rng(4)
+    for dt in (np.float64, np.float32):
+        raw = np.asfortranarray(rng.random((10, 80)).astype(dt))
+        sm, _ = H.UniformSampling(0.0, 1.0)._descriptor(10)
+        z = O.mc_sample(sm, raw)
+        assert z.shape == raw.shape and z.dtype == raw.dtype and np.all((z >= 0) & (z < 1))
+        sm, _ = H.UniformSampling(-1.0, 1.0)._descriptor(10)
+        z = O.mc_sample(sm, raw)
+        assert np.all((z >= -1) & (z < 1)) and np.allclose(z, (raw - 0.5) * 2.0)
+        n = np.asfortranarray(rng.standard_normal((10, 80, 3)).astype(dt))
+        y1 = np.asfortranarray(rng.standard_normal((10, 80)).astype(dt))
+        sm, _ = H.NormalSampling(2.0, False)._descriptor(10)
+        assert np.array_equal(O.mc_sample(sm, n, y1), n * dt(2.0))
+        sm, _ = H.NormalSampling(2.0, True)._descriptor(10)
+        assert np.array_equal(O.mc_sample(sm, n, y1), n * dt(2.0) + y1[:, :, None])
+
+
+def test_sde_loop_oracle_matches_numpy(O, H):
+    """sde_loop! (src/DeepSplitting.jl:153-166) without bc is a plain cumulative sum."""
+    rng = np.random.default_rng(5)
+    d, B, N = 6, 33, 7
+    dW = rng.standard_normal((d, B, N))
+    prob = H.ParabolicPDEProblem(0.5, 2.0, np.zeros(d), (0.0, 1.0), g=H.SumSq(), f=H.FZero())
+    pb, _ = prob.to_c()
+    y0, y1, _ = O.sde_loop(pb, np.zeros((d, B), order="F"), N, 0.1, dW)
+    want = np.zeros((d, B))
+    prev = want
+    for i in range(N):
+        prev = want
+        want = (prev + 0.5 * 0.1) + (2.0 * math.sqrt(0.1)) * dW[:, :, i]
+    assert np.array_equal(y1, want) and np.array_equal(y0, prev)
