@@ -1,5 +1,5 @@
 """Small fixed workloads for ncu captures (see profiles/README.md).
-usage: python tools/prof_workload.py mlp [n_solves] | sde [B] | c4 | c5"""
+usage: python profiles/prof_workload.py mlp [n_solves] | sde [B] | c4 | c5"""
 import ctypes as C
 import os
 import sys
