@@ -14,7 +14,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhdpde_b200.so")
+LIB_PATH = os.environ.get("HDPDE_B200_LIB") or os.path.join(_HERE, "libhdpde_b200.so")
 
 # ---- status codes (include/hdpde.h) ----
 HDP_OK = 0

@@ -76,6 +76,7 @@ __device__ __forceinline__ float sqrt_rn(float a) { return __fsqrt_rn(a); }
 // Philox4x32-10.  ctr = (ordinal_lo, ordinal_hi, group, stream),
 // key = (seed_lo, seed_hi).  Addressing by consumption ordinal — never by
 // thread id — makes every draw independent of launch geometry and GPU count.
+// One 32x32->64 multiply (IMAD.WIDE.U32) yields both halves of a round product.
 // ---------------------------------------------------------------------
 struct Philox4 { uint32_t w[4]; };
 
@@ -84,11 +85,11 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
 {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        uint32_t n0 = hi1 ^ c1 ^ k0;
-        uint32_t n2 = hi0 ^ c3 ^ k1;
-        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        const u64 p0 = (u64)0xD2511F53u * (u64)c0;
+        const u64 p1 = (u64)0xCD9E8D57u * (u64)c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
         k0 += 0x9E3779B9u;
         k1 += 0xBB67AE85u;
     }
@@ -97,57 +98,178 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
     return o;
 }
 
-__device__ __forceinline__ double bits53(uint32_t hi, uint32_t lo)
-{ // integer k in [0, 2^53) as a double
-    return (double)(((u64)(hi >> 5) << 26) | (u64)(lo >> 6));
+// ---------------------------------------------------------------------
+// bit-level helpers (host emulation provides the same functions)
+// ---------------------------------------------------------------------
+#ifndef HDP_HOST_EMU
+__device__ __forceinline__ double hilo2d(uint32_t hi, uint32_t lo) { return __hiloint2double((int)hi, (int)lo); }
+__device__ __forceinline__ uint32_t d2hi(double x) { return (uint32_t)__double2hiint(x); }
+__device__ __forceinline__ uint32_t d2lo(double x) { return (uint32_t)__double2loint(x); }
+__device__ __forceinline__ float u2f(uint32_t b) { return __uint_as_float(b); }
+__device__ __forceinline__ double rcp_approx(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+__device__ __forceinline__ double rsqrt_approx(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+__device__ __forceinline__ double xfma(double a, double b, double c) { return fma(a, b, c); }
+__device__ __forceinline__ float xfma(float a, float b, float c) { return fmaf(a, b, c); }
+template <int G> __device__ __forceinline__ bool group_any(unsigned mask, bool p)
+{
+    if constexpr (G == 1) return p;
+    return __any_sync(mask, p) != 0;
+}
+#endif
+
+// ---------------------------------------------------------------------
+// Uniform and normal draws.
+// f64: 52-bit uniforms.  Words (w_hi, w_lo) -> k = (w_hi >> 12) : w_lo in [0, 2^52);
+//      the double with exponent field 0x3ff and mantissa k is 1 + k*2^-52, so
+//      u = that - 1 in [0,1)                       (one exact DADD, no I2F)
+//      u1 = that - (1 - 2^-53) = (k + 1/2)*2^-52 in (0,1)   (Box–Muller radius)
+// Box–Muller: z0 = R cos(T), z1 = R sin(T), R = sqrt(-2 ln u1), T = 2π k2 / 2^52.
+//      -2 ln u1: exponent/mantissa split, ln(m) = 2 atanh((m-1)/(m+1)), MUFU.RCP64H seed
+//      + 2 Newton steps for the quotient, degree-8 series — no special cases since
+//      u1 is a normal number in (0,1).
+//      sqrt: MUFU.RSQ64H seed + 1 Newton step + Heron correction.
+//      sin/cos: octant from the top 3 bits of k2 (exact integer range reduction, odd
+//      octants mirrored in integers), Taylor polynomials on [0, π/4].
+// f32: 23-bit uniforms by the same trick; Box–Muller on the MUFU pipe.
+// ---------------------------------------------------------------------
+#ifndef HDP_HOST_EMU
+#define HDP_CONST __constant__
+#else
+#define HDP_CONST static const
+#endif
+// atanh series 1/3 .. 1/19, Taylor sin (-1/3! .. -1/15!) and cos (-1/2! .. 1/16!)
+HDP_CONST double kAtanhC[9] = {1.0 / 3.0, 1.0 / 5.0, 1.0 / 7.0, 1.0 / 9.0, 1.0 / 11.0, 1.0 / 13.0, 1.0 / 15.0,
+                               1.0 / 17.0, 1.0 / 19.0};
+HDP_CONST double kSinC[7] = {-1.6666666666666666667e-01, 8.3333333333333333333e-03, -1.9841269841269841270e-04,
+                             2.7557319223985890653e-06, -2.5052108385441718775e-08, 1.6059043836821614599e-10,
+                             -7.6471637318198164759e-13};
+HDP_CONST double kCosC[8] = {-0.5, 4.1666666666666666667e-02, -1.3888888888888888889e-03, 2.4801587301587301587e-05,
+                             -2.7557319223985890653e-07, 2.0876756987868098979e-09, -1.1470745597729724714e-11,
+                             4.7794773323873852974e-14};
+HDP_CONST double kMisc[6] = {-4.638093627692599e-17, -1.3862943611198906, 4503601774854144.0, 4503599627370496.0,
+                             1.3951473992034527e-15, 0.99999999999999988898};
+
+__device__ __forceinline__ double neg2log_unit(double u)
+{
+    uint32_t hi = d2hi(u);
+    const uint32_t lo = d2lo(u);
+    int e = (int)(hi >> 20) - 1023;                // u = 2^e * 1.f
+    hi = (hi & 0x000fffffu) | 0x3ff00000u;          // m in [1,2)
+    const uint32_t adj = hi >= 0x3ff6a09fu ? 1u : 0u; // m >= ~sqrt(2): halve
+    hi -= adj << 20;
+    e += (int)adj;
+    const double m = hilo2d(hi, lo);                // m in [~0.7071, ~1.4142)
+    const double f = m - 1.0;
+    const double dn = m + 1.0;
+    double r = rcp_approx(dn);
+    double t = xfma(-dn, r, 1.0);
+    r = xfma(r, t, r);
+    t = xfma(-dn, r, 1.0);
+    r = xfma(r, t, r);
+    const double sv = f * r;                        // s = (m-1)/(m+1), |s| <= 0.1716
+    const double s2 = sv * sv;
+    // atanh(s)/s - 1 = s2/3 + s2^2/5 + ... + s2^9/19
+    double pl = kAtanhC[8];
+#pragma unroll
+    for (int i = 7; i >= 0; --i) pl = xfma(pl, s2, kAtanhC[i]);
+    const double lm2 = xfma(sv * s2, pl, sv);       // atanh(s) = ln(m)/2
+    // e as a double without I2F: (2^52 + 2^31 + e) - (2^52 + 2^31)
+    const double ed = hilo2d(0x43300000u, (uint32_t)e ^ 0x80000000u) - kMisc[2];
+    // -2 ln u = -2 e ln2 - 4 atanh(s)
+    double res = xfma(ed, kMisc[0], -4.0 * lm2); // -2 ln2, low part
+    return xfma(ed, kMisc[1], res);              // -2 ln2, high part
 }
 
-// VEC draws (uniform in [0,1) or standard normal) for (stream, ordinal, group).
-// f64: 53-bit uniforms; Box–Muller with fp64 log / sincospi (u1 in (0,1]).
+__device__ __forceinline__ double sqrt_pos(double x)
+{
+    double y = rsqrt_approx(x);
+    const double h = 0.5 * x;
+    double t = y * y;
+    t = xfma(-h, t, 1.5);
+    y = y * t;
+    double sq = x * y;
+    const double er = xfma(-sq, sq, x);
+    return xfma(er, 0.5 * y, sq);
+}
+
+// (cos, sin) of 2π k / 2^52 for the 52-bit integer k = (kh : kl), kh < 2^20
+__device__ __forceinline__ void sincos_turn52(uint32_t kh, uint32_t kl, double& sn, double& cs)
+{
+    const uint32_t q = kh >> 17;                    // octant 0..7
+    u64 f = ((u64)(kh & 0x1ffffu) << 32) | (u64)kl; // 49-bit fraction within the octant
+    if (q & 1u) f = ((u64)1 << 49) - f;             // mirror odd octants (exact)
+    const double t = hilo2d(0x43300000u | (uint32_t)(f >> 32), (uint32_t)f) - kMisc[3]; // f as double
+    const double a = t * kMisc[4];                  // (π/4) * 2^-49, a in [0, π/4]
+    const double a2 = a * a;
+    double ps = kSinC[6];
+#pragma unroll
+    for (int i = 5; i >= 0; --i) ps = xfma(ps, a2, kSinC[i]);
+    const double sa = xfma(a * a2, ps, a);
+    double pc = kCosC[7];
+#pragma unroll
+    for (int i = 6; i >= 0; --i) pc = xfma(pc, a2, kCosC[i]);
+    const double ca = xfma(a2, pc, 1.0);
+    const bool swap = ((q + 1u) & 2u) != 0;          // octants 1,2,5,6
+    double s0 = swap ? ca : sa;
+    double c0 = swap ? sa : ca;
+    // signs: sin < 0 in octants 4..7, cos < 0 in octants 2..5
+    const uint32_t ssign = (q & 4u) << 29;
+    const uint32_t csign = ((q + 2u) & 4u) << 29;
+    sn = hilo2d(d2hi(s0) ^ ssign, d2lo(s0));
+    cs = hilo2d(d2hi(c0) ^ csign, d2lo(c0));
+}
+
 template <typename T>
 __device__ __forceinline__ Vec<T> draw_vec(u64 seed, int stream, u64 ord, uint32_t group, bool normal);
 
 template <>
 __device__ __forceinline__ Vec<double> draw_vec<double>(u64 seed, int stream, u64 ord, uint32_t group, bool normal)
 {
-    Philox4 p = philox4x32_10((uint32_t)ord, (uint32_t)(ord >> 32), group, (uint32_t)stream,
-                              (uint32_t)seed, (uint32_t)(seed >> 32));
+    const Philox4 p = philox4x32_10((uint32_t)ord, (uint32_t)(ord >> 32), group, (uint32_t)stream,
+                                    (uint32_t)seed, (uint32_t)(seed >> 32));
     Vec<double> r;
-    double k1 = bits53(p.w[0], p.w[1]);
-    double k2 = bits53(p.w[2], p.w[3]);
+    const uint32_t h1 = p.w[0] >> 12, h2 = p.w[2] >> 12;
     if (!normal) {
-        r.v[0] = k1 * 0x1.0p-53;
-        r.v[1] = k2 * 0x1.0p-53;
+        r.v[0] = hilo2d(0x3ff00000u | h1, p.w[1]) - 1.0;
+        r.v[1] = hilo2d(0x3ff00000u | h2, p.w[3]) - 1.0;
     } else {
-        double u1 = (k1 + 1.0) * 0x1.0p-53;
-        double u2 = k2 * 0x1.0p-53;
-        double rad = sqrt(-2.0 * log(u1));
-        double s, c;
-        sincospi(2.0 * u2, &s, &c);
-        r.v[0] = rad * c;
-        r.v[1] = rad * s;
+        const double u1 = hilo2d(0x3ff00000u | h1, p.w[1]) - kMisc[5]; // 1 - 2^-53
+        const double rad = sqrt_pos(neg2log_unit(u1));
+        double sn, cs;
+        sincos_turn52(h2, p.w[3], sn, cs);
+        r.v[0] = rad * cs;
+        r.v[1] = rad * sn;
     }
     return r;
 }
 
-// f32: 24-bit uniforms; Box–Muller on the MUFU pipe (lg2 / sin / cos approx).
 template <>
 __device__ __forceinline__ Vec<float> draw_vec<float>(u64 seed, int stream, u64 ord, uint32_t group, bool normal)
 {
-    Philox4 p = philox4x32_10((uint32_t)ord, (uint32_t)(ord >> 32), group, (uint32_t)stream,
-                              (uint32_t)seed, (uint32_t)(seed >> 32));
+    const Philox4 p = philox4x32_10((uint32_t)ord, (uint32_t)(ord >> 32), group, (uint32_t)stream,
+                                    (uint32_t)seed, (uint32_t)(seed >> 32));
     Vec<float> r;
     if (!normal) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) r.v[e] = (float)(p.w[e] >> 8) * 0x1.0p-24f;
+        for (int e = 0; e < 4; ++e) r.v[e] = u2f(0x3f800000u | (p.w[e] >> 9)) - 1.0f;
     } else {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            float u1 = ((float)(p.w[2 * h] >> 8) + 1.0f) * 0x1.0p-24f;
-            float u2 = (float)(p.w[2 * h + 1] >> 8) * 0x1.0p-24f;
+            const float u1 = u2f(0x3f800000u | (p.w[2 * h] >> 9)) - 0.99999994f; // (k + 1/2) 2^-23 in (0,1)
+            const float u2 = u2f(0x3f800000u | (p.w[2 * h + 1] >> 9)) - 1.0f;
             // -2 ln u1 = -2 ln2 * log2(u1)
-            float rad = sqrtf(-1.3862943611198906f * __log2f(u1));
-            float th = 6.283185307179586f * u2;
+            const float rad = sqrtf(-1.3862943611198906f * __log2f(u1));
+            const float th = 6.283185307179586f * u2;
             r.v[2 * h] = rad * __cosf(th);
             r.v[2 * h + 1] = rad * __sinf(th);
         }
@@ -202,31 +324,81 @@ template <typename T> __device__ __forceinline__ T em_ds(T y0, T mu, T sg, T dt,
 // (src/reflect.jl:31-53) decouples per coordinate: coordinate i is mirrored
 // at each of its own wall hits, b_i <- b_i - 2*(b_i - c_i) with c_i the hit
 // point (the wall).  We iterate exactly that mirror; nb counts wall hits.
-// A far excursion (> 64 box widths) is first folded in closed form.
+// A far excursion (> 64 box widths, or a degenerate box) is folded in closed
+// form by a cold out-of-line routine.
 // ---------------------------------------------------------------------
-template <typename T> __device__ __forceinline__ T reflect_coord(T b, T lo, T hi, int& nb)
+template <typename T> __device__ HDP_NOINLINE T reflect_far(T b, T lo, T hi, int* nb)
 {
     const T w = sub_rn(hi, lo);
     if (!(w > (T)0)) return b != b ? b : lo; // degenerate box
-    T y = sub_rn(b, lo);
-    if (fabs(y) > (T)64 * w) {
-        T per = (T)2 * w;
-        T z = fmod(y, per);
-        if (z < (T)0) z += per;
-        T q = y > (T)0 ? ceil(y / w) - (T)1 : floor(-y / w) + (T)1; // wall hits, closed form
-        nb += (int)fmin(q, (T)1.0e9);
-        b = add_rn(lo, z <= w ? z : sub_rn(per, z));
-        if (b < lo) b = lo;
-        if (b > hi) b = hi;
-        return b;
-    }
-    for (int it = 0; it < 256; ++it) {
-        if (b < lo) b = sub_rn(b, mul_rn((T)2, sub_rn(b, lo)));
-        else if (b > hi) b = sub_rn(b, mul_rn((T)2, sub_rn(b, hi)));
-        else break;
-        ++nb;
+    const T y = sub_rn(b, lo);
+    const T per = (T)2 * w;
+    T z = fmod(y, per);
+    if (z < (T)0) z += per;
+    const T q = y > (T)0 ? ceil(y / w) - (T)1 : floor(-y / w) + (T)1; // wall hits, closed form
+    *nb += (int)fmin(q, (T)1.0e9);
+    b = add_rn(lo, z <= w ? z : sub_rn(per, z));
+    if (b < lo) b = lo;
+    if (b > hi) b = hi;
+    return b;
+}
+
+template <typename T> __device__ __forceinline__ T mirror_once(T b, T wall)
+{
+    return sub_rn(b, mul_rn((T)2, sub_rn(b, wall))); // b - 2*(b - c), src/reflect.jl:34 for the hit coordinate
+}
+
+template <typename T> __device__ __forceinline__ T reflect_coord(T b, T lo, T hi, int& nb)
+{
+    bool below = b < lo, above = b > hi;
+    if (below | above) {
+        if (!(fabs(sub_rn(b, lo)) <= (T)64 * sub_rn(hi, lo))) return reflect_far<T>(b, lo, hi, &nb);
+        do {
+            b = mirror_once<T>(b, below ? lo : hi);
+            ++nb;
+            below = b < lo;
+            above = b > hi;
+        } while (below | above);
     }
     return b;
+}
+
+// VEC coordinates of one lane at once, the loop trip count agreed by a vote over the
+// lane group so the whole group stays convergent (branch-light: the body is selects).
+template <typename T, int G>
+__device__ __forceinline__ void reflect_vec(Vec<T>& x, const Vec<T>& lo, const Vec<T>& hi, unsigned gmask, int& nb)
+{
+    constexpr int VEC = Tr<T>::VEC;
+    bool below[VEC], above[VEC];
+    bool any = false, far = false;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+        below[e] = x.v[e] < lo.v[e];
+        above[e] = x.v[e] > hi.v[e];
+        any |= below[e] | above[e];
+    }
+    if (!group_any<G>(gmask, any)) return;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e)
+        far |= (below[e] | above[e]) && !(fabs(sub_rn(x.v[e], lo.v[e])) <= (T)64 * sub_rn(hi.v[e], lo.v[e]));
+    if (group_any<G>(gmask, far)) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) x.v[e] = reflect_coord<T>(x.v[e], lo.v[e], hi.v[e], nb);
+        return;
+    }
+    do {
+        any = false;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const bool o = below[e] | above[e];
+            const T t = mirror_once<T>(x.v[e], below[e] ? lo.v[e] : hi.v[e]);
+            x.v[e] = o ? t : x.v[e];
+            nb += o ? 1 : 0;
+            below[e] = x.v[e] < lo.v[e];
+            above[e] = x.v[e] > hi.v[e];
+            any |= below[e] | above[e];
+        }
+    } while (group_any<G>(gmask, any));
 }
 
 // ---------------------------------------------------------------------

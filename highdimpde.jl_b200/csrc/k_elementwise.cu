@@ -118,8 +118,10 @@ mc_sample_kernel(T* __restrict__ z, const T* __restrict__ y1, const T* __restric
 // ------------------------------ K1 -----------------------------------
 // N reflected EM steps per element; normals from dWall (INJECT) or Philox in
 // registers.  draw addressing: dWall[q + n_el*step] == draw(SDE, ordinal=step, i=q).
+// Bounds, coefficient products and validity flags are resolved into registers before
+// the step loop, so the loop body is: 1 Philox call, VEC x (Box–Muller, 3 flops, mirror).
 template <typename T, bool ALIGNED, bool INJECT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 sde_loop_kernel(DevProblem<T> pb, T* __restrict__ y0, T* __restrict__ y1, size_t n_el, int nsteps, T dt,
                 DevSampler<T> x0s, const T* __restrict__ x0_inject, u64 seed, const T* __restrict__ dW,
                 DevSampler<T> mc, T* __restrict__ z, int K, int* flags, unsigned long long* bounce_ctr)
@@ -128,12 +130,14 @@ sde_loop_kernel(DevProblem<T> pb, T* __restrict__ y0, T* __restrict__ y1, size_t
     const int d = pb.d;
     const size_t nv = (n_el + VEC - 1) / VEC;
     const T sq = sqrt_rn(dt);
-    Bounds<T> bd{pb.bc_is_scalar, pb.lo_s, pb.hi_s, pb.lo, pb.hi};
+    const bool has_bc = pb.has_bc != 0;
+    const bool mu_lin = pb.mu_kind == HDP_COEF_LINEAR, sg_lin = pb.sigma_kind == HDP_COEF_LINEAR;
+    const T mudt_c = mul_rn(pb.mu_c, dt), sgsq_c = mul_rn(pb.sigma_c, sq);
     bool bad = false;
     int nb_total = 0;
     for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (size_t)gridDim.x * blockDim.x) {
         const size_t q0 = v * VEC;
-        const int i0 = (int)(q0 % (size_t)d);
+        const int i0 = n_el <= 0xffffffffull ? (int)((uint32_t)q0 % (uint32_t)d) : (int)(q0 % (size_t)d);
         Vec<T> cur = load_el<T, ALIGNED>(y1, q0, n_el);
         // x0_sample!(y1), 1-argument sampler form (src/DeepSplitting.jl:155)
         if (x0s.kind != HDP_SAMPLER_NONE) {
@@ -147,27 +151,32 @@ sde_loop_kernel(DevProblem<T> pb, T* __restrict__ y0, T* __restrict__ y1, size_t
                 if (++i == d) i = 0;
             }
         }
+        Vec<T> lo, hi;
+        if (has_bc) {
+            int i = i0;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                lo.v[e] = pb.bc_is_scalar ? pb.lo_s : pb.lo[i];
+                hi.v[e] = pb.bc_is_scalar ? pb.hi_s : pb.hi[i];
+                // @assert all((a .>= s) .& (a .<= e))  (src/reflect.jl:59): a = y0 of the first step
+                if (q0 + e < n_el && !(cur.v[e] >= lo.v[e] && cur.v[e] <= hi.v[e])) bad = true;
+                if (++i == d) i = 0;
+            }
+        }
         Vec<T> prev = cur;
         for (int st = 0; st < nsteps; ++st) {
             Vec<T> xi;
             if constexpr (INJECT) xi = load_el<T, ALIGNED>(dW + (size_t)st * n_el, q0, n_el);
             else xi = draw_vec<T>(seed, HDP_STREAM_SDE, (u64)st, (uint32_t)v, true);
             prev = cur; // y0 .= y1 (:159)
-            int i = i0;
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
-                T x = prev.v[e];
-                T mu = coef<T>(pb.mu_kind, pb.mu_c, x);
-                T sg = coef<T>(pb.sigma_kind, pb.sigma_c, x);
-                T nx = em_ds<T>(x, mu, sg, dt, sq, xi.v[e]); // :160
-                if (pb.has_bc) {
-                    T lo = bd.lo_at(i), hi = bd.hi_at(i);
-                    if (st == 0 && q0 + e < n_el && !(x >= lo && x <= hi)) bad = true; // :59
-                    nx = reflect_coord<T>(nx, lo, hi, nb_total);                      // :161-163
-                }
-                cur.v[e] = nx;
-                if (++i == d) i = 0;
+                const T x = prev.v[e];
+                const T mudt = mu_lin ? mul_rn(mul_rn(pb.mu_c, x), dt) : mudt_c;
+                const T sgsq = sg_lin ? mul_rn(mul_rn(pb.sigma_c, x), sq) : sgsq_c;
+                cur.v[e] = add_rn(add_rn(x, mudt), mul_rn(sgsq, xi.v[e])); // :160 (y0 + μ*dt) + (σ*sq)*dW
             }
+            if (has_bc) reflect_vec<T, 1>(cur, lo, hi, 0u, nb_total); // :161-163
         }
         store_el<T, ALIGNED>(y0, q0, n_el, prev);
         store_el<T, ALIGNED>(y1, q0, n_el, cur);

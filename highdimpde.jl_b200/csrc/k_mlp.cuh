@@ -13,6 +13,7 @@
 // transaction (SoA).  All draws are addressed by the reference's consumption
 // ordinal, so results do not depend on G, on the cut, or on the GPU count.
 #pragma once
+#include <type_traits>
 #include "hdp_device.cuh"
 #include "mlp_plan.h"
 
@@ -53,6 +54,7 @@ template <typename T> struct MlpParams {
 template <typename T> struct XAcc {
     T* base;
     u64 vstride, voff;
+    int unchecked; // 1: the point may lie outside the box (user x0, sampled x3) -> `_reflect` asserts it (src/reflect.jl:12)
     __device__ __forceinline__ T* at(int j) const { return base + ((u64)j * vstride + voff) * Tr<T>::VEC; }
 };
 
@@ -70,6 +72,7 @@ template <typename T, int G> struct Ctx {
         a.base = P->scratch + (u64)k * (u64)P->npl * P->total_threads * Tr<T>::VEC;
         a.vstride = P->total_threads;
         a.voff = tid;
+        a.unchecked = k & 1; // odd slots hold sampled points x3, even slots reflected points x2
         return a;
     }
     __device__ __forceinline__ XAcc<T> point(int solve, int pt) const
@@ -78,6 +81,7 @@ template <typename T, int G> struct Ctx {
         a.base = P->points + ((u64)solve * (u64)P->n_points + (u64)pt) * (u64)P->dpad;
         a.vstride = G;
         a.voff = (u64)lane;
+        a.unchecked = 1;
         return a;
     }
 };
@@ -117,56 +121,91 @@ template <typename T, int G> __device__ __forceinline__ T time_uniform(const Ctx
 // `_mlt_sde_loop!(x2, x, s, t, prob, neumann_bc)`  (src/MLP.jl:406-421):
 // one Euler–Maruyama step s -> tend from the point `src`, then reflection.
 // Writes x2 to `dst` when non-null; returns sum(x2^2) and min(x2).
+// Everything the coordinate loop needs is copied into locals first (the parameter
+// block is only reachable through a pointer here); padding coordinates (i >= d) are
+// neutralised with selects, not branches.
 template <typename T, int G>
 __device__ HDP_NOINLINE Feat<T> em_step(Ctx<T, G>& c, const XAcc<T>& src, const XAcc<T>* dst, T s, T tend, u64 ord)
 {
     constexpr int VEC = Tr<T>::VEC;
     const MlpParams<T>& P = *c.P;
-    const DevProblem<T>& pb = P.pb;
-    const int d = pb.d;
+    const int d = P.pb.d, nvec = P.nvec;
+    const int lane = c.lane;
+    const unsigned gmask = c.gmask;
+    const u64 seed = c.seed;
+    const T* __restrict__ tape = P.n_tape;
+    const bool has_bc = P.pb.has_bc != 0, bc_scalar = P.pb.bc_is_scalar != 0;
+    const bool check_src = has_bc && src.unchecked != 0;
+    const T* __restrict__ lo_v = P.pb.lo;
+    const T* __restrict__ hi_v = P.pb.hi;
+    const T lo_s = P.pb.lo_s, hi_s = P.pb.hi_s;
+    const bool mu_lin = P.pb.mu_kind == HDP_COEF_LINEAR, sg_lin = P.pb.sigma_kind == HDP_COEF_LINEAR;
+    const T mu_c = P.pb.mu_c, sg_c = P.pb.sigma_c;
+    const bool want_min = P.pb.g_kind == HDP_G_MIN;
     const T dt = sub_rn(tend, s);  // :415
     const T sq = sqrt_rn(dt);
-    Feat<T> f;
-    f.ssq = (T)0;
-    f.mn = big<T>();
-    for (int j = 0; j < P.npl; ++j) {
-        const int p = c.lane + G * j;
-        if (p < P.nvec) {
-            Vec<T> xi;
-            if (P.n_tape) {
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) {
-                    int i = p * VEC + e;
-                    xi.v[e] = i < d ? P.n_tape[ord * (u64)d + (u64)i] : (T)0;
-                }
-            } else xi = draw_vec<T>(c.seed, HDP_STREAM_STEP, ord, (uint32_t)p, true); // :416 randn!(x2)
-            const Vec<T> xv = ldv<T>(src.at(j));
-            Vec<T> o;
+    const T mudt_c = mul_rn(mu_c, dt), sgsq_c = mul_rn(sg_c, sq); // constant-coefficient products
+    const T* sp = src.base + src.voff * VEC;
+    const u64 sstride = src.vstride * VEC;
+    T* dp = dst ? dst->base + dst->voff * VEC : nullptr;
+    const u64 dstride = dst ? dst->vstride * VEC : 0;
+    T ssq = (T)0, mn = big<T>();
+    int nb = 0, bad = 0;
+    // FULL: every coordinate of the vec-group is a real coordinate (no padding selects)
+    auto body = [&](int p, auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        Vec<T> xi;
+        if (tape) {
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
                 const int i = p * VEC + e;
-                T nx = (T)0;
-                if (i < d) {
-                    const T x = xv.v[e];
-                    const T mu = coef<T>(pb.mu_kind, pb.mu_c, x);
-                    const T sg = coef<T>(pb.sigma_kind, pb.sigma_c, x);
-                    nx = em_mlp<T>(x, mu, sg, dt, sq, xi.v[e]); // :417
-                    if (pb.has_bc) {                             // :418-420
-                        const T lo = pb.bc_is_scalar ? pb.lo_s : pb.lo[i];
-                        const T hi = pb.bc_is_scalar ? pb.hi_s : pb.hi[i];
-                        if (!(x >= lo && x <= hi)) c.bad = 1;     // src/reflect.jl:12
-                        nx = reflect_coord<T>(nx, lo, hi, c.nb);
-                    }
-                    f.ssq += nx * nx;
-                    f.mn = nx < f.mn ? nx : f.mn;
-                }
-                o.v[e] = nx;
+                xi.v[e] = (FULL || i < d) ? tape[ord * (u64)d + (u64)i] : (T)0;
             }
-            if (dst) stv<T>(dst->at(j), o);
+        } else xi = draw_vec<T>(seed, HDP_STREAM_STEP, ord, (uint32_t)p, true); // :416 randn!(x2)
+        const Vec<T> xv = ldv<T>(sp);
+        sp += sstride;
+        Vec<T> o, lo, hi;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const T x = xv.v[e];
+            const T mudt = mu_lin ? mul_rn(mul_rn(mu_c, x), dt) : mudt_c;
+            const T sgsq = sg_lin ? mul_rn(mul_rn(sg_c, x), sq) : sgsq_c;
+            o.v[e] = add_rn(x, add_rn(mudt, mul_rn(sgsq, xi.v[e]))); // :417  x + (μ*dt + (σ*sq)*ξ)
         }
-    }
-    f.ssq = gsum<T, G>(f.ssq, c.gmask);
-    if (pb.g_kind == HDP_G_MIN) f.mn = gmin<T, G>(f.mn, c.gmask);
+        if (has_bc) { // :418-420
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                const int i = p * VEC + e;
+                const bool valid = FULL || i < d;
+                lo.v[e] = bc_scalar ? lo_s : (valid ? lo_v[i] : (T)0);
+                hi.v[e] = bc_scalar ? hi_s : (valid ? hi_v[i] : (T)0);
+                if (!valid) { lo.v[e] = -big<T>(); hi.v[e] = big<T>(); } // padding never reflects
+                if (check_src && !(xv.v[e] >= lo.v[e] && xv.v[e] <= hi.v[e])) bad = 1; // src/reflect.jl:12
+            }
+            reflect_vec<T, G>(o, lo, hi, gmask, nb);
+        }
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const bool valid = FULL || (p * VEC + e < d);
+            const T nx = valid ? o.v[e] : (T)0;
+            o.v[e] = nx;
+            ssq = xfma(nx, nx, ssq);
+            if (want_min) mn = (valid && nx < mn) ? nx : mn;
+        }
+        if (dp) {
+            stv<T>(dp, o);
+            dp += dstride;
+        }
+    };
+    const int nfull = d / VEC;
+    int p = lane;
+    for (; p < nfull; p += G) body(p, std::true_type{});
+    if (p < nvec) body(p, std::false_type{}); // the single partial vec-group, if d % VEC != 0
+    c.nb += nb;
+    c.bad |= bad;
+    Feat<T> f;
+    f.ssq = gsum<T, G>(ssq, gmask);
+    f.mn = want_min ? gmin<T, G>(mn, gmask) : mn;
     return f;
 }
 
@@ -176,42 +215,55 @@ __device__ HDP_NOINLINE Feat<T> sample_step(Ctx<T, G>& c, const XAcc<T>* dst, co
 {
     constexpr int VEC = Tr<T>::VEC;
     const MlpParams<T>& P = *c.P;
-    const DevSampler<T>& sm = P.sm;
-    const int d = P.pb.d;
-    const bool normal = sm.kind == HDP_SAMPLER_NORMAL;
-    const bool shifted = normal && sm.shifted;
-    Feat<T> f;
-    f.ssq = (T)0;
-    f.mn = big<T>();
-    for (int j = 0; j < P.npl; ++j) {
-        const int p = c.lane + G * j;
-        if (p < P.nvec) {
-            Vec<T> raw;
-            if (P.s_tape) {
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) {
-                    int i = p * VEC + e;
-                    raw.v[e] = i < d ? P.s_tape[ord * (u64)d + (u64)i] : (T)0;
-                }
-            } else raw = draw_vec<T>(c.seed, HDP_STREAM_SAMPLER, ord, (uint32_t)p, normal);
-            Vec<T> ref;
-            if (shifted) ref = ldv<T>(x2.at(j));
-            Vec<T> o;
+    const int d = P.pb.d, nvec = P.nvec;
+    const int lane = c.lane;
+    const u64 seed = c.seed;
+    const T* __restrict__ tape = P.s_tape;
+    const bool normal = P.sm.kind == HDP_SAMPLER_NORMAL;
+    const bool shifted = normal && P.sm.shifted;
+    const bool scalar = P.sm.scalar != 0;
+    const T* __restrict__ a_v = P.sm.a;
+    const T* __restrict__ b_v = P.sm.b;
+    const T a_s = P.sm.a_s, b_s = P.sm.b_s, sigma = P.sm.sigma;
+    const T* rp = x2.base + x2.voff * VEC;
+    const u64 rstride = x2.vstride * VEC;
+    T* dp = dst ? dst->base + dst->voff * VEC : nullptr;
+    const u64 dstride = dst ? dst->vstride * VEC : 0;
+    T ssq = (T)0;
+    for (int p = lane; p < nvec; p += G) {
+        Vec<T> raw;
+        if (tape) {
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
                 const int i = p * VEC + e;
-                T v = (T)0;
-                if (i < d) {
-                    if (normal) v = normal_map<T>(raw.v[e], sm.sigma, shifted, shifted ? ref.v[e] : (T)0);
-                    else v = uniform_map<T>(raw.v[e], sm.scalar ? sm.a_s : sm.a[i], sm.scalar ? sm.b_s : sm.b[i]);
-                    f.ssq += v * v;
-                }
-                o.v[e] = v;
+                raw.v[e] = i < d ? tape[ord * (u64)d + (u64)i] : (T)0;
             }
-            if (dst) stv<T>(dst->at(j), o);
+        } else raw = draw_vec<T>(seed, HDP_STREAM_SAMPLER, ord, (uint32_t)p, normal);
+        Vec<T> ref;
+        if (shifted) {
+            ref = ldv<T>(rp);
+            rp += rstride;
+        }
+        Vec<T> o;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const int i = p * VEC + e;
+            const bool valid = i < d;
+            T v;
+            if (normal) v = normal_map<T>(raw.v[e], sigma, shifted, shifted ? ref.v[e] : (T)0);
+            else v = uniform_map<T>(raw.v[e], scalar ? a_s : (valid ? a_v[i] : (T)0), scalar ? b_s : (valid ? b_v[i] : (T)0));
+            v = valid ? v : (T)0;
+            ssq = xfma(v, v, ssq);
+            o.v[e] = v;
+        }
+        if (dp) {
+            stv<T>(dp, o);
+            dp += dstride;
         }
     }
-    f.ssq = gsum<T, G>(f.ssq, c.gmask);
+    Feat<T> f;
+    f.ssq = gsum<T, G>(ssq, c.gmask);
+    f.mn = big<T>();
     return f;
 }
 
@@ -522,8 +574,11 @@ __global__ void __launch_bounds__(128) mlp_expand_kernel(const __grid_constant__
 
 // the work units: dynamic fetch, one warp takes 32/G consecutive work items at a time
 // (lane groups of a warp then run equal-shaped units in lockstep)
+#ifndef HDP_MLP_MINBLOCKS
+#define HDP_MLP_MINBLOCKS 3
+#endif
 template <typename T, int G>
-__global__ void __launch_bounds__(128, 3) mlp_units_kernel(const __grid_constant__ MlpParams<T> P)
+__global__ void __launch_bounds__(128, HDP_MLP_MINBLOCKS) mlp_units_kernel(const __grid_constant__ MlpParams<T> P)
 {
     constexpr int GPW = 32 / G;
     Ctx<T, G> c;

@@ -62,13 +62,15 @@ void hdp_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-static inline double u53(uint32_t hi, uint32_t lo)
-{ /* 53-bit integer k in [0, 2^53) */
-    return (double)(((uint64_t)(hi >> 5) << 26) | (uint64_t)(lo >> 6));
+static inline double k52(uint32_t hi, uint32_t lo)
+{ /* 52-bit integer k = (hi >> 12) : lo in [0, 2^52) */
+    return (double)(((uint64_t)(hi >> 12) << 32) | (uint64_t)lo);
 }
 
-/* value i of ordinal `ord` in `stream`; element type f64: one Philox call
- * yields 2 draws (group = i>>1).  Box–Muller: u1 in (0,1], u2 in [0,1). */
+/* value i of ordinal `ord` in `stream`; element type f64: one Philox call yields 2 draws
+ * (group = i>>1).  Uniform u = k*2^-52 in [0,1).  Box–Muller: u1 = (k1 + 1/2)*2^-52 in (0,1),
+ * angle 2*pi*k2/2^52.  Same definitions as hdp_device.cuh (which evaluates the
+ * transcendentals with its own polynomials: the two agree to ~1e-15, not bit for bit). */
 double hdp_oracle_draw_f64(uint64_t seed, int stream, uint64_t ord, uint32_t i, int want_normal)
 {
     uint32_t ctr[4] = {(uint32_t)ord, (uint32_t)(ord >> 32), i >> 1, (uint32_t)stream};
@@ -76,17 +78,17 @@ double hdp_oracle_draw_f64(uint64_t seed, int stream, uint64_t ord, uint32_t i, 
     uint32_t w[4];
     hdp_oracle_philox4x32_10(ctr, key, w);
     if (!want_normal) {
-        return (i & 1) ? u53(w[2], w[3]) * 0x1.0p-53 : u53(w[0], w[1]) * 0x1.0p-53;
+        return (i & 1) ? k52(w[2], w[3]) * 0x1.0p-52 : k52(w[0], w[1]) * 0x1.0p-52;
     }
-    double u1 = (u53(w[0], w[1]) + 1.0) * 0x1.0p-53;
-    double u2 = u53(w[2], w[3]) * 0x1.0p-53;
+    double u1 = (k52(w[0], w[1]) + 0.5) * 0x1.0p-52;
+    double turn = k52(w[2], w[3]) * 0x1.0p-52;
     double r = sqrt(-2.0 * log(u1));
-    double th = 2.0 * M_PI * u2;
+    double th = 2.0 * M_PI * turn;
     return (i & 1) ? r * sin(th) : r * cos(th);
 }
 
-/* element type f32: one Philox call yields 4 draws (group = i>>2);
- * normals pair (w0,w1)->(z0,z1), (w2,w3)->(z2,z3). */
+/* element type f32: one Philox call yields 4 draws (group = i>>2); 23-bit uniforms
+ * u = (w >> 9)*2^-23; normals pair (w0,w1)->(z0,z1), (w2,w3)->(z2,z3). */
 float hdp_oracle_draw_f32(uint64_t seed, int stream, uint64_t ord, uint32_t i, int want_normal)
 {
     uint32_t ctr[4] = {(uint32_t)ord, (uint32_t)(ord >> 32), i >> 2, (uint32_t)stream};
@@ -94,10 +96,10 @@ float hdp_oracle_draw_f32(uint64_t seed, int stream, uint64_t ord, uint32_t i, i
     uint32_t w[4];
     hdp_oracle_philox4x32_10(ctr, key, w);
     uint32_t e = i & 3;
-    if (!want_normal) return (float)(w[e] >> 8) * 0x1.0p-24f;
+    if (!want_normal) return (float)(w[e] >> 9) * 0x1.0p-23f;
     uint32_t wa = w[e & 2], wb = w[(e & 2) + 1];
-    float u1 = ((float)(wa >> 8) + 1.0f) * 0x1.0p-24f;
-    float u2 = (float)(wb >> 8) * 0x1.0p-24f;
+    float u1 = ((float)(wa >> 9) + 0.5f) * 0x1.0p-23f;
+    float u2 = (float)(wb >> 9) * 0x1.0p-23f;
     float r = sqrtf(-2.0f * logf(u1));
     float th = 2.0f * (float)M_PI * u2;
     return (e & 1) ? r * sinf(th) : r * cosf(th);

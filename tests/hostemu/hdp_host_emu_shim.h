@@ -35,6 +35,21 @@ static inline void sincospi(double x, double* s, double* c) { *s = sin(M_PI * x)
 #define __log2f(x) log2f(x)
 #define __cosf(x) cosf(x)
 #define __sinf(x) sinf(x)
+static inline double hilo2d(uint32_t hi, uint32_t lo)
+{
+    uint64_t b = ((uint64_t)hi << 32) | lo;
+    double d;
+    memcpy(&d, &b, 8);
+    return d;
+}
+static inline uint32_t d2hi(double x) { uint64_t b; memcpy(&b, &x, 8); return (uint32_t)(b >> 32); }
+static inline uint32_t d2lo(double x) { uint64_t b; memcpy(&b, &x, 8); return (uint32_t)b; }
+static inline float u2f(uint32_t b) { float f; memcpy(&f, &b, 4); return f; }
+static inline double rcp_approx(double x) { return (double)(float)(1.0 / x); }     // ~24-bit seed, like MUFU.RCP64H
+static inline double rsqrt_approx(double x) { return (double)(float)(1.0 / sqrt(x)); }
+static inline double xfma(double a, double b, double c) { return fma(a, b, c); }
+static inline float xfma(float a, float b, float c) { return fmaf(a, b, c); }
+template <int G> static inline bool group_any(unsigned, bool p) { return p; }
 template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int) { return v; }
 template <typename T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v)
