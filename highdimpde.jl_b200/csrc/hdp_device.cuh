@@ -143,7 +143,7 @@ template <int G> __device__ __forceinline__ bool group_any(unsigned mask, bool p
 // f32: 23-bit uniforms by the same trick; Box–Muller on the MUFU pipe.
 // ---------------------------------------------------------------------
 #ifndef HDP_HOST_EMU
-#define HDP_CONST __constant__
+#define HDP_CONST static __constant__
 #else
 #define HDP_CONST static const
 #endif

@@ -12,7 +12,7 @@ namespace {
 typedef HDP_INST_T T_;
 constexpr int G_ = HDP_INST_G;
 
-int inst_max_blocks(int block)
+static int inst_max_blocks(int block)
 {
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mlp_units_kernel<T_, G_>, block, 0) != cudaSuccess) {
@@ -21,12 +21,12 @@ int inst_max_blocks(int block)
     }
     return nb;
 }
-cudaError_t inst_units(const MlpParams<T_>& P, int grid, int block, cudaStream_t st)
+static cudaError_t inst_units(const MlpParams<T_>& P, int grid, int block, cudaStream_t st)
 {
     mlp_units_kernel<T_, G_><<<grid, block, 0, st>>>(P);
     return cudaGetLastError();
 }
-cudaError_t inst_expand(const MlpParams<T_>& P, int off, int count, int grid, int block, cudaStream_t st)
+static cudaError_t inst_expand(const MlpParams<T_>& P, int off, int count, int grid, int block, cudaStream_t st)
 {
     mlp_expand_kernel<T_, G_><<<grid, block, 0, st>>>(P, off, count);
     return cudaGetLastError();
