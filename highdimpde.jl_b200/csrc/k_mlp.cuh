@@ -180,7 +180,7 @@ __device__ HDP_NOINLINE Feat<T> em_step(Ctx<T, G>& c, const XAcc<T>& src, const 
                 lo.v[e] = bc_scalar ? lo_s : (valid ? lo_v[i] : (T)0);
                 hi.v[e] = bc_scalar ? hi_s : (valid ? hi_v[i] : (T)0);
                 if (!valid) { lo.v[e] = -big<T>(); hi.v[e] = big<T>(); } // padding never reflects
-                if (check_src && !(xv.v[e] >= lo.v[e] && xv.v[e] <= hi.v[e])) bad = 1; // src/reflect.jl:12
+                if (valid && check_src && !(xv.v[e] >= lo.v[e] && xv.v[e] <= hi.v[e])) bad = 1; // src/reflect.jl:12
             }
             reflect_vec<T, G>(o, lo, hi, gmask, nb);
         }
@@ -197,10 +197,14 @@ __device__ HDP_NOINLINE Feat<T> em_step(Ctx<T, G>& c, const XAcc<T>& src, const 
             dp += dstride;
         }
     };
-    const int nfull = d / VEC;
-    int p = lane;
-    for (; p < nfull; p += G) body(p, std::true_type{});
-    if (p < nvec) body(p, std::false_type{}); // the single partial vec-group, if d % VEC != 0
+    // Every lane of the group runs the same number of iterations (the mirror loop votes
+    // across the group): rows of G vec-groups that are complete for all lanes take the FULL
+    // body, the remaining row(s) the predicated one (padding coordinates never reflect).
+    const int npl = P.npl;
+    const int full_rows = (d / VEC) / G;
+    int j = 0;
+    for (; j < full_rows; ++j) body(lane + G * j, std::true_type{});
+    for (; j < npl; ++j) body(lane + G * j, std::false_type{});
     c.nb += nb;
     c.bad |= bad;
     Feat<T> f;
