@@ -76,7 +76,6 @@ __device__ __forceinline__ float sqrt_rn(float a) { return __fsqrt_rn(a); }
 // Philox4x32-10.  ctr = (ordinal_lo, ordinal_hi, group, stream),
 // key = (seed_lo, seed_hi).  Addressing by consumption ordinal — never by
 // thread id — makes every draw independent of launch geometry and GPU count.
-// One 32x32->64 multiply (IMAD.WIDE.U32) yields both halves of a round product.
 // ---------------------------------------------------------------------
 struct Philox4 { uint32_t w[4]; };
 
@@ -85,11 +84,11 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
 {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        const u64 p0 = (u64)0xD2511F53u * (u64)c0;
-        const u64 p1 = (u64)0xCD9E8D57u * (u64)c2;
-        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
-        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
-        c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0;
+        const uint32_t n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
         k0 += 0x9E3779B9u;
         k1 += 0xBB67AE85u;
     }
@@ -120,11 +119,6 @@ __device__ __forceinline__ double rsqrt_approx(double x)
 }
 __device__ __forceinline__ double xfma(double a, double b, double c) { return fma(a, b, c); }
 __device__ __forceinline__ float xfma(float a, float b, float c) { return fmaf(a, b, c); }
-template <int G> __device__ __forceinline__ bool group_any(unsigned mask, bool p)
-{
-    if constexpr (G == 1) return p;
-    return __any_sync(mask, p) != 0;
-}
 #endif
 
 // ---------------------------------------------------------------------
@@ -363,25 +357,28 @@ template <typename T> __device__ __forceinline__ T reflect_coord(T b, T lo, T hi
     return b;
 }
 
-// VEC coordinates of one lane at once, the loop trip count agreed by a vote over the
-// lane group so the whole group stays convergent (branch-light: the body is selects).
+// VEC coordinates of one lane at once.  The mirror loop is an ordinary per-lane loop
+// (no collective inside): its body is selects, so lanes that are done simply idle while
+// the slowest coordinate of the warp finishes.
 template <typename T, int G>
 __device__ __forceinline__ void reflect_vec(Vec<T>& x, const Vec<T>& lo, const Vec<T>& hi, unsigned gmask, int& nb)
 {
     constexpr int VEC = Tr<T>::VEC;
+    (void)gmask;
     bool below[VEC], above[VEC];
-    bool any = false, far = false;
+    bool any = false;
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
         below[e] = x.v[e] < lo.v[e];
         above[e] = x.v[e] > hi.v[e];
         any |= below[e] | above[e];
     }
-    if (!group_any<G>(gmask, any)) return;
+    if (!any) return;
+    bool far = false;
 #pragma unroll
     for (int e = 0; e < VEC; ++e)
         far |= (below[e] | above[e]) && !(fabs(sub_rn(x.v[e], lo.v[e])) <= (T)64 * sub_rn(hi.v[e], lo.v[e]));
-    if (group_any<G>(gmask, far)) {
+    if (far) {
 #pragma unroll
         for (int e = 0; e < VEC; ++e) x.v[e] = reflect_coord<T>(x.v[e], lo.v[e], hi.v[e], nb);
         return;
@@ -398,7 +395,7 @@ __device__ __forceinline__ void reflect_vec(Vec<T>& x, const Vec<T>& lo, const V
             above[e] = x.v[e] > hi.v[e];
             any |= below[e] | above[e];
         }
-    } while (group_any<G>(gmask, any));
+    } while (any);
 }
 
 // ---------------------------------------------------------------------

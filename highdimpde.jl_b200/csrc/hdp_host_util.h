@@ -26,7 +26,19 @@ int make_dev_problem(hdp_context* h, const hdp_problem* p, int which, DevProblem
     if (rc != HDP_OK) return rc;
     fill_dev_problem<T>(p, out);
     DevProblem<T>& q = *out;
+    bool uniform_vec = false;
     if (p->has_bc && !p->bc_is_scalar) {
+        // neumann_bc = [fill(lo, d), fill(hi, d)] (test/MLP.jl:86): identical to scalar bounds
+        uniform_vec = true;
+        for (int i = 1; i < p->d; ++i)
+            if (p->lo[i] != p->lo[0] || p->hi[i] != p->hi[0]) { uniform_vec = false; break; }
+        if (uniform_vec) {
+            q.bc_is_scalar = 1;
+            q.lo_s = (T)p->lo[0];
+            q.hi_s = (T)p->hi[0];
+        }
+    }
+    if (p->has_bc && !p->bc_is_scalar && !uniform_vec) {
         std::vector<T> tmp(2 * (size_t)p->d);
         for (int i = 0; i < p->d; ++i) { tmp[i] = (T)p->lo[i]; tmp[p->d + i] = (T)p->hi[i]; }
         T* d = (T*)ensure(h, which, tmp.size() * sizeof(T));
@@ -52,6 +64,15 @@ int make_dev_sampler(hdp_context* h, const hdp_sampler* s, int d, int which, Dev
     if (!s || s->kind == HDP_SAMPLER_NONE) return HDP_OK;
     if (s->kind == HDP_SAMPLER_UNIFORM && !s->bounds_are_scalar) {
         if (!s->a || !s->b) return set_err(h, HDP_ERR_BAD_ARG, "UniformSampling vector bounds missing");
+        bool uni = true;
+        for (int i = 1; i < d; ++i)
+            if (s->a[i] != s->a[0] || s->b[i] != s->b[0]) { uni = false; break; }
+        if (uni) { // UniformSampling(fill(a, d), fill(b, d)): identical to scalar bounds
+            q.scalar = 1;
+            q.a_s = (T)s->a[0];
+            q.b_s = (T)s->b[0];
+            return HDP_OK;
+        }
         std::vector<T> tmp(2 * (size_t)d);
         for (int i = 0; i < d; ++i) { tmp[i] = (T)s->a[i]; tmp[d + i] = (T)s->b[i]; }
         T* dv = (T*)ensure(h, which, tmp.size() * sizeof(T));

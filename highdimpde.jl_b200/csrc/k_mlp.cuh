@@ -66,6 +66,7 @@ template <typename T, int G> struct Ctx {
     unsigned gmask;
     int nb;
     int bad;
+    int fast, fast_s; // em_step / sample_step may take their FAST specialisation
     __device__ __forceinline__ XAcc<T> slot(int k) const
     {
         XAcc<T> a;
@@ -124,8 +125,10 @@ template <typename T, int G> __device__ __forceinline__ T time_uniform(const Ctx
 // Everything the coordinate loop needs is copied into locals first (the parameter
 // block is only reachable through a pointer here); padding coordinates (i >= d) are
 // neutralised with selects, not branches.
-template <typename T, int G>
-__device__ HDP_NOINLINE Feat<T> em_step(Ctx<T, G>& c, const XAcc<T>& src, const XAcc<T>* dst, T s, T tend, u64 ord)
+// FAST: constant coefficients, no or scalar bounds, in-register RNG, g does not need min(x)
+// (every BASELINE configuration) — the generic machinery folds away at compile time.
+template <typename T, int G, bool FAST>
+__device__ HDP_NOINLINE Feat<T> em_step_t(Ctx<T, G>& c, const XAcc<T>& src, const XAcc<T>* dst, T s, T tend, u64 ord)
 {
     constexpr int VEC = Tr<T>::VEC;
     const MlpParams<T>& P = *c.P;
@@ -133,15 +136,16 @@ __device__ HDP_NOINLINE Feat<T> em_step(Ctx<T, G>& c, const XAcc<T>& src, const 
     const int lane = c.lane;
     const unsigned gmask = c.gmask;
     const u64 seed = c.seed;
-    const T* __restrict__ tape = P.n_tape;
-    const bool has_bc = P.pb.has_bc != 0, bc_scalar = P.pb.bc_is_scalar != 0;
+    const T* __restrict__ tape = FAST ? nullptr : P.n_tape;
+    const bool has_bc = P.pb.has_bc != 0, bc_scalar = FAST ? true : (P.pb.bc_is_scalar != 0);
     const bool check_src = has_bc && src.unchecked != 0;
-    const T* __restrict__ lo_v = P.pb.lo;
-    const T* __restrict__ hi_v = P.pb.hi;
+    const T* __restrict__ lo_v = FAST ? nullptr : P.pb.lo;
+    const T* __restrict__ hi_v = FAST ? nullptr : P.pb.hi;
     const T lo_s = P.pb.lo_s, hi_s = P.pb.hi_s;
-    const bool mu_lin = P.pb.mu_kind == HDP_COEF_LINEAR, sg_lin = P.pb.sigma_kind == HDP_COEF_LINEAR;
+    const bool mu_lin = FAST ? false : (P.pb.mu_kind == HDP_COEF_LINEAR);
+    const bool sg_lin = FAST ? false : (P.pb.sigma_kind == HDP_COEF_LINEAR);
     const T mu_c = P.pb.mu_c, sg_c = P.pb.sigma_c;
-    const bool want_min = P.pb.g_kind == HDP_G_MIN;
+    const bool want_min = FAST ? false : (P.pb.g_kind == HDP_G_MIN);
     const T dt = sub_rn(tend, s);  // :415
     const T sq = sqrt_rn(dt);
     const T mudt_c = mul_rn(mu_c, dt), sgsq_c = mul_rn(sg_c, sq); // constant-coefficient products
@@ -197,14 +201,13 @@ __device__ HDP_NOINLINE Feat<T> em_step(Ctx<T, G>& c, const XAcc<T>& src, const 
             dp += dstride;
         }
     };
-    // Every lane of the group runs the same number of iterations (the mirror loop votes
-    // across the group): rows of G vec-groups that are complete for all lanes take the FULL
-    // body, the remaining row(s) the predicated one (padding coordinates never reflect).
-    const int npl = P.npl;
-    const int full_rows = (d / VEC) / G;
-    int j = 0;
-    for (; j < full_rows; ++j) body(lane + G * j, std::true_type{});
-    for (; j < npl; ++j) body(lane + G * j, std::false_type{});
+    // full vec-groups take the FULL body; the single partial vec-group (d % VEC != 0), if this
+    // lane owns it, the predicated one.  No collective is executed inside the loop, so lanes
+    // of a group may run different trip counts.
+    const int nfull = d / VEC;
+    int p = lane;
+    for (; p < nfull; p += G) body(p, std::true_type{});
+    if (p < nvec) body(p, std::false_type{});
     c.nb += nb;
     c.bad |= bad;
     Feat<T> f;
@@ -212,22 +215,27 @@ __device__ HDP_NOINLINE Feat<T> em_step(Ctx<T, G>& c, const XAcc<T>& src, const 
     f.mn = want_min ? gmin<T, G>(mn, gmask) : mn;
     return f;
 }
+template <typename T, int G>
+__device__ __forceinline__ Feat<T> em_step(Ctx<T, G>& c, const XAcc<T>& src, const XAcc<T>* dst, T s, T tend, u64 ord)
+{
+    return c.fast ? em_step_t<T, G, true>(c, src, dst, s, tend, ord) : em_step_t<T, G, false>(c, src, dst, s, tend, ord);
+}
 
 // mc_sample!(x3, x2)  (src/MLP.jl:139,177; src/MCSample.jl:28-33, 63-71)
-template <typename T, int G>
-__device__ HDP_NOINLINE Feat<T> sample_step(Ctx<T, G>& c, const XAcc<T>* dst, const XAcc<T>& x2, u64 ord)
+template <typename T, int G, bool FAST>
+__device__ HDP_NOINLINE Feat<T> sample_step_t(Ctx<T, G>& c, const XAcc<T>* dst, const XAcc<T>& x2, u64 ord)
 {
     constexpr int VEC = Tr<T>::VEC;
     const MlpParams<T>& P = *c.P;
     const int d = P.pb.d, nvec = P.nvec;
     const int lane = c.lane;
     const u64 seed = c.seed;
-    const T* __restrict__ tape = P.s_tape;
+    const T* __restrict__ tape = FAST ? nullptr : P.s_tape;
     const bool normal = P.sm.kind == HDP_SAMPLER_NORMAL;
     const bool shifted = normal && P.sm.shifted;
-    const bool scalar = P.sm.scalar != 0;
-    const T* __restrict__ a_v = P.sm.a;
-    const T* __restrict__ b_v = P.sm.b;
+    const bool scalar = FAST ? true : (P.sm.scalar != 0);
+    const T* __restrict__ a_v = FAST ? nullptr : P.sm.a;
+    const T* __restrict__ b_v = FAST ? nullptr : P.sm.b;
     const T a_s = P.sm.a_s, b_s = P.sm.b_s, sigma = P.sm.sigma;
     const T* rp = x2.base + x2.voff * VEC;
     const u64 rstride = x2.vstride * VEC;
@@ -269,6 +277,11 @@ __device__ HDP_NOINLINE Feat<T> sample_step(Ctx<T, G>& c, const XAcc<T>* dst, co
     f.ssq = gsum<T, G>(ssq, c.gmask);
     f.mn = big<T>();
     return f;
+}
+template <typename T, int G>
+__device__ __forceinline__ Feat<T> sample_step(Ctx<T, G>& c, const XAcc<T>* dst, const XAcc<T>& x2, u64 ord)
+{
+    return c.fast_s ? sample_step_t<T, G, true>(c, dst, x2, ord) : sample_step_t<T, G, false>(c, dst, x2, ord);
 }
 
 template <typename T, int G, int LV> struct Call;
@@ -421,6 +434,9 @@ __device__ __forceinline__ void ctx_init(Ctx<T, G>& c, const MlpParams<T>& P, u6
     c.nb = 0;
     c.bad = 0;
     c.seed = 0;
+    c.fast = P.pb.mu_kind == HDP_COEF_CONST && P.pb.sigma_kind == HDP_COEF_CONST && (!P.pb.has_bc || P.pb.bc_is_scalar) &&
+             P.n_tape == nullptr && P.pb.g_kind != HDP_G_MIN;
+    c.fast_s = P.s_tape == nullptr && (P.sm.kind != HDP_SAMPLER_UNIFORM || P.sm.scalar);
 }
 
 // ---------------------------------------------------------------------

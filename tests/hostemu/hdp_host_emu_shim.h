@@ -49,7 +49,6 @@ static inline double rcp_approx(double x) { return (double)(float)(1.0 / x); }  
 static inline double rsqrt_approx(double x) { return (double)(float)(1.0 / sqrt(x)); }
 static inline double xfma(double a, double b, double c) { return fma(a, b, c); }
 static inline float xfma(float a, float b, float c) { return fmaf(a, b, c); }
-template <int G> static inline bool group_any(unsigned, bool p) { return p; }
 template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int) { return v; }
 template <typename T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v)
