@@ -595,7 +595,7 @@ __global__ void __launch_bounds__(128) mlp_expand_kernel(const __grid_constant__
 // the work units: dynamic fetch, one warp takes 32/G consecutive work items at a time
 // (lane groups of a warp then run equal-shaped units in lockstep)
 #ifndef HDP_MLP_MINBLOCKS
-#define HDP_MLP_MINBLOCKS 4
+#define HDP_MLP_MINBLOCKS 6
 #endif
 template <typename T, int G>
 __global__ void __launch_bounds__(128, HDP_MLP_MINBLOCKS) mlp_units_kernel(const __grid_constant__ MlpParams<T> P)

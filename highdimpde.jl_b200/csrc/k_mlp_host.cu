@@ -43,7 +43,7 @@ int pick_group(int nvec)
         if (g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32) return g;
     }
     int G = 1;
-    while (G < 32 && (nvec + G - 1) / G > 8) G *= 2;
+    while (G < 32 && (nvec + G - 1) / G > 16) G *= 2;
     return G;
 }
 
