@@ -102,7 +102,7 @@ class ClockSampler:
                             self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.01)
 
     def start(self):
         self._t = threading.Thread(target=self._loop, daemon=True)

@@ -197,7 +197,9 @@ sde_loop_kernel(DevProblem<T> pb, T* __restrict__ y0, T* __restrict__ y1, size_t
         }
     }
     if (bad) atomicExch(&flags[0], 1);
-    if (bounce_ctr && nb_total) atomicAdd(bounce_ctr, (unsigned long long)nb_total);
+    // one atomic per warp, not per thread: a single-address atomic serialises
+    nb_total = __reduce_add_sync(0xffffffffu, nb_total);
+    if (bounce_ctr && nb_total && (threadIdx.x & 31) == 0) atomicAdd(bounce_ctr, (unsigned long long)nb_total);
 }
 
 inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
