@@ -119,6 +119,7 @@ __device__ __forceinline__ double rsqrt_approx(double x)
 }
 __device__ __forceinline__ double xfma(double a, double b, double c) { return fma(a, b, c); }
 __device__ __forceinline__ float xfma(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ float rsq_approx(float x) { return rsqrtf(x); }
 #endif
 
 // ---------------------------------------------------------------------
@@ -173,9 +174,18 @@ __device__ __forceinline__ double neg2log_unit(double u)
     const double sv = f * r;                        // s = (m-1)/(m+1), |s| <= 0.1716
     const double s2 = sv * sv;
     // atanh(s)/s - 1 = s2/3 + s2^2/5 + ... + s2^9/19
-    double pl = kAtanhC[8];
-#pragma unroll
-    for (int i = 7; i >= 0; --i) pl = xfma(pl, s2, kAtanhC[i]);
+    // even/odd split: two half-length Horner chains in s4 = s2^2 (shorter dependent latency)
+    const double s4 = s2 * s2;
+    double pe = kAtanhC[8];
+    pe = xfma(pe, s4, kAtanhC[6]);
+    pe = xfma(pe, s4, kAtanhC[4]);
+    pe = xfma(pe, s4, kAtanhC[2]);
+    pe = xfma(pe, s4, kAtanhC[0]);
+    double po = kAtanhC[7];
+    po = xfma(po, s4, kAtanhC[5]);
+    po = xfma(po, s4, kAtanhC[3]);
+    po = xfma(po, s4, kAtanhC[1]);
+    const double pl = xfma(po, s2, pe);
     const double lm2 = xfma(sv * s2, pl, sv);       // atanh(s) = ln(m)/2
     // e as a double without I2F: (2^52 + 2^31 + e) - (2^52 + 2^31)
     const double ed = hilo2d(0x43300000u, (uint32_t)e ^ 0x80000000u) - kMisc[2];
@@ -205,13 +215,25 @@ __device__ __forceinline__ void sincos_turn52(uint32_t kh, uint32_t kl, double& 
     const double t = hilo2d(0x43300000u | (uint32_t)(f >> 32), (uint32_t)f) - kMisc[3]; // f as double
     const double a = t * kMisc[4];                  // (π/4) * 2^-49, a in [0, π/4]
     const double a2 = a * a;
-    double ps = kSinC[6];
-#pragma unroll
-    for (int i = 5; i >= 0; --i) ps = xfma(ps, a2, kSinC[i]);
+    const double a4 = a2 * a2;
+    double se = kSinC[6];
+    se = xfma(se, a4, kSinC[4]);
+    se = xfma(se, a4, kSinC[2]);
+    se = xfma(se, a4, kSinC[0]);
+    double so = kSinC[5];
+    so = xfma(so, a4, kSinC[3]);
+    so = xfma(so, a4, kSinC[1]);
+    const double ps = xfma(so, a2, se);
     const double sa = xfma(a * a2, ps, a);
-    double pc = kCosC[7];
-#pragma unroll
-    for (int i = 6; i >= 0; --i) pc = xfma(pc, a2, kCosC[i]);
+    double ce = kCosC[6];
+    ce = xfma(ce, a4, kCosC[4]);
+    ce = xfma(ce, a4, kCosC[2]);
+    ce = xfma(ce, a4, kCosC[0]);
+    double co = kCosC[7];
+    co = xfma(co, a4, kCosC[5]);
+    co = xfma(co, a4, kCosC[3]);
+    co = xfma(co, a4, kCosC[1]);
+    const double pc = xfma(co, a2, ce);
     const double ca = xfma(a2, pc, 1.0);
     const bool swap = ((q + 1u) & 2u) != 0;          // octants 1,2,5,6
     double s0 = swap ? ca : sa;
@@ -262,7 +284,8 @@ __device__ __forceinline__ Vec<float> draw_vec<float>(u64 seed, int stream, u64 
             const float u1 = u2f(0x3f800000u | (p.w[2 * h] >> 9)) - 0.99999994f; // (k + 1/2) 2^-23 in (0,1)
             const float u2 = u2f(0x3f800000u | (p.w[2 * h + 1] >> 9)) - 1.0f;
             // -2 ln u1 = -2 ln2 * log2(u1)
-            const float rad = sqrtf(-1.3862943611198906f * __log2f(u1));
+            const float tt = -1.3862943611198906f * __log2f(u1); // > 0: u1 < 1
+            const float rad = tt * rsq_approx(tt);
             const float th = 6.283185307179586f * u2;
             r.v[2 * h] = rad * __cosf(th);
             r.v[2 * h + 1] = rad * __sinf(th);

@@ -47,6 +47,7 @@ static inline uint32_t d2lo(double x) { uint64_t b; memcpy(&b, &x, 8); return (u
 static inline float u2f(uint32_t b) { float f; memcpy(&f, &b, 4); return f; }
 static inline double rcp_approx(double x) { return (double)(float)(1.0 / x); }     // ~24-bit seed, like MUFU.RCP64H
 static inline double rsqrt_approx(double x) { return (double)(float)(1.0 / sqrt(x)); }
+static inline float rsq_approx(float x) { return 1.0f / sqrtf(x); }
 static inline double xfma(double a, double b, double c) { return fma(a, b, c); }
 static inline float xfma(float a, float b, float c) { return fmaf(a, b, c); }
 template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int) { return v; }
