@@ -82,6 +82,11 @@ struct Philox4 { uint32_t w[4]; };
 __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                  uint32_t k0, uint32_t k1)
 {
+#ifndef HDP_HOST_EMU
+    // keep the round keys as immediates added to the two seed registers: without this the
+    // compiler hoists the 18 bumped keys out of the caller's coordinate loop and spills them
+    asm volatile("" : "+r"(k0), "+r"(k1));
+#endif
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
@@ -344,20 +349,28 @@ template <typename T> __device__ __forceinline__ T em_ds(T y0, T mu, T sg, T dt,
 // A far excursion (> 64 box widths, or a degenerate box) is folded in closed
 // form by a cold out-of-line routine.
 // ---------------------------------------------------------------------
-template <typename T> __device__ HDP_NOINLINE T reflect_far(T b, T lo, T hi, int* nb)
+template <typename T> struct FarResult {
+    T b;
+    int hits;
+};
+// (returns the hit count by value: a pointer argument would force the caller's counter into memory)
+template <typename T> __device__ HDP_NOINLINE FarResult<T> reflect_far(T b, T lo, T hi)
 {
+    FarResult<T> res;
+    res.hits = 0;
     const T w = sub_rn(hi, lo);
-    if (!(w > (T)0)) return b != b ? b : lo; // degenerate box
+    if (!(w > (T)0)) { res.b = b != b ? b : lo; return res; } // degenerate box
     const T y = sub_rn(b, lo);
     const T per = (T)2 * w;
     T z = fmod(y, per);
     if (z < (T)0) z += per;
     const T q = y > (T)0 ? ceil(y / w) - (T)1 : floor(-y / w) + (T)1; // wall hits, closed form
-    *nb += (int)fmin(q, (T)1.0e9);
+    res.hits = (int)fmin(q, (T)1.0e9);
     b = add_rn(lo, z <= w ? z : sub_rn(per, z));
     if (b < lo) b = lo;
     if (b > hi) b = hi;
-    return b;
+    res.b = b;
+    return res;
 }
 
 template <typename T> __device__ __forceinline__ T mirror_once(T b, T wall)
@@ -369,7 +382,11 @@ template <typename T> __device__ __forceinline__ T reflect_coord(T b, T lo, T hi
 {
     bool below = b < lo, above = b > hi;
     if (below | above) {
-        if (!(fabs(sub_rn(b, lo)) <= (T)64 * sub_rn(hi, lo))) return reflect_far<T>(b, lo, hi, &nb);
+        if (!(fabs(sub_rn(b, lo)) <= (T)64 * sub_rn(hi, lo))) {
+            const FarResult<T> fr = reflect_far<T>(b, lo, hi);
+            nb += fr.hits;
+            return fr.b;
+        }
         do {
             b = mirror_once<T>(b, below ? lo : hi);
             ++nb;
