@@ -397,45 +397,29 @@ template <typename T> __device__ __forceinline__ T reflect_coord(T b, T lo, T hi
     return b;
 }
 
-// VEC coordinates of one lane at once.  The mirror loop is an ordinary per-lane loop
-// (no collective inside): its body is selects, so lanes that are done simply idle while
-// the slowest coordinate of the warp finishes.
+// VEC coordinates of one lane at once.  The first wall hit is applied branch-free
+// (selects) to every coordinate; only coordinates that are still outside afterwards — a
+// second hit in the same step — enter the per-coordinate loop.  No collective inside.
 template <typename T, int G>
 __device__ __forceinline__ void reflect_vec(Vec<T>& x, const Vec<T>& lo, const Vec<T>& hi, unsigned gmask, int& nb)
 {
     constexpr int VEC = Tr<T>::VEC;
     (void)gmask;
-    bool below[VEC], above[VEC];
-    bool any = false;
+    bool again = false;
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
-        below[e] = x.v[e] < lo.v[e];
-        above[e] = x.v[e] > hi.v[e];
-        any |= below[e] | above[e];
+        const bool below = x.v[e] < lo.v[e];
+        const bool above = x.v[e] > hi.v[e];
+        const bool o = below | above;
+        const T t = mirror_once<T>(x.v[e], below ? lo.v[e] : hi.v[e]);
+        x.v[e] = o ? t : x.v[e];
+        nb += o ? 1 : 0;
+        again |= o && ((x.v[e] < lo.v[e]) | (x.v[e] > hi.v[e]));
     }
-    if (!any) return;
-    bool far = false;
-#pragma unroll
-    for (int e = 0; e < VEC; ++e)
-        far |= (below[e] | above[e]) && !(fabs(sub_rn(x.v[e], lo.v[e])) <= (T)64 * sub_rn(hi.v[e], lo.v[e]));
-    if (far) {
+    if (again) {
 #pragma unroll
         for (int e = 0; e < VEC; ++e) x.v[e] = reflect_coord<T>(x.v[e], lo.v[e], hi.v[e], nb);
-        return;
     }
-    do {
-        any = false;
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-            const bool o = below[e] | above[e];
-            const T t = mirror_once<T>(x.v[e], below[e] ? lo.v[e] : hi.v[e]);
-            x.v[e] = o ? t : x.v[e];
-            nb += o ? 1 : 0;
-            below[e] = x.v[e] < lo.v[e];
-            above[e] = x.v[e] > hi.v[e];
-            any |= below[e] | above[e];
-        }
-    } while (any);
 }
 
 // ---------------------------------------------------------------------
