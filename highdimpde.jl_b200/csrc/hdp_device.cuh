@@ -124,7 +124,32 @@ __device__ __forceinline__ double rsqrt_approx(double x)
 }
 __device__ __forceinline__ double xfma(double a, double b, double c) { return fma(a, b, c); }
 __device__ __forceinline__ float xfma(float a, float b, float c) { return fmaf(a, b, c); }
-__device__ __forceinline__ float rsq_approx(float x) { return rsqrtf(x); }
+// MUFU approximations with flush-to-zero: the arguments are never denormal here, and the
+// non-ftz forms carry denormal fix-up code (extra FSETP/FMUL per call)
+__device__ __forceinline__ float rsq_approx(float x)
+{
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x)
+{
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sin_approx(float x)
+{
+    float y;
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float cos_approx(float x)
+{
+    float y;
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 #endif
 
 // ---------------------------------------------------------------------
@@ -289,11 +314,11 @@ __device__ __forceinline__ Vec<float> draw_vec<float>(u64 seed, int stream, u64 
             const float u1 = u2f(0x3f800000u | (p.w[2 * h] >> 9)) - 0.99999994f; // (k + 1/2) 2^-23 in (0,1)
             const float u2 = u2f(0x3f800000u | (p.w[2 * h + 1] >> 9)) - 1.0f;
             // -2 ln u1 = -2 ln2 * log2(u1)
-            const float tt = -1.3862943611198906f * __log2f(u1); // > 0: u1 < 1
+            const float tt = -1.3862943611198906f * lg2_approx(u1); // > 0: u1 < 1
             const float rad = tt * rsq_approx(tt);
             const float th = 6.283185307179586f * u2;
-            r.v[2 * h] = rad * __cosf(th);
-            r.v[2 * h + 1] = rad * __sinf(th);
+            r.v[2 * h] = rad * cos_approx(th);
+            r.v[2 * h + 1] = rad * sin_approx(th);
         }
     }
     return r;
