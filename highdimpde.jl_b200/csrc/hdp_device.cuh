@@ -425,7 +425,7 @@ template <typename T> __device__ __forceinline__ T reflect_coord(T b, T lo, T hi
 // VEC coordinates of one lane at once.  The first wall hit is applied branch-free
 // (selects) to every coordinate; only coordinates that are still outside afterwards — a
 // second hit in the same step — enter the per-coordinate loop.  No collective inside.
-template <typename T, int G>
+template <typename T, int G, bool COUNT = true>
 __device__ __forceinline__ void reflect_vec(Vec<T>& x, const Vec<T>& lo, const Vec<T>& hi, unsigned gmask, int& nb)
 {
     constexpr int VEC = Tr<T>::VEC;
@@ -438,7 +438,7 @@ __device__ __forceinline__ void reflect_vec(Vec<T>& x, const Vec<T>& lo, const V
         const bool o = below | above;
         const T t = mirror_once<T>(x.v[e], below ? lo.v[e] : hi.v[e]);
         x.v[e] = o ? t : x.v[e];
-        nb += o ? 1 : 0;
+        if (COUNT) nb += o ? 1 : 0;
         again |= o && ((x.v[e] < lo.v[e]) | (x.v[e] > hi.v[e]));
     }
     if (again) {

@@ -176,7 +176,7 @@ sde_loop_kernel(DevProblem<T> pb, T* __restrict__ y0, T* __restrict__ y1, size_t
                 const T sgsq = sg_lin ? mul_rn(mul_rn(pb.sigma_c, x), sq) : sgsq_c;
                 cur.v[e] = add_rn(add_rn(x, mudt), mul_rn(sgsq, xi.v[e])); // :160 (y0 + μ*dt) + (σ*sq)*dW
             }
-            if (has_bc) reflect_vec<T, 1>(cur, lo, hi, 0u, nb_total); // :161-163
+            if (has_bc) reflect_vec<T, 1, false>(cur, lo, hi, 0u, nb_total); // :161-163
         }
         store_el<T, ALIGNED>(y0, q0, n_el, prev);
         store_el<T, ALIGNED>(y1, q0, n_el, cur);
