@@ -35,7 +35,11 @@ template <> MlpLaunchers<float> launchers_for<float>(int G)
     return MlpLaunchers<float>{nullptr, nullptr, nullptr};
 }
 
-int pick_group(int nvec)
+// Lane-group width.  Throughput regime (plenty of work): the narrowest group with at most 16
+// vec-groups per lane — fewest idle lanes, fewest shuffles.  Latency regime (a single small
+// solve cannot fill the GPU with narrow groups): widen the group so that one path-step is
+// spread over more lanes.
+int pick_group(int nvec, double est_units, double resident_lanes)
 {
     const char* env = getenv("HDP_MLP_GROUP");
     if (env) {
@@ -44,6 +48,7 @@ int pick_group(int nvec)
     }
     int G = 1;
     while (G < 32 && (nvec + G - 1) / G > 16) G *= 2;
+    while (G < 32 && G < nvec && est_units * G * 2 <= 0.5 * resident_lanes) G *= 2;
     return G;
 }
 
@@ -141,7 +146,9 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
     constexpr int VEC = Tr<T>::VEC;
     const int d = prob->d;
     const int nvec = (d + VEC - 1) / VEC;
-    const int G = pick_group(nvec);
+    const double min_unit = 8.0; // smallest work unit (path-steps + half the sampler calls)
+    const int G = pick_group(nvec, tab.W[L] * (double)n_solves / min_unit,
+                             (double)h->prop.multiProcessorCount * 768.0);
     const MlpLaunchers<T> LN = launchers_for<T>(G);
     if (!LN.units) return set_err(h, HDP_ERR_UNSUPPORTED, "no kernel for group size %d", G);
     const int block = 128;
@@ -156,7 +163,6 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
     double target = cfg->target_units > 0 ? (double)cfg->target_units : resident_groups * 8.0 * nranks;
     const double total_work = tab.W[L] * (double)n_solves;
     double thresh = total_work / target;
-    const double min_unit = 24.0;
     if (thresh < min_unit) thresh = min_unit;
     if (thresh >= tab.W[L]) thresh = tab.W[L]; // one WHOLE unit per solve
     {
