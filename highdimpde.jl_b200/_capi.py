@@ -76,7 +76,8 @@ class hdp_mlp_counts(C.Structure):
 class hdp_mlp_stats(C.Structure):
     _fields_ = [("per_solve", hdp_mlp_counts), ("bounces", C.c_uint64), ("n_units", C.c_uint64),
                 ("n_nodes", C.c_uint64), ("n_sites", C.c_uint64), ("device_ms", C.c_double),
-                ("group_size", C.c_int32), ("n_launches", C.c_int32)]
+                ("group_size", C.c_int32), ("n_launches", C.c_int32),
+                ("phase_ms", C.c_double * 4)]
 
 
 class hdp_devinfo(C.Structure):

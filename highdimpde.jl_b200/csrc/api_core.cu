@@ -87,6 +87,8 @@ extern "C" int hdp_create(hdp_handle* out, int device)
     }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
+        cudaEventCreate(&h->evp[0]) != cudaSuccess || cudaEventCreate(&h->evp[1]) != cudaSuccess ||
+        cudaEventCreate(&h->evp[2]) != cudaSuccess ||
         cudaMalloc(&h->d_flags, 64 * sizeof(int)) != cudaSuccess ||
         cudaMalloc(&h->d_ctr, 64 * sizeof(unsigned long long)) != cudaSuccess) {
         const char* m = cudaGetErrorString(cudaGetLastError());
@@ -117,6 +119,8 @@ extern "C" int hdp_destroy(hdp_handle h)
         if (h->d_ctr) cudaFree(h->d_ctr);
         if (h->ev0) cudaEventDestroy(h->ev0);
         if (h->ev1) cudaEventDestroy(h->ev1);
+        for (auto& e : h->evp)
+            if (e) cudaEventDestroy(e);
         if (h->stream) cudaStreamDestroy(h->stream);
     }
     delete h;

@@ -26,6 +26,7 @@ struct hdp_context {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t evp[3] = {nullptr, nullptr, nullptr}; // phase boundaries inside hdp_mlp_solve_*
     cudaDeviceProp prop{};
     std::mutex mu;
     std::string err;

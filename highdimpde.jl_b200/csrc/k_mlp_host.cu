@@ -262,15 +262,18 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
         HDP_CUDA(h, LN.expand(Pe, off, cnt, ge, block, h->stream));
         h->launches++;
     }
+    HDP_CUDA(h, cudaEventRecord(h->evp[0], h->stream));
     // the work units
     if (n_local > 0) {
         HDP_CUDA(h, LN.units(P, grid, block, h->stream));
         h->launches++;
     }
+    HDP_CUDA(h, cudaEventRecord(h->evp[1], h->stream));
     if (nranks > 1) {
         rc = nccl_allreduce_f64_device(h, d_partial, (size_t)n_solves * P.n_units);
         if (rc != HDP_OK) return rc;
     }
+    HDP_CUDA(h, cudaEventRecord(h->evp[2], h->stream));
     // bottom-up combine
     for (int dep = plan->max_depth; dep >= 0; --dep) {
         const int off = plan->node_depth_off[dep];
@@ -295,6 +298,12 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
         float ms = 0;
         cudaEventElapsedTime(&ms, h->ev0, h->ev1);
         stats->device_ms = ms;
+        cudaEvent_t seq[5] = {h->ev0, h->evp[0], h->evp[1], h->evp[2], h->ev1};
+        for (int i = 0; i < 4; ++i) {
+            float pm = 0;
+            cudaEventElapsedTime(&pm, seq[i], seq[i + 1]);
+            stats->phase_ms[i] = pm;
+        }
         stats->bounces = ctr[1];
         stats->n_units = P.n_units;
         stats->n_nodes = P.n_nodes;

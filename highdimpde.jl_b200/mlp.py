@@ -85,7 +85,9 @@ def _ml_picard_batch(prob: _Problem, alg: MLP, *, n_solves=1, x0=None, seed=0, t
              "sampler_calls": st.per_solve.sampler_calls, "f_evals": st.per_solve.f_evals,
              "g_evals": st.per_solve.g_evals, "bounces": st.bounces, "n_units": st.n_units,
              "n_nodes": st.n_nodes, "n_sites": st.n_sites, "device_ms": st.device_ms,
-             "group_size": st.group_size, "n_launches": st.n_launches}
+             "group_size": st.group_size, "n_launches": st.n_launches,
+             "phase_ms": {"expand": st.phase_ms[0], "units": st.phase_ms[1], "allreduce": st.phase_ms[2],
+                          "combine": st.phase_ms[3]}}
     del keep, keep2, tp
     return u, stats
 

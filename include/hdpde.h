@@ -185,6 +185,8 @@ typedef struct hdp_mlp_stats {
     double device_ms;          /* CUDA-event time of the device work of this call   */
     int32_t group_size;        /* lanes that own one path                           */
     int32_t n_launches;        /* kernels launched by this call                     */
+    double phase_ms[4];        /* device time of: expand (top-down geometry), units,
+                                  all-reduce of the partial sums, combine (bottom-up) */
 } hdp_mlp_stats;
 
 typedef struct hdp_devinfo {

@@ -25,8 +25,9 @@ elif what == "c4":
                          neumann_bc=(np.full(d, -0.5), np.full(d, 0.5)))
     Lv = int(sys.argv[2]) if len(sys.argv) > 2 else 4
     alg = H.MLP(M=4, L=Lv, K=10, mc_sample=H.UniformSampling(np.full(d, -0.5), np.full(d, 0.5)))
+    tu = int(sys.argv[3]) if len(sys.argv) > 3 else 0
     for it in range(2):
-        u, st = H._ml_picard_batch(prob, alg, n_solves=1, seed=3 + it, handle=h)
+        u, st = H._ml_picard_batch(prob, alg, n_solves=1, seed=3 + it, handle=h, target_units=tu)
         print(it, u, st)
 elif what == "c5":
     d = 1000
