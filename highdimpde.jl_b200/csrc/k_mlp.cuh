@@ -531,16 +531,20 @@ __device__ __forceinline__ void combine_item(const MlpParams<T>& P, int off, u64
             const int l = st.l;
             const int32_t* ch = P.children + st.child0;
             const T f2 = feat[st.x2_point];
-            const T b2 = ch[0] >= 0 ? val[ch[0]] : (T)0;
-            const T b4 = ch[1] >= 0 ? val[ch[1]] : (T)0;
+            // child value: explicit node, whole-call leaf (straight from its unit's partial), or 0
+            auto cv = [&](int32_t code) -> T {
+                return code >= 0 ? val[code] : (code == -1 ? (T)0 : (T)part[-2 - code]);
+            };
+            const T b2 = cv(ch[0]);
+            const T b4 = cv(ch[1]);
             T b3 = (T)0;
             if (P.Kp > 0) {
                 for (int h = 0; h < P.K; ++h) {
                     const T f3 = feat[st.x3_point0 + h];
-                    const T v = ch[2 + 2 * h] >= 0 ? val[ch[2 + 2 * h]] : (T)0;
+                    const T v = cv(ch[2 + 2 * h]);
                     T term = f_eval<T>(pb, f2, f3, b2, v);
                     if (l >= 2) {
-                        const T w = ch[3 + 2 * h] >= 0 ? val[ch[3 + 2 * h]] : (T)0;
+                        const T w = cv(ch[3 + 2 * h]);
                         term = term - f_eval<T>(pb, f2, f3, b4, w);
                     }
                     b3 += term;

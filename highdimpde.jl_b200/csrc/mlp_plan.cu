@@ -108,6 +108,15 @@ struct Builder {
         }
     }
 
+    // a child that is a single whole-call unit is read straight from partial[] by its parent site
+    int32_t child_code(int node) const
+    {
+        const PlanNode& n = p->nodes[node];
+        if (n.unit_end - n.unit_begin == 1 && n.site_end == n.site_begin && p->units[n.unit_begin].kind == UNIT_WHOLE)
+            return -2 - n.unit_begin;
+        return node;
+    }
+
     int build_node(int lv, int point, int time_site, int depth, uint64_t c0, uint64_t r0, uint64_t s0, bool root)
     {
         const int id = (int)p->nodes.size();
@@ -154,21 +163,21 @@ struct Builder {
             uint64_t c = st.c + 1, r = st.r + 1, s = st.s;
             int ch = st.child0;
             int id0 = build_node(l, st.x2_point, si, depth + 1, c, r, s, false);
-            p->children[ch++] = id0;
+            p->children[ch++] = child_code(id0);
             c += t.C[l]; r += t.R[l]; s += t.S[l];
             if (l >= 2) {
                 int id1 = build_node(l - 1, st.x2_point, si, depth + 1, c, r, s, false);
-                p->children[ch++] = id1;
+                p->children[ch++] = child_code(id1);
                 c += t.C[l - 1]; r += t.R[l - 1]; s += t.S[l - 1];
             } else ch++;
             for (int h = 0; h < t.Kp; ++h) {
                 s += 1; // the sampler call itself
                 int idh = build_node(l, st.x3_point0 + h, si, depth + 1, c, r, s, false);
-                p->children[ch++] = idh;
+                p->children[ch++] = child_code(idh);
                 c += t.C[l]; r += t.R[l]; s += t.S[l];
                 if (l >= 2) {
                     int idh1 = build_node(l - 1, st.x3_point0 + h, si, depth + 1, c, r, s, false);
-                    p->children[ch++] = idh1;
+                    p->children[ch++] = child_code(idh1);
                     c += t.C[l - 1]; r += t.R[l - 1]; s += t.S[l - 1];
                 } else ch++;
             }
@@ -199,17 +208,25 @@ void mlp_build_plan(int M, int L, int K, bool nonlocal, double thresh, int compa
     plan->site_depth_off.assign(nd + 1, 0);
     plan->node_depth_off.assign(nd + 1, 0);
     for (auto& s : plan->sites) plan->site_depth_off[s.depth + 1]++;
-    for (auto& n : plan->nodes) plan->node_depth_off[n.depth + 1]++;
+    auto needs_combine = [&](size_t i) {
+        const PlanNode& n = plan->nodes[i];
+        const bool leaf = n.unit_end - n.unit_begin == 1 && n.site_end == n.site_begin &&
+                          plan->units[n.unit_begin].kind == UNIT_WHOLE;
+        return i == 0 || !leaf;
+    };
+    for (size_t i = 0; i < plan->nodes.size(); ++i)
+        if (needs_combine(i)) plan->node_depth_off[plan->nodes[i].depth + 1]++;
     for (int i = 0; i < nd; ++i) {
         plan->site_depth_off[i + 1] += plan->site_depth_off[i];
         plan->node_depth_off[i + 1] += plan->node_depth_off[i];
     }
     plan->sites_by_depth.resize(plan->sites.size());
-    plan->nodes_by_depth.resize(plan->nodes.size());
+    plan->nodes_by_depth.resize((size_t)plan->node_depth_off[nd]);
     std::vector<int32_t> so(plan->site_depth_off.begin(), plan->site_depth_off.end() - 1);
     std::vector<int32_t> no(plan->node_depth_off.begin(), plan->node_depth_off.end() - 1);
     for (size_t i = 0; i < plan->sites.size(); ++i) plan->sites_by_depth[so[plan->sites[i].depth]++] = (int32_t)i;
-    for (size_t i = 0; i < plan->nodes.size(); ++i) plan->nodes_by_depth[no[plan->nodes[i].depth]++] = (int32_t)i;
+    for (size_t i = 0; i < plan->nodes.size(); ++i)
+        if (needs_combine(i)) plan->nodes_by_depth[no[plan->nodes[i].depth]++] = (int32_t)i;
 }
 
 } // namespace hdp

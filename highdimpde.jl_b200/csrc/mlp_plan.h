@@ -44,7 +44,9 @@ struct PlanSite {
     int32_t l;         // level of this site
     int32_t x2_point;  // point index of x2
     int32_t x3_point0; // first of K' consecutive x3 points (-1 if local)
-    int32_t child0;    // index into children[]: [U_l(x2), U_{l-1}(x2), {U_l(x3_h), U_{l-1}(x3_h)}_h], -1 = identically 0
+    int32_t child0;    // index into children[]: [U_l(x2), U_{l-1}(x2), {U_l(x3_h), U_{l-1}(x3_h)}_h];
+                       // entry >= 0: explicit node (value[node]); -1: identically 0;
+                       // <= -2: a whole-call leaf, its value is partial[-2 - entry] (no combine needed)
     int32_t depth;     // depth of the parent node
     uint64_t c, r, s;  // ordinals at the start of the site
 };
@@ -72,7 +74,7 @@ struct MlpPlan {
     std::vector<int32_t> exec_order;    // unit ids, most expensive first
     std::vector<int32_t> sites_by_depth;  // site ids grouped by depth
     std::vector<int32_t> site_depth_off;  // size max_depth+2
-    std::vector<int32_t> nodes_by_depth;
+    std::vector<int32_t> nodes_by_depth;  // nodes that need a combine (not whole-call leaves)
     std::vector<int32_t> node_depth_off;
     int n_points = 1;
     int max_depth = 0;
