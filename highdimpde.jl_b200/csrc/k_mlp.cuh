@@ -32,6 +32,7 @@ template <typename T> struct MlpParams {
     int n_solves, n_x0;
     const PlanUnit* units;
     const int32_t* exec;
+    const int8_t* unit_tag;
     const PlanNode* nodes;
     const PlanSite* sites;
     const int32_t* children;
@@ -512,7 +513,7 @@ __device__ __forceinline__ void combine_item(const MlpParams<T>& P, int off, u64
     const T* val = P.value + (u64)solve * P.n_nodes;
     const T* feat = P.feat + (u64)solve * P.n_points;
     T result;
-    if (nd.unit_end - nd.unit_begin == 1 && P.units[nd.unit_begin].kind == UNIT_WHOLE) {
+    if (nd.unit_end - nd.unit_begin == 1 && (P.unit_tag[nd.unit_begin] >> 4) == UNIT_WHOLE) {
         result = (T)part[nd.unit_begin];
     } else {
         const T s = nd.time_site < 0 ? pb.t0 : P.site_r[(u64)solve * P.n_sites + nd.time_site];
@@ -521,10 +522,10 @@ __device__ __forceinline__ void combine_item(const MlpParams<T>& P, int off, u64
         for (int l = 0; l < kMaxL; ++l) Bl[l] = (T)0;
         T Gs = (T)0;
         for (int u = nd.unit_begin; u < nd.unit_end; ++u) {
-            const int kind = P.units[u].kind;
+            const int tag = P.unit_tag[u];
             const T v = (T)part[u];
-            if (kind == UNIT_G) Gs += v;
-            else Bl[P.units[u].l] += v;
+            if ((tag >> 4) == UNIT_G) Gs += v;
+            else Bl[tag & 15] += v;
         }
         for (int si = nd.site_begin; si < nd.site_end; ++si) {
             const PlanSite st = P.sites[si];

@@ -14,7 +14,7 @@ using namespace hdp;
 namespace hdp {
 MlpPlan::~MlpPlan()
 {
-    void* ps[] = {d_nodes, d_sites, d_units, d_children, d_exec, d_sites_by_depth, d_nodes_by_depth};
+    void* ps[] = {d_nodes, d_sites, d_units, d_children, d_exec, d_sites_by_depth, d_nodes_by_depth, d_unit_tag};
     for (void* p : ps)
         if (p) cudaFree(p);
 }
@@ -75,6 +75,7 @@ int get_plan(hdp_context* h, int M, int L, int K, bool nonlocal, double thresh, 
     if ((rc = upload(h, plan->units, &plan->d_units)) != HDP_OK) return rc;
     if ((rc = upload(h, plan->children, &plan->d_children)) != HDP_OK) return rc;
     if ((rc = upload(h, plan->exec_order, &plan->d_exec)) != HDP_OK) return rc;
+    if ((rc = upload(h, plan->unit_tag, &plan->d_unit_tag)) != HDP_OK) return rc;
     if ((rc = upload(h, plan->sites_by_depth, &plan->d_sites_by_depth)) != HDP_OK) return rc;
     if ((rc = upload(h, plan->nodes_by_depth, &plan->d_nodes_by_depth)) != HDP_OK) return rc;
     if (h->plans.size() > 64) h->plans.clear();
@@ -191,6 +192,7 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
     P.n_x0 = cfg->n_x0;
     P.units = (const PlanUnit*)plan->d_units;
     P.exec = (const int32_t*)plan->d_exec;
+    P.unit_tag = (const int8_t*)plan->d_unit_tag;
     P.nodes = (const PlanNode*)plan->d_nodes;
     P.sites = (const PlanSite*)plan->d_sites;
     P.children = (const int32_t*)plan->d_children;

@@ -197,6 +197,9 @@ void mlp_build_plan(int M, int L, int K, bool nonlocal, double thresh, int compa
     plan->max_depth = 0;
     Builder b{plan, plan->tab, thresh, compat_threads, {}};
     b.build_node(L, 0, -1, 0, 0, 0, 0, true);
+    plan->unit_tag.resize(plan->units.size());
+    for (size_t i = 0; i < plan->units.size(); ++i)
+        plan->unit_tag[i] = (int8_t)((plan->units[i].kind << 4) | (plan->units[i].l & 15));
     // execution order: most expensive first (LPT); ties keep creation order so that
     // equal-shaped units stay adjacent (lane groups of one warp run in lockstep)
     plan->exec_order.resize(plan->units.size());

@@ -71,6 +71,7 @@ struct MlpPlan {
     std::vector<PlanSite> sites;
     std::vector<PlanUnit> units;
     std::vector<int32_t> children;
+    std::vector<int8_t> unit_tag;       // (kind << 4) | level, the only unit fields the combine pass reads
     std::vector<int32_t> exec_order;    // unit ids, most expensive first
     std::vector<int32_t> sites_by_depth;  // site ids grouped by depth
     std::vector<int32_t> site_depth_off;  // size max_depth+2
@@ -83,6 +84,7 @@ struct MlpPlan {
     void* d_sites = nullptr;
     void* d_units = nullptr;
     void* d_children = nullptr;
+    void* d_unit_tag = nullptr;
     void* d_exec = nullptr;
     void* d_sites_by_depth = nullptr;
     void* d_nodes_by_depth = nullptr;

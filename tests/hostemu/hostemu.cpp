@@ -57,7 +57,7 @@ static int emu_solve(const hdp_problem* prob, const hdp_mlp_cfg* cfg, const T* x
     }
     for (int i = 0; i <= kMaxL + 1; ++i) P.Mpow[i] = tab.Mpow[i];
     P.seed0 = cfg->seed; P.n_solves = n_solves; P.n_x0 = cfg->n_x0;
-    P.units = plan.units.data(); P.exec = plan.exec_order.data(); P.nodes = plan.nodes.data();
+    P.units = plan.units.data(); P.exec = plan.exec_order.data(); P.unit_tag = plan.unit_tag.data(); P.nodes = plan.nodes.data();
     P.sites = plan.sites.data(); P.children = plan.children.data();
     P.sites_by_depth = plan.sites_by_depth.data(); P.nodes_by_depth = plan.nodes_by_depth.data();
     P.n_units = (int)plan.units.size(); P.n_nodes = (int)plan.nodes.size();
