@@ -68,6 +68,7 @@ template <typename T, int G> struct Ctx {
     int nb;
     int bad;
     int fast, fast_s; // em_step / sample_step may take their FAST specialisation
+    int f_uses_z;     // f reads the sampled point itself (sum(z^2)), not only u(z)
     __device__ __forceinline__ XAcc<T> slot(int k) const
     {
         XAcc<T> a;
@@ -313,7 +314,12 @@ __device__ __forceinline__ T eval_site(Ctx<T, G>& c, const XAcc<T>& xp, T s, u64
         cc += P.C[l - 1]; rr += P.R[l - 1]; qq += P.S[l - 1];
     }
     T b3 = (T)0;
-    if (P.Kp > 0) {
+    // At a level-0 site both U_0 arguments of f are identically zero (:117-119) and no
+    // recursion starts from x3.  When f reads z only through u_z (every non-local kind but the
+    // replicator–mutator), the K sampled points cannot influence the result: they are not
+    // generated.  Their consumption ordinals are still skipped, so tapes stay aligned.
+    const bool dead_samples = (l == 0) && !c.f_uses_z;
+    if (P.Kp > 0 && !dead_samples) {
         for (int h = 0; h < P.K; ++h) { // :137, :176
             const Feat<T> f3 = sample_step<T, G>(c, l >= 1 ? &x3 : nullptr, x2, qq); // :139, :177
             qq += 1;
@@ -438,6 +444,7 @@ __device__ __forceinline__ void ctx_init(Ctx<T, G>& c, const MlpParams<T>& P, u6
     c.fast = P.pb.mu_kind == HDP_COEF_CONST && P.pb.sigma_kind == HDP_COEF_CONST && (!P.pb.has_bc || P.pb.bc_is_scalar) &&
              P.n_tape == nullptr && P.pb.g_kind != HDP_G_MIN;
     c.fast_s = P.s_tape == nullptr && (P.sm.kind != HDP_SAMPLER_UNIFORM || P.sm.scalar);
+    c.f_uses_z = P.pb.f_kind == HDP_F_NL_REPLICATOR;
 }
 
 // ---------------------------------------------------------------------
