@@ -218,6 +218,13 @@ def run_ours(args, rank, world, local_rank):
         try:
             extra = bench_sde_loop(torch, H, h, local_rank)       # configs[2] (C3)
             extra.update(bench_other_configs(H, h))                # configs[0], [3], [4]
+            p32 = h.measure_pipe_peak(32)
+            for k, v in extra.items():
+                if k.startswith("sde_loop_f32"):
+                    v["roofline"] = {"bound": "fp32", "achieved": v["fp32_pipe_lane_instr_per_s_at_I32_11"] / 1e12,
+                                     "peak": p32 / 1e12, "unit": "Tlane-instr/s",
+                                     "frac": v["fp32_pipe_lane_instr_per_s_at_I32_11"] / p32,
+                                     "hbm_frac_of_6542GBs": v["hbm_gbs"] / 6542.1}
         except Exception as e:  # pragma: no cover
             extra["extra_error"] = repr(e)
 
@@ -299,7 +306,8 @@ def bench_sde_loop(torch, H, h, local_rank):
         h.sync()
         ps = B * N / (best * 1e-3)
         out[f"sde_loop_f32_B{B}"] = {"path_steps_per_sec": ps, "coord_steps_per_sec": ps * d, "kernel_ms": best,
-                                     "bytes_written": 2 * d * B * 4}
+                                     "hbm_bytes": 3 * d * B * 4, "hbm_gbs": 3 * d * B * 4 / (best * 1e-3) / 1e9,
+                                     "fp32_pipe_lane_instr_per_s_at_I32_11": ps * d * 11}
     return out
 
 
