@@ -208,6 +208,12 @@ __device__ HDP_NOINLINE Feat<T> em_step_t(Ctx<T, G>& c, const XAcc<T>& src, cons
     // of a group may run different trip counts.
     const int nfull = d / VEC;
     int p = lane;
+#ifdef HDP_EM_UNROLL2
+    for (; p + G < nfull; p += 2 * G) { // two independent vec-groups per trip: more ILP, more registers
+        body(p, std::true_type{});
+        body(p + G, std::true_type{});
+    }
+#endif
     for (; p < nfull; p += G) body(p, std::true_type{});
     if (p < nvec) body(p, std::false_type{});
     c.nb += nb;
