@@ -26,12 +26,14 @@ HDP_ERR_NCCL = -5
 HDP_ERR_NO_DEVICE = -6
 HDP_ERR_ALLOC = -7
 HDP_ERR_UNSUPPORTED = -8
+HDP_ERR_NVRTC = -9
 
 HDP_MEM_HOST = 0
 HDP_MEM_DEVICE = 1
 HDP_ASYNC = 2
 
-HDP_COEF_CONST, HDP_COEF_LINEAR = 0, 1
+HDP_COEF_CONST, HDP_COEF_LINEAR, HDP_COEF_USER = 0, 1, 2
+HDP_G_USER, HDP_F_USER, HDP_F_NL_USER = 64, 64, 65
 HDP_G_SUMSQ, HDP_G_INV_SUMSQ, HDP_G_EXP_SUMSQ, HDP_G_MIN, HDP_G_GAUSS = 0, 1, 2, 3, 4
 HDP_F_ZERO, HDP_F_LINEAR, HDP_F_ALLEN_CAHN, HDP_F_DEFAULT_RISK, HDP_F_FISHER_KPP = 0, 1, 2, 3, 4
 HDP_F_NL_FIRST = 16
@@ -61,11 +63,16 @@ class hdp_problem(C.Structure):
                 ("lo", _DP), ("hi", _DP)]
 
 
+class hdp_user_exprs(C.Structure):
+    _fields_ = [("mu", C.c_char_p), ("sigma", C.c_char_p), ("g", C.c_char_p), ("f", C.c_char_p)]
+
+
 class hdp_mlp_cfg(C.Structure):
     _fields_ = [("M", C.c_int32), ("L", C.c_int32), ("K", C.c_int32), ("n_solves", C.c_int32),
                 ("n_x0", C.c_int32), ("normal_mode", C.c_int32), ("compat_mlt_threads", C.c_int32),
                 ("target_units", C.c_int32), ("seed", C.c_uint64), ("sampler", hdp_sampler),
-                ("r_tape", C.c_void_p), ("n_tape", C.c_void_p), ("s_tape", C.c_void_p)]
+                ("r_tape", C.c_void_p), ("n_tape", C.c_void_p), ("s_tape", C.c_void_p),
+                ("user", C.POINTER(hdp_user_exprs))]
 
 
 class hdp_mlp_counts(C.Structure):
@@ -113,6 +120,7 @@ SYMBOLS = {
     "hdp_mlp_counts_get": (_i, [_i, _i, _i, _i, _i, C.POINTER(hdp_mlp_counts)]),
     "hdp_mlp_solve_f64": (_i, [_H, _PP, C.POINTER(hdp_mlp_cfg), _VP, _VP, C.POINTER(hdp_mlp_stats)]),
     "hdp_mlp_solve_f32": (_i, [_H, _PP, C.POINTER(hdp_mlp_cfg), _VP, _VP, C.POINTER(hdp_mlp_stats)]),
+    "hdp_user_kinds_check": (_i, [_PP, C.POINTER(hdp_user_exprs), _i, C.c_char_p, C.c_size_t]),
     "hdp_tape_fill_f64": (_i, [_H, _VP, _i, _i, _i, _u64, _u64, _u64, _i]),
     "hdp_tape_fill_f32": (_i, [_H, _VP, _i, _i, _i, _u64, _u64, _u64, _i]),
     "hdp_measure_pipe_peak": (_i, [_H, _i, C.POINTER(C.c_double)]),

@@ -113,6 +113,9 @@ extern "C" int hdp_destroy(hdp_handle h)
         cudaStreamSynchronize(h->stream);
         hdp_comm_destroy(h);
         h->plans.clear();
+        for (auto& kv : h->user_modules)
+            if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
+        h->user_modules.clear();
         for (auto& b : h->buf)
             if (b.p) cudaFree(b.p);
         if (h->d_flags) cudaFree(h->d_flags);

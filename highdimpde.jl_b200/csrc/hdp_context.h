@@ -20,6 +20,12 @@ struct DevBuf {
 
 struct MlpPlan; // mlp_plan.h
 
+// K3 kernels compiled by NVRTC for one set of user expressions (user_kinds.cu)
+struct UserModule {
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t units = nullptr, expand = nullptr, combine = nullptr;
+};
+
 } // namespace hdp
 
 struct hdp_context {
@@ -40,6 +46,7 @@ struct hdp_context {
     int nccl_rank = 0, nccl_nranks = 1;
     // MLP plan cache
     std::map<std::string, std::shared_ptr<hdp::MlpPlan>> plans;
+    std::map<std::string, hdp::UserModule> user_modules;
     int launches = 0;
 };
 

@@ -20,6 +20,7 @@ template <typename T> void fill_dev_problem(const hdp_problem* p, DevProblem<T>*
     q.t1 = (T)p->t1;
     q.mu_c = (T)p->mu_p[0];
     q.sigma_c = (T)p->sigma_p[0];
+    for (int i = 0; i < 2; ++i) { q.mu_p[i] = (T)p->mu_p[i]; q.sigma_p[i] = (T)p->sigma_p[i]; }
     for (int i = 0; i < 4; ++i) q.g_p[i] = (T)p->g_p[i];
     for (int i = 0; i < 8; ++i) q.f_p[i] = (T)p->f_p[i];
     q.f_pd[0] = q.f_pd[1] = 0;

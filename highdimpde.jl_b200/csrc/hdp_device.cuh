@@ -16,11 +16,31 @@
 #include "hdp_host_emu_shim.h"
 #define HDP_NOINLINE __attribute__((noinline))
 #else
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
+#endif
 #define HDP_NOINLINE __noinline__
 #endif
+#ifndef __CUDACC_RTC__
 #include <stdint.h>
+#endif
 #include "../../include/hdpde.h"
+
+// Bodies of the *_USER kinds: CUDA-C expressions that the NVRTC build of the K3 kernels
+// defines before including this file (hdp_user_exprs, include/hdpde.h).  In the static
+// library they are inert.
+#ifndef HDP_USER_MU_EXPR
+#define HDP_USER_MU_EXPR (0)
+#endif
+#ifndef HDP_USER_SIGMA_EXPR
+#define HDP_USER_SIGMA_EXPR (0)
+#endif
+#ifndef HDP_USER_G_EXPR
+#define HDP_USER_G_EXPR (0)
+#endif
+#ifndef HDP_USER_F_EXPR
+#define HDP_USER_F_EXPR (0)
+#endif
 
 namespace hdp {
 
@@ -332,7 +352,8 @@ template <typename T> struct DevProblem {
     int mu_kind, sigma_kind, g_kind, f_kind;
     int has_bc, bc_is_scalar;
     T t0, t1;
-    T mu_c, sigma_c;
+    T mu_c, sigma_c;  // p[0] of μ, σ
+    T mu_p[2], sigma_p[2];
     T g_p[4];
     T f_p[8];
     double f_pd[2];   // replicator–mutator weights precomputed in fp64
@@ -352,6 +373,18 @@ template <typename T> struct DevSampler {
 template <typename T> __device__ __forceinline__ T coef(int kind, T c, T xi)
 {
     return kind == HDP_COEF_LINEAR ? mul_rn(c, xi) : c;
+}
+
+// user-defined μ(x,p,t)[i], σ(x,p,t)[i] (HDP_COEF_USER)
+template <typename T> __device__ __forceinline__ T user_mu(T x, int i, T t, int d, const T* p)
+{
+    (void)x; (void)i; (void)t; (void)d; (void)p;
+    return (T)(HDP_USER_MU_EXPR);
+}
+template <typename T> __device__ __forceinline__ T user_sigma(T x, int i, T t, int d, const T* p)
+{
+    (void)x; (void)i; (void)t; (void)d; (void)p;
+    return (T)(HDP_USER_SIGMA_EXPR);
 }
 
 // MLP step, src/MLP.jl:417:  x + ((μ*dt) + ((σ*sq)*ξ))
@@ -480,6 +513,13 @@ template <typename T> __device__ __forceinline__ T g_eval(const DevProblem<T>& p
     case HDP_G_EXP_SUMSQ: return xexp(-pb.g_p[0] * f.ssq);
     case HDP_G_MIN: return f.mn;
     case HDP_G_GAUSS: return (T)(pb.g_pd[0] * exp(-0.5 * (double)f.ssq / pb.g_pd[1]));
+    case HDP_G_USER: {
+        const T ssq = f.ssq, mn = f.mn;
+        const int d = pb.d;
+        const T* p = pb.g_p;
+        (void)ssq; (void)mn; (void)d; (void)p;
+        return (T)(HDP_USER_G_EXPR);
+    }
     }
     return (T)0;
 }
@@ -510,6 +550,13 @@ __device__ __forceinline__ T f_eval(const DevProblem<T>& pb, T ssq_y, T ssq_z, T
         double my = -0.5 * (double)ssq_y, mz = -0.5 * (double)ssq_z;
         double w = pb.f_pd[0] * exp(pb.f_pd[1] * (double)ssq_z);
         return (T)((double)maxz(vy) * (my - (double)maxz(vz) * mz * w));
+    }
+    case HDP_F_USER:
+    case HDP_F_NL_USER: {
+        const T t = pb.t1; // f is always called with the outer end time (src/MLP.jl:140-146, quirk Q2)
+        const int d = pb.d;
+        (void)t; (void)d; (void)ssq_y; (void)ssq_z; (void)vz;
+        return (T)(HDP_USER_F_EXPR);
     }
     }
     return (T)0;

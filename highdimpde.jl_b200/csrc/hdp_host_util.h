@@ -7,12 +7,13 @@
 
 namespace hdp {
 
-inline int validate_problem(hdp_context* h, const hdp_problem* p)
+inline int validate_problem(hdp_context* h, const hdp_problem* p, bool allow_user = false)
 {
     if (!p) return set_err(h, HDP_ERR_BAD_ARG, "problem is NULL");
     if (p->d <= 0) return set_err(h, HDP_ERR_BAD_ARG, "problem.d = %d", p->d);
-    if (p->mu_kind < 0 || p->mu_kind > HDP_COEF_LINEAR || p->sigma_kind < 0 || p->sigma_kind > HDP_COEF_LINEAR)
-        return set_err(h, HDP_ERR_BAD_ARG, "unknown mu/sigma kind");
+    const int max_coef = allow_user ? HDP_COEF_USER : HDP_COEF_LINEAR;
+    if (p->mu_kind < 0 || p->mu_kind > max_coef || p->sigma_kind < 0 || p->sigma_kind > max_coef)
+        return set_err(h, HDP_ERR_BAD_ARG, "unknown mu/sigma kind (user-defined coefficients are accepted by hdp_mlp_solve_* only)");
     if (p->has_bc && !p->bc_is_scalar && (!p->lo || !p->hi))
         return set_err(h, HDP_ERR_BAD_ARG, "vector neumann_bc without lo/hi arrays");
     return HDP_OK;
@@ -20,9 +21,9 @@ inline int validate_problem(hdp_context* h, const hdp_problem* p)
 
 // Uploads vector bounds (if any) into handle buffer `which` (2*d elements).
 template <typename T>
-int make_dev_problem(hdp_context* h, const hdp_problem* p, int which, DevProblem<T>* out)
+int make_dev_problem(hdp_context* h, const hdp_problem* p, int which, DevProblem<T>* out, bool allow_user = false)
 {
-    int rc = validate_problem(h, p);
+    int rc = validate_problem(h, p, allow_user);
     if (rc != HDP_OK) return rc;
     fill_dev_problem<T>(p, out);
     DevProblem<T>& q = *out;

@@ -13,11 +13,13 @@
 // transaction (SoA).  All draws are addressed by the reference's consumption
 // ordinal, so results do not depend on G, on the cut, or on the GPU count.
 #pragma once
-#include <type_traits>
 #include "hdp_device.cuh"
-#include "mlp_plan.h"
+#include "mlp_plan_pod.h"
 
 namespace hdp {
+
+struct FullTag { static constexpr bool value = true; };
+struct PartTag { static constexpr bool value = false; };
 
 template <typename T> struct MlpParams {
     DevProblem<T> pb;
@@ -146,8 +148,10 @@ __device__ HDP_NOINLINE Feat<T> em_step_t(Ctx<T, G>& c, const XAcc<T>& src, cons
     const T lo_s = P.pb.lo_s, hi_s = P.pb.hi_s;
     const bool mu_lin = FAST ? false : (P.pb.mu_kind == HDP_COEF_LINEAR);
     const bool sg_lin = FAST ? false : (P.pb.sigma_kind == HDP_COEF_LINEAR);
+    const bool mu_usr = FAST ? false : (P.pb.mu_kind == HDP_COEF_USER);
+    const bool sg_usr = FAST ? false : (P.pb.sigma_kind == HDP_COEF_USER);
     const T mu_c = P.pb.mu_c, sg_c = P.pb.sigma_c;
-    const bool want_min = FAST ? false : (P.pb.g_kind == HDP_G_MIN);
+    const bool want_min = FAST ? false : (P.pb.g_kind == HDP_G_MIN || P.pb.g_kind == HDP_G_USER);
     const T dt = sub_rn(tend, s);  // :415
     const T sq = sqrt_rn(dt);
     const T mudt_c = mul_rn(mu_c, dt), sgsq_c = mul_rn(sg_c, sq); // constant-coefficient products
@@ -174,8 +178,12 @@ __device__ HDP_NOINLINE Feat<T> em_step_t(Ctx<T, G>& c, const XAcc<T>& src, cons
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
             const T x = xv.v[e];
-            const T mudt = mu_lin ? mul_rn(mul_rn(mu_c, x), dt) : mudt_c;
-            const T sgsq = sg_lin ? mul_rn(mul_rn(sg_c, x), sq) : sgsq_c;
+            T mudt = mu_lin ? mul_rn(mul_rn(mu_c, x), dt) : mudt_c;
+            T sgsq = sg_lin ? mul_rn(mul_rn(sg_c, x), sq) : sgsq_c;
+            if (!FAST) { // μ(x,p,t), σ(x,p,t) are evaluated at the start point and the END time (:417)
+                if (mu_usr) mudt = mul_rn(user_mu<T>(x, p * VEC + e, tend, d, P.pb.mu_p), dt);
+                if (sg_usr) sgsq = mul_rn(user_sigma<T>(x, p * VEC + e, tend, d, P.pb.sigma_p), sq);
+            }
             o.v[e] = add_rn(x, add_rn(mudt, mul_rn(sgsq, xi.v[e]))); // :417  x + (μ*dt + (σ*sq)*ξ)
         }
         if (has_bc) { // :418-420
@@ -210,12 +218,12 @@ __device__ HDP_NOINLINE Feat<T> em_step_t(Ctx<T, G>& c, const XAcc<T>& src, cons
     int p = lane;
 #ifdef HDP_EM_UNROLL2
     for (; p + G < nfull; p += 2 * G) { // two independent vec-groups per trip: more ILP, more registers
-        body(p, std::true_type{});
-        body(p + G, std::true_type{});
+        body(p, FullTag{});
+        body(p + G, FullTag{});
     }
 #endif
-    for (; p < nfull; p += G) body(p, std::true_type{});
-    if (p < nvec) body(p, std::false_type{});
+    for (; p < nfull; p += G) body(p, FullTag{});
+    if (p < nvec) body(p, PartTag{});
     c.nb += nb;
     c.bad |= bad;
     Feat<T> f;
@@ -448,9 +456,9 @@ __device__ __forceinline__ void ctx_init(Ctx<T, G>& c, const MlpParams<T>& P, u6
     c.bad = 0;
     c.seed = 0;
     c.fast = P.pb.mu_kind == HDP_COEF_CONST && P.pb.sigma_kind == HDP_COEF_CONST && (!P.pb.has_bc || P.pb.bc_is_scalar) &&
-             P.n_tape == nullptr && P.pb.g_kind != HDP_G_MIN;
+             P.n_tape == nullptr && P.pb.g_kind != HDP_G_MIN && P.pb.g_kind != HDP_G_USER;
     c.fast_s = P.s_tape == nullptr && (P.sm.kind != HDP_SAMPLER_UNIFORM || P.sm.scalar);
-    c.f_uses_z = P.pb.f_kind == HDP_F_NL_REPLICATOR;
+    c.f_uses_z = P.pb.f_kind == HDP_F_NL_REPLICATOR || P.pb.f_kind == HDP_F_NL_USER;
 }
 
 // ---------------------------------------------------------------------

@@ -8,6 +8,8 @@
 #include <algorithm>
 #include "hdp_host_util.h"
 #include "k_mlp_launch.h"
+#include "mlp_plan.h"
+#include "user_kinds.h"
 
 using namespace hdp;
 
@@ -84,6 +86,27 @@ int get_plan(hdp_context* h, int M, int L, int K, bool nonlocal, double thresh, 
     return HDP_OK;
 }
 
+// NVRTC-built kernels for a problem with *_USER kinds (compiled once per handle and expression set)
+int get_user_module(hdp_context* h, const hdp_problem* prob, const hdp_user_exprs* user, bool f32, int G,
+                    UserModule** out)
+{
+    if (!user) return set_err(h, HDP_ERR_BAD_ARG, "the problem uses a *_USER kind but cfg.user is NULL");
+    const std::string key = user_key(prob, user, f32, G);
+    auto it = h->user_modules.find(key);
+    if (it != h->user_modules.end()) { *out = &it->second; return HDP_OK; }
+    UserBuild b;
+    int rc = user_compile(prob, user, f32, G, &b);
+    if (rc != HDP_OK) return set_err(h, rc, "%s", b.log.c_str());
+    UserModule m;
+    HDP_CUDA(h, cudaLibraryLoadData(&m.lib, b.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+    HDP_CUDA(h, cudaLibraryGetKernel(&m.units, m.lib, b.units_name.c_str()));
+    HDP_CUDA(h, cudaLibraryGetKernel(&m.expand, m.lib, b.expand_name.c_str()));
+    HDP_CUDA(h, cudaLibraryGetKernel(&m.combine, m.lib, b.combine_name.c_str()));
+    auto ins = h->user_modules.emplace(key, m);
+    *out = &ins.first->second;
+    return HDP_OK;
+}
+
 void compat_counts(const MlpCountTables& t, int NT, uint64_t* C, uint64_t* R, uint64_t* S)
 {
     uint64_t c = 0, r = 0, s = 0;
@@ -113,7 +136,8 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
         cfg->normal_mode != (sizeof(T) == 8 ? HDP_NORMAL_BM64 : HDP_NORMAL_BM32))
         return set_err(h, HDP_ERR_UNSUPPORTED, "normal_mode %d not supported for this element type", cfg->normal_mode);
     const bool nonlocal = cfg->sampler.kind != HDP_SAMPLER_NONE;
-    if (prob->f_kind >= HDP_F_NL_FIRST && !nonlocal)
+    const bool f_nonlocal = (prob->f_kind >= HDP_F_NL_FIRST && prob->f_kind < HDP_F_USER) || prob->f_kind == HDP_F_NL_USER;
+    if (f_nonlocal && !nonlocal)
         return set_err(h, HDP_ERR_BAD_ARG, "non-local f kind needs a sampler (MLP(mc_sample = ...))");
     const bool taped = cfg->r_tape || cfg->n_tape || cfg->s_tape;
     if (taped && n_solves != 1) return set_err(h, HDP_ERR_BAD_ARG, "injected tapes require n_solves == 1");
@@ -123,8 +147,11 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
 
     MlpParams<T> P;
     memset(&P, 0, sizeof(P));
-    int rc = make_dev_problem<T>(h, prob, hdp_context::B_E, &P.pb);
+    int rc = make_dev_problem<T>(h, prob, hdp_context::B_E, &P.pb, /*allow_user=*/true);
     if (rc != HDP_OK) return rc;
+    const bool uses_user = user_needed(prob) != 0;
+    if (prob->f_kind == HDP_F_NL_USER && cfg->sampler.kind == HDP_SAMPLER_NONE)
+        return set_err(h, HDP_ERR_BAD_ARG, "non-local user f needs a sampler (MLP(mc_sample = ...))");
     if ((rc = make_dev_sampler<T>(h, &cfg->sampler, prob->d, hdp_context::B_F, &P.sm)) != HDP_OK) return rc;
 
     MlpCountTables tab;
@@ -152,8 +179,16 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
                              (double)h->prop.multiProcessorCount * 768.0);
     const MlpLaunchers<T> LN = launchers_for<T>(G);
     if (!LN.units) return set_err(h, HDP_ERR_UNSUPPORTED, "no kernel for group size %d", G);
+    UserModule* um = nullptr;
+    if (uses_user && (rc = get_user_module(h, prob, cfg->user, sizeof(T) == 4, G, &um)) != HDP_OK) return rc;
     const int block = 128;
-    int bps = LN.max_blocks_per_sm(block);
+    int bps = 0;
+    if (um) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, (const void*)um->units, block, 0) != cudaSuccess) {
+            (void)cudaGetLastError();
+            bps = 0;
+        }
+    } else bps = LN.max_blocks_per_sm(block);
     if (bps < 1) return set_err(h, HDP_ERR_CUDA, "occupancy query failed for the MLP kernel");
     const int sms = h->prop.multiProcessorCount;
     const int nranks = h->nccl_comm ? h->nccl_nranks : 1;
@@ -264,14 +299,20 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
         if (cnt == 0) continue;
         uint64_t groups = (uint64_t)cnt * n_solves;
         int ge = (int)((groups * G + block - 1) / block);
-        MlpParams<T> Pe = P; // expand never touches scratch slots
-        HDP_CUDA(h, LN.expand(Pe, off, cnt, ge, block, h->stream));
+        if (um) {
+            int off_ = off, cnt_ = cnt;
+            void* args[3] = {(void*)&P, (void*)&off_, (void*)&cnt_};
+            HDP_CUDA(h, cudaLaunchKernel((const void*)um->expand, dim3(ge), dim3(block), args, 0, h->stream));
+        } else HDP_CUDA(h, LN.expand(P, off, cnt, ge, block, h->stream));
         h->launches++;
     }
     HDP_CUDA(h, cudaEventRecord(h->evp[0], h->stream));
     // the work units
     if (n_local > 0) {
-        HDP_CUDA(h, LN.units(P, grid, block, h->stream));
+        if (um) {
+            void* args[1] = {(void*)&P};
+            HDP_CUDA(h, cudaLaunchKernel((const void*)um->units, dim3(grid), dim3(block), args, 0, h->stream));
+        } else HDP_CUDA(h, LN.units(P, grid, block, h->stream));
         h->launches++;
     }
     HDP_CUDA(h, cudaEventRecord(h->evp[1], h->stream));
@@ -287,7 +328,11 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
         if (cnt == 0) continue;
         uint64_t tot = (uint64_t)cnt * n_solves;
         int gc = (int)((tot + 127) / 128);
-        mlp_combine_kernel<T><<<gc, 128, 0, h->stream>>>(P, off, cnt);
+        if (um) { // f is applied in the combine too: the user module's build of it
+            int off_ = off, cnt_ = cnt;
+            void* args[3] = {(void*)&P, (void*)&off_, (void*)&cnt_};
+            HDP_CUDA(h, cudaLaunchKernel((const void*)um->combine, dim3(gc), dim3(128), args, 0, h->stream));
+        } else mlp_combine_kernel<T><<<gc, 128, 0, h->stream>>>(P, off, cnt);
         h->launches++;
         HDP_CUDA(h, cudaGetLastError());
     }

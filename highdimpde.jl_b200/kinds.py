@@ -43,8 +43,36 @@ class LinearCoef:
         return [self.c, 0.0]
 
 
+_PY_ENV = {"exp": math.exp, "log": math.log, "sqrt": math.sqrt, "fabs": abs, "abs": abs, "pow": pow, "sin": math.sin,
+           "cos": math.cos, "tanh": math.tanh, "fmax": max, "fmin": min, "max": max, "min": min, "floor": math.floor,
+           "erf": math.erf, "M_PI": math.pi}
+
+
+def _py_eval(expr, **names):
+    """Best-effort host evaluation of a CUDA-C expression (same syntax as Python for the arithmetic subset);
+    `a ? b : c` is not supported here — the GPU is the implementation, this only serves `g(x)` in PIDESolution."""
+    return eval(expr.replace("&&", " and ").replace("||", " or "), {"__builtins__": {}}, {**_PY_ENV, **names})
+
+
+@dataclass(frozen=True)
+class UserCoef:
+    """μ(x,p,t)[i] / σ(x,p,t)[i] as a CUDA-C expression over `x` (the coordinate), `i`, `t` (the time the
+    reference passes: the end of the step), `d`, `p[0..1]` — compiled with NVRTC into the MLP kernels."""
+    expr: str
+    p: tuple = ()
+    kind = capi.HDP_COEF_USER
+
+    def __call__(self, x, p=None, t=0.0):
+        x = np.asarray(x, dtype=float)
+        return np.array([_py_eval(self.expr, x=float(v), i=i, t=t, d=x.shape[0], p=list(self.p) + [0, 0])
+                         for i, v in enumerate(x)])
+
+    def params(self):
+        return (list(self.p) + [0.0, 0.0])[:2]
+
+
 def as_coef(v):
-    if isinstance(v, (ConstCoef, LinearCoef)):
+    if isinstance(v, (ConstCoef, LinearCoef, UserCoef)):
         return v
     if isinstance(v, (int, float, np.floating)):
         return ConstCoef(float(v))
@@ -118,6 +146,22 @@ class GaussDensity:
 
     def params(self):
         return [self.ss0, 0, 0, 0]
+
+
+@dataclass(frozen=True)
+class UserG:
+    """g(x) as a CUDA-C expression over `ssq` (= sum(x.^2)), `mn` (= minimum(x)), `d`, `p[0..3]`."""
+    expr: str
+    p: tuple = ()
+    kind = capi.HDP_G_USER
+
+    def __call__(self, x):
+        x = np.asarray(x, dtype=float)
+        return float(_py_eval(self.expr, ssq=float(np.sum(x ** 2)), mn=float(np.min(x)), d=x.shape[0],
+                              p=list(self.p) + [0] * 4))
+
+    def params(self):
+        return (list(self.p) + [0.0] * 4)[:4]
 
 
 # ------------------------------ f ---------------------------------------
@@ -245,5 +289,38 @@ class FNLReplicatorMutator(_FNL):
         return [self.sigma_sampling] + [0.0] * 7
 
 
-G_KINDS = (SumSq, InvSumSq, ExpSumSq, MinCoord, GaussDensity)
-F_KINDS = (FZero, FLinear, FAllenCahn, FDefaultRisk, FFisherKPP, FNLAllenCahnDiff, FNLFisher, FNLReplicatorMutator)
+@dataclass(frozen=True)
+class UserF(_F):
+    """Local f(y, v_y, ∇v_y, p, t) as a CUDA-C expression over `vy`, `ssq_y` (= sum(y.^2)), `t`, `d`, `p[0..7]`."""
+    expr: str
+    p: tuple = ()
+    kind = capi.HDP_F_USER
+
+    def __call__(self, y, v_y, *a):
+        y = np.asarray(y, dtype=float)
+        return _py_eval(self.expr, vy=v_y, vz=0.0, ssq_y=float(np.sum(y ** 2)), ssq_z=0.0, t=0.0, d=y.shape[0],
+                        p=list(self.p) + [0] * 8)
+
+    def params(self):
+        return (list(self.p) + [0.0] * 8)[:8]
+
+
+@dataclass(frozen=True)
+class UserFNL(_FNL):
+    """Non-local f(y, z, v_y, v_z, …) as a CUDA-C expression over `vy`, `vz`, `ssq_y`, `ssq_z`, `t`, `d`, `p[0..7]`."""
+    expr: str
+    p: tuple = ()
+    kind = capi.HDP_F_NL_USER
+
+    def __call__(self, y, z, v_y, v_z, *a):
+        y, z = np.asarray(y, dtype=float), np.asarray(z, dtype=float)
+        return _py_eval(self.expr, vy=v_y, vz=v_z, ssq_y=float(np.sum(y ** 2)), ssq_z=float(np.sum(z ** 2)), t=0.0,
+                        d=y.shape[0], p=list(self.p) + [0] * 8)
+
+    def params(self):
+        return (list(self.p) + [0.0] * 8)[:8]
+
+
+G_KINDS = (SumSq, InvSumSq, ExpSumSq, MinCoord, GaussDensity, UserG)
+F_KINDS = (FZero, FLinear, FAllenCahn, FDefaultRisk, FFisherKPP, FNLAllenCahnDiff, FNLFisher, FNLReplicatorMutator,
+           UserF, UserFNL)

@@ -64,6 +64,9 @@ def _ml_picard_batch(prob: _Problem, alg: MLP, *, n_solves=1, x0=None, seed=0, t
     cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     sm, keep2 = alg.mc_sample._descriptor(d)
     cfg.sampler = sm
+    ue = prob.user_exprs()
+    if ue is not None:
+        cfg.user = C.pointer(ue)
     tp = []
     if tapes is not None:
         r_t, n_t, s_t = tapes

@@ -50,6 +50,30 @@ class _Problem:
     def d(self) -> int:
         return int(self.x.shape[0])
 
+    def user_exprs(self):
+        """hdp_user_exprs for the *_USER kinds of this problem, or None."""
+        ue = capi.hdp_user_exprs()
+        used = False
+        for field, obj in (("mu", self.mu), ("sigma", self.sigma), ("g", self.g), ("f", self.f)):
+            if isinstance(obj, (K.UserCoef, K.UserG, K.UserF, K.UserFNL)):
+                setattr(ue, field, obj.expr.encode())
+                used = True
+        return ue if used else None
+
+    def check_user_kinds(self, dtype=np.float64) -> str:
+        """Compile the user expressions (NVRTC, no GPU needed); raises HdpError with the compiler log."""
+        ue = self.user_exprs()
+        if ue is None:
+            return ""
+        lib = capi.load_library()
+        pb, keep = self.to_c()
+        log = C.create_string_buffer(1 << 16)
+        rc = lib.hdp_user_kinds_check(C.byref(pb), C.byref(ue), int(np.dtype(dtype) == np.float32), log, len(log))
+        msg = log.value.decode("utf-8", "replace")
+        if rc != capi.HDP_OK:
+            raise capi.HdpError(rc, msg)
+        return msg
+
     def to_c(self):
         """hdp_problem descriptor (+ the numpy arrays it points to, which must stay alive)."""
         pb = capi.hdp_problem()

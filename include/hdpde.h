@@ -26,8 +26,10 @@
 #ifndef HDPDE_H
 #define HDPDE_H
 
+#ifndef __CUDACC_RTC__
 #include <stdint.h>
 #include <stddef.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -51,7 +53,8 @@ enum {
     HDP_ERR_NCCL = -5,
     HDP_ERR_NO_DEVICE = -6,
     HDP_ERR_ALLOC = -7,
-    HDP_ERR_UNSUPPORTED = -8
+    HDP_ERR_UNSUPPORTED = -8,
+    HDP_ERR_NVRTC = -9
 };
 
 /* ------------------------------------------------------------------ */
@@ -73,7 +76,10 @@ enum {
  * as the reference's broadcast expression requires. */
 enum {
     HDP_COEF_CONST = 0,  /* c             p[0]=c   (test/MLP.jl:24-25)    */
-    HDP_COEF_LINEAR = 1  /* c * x_i       p[0]=c   (test/MLP.jl:191-192)  */
+    HDP_COEF_LINEAR = 1, /* c * x_i       p[0]=c   (test/MLP.jl:191-192)  */
+    HDP_COEF_USER = 2    /* hdp_user_exprs.mu / .sigma: a CUDA-C expression over
+                            x (the coordinate), i (its index), t (the time the
+                            reference passes: the step's end time), d, p[0..1]  */
 };
 
 /* g(x): terminal/initial condition prob.g, used at src/MLP.jl:203 */
@@ -82,7 +88,9 @@ enum {
     HDP_G_INV_SUMSQ = 1,    /* 1/(p0 + p1*sum(x^2))          (test/MLP.jl:146)         */
     HDP_G_EXP_SUMSQ = 2,    /* exp(-p0*sum(x^2))             (test/MLP.jl:174; docs/src/tutorials/mlp.md:17) */
     HDP_G_MIN = 3,          /* minimum(x)                    (test/MLP.jl:199)         */
-    HDP_G_GAUSS = 4         /* (2pi)^(-d/2) p0^(-d/2) exp(-0.5*sum(x^2)/p0)  (test/MLP.jl:265) */
+    HDP_G_GAUSS = 4,        /* (2pi)^(-d/2) p0^(-d/2) exp(-0.5*sum(x^2)/p0)  (test/MLP.jl:265) */
+    HDP_G_USER = 64         /* hdp_user_exprs.g: CUDA-C expression over ssq (= sum(x^2)),
+                               mn (= minimum(x)), d, p[0..3]                          */
 };
 
 /* f: nonlinearity prob.f.  Local kinds take (u_y); non-local kinds take
@@ -98,8 +106,10 @@ enum {
     HDP_F_NL_FIRST = 16,
     HDP_F_NL_ALLEN_CAHN_DIFF = 16, /* a(u_y) - a(u_z), a(u)=u-u^3  (test/MLP.jl:304)     */
     HDP_F_NL_FISHER = 17,     /* max(0,u_y)*(1-max(0,u_z))         (docs/src/tutorials/mlp.md:52) */
-    HDP_F_NL_REPLICATOR = 18  /* max(0,u_y)*(m(y) - max(0,u_z)*m(z)*(2pi)^(d/2)*p0^d*exp(0.5*sum(z^2)/p0^2)),
+    HDP_F_NL_REPLICATOR = 18, /* max(0,u_y)*(m(y) - max(0,u_z)*m(z)*(2pi)^(d/2)*p0^d*exp(0.5*sum(z^2)/p0^2)),
                                  m(x) = -0.5*sum(x^2), p0 = sigma_sampling  (test/MLP.jl:266-274) */
+    HDP_F_USER = 64,          /* local:     hdp_user_exprs.f over vy, ssq_y, t, d, p[0..7]          */
+    HDP_F_NL_USER = 65        /* non-local: hdp_user_exprs.f over vy, vz, ssq_y, ssq_z, t, d, p[0..7] */
 };
 
 /* samplers: src/MCSample.jl:22-94 */
@@ -114,6 +124,16 @@ enum {
     HDP_NORMAL_DEFAULT = 0,  /* BM64 for f64 entry points, BM32 for f32    */
     HDP_NORMAL_BM64 = 1,     /* Box-Muller, 53-bit uniforms, fp64 log/sincospi */
     HDP_NORMAL_BM32 = 2      /* Box-Muller, 32-bit uniforms, fp32 MUFU transcendentals */
+};
+
+/* random streams (one Philox stream id per consumer) */
+enum {
+    HDP_STREAM_TIME = 0,     /* uniforms r   (src/MLP.jl:132)          */
+    HDP_STREAM_STEP = 1,     /* normals of `_mlt_sde_loop!` (:416)     */
+    HDP_STREAM_SAMPLER = 2,  /* mc_sample! draws inside MLP            */
+    HDP_STREAM_SDE = 3,      /* dWall of sde_loop! (DeepSplitting.jl:154) */
+    HDP_STREAM_X0 = 4,       /* x0_sample!(y1) (DeepSplitting.jl:155)  */
+    HDP_STREAM_MC = 5        /* mc_sample!(z, y1) (DeepSplitting.jl:188) */
 };
 
 /* ------------------------------------------------------------------ */
@@ -149,6 +169,18 @@ typedef struct hdp_problem {
     const double *lo, *hi;     /* length-d HOST arrays when has_bc && !bc_is_scalar */
 } hdp_problem;
 
+/* User-supplied function bodies for the *_USER kinds: CUDA-C
+ * expressions compiled with NVRTC into the K3 kernels on first use and cached in the
+ * handle.  Arbitrary Julia closures still cannot cross the ABI, but any g, f, μ, σ that
+ * can be written as an expression of the quantities the hot path carries can.
+ * NULL members are unused.  Only hdp_mlp_solve_* accepts USER kinds.                 */
+typedef struct hdp_user_exprs {
+    const char* mu;
+    const char* sigma;
+    const char* g;
+    const char* f;
+} hdp_user_exprs;
+
 /* MLP(M, L, K, mc_sample) (src/MLP.jl:24-32) plus the knobs a GPU needs. */
 typedef struct hdp_mlp_cfg {
     int32_t M, L, K;
@@ -166,6 +198,7 @@ typedef struct hdp_mlp_cfg {
      * r_tape[R], n_tape[C*d], s_tape[S*d] with R, C, S from hdp_mlp_counts.
      * All three NULL => counter-based Philox generated in registers. */
     const void *r_tape, *n_tape, *s_tape;
+    const hdp_user_exprs* user; /* required iff the problem uses a *_USER kind, else NULL */
 } hdp_mlp_cfg;
 
 typedef struct hdp_mlp_counts {
@@ -200,6 +233,8 @@ typedef struct hdp_devinfo {
     char name[128];
 } hdp_devinfo;
 
+/* entry points: host only (the NVRTC build of the kernels sees the descriptors above) */
+#ifndef __CUDACC_RTC__
 typedef struct hdp_context* hdp_handle;
 
 /* ------------------------------------------------------------------ */
@@ -305,6 +340,11 @@ int hdp_mlp_solve_f64(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* 
                       const double* x0, double* u_out, hdp_mlp_stats* stats);
 int hdp_mlp_solve_f32(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg,
                       const float* x0, float* u_out, hdp_mlp_stats* stats);
+/* Compiles the user expressions exactly as hdp_mlp_solve_* would (NVRTC, sm_100a) without
+ * touching a device: validation on a machine without a GPU.  is_f32: element type;
+ * log (nullable) receives the compiler log.  Returns HDP_OK or HDP_ERR_BAD_ARG.          */
+int hdp_user_kinds_check(const hdp_problem* prob, const hdp_user_exprs* user, int is_f32,
+                         char* log, size_t log_cap);
 
 /* ------------------------------------------------------------------ */
 /* Random tapes: the exact numbers the in-register generator produces,
@@ -312,14 +352,6 @@ int hdp_mlp_solve_f32(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* 
  * stream: HDP_STREAM_*; ordinal0: first ordinal; n_ord × width values,
  * value (o, i) = draw i of ordinal ordinal0+o.                         */
 /* ------------------------------------------------------------------ */
-enum {
-    HDP_STREAM_TIME = 0,     /* uniforms r   (src/MLP.jl:132)          */
-    HDP_STREAM_STEP = 1,     /* normals of `_mlt_sde_loop!` (:416)     */
-    HDP_STREAM_SAMPLER = 2,  /* mc_sample! draws inside MLP            */
-    HDP_STREAM_SDE = 3,      /* dWall of sde_loop! (DeepSplitting.jl:154) */
-    HDP_STREAM_X0 = 4,       /* x0_sample!(y1) (DeepSplitting.jl:155)  */
-    HDP_STREAM_MC = 5        /* mc_sample!(z, y1) (DeepSplitting.jl:188) */
-};
 int hdp_tape_fill_f64(hdp_handle h, double* out, int stream, int want_normal, int normal_mode,
                       uint64_t seed, uint64_t ordinal0, uint64_t n_ord, int width);
 int hdp_tape_fill_f32(hdp_handle h, float* out, int stream, int want_normal, int normal_mode,
@@ -334,6 +366,7 @@ int hdp_measure_pipe_peak(hdp_handle h, int which, double* lane_instr_per_s);
 /* CUDA-event time (ms) of the kernels launched by the last entry-point call on this
  * handle (K1/K2/K3/K4); synchronises the handle's stream. */
 int hdp_last_device_ms(hdp_handle h, double* ms);
+#endif /* __CUDACC_RTC__ */
 
 #ifdef __cplusplus
 }

@@ -347,6 +347,15 @@ void hdp_oracle_mlp_counts(int M, int L, int K, int nonlocal, int64_t out[5])
     out[0] = C[L]; out[1] = R[L]; out[2] = S[L]; out[3] = F[L]; out[4] = G[L];
 }
 
+hdp_oracle_user_fns hdp_oracle_user = {0, 0, 0, 0};
+void hdp_oracle_set_user_fns(void* mu, void* sigma, void* g, void* f)
+{
+    hdp_oracle_user.mu = (hdp_oracle_user_coef)mu;
+    hdp_oracle_user.sigma = (hdp_oracle_user_coef)sigma;
+    hdp_oracle_user.g = (hdp_oracle_user_g)g;
+    hdp_oracle_user.f = (hdp_oracle_user_f)f;
+}
+
 /* ================================================================ */
 /* the two instantiations of the restatement                           */
 /* ================================================================ */

@@ -23,6 +23,19 @@ typedef struct hdp_oracle_rng {
     int kind; /* 1 tape, 2 philox-by-ordinal, 3 xoshiro+ziggurat */
 } hdp_oracle_rng;
 
+/* user-defined kinds (HDP_*_USER): plain C function pointers, set by the tests from a
+ * gcc-compiled twin of the CUDA-C expressions handed to the library */
+typedef double (*hdp_oracle_user_coef)(double x, int i, double t, int d, const double* p);
+typedef double (*hdp_oracle_user_g)(double ssq, double mn, int d, const double* p);
+typedef double (*hdp_oracle_user_f)(double vy, double vz, double ssq_y, double ssq_z, double t, int d, const double* p);
+typedef struct hdp_oracle_user_fns {
+    hdp_oracle_user_coef mu, sigma;
+    hdp_oracle_user_g g;
+    hdp_oracle_user_f f;
+} hdp_oracle_user_fns;
+extern hdp_oracle_user_fns hdp_oracle_user;
+void hdp_oracle_set_user_fns(void* mu, void* sigma, void* g, void* f);
+
 hdp_oracle_rng* hdp_oracle_rng_tape(int is_f32, const void* r, uint64_t rn, const void* n, uint64_t nn,
                                     const void* s, uint64_t sn);
 void hdp_oracle_rng_tape_pos(hdp_oracle_rng* g, uint64_t out[4]);

@@ -26,9 +26,13 @@
 /* ---------------------------------------------------------------- */
 
 /* μ(x,p,t)[i] or σ(x,p,t)[i]; scalar-valued kinds broadcast. */
-static inline REAL FN(coef)(int kind, const double* p, REAL xi)
+static inline REAL FN(coef)(int kind, const double* p, REAL xi, int i, REAL t, int d, int which)
 {
     if (kind == HDP_COEF_LINEAR) return (REAL)p[0] * xi; /* test/MLP.jl:191-192: 0.02f0 * x */
+    if (kind == HDP_COEF_USER) {                        /* user μ(x,p,t)[i] / σ(x,p,t)[i] */
+        hdp_oracle_user_coef fn = which ? hdp_oracle_user.sigma : hdp_oracle_user.mu;
+        return (REAL)fn((double)xi, i, (double)t, d, p);
+    }
     return (REAL)p[0];                                  /* test/MLP.jl:24-25 */
 }
 
@@ -61,6 +65,11 @@ static REAL FN(g_eval)(const hdp_problem* pb, const REAL* x)
         double s = 0;
         for (int i = 0; i < d; ++i) s += ((double)x[i] * (double)x[i]) / ss0;
         return (REAL)(pow(2.0 * M_PI, -d / 2.0) * pow(ss0, -d * 0.5) * exp(-0.5 * s));
+    }
+    case HDP_G_USER: {
+        REAL m = x[0];
+        for (int i = 1; i < d; ++i) m = x[i] < m ? x[i] : m;
+        return (REAL)hdp_oracle_user.g((double)FN(sumsq)(x, d), (double)m, d, p);
     }
     }
     return 0;
@@ -101,6 +110,9 @@ static REAL FN(f_eval)(const hdp_problem* pb, REAL ssq_y, REAL ssq_z, REAL vy, R
         double r = (double)FN(maxz)(vy) * (my - (double)FN(maxz)(vz) * mz * w);
         return (REAL)r;
     }
+    case HDP_F_USER:
+    case HDP_F_NL_USER: /* f(..., p, t) is called with the outer end time (src/MLP.jl:140-146) */
+        return (REAL)hdp_oracle_user.f((double)vy, (double)vz, (double)ssq_y, (double)ssq_z, pb->t1, pb->d, p);
     }
     return 0;
 }
@@ -332,8 +344,8 @@ static void FN(mlt_sde_loop)(FN(mlp_ctx)* c, REAL* x2, const REAL* x, REAL s, RE
     c->rng->normals(c->rng->ctx, c->tmp_d, d);                 /* :416 randn!(x2) */
     for (int i = 0; i < d; ++i) {
         REAL xi = (REAL)c->tmp_d[i];
-        REAL mu = FN(coef)(pb->mu_kind, pb->mu_p, x[i]);
-        REAL sg = FN(coef)(pb->sigma_kind, pb->sigma_p, x[i]);
+        REAL mu = FN(coef)(pb->mu_kind, pb->mu_p, x[i], i, t, d, 0); /* μ(x, p, t): start point, END time */
+        REAL sg = FN(coef)(pb->sigma_kind, pb->sigma_p, x[i], i, t, d, 1);
         /* :417 x2 .= x + (μ .* dt .+ σ .* sqrt(dt) .* x2) */
         x2[i] = x[i] + ((mu * dt) + ((sg * sq) * xi));
     }
@@ -510,7 +522,8 @@ static int FN(ctx_init)(FN(mlp_ctx)* c, const hdp_problem* pb, const hdp_sampler
         c->lo[i] = (REAL)(pb->has_bc ? (pb->bc_is_scalar ? pb->lo_scalar : pb->lo[i]) : 0.0);
         c->hi[i] = (REAL)(pb->has_bc ? (pb->bc_is_scalar ? pb->hi_scalar : pb->hi[i]) : 0.0);
     }
-    if (pb->f_kind >= HDP_F_NL_FIRST && !c->integrate) return HDP_ERR_BAD_ARG;
+    if (((pb->f_kind >= HDP_F_NL_FIRST && pb->f_kind < HDP_F_USER) || pb->f_kind == HDP_F_NL_USER) && !c->integrate)
+        return HDP_ERR_BAD_ARG;
     return HDP_OK;
 }
 static void FN(ctx_free)(FN(mlp_ctx)* c)
@@ -639,8 +652,8 @@ int FN(hdp_oracle_sde_loop)(const hdp_problem* pb, REAL* y0, REAL* y1, int B, in
         const REAL* dW = dWall + (size_t)st * n_el;             /* :158 */
         memcpy(y0, y1, sizeof(REAL) * n_el);                    /* :159 y0 .= y1 */
         for (size_t q = 0; q < n_el; ++q) {
-            REAL mu = FN(coef)(pb->mu_kind, pb->mu_p, y0[q]);
-            REAL sg = FN(coef)(pb->sigma_kind, pb->sigma_p, y0[q]);
+            REAL mu = FN(coef)(pb->mu_kind, pb->mu_p, y0[q], (int)(q % (size_t)d), (REAL)0, d, 0);
+            REAL sg = FN(coef)(pb->sigma_kind, pb->sigma_p, y0[q], (int)(q % (size_t)d), (REAL)0, d, 1);
             /* :160 y1 .= y0 .+ μ .* dt .+ σ .* sqrt(dt) .* dW   →  (y0 + μ*dt) + ((σ*sqrt(dt))*dW) */
             y1[q] = (y0[q] + mu * dt) + ((sg * sq) * dW[q]);
         }

@@ -273,3 +273,34 @@ def bench_solves(pb_struct, sampler_struct, M, L, K, x, n_solves, nthreads, seed
     if rc != 0:
         raise ValueError(f"oracle bench_solves rc={rc}")
     return u, sec.value
+
+
+_user_libs = []
+
+
+def set_user_kinds(mu=None, sigma=None, g=None, f=None):
+    """Compile the C twins of the CUDA-C user expressions (hdp_user_exprs) with gcc and register them
+    with the oracle (HDP_*_USER kinds).  Expressions use the same variable names as on the device."""
+    import hashlib
+    import tempfile
+    src = ["#include <math.h>", "#define fmax2(a,b) ((a)>(b)?(a):(b))"]
+    src.append("double u_mu(double x, int i, double t, int d, const double* p) { (void)x;(void)i;(void)t;(void)d;(void)p; return (%s); }" % (mu or "0"))
+    src.append("double u_sigma(double x, int i, double t, int d, const double* p) { (void)x;(void)i;(void)t;(void)d;(void)p; return (%s); }" % (sigma or "0"))
+    src.append("double u_g(double ssq, double mn, int d, const double* p) { (void)ssq;(void)mn;(void)d;(void)p; return (%s); }" % (g or "0"))
+    src.append("double u_f(double vy, double vz, double ssq_y, double ssq_z, double t, int d, const double* p) { (void)vy;(void)vz;(void)ssq_y;(void)ssq_z;(void)t;(void)d;(void)p; return (%s); }" % (f or "0"))
+    code = "\n".join(src)
+    tag = hashlib.sha1(code.encode()).hexdigest()[:16]
+    d = os.path.join(tempfile.gettempdir(), "hdp_oracle_user")
+    os.makedirs(d, exist_ok=True)
+    so = os.path.join(d, f"u_{tag}.so")
+    if not os.path.exists(so):
+        cfile = os.path.join(d, f"u_{tag}.c")
+        with open(cfile, "w") as fh:
+            fh.write(code)
+        subprocess.run(["gcc", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-o", so, cfile, "-lm"], check=True)
+    ul = C.CDLL(so)
+    _user_libs.append(ul)
+    L = lib()
+    L.hdp_oracle_set_user_fns.argtypes = [C.c_void_p] * 4
+    L.hdp_oracle_set_user_fns(C.cast(ul.u_mu, C.c_void_p), C.cast(ul.u_sigma, C.c_void_p),
+                              C.cast(ul.u_g, C.c_void_p), C.cast(ul.u_f, C.c_void_p))

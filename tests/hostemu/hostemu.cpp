@@ -7,6 +7,7 @@
 #include <vector>
 #include <algorithm>
 #include "k_mlp.cuh"
+#include "mlp_plan.h"
 #include "hdp_convert.h"
 
 using namespace hdp;

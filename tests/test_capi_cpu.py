@@ -33,14 +33,15 @@ def test_struct_layouts_match_c(H, tmp_path):
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "hdpde.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    "sizeof(hdp_sampler),sizeof(hdp_problem),sizeof(hdp_mlp_cfg),sizeof(hdp_mlp_counts),sizeof(hdp_mlp_stats),"
-                   "sizeof(hdp_devinfo),offsetof(hdp_problem,lo),offsetof(hdp_mlp_cfg,sampler),offsetof(hdp_mlp_cfg,r_tape));return 0;}\n")
+                   "sizeof(hdp_devinfo),offsetof(hdp_problem,lo),offsetof(hdp_mlp_cfg,sampler),offsetof(hdp_mlp_cfg,r_tape));"
+                   'printf("%zu %zu\\n", offsetof(hdp_mlp_cfg,user), sizeof(hdp_user_exprs));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
     c = H.capi
     want = [C.sizeof(c.hdp_sampler), C.sizeof(c.hdp_problem), C.sizeof(c.hdp_mlp_cfg), C.sizeof(c.hdp_mlp_counts),
             C.sizeof(c.hdp_mlp_stats), C.sizeof(c.hdp_devinfo), c.hdp_problem.lo.offset, c.hdp_mlp_cfg.sampler.offset,
-            c.hdp_mlp_cfg.r_tape.offset]
+            c.hdp_mlp_cfg.r_tape.offset, c.hdp_mlp_cfg.user.offset, C.sizeof(c.hdp_user_exprs)]
     assert [int(v) for v in out] == want
 
 
