@@ -40,6 +40,10 @@ struct HdpMlpCfg
     seed::UInt64
     sampler::HdpSampler
     r_tape::Ptr{Cvoid}; n_tape::Ptr{Cvoid}; s_tape::Ptr{Cvoid}
+    user::Ptr{Cvoid}             # Ptr{HdpUserExprs} for the *_USER kinds, else C_NULL
+end
+struct HdpUserExprs                # CUDA-C expressions compiled by NVRTC (include/hdpde.h: hdp_user_exprs)
+    mu::Cstring; sigma::Cstring; g::Cstring; f::Cstring
 end
 
 # ------------------------------------------------------------------ kinds: callable structs
@@ -148,7 +152,7 @@ function _mlp_b200(M, L, K, x::Vector{T}, mc_sample!, prob, neumann_bc, compat_t
     keep = Any[]
     pb = problem_desc(prob, prob.f, neumann_bc, keep)
     cfg = HdpMlpCfg(M, L, K, 1, 1, 0, compat_threads, 0, rand(UInt64), sampler_desc(mc_sample!, keep),
-                    C_NULL, C_NULL, C_NULL)
+                    C_NULL, C_NULL, C_NULL, C_NULL)
     u = Vector{T}(undef, 1)
     h = handle()
     sym = T === Float64 ? :hdp_mlp_solve_f64 : :hdp_mlp_solve_f32
