@@ -243,7 +243,8 @@ def run_ours(args, rank, world, local_rank):
         e2e = n_total * args.steps / e2e_s
         coord_steps_per_s_gpu = (n_local * args.steps * PATH_STEPS_PER_SOLVE * D) / (dev_ms * 1e-3)
         achieved = coord_steps_per_s_gpu * I64_PER_COORD_STEP
-        cpu = cpu_baseline(H, prob, alg)
+        # reported baseline, rank 0 at N=1 only (keeps multi-GPU runs short)
+        cpu = cpu_baseline(H, prob, alg) if world == 1 else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,

@@ -216,12 +216,6 @@ __device__ HDP_NOINLINE Feat<T> em_step_t(Ctx<T, G>& c, const XAcc<T>& src, cons
     // of a group may run different trip counts.
     const int nfull = d / VEC;
     int p = lane;
-#ifdef HDP_EM_UNROLL2
-    for (; p + G < nfull; p += 2 * G) { // two independent vec-groups per trip: more ILP, more registers
-        body(p, FullTag{});
-        body(p + G, FullTag{});
-    }
-#endif
     for (; p < nfull; p += G) body(p, FullTag{});
     if (p < nvec) body(p, PartTag{});
     c.nb += nb;

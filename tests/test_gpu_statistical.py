@@ -88,3 +88,25 @@ def test_full_size_c4_nonlocal_fisher_smaller_levels(H, O, handle):
     sm, k2 = alg.mc_sample._descriptor(d)
     uo, info = O.ml_picard(pb, sm, alg.M, alg.L, alg.K, prob.x, O.Rng.philox(3, np.float64, False))
     assert abs(ua[0] - uo) <= 1e-9 * abs(uo)
+
+
+def test_full_size_c4_nonlocal_fisher_L5(H, handle):
+    """BASELINE C4 at its full size (non-local Fisher–KPP d=10, UniformSampling, M=4, K=10, L=5:
+    45 384 692 path-steps + 229 267 720 sampler calls per solve; the CPU oracle needs ~100 s for it, so
+    the full size is checked through size-independent properties): the result does not depend on how the
+    tree is cut into work units (three very different cuts agree to 1e-12 with identical reflection
+    counts), is bitwise reproducible, and sits where the L=4 oracle-checked value does."""
+    d = 10
+    prob = H.PIDEProblem(0.0, 0.1, np.zeros(d), (0.0, 0.5), H.ExpSumSq(1.0), H.FNLFisher(),
+                         neumann_bc=(np.full(d, -0.5), np.full(d, 0.5)))
+    alg = H.MLP(M=4, L=5, K=10, mc_sample=H.UniformSampling(np.full(d, -0.5), np.full(d, 0.5)))
+    ua, sa = H._ml_picard_batch(prob, alg, n_solves=1, seed=11, handle=handle)
+    ub, sb = H._ml_picard_batch(prob, alg, n_solves=1, seed=11, target_units=3000000, handle=handle)
+    uc, sc = H._ml_picard_batch(prob, alg, n_solves=1, seed=11, target_units=150000, handle=handle)
+    ud, sd = H._ml_picard_batch(prob, alg, n_solves=1, seed=11, handle=handle)
+    assert sa["path_steps"] == 45384692 and sa["sampler_calls"] == 229267720
+    assert len({sa["n_units"], sb["n_units"], sc["n_units"]}) == 3
+    assert sa["bounces"] == sb["bounces"] == sc["bounces"] == sd["bounces"] > 0
+    assert abs(ua[0] - ub[0]) <= 1e-12 * abs(ua[0]) and abs(ua[0] - uc[0]) <= 1e-12 * abs(ua[0])
+    assert ua[0] == ud[0]
+    assert 1.15 < ua[0] < 1.28
