@@ -16,6 +16,6 @@ from .kinds import (ConstCoef, LinearCoef, SumSq, InvSumSq, ExpSumSq, MinCoord, 
 from .sampling import UniformSampling, NormalSampling, NoSampling, _integrate
 from .problems import PIDEProblem, ParabolicPDEProblem, PIDESolution
 from .mlp import MLP, solve, mlp_counts, _ml_picard_batch
-from .sde import _reflect, sde_loop
+from .sde import _reflect, sde_loop, _mlt_sde_loop
 
 __all__ = [n for n in dir() if not n.startswith("__")]

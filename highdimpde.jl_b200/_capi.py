@@ -117,6 +117,8 @@ SYMBOLS = {
     "hdp_mc_sample_f32": (_i, [_H, _VP, _VP, _i, _i, _i, _SP, _u64, _VP, _u]),
     "hdp_sde_loop_f64": (_i, [_H, _PP, _VP, _VP, _i, _i, C.c_double, _VP, _SP, _u64, _VP, _SP, _VP, _i, _i, _u]),
     "hdp_sde_loop_f32": (_i, [_H, _PP, _VP, _VP, _i, _i, C.c_float, _VP, _SP, _u64, _VP, _SP, _VP, _i, _i, _u]),
+    "hdp_mlt_sde_loop_f64": (_i, [_H, _PP, _VP, _VP, _i, C.c_double, C.c_double, _u64, _VP, _u]),
+    "hdp_mlt_sde_loop_f32": (_i, [_H, _PP, _VP, _VP, _i, C.c_float, C.c_float, _u64, _VP, _u]),
     "hdp_mlp_counts_get": (_i, [_i, _i, _i, _i, _i, C.POINTER(hdp_mlp_counts)]),
     "hdp_mlp_solve_f64": (_i, [_H, _PP, C.POINTER(hdp_mlp_cfg), _VP, _VP, C.POINTER(hdp_mlp_stats)]),
     "hdp_mlp_solve_f32": (_i, [_H, _PP, C.POINTER(hdp_mlp_cfg), _VP, _VP, C.POINTER(hdp_mlp_stats)]),

@@ -6,6 +6,7 @@
 // Replaces: sde_loop! (src/DeepSplitting.jl:153-166), _reflect
 // (src/reflect.jl:8-82), UniformSampling/NormalSampling call operators
 // (src/MCSample.jl:28-33, 63-71).
+#include <string.h>
 #include "hdp_host_util.h"
 
 using namespace hdp;
@@ -124,13 +125,15 @@ template <typename T, bool ALIGNED, bool INJECT>
 __global__ void __launch_bounds__(128)
 sde_loop_kernel(DevProblem<T> pb, T* __restrict__ y0, T* __restrict__ y1, size_t n_el, int nsteps, T dt,
                 DevSampler<T> x0s, const T* __restrict__ x0_inject, u64 seed, const T* __restrict__ dW,
-                DevSampler<T> mc, T* __restrict__ z, int K, int* flags, unsigned long long* bounce_ctr)
+                DevSampler<T> mc, T* __restrict__ z, int K, int* flags, unsigned long long* bounce_ctr,
+                int mlp_assoc)
 {
     constexpr int VEC = Tr<T>::VEC;
     const int d = pb.d;
     const size_t nv = (n_el + VEC - 1) / VEC;
     const T sq = sqrt_rn(dt);
     const bool has_bc = pb.has_bc != 0;
+    const int stream = mlp_assoc ? HDP_STREAM_STEP : HDP_STREAM_SDE;
     const bool mu_lin = pb.mu_kind == HDP_COEF_LINEAR, sg_lin = pb.sigma_kind == HDP_COEF_LINEAR;
     const T mudt_c = mul_rn(pb.mu_c, dt), sgsq_c = mul_rn(pb.sigma_c, sq);
     bool bad = false;
@@ -167,14 +170,15 @@ sde_loop_kernel(DevProblem<T> pb, T* __restrict__ y0, T* __restrict__ y1, size_t
         for (int st = 0; st < nsteps; ++st) {
             Vec<T> xi;
             if constexpr (INJECT) xi = load_el<T, ALIGNED>(dW + (size_t)st * n_el, q0, n_el);
-            else xi = draw_vec<T>(seed, HDP_STREAM_SDE, (u64)st, (uint32_t)v, true);
+            else xi = draw_vec<T>(seed, stream, (u64)st, (uint32_t)v, true);
             prev = cur; // y0 .= y1 (:159)
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
                 const T x = prev.v[e];
                 const T mudt = mu_lin ? mul_rn(mul_rn(pb.mu_c, x), dt) : mudt_c;
                 const T sgsq = sg_lin ? mul_rn(mul_rn(pb.sigma_c, x), sq) : sgsq_c;
-                cur.v[e] = add_rn(add_rn(x, mudt), mul_rn(sgsq, xi.v[e])); // :160 (y0 + μ*dt) + (σ*sq)*dW
+                if (mlp_assoc) cur.v[e] = add_rn(x, add_rn(mudt, mul_rn(sgsq, xi.v[e]))); // src/MLP.jl:417
+                else cur.v[e] = add_rn(add_rn(x, mudt), mul_rn(sgsq, xi.v[e])); // :160 (y0 + μ*dt) + (σ*sq)*dW
             }
             if (has_bc) reflect_vec<T, 1, false>(cur, lo, hi, 0u, nb_total); // :161-163
         }
@@ -342,7 +346,7 @@ int mc_sample_impl(hdp_handle h, T* z, const T* y1, int d, int B, int K, const h
 template <typename T>
 int sde_loop_impl(hdp_handle h, const hdp_problem* prob, T* y0, T* y1, int B, int nsteps, T dt, const T* ts,
                   const hdp_sampler* x0_sampler, uint64_t seed, const T* dWall_inject,
-                  const hdp_sampler* mc, T* z, int K, int normal_mode, unsigned mem_flags)
+                  const hdp_sampler* mc, T* z, int K, int normal_mode, unsigned mem_flags, int mlp_assoc = 0)
 {
     (void)ts; // every supported coefficient kind is time-independent
     if (!h || !prob || !y0 || !y1 || B < 0 || nsteps < 0) return HDP_ERR_BAD_ARG;
@@ -388,7 +392,7 @@ int sde_loop_impl(hdp_handle h, const hdp_problem* prob, T* y0, T* y1, int B, in
 #define LAUNCH(AL, INJ)                                                                                  \
     sde_loop_kernel<T, AL, INJ><<<grid, threads, 0, h->stream>>>(pb, dy0, dy1, n_el, nsteps, dt, x0s,    \
                                                                  nullptr, seed, ddw, mcs, dz, K,          \
-                                                                 h->d_flags, h->d_ctr + 1)
+                                                                 h->d_flags, h->d_ctr + 1, mlp_assoc)
     HDP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     if (al && ddw) LAUNCH(true, true);
     else if (al) LAUNCH(true, false);
@@ -408,7 +412,49 @@ int sde_loop_impl(hdp_handle h, const hdp_problem* prob, T* y0, T* y1, int B, in
     return HDP_OK;
 }
 
+// `_mlt_sde_loop!`: one step with the MLP association; x2 receives the result, x is untouched
+template <typename T>
+int mlt_sde_loop_impl(hdp_handle h, const hdp_problem* prob, T* x2, const T* x, int B, T s, T t, uint64_t seed,
+                      const T* inject, unsigned mem_flags)
+{
+    if (!h || !prob || !x2 || !x || B < 0) return HDP_ERR_BAD_ARG;
+    const size_t n_el = (size_t)prob->d * (size_t)B;
+    if (n_el == 0) return HDP_OK;
+    {
+        // x2 <- x, then step x2 in place; the kernel's y0 output (the start state) goes to scratch
+        std::lock_guard<std::mutex> lk(h->mu);
+        DeviceGuard g(h->device);
+        if (mem_flags & HDP_MEM_DEVICE)
+            HDP_CUDA(h, cudaMemcpyAsync(x2, x, n_el * sizeof(T), cudaMemcpyDeviceToDevice, h->stream));
+        else memcpy(x2, x, n_el * sizeof(T));
+    }
+    T* y0 = nullptr;
+    std::vector<T> y0_host;
+    if (mem_flags & HDP_MEM_DEVICE) {
+        std::lock_guard<std::mutex> lk(h->mu);
+        DeviceGuard g(h->device);
+        y0 = (T*)ensure(h, hdp_context::B_H, n_el * sizeof(T));
+        if (!y0) return HDP_ERR_ALLOC;
+    } else {
+        y0_host.resize(n_el);
+        y0 = y0_host.data();
+    }
+    return sde_loop_impl<T>(h, prob, y0, x2, B, 1, (T)(t - s), nullptr, nullptr, seed, inject, nullptr, nullptr, 0,
+                            HDP_NORMAL_DEFAULT, mem_flags & ~(unsigned)HDP_ASYNC, /*mlp_assoc=*/1);
+}
+
 } // namespace
+
+extern "C" int hdp_mlt_sde_loop_f64(hdp_handle h, const hdp_problem* prob, double* x2, const double* x, int B,
+                                    double s, double t, uint64_t seed, const double* normals_inject, unsigned mem_flags)
+{
+    return mlt_sde_loop_impl<double>(h, prob, x2, x, B, s, t, seed, normals_inject, mem_flags);
+}
+extern "C" int hdp_mlt_sde_loop_f32(hdp_handle h, const hdp_problem* prob, float* x2, const float* x, int B,
+                                    float s, float t, uint64_t seed, const float* normals_inject, unsigned mem_flags)
+{
+    return mlt_sde_loop_impl<float>(h, prob, x2, x, B, s, t, seed, normals_inject, mem_flags);
+}
 
 extern "C" int hdp_reflect_f64(hdp_handle h, const double* a, const double* b, double* out, int d, int B,
                                const double* lo, const double* hi, int bounds_are_scalar,

@@ -79,3 +79,28 @@ def sde_loop(prob, y0, y1, nsteps, dt, *, ts=None, dWall=None, seed=0, mc_sample
                        capi.np_ptr(z), K, capi.HDP_NORMAL_DEFAULT, capi.HDP_MEM_HOST))
     del keep, keep2, keep3
     return y0, y1
+
+
+def _mlt_sde_loop(x2, x, s, t, prob, *, normals=None, seed=0, handle=None):
+    """_mlt_sde_loop!(x2, x, s, t, prob, neumann_bc) (src/MLP.jl:406-421): one Euler–Maruyama step
+    s -> t of the MLP recursion (x2 = x + (μ*dt + σ*sqrt(dt)*ξ), then `_reflect`), mutating x2.
+    x, x2: d-vectors or d×B column-major matrices; normals: optional injected ξ (`randn!(x2)`)."""
+    h = handle or capi.default_handle()
+    dt_ = x.dtype
+    if dt_ not in (np.float32, np.float64) or x2.dtype != dt_ or x2.shape != x.shape:
+        raise TypeError("x, x2 must have the same float32/float64 dtype and shape")
+    xa = np.asarray(x, order="F")
+    if not (x2.flags.f_contiguous or x2.ndim == 1):
+        raise ValueError("x2 must be column-major")
+    d = x.shape[0]
+    B = 1 if x.ndim == 1 else int(np.prod(x.shape[1:]))
+    pb, keep = prob.to_c()
+    inj = None if normals is None else np.asarray(normals, dtype=dt_, order="F")
+    if dt_ == np.float64:
+        fn, a, b = h.lib.hdp_mlt_sde_loop_f64, C.c_double(s), C.c_double(t)
+    else:
+        fn, a, b = h.lib.hdp_mlt_sde_loop_f32, C.c_float(s), C.c_float(t)
+    capi.check(h.h, fn(h.h, C.byref(pb), capi.np_ptr(x2), capi.np_ptr(xa), B, a, b, int(seed), capi.np_ptr(inj),
+                       capi.HDP_MEM_HOST))
+    del keep
+    return x2

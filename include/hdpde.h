@@ -325,6 +325,20 @@ int hdp_sde_loop_f32(hdp_handle h, const hdp_problem* prob, float* y0, float* y1
                      int normal_mode, unsigned mem_flags);
 
 /* ------------------------------------------------------------------ */
+/* One Euler–Maruyama step of the MLP recursion, stand-alone              */
+/* replaces `_mlt_sde_loop!(x2, x, s, t, prob, neumann_bc)` (src/MLP.jl:406-421):
+ * x2 = x + (μ(x,p,t)*dt + σ(x,p,t)*sqrt(dt)*ξ), dt = t - s, then `_reflect(x, x2, bc...)`.
+ * Note the association differs from the DeepSplitting step (hdp_sde_loop_*).
+ * x, x2: d×B (B independent columns; the reference is B = 1).
+ * normals_inject: nullable d×B standard normals (`randn!(x2)`, :416); NULL => Philox
+ * (stream HDP_STREAM_STEP, ordinal 0, draw index = linear element index).   */
+/* ------------------------------------------------------------------ */
+int hdp_mlt_sde_loop_f64(hdp_handle h, const hdp_problem* prob, double* x2, const double* x, int B,
+                         double s, double t, uint64_t seed, const double* normals_inject, unsigned mem_flags);
+int hdp_mlt_sde_loop_f32(hdp_handle h, const hdp_problem* prob, float* x2, const float* x, int B,
+                         float s, float t, uint64_t seed, const float* normals_inject, unsigned mem_flags);
+
+/* ------------------------------------------------------------------ */
 /* K3: multilevel Picard                                               */
 /* replaces `_ml_picard` / `_ml_picard_mlt` / `_ml_picard_call`
  * (src/MLP.jl:102-388) as called from solve(::MLP) (src/MLP.jl:68-98),

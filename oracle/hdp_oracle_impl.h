@@ -368,6 +368,9 @@ static void FN(mlp_sample)(FN(mlp_ctx)* c, REAL* x3, const REAL* x2)
     c->n_samp++;
 }
 
+/* public single step for unit tests: normals = ξ (d values), x2_out = result */
+int FN(hdp_oracle_mlt_sde_loop)(const hdp_problem* pb, const REAL* x, REAL s, REAL t, const REAL* normals, REAL* x2_out);
+
 static int64_t FN(ipow)(int M, int e)
 {
     int64_t r = 1;
@@ -530,6 +533,26 @@ static void FN(ctx_free)(FN(mlp_ctx)* c)
 {
     free(c->tmp);
     free(c->tmp_d);
+}
+
+typedef struct FN(one_step_rng) { const REAL* xi; } FN(one_step_rng);
+static void FN(one_step_normals)(void* c, double* out, int d)
+{
+    const REAL* xi = ((FN(one_step_rng)*)c)->xi;
+    for (int i = 0; i < d; ++i) out[i] = (double)xi[i];
+}
+int FN(hdp_oracle_mlt_sde_loop)(const hdp_problem* pb, const REAL* x, REAL s, REAL t, const REAL* normals, REAL* x2_out)
+{
+    FN(one_step_rng) st = {normals};
+    hdp_oracle_rng rng = {&st, NULL, FN(one_step_normals), NULL, 0};
+    FN(mlp_ctx) c;
+    int rc = FN(ctx_init)(&c, pb, NULL, 1, 1, &rng);
+    if (rc == HDP_OK) {
+        FN(mlt_sde_loop)(&c, x2_out, x, s, t);
+        rc = c.err;
+    }
+    FN(ctx_free)(&c);
+    return rc;
 }
 
 /* solve(prob, alg::MLP; multithreading=false) → `_ml_picard` (src/MLP.jl:84-98).

@@ -244,6 +244,21 @@ def ml_picard_mlt(pb_struct, sampler_struct, M, L, K, x, nthreads, rngs, paralle
     return u[0].item(), info
 
 
+def mlt_sde_loop(pb_struct, x, s, t, normals):
+    """_mlt_sde_loop!(x2, x, s, t, prob, neumann_bc) (src/MLP.jl:406-421) for one d-vector."""
+    x = np.ascontiguousarray(x)
+    dt = x.dtype
+    xi = np.ascontiguousarray(normals, dtype=dt)
+    out = np.empty_like(x)
+    real = C.c_double if dt == np.float64 else C.c_float
+    fn = getattr(lib(), "hdp_oracle_mlt_sde_loop" + _sfx(dt))
+    fn.argtypes = [C.c_void_p, C.c_void_p, real, real, C.c_void_p, C.c_void_p]
+    rc = fn(C.byref(pb_struct), _p(x), real(s), real(t), _p(xi), _p(out))
+    if rc != 0:
+        raise ValueError(f"oracle mlt_sde_loop rc={rc}")
+    return out
+
+
 def sde_loop(pb_struct, y1, nsteps, dt, dWall, x0_sampler_struct=None, x0_raw=None):
     """sde_loop!(y0, y1, dWall) (src/DeepSplitting.jl:153-166). Returns (y0, y1, iters_per_step)."""
     y1 = np.array(y1, order="F", copy=True)

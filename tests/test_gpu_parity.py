@@ -295,3 +295,35 @@ def test_solve_dropin_surface(H, handle):
         assert abs(sol2.us[-1] - 40.05) / 40.05 < 0.1
     finally:
         H.set_default_handle(None)
+
+
+# ------------------------------ `_mlt_sde_loop!` stand-alone ----------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_mlt_sde_loop_single_step_matches_oracle(H, O, handle, dtype):
+    """src/MLP.jl:406-421: x2 = x + (μ*dt + σ*sqrt(dt)*ξ) — the MLP association, which differs from the
+    DeepSplitting step — followed by the Vector `_reflect`."""
+    rng = np.random.default_rng(12)
+    d, B = 10, 37
+    bc = (np.linspace(-1.0, -0.5, d), np.linspace(0.5, 1.0, d))
+    prob = H.ParabolicPDEProblem(H.LinearCoef(0.3), 0.8, np.zeros(d, dtype=dtype), (0.0, 1.0), g=H.SumSq(), f=H.FZero(),
+                                 neumann_bc=bc)
+    x = np.asfortranarray(rng.uniform(-0.5, 0.5, (d, B)).astype(dtype))
+    xi = np.asfortranarray(rng.standard_normal((d, B)).astype(dtype))
+    x2 = np.empty_like(x, order="F")
+    H._mlt_sde_loop(x2, x, 0.1, 0.45, prob, normals=xi, handle=handle)
+    pb, _k = prob.to_c()
+    tol = 1e-12 if dtype == np.float64 else 2e-6
+    for j in range(B):
+        want = O.mlt_sde_loop(pb, x[:, j].copy(), 0.1, 0.45, xi[:, j].copy())
+        assert np.max(np.abs(x2[:, j] - want)) <= tol
+    # without bc: the same IEEE operations in the same order, bit-equal
+    prob_nb = H.ParabolicPDEProblem(H.LinearCoef(0.3), 0.8, np.zeros(d, dtype=dtype), (0.0, 1.0), g=H.SumSq(), f=H.FZero())
+    H._mlt_sde_loop(x2, x, 0.1, 0.45, prob_nb, normals=xi, handle=handle)
+    pbn, _k = prob_nb.to_c()
+    want = np.stack([O.mlt_sde_loop(pbn, x[:, j].copy(), 0.1, 0.45, xi[:, j].copy()) for j in range(B)], axis=1)
+    assert np.array_equal(x2, want)
+    # in-register normals: the same numbers hdp_tape_fill reports
+    H._mlt_sde_loop(x2, x, 0.1, 0.45, prob_nb, seed=3, handle=handle)
+    z = handle.tape_fill(dtype, H.capi.HDP_STREAM_STEP, True, 3, 0, 1, d * B).reshape(B, d).T
+    want = np.stack([O.mlt_sde_loop(pbn, x[:, j].copy(), 0.1, 0.45, np.ascontiguousarray(z[:, j])) for j in range(B)], axis=1)
+    assert np.array_equal(x2, want)
