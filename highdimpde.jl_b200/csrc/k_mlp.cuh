@@ -516,9 +516,12 @@ __device__ __forceinline__ void unit_item(Ctx<T, G>& c, const MlpParams<T>& P, u
     }
 }
 
-// value of one explicit node from its units' partial sums and its explicit sites
+// value of one explicit node from its units' partial sums and its explicit sites.
+// `nl` lanes (a warp on the device, 1 in the host emulation) share the node: they stride over
+// its units and over its explicit sites, then the per-level sums are butterfly-reduced — the
+// root of a deeply cut tree has thousands of children, one thread would walk them serially.
 template <typename T>
-__device__ __forceinline__ void combine_item(const MlpParams<T>& P, int off, u64 item)
+__device__ __forceinline__ void combine_item(const MlpParams<T>& P, int off, u64 item, int lane, int nl)
 {
     const int solve = (int)(item % (u64)P.n_solves);
     const int nidx = P.nodes_by_depth[off + (int)(item / (u64)P.n_solves)];
@@ -528,7 +531,8 @@ __device__ __forceinline__ void combine_item(const MlpParams<T>& P, int off, u64
     const T* val = P.value + (u64)solve * P.n_nodes;
     const T* feat = P.feat + (u64)solve * P.n_points;
     T result;
-    if (nd.unit_end - nd.unit_begin == 1 && (P.unit_tag[nd.unit_begin] >> 4) == UNIT_WHOLE) {
+    if (nd.unit_end - nd.unit_begin == 1 && nd.site_end == nd.site_begin &&
+        (P.unit_tag[nd.unit_begin] >> 4) == UNIT_WHOLE) {
         result = (T)part[nd.unit_begin];
     } else {
         const T s = nd.time_site < 0 ? pb.t0 : P.site_r[(u64)solve * P.n_sites + nd.time_site];
@@ -536,13 +540,17 @@ __device__ __forceinline__ void combine_item(const MlpParams<T>& P, int off, u64
 #pragma unroll
         for (int l = 0; l < kMaxL; ++l) Bl[l] = (T)0;
         T Gs = (T)0;
-        for (int u = nd.unit_begin; u < nd.unit_end; ++u) {
+        for (int u = nd.unit_begin + lane; u < nd.unit_end; u += nl) {
             const int tag = P.unit_tag[u];
             const T v = (T)part[u];
             if ((tag >> 4) == UNIT_G) Gs += v;
-            else Bl[tag & 15] += v;
+            else {
+#pragma unroll
+                for (int l = 0; l < kMaxL; ++l)
+                    if (l == (tag & 15)) Bl[l] += v;
+            }
         }
-        for (int si = nd.site_begin; si < nd.site_end; ++si) {
+        for (int si = nd.site_begin + lane; si < nd.site_end; si += nl) {
             const PlanSite st = P.sites[si];
             const int l = st.l;
             const int32_t* ch = P.children + st.child0;
@@ -570,14 +578,24 @@ __device__ __forceinline__ void combine_item(const MlpParams<T>& P, int off, u64
                 if (l >= 2) term = term - f_eval<T>(pb, f2, (T)0, b4, (T)0);
                 for (int h = 0; h < P.K; ++h) b3 += term;
             }
-            Bl[l] += b3 / (T)P.K;
+            const T add = b3 / (T)P.K;
+#pragma unroll
+            for (int q = 0; q < kMaxL; ++q)
+                if (q == l) Bl[q] += add;
+        }
+        if (nl > 1) {
+#pragma unroll
+            for (int l = 0; l < kMaxL; ++l) Bl[l] = gsum<T, 32>(Bl[l], 0xffffffffu);
+            Gs = gsum<T, 32>(Gs, 0xffffffffu);
         }
         T a = (T)0;
-        for (int l = 0; l < nd.lv; ++l) a += ((pb.t1 - s) * Bl[l]) / (T)P.Mpow[nd.lv - l];
+#pragma unroll
+        for (int l = 0; l < kMaxL; ++l)
+            if (l < nd.lv) a += ((pb.t1 - s) * Bl[l]) / (T)P.Mpow[nd.lv - l];
         const T a2 = Gs / (T)P.Mpow[nd.lv];
         result = a + a2;
     }
-    P.value[(u64)solve * P.n_nodes + nidx] = result;
+    if (lane == 0) P.value[(u64)solve * P.n_nodes + nidx] = result;
 }
 
 // points[solve][0] <- x0 (padded with zeros)
@@ -641,9 +659,9 @@ __global__ void __launch_bounds__(128, HDP_MLP_MINBLOCKS) mlp_units_kernel(const
 template <typename T>
 __global__ void __launch_bounds__(128) mlp_combine_kernel(const __grid_constant__ MlpParams<T> P, int off, int count)
 {
-    const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 gid = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; // one warp per (node, solve)
     if (gid >= (u64)count * (u64)P.n_solves) return;
-    combine_item<T>(P, off, gid);
+    combine_item<T>(P, off, gid, threadIdx.x & 31, 32);
 }
 #endif // HDP_HOST_EMU
 

@@ -326,7 +326,7 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
         const int off = plan->node_depth_off[dep];
         const int cnt = plan->node_depth_off[dep + 1] - off;
         if (cnt == 0) continue;
-        uint64_t tot = (uint64_t)cnt * n_solves;
+        uint64_t tot = (uint64_t)cnt * n_solves * 32; // one warp per (node, solve)
         int gc = (int)((tot + 127) / 128);
         if (um) { // f is applied in the combine too: the user module's build of it
             int off_ = off, cnt_ = cnt;

@@ -89,7 +89,7 @@ static int emu_solve(const hdp_problem* prob, const hdp_mlp_cfg* cfg, const T* x
     if (c.bad) flags[0] = 1;
     for (int dep = plan.max_depth; dep >= 0; --dep) {
         int off = plan.node_depth_off[dep], cnt = plan.node_depth_off[dep + 1] - off;
-        for (u64 it = 0; it < (u64)cnt * n_solves; ++it) combine_item<T>(P, off, it);
+        for (u64 it = 0; it < (u64)cnt * n_solves; ++it) combine_item<T>(P, off, it, 0, 1);
     }
     for (int i = 0; i < n_solves; ++i) u_out[i] = value[(size_t)i * P.n_nodes];
     if (stats) {
