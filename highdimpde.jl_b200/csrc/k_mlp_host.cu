@@ -198,7 +198,9 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
     const double resident_groups = (double)sms * bps * block / G;
     // units per resident lane group: enough for the LPT-ordered dynamic fetch to balance, few
     // enough that the replicated expand/combine passes and the all-reduce stay small
-    double oversub = 8.0;
+    // (measured, C4 L=5: 1 GPU best at 8; 8 GPUs: 2 per rank gives 0.9 M units and 3.7x, 8 per rank
+    // cuts one level deeper — 16 M units — and the all-reduce + combine then dominate)
+    double oversub = nranks > 1 ? 2.0 : 8.0;
     if (const char* ev = getenv("HDP_MLP_OVERSUB")) oversub = std::max(1.0, atof(ev));
     double target = cfg->target_units > 0 ? (double)cfg->target_units : resident_groups * oversub * nranks;
     const double total_work = tab.W[L] * (double)n_solves;
