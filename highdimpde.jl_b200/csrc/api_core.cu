@@ -298,11 +298,12 @@ __global__ void tape_fill_kernel(T* __restrict__ out, int stream, int want_norma
                                  u64 n_ord, int width)
 {
     constexpr int VEC = Tr<T>::VEC;
+    if constexpr (sizeof(T) == 8) tables_init();
     const u64 ngroups = ((u64)width + VEC - 1) / VEC;
     const u64 total = n_ord * ngroups;
     for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (u64)gridDim.x * blockDim.x) {
         u64 o = w / ngroups;
-        uint32_t grp = (uint32_t)(w % ngroups);
+        u64 grp = w % ngroups;
         Vec<T> v = draw_vec<T>(seed, stream, ord0 + o, grp, want_normal != 0);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
@@ -324,6 +325,9 @@ static int tape_fill_impl(hdp_handle h, T* out, int stream, int want_normal, int
     DeviceGuard g(h->device);
     size_t n = (size_t)n_ord * (size_t)width;
     if (n == 0) return HDP_OK;
+    if (stream < HDP_STREAM_TIME || stream > HDP_STREAM_MC ||
+        !draw_address_ok(stream, ord0 + n_ord, ((u64)width + Tr<T>::VEC - 1) / Tr<T>::VEC))
+        return set_err(h, HDP_ERR_BAD_ARG, "tape_fill: ordinal or width beyond the addressable range of stream %d", stream);
     T* d = (T*)ensure(h, hdp_context::B_A, n * sizeof(T));
     if (!d) return HDP_ERR_ALLOC;
     int blocks = h->prop.multiProcessorCount * 8;

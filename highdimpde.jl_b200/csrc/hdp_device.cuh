@@ -93,33 +93,53 @@ __device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, 
 __device__ __forceinline__ float sqrt_rn(float a) { return __fsqrt_rn(a); }
 
 // ---------------------------------------------------------------------
-// Philox4x32-10.  ctr = (ordinal_lo, ordinal_hi, group, stream),
-// key = (seed_lo, seed_hi).  Addressing by consumption ordinal — never by
-// thread id — makes every draw independent of launch geometry and GPU count.
+// Philox4x32-10 with a FIXED key; the 64-bit seed travels in the counter:
+//   ctr = (w0, w1, seed_lo, seed_hi),   (w0, w1) = draw_address(stream, ordinal, group)
+// Addressing by consumption ordinal — never by thread id — makes every draw independent of
+// launch geometry and GPU count.  The fixed key makes the ten round keys immediates of the
+// two XORs of a round (2 IMAD.WIDE + 2 LOP3 per round, no key registers), whatever seed each
+// lane group of a warp works on.  The word that varies fastest inside a loop (the group
+// inside a path-step, the step inside `sde_loop!`) sits in w1, which enters the first round
+// only through an XOR: the compiler hoists the loop-invariant multiplies of rounds 1–3.
 // ---------------------------------------------------------------------
 struct Philox4 { uint32_t w[4]; };
 
-__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                                 uint32_t k0, uint32_t k1)
+constexpr uint32_t kPhiloxKey0 = 0xA4093822u, kPhiloxKey1 = 0x299F31D0u; // fractional digits of pi
+
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3)
 {
-#ifndef HDP_HOST_EMU
-    // keep the round keys as immediates added to the two seed registers: without this the
-    // compiler hoists the 18 bumped keys out of the caller's coordinate loop and spills them
-    asm volatile("" : "+r"(k0), "+r"(k1));
-#endif
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
+        const uint32_t k0 = kPhiloxKey0 + (uint32_t)r * 0x9E3779B9u, k1 = kPhiloxKey1 + (uint32_t)r * 0xBB67AE85u;
         const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
         const uint32_t n0 = hi1 ^ c1 ^ k0;
         const uint32_t n2 = hi0 ^ c3 ^ k1;
         c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
     }
     Philox4 o;
     o.w[0] = c0; o.w[1] = c1; o.w[2] = c2; o.w[3] = c3;
     return o;
+}
+
+// (w0, w1) of a draw.  Streams of the MLP tree (TIME, STEP, SAMPLER): ordinal < 2^40 (the
+// reference's consumption ordinal), group < 2^21 (vec-group inside a point).  Streams of the
+// batched loop (SDE, X0, MC): ordinal < 2^24 (step / sample index), group < 2^37 (vec-group
+// of the whole d×B array).  The host checks the limits (draw_address_ok).
+__device__ __forceinline__ void draw_address(int stream, u64 ord, u64 group, uint32_t& w0, uint32_t& w1)
+{
+    if (stream <= HDP_STREAM_SAMPLER) {
+        w0 = (uint32_t)ord;
+        w1 = (uint32_t)(ord >> 32) | ((uint32_t)group << 8) | ((uint32_t)stream << 29);
+    } else {
+        w0 = (uint32_t)group;
+        w1 = (uint32_t)(group >> 32) | ((uint32_t)ord << 5) | ((uint32_t)stream << 29);
+    }
+}
+__host__ __device__ inline bool draw_address_ok(int stream, u64 n_ord, u64 n_group)
+{
+    if (stream <= HDP_STREAM_SAMPLER) return n_ord <= ((u64)1 << 40) && n_group <= ((u64)1 << 21);
+    return n_ord <= ((u64)1 << 24) && n_group <= ((u64)1 << 37);
 }
 
 // ---------------------------------------------------------------------
@@ -130,12 +150,7 @@ __device__ __forceinline__ double hilo2d(uint32_t hi, uint32_t lo) { return __hi
 __device__ __forceinline__ uint32_t d2hi(double x) { return (uint32_t)__double2hiint(x); }
 __device__ __forceinline__ uint32_t d2lo(double x) { return (uint32_t)__double2loint(x); }
 __device__ __forceinline__ float u2f(uint32_t b) { return __uint_as_float(b); }
-__device__ __forceinline__ double rcp_approx(double x)
-{
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    return y;
-}
+__device__ __forceinline__ uint32_t f2u(float x) { return __float_as_uint(x); }
 __device__ __forceinline__ double rsqrt_approx(double x)
 {
     double y;
@@ -144,6 +159,7 @@ __device__ __forceinline__ double rsqrt_approx(double x)
 }
 __device__ __forceinline__ double xfma(double a, double b, double c) { return fma(a, b, c); }
 __device__ __forceinline__ float xfma(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.L1 [%0];" ::"l"(p)); }
 // MUFU approximations with flush-to-zero: the arguments are never denormal here, and the
 // non-ftz forms carry denormal fix-up code (extra FSETP/FMUL per call)
 __device__ __forceinline__ float rsq_approx(float x)
@@ -179,69 +195,121 @@ __device__ __forceinline__ float cos_approx(float x)
 //      u = that - 1 in [0,1)                       (one exact DADD, no I2F)
 //      u1 = that - (1 - 2^-53) = (k + 1/2)*2^-52 in (0,1)   (Box–Muller radius)
 // Box–Muller: z0 = R cos(T), z1 = R sin(T), R = sqrt(-2 ln u1), T = 2π k2 / 2^52.
-//      -2 ln u1: exponent/mantissa split, ln(m) = 2 atanh((m-1)/(m+1)), MUFU.RCP64H seed
-//      + 2 Newton steps for the quotient, degree-8 series — no special cases since
-//      u1 is a normal number in (0,1).
-//      sqrt: MUFU.RSQ64H seed + 1 Newton step + Heron correction.
-//      sin/cos: octant from the top 3 bits of k2 (exact integer range reduction, odd
-//      octants mirrored in integers), Taylor polynomials on [0, π/4].
+//   Both transcendentals are table driven; the tables (6 KB, hdp_tables.h) are staged in
+//   shared memory by tables_init() at kernel start.
+//   -2 ln u1: u1 = 2^e * m, m in [1,2).  idx = m rounded to 7 fraction bits (0..128) selects
+//      rc ≈ 1/(1 + idx/128) and lm2 = -2 ln(1/rc) (shifted by ln 2 for idx >= 54, so the
+//      entries next to u1 = 1 are exactly zero and nothing cancels there); r = fma(m, rc, -1),
+//      |r| <= 2^-8, log1p(r) by its degree-7 Taylor polynomial.  No special cases: u1 is a
+//      normal number in (0,1).  Agrees with glibc's log to 2 ulp.
+//   sqrt: MUFU.RSQ64H seed + 1 Newton step + Heron correction.
+//   sin/cos: the top 8 bits of k2 select (sin, cos) at the centre of a 1/256 turn, the other
+//      44 bits give the offset |δ| <= π/256 exactly; sin δ, cos δ − 1 by degree-5/6 Taylor
+//      polynomials and the angle-sum formulas.  No octant logic.
 // f32: 23-bit uniforms by the same trick; Box–Muller on the MUFU pipe.
 // ---------------------------------------------------------------------
 #ifndef HDP_HOST_EMU
-#define HDP_CONST static __constant__
+#define HDP_TABLE static __device__ const
 #else
-#define HDP_CONST static const
+#define HDP_TABLE static const
 #endif
-// atanh series 1/3 .. 1/19, Taylor sin (-1/3! .. -1/15!) and cos (-1/2! .. 1/16!)
-HDP_CONST double kAtanhC[9] = {1.0 / 3.0, 1.0 / 5.0, 1.0 / 7.0, 1.0 / 9.0, 1.0 / 11.0, 1.0 / 13.0, 1.0 / 15.0,
-                               1.0 / 17.0, 1.0 / 19.0};
-HDP_CONST double kSinC[7] = {-1.6666666666666666667e-01, 8.3333333333333333333e-03, -1.9841269841269841270e-04,
-                             2.7557319223985890653e-06, -2.5052108385441718775e-08, 1.6059043836821614599e-10,
-                             -7.6471637318198164759e-13};
-HDP_CONST double kCosC[8] = {-0.5, 4.1666666666666666667e-02, -1.3888888888888888889e-03, 2.4801587301587301587e-05,
-                             -2.7557319223985890653e-07, 2.0876756987868098979e-09, -1.1470745597729724714e-11,
-                             4.7794773323873852974e-14};
-HDP_CONST double kMisc[6] = {-4.638093627692599e-17, -1.3862943611198906, 4503601774854144.0, 4503599627370496.0,
-                             1.3951473992034527e-15, 0.99999999999999988898};
+#include "hdp_tables.h"
 
-__device__ __forceinline__ double neg2log_unit(double u)
+// Constants of the fp64 transform.  The five that need all 53 bits are handed to the draw
+// functions in a DrawK, which hot loops build once (draw_k_init) as opaque registers — left
+// to itself the compiler re-materialises each of them with two UMOVs per loop iteration.
+// The rest multiply small corrections: they are rounded to 21 significant bits so that they
+// encode as 32-bit immediates of DFMA.
+#define HDP_C5T 0x1.9999ap-3    /* 1/5   */
+#define HDP_C6T 0x1.55555p-3    /* 1/6   */
+#define HDP_C7T 0x1.24925p-3    /* 1/7   */
+#define HDP_C120T 0x1.11111p-7  /* 1/120 */
+#define HDP_C720T 0x1.6c16cp-10 /* 1/720 */
+#define HDP_TWO_LN2_LOT 0x1.abc9ep-55
+
+template <typename T> struct DrawK {};
+template <> struct DrawK<double> {
+    double c3, two_ln2, turn, c6, c24; // 1/3, 2 ln 2 (high part), 2π/2^52, 1/6, 1/24
+    uint32_t log_tab, sincos_tab;      // shared-window addresses of the tables
+};
+
+#ifndef HDP_HOST_EMU
+__shared__ double2 s_log_tab[129];
+__shared__ double2 s_sincos_tab[256];
+// every kernel that draws fp64 normals calls this first, with all threads of the block
+__device__ __forceinline__ void tables_init()
 {
-    uint32_t hi = d2hi(u);
-    const uint32_t lo = d2lo(u);
-    int e = (int)(hi >> 20) - 1023;                // u = 2^e * 1.f
-    hi = (hi & 0x000fffffu) | 0x3ff00000u;          // m in [1,2)
-    const uint32_t adj = hi >= 0x3ff6a09fu ? 1u : 0u; // m >= ~sqrt(2): halve
-    hi -= adj << 20;
-    e += (int)adj;
-    const double m = hilo2d(hi, lo);                // m in [~0.7071, ~1.4142)
-    const double f = m - 1.0;
-    const double dn = m + 1.0;
-    double r = rcp_approx(dn);
-    double t = xfma(-dn, r, 1.0);
-    r = xfma(r, t, r);
-    t = xfma(-dn, r, 1.0);
-    r = xfma(r, t, r);
-    const double sv = f * r;                        // s = (m-1)/(m+1), |s| <= 0.1716
-    const double s2 = sv * sv;
-    // atanh(s)/s - 1 = s2/3 + s2^2/5 + ... + s2^9/19
-    // even/odd split: two half-length Horner chains in s4 = s2^2 (shorter dependent latency)
-    const double s4 = s2 * s2;
-    double pe = kAtanhC[8];
-    pe = xfma(pe, s4, kAtanhC[6]);
-    pe = xfma(pe, s4, kAtanhC[4]);
-    pe = xfma(pe, s4, kAtanhC[2]);
-    pe = xfma(pe, s4, kAtanhC[0]);
-    double po = kAtanhC[7];
-    po = xfma(po, s4, kAtanhC[5]);
-    po = xfma(po, s4, kAtanhC[3]);
-    po = xfma(po, s4, kAtanhC[1]);
-    const double pl = xfma(po, s2, pe);
-    const double lm2 = xfma(sv * s2, pl, sv);       // atanh(s) = ln(m)/2
-    // e as a double without I2F: (2^52 + 2^31 + e) - (2^52 + 2^31)
-    const double ed = hilo2d(0x43300000u, (uint32_t)e ^ 0x80000000u) - kMisc[2];
-    // -2 ln u = -2 e ln2 - 4 atanh(s)
-    double res = xfma(ed, kMisc[0], -4.0 * lm2); // -2 ln2, low part
-    return xfma(ed, kMisc[1], res);              // -2 ln2, high part
+    for (int i = threadIdx.x; i < 129; i += blockDim.x) s_log_tab[i] = make_double2(kLogTab[i][0], kLogTab[i][1]);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        s_sincos_tab[i] = make_double2(kSinCosTab[i][0], kSinCosTab[i][1]);
+    __syncthreads();
+}
+__device__ __forceinline__ void tab_entry(uint32_t base, uint32_t idx, double& a, double& b)
+{
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(base + idx * 16u));
+}
+// `zero` is 0.  Hot loops pass a zero the compiler cannot see through (a kernel parameter),
+// which pins the five constants and the two table addresses in registers for the whole loop;
+// cold call sites pass the literal and everything folds.
+__device__ __forceinline__ double opaque_const(double c, int zero)
+{
+    return hilo2d(d2hi(c) + (uint32_t)zero, d2lo(c) + (uint32_t)zero);
+}
+template <typename T> __device__ __forceinline__ DrawK<T> draw_k_init(int zero)
+{
+    DrawK<T> k;
+    if constexpr (sizeof(T) == 8) {
+        k.c3 = opaque_const(1.0 / 3.0, zero);
+        k.two_ln2 = opaque_const(HDP_TWO_LN2_HI, zero);
+        k.turn = opaque_const(HDP_TURN52, zero);
+        k.c6 = opaque_const(1.0 / 6.0, zero);
+        k.c24 = opaque_const(1.0 / 24.0, zero);
+        k.log_tab = (uint32_t)__cvta_generic_to_shared(s_log_tab) + (uint32_t)zero;
+        k.sincos_tab = (uint32_t)__cvta_generic_to_shared(s_sincos_tab) + (uint32_t)zero;
+    }
+    return k;
+}
+#else
+static inline void tables_init() {}
+static inline void tab_entry(uint32_t base, uint32_t idx, double& a, double& b)
+{
+    const double(*t)[2] = base ? kSinCosTab : kLogTab;
+    a = t[idx][0]; b = t[idx][1];
+}
+template <typename T> static inline DrawK<T> draw_k_init(int)
+{
+    DrawK<T> k;
+    if constexpr (sizeof(T) == 8) {
+        k.c3 = 1.0 / 3.0; k.two_ln2 = HDP_TWO_LN2_HI; k.turn = HDP_TURN52; k.c6 = 1.0 / 6.0; k.c24 = 1.0 / 24.0;
+        k.log_tab = 0; k.sincos_tab = 1;
+    }
+    return k;
+}
+#endif
+
+// -2 ln(u) for a normal double u in (0,1)
+__device__ __forceinline__ double neg2log_unit(double u, const DrawK<double>& k)
+{
+    const uint32_t hi = d2hi(u), lo = d2lo(u);
+    const uint32_t mh = (hi & 0x000fffffu) | 0x3ff00000u;   // m = 1.f in [1,2)
+    const uint32_t idx = (mh - 0x3feff800u) >> 13;          // f rounded to 7 bits: 0..128
+    double rc, lm2;
+    tab_entry(k.log_tab, idx, rc, lm2);
+    const double r = xfma(hilo2d(mh, lo), rc, -1.0);        // |r| <= 2^-8
+    // ne = -(e + [idx >= HDP_LOG_SPLIT]) >= 0 as a double without I2F: (2^52 + ne) - 2^52
+    const uint32_t ne = 1023u - (hi >> 20) - ((idx + (128u - HDP_LOG_SPLIT)) >> 7);
+    const double ned = hilo2d(0x43300000u, ne) - 0x1p+52;
+    // log1p(r) = r + r^2 q(r)
+    double q = HDP_C7T;
+    q = xfma(q, r, -HDP_C6T);
+    q = xfma(q, r, HDP_C5T);
+    q = xfma(q, r, -0.25);
+    q = xfma(q, r, k.c3);
+    q = xfma(q, r, -0.5);
+    const double p = xfma(r * r, q, r);
+    double res = xfma(p, -2.0, lm2);
+    res = xfma(ned, HDP_TWO_LN2_LOT, res);
+    return xfma(ned, k.two_ln2, res);
 }
 
 __device__ __forceinline__ double sqrt_pos(double x)
@@ -256,63 +324,43 @@ __device__ __forceinline__ double sqrt_pos(double x)
     return xfma(er, 0.5 * y, sq);
 }
 
-// (cos, sin) of 2π k / 2^52 for the 52-bit integer k = (kh : kl), kh < 2^20
-__device__ __forceinline__ void sincos_turn52(uint32_t kh, uint32_t kl, double& sn, double& cs)
+// (sin, cos) of 2π k / 2^52 for the 52-bit integer k = (kh : kl), kh < 2^20
+__device__ __forceinline__ void sincos_turn52(uint32_t kh, uint32_t kl, double& sn, double& cs, const DrawK<double>& k)
 {
-    const uint32_t q = kh >> 17;                    // octant 0..7
-    u64 f = ((u64)(kh & 0x1ffffu) << 32) | (u64)kl; // 49-bit fraction within the octant
-    if (q & 1u) f = ((u64)1 << 49) - f;             // mirror odd octants (exact)
-    const double t = hilo2d(0x43300000u | (uint32_t)(f >> 32), (uint32_t)f) - kMisc[3]; // f as double
-    const double a = t * kMisc[4];                  // (π/4) * 2^-49, a in [0, π/4]
-    const double a2 = a * a;
-    const double a4 = a2 * a2;
-    double se = kSinC[6];
-    se = xfma(se, a4, kSinC[4]);
-    se = xfma(se, a4, kSinC[2]);
-    se = xfma(se, a4, kSinC[0]);
-    double so = kSinC[5];
-    so = xfma(so, a4, kSinC[3]);
-    so = xfma(so, a4, kSinC[1]);
-    const double ps = xfma(so, a2, se);
-    const double sa = xfma(a * a2, ps, a);
-    double ce = kCosC[6];
-    ce = xfma(ce, a4, kCosC[4]);
-    ce = xfma(ce, a4, kCosC[2]);
-    ce = xfma(ce, a4, kCosC[0]);
-    double co = kCosC[7];
-    co = xfma(co, a4, kCosC[5]);
-    co = xfma(co, a4, kCosC[3]);
-    co = xfma(co, a4, kCosC[1]);
-    const double pc = xfma(co, a2, ce);
-    const double ca = xfma(a2, pc, 1.0);
-    const bool swap = ((q + 1u) & 2u) != 0;          // octants 1,2,5,6
-    double s0 = swap ? ca : sa;
-    double c0 = swap ? sa : ca;
-    // signs: sin < 0 in octants 4..7, cos < 0 in octants 2..5
-    const uint32_t ssign = (q & 4u) << 29;
-    const uint32_t csign = ((q + 2u) & 4u) << 29;
-    sn = hilo2d(d2hi(s0) ^ ssign, d2lo(s0));
-    cs = hilo2d(d2hi(c0) ^ csign, d2lo(c0));
+    double sj, cj;
+    tab_entry(k.sincos_tab, kh >> 12, sj, cj);
+    // offset from the centre of the 1/256 turn: (f - 2^43) * 2π/2^52, f = low 44 bits of k
+    const double dl = (hilo2d(0x43300000u | (kh & 0xfffu), kl) - 0x1.008p+52 /* 2^52 + 2^43 */) * k.turn;
+    const double t = dl * dl;
+    const double ps = xfma(t, HDP_C120T, -k.c6);
+    const double sd = xfma(dl * t, ps, dl);                 // sin δ
+    double pc = xfma(t, -HDP_C720T, k.c24);
+    pc = xfma(t, pc, -0.5);
+    const double cd1 = t * pc;                              // cos δ − 1
+    sn = sj + xfma(cj, sd, sj * cd1);
+    cs = cj + xfma(-sj, sd, cj * cd1);
 }
 
 template <typename T>
-__device__ __forceinline__ Vec<T> draw_vec(u64 seed, int stream, u64 ord, uint32_t group, bool normal);
+__device__ __forceinline__ Vec<T> draw_vec(u64 seed, int stream, u64 ord, u64 group, bool normal, const DrawK<T>& k);
 
 template <>
-__device__ __forceinline__ Vec<double> draw_vec<double>(u64 seed, int stream, u64 ord, uint32_t group, bool normal)
+__device__ __forceinline__ Vec<double> draw_vec<double>(u64 seed, int stream, u64 ord, u64 group, bool normal,
+                                                        const DrawK<double>& k)
 {
-    const Philox4 p = philox4x32_10((uint32_t)ord, (uint32_t)(ord >> 32), group, (uint32_t)stream,
-                                    (uint32_t)seed, (uint32_t)(seed >> 32));
+    uint32_t w0, w1;
+    draw_address(stream, ord, group, w0, w1);
+    const Philox4 p = philox4x32_10(w0, w1, (uint32_t)seed, (uint32_t)(seed >> 32));
     Vec<double> r;
     const uint32_t h1 = p.w[0] >> 12, h2 = p.w[2] >> 12;
     if (!normal) {
         r.v[0] = hilo2d(0x3ff00000u | h1, p.w[1]) - 1.0;
         r.v[1] = hilo2d(0x3ff00000u | h2, p.w[3]) - 1.0;
     } else {
-        const double u1 = hilo2d(0x3ff00000u | h1, p.w[1]) - kMisc[5]; // 1 - 2^-53
-        const double rad = sqrt_pos(neg2log_unit(u1));
+        const double u1 = hilo2d(0x3ff00000u | h1, p.w[1] | 1u) - 1.0; // (k1 | 1) 2^-52 in (0,1)
+        const double rad = sqrt_pos(neg2log_unit(u1, k));
         double sn, cs;
-        sincos_turn52(h2, p.w[3], sn, cs);
+        sincos_turn52(h2, p.w[3], sn, cs, k);
         r.v[0] = rad * cs;
         r.v[1] = rad * sn;
     }
@@ -320,10 +368,12 @@ __device__ __forceinline__ Vec<double> draw_vec<double>(u64 seed, int stream, u6
 }
 
 template <>
-__device__ __forceinline__ Vec<float> draw_vec<float>(u64 seed, int stream, u64 ord, uint32_t group, bool normal)
+__device__ __forceinline__ Vec<float> draw_vec<float>(u64 seed, int stream, u64 ord, u64 group, bool normal,
+                                                      const DrawK<float>&)
 {
-    const Philox4 p = philox4x32_10((uint32_t)ord, (uint32_t)(ord >> 32), group, (uint32_t)stream,
-                                    (uint32_t)seed, (uint32_t)(seed >> 32));
+    uint32_t w0, w1;
+    draw_address(stream, ord, group, w0, w1);
+    const Philox4 p = philox4x32_10(w0, w1, (uint32_t)seed, (uint32_t)(seed >> 32));
     Vec<float> r;
     if (!normal) {
 #pragma unroll
@@ -342,6 +392,12 @@ __device__ __forceinline__ Vec<float> draw_vec<float>(u64 seed, int stream, u64 
         }
     }
     return r;
+}
+// convenience form for cold call sites
+template <typename T>
+__device__ __forceinline__ Vec<T> draw_vec(u64 seed, int stream, u64 ord, u64 group, bool normal)
+{
+    return draw_vec<T>(seed, stream, ord, group, normal, draw_k_init<T>(0));
 }
 
 // ---------------------------------------------------------------------
@@ -431,6 +487,10 @@ template <typename T> __device__ HDP_NOINLINE FarResult<T> reflect_far(T b, T lo
     return res;
 }
 
+// m with its sign flipped where s is negative
+__device__ __forceinline__ double xor_sign(double m, double s) { return hilo2d(d2hi(m) ^ (d2hi(s) & 0x80000000u), d2lo(m)); }
+__device__ __forceinline__ float xor_sign(float m, float s) { return u2f(f2u(m) ^ (f2u(s) & 0x80000000u)); }
+
 template <typename T> __device__ __forceinline__ T mirror_once(T b, T wall)
 {
     return sub_rn(b, mul_rn((T)2, sub_rn(b, wall))); // b - 2*(b - c), src/reflect.jl:34 for the hit coordinate
@@ -455,9 +515,33 @@ template <typename T> __device__ __forceinline__ T reflect_coord(T b, T lo, T hi
     return b;
 }
 
+// Coordinates that are still outside after their first mirror (a second wall hit in the same
+// step) finish in this out-of-line routine: one call for the whole vec-group keeps loops and
+// the far-excursion fold out of the callers' coordinate loop.
+template <typename T> struct SlowResult {
+    Vec<T> x;
+    int hits;
+};
+template <typename T> __device__ HDP_NOINLINE SlowResult<T> reflect_slow(Vec<T> x, Vec<T> lo, Vec<T> hi)
+{
+    SlowResult<T> r;
+    r.hits = 0;
+#pragma unroll
+    for (int e = 0; e < Tr<T>::VEC; ++e) r.x.v[e] = reflect_coord<T>(x.v[e], lo.v[e], hi.v[e], r.hits);
+    return r;
+}
+template <typename T> __device__ HDP_NOINLINE SlowResult<T> reflect_slow_sym(Vec<T> x, T h)
+{
+    SlowResult<T> r;
+    r.hits = 0;
+#pragma unroll
+    for (int e = 0; e < Tr<T>::VEC; ++e) r.x.v[e] = reflect_coord<T>(x.v[e], -h, h, r.hits);
+    return r;
+}
+
 // VEC coordinates of one lane at once.  The first wall hit is applied branch-free
-// (selects) to every coordinate; only coordinates that are still outside afterwards — a
-// second hit in the same step — enter the per-coordinate loop.  No collective inside.
+// (selects) to every coordinate; only when a coordinate is still outside afterwards — a
+// second hit in the same step — is the slow routine called.  No collective inside.
 template <typename T, int G, bool COUNT = true>
 __device__ __forceinline__ void reflect_vec(Vec<T>& x, const Vec<T>& lo, const Vec<T>& hi, unsigned gmask, int& nb)
 {
@@ -475,8 +559,38 @@ __device__ __forceinline__ void reflect_vec(Vec<T>& x, const Vec<T>& lo, const V
         again |= o && ((x.v[e] < lo.v[e]) | (x.v[e] > hi.v[e]));
     }
     if (again) {
+        const SlowResult<T> r = reflect_slow<T>(x, lo, hi);
+        x = r.x;
+        nb += r.hits;
+    }
+}
+
+// Symmetric scalar box [-h, h] (every BASELINE configuration with a boundary): |x| > h is the
+// same decision as (x < -h) | (x > h), and the wall that was hit is copysign(h, x).  Same
+// mirror arithmetic, fewer compares and selects.
+template <typename T, bool COUNT = true>
+__device__ __forceinline__ void reflect_vec_sym(Vec<T>& x, T h, int& nb)
+{
+    constexpr int VEC = Tr<T>::VEC;
+    bool again = false;
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) x.v[e] = reflect_coord<T>(x.v[e], lo.v[e], hi.v[e], nb);
+    for (int e = 0; e < VEC; ++e) {
+        const T v = x.v[e];
+        const T a = fabs(v);
+        const bool o = a > h;
+        // b - 2*(b - wall) with wall = copysign(h, b) is sign(b) * (|b| - 2*(|b| - h)): rounding is
+        // symmetric and 2*(.) is exact, so the single fma below rounds exactly like the
+        // reference's subtract, double, subtract (src/reflect.jl:34)
+        const T ta = xfma((T)-2, sub_rn(a, h), a);
+        const T t = xor_sign(ta, v);
+        x.v[e] = o ? t : v;
+        if (COUNT) nb += o ? 1 : 0;
+        again |= o && (fabs(ta) > h);
+    }
+    if (again) {
+        const SlowResult<T> r = reflect_slow_sym<T>(x, h);
+        x = r.x;
+        nb += r.hits;
     }
 }
 

@@ -90,6 +90,7 @@ mc_sample_kernel(T* __restrict__ z, const T* __restrict__ y1, const T* __restric
                  size_t n_el, int d, int K, DevSampler<T> sm, u64 seed, int stream)
 {
     constexpr int VEC = Tr<T>::VEC;
+    if constexpr (sizeof(T) == 8) tables_init();
     const size_t nv = (n_el + VEC - 1) / VEC;
     const bool normal = sm.kind == HDP_SAMPLER_NORMAL;
     const bool use_ref = normal && sm.shifted && y1 != nullptr;
@@ -102,7 +103,7 @@ mc_sample_kernel(T* __restrict__ z, const T* __restrict__ y1, const T* __restric
         const int i0 = (int)(q0 % (size_t)d);
         for (int k = 0; k < K; ++k) {
             Vec<T> raw = inject ? load_el<T, ALIGNED>(inject + (size_t)k * n_el, q0, n_el)
-                                : draw_vec<T>(seed, stream, (u64)k, (uint32_t)v, normal);
+                                : draw_vec<T>(seed, stream, (u64)k, (u64)v, normal);
             int i = i0;
             Vec<T> o;
 #pragma unroll
@@ -121,23 +122,29 @@ mc_sample_kernel(T* __restrict__ z, const T* __restrict__ y1, const T* __restric
 // registers.  draw addressing: dWall[q + n_el*step] == draw(SDE, ordinal=step, i=q).
 // Bounds, coefficient products and validity flags are resolved into registers before
 // the step loop, so the loop body is: 1 Philox call, VEC x (Box–Muller, 3 flops, mirror).
-template <typename T, bool ALIGNED, bool INJECT>
+// BC: K1_GENERIC — any coefficient kind, any bounds, either association;
+//     K1_NOBC / K1_SYM — constant coefficients, DeepSplitting association, no boundary /
+//     symmetric scalar box (the BASELINE shape): nothing but the arithmetic is left in the loop.
+enum { K1_GENERIC = 0, K1_NOBC = 1, K1_SYM = 2 };
+
+template <typename T, bool ALIGNED, bool INJECT, int BC>
 __global__ void __launch_bounds__(128)
 sde_loop_kernel(DevProblem<T> pb, T* __restrict__ y0, T* __restrict__ y1, size_t n_el, int nsteps, T dt,
                 DevSampler<T> x0s, const T* __restrict__ x0_inject, u64 seed, const T* __restrict__ dW,
                 DevSampler<T> mc, T* __restrict__ z, int K, int* flags, unsigned long long* bounce_ctr,
-                int mlp_assoc)
+                int mlp_assoc, int zero)
 {
     constexpr int VEC = Tr<T>::VEC;
+    if constexpr (sizeof(T) == 8) tables_init();
     const int d = pb.d;
     const size_t nv = (n_el + VEC - 1) / VEC;
     const T sq = sqrt_rn(dt);
-    const bool has_bc = pb.has_bc != 0;
-    const int stream = mlp_assoc ? HDP_STREAM_STEP : HDP_STREAM_SDE;
+    const bool has_bc = BC == K1_GENERIC ? pb.has_bc != 0 : BC == K1_SYM;
     const bool mu_lin = pb.mu_kind == HDP_COEF_LINEAR, sg_lin = pb.sigma_kind == HDP_COEF_LINEAR;
     const T mudt_c = mul_rn(pb.mu_c, dt), sgsq_c = mul_rn(pb.sigma_c, sq);
     bool bad = false;
     int nb_total = 0;
+    const DrawK<T> dk = draw_k_init<T>(BC != K1_GENERIC ? zero : 0);
     for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (size_t)gridDim.x * blockDim.x) {
         const size_t q0 = v * VEC;
         const int i0 = n_el <= 0xffffffffull ? (int)((uint32_t)q0 % (uint32_t)d) : (int)(q0 % (size_t)d);
@@ -145,7 +152,7 @@ sde_loop_kernel(DevProblem<T> pb, T* __restrict__ y0, T* __restrict__ y1, size_t
         // x0_sample!(y1), 1-argument sampler form (src/DeepSplitting.jl:155)
         if (x0s.kind != HDP_SAMPLER_NONE) {
             Vec<T> raw = x0_inject ? load_el<T, ALIGNED>(x0_inject, q0, n_el)
-                                   : draw_vec<T>(seed, HDP_STREAM_X0, 0, (uint32_t)v, x0s.kind == HDP_SAMPLER_NORMAL);
+                                   : draw_vec<T>(seed, HDP_STREAM_X0, 0, (u64)v, x0s.kind == HDP_SAMPLER_NORMAL);
             int i = i0;
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
@@ -170,17 +177,24 @@ sde_loop_kernel(DevProblem<T> pb, T* __restrict__ y0, T* __restrict__ y1, size_t
         for (int st = 0; st < nsteps; ++st) {
             Vec<T> xi;
             if constexpr (INJECT) xi = load_el<T, ALIGNED>(dW + (size_t)st * n_el, q0, n_el);
-            else xi = draw_vec<T>(seed, stream, (u64)st, (uint32_t)v, true);
+            else xi = draw_vec<T>(seed, HDP_STREAM_SDE, (u64)st, (u64)v, true, dk);
             prev = cur; // y0 .= y1 (:159)
+            if constexpr (BC == K1_GENERIC) {
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) {
-                const T x = prev.v[e];
-                const T mudt = mu_lin ? mul_rn(mul_rn(pb.mu_c, x), dt) : mudt_c;
-                const T sgsq = sg_lin ? mul_rn(mul_rn(pb.sigma_c, x), sq) : sgsq_c;
-                if (mlp_assoc) cur.v[e] = add_rn(x, add_rn(mudt, mul_rn(sgsq, xi.v[e]))); // src/MLP.jl:417
-                else cur.v[e] = add_rn(add_rn(x, mudt), mul_rn(sgsq, xi.v[e])); // :160 (y0 + μ*dt) + (σ*sq)*dW
+                for (int e = 0; e < VEC; ++e) {
+                    const T x = prev.v[e];
+                    const T mudt = mu_lin ? mul_rn(mul_rn(pb.mu_c, x), dt) : mudt_c;
+                    const T sgsq = sg_lin ? mul_rn(mul_rn(pb.sigma_c, x), sq) : sgsq_c;
+                    if (mlp_assoc) cur.v[e] = add_rn(x, add_rn(mudt, mul_rn(sgsq, xi.v[e]))); // src/MLP.jl:417
+                    else cur.v[e] = add_rn(add_rn(x, mudt), mul_rn(sgsq, xi.v[e])); // :160 (y0 + μ*dt) + (σ*sq)*dW
+                }
+                if (has_bc) reflect_vec<T, 1, false>(cur, lo, hi, 0u, nb_total); // :161-163
+            } else {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e)
+                    cur.v[e] = add_rn(add_rn(prev.v[e], mudt_c), mul_rn(sgsq_c, xi.v[e])); // :160
+                if constexpr (BC == K1_SYM) reflect_vec_sym<T, false>(cur, pb.hi_s, nb_total); // :161-163
             }
-            if (has_bc) reflect_vec<T, 1, false>(cur, lo, hi, 0u, nb_total); // :161-163
         }
         store_el<T, ALIGNED>(y0, q0, n_el, prev);
         store_el<T, ALIGNED>(y1, q0, n_el, cur);
@@ -188,7 +202,7 @@ sde_loop_kernel(DevProblem<T> pb, T* __restrict__ y0, T* __restrict__ y1, size_t
         if (z != nullptr && mc.kind != HDP_SAMPLER_NONE) {
             const bool normal = mc.kind == HDP_SAMPLER_NORMAL;
             for (int k = 0; k < K; ++k) {
-                Vec<T> raw = draw_vec<T>(seed, HDP_STREAM_MC, (u64)k, (uint32_t)v, normal);
+                Vec<T> raw = draw_vec<T>(seed, HDP_STREAM_MC, (u64)k, (u64)v, normal);
                 int i = i0;
                 Vec<T> o;
 #pragma unroll
@@ -329,6 +343,8 @@ int mc_sample_impl(hdp_handle h, T* z, const T* y1, int d, int B, int K, const h
     if ((rc = stage_out(h, z, n_el * (size_t)K, mem_flags, hdp_context::B_C, &dz)) != HDP_OK) return rc;
     constexpr int VEC = Tr<T>::VEC;
     const size_t nv = (n_el + VEC - 1) / VEC;
+    if (!draw_address_ok(HDP_STREAM_MC, (u64)K, (u64)nv))
+        return set_err(h, HDP_ERR_BAD_ARG, "mc_sample!: more than 2^24 samples or 2^37 vec-groups");
     const bool al = (n_el % VEC == 0) && aligned16(dz) && aligned16(dy1) && aligned16(dinj);
     const int grid = grid_for(h, nv, 256, 16);
     HDP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
@@ -386,18 +402,31 @@ int sde_loop_impl(hdp_handle h, const hdp_problem* prob, T* y0, T* y1, int B, in
     if (!want_z) dz = nullptr;
     constexpr int VEC = Tr<T>::VEC;
     const size_t nv = (n_el + VEC - 1) / VEC;
+    if (!draw_address_ok(HDP_STREAM_SDE, (u64)nsteps, (u64)nv) || !draw_address_ok(HDP_STREAM_MC, (u64)(K > 0 ? K : 0), (u64)nv))
+        return set_err(h, HDP_ERR_BAD_ARG, "sde_loop!: more than 2^24 steps/samples or 2^37 vec-groups");
     const bool al = (n_el % VEC == 0) && aligned16(dy0) && aligned16(dy1) && aligned16(dz) && aligned16(ddw);
     const int threads = 128;
     const int grid = grid_for(h, nv, threads, 64);
-#define LAUNCH(AL, INJ)                                                                                  \
-    sde_loop_kernel<T, AL, INJ><<<grid, threads, 0, h->stream>>>(pb, dy0, dy1, n_el, nsteps, dt, x0s,    \
-                                                                 nullptr, seed, ddw, mcs, dz, K,          \
-                                                                 h->d_flags, h->d_ctr + 1, mlp_assoc)
+    const bool const_coef = prob->mu_kind == HDP_COEF_CONST && prob->sigma_kind == HDP_COEF_CONST && !mlp_assoc;
+    const int bc = !const_coef ? K1_GENERIC
+                   : !pb.has_bc ? K1_NOBC
+                   : (pb.bc_is_scalar && pb.lo_s == -pb.hi_s) ? K1_SYM : K1_GENERIC;
+#define LAUNCH3(AL, INJ, BC)                                                                              \
+    sde_loop_kernel<T, AL, INJ, BC><<<grid, threads, 0, h->stream>>>(pb, dy0, dy1, n_el, nsteps, dt, x0s, \
+                                                                     nullptr, seed, ddw, mcs, dz, K,       \
+                                                                     h->d_flags, h->d_ctr + 1, mlp_assoc, 0)
+#define LAUNCH(AL, INJ)                                                                                   \
+    do {                                                                                                  \
+        if (bc == K1_SYM) LAUNCH3(AL, INJ, K1_SYM);                                                       \
+        else if (bc == K1_NOBC) LAUNCH3(AL, INJ, K1_NOBC);                                                \
+        else LAUNCH3(AL, INJ, K1_GENERIC);                                                                \
+    } while (0)
     HDP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     if (al && ddw) LAUNCH(true, true);
     else if (al) LAUNCH(true, false);
     else if (ddw) LAUNCH(false, true);
     else LAUNCH(false, false);
+#undef LAUNCH3
 #undef LAUNCH
     HDP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     h->launches++;

@@ -18,6 +18,10 @@
 
 namespace hdp {
 
+#ifndef HDP_EM_UNROLL
+#define HDP_EM_UNROLL 1
+#endif
+template <int N> struct IntTag { static constexpr int value = N; };
 struct FullTag { static constexpr bool value = true; };
 struct PartTag { static constexpr bool value = false; };
 
@@ -49,6 +53,7 @@ template <typename T> struct MlpParams {
     T* scratch;
     u64 total_threads;
     int rank, nranks;
+    int zero;        // 0, opaque to the compiler (draw_k_init)
     unsigned long long* work_ctr;
     unsigned long long* bounce_ctr;
     int* flags;
@@ -69,7 +74,7 @@ template <typename T, int G> struct Ctx {
     unsigned gmask;
     int nb;
     int bad;
-    int fast, fast_s; // em_step / sample_step may take their FAST specialisation
+    int fast, fast_s; // em_step (EM_* mode, 0 = general form) / sample_step may take their fast specialisation
     int f_uses_z;     // f reads the sampled point itself (sum(z^2)), not only u(z)
     __device__ __forceinline__ XAcc<T> slot(int k) const
     {
@@ -86,7 +91,7 @@ template <typename T, int G> struct Ctx {
         a.base = P->points + ((u64)solve * (u64)P->n_points + (u64)pt) * (u64)P->dpad;
         a.vstride = G;
         a.voff = (u64)lane;
-        a.unchecked = 1;
+        a.unchecked = 0; // explicit points are checked once, where they are created (init_item, expand_item)
         return a;
     }
 };
@@ -120,19 +125,107 @@ template <typename T, int G> __device__ __forceinline__ T time_uniform(const Ctx
 {
     const MlpParams<T>& P = *c.P;
     if (P.r_tape) return P.r_tape[ro];
-    return draw_vec<T>(c.seed, HDP_STREAM_TIME, ro, 0u, false).v[0];
+    return draw_vec<T>(c.seed, HDP_STREAM_TIME, ro, 0, false).v[0];
 }
 
 // `_mlt_sde_loop!(x2, x, s, t, prob, neumann_bc)`  (src/MLP.jl:406-421):
 // one Euler–Maruyama step s -> tend from the point `src`, then reflection.
-// Writes x2 to `dst` when non-null; returns sum(x2^2) and min(x2).
-// Everything the coordinate loop needs is copied into locals first (the parameter
-// block is only reachable through a pointer here); padding coordinates (i >= d) are
-// neutralised with selects, not branches.
-// FAST: constant coefficients, no or scalar bounds, in-register RNG, g does not need min(x)
-// (every BASELINE configuration) — the generic machinery folds away at compile time.
-template <typename T, int G, bool FAST>
-__device__ HDP_NOINLINE Feat<T> em_step_t(Ctx<T, G>& c, const XAcc<T>& src, const XAcc<T>* dst, T s, T tend, u64 ord)
+// Writes x2 to `dst` when STORE; returns sum(x2^2) and min(x2).
+//
+// em_step_fast — constant coefficients, in-register RNG, g does not need min(x), and the
+// boundary is absent (EM_NOBC), a symmetric scalar box (EM_SYM) or a general scalar box
+// (EM_BOX): every BASELINE configuration.  The coordinate loop is 1 Philox call, the
+// Box–Muller pair, 3 flops per coordinate, the mirror, one 128-bit load and (STORE) store.
+// The start-point assertion of `_reflect` (src/reflect.jl:12) runs as a separate pass, only
+// for points that can be outside the box (user x0, sampled x3).
+enum { EM_NOBC = 1, EM_SYM = 2, EM_BOX = 3 };
+
+template <typename T, int G, int MODE, bool STORE>
+__device__ HDP_NOINLINE Feat<T> em_step_fast(Ctx<T, G>& c, const XAcc<T>& src, const XAcc<T>& dst, T s, T tend, u64 ord)
+{
+    constexpr int VEC = Tr<T>::VEC;
+    const MlpParams<T>& P = *c.P;
+    const int d = P.pb.d, nvec = P.nvec;
+    const int lane = c.lane;
+    const u64 seed = c.seed;
+    const T lo_s = P.pb.lo_s, hi_s = P.pb.hi_s;
+    const T dt = sub_rn(tend, s);  // :415
+    const T sq = sqrt_rn(dt);
+    const T mudt = mul_rn(P.pb.mu_c, dt), sgsq = mul_rn(P.pb.sigma_c, sq);
+    const T* sp = src.base + src.voff * VEC;
+    const uint32_t sstride = (uint32_t)src.vstride * VEC; // < 2^32: vstride is the thread count or G
+    T* dp = dst.base + dst.voff * VEC;
+    const uint32_t dstride = (uint32_t)dst.vstride * VEC;
+    const int nfull = d / VEC;
+    if (MODE != EM_NOBC && src.unchecked) { // src/reflect.jl:12
+        const T* q = sp;
+        int bad = 0;
+        for (int p = lane; p < nvec; p += G, q += sstride) {
+            const Vec<T> xv = ldv<T>(q);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e)
+                if (p * VEC + e < d && !(xv.v[e] >= lo_s && xv.v[e] <= hi_s)) bad = 1;
+        }
+        c.bad |= bad;
+    }
+    T ssq = (T)0;
+    int nb = 0;
+    const DrawK<T> dk = draw_k_init<T>(P.zero);
+    // U vec-groups of this lane (p, p+G, …) per pass: U independent Philox / Box–Muller chains
+    // in flight hide the dependent-issue latency of each other
+    auto body = [&](int p, auto full_tag, auto u_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        constexpr int U = decltype(u_tag)::value;
+        Vec<T> xi[U], o[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) xi[u] = draw_vec<T>(seed, HDP_STREAM_STEP, ord, (u64)(p + u * G), true, dk); // :416 randn!(x2)
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            o[u] = ldv<T>(sp);
+            sp += sstride;
+        }
+        if (FULL && p + U * G < nvec) prefetch_l1(sp); // next pass: the address does not depend on the draws
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                o[u].v[e] = add_rn(o[u].v[e], add_rn(mudt, mul_rn(sgsq, xi[u].v[e]))); // :417
+                if (!FULL && !((p + u * G) * VEC + e < d)) o[u].v[e] = MODE == EM_BOX ? lo_s : (T)0; // padding never reflects
+            }
+            if (MODE == EM_SYM) reflect_vec_sym<T>(o[u], hi_s, nb);              // :418-420
+            if (MODE == EM_BOX) {
+                Vec<T> lo, hi;
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) { lo.v[e] = lo_s; hi.v[e] = hi_s; }
+                reflect_vec<T, G>(o[u], lo, hi, 0u, nb);
+            }
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                if (!FULL && !((p + u * G) * VEC + e < d)) o[u].v[e] = (T)0; // padding coordinate
+                ssq = xfma(o[u].v[e], o[u].v[e], ssq);
+            }
+            if (STORE) {
+                stv<T>(dp, o[u]);
+                dp += dstride;
+            }
+        }
+    };
+    int p = lane;
+#if HDP_EM_UNROLL > 1
+    for (; p + (HDP_EM_UNROLL - 1) * G < nfull; p += HDP_EM_UNROLL * G) body(p, FullTag{}, IntTag<HDP_EM_UNROLL>{});
+#endif
+    for (; p < nfull; p += G) body(p, FullTag{}, IntTag<1>{});
+    if (p < nvec) body(p, PartTag{}, IntTag<1>{});
+    if (MODE != EM_NOBC) c.nb += nb;
+    Feat<T> f;
+    f.ssq = gsum<T, G>(ssq, c.gmask);
+    f.mn = big<T>();
+    return f;
+}
+
+// the general form: injected tapes, vector bounds, state-dependent and user-defined coefficients, min(x)
+template <typename T, int G>
+__device__ HDP_NOINLINE Feat<T> em_step_generic(Ctx<T, G>& c, const XAcc<T>& src, const XAcc<T>* dst, T s, T tend, u64 ord)
 {
     constexpr int VEC = Tr<T>::VEC;
     const MlpParams<T>& P = *c.P;
@@ -140,18 +233,18 @@ __device__ HDP_NOINLINE Feat<T> em_step_t(Ctx<T, G>& c, const XAcc<T>& src, cons
     const int lane = c.lane;
     const unsigned gmask = c.gmask;
     const u64 seed = c.seed;
-    const T* __restrict__ tape = FAST ? nullptr : P.n_tape;
-    const bool has_bc = P.pb.has_bc != 0, bc_scalar = FAST ? true : (P.pb.bc_is_scalar != 0);
+    const T* __restrict__ tape = P.n_tape;
+    const bool has_bc = P.pb.has_bc != 0, bc_scalar = P.pb.bc_is_scalar != 0;
     const bool check_src = has_bc && src.unchecked != 0;
-    const T* __restrict__ lo_v = FAST ? nullptr : P.pb.lo;
-    const T* __restrict__ hi_v = FAST ? nullptr : P.pb.hi;
+    const T* __restrict__ lo_v = P.pb.lo;
+    const T* __restrict__ hi_v = P.pb.hi;
     const T lo_s = P.pb.lo_s, hi_s = P.pb.hi_s;
-    const bool mu_lin = FAST ? false : (P.pb.mu_kind == HDP_COEF_LINEAR);
-    const bool sg_lin = FAST ? false : (P.pb.sigma_kind == HDP_COEF_LINEAR);
-    const bool mu_usr = FAST ? false : (P.pb.mu_kind == HDP_COEF_USER);
-    const bool sg_usr = FAST ? false : (P.pb.sigma_kind == HDP_COEF_USER);
+    const bool mu_lin = P.pb.mu_kind == HDP_COEF_LINEAR;
+    const bool sg_lin = P.pb.sigma_kind == HDP_COEF_LINEAR;
+    const bool mu_usr = P.pb.mu_kind == HDP_COEF_USER;
+    const bool sg_usr = P.pb.sigma_kind == HDP_COEF_USER;
     const T mu_c = P.pb.mu_c, sg_c = P.pb.sigma_c;
-    const bool want_min = FAST ? false : (P.pb.g_kind == HDP_G_MIN || P.pb.g_kind == HDP_G_USER);
+    const bool want_min = P.pb.g_kind == HDP_G_MIN || P.pb.g_kind == HDP_G_USER;
     const T dt = sub_rn(tend, s);  // :415
     const T sq = sqrt_rn(dt);
     const T mudt_c = mul_rn(mu_c, dt), sgsq_c = mul_rn(sg_c, sq); // constant-coefficient products
@@ -161,17 +254,15 @@ __device__ HDP_NOINLINE Feat<T> em_step_t(Ctx<T, G>& c, const XAcc<T>& src, cons
     const u64 dstride = dst ? dst->vstride * VEC : 0;
     T ssq = (T)0, mn = big<T>();
     int nb = 0, bad = 0;
-    // FULL: every coordinate of the vec-group is a real coordinate (no padding selects)
-    auto body = [&](int p, auto full_tag) {
-        constexpr bool FULL = decltype(full_tag)::value;
+    for (int p = lane; p < nvec; p += G) {
         Vec<T> xi;
         if (tape) {
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
                 const int i = p * VEC + e;
-                xi.v[e] = (FULL || i < d) ? tape[ord * (u64)d + (u64)i] : (T)0;
+                xi.v[e] = i < d ? tape[ord * (u64)d + (u64)i] : (T)0;
             }
-        } else xi = draw_vec<T>(seed, HDP_STREAM_STEP, ord, (uint32_t)p, true); // :416 randn!(x2)
+        } else xi = draw_vec<T>(seed, HDP_STREAM_STEP, ord, (u64)p, true); // :416 randn!(x2)
         const Vec<T> xv = ldv<T>(sp);
         sp += sstride;
         Vec<T> o, lo, hi;
@@ -180,17 +271,16 @@ __device__ HDP_NOINLINE Feat<T> em_step_t(Ctx<T, G>& c, const XAcc<T>& src, cons
             const T x = xv.v[e];
             T mudt = mu_lin ? mul_rn(mul_rn(mu_c, x), dt) : mudt_c;
             T sgsq = sg_lin ? mul_rn(mul_rn(sg_c, x), sq) : sgsq_c;
-            if (!FAST) { // μ(x,p,t), σ(x,p,t) are evaluated at the start point and the END time (:417)
-                if (mu_usr) mudt = mul_rn(user_mu<T>(x, p * VEC + e, tend, d, P.pb.mu_p), dt);
-                if (sg_usr) sgsq = mul_rn(user_sigma<T>(x, p * VEC + e, tend, d, P.pb.sigma_p), sq);
-            }
+            // μ(x,p,t), σ(x,p,t) are evaluated at the start point and the END time (:417)
+            if (mu_usr) mudt = mul_rn(user_mu<T>(x, p * VEC + e, tend, d, P.pb.mu_p), dt);
+            if (sg_usr) sgsq = mul_rn(user_sigma<T>(x, p * VEC + e, tend, d, P.pb.sigma_p), sq);
             o.v[e] = add_rn(x, add_rn(mudt, mul_rn(sgsq, xi.v[e]))); // :417  x + (μ*dt + (σ*sq)*ξ)
         }
         if (has_bc) { // :418-420
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
                 const int i = p * VEC + e;
-                const bool valid = FULL || i < d;
+                const bool valid = i < d;
                 lo.v[e] = bc_scalar ? lo_s : (valid ? lo_v[i] : (T)0);
                 hi.v[e] = bc_scalar ? hi_s : (valid ? hi_v[i] : (T)0);
                 if (!valid) { lo.v[e] = -big<T>(); hi.v[e] = big<T>(); } // padding never reflects
@@ -200,7 +290,7 @@ __device__ HDP_NOINLINE Feat<T> em_step_t(Ctx<T, G>& c, const XAcc<T>& src, cons
         }
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
-            const bool valid = FULL || (p * VEC + e < d);
+            const bool valid = p * VEC + e < d;
             const T nx = valid ? o.v[e] : (T)0;
             o.v[e] = nx;
             ssq = xfma(nx, nx, ssq);
@@ -210,14 +300,7 @@ __device__ HDP_NOINLINE Feat<T> em_step_t(Ctx<T, G>& c, const XAcc<T>& src, cons
             stv<T>(dp, o);
             dp += dstride;
         }
-    };
-    // full vec-groups take the FULL body; the single partial vec-group (d % VEC != 0), if this
-    // lane owns it, the predicated one.  No collective is executed inside the loop, so lanes
-    // of a group may run different trip counts.
-    const int nfull = d / VEC;
-    int p = lane;
-    for (; p < nfull; p += G) body(p, FullTag{});
-    if (p < nvec) body(p, PartTag{});
+    }
     c.nb += nb;
     c.bad |= bad;
     Feat<T> f;
@@ -225,10 +308,21 @@ __device__ HDP_NOINLINE Feat<T> em_step_t(Ctx<T, G>& c, const XAcc<T>& src, cons
     f.mn = want_min ? gmin<T, G>(mn, gmask) : mn;
     return f;
 }
+
+template <typename T, int G, bool STORE>
+__device__ __forceinline__ Feat<T> em_step_s(Ctx<T, G>& c, const XAcc<T>& src, const XAcc<T>& dst, T s, T tend, u64 ord)
+{
+    switch (c.fast) {
+    case EM_NOBC: return em_step_fast<T, G, EM_NOBC, STORE>(c, src, dst, s, tend, ord);
+    case EM_SYM: return em_step_fast<T, G, EM_SYM, STORE>(c, src, dst, s, tend, ord);
+    case EM_BOX: return em_step_fast<T, G, EM_BOX, STORE>(c, src, dst, s, tend, ord);
+    }
+    return em_step_generic<T, G>(c, src, STORE ? &dst : nullptr, s, tend, ord);
+}
 template <typename T, int G>
 __device__ __forceinline__ Feat<T> em_step(Ctx<T, G>& c, const XAcc<T>& src, const XAcc<T>* dst, T s, T tend, u64 ord)
 {
-    return c.fast ? em_step_t<T, G, true>(c, src, dst, s, tend, ord) : em_step_t<T, G, false>(c, src, dst, s, tend, ord);
+    return dst ? em_step_s<T, G, true>(c, src, *dst, s, tend, ord) : em_step_s<T, G, false>(c, src, src, s, tend, ord);
 }
 
 // mc_sample!(x3, x2)  (src/MLP.jl:139,177; src/MCSample.jl:28-33, 63-71)
@@ -260,7 +354,7 @@ __device__ HDP_NOINLINE Feat<T> sample_step_t(Ctx<T, G>& c, const XAcc<T>* dst, 
                 const int i = p * VEC + e;
                 raw.v[e] = i < d ? tape[ord * (u64)d + (u64)i] : (T)0;
             }
-        } else raw = draw_vec<T>(seed, HDP_STREAM_SAMPLER, ord, (uint32_t)p, normal);
+        } else raw = draw_vec<T>(seed, HDP_STREAM_SAMPLER, ord, (u64)p, normal);
         Vec<T> ref;
         if (shifted) {
             ref = ldv<T>(rp);
@@ -449,8 +543,10 @@ __device__ __forceinline__ void ctx_init(Ctx<T, G>& c, const MlpParams<T>& P, u6
     c.nb = 0;
     c.bad = 0;
     c.seed = 0;
-    c.fast = P.pb.mu_kind == HDP_COEF_CONST && P.pb.sigma_kind == HDP_COEF_CONST && (!P.pb.has_bc || P.pb.bc_is_scalar) &&
-             P.n_tape == nullptr && P.pb.g_kind != HDP_G_MIN && P.pb.g_kind != HDP_G_USER;
+    c.fast = 0;
+    if (P.pb.mu_kind == HDP_COEF_CONST && P.pb.sigma_kind == HDP_COEF_CONST && (!P.pb.has_bc || P.pb.bc_is_scalar) &&
+        P.n_tape == nullptr && P.pb.g_kind != HDP_G_MIN && P.pb.g_kind != HDP_G_USER)
+        c.fast = !P.pb.has_bc ? EM_NOBC : (P.pb.lo_s == -P.pb.hi_s ? EM_SYM : EM_BOX);
     c.fast_s = P.s_tape == nullptr && (P.sm.kind != HDP_SAMPLER_UNIFORM || P.sm.scalar);
     c.f_uses_z = P.pb.f_kind == HDP_F_NL_REPLICATOR || P.pb.f_kind == HDP_F_NL_USER;
 }
@@ -458,6 +554,25 @@ __device__ __forceinline__ void ctx_init(Ctx<T, G>& c, const MlpParams<T>& P, u6
 // ---------------------------------------------------------------------
 // per-item bodies (shared by the kernels and by the test-only host emulation)
 // ---------------------------------------------------------------------
+// `@assert all((a .>= s) .& (a .<= e))` (src/reflect.jl:12) for an explicit point that later steps start from
+template <typename T, int G>
+__device__ __forceinline__ void assert_in_box(Ctx<T, G>& c, const MlpParams<T>& P, const XAcc<T>& x)
+{
+    constexpr int VEC = Tr<T>::VEC;
+    const bool scalar = P.pb.bc_is_scalar != 0;
+    for (int p = c.lane; p < P.nvec; p += G) {
+        const Vec<T> xv = ldv<T>(x.at(p));
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const int i = p * VEC + e;
+            if (i < P.pb.d) {
+                const T lo = scalar ? P.pb.lo_s : P.pb.lo[i], hi = scalar ? P.pb.hi_s : P.pb.hi[i];
+                if (!(xv.v[e] >= lo && xv.v[e] <= hi)) c.bad = 1;
+            }
+        }
+    }
+}
+
 // geometry of one explicit site: r, x2, x3_h
 template <typename T, int G>
 __device__ __forceinline__ void expand_item(Ctx<T, G>& c, const MlpParams<T>& P, int off, u64 item)
@@ -485,6 +600,7 @@ __device__ __forceinline__ void expand_item(Ctx<T, G>& c, const MlpParams<T>& P,
             const XAcc<T> x3 = c.point(solve, st.x3_point0 + h);
             const Feat<T> f3 = sample_step<T, G>(c, &x3, x2, qq);
             if (c.lane == 0) P.feat[(u64)solve * P.n_points + st.x3_point0 + h] = f3.ssq;
+            if (P.pb.has_bc && l >= 1) assert_in_box<T, G>(c, P, x3); // U_l(x3) steps from x3 (a level-0 site never does)
             qq += 1 + sub;
         }
     }
@@ -605,7 +721,12 @@ __device__ __forceinline__ void init_item(const MlpParams<T>& P, const T* x0, u6
     const u64 solve = q / (u64)P.dpad;
     const int i = (int)(q % (u64)P.dpad);
     const u64 src = (P.n_x0 == 1 ? 0 : solve) * (u64)P.pb.d;
-    P.points[solve * (u64)P.n_points * (u64)P.dpad + i] = i < P.pb.d ? x0[src + i] : (T)0;
+    const T v = i < P.pb.d ? x0[src + i] : (T)0;
+    P.points[solve * (u64)P.n_points * (u64)P.dpad + i] = v;
+    if (P.pb.has_bc && i < P.pb.d) { // every solve steps from x0 (src/reflect.jl:12)
+        const T lo = P.pb.bc_is_scalar ? P.pb.lo_s : P.pb.lo[i], hi = P.pb.bc_is_scalar ? P.pb.hi_s : P.pb.hi[i];
+        if (!(v >= lo && v <= hi)) atomicExch(&P.flags[0], 1);
+    }
 }
 
 #ifndef HDP_HOST_EMU
@@ -623,6 +744,7 @@ __global__ void mlp_init_kernel(const __grid_constant__ MlpParams<T> P, const T*
 template <typename T, int G>
 __global__ void __launch_bounds__(128) mlp_expand_kernel(const __grid_constant__ MlpParams<T> P, int off, int count)
 {
+    if constexpr (sizeof(T) == 8) tables_init();
     Ctx<T, G> c;
     ctx_init<T, G>(c, P, (u64)blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31);
     const u64 gid = c.tid / G;
@@ -639,6 +761,7 @@ template <typename T, int G>
 __global__ void __launch_bounds__(128, HDP_MLP_MINBLOCKS) mlp_units_kernel(const __grid_constant__ MlpParams<T> P)
 {
     constexpr int GPW = 32 / G;
+    if constexpr (sizeof(T) == 8) tables_init();
     Ctx<T, G> c;
     const int lane_w = threadIdx.x & 31;
     ctx_init<T, G>(c, P, (u64)blockIdx.x * blockDim.x + threadIdx.x, lane_w);

@@ -215,6 +215,8 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
     std::shared_ptr<MlpPlan> plan;
     if ((rc = get_plan(h, M, L, K, nonlocal, thresh, compat, &plan)) != HDP_OK) return rc;
 
+    if (!draw_address_ok(HDP_STREAM_STEP, tab.C[L] + 1, (u64)nvec) || !draw_address_ok(HDP_STREAM_SAMPLER, tab.S[L] + 1, (u64)nvec))
+        return set_err(h, HDP_ERR_BAD_ARG, "MLP: more than 2^40 path-steps per solve or 2^21 vec-groups per point");
     P.M = M; P.K = K; P.L = L; P.Kp = tab.Kp;
     P.nvec = nvec;
     P.npl = (nvec + G - 1) / G;

@@ -331,7 +331,7 @@ int hdp_sde_loop_f32(hdp_handle h, const hdp_problem* prob, float* y0, float* y1
  * Note the association differs from the DeepSplitting step (hdp_sde_loop_*).
  * x, x2: d×B (B independent columns; the reference is B = 1).
  * normals_inject: nullable d×B standard normals (`randn!(x2)`, :416); NULL => Philox
- * (stream HDP_STREAM_STEP, ordinal 0, draw index = linear element index).   */
+ * (stream HDP_STREAM_SDE, ordinal 0, draw index = linear element index).    */
 /* ------------------------------------------------------------------ */
 int hdp_mlt_sde_loop_f64(hdp_handle h, const hdp_problem* prob, double* x2, const double* x, int B,
                          double s, double t, uint64_t seed, const double* normals_inject, unsigned mem_flags);

@@ -40,9 +40,11 @@
 #endif
 
 /* ================================================================ */
-/* Philox4x32-10 (Salmon et al., SC'11) — the same counter layout the  */
-/* CUDA library uses: ctr = (ordinal_lo, ordinal_hi, group, stream),   */
-/* key = (seed_lo, seed_hi).                                           */
+/* Philox4x32-10 (Salmon et al., SC'11), generic in counter and key.   */
+/* The CUDA library's draws use a FIXED key and carry the 64-bit seed   */
+/* in the counter: ctr = (w0, w1, seed_lo, seed_hi) with (w0, w1) the   */
+/* packed address (stream, ordinal, group) — see draw_address() in      */
+/* highdimpde.jl_b200/csrc/hdp_device.cuh.                              */
 /* ================================================================ */
 void hdp_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
 {
@@ -62,26 +64,43 @@ void hdp_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-static inline double k52(uint32_t hi, uint32_t lo)
+/* the library's draw: streams TIME/STEP/SAMPLER pack (ordinal < 2^40, group < 2^21),
+ * streams SDE/X0/MC pack (ordinal < 2^24, group < 2^37) */
+static void draw_words(uint64_t seed, int stream, uint64_t ord, uint64_t group, uint32_t w[4])
+{
+    static const uint32_t key[2] = {0xA4093822u, 0x299F31D0u};
+    uint32_t ctr[4];
+    if (stream <= HDP_STREAM_SAMPLER) {
+        ctr[0] = (uint32_t)ord;
+        ctr[1] = (uint32_t)(ord >> 32) | ((uint32_t)group << 8) | ((uint32_t)stream << 29);
+    } else {
+        ctr[0] = (uint32_t)group;
+        ctr[1] = (uint32_t)(group >> 32) | ((uint32_t)ord << 5) | ((uint32_t)stream << 29);
+    }
+    ctr[2] = (uint32_t)seed;
+    ctr[3] = (uint32_t)(seed >> 32);
+    hdp_oracle_philox4x32_10(ctr, key, w);
+}
+
+static inline uint64_t k52(uint32_t hi, uint32_t lo)
 { /* 52-bit integer k = (hi >> 12) : lo in [0, 2^52) */
-    return (double)(((uint64_t)(hi >> 12) << 32) | (uint64_t)lo);
+    return ((uint64_t)(hi >> 12) << 32) | (uint64_t)lo;
 }
 
 /* value i of ordinal `ord` in `stream`; element type f64: one Philox call yields 2 draws
- * (group = i>>1).  Uniform u = k*2^-52 in [0,1).  Box–Muller: u1 = (k1 + 1/2)*2^-52 in (0,1),
+ * (group = i>>1).  Uniform u = k*2^-52 in [0,1).  Box–Muller: u1 = (k1 | 1)*2^-52 in (0,1),
  * angle 2*pi*k2/2^52.  Same definitions as hdp_device.cuh (which evaluates the
- * transcendentals with its own polynomials: the two agree to ~1e-15, not bit for bit). */
-double hdp_oracle_draw_f64(uint64_t seed, int stream, uint64_t ord, uint32_t i, int want_normal)
+ * transcendentals with its own tables and polynomials: the two agree to ~1e-15, not bit
+ * for bit). */
+double hdp_oracle_draw_f64(uint64_t seed, int stream, uint64_t ord, uint64_t i, int want_normal)
 {
-    uint32_t ctr[4] = {(uint32_t)ord, (uint32_t)(ord >> 32), i >> 1, (uint32_t)stream};
-    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     uint32_t w[4];
-    hdp_oracle_philox4x32_10(ctr, key, w);
+    draw_words(seed, stream, ord, i >> 1, w);
     if (!want_normal) {
-        return (i & 1) ? k52(w[2], w[3]) * 0x1.0p-52 : k52(w[0], w[1]) * 0x1.0p-52;
+        return (i & 1) ? (double)k52(w[2], w[3]) * 0x1.0p-52 : (double)k52(w[0], w[1]) * 0x1.0p-52;
     }
-    double u1 = (k52(w[0], w[1]) + 0.5) * 0x1.0p-52;
-    double turn = k52(w[2], w[3]) * 0x1.0p-52;
+    double u1 = (double)(k52(w[0], w[1]) | 1u) * 0x1.0p-52;
+    double turn = (double)k52(w[2], w[3]) * 0x1.0p-52;
     double r = sqrt(-2.0 * log(u1));
     double th = 2.0 * M_PI * turn;
     return (i & 1) ? r * sin(th) : r * cos(th);
@@ -89,13 +108,11 @@ double hdp_oracle_draw_f64(uint64_t seed, int stream, uint64_t ord, uint32_t i, 
 
 /* element type f32: one Philox call yields 4 draws (group = i>>2); 23-bit uniforms
  * u = (w >> 9)*2^-23; normals pair (w0,w1)->(z0,z1), (w2,w3)->(z2,z3). */
-float hdp_oracle_draw_f32(uint64_t seed, int stream, uint64_t ord, uint32_t i, int want_normal)
+float hdp_oracle_draw_f32(uint64_t seed, int stream, uint64_t ord, uint64_t i, int want_normal)
 {
-    uint32_t ctr[4] = {(uint32_t)ord, (uint32_t)(ord >> 32), i >> 2, (uint32_t)stream};
-    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     uint32_t w[4];
-    hdp_oracle_philox4x32_10(ctr, key, w);
-    uint32_t e = i & 3;
+    draw_words(seed, stream, ord, i >> 2, w);
+    uint32_t e = (uint32_t)(i & 3);
     if (!want_normal) return (float)(w[e] >> 9) * 0x1.0p-23f;
     uint32_t wa = w[e & 2], wb = w[(e & 2) + 1];
     float u1 = ((float)(wa >> 9) + 0.5f) * 0x1.0p-23f;
@@ -157,8 +174,8 @@ static void philox_normals(void* c, double* out, int d)
     philox_state* p = (philox_state*)c;
     uint64_t o = p->n_ord++;
     for (int i = 0; i < d; ++i)
-        out[i] = p->is_f32 ? (double)hdp_oracle_draw_f32(p->seed, HDP_STREAM_STEP, o, (uint32_t)i, 1)
-                           : hdp_oracle_draw_f64(p->seed, HDP_STREAM_STEP, o, (uint32_t)i, 1);
+        out[i] = p->is_f32 ? (double)hdp_oracle_draw_f32(p->seed, HDP_STREAM_STEP, o, (uint64_t)i, 1)
+                           : hdp_oracle_draw_f64(p->seed, HDP_STREAM_STEP, o, (uint64_t)i, 1);
 }
 static void philox_sampler(void* c, double* out, int d)
 {
@@ -166,8 +183,8 @@ static void philox_sampler(void* c, double* out, int d)
     uint64_t o = p->s_ord++;
     for (int i = 0; i < d; ++i)
         out[i] = p->is_f32
-                     ? (double)hdp_oracle_draw_f32(p->seed, HDP_STREAM_SAMPLER, o, (uint32_t)i, p->sampler_normal)
-                     : hdp_oracle_draw_f64(p->seed, HDP_STREAM_SAMPLER, o, (uint32_t)i, p->sampler_normal);
+                     ? (double)hdp_oracle_draw_f32(p->seed, HDP_STREAM_SAMPLER, o, (uint64_t)i, p->sampler_normal)
+                     : hdp_oracle_draw_f64(p->seed, HDP_STREAM_SAMPLER, o, (uint64_t)i, p->sampler_normal);
 }
 
 /* xoshiro256++ + 128-layer ziggurat (Doornik's ZIGNOR): a fast host

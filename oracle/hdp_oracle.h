@@ -45,8 +45,8 @@ void hdp_oracle_rng_free(hdp_oracle_rng* g);
 void hdp_oracle_rng_fill(hdp_oracle_rng* g, int what, double* out, int n);
 
 void hdp_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
-double hdp_oracle_draw_f64(uint64_t seed, int stream, uint64_t ord, uint32_t i, int want_normal);
-float hdp_oracle_draw_f32(uint64_t seed, int stream, uint64_t ord, uint32_t i, int want_normal);
+double hdp_oracle_draw_f64(uint64_t seed, int stream, uint64_t ord, uint64_t i, int want_normal);
+float hdp_oracle_draw_f32(uint64_t seed, int stream, uint64_t ord, uint64_t i, int want_normal);
 void hdp_oracle_mlp_counts(int M, int L, int K, int nonlocal, int64_t out[5]);
 
 #define HDP_ORACLE_DECL(REAL, SFX)                                                                     \

@@ -49,9 +49,9 @@ def lib():
         L.hdp_oracle_rng_fill.argtypes = [vp, i, vp, i]
         L.hdp_oracle_philox4x32_10.argtypes = [vp, vp, vp]
         L.hdp_oracle_draw_f64.restype = C.c_double
-        L.hdp_oracle_draw_f64.argtypes = [u64, i, u64, C.c_uint32, i]
+        L.hdp_oracle_draw_f64.argtypes = [u64, i, u64, u64, i]
         L.hdp_oracle_draw_f32.restype = C.c_float
-        L.hdp_oracle_draw_f32.argtypes = [u64, i, u64, C.c_uint32, i]
+        L.hdp_oracle_draw_f32.argtypes = [u64, i, u64, u64, i]
         L.hdp_oracle_mlp_counts.argtypes = [i, i, i, i, i64p]
         for sfx in ("_f64", "_f32"):
             real = C.c_double if sfx == "_f64" else C.c_float

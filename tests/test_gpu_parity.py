@@ -324,6 +324,6 @@ def test_mlt_sde_loop_single_step_matches_oracle(H, O, handle, dtype):
     assert np.array_equal(x2, want)
     # in-register normals: the same numbers hdp_tape_fill reports
     H._mlt_sde_loop(x2, x, 0.1, 0.45, prob_nb, seed=3, handle=handle)
-    z = handle.tape_fill(dtype, H.capi.HDP_STREAM_STEP, True, 3, 0, 1, d * B).reshape(B, d).T
+    z = handle.tape_fill(dtype, H.capi.HDP_STREAM_SDE, True, 3, 0, 1, d * B).reshape(B, d).T
     want = np.stack([O.mlt_sde_loop(pbn, x[:, j].copy(), 0.1, 0.45, np.ascontiguousarray(z[:, j])) for j in range(B)], axis=1)
     assert np.array_equal(x2, want)
