@@ -140,39 +140,30 @@ template <typename T, int G> __device__ __forceinline__ T time_uniform(const Ctx
 // for points that can be outside the box (user x0, sampled x3).
 enum { EM_NOBC = 1, EM_SYM = 2, EM_BOX = 3 };
 
-template <typename T, int G, int MODE, bool STORE>
-__device__ HDP_NOINLINE Feat<T> em_step_fast(Ctx<T, G>& c, const XAcc<T>& src, const XAcc<T>& dst, T s, T tend, u64 ord)
+// The coordinate loop itself; returns this lane's share of sum(x2^2).
+template <typename T, int G, int MODE>
+__device__ __forceinline__ T em_loop_fast(const MlpParams<T>& P, const DrawK<T>& dk, u64 seed, int lane, const T* sp,
+                                          uint32_t sstride, T* dp, uint32_t dstride, bool store, bool check_src, T s,
+                                          T tend, u64 ord, int& nb, int& bad)
 {
     constexpr int VEC = Tr<T>::VEC;
-    const MlpParams<T>& P = *c.P;
     const int d = P.pb.d, nvec = P.nvec;
-    const int lane = c.lane;
-    const u64 seed = c.seed;
     const T lo_s = P.pb.lo_s, hi_s = P.pb.hi_s;
     const T dt = sub_rn(tend, s);  // :415
     const T sq = sqrt_rn(dt);
     const T mudt = mul_rn(P.pb.mu_c, dt), sgsq = mul_rn(P.pb.sigma_c, sq);
-    const T* sp = src.base + src.voff * VEC;
-    const uint32_t sstride = (uint32_t)src.vstride * VEC; // < 2^32: vstride is the thread count or G
-    T* dp = dst.base + dst.voff * VEC;
-    const uint32_t dstride = (uint32_t)dst.vstride * VEC;
     const int nfull = d / VEC;
-    if (MODE != EM_NOBC && src.unchecked) { // src/reflect.jl:12
+    if (MODE != EM_NOBC && check_src) { // src/reflect.jl:12
         const T* q = sp;
-        int bad = 0;
         for (int p = lane; p < nvec; p += G, q += sstride) {
             const Vec<T> xv = ldv<T>(q);
 #pragma unroll
             for (int e = 0; e < VEC; ++e)
                 if (p * VEC + e < d && !(xv.v[e] >= lo_s && xv.v[e] <= hi_s)) bad = 1;
         }
-        c.bad |= bad;
     }
     T ssq = (T)0;
-    int nb = 0;
-    const DrawK<T> dk = draw_k_init<T>(P.zero);
-    // U vec-groups of this lane (p, p+G, …) per pass: U independent Philox / Box–Muller chains
-    // in flight hide the dependent-issue latency of each other
+    // U vec-groups of this lane (p, p+G, …) per pass
     auto body = [&](int p, auto full_tag, auto u_tag) {
         constexpr bool FULL = decltype(full_tag)::value;
         constexpr int U = decltype(u_tag)::value;
@@ -184,7 +175,6 @@ __device__ HDP_NOINLINE Feat<T> em_step_fast(Ctx<T, G>& c, const XAcc<T>& src, c
             o[u] = ldv<T>(sp);
             sp += sstride;
         }
-        if (FULL && p + U * G < nvec) prefetch_l1(sp); // next pass: the address does not depend on the draws
 #pragma unroll
         for (int u = 0; u < U; ++u) {
 #pragma unroll
@@ -204,7 +194,7 @@ __device__ HDP_NOINLINE Feat<T> em_step_fast(Ctx<T, G>& c, const XAcc<T>& src, c
                 if (!FULL && !((p + u * G) * VEC + e < d)) o[u].v[e] = (T)0; // padding coordinate
                 ssq = xfma(o[u].v[e], o[u].v[e], ssq);
             }
-            if (STORE) {
+            if (store) {
                 stv<T>(dp, o[u]);
                 dp += dstride;
             }
@@ -216,7 +206,21 @@ __device__ HDP_NOINLINE Feat<T> em_step_fast(Ctx<T, G>& c, const XAcc<T>& src, c
 #endif
     for (; p < nfull; p += G) body(p, FullTag{}, IntTag<1>{});
     if (p < nvec) body(p, PartTag{}, IntTag<1>{});
-    if (MODE != EM_NOBC) c.nb += nb;
+    return ssq;
+}
+
+template <typename T, int G, int MODE, bool STORE>
+__device__ HDP_NOINLINE Feat<T> em_step_fast(Ctx<T, G>& c, const XAcc<T>& src, const XAcc<T>& dst, T s, T tend, u64 ord)
+{
+    constexpr int VEC = Tr<T>::VEC;
+    const MlpParams<T>& P = *c.P;
+    const DrawK<T> dk = draw_k_init<T>(P.zero);
+    int nb = 0, bad = 0;
+    const T ssq = em_loop_fast<T, G, MODE>(P, dk, c.seed, c.lane, src.base + src.voff * VEC, (uint32_t)src.vstride * VEC,
+                                           dst.base + dst.voff * VEC, (uint32_t)dst.vstride * VEC, STORE,
+                                           src.unchecked != 0, s, tend, ord, nb, bad);
+    c.nb += nb;
+    c.bad |= bad;
     Feat<T> f;
     f.ssq = gsum<T, G>(ssq, c.gmask);
     f.mn = big<T>();
@@ -506,6 +510,197 @@ __device__ HDP_NOINLINE T level_slice(Ctx<T, G>& c, XAcc<T> xp, T s, u64 co, u64
     return b;
 }
 
+// ---------------------------------------------------------------------
+// The same recursion without calls.  At any moment at most one call of each level is active
+// (a call of level LV only ever starts calls of lower levels), so the frames of the active
+// calls live in an array indexed by call level, and the walk is a state machine that runs
+// bookkeeping until the next path-step or sampler call is due.  There is exactly one copy of
+// the coordinate loop in the kernel, it is inlined in the kernel body (parameters come straight
+// from the constant bank, no call ABI in the way of register allocation), and nothing is
+// re-loaded per path-step.  Arithmetic and ordinals are those of Call<LV> / eval_site<l> above.
+// ---------------------------------------------------------------------
+template <typename T> struct Frame {
+    T s, r, a, b, b3, b2, b4, f2, f3, term;
+    u64 k, num, gnum, co, ro, so, cc, rr, qq;
+    int lv, l, lend, h, phase, xslot, parent, pad_;
+};
+enum { PH_B2 = 0, PH_B4 = 1, PH_V = 2, PH_W = 3 };
+enum { ST_LEVEL = 0, ST_SITE, ST_SITE_POST, ST_AFTER_B2, ST_SAMPLES, ST_SAMPLE_POST, ST_SITE_END, ST_G, ST_G_POST, ST_RETURN };
+enum { ACT_NONE = 0, ACT_EM = 1, ACT_SAMPLE = 2 };
+
+template <typename T, int G, int MODE>
+__device__ __forceinline__ T run_unit_iter(Ctx<T, G>& c, const MlpParams<T>& P, const PlanUnit& u, const PlanNode& nd,
+                                           const XAcc<T>& xp, T s0)
+{
+    constexpr int VEC = Tr<T>::VEC;
+    const DevProblem<T>& pb = P.pb;
+    const T t1 = pb.t1;
+    const bool shifted = P.sm.kind == HDP_SAMPLER_NORMAL && P.sm.shifted;
+    const bool has_samples = P.Kp > 0;
+    const int K = P.K;
+    const int kind = u.kind;
+    const DrawK<T> dk = draw_k_init<T>(P.zero);
+    Frame<T> fr[kMaxL + 1];
+    int cur, root;
+    {
+        const u64 n = (u64)(u.k1 - u.k0);
+        root = kind == UNIT_WHOLE ? nd.lv : (kind == UNIT_G ? 1 : u.l + 1);
+        Frame<T>& F = fr[root];
+        F.lv = root;
+        F.l = kind == UNIT_LEVEL ? u.l : 0;
+        F.lend = kind == UNIT_WHOLE ? nd.lv : (kind == UNIT_G ? 0 : u.l + 1);
+        F.k = 0;
+        F.num = kind == UNIT_LEVEL ? n : P.Mpow[root];
+        F.gnum = kind == UNIT_G ? n : P.Mpow[root];
+        F.a = (T)0; F.b = (T)0;
+        F.s = s0;
+        F.xslot = -1;
+        F.co = u.c; F.ro = u.r; F.so = u.s;
+        F.parent = -1;
+        cur = root;
+    }
+    auto push = [&](int lvc, int xslot, T s, u64 co, u64 ro, u64 so, int parent) {
+        Frame<T>& Cf = fr[lvc];
+        Cf.lv = lvc; Cf.l = 0; Cf.lend = lvc; Cf.k = 0;
+        Cf.num = P.Mpow[lvc]; Cf.gnum = P.Mpow[lvc];
+        Cf.a = (T)0; Cf.b = (T)0; Cf.s = s; Cf.xslot = xslot;
+        Cf.co = co; Cf.ro = ro; Cf.so = so; Cf.parent = parent;
+    };
+    int st = ST_LEVEL, nb = 0, bad = 0;
+    T ret = (T)0, result = (T)0;
+    Feat<T> feat;
+    feat.ssq = (T)0; feat.mn = big<T>();
+    for (;;) {
+        Frame<T>& F = fr[cur];
+        const int l = F.l;
+        int act = ACT_NONE;
+        // action parameters
+        int a_src = 0, a_dst = 0;
+        bool a_store = false;
+        T a_s = (T)0, a_t = (T)0;
+        u64 a_ord = 0;
+        if (st == ST_LEVEL) {
+            if (l < F.lend) {
+                if (F.k < F.num) st = ST_SITE;
+                else {
+                    if (cur == root && kind == UNIT_LEVEL) { result = F.b; break; }
+                    F.a += ((t1 - F.s) * F.b) / (T)F.num; // :150, :195
+                    F.l = l + 1; F.k = 0; F.b = (T)0;
+                    F.num = P.Mpow[F.lv - (l + 1)];
+                }
+            } else { F.k = 0; F.b = (T)0; st = ST_G; }
+        } else if (st == ST_SITE) {
+            const T uu = time_uniform<T, G>(c, F.ro);
+            const T r = add_rn(F.s, mul_rn(sub_rn(t1, F.s), uu)); // :132
+            F.r = r;
+            act = ACT_EM; a_src = F.xslot; a_dst = 2 * l; a_store = (l >= 1) || shifted; a_s = F.s; a_t = r; a_ord = F.co; // :133
+            st = ST_SITE_POST;
+        } else if (st == ST_SITE_POST) {
+            F.f2 = feat.ssq;
+            F.cc = F.co + 1; F.rr = F.ro + 1; F.qq = F.so;
+            F.b2 = (T)0; F.b4 = (T)0; F.b3 = (T)0; F.h = 0;
+            if (l >= 1) { // :134
+                push(l, 2 * l, F.r, F.cc, F.rr, F.qq, cur);
+                F.cc += P.C[l]; F.rr += P.R[l]; F.qq += P.S[l];
+                F.phase = PH_B2; cur = l; st = ST_LEVEL;
+            } else st = ST_SAMPLES;
+        } else if (st == ST_AFTER_B2) {
+            if (l >= 2) { // :160-173
+                push(l - 1, 2 * l, F.r, F.cc, F.rr, F.qq, cur);
+                F.cc += P.C[l - 1]; F.rr += P.R[l - 1]; F.qq += P.S[l - 1];
+                F.phase = PH_B4; cur = l - 1; st = ST_LEVEL;
+            } else st = ST_SAMPLES;
+        } else if (st == ST_SAMPLES) {
+            const bool dead_samples = (l == 0) && !c.f_uses_z;
+            if (has_samples && !dead_samples) {
+                if (F.h < K) { // :137, :176
+                    act = ACT_SAMPLE; a_dst = 2 * l + 1; a_store = l >= 1; a_src = 2 * l; a_ord = F.qq; // :139, :177
+                    st = ST_SAMPLE_POST;
+                } else st = ST_SITE_END;
+            } else {
+                // NoSampling: the K-loop re-evaluates f on identical arguments (:137-147, :210-216)
+                T term = f_eval<T>(pb, F.f2, (T)0, F.b2, (T)0);
+                if (l >= 2) term = term - f_eval<T>(pb, F.f2, (T)0, F.b4, (T)0);
+                T b3 = (T)0;
+                for (int h = 0; h < K; ++h) b3 += term;
+                F.b3 = b3;
+                st = ST_SITE_END;
+            }
+        } else if (st == ST_SAMPLE_POST) {
+            F.f3 = feat.ssq;
+            F.qq += 1;
+            if (l >= 1) {
+                push(l, 2 * l + 1, F.r, F.cc, F.rr, F.qq, cur);
+                F.cc += P.C[l]; F.rr += P.R[l]; F.qq += P.S[l];
+                F.phase = PH_V; cur = l; st = ST_LEVEL;
+            } else {
+                F.b3 += f_eval<T>(pb, F.f2, F.f3, (T)0, (T)0); // :140-146 with U_0 = 0
+                F.h += 1;
+                st = ST_SAMPLES;
+            }
+        } else if (st == ST_SITE_END) {
+            F.b += F.b3 / (T)K; // :148
+            F.k += 1;
+            F.co += P.cs[l]; F.ro += P.rs[l]; F.so += P.ss[l];
+            st = ST_LEVEL;
+        } else if (st == ST_G) {
+            if (F.k < F.gnum) { // :198-205
+                act = ACT_EM; a_src = F.xslot; a_store = false; a_s = F.s; a_t = t1; a_ord = F.co + F.k; // :202
+                st = ST_G_POST;
+            } else {
+                if (cur == root && kind == UNIT_G) { result = F.b; break; }
+                ret = F.a + F.b / (T)F.gnum; // :205, :207
+                st = ST_RETURN;
+            }
+        } else if (st == ST_G_POST) {
+            F.b += g_eval<T>(pb, feat); // :203
+            F.k += 1;
+            st = ST_G;
+        } else { // ST_RETURN
+            if (cur == root) { result = ret; break; }
+            cur = F.parent;
+            Frame<T>& Pf = fr[cur];
+            const int pl = Pf.l;
+            if (Pf.phase == PH_B2) { Pf.b2 = ret; st = ST_AFTER_B2; }
+            else if (Pf.phase == PH_B4) { Pf.b4 = ret; st = ST_SAMPLES; }
+            else if (Pf.phase == PH_V) {
+                const T term = f_eval<T>(pb, Pf.f2, Pf.f3, Pf.b2, ret); // :140-146
+                if (pl >= 2) {
+                    Pf.term = term;
+                    push(pl - 1, 2 * pl + 1, Pf.r, Pf.cc, Pf.rr, Pf.qq, cur);
+                    Pf.cc += P.C[pl - 1]; Pf.rr += P.R[pl - 1]; Pf.qq += P.S[pl - 1];
+                    Pf.phase = PH_W; cur = pl - 1; st = ST_LEVEL;
+                } else { Pf.b3 += term; Pf.h += 1; st = ST_SAMPLES; }
+            } else {
+                Pf.b3 += Pf.term - f_eval<T>(pb, Pf.f2, Pf.f3, Pf.b4, ret); // :178-191
+                Pf.h += 1;
+                st = ST_SAMPLES;
+            }
+        }
+        if (act == ACT_NONE) continue;
+        const XAcc<T> xs = a_src < 0 ? xp : c.slot(a_src);
+        if (act == ACT_EM) {
+            if (MODE == 0) {
+                const XAcc<T> xd = c.slot(a_dst);
+                feat = em_step_generic<T, G>(c, xs, a_store ? &xd : nullptr, a_s, a_t, a_ord);
+            } else {
+                const XAcc<T> xd = c.slot(a_store ? a_dst : 0);
+                const T ssq = em_loop_fast<T, G, MODE>(P, dk, c.seed, c.lane, xs.base + xs.voff * VEC,
+                                                       (uint32_t)xs.vstride * VEC, xd.base + xd.voff * VEC,
+                                                       (uint32_t)xd.vstride * VEC, a_store, xs.unchecked != 0, a_s,
+                                                       a_t, a_ord, nb, bad);
+                feat.ssq = gsum<T, G>(ssq, c.gmask);
+            }
+        } else {
+            const XAcc<T> xd = c.slot(a_dst);
+            feat = sample_step<T, G>(c, a_store ? &xd : nullptr, xs, a_ord);
+        }
+    }
+    c.nb += nb;
+    c.bad |= bad;
+    return result;
+}
+
 template <typename T, int G>
 __device__ __forceinline__ T run_unit(Ctx<T, G>& c, const PlanUnit& u, const PlanNode& nd, const XAcc<T>& xp, T s)
 {
@@ -560,8 +755,8 @@ __device__ __forceinline__ void assert_in_box(Ctx<T, G>& c, const MlpParams<T>& 
 {
     constexpr int VEC = Tr<T>::VEC;
     const bool scalar = P.pb.bc_is_scalar != 0;
-    for (int p = c.lane; p < P.nvec; p += G) {
-        const Vec<T> xv = ldv<T>(x.at(p));
+    for (int p = c.lane, j = 0; p < P.nvec; p += G, ++j) { // j-th vec-group of this lane
+        const Vec<T> xv = ldv<T>(x.at(j));
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
             const int i = p * VEC + e;
@@ -624,7 +819,17 @@ __device__ __forceinline__ void unit_item(Ctx<T, G>& c, const MlpParams<T>& P, u
     c.nb = 0;
     const T s = nd.time_site < 0 ? P.pb.t0 : P.site_r[(u64)solve * P.n_sites + nd.time_site];
     const XAcc<T> xp = c.point(solve, nd.point);
+#ifdef HDP_MLP_RECURSIVE
     const T v = run_unit<T, G>(c, un, nd, xp, s);
+#else
+    T v;
+    switch (c.fast) {
+    case EM_NOBC: v = run_unit_iter<T, G, EM_NOBC>(c, P, un, nd, xp, s); break;
+    case EM_SYM: v = run_unit_iter<T, G, EM_SYM>(c, P, un, nd, xp, s); break;
+    case EM_BOX: v = run_unit_iter<T, G, EM_BOX>(c, P, un, nd, xp, s); break;
+    default: v = run_unit_iter<T, G, 0>(c, P, un, nd, xp, s); break;
+    }
+#endif
     const int nb = gsumi<G>(c.nb, c.gmask);
     if (c.lane == 0) {
         P.partial[(u64)solve * P.n_units + uid] = (double)v;
