@@ -515,61 +515,31 @@ template <typename T> __device__ __forceinline__ T reflect_coord(T b, T lo, T hi
     return b;
 }
 
-// Coordinates that are still outside after their first mirror (a second wall hit in the same
-// step) finish in this out-of-line routine: one call for the whole vec-group keeps loops and
-// the far-excursion fold out of the callers' coordinate loop.
-template <typename T> struct SlowResult {
-    Vec<T> x;
-    int hits;
-};
-template <typename T> __device__ HDP_NOINLINE SlowResult<T> reflect_slow(Vec<T> x, Vec<T> lo, Vec<T> hi)
-{
-    SlowResult<T> r;
-    r.hits = 0;
-#pragma unroll
-    for (int e = 0; e < Tr<T>::VEC; ++e) r.x.v[e] = reflect_coord<T>(x.v[e], lo.v[e], hi.v[e], r.hits);
-    return r;
-}
-template <typename T> __device__ HDP_NOINLINE SlowResult<T> reflect_slow_sym(Vec<T> x, T h)
-{
-    SlowResult<T> r;
-    r.hits = 0;
-#pragma unroll
-    for (int e = 0; e < Tr<T>::VEC; ++e) r.x.v[e] = reflect_coord<T>(x.v[e], -h, h, r.hits);
-    return r;
-}
-
-// VEC coordinates of one lane at once.  The first wall hit is applied branch-free
-// (selects) to every coordinate; only when a coordinate is still outside afterwards — a
-// second hit in the same step — is the slow routine called.  No collective inside.
-template <typename T, int G, bool COUNT = true>
-__device__ __forceinline__ void reflect_vec(Vec<T>& x, const Vec<T>& lo, const Vec<T>& hi, unsigned gmask, int& nb)
+// VEC coordinates of one lane at once.  The first wall hit is applied branch-free (selects)
+// to every coordinate; the return value says whether some coordinate is still outside
+// afterwards — a second hit in the same step — and needs reflect_coord.  No collective inside.
+template <typename T, bool COUNT = true>
+__device__ __forceinline__ bool reflect_first(Vec<T>& x, T lo, T hi, int& nb)
 {
     constexpr int VEC = Tr<T>::VEC;
-    (void)gmask;
     bool again = false;
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
-        const bool below = x.v[e] < lo.v[e];
-        const bool above = x.v[e] > hi.v[e];
+        const bool below = x.v[e] < lo;
+        const bool above = x.v[e] > hi;
         const bool o = below | above;
-        const T t = mirror_once<T>(x.v[e], below ? lo.v[e] : hi.v[e]);
+        const T t = mirror_once<T>(x.v[e], below ? lo : hi);
         x.v[e] = o ? t : x.v[e];
         if (COUNT) nb += o ? 1 : 0;
-        again |= o && ((x.v[e] < lo.v[e]) | (x.v[e] > hi.v[e]));
+        again |= o && ((t < lo) | (t > hi));
     }
-    if (again) {
-        const SlowResult<T> r = reflect_slow<T>(x, lo, hi);
-        x = r.x;
-        nb += r.hits;
-    }
+    return again;
 }
-
 // Symmetric scalar box [-h, h] (every BASELINE configuration with a boundary): |x| > h is the
 // same decision as (x < -h) | (x > h), and the wall that was hit is copysign(h, x).  Same
 // mirror arithmetic, fewer compares and selects.
 template <typename T, bool COUNT = true>
-__device__ __forceinline__ void reflect_vec_sym(Vec<T>& x, T h, int& nb)
+__device__ __forceinline__ bool reflect_first_sym(Vec<T>& x, T h, int& nb)
 {
     constexpr int VEC = Tr<T>::VEC;
     bool again = false;
@@ -587,10 +557,35 @@ __device__ __forceinline__ void reflect_vec_sym(Vec<T>& x, T h, int& nb)
         if (COUNT) nb += o ? 1 : 0;
         again |= o && (fabs(ta) > h);
     }
+    return again;
+}
+template <typename T, int G, bool COUNT = true>
+__device__ __forceinline__ void reflect_vec(Vec<T>& x, const Vec<T>& lo, const Vec<T>& hi, unsigned gmask, int& nb)
+{
+    constexpr int VEC = Tr<T>::VEC;
+    (void)gmask;
+    bool again = false;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+        const bool below = x.v[e] < lo.v[e];
+        const bool above = x.v[e] > hi.v[e];
+        const bool o = below | above;
+        const T t = mirror_once<T>(x.v[e], below ? lo.v[e] : hi.v[e]);
+        x.v[e] = o ? t : x.v[e];
+        if (COUNT) nb += o ? 1 : 0;
+        again |= o && ((x.v[e] < lo.v[e]) | (x.v[e] > hi.v[e]));
+    }
     if (again) {
-        const SlowResult<T> r = reflect_slow_sym<T>(x, h);
-        x = r.x;
-        nb += r.hits;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) x.v[e] = reflect_coord<T>(x.v[e], lo.v[e], hi.v[e], nb);
+    }
+}
+template <typename T, bool COUNT = true>
+__device__ __forceinline__ void reflect_vec_sym(Vec<T>& x, T h, int& nb)
+{
+    if (reflect_first_sym<T, COUNT>(x, h, nb)) {
+#pragma unroll
+        for (int e = 0; e < Tr<T>::VEC; ++e) x.v[e] = reflect_coord<T>(x.v[e], -h, h, nb);
     }
 }
 

@@ -141,19 +141,25 @@ template <typename T, int G> __device__ __forceinline__ T time_uniform(const Ctx
 enum { EM_NOBC = 1, EM_SYM = 2, EM_BOX = 3 };
 
 // The coordinate loop itself; returns this lane's share of sum(x2^2).
+// With a boundary the loop always writes x2 (`dp` must be valid; callers that do not keep x2
+// pass a free scratch slot): a vec-group in which a coordinate is still outside after its
+// first mirror — a second wall hit in one step, ≈0.5 % of the coordinates of BASELINE C2 — is
+// only flagged in a bit mask, and finished after the loop from the stored values.  The loop
+// body therefore has no branch, no call and no convergence barrier.
 template <typename T, int G, int MODE>
 __device__ __forceinline__ T em_loop_fast(const MlpParams<T>& P, const DrawK<T>& dk, u64 seed, int lane, const T* sp,
                                           uint32_t sstride, T* dp, uint32_t dstride, bool store, bool check_src, T s,
                                           T tend, u64 ord, int& nb, int& bad)
 {
     constexpr int VEC = Tr<T>::VEC;
+    constexpr bool BC = MODE != EM_NOBC;
     const int d = P.pb.d, nvec = P.nvec;
-    const T lo_s = P.pb.lo_s, hi_s = P.pb.hi_s;
+    const T lo_s = MODE == EM_SYM ? -P.pb.hi_s : P.pb.lo_s, hi_s = P.pb.hi_s;
     const T dt = sub_rn(tend, s);  // :415
     const T sq = sqrt_rn(dt);
     const T mudt = mul_rn(P.pb.mu_c, dt), sgsq = mul_rn(P.pb.sigma_c, sq);
     const int nfull = d / VEC;
-    if (MODE != EM_NOBC && check_src) { // src/reflect.jl:12
+    if (BC && check_src) { // src/reflect.jl:12
         const T* q = sp;
         for (int p = lane; p < nvec; p += G, q += sstride) {
             const Vec<T> xv = ldv<T>(q);
@@ -162,7 +168,11 @@ __device__ __forceinline__ T em_loop_fast(const MlpParams<T>& P, const DrawK<T>&
                 if (p * VEC + e < d && !(xv.v[e] >= lo_s && xv.v[e] <= hi_s)) bad = 1;
         }
     }
+    if (BC) store = true;
     T ssq = (T)0;
+    unsigned fix = 0; // bit j: the j-th vec-group of the current chunk needs its reflection finished
+    int it = 0, p0 = lane;
+    T* dp0 = dp;
     // U vec-groups of this lane (p, p+G, …) per pass
     auto body = [&](int p, auto full_tag, auto u_tag) {
         constexpr bool FULL = decltype(full_tag)::value;
@@ -182,42 +192,72 @@ __device__ __forceinline__ T em_loop_fast(const MlpParams<T>& P, const DrawK<T>&
                 o[u].v[e] = add_rn(o[u].v[e], add_rn(mudt, mul_rn(sgsq, xi[u].v[e]))); // :417
                 if (!FULL && !((p + u * G) * VEC + e < d)) o[u].v[e] = MODE == EM_BOX ? lo_s : (T)0; // padding never reflects
             }
-            if (MODE == EM_SYM) reflect_vec_sym<T>(o[u], hi_s, nb);              // :418-420
-            if (MODE == EM_BOX) {
-                Vec<T> lo, hi;
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) { lo.v[e] = lo_s; hi.v[e] = hi_s; }
-                reflect_vec<T, G>(o[u], lo, hi, 0u, nb);
-            }
+            bool again = false;
+            if (MODE == EM_SYM) again = reflect_first_sym<T>(o[u], hi_s, nb);    // :418-420
+            if (MODE == EM_BOX) again = reflect_first<T>(o[u], lo_s, hi_s, nb);
+            T q = ssq;
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
                 if (!FULL && !((p + u * G) * VEC + e < d)) o[u].v[e] = (T)0; // padding coordinate
-                ssq = xfma(o[u].v[e], o[u].v[e], ssq);
+                q = xfma(o[u].v[e], o[u].v[e], q);
             }
+            ssq = again ? ssq : q;
+            if (BC) fix |= (again ? 1u : 0u) << it;
+            ++it;
             if (store) {
                 stv<T>(dp, o[u]);
                 dp += dstride;
             }
         }
     };
-    int p = lane;
-#if HDP_EM_UNROLL > 1
-    for (; p + (HDP_EM_UNROLL - 1) * G < nfull; p += HDP_EM_UNROLL * G) body(p, FullTag{}, IntTag<HDP_EM_UNROLL>{});
+    // second and later wall hits of the flagged vec-groups, from the values the loop stored
+    auto finish = [&]() {
+        while (fix) {
+#ifdef HDP_HOST_EMU
+            const int j = __builtin_ctz(fix);
+#else
+            const int j = __ffs((int)fix) - 1;
 #endif
-    for (; p < nfull; p += G) body(p, FullTag{}, IntTag<1>{});
-    if (p < nvec) body(p, PartTag{}, IntTag<1>{});
+            fix &= fix - 1;
+            T* q = dp0 + (size_t)j * dstride;
+            Vec<T> o = ldv<T>(q);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                if ((p0 + j * G) * VEC + e < d) o.v[e] = reflect_coord<T>(o.v[e], lo_s, hi_s, nb);
+                ssq = xfma(o.v[e], o.v[e], ssq);
+            }
+            stv<T>(q, o);
+        }
+    };
+    int p = lane;
+    while (p < nvec) {
+        // at most 32 vec-groups per chunk: one bit each in `fix`
+        it = 0;
+        dp0 = dp;
+        p0 = p;
+        const int pe = p + 32 * G < nfull ? p + 32 * G : nfull;
+#if HDP_EM_UNROLL > 1
+        for (; p + (HDP_EM_UNROLL - 1) * G < pe; p += HDP_EM_UNROLL * G) body(p, FullTag{}, IntTag<HDP_EM_UNROLL>{});
+#endif
+        for (; p < pe; p += G) body(p, FullTag{}, IntTag<1>{});
+        if (p >= nfull && p < nvec && it < 32) { // the one partial vec-group (d % VEC != 0), if this lane owns it
+            body(p, PartTag{}, IntTag<1>{});
+            p += G;
+        }
+        if (BC) finish();
+    }
     return ssq;
 }
 
-template <typename T, int G, int MODE, bool STORE>
+template <typename T, int G, int MODE>
 __device__ HDP_NOINLINE Feat<T> em_step_fast(Ctx<T, G>& c, const XAcc<T>& src, const XAcc<T>& dst, T s, T tend, u64 ord)
 {
     constexpr int VEC = Tr<T>::VEC;
     const MlpParams<T>& P = *c.P;
-    const DrawK<T> dk = draw_k_init<T>(P.zero);
+    const DrawK<T> dk = draw_k_init<T>(P.zero & (c.lane + 1));
     int nb = 0, bad = 0;
     const T ssq = em_loop_fast<T, G, MODE>(P, dk, c.seed, c.lane, src.base + src.voff * VEC, (uint32_t)src.vstride * VEC,
-                                           dst.base + dst.voff * VEC, (uint32_t)dst.vstride * VEC, STORE,
+                                           dst.base + dst.voff * VEC, (uint32_t)dst.vstride * VEC, true,
                                            src.unchecked != 0, s, tend, ord, nb, bad);
     c.nb += nb;
     c.bad |= bad;
@@ -313,20 +353,16 @@ __device__ HDP_NOINLINE Feat<T> em_step_generic(Ctx<T, G>& c, const XAcc<T>& src
     return f;
 }
 
-template <typename T, int G, bool STORE>
-__device__ __forceinline__ Feat<T> em_step_s(Ctx<T, G>& c, const XAcc<T>& src, const XAcc<T>& dst, T s, T tend, u64 ord)
+// the stand-alone step (expand pass): dispatch on the mode of this launch; x2 is always kept
+template <typename T, int G>
+__device__ __forceinline__ Feat<T> em_step(Ctx<T, G>& c, const XAcc<T>& src, const XAcc<T>& dst, T s, T tend, u64 ord)
 {
     switch (c.fast) {
-    case EM_NOBC: return em_step_fast<T, G, EM_NOBC, STORE>(c, src, dst, s, tend, ord);
-    case EM_SYM: return em_step_fast<T, G, EM_SYM, STORE>(c, src, dst, s, tend, ord);
-    case EM_BOX: return em_step_fast<T, G, EM_BOX, STORE>(c, src, dst, s, tend, ord);
+    case EM_NOBC: return em_step_fast<T, G, EM_NOBC>(c, src, dst, s, tend, ord);
+    case EM_SYM: return em_step_fast<T, G, EM_SYM>(c, src, dst, s, tend, ord);
+    case EM_BOX: return em_step_fast<T, G, EM_BOX>(c, src, dst, s, tend, ord);
     }
-    return em_step_generic<T, G>(c, src, STORE ? &dst : nullptr, s, tend, ord);
-}
-template <typename T, int G>
-__device__ __forceinline__ Feat<T> em_step(Ctx<T, G>& c, const XAcc<T>& src, const XAcc<T>* dst, T s, T tend, u64 ord)
-{
-    return dst ? em_step_s<T, G, true>(c, src, *dst, s, tend, ord) : em_step_s<T, G, false>(c, src, src, s, tend, ord);
+    return em_step_generic<T, G>(c, src, &dst, s, tend, ord);
 }
 
 // mc_sample!(x3, x2)  (src/MLP.jl:139,177; src/MCSample.jl:28-33, 63-71)
@@ -392,124 +428,6 @@ __device__ __forceinline__ Feat<T> sample_step(Ctx<T, G>& c, const XAcc<T>* dst,
     return c.fast_s ? sample_step_t<T, G, true>(c, dst, x2, ord) : sample_step_t<T, G, false>(c, dst, x2, ord);
 }
 
-template <typename T, int G, int LV> struct Call;
-
-// One (l,k) iteration of the level loops: src/MLP.jl:132-148 (l<=1), :157-194 (l>=2).
-// Returns b3 / K.  (co, ro, so): consumption ordinals at the start of the site.
-template <typename T, int G, int l>
-__device__ __forceinline__ T eval_site(Ctx<T, G>& c, const XAcc<T>& xp, T s, u64 co, u64 ro, u64 so)
-{
-    const MlpParams<T>& P = *c.P;
-    const DevProblem<T>& pb = P.pb;
-    const T t1 = pb.t1;
-    const T u = time_uniform<T, G>(c, ro);
-    const T r = add_rn(s, mul_rn(sub_rn(t1, s), u)); // :132
-    const XAcc<T> x2 = c.slot(2 * l);
-    const XAcc<T> x3 = c.slot(2 * l + 1);
-    const bool shifted = P.sm.kind == HDP_SAMPLER_NORMAL && P.sm.shifted;
-    const bool keep_x2 = (l >= 1) || shifted;
-    const Feat<T> f2 = em_step<T, G>(c, xp, keep_x2 ? &x2 : nullptr, s, r, co); // :133
-    u64 cc = co + 1, rr = ro + 1, qq = so;
-    T b2 = (T)0, b4 = (T)0;
-    if constexpr (l >= 1) {
-        b2 = Call<T, G, l>::run(c, x2, r, cc, rr, qq); // :134
-        cc += P.C[l]; rr += P.R[l]; qq += P.S[l];
-    }
-    if constexpr (l >= 2) {
-        b4 = Call<T, G, l - 1>::run(c, x2, r, cc, rr, qq); // :160-173
-        cc += P.C[l - 1]; rr += P.R[l - 1]; qq += P.S[l - 1];
-    }
-    T b3 = (T)0;
-    // At a level-0 site both U_0 arguments of f are identically zero (:117-119) and no
-    // recursion starts from x3.  When f reads z only through u_z (every non-local kind but the
-    // replicator–mutator), the K sampled points cannot influence the result: they are not
-    // generated.  Their consumption ordinals are still skipped, so tapes stay aligned.
-    const bool dead_samples = (l == 0) && !c.f_uses_z;
-    if (P.Kp > 0 && !dead_samples) {
-        for (int h = 0; h < P.K; ++h) { // :137, :176
-            const Feat<T> f3 = sample_step<T, G>(c, l >= 1 ? &x3 : nullptr, x2, qq); // :139, :177
-            qq += 1;
-            T v = (T)0;
-            if constexpr (l >= 1) {
-                v = Call<T, G, l>::run(c, x3, r, cc, rr, qq);
-                cc += P.C[l]; rr += P.R[l]; qq += P.S[l];
-            }
-            T term = f_eval<T>(pb, f2.ssq, f3.ssq, b2, v); // :140-146
-            if constexpr (l >= 2) {
-                const T w = Call<T, G, l - 1>::run(c, x3, r, cc, rr, qq);
-                cc += P.C[l - 1]; rr += P.R[l - 1]; qq += P.S[l - 1];
-                term = term - f_eval<T>(pb, f2.ssq, f3.ssq, b4, w); // :178-191
-            }
-            b3 += term;
-        }
-    } else {
-        // NoSampling: the K-loop re-evaluates f on identical arguments (:137-147, :210-216)
-        T term = f_eval<T>(pb, f2.ssq, (T)0, b2, (T)0);
-        if constexpr (l >= 2) term = term - f_eval<T>(pb, f2.ssq, (T)0, b4, (T)0);
-        for (int h = 0; h < P.K; ++h) b3 += term;
-    }
-    return b3 / (T)P.K; // :148
-}
-
-// sum of g over `n` plain steps s -> t1 (src/MLP.jl:198-205), ordinals co..co+n-1
-template <typename T, int G>
-__device__ __forceinline__ T g_sum(Ctx<T, G>& c, const XAcc<T>& xp, T s, u64 co, u64 n)
-{
-    const DevProblem<T>& pb = c.P->pb;
-    T a2 = (T)0;
-    for (u64 k = 0; k < n; ++k) {
-        const Feat<T> f = em_step<T, G>(c, xp, nullptr, s, pb.t1, co + k); // :202
-        a2 += g_eval<T>(pb, f);                                            // :203
-    }
-    return a2;
-}
-
-template <typename T, int G, int LV, int l> struct LevelLoop {
-    static __device__ __forceinline__ void run(Ctx<T, G>& c, const XAcc<T>& xp, T s, u64& co, u64& ro, u64& so, T& a)
-    {
-        const MlpParams<T>& P = *c.P;
-        const u64 num = P.Mpow[LV - l];
-        T b = (T)0;
-        for (u64 k = 0; k < num; ++k) {
-            b += eval_site<T, G, l>(c, xp, s, co, ro, so);
-            co += P.cs[l]; ro += P.rs[l]; so += P.ss[l];
-        }
-        a += ((P.pb.t1 - s) * b) / (T)num; // :150, :195
-        LevelLoop<T, G, LV, l + 1>::run(c, xp, s, co, ro, so, a);
-    }
-};
-template <typename T, int G, int LV> struct LevelLoop<T, G, LV, LV> {
-    static __device__ __forceinline__ void run(Ctx<T, G>&, const XAcc<T>&, T, u64&, u64&, u64&, T&) {}
-};
-
-// `_ml_picard(M, LV, K, x, s, t, ...)`  (src/MLP.jl:102-208)
-template <typename T, int G, int LV> struct Call {
-    static __device__ HDP_NOINLINE T run(Ctx<T, G>& c, XAcc<T> xp, T s, u64 co, u64 ro, u64 so)
-    {
-        T a = (T)0;
-        LevelLoop<T, G, LV, 0>::run(c, xp, s, co, ro, so, a);
-        const u64 num = c.P->Mpow[LV];
-        T a2 = g_sum<T, G>(c, xp, s, co, num);
-        a2 /= (T)num;   // :205
-        return a + a2;  // :207
-    }
-};
-template <typename T, int G> struct Call<T, G, 0> {
-    static __device__ __forceinline__ T run(Ctx<T, G>&, XAcc<T>, T, u64, u64, u64) { return (T)0; } // :117-119
-};
-
-template <typename T, int G, int l>
-__device__ HDP_NOINLINE T level_slice(Ctx<T, G>& c, XAcc<T> xp, T s, u64 co, u64 ro, u64 so, u64 n)
-{
-    const MlpParams<T>& P = *c.P;
-    T b = (T)0;
-    for (u64 k = 0; k < n; ++k) {
-        b += eval_site<T, G, l>(c, xp, s, co, ro, so);
-        co += P.cs[l]; ro += P.rs[l]; so += P.ss[l];
-    }
-    return b;
-}
-
 // ---------------------------------------------------------------------
 // The same recursion without calls.  At any moment at most one call of each level is active
 // (a call of level LV only ever starts calls of lower levels), so the frames of the active
@@ -539,7 +457,10 @@ __device__ __forceinline__ T run_unit_iter(Ctx<T, G>& c, const MlpParams<T>& P, 
     const bool has_samples = P.Kp > 0;
     const int K = P.K;
     const int kind = u.kind;
-    const DrawK<T> dk = draw_k_init<T>(P.zero);
+    const u64 seed = c.seed;
+    const int lane = c.lane;
+    const unsigned gmask = c.gmask;
+    const DrawK<T> dk = draw_k_init<T>(P.zero & (lane + 1)); // 0, but neither constant nor uniform to the compiler
     Frame<T> fr[kMaxL + 1];
     int cur, root;
     {
@@ -684,12 +605,14 @@ __device__ __forceinline__ T run_unit_iter(Ctx<T, G>& c, const MlpParams<T>& P, 
                 const XAcc<T> xd = c.slot(a_dst);
                 feat = em_step_generic<T, G>(c, xs, a_store ? &xd : nullptr, a_s, a_t, a_ord);
             } else {
+                // steps that do not keep x2 (level-0 sites, the g term) write it to slot 0, which is
+                // free then: no level-0 site with a kept x2 is active during them
                 const XAcc<T> xd = c.slot(a_store ? a_dst : 0);
-                const T ssq = em_loop_fast<T, G, MODE>(P, dk, c.seed, c.lane, xs.base + xs.voff * VEC,
+                const T ssq = em_loop_fast<T, G, MODE>(P, dk, seed, lane, xs.base + xs.voff * VEC,
                                                        (uint32_t)xs.vstride * VEC, xd.base + xd.voff * VEC,
                                                        (uint32_t)xd.vstride * VEC, a_store, xs.unchecked != 0, a_s,
                                                        a_t, a_ord, nb, bad);
-                feat.ssq = gsum<T, G>(ssq, c.gmask);
+                feat.ssq = gsum<T, G>(ssq, gmask);
             }
         } else {
             const XAcc<T> xd = c.slot(a_dst);
@@ -699,33 +622,6 @@ __device__ __forceinline__ T run_unit_iter(Ctx<T, G>& c, const MlpParams<T>& P, 
     c.nb += nb;
     c.bad |= bad;
     return result;
-}
-
-template <typename T, int G>
-__device__ __forceinline__ T run_unit(Ctx<T, G>& c, const PlanUnit& u, const PlanNode& nd, const XAcc<T>& xp, T s)
-{
-    const u64 n = (u64)(u.k1 - u.k0);
-    if (u.kind == UNIT_WHOLE) {
-        switch (nd.lv) {
-        case 1: return Call<T, G, 1>::run(c, xp, s, u.c, u.r, u.s);
-        case 2: return Call<T, G, 2>::run(c, xp, s, u.c, u.r, u.s);
-        case 3: return Call<T, G, 3>::run(c, xp, s, u.c, u.r, u.s);
-        case 4: return Call<T, G, 4>::run(c, xp, s, u.c, u.r, u.s);
-        case 5: return Call<T, G, 5>::run(c, xp, s, u.c, u.r, u.s);
-        case 6: return Call<T, G, 6>::run(c, xp, s, u.c, u.r, u.s);
-        }
-        return (T)0;
-    }
-    if (u.kind == UNIT_G) return g_sum<T, G>(c, xp, s, u.c, n);
-    switch (u.l) {
-    case 0: return level_slice<T, G, 0>(c, xp, s, u.c, u.r, u.s, n);
-    case 1: return level_slice<T, G, 1>(c, xp, s, u.c, u.r, u.s, n);
-    case 2: return level_slice<T, G, 2>(c, xp, s, u.c, u.r, u.s, n);
-    case 3: return level_slice<T, G, 3>(c, xp, s, u.c, u.r, u.s, n);
-    case 4: return level_slice<T, G, 4>(c, xp, s, u.c, u.r, u.s, n);
-    case 5: return level_slice<T, G, 5>(c, xp, s, u.c, u.r, u.s, n);
-    }
-    return (T)0;
 }
 
 template <typename T, int G>
@@ -782,7 +678,7 @@ __device__ __forceinline__ void expand_item(Ctx<T, G>& c, const MlpParams<T>& P,
     const T u = time_uniform<T, G>(c, st.r);
     const T r = add_rn(s, mul_rn(sub_rn(P.pb.t1, s), u));
     const XAcc<T> x2 = c.point(solve, st.x2_point);
-    const Feat<T> f2 = em_step<T, G>(c, xp, &x2, s, r, st.c);
+    const Feat<T> f2 = em_step<T, G>(c, xp, x2, s, r, st.c);
     if (c.lane == 0) {
         P.site_r[(u64)solve * P.n_sites + sidx] = r;
         P.feat[(u64)solve * P.n_points + st.x2_point] = f2.ssq;
@@ -819,9 +715,6 @@ __device__ __forceinline__ void unit_item(Ctx<T, G>& c, const MlpParams<T>& P, u
     c.nb = 0;
     const T s = nd.time_site < 0 ? P.pb.t0 : P.site_r[(u64)solve * P.n_sites + nd.time_site];
     const XAcc<T> xp = c.point(solve, nd.point);
-#ifdef HDP_MLP_RECURSIVE
-    const T v = run_unit<T, G>(c, un, nd, xp, s);
-#else
     T v;
     switch (c.fast) {
     case EM_NOBC: v = run_unit_iter<T, G, EM_NOBC>(c, P, un, nd, xp, s); break;
@@ -829,7 +722,6 @@ __device__ __forceinline__ void unit_item(Ctx<T, G>& c, const MlpParams<T>& P, u
     case EM_BOX: v = run_unit_iter<T, G, EM_BOX>(c, P, un, nd, xp, s); break;
     default: v = run_unit_iter<T, G, 0>(c, P, un, nd, xp, s); break;
     }
-#endif
     const int nb = gsumi<G>(c.nb, c.gmask);
     if (c.lane == 0) {
         P.partial[(u64)solve * P.n_units + uid] = (double)v;
