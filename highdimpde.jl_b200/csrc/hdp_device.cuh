@@ -344,53 +344,65 @@ __device__ __forceinline__ void sincos_turn52(uint32_t kh, uint32_t kl, double& 
 template <typename T>
 __device__ __forceinline__ Vec<T> draw_vec(u64 seed, int stream, u64 ord, u64 group, bool normal, const DrawK<T>& k);
 
-template <>
-__device__ __forceinline__ Vec<double> draw_vec<double>(u64 seed, int stream, u64 ord, u64 group, bool normal,
-                                                        const DrawK<double>& k)
+// the 128 random bits of a draw, and the VEC normals made from them (two stages, so that a loop can
+// start the integer work of its next pass while the floating-point work of this one is in flight)
+__device__ __forceinline__ Philox4 draw_words(u64 seed, int stream, u64 ord, u64 group)
 {
     uint32_t w0, w1;
     draw_address(stream, ord, group, w0, w1);
-    const Philox4 p = philox4x32_10(w0, w1, (uint32_t)seed, (uint32_t)(seed >> 32));
+    return philox4x32_10(w0, w1, (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+template <typename T> __device__ __forceinline__ Vec<T> normals_from_words(const Philox4& p, const DrawK<T>& k);
+template <> __device__ __forceinline__ Vec<double> normals_from_words<double>(const Philox4& p, const DrawK<double>& k)
+{
     Vec<double> r;
     const uint32_t h1 = p.w[0] >> 12, h2 = p.w[2] >> 12;
-    if (!normal) {
-        r.v[0] = hilo2d(0x3ff00000u | h1, p.w[1]) - 1.0;
-        r.v[1] = hilo2d(0x3ff00000u | h2, p.w[3]) - 1.0;
-    } else {
-        const double u1 = hilo2d(0x3ff00000u | h1, p.w[1] | 1u) - 1.0; // (k1 | 1) 2^-52 in (0,1)
-        const double rad = sqrt_pos(neg2log_unit(u1, k));
-        double sn, cs;
-        sincos_turn52(h2, p.w[3], sn, cs, k);
-        r.v[0] = rad * cs;
-        r.v[1] = rad * sn;
+    const double u1 = hilo2d(0x3ff00000u | h1, p.w[1] | 1u) - 1.0; // (k1 | 1) 2^-52 in (0,1)
+    const double rad = sqrt_pos(neg2log_unit(u1, k));
+    double sn, cs;
+    sincos_turn52(h2, p.w[3], sn, cs, k);
+    r.v[0] = rad * cs;
+    r.v[1] = rad * sn;
+    return r;
+}
+template <> __device__ __forceinline__ Vec<float> normals_from_words<float>(const Philox4& p, const DrawK<float>&)
+{
+    Vec<float> r;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const float u1 = u2f(0x3f800000u | (p.w[2 * h] >> 9)) - 0.99999994f; // (k + 1/2) 2^-23 in (0,1)
+        const float u2 = u2f(0x3f800000u | (p.w[2 * h + 1] >> 9)) - 1.0f;
+        // -2 ln u1 = -2 ln2 * log2(u1)
+        const float tt = -1.3862943611198906f * lg2_approx(u1); // > 0: u1 < 1
+        const float rad = tt * rsq_approx(tt);
+        const float th = 6.283185307179586f * u2;
+        r.v[2 * h] = rad * cos_approx(th);
+        r.v[2 * h + 1] = rad * sin_approx(th);
     }
     return r;
 }
 
 template <>
-__device__ __forceinline__ Vec<float> draw_vec<float>(u64 seed, int stream, u64 ord, u64 group, bool normal,
-                                                      const DrawK<float>&)
+__device__ __forceinline__ Vec<double> draw_vec<double>(u64 seed, int stream, u64 ord, u64 group, bool normal,
+                                                        const DrawK<double>& k)
 {
-    uint32_t w0, w1;
-    draw_address(stream, ord, group, w0, w1);
-    const Philox4 p = philox4x32_10(w0, w1, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const Philox4 p = draw_words(seed, stream, ord, group);
+    if (normal) return normals_from_words<double>(p, k);
+    Vec<double> r;
+    r.v[0] = hilo2d(0x3ff00000u | (p.w[0] >> 12), p.w[1]) - 1.0;
+    r.v[1] = hilo2d(0x3ff00000u | (p.w[2] >> 12), p.w[3]) - 1.0;
+    return r;
+}
+
+template <>
+__device__ __forceinline__ Vec<float> draw_vec<float>(u64 seed, int stream, u64 ord, u64 group, bool normal,
+                                                      const DrawK<float>& k)
+{
+    const Philox4 p = draw_words(seed, stream, ord, group);
+    if (normal) return normals_from_words<float>(p, k);
     Vec<float> r;
-    if (!normal) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) r.v[e] = u2f(0x3f800000u | (p.w[e] >> 9)) - 1.0f;
-    } else {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const float u1 = u2f(0x3f800000u | (p.w[2 * h] >> 9)) - 0.99999994f; // (k + 1/2) 2^-23 in (0,1)
-            const float u2 = u2f(0x3f800000u | (p.w[2 * h + 1] >> 9)) - 1.0f;
-            // -2 ln u1 = -2 ln2 * log2(u1)
-            const float tt = -1.3862943611198906f * lg2_approx(u1); // > 0: u1 < 1
-            const float rad = tt * rsq_approx(tt);
-            const float th = 6.283185307179586f * u2;
-            r.v[2 * h] = rad * cos_approx(th);
-            r.v[2 * h + 1] = rad * sin_approx(th);
-        }
-    }
+    for (int e = 0; e < 4; ++e) r.v[e] = u2f(0x3f800000u | (p.w[e] >> 9)) - 1.0f;
     return r;
 }
 // convenience form for cold call sites

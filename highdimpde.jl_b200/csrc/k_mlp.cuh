@@ -492,110 +492,122 @@ __device__ __forceinline__ T run_unit_iter(Ctx<T, G>& c, const MlpParams<T>& P, 
     Feat<T> feat;
     feat.ssq = (T)0; feat.mn = big<T>();
     for (;;) {
-        Frame<T>& F = fr[cur];
-        const int l = F.l;
+        // One pass runs the bookkeeping from the result of the last action to the next one.  The
+        // handlers are ordered so that every transition except "return to the parent" lands on a
+        // handler further down the same pass.
+        Frame<T>* F = &fr[cur];
+        int l = F->l;
         int act = ACT_NONE;
         // action parameters
         int a_src = 0, a_dst = 0;
         bool a_store = false;
         T a_s = (T)0, a_t = (T)0;
         u64 a_ord = 0;
-        if (st == ST_LEVEL) {
-            if (l < F.lend) {
-                if (F.k < F.num) st = ST_SITE;
-                else {
-                    if (cur == root && kind == UNIT_LEVEL) { result = F.b; break; }
-                    F.a += ((t1 - F.s) * F.b) / (T)F.num; // :150, :195
-                    F.l = l + 1; F.k = 0; F.b = (T)0;
-                    F.num = P.Mpow[F.lv - (l + 1)];
-                }
-            } else { F.k = 0; F.b = (T)0; st = ST_G; }
-        } else if (st == ST_SITE) {
-            const T uu = time_uniform<T, G>(c, F.ro);
-            const T r = add_rn(F.s, mul_rn(sub_rn(t1, F.s), uu)); // :132
-            F.r = r;
-            act = ACT_EM; a_src = F.xslot; a_dst = 2 * l; a_store = (l >= 1) || shifted; a_s = F.s; a_t = r; a_ord = F.co; // :133
-            st = ST_SITE_POST;
-        } else if (st == ST_SITE_POST) {
-            F.f2 = feat.ssq;
-            F.cc = F.co + 1; F.rr = F.ro + 1; F.qq = F.so;
-            F.b2 = (T)0; F.b4 = (T)0; F.b3 = (T)0; F.h = 0;
-            if (l >= 1) { // :134
-                push(l, 2 * l, F.r, F.cc, F.rr, F.qq, cur);
-                F.cc += P.C[l]; F.rr += P.R[l]; F.qq += P.S[l];
-                F.phase = PH_B2; cur = l; st = ST_LEVEL;
-            } else st = ST_SAMPLES;
-        } else if (st == ST_AFTER_B2) {
+        auto enter = [&](int lvc, int xslot) { // start the call U_lvc(slot, r) of the current site
+            push(lvc, xslot, F->r, F->cc, F->rr, F->qq, cur);
+            F->cc += P.C[lvc]; F->rr += P.R[lvc]; F->qq += P.S[lvc];
+            cur = lvc; F = &fr[cur]; l = 0; st = ST_LEVEL;
+        };
+        if (st == ST_RETURN) {
+            if (cur == root) { result = ret; break; }
+            cur = F->parent; F = &fr[cur]; l = F->l;
+            if (F->phase == PH_B2) { F->b2 = ret; st = ST_AFTER_B2; }
+            else if (F->phase == PH_B4) { F->b4 = ret; st = ST_SAMPLES; }
+            else if (F->phase == PH_V) {
+                const T term = f_eval<T>(pb, F->f2, F->f3, F->b2, ret); // :140-146
+                if (l >= 2) {
+                    F->term = term;
+                    F->phase = PH_W;
+                    enter(l - 1, 2 * l + 1);
+                } else { F->b3 += term; F->h += 1; st = ST_SAMPLES; }
+            } else {
+                F->b3 += F->term - f_eval<T>(pb, F->f2, F->f3, F->b4, ret); // :178-191
+                F->h += 1;
+                st = ST_SAMPLES;
+            }
+        }
+        if (st == ST_AFTER_B2) {
             if (l >= 2) { // :160-173
-                push(l - 1, 2 * l, F.r, F.cc, F.rr, F.qq, cur);
-                F.cc += P.C[l - 1]; F.rr += P.R[l - 1]; F.qq += P.S[l - 1];
-                F.phase = PH_B4; cur = l - 1; st = ST_LEVEL;
+                F->phase = PH_B4;
+                enter(l - 1, 2 * l);
             } else st = ST_SAMPLES;
-        } else if (st == ST_SAMPLES) {
+        }
+        if (st == ST_SITE_POST) {
+            F->f2 = feat.ssq;
+            F->cc = F->co + 1; F->rr = F->ro + 1; F->qq = F->so;
+            F->b2 = (T)0; F->b4 = (T)0; F->b3 = (T)0; F->h = 0;
+            if (l >= 1) { // :134
+                F->phase = PH_B2;
+                enter(l, 2 * l);
+            } else st = ST_SAMPLES;
+        }
+        if (st == ST_SAMPLE_POST) {
+            F->f3 = feat.ssq;
+            F->qq += 1;
+            if (l >= 1) {
+                F->phase = PH_V;
+                enter(l, 2 * l + 1);
+            } else {
+                F->b3 += f_eval<T>(pb, F->f2, F->f3, (T)0, (T)0); // :140-146 with U_0 = 0
+                F->h += 1;
+                st = ST_SAMPLES;
+            }
+        }
+        if (st == ST_G_POST) {
+            F->b += g_eval<T>(pb, feat); // :203
+            F->k += 1;
+            st = ST_G;
+        }
+        if (st == ST_SAMPLES) {
             const bool dead_samples = (l == 0) && !c.f_uses_z;
             if (has_samples && !dead_samples) {
-                if (F.h < K) { // :137, :176
-                    act = ACT_SAMPLE; a_dst = 2 * l + 1; a_store = l >= 1; a_src = 2 * l; a_ord = F.qq; // :139, :177
+                if (F->h < K) { // :137, :176
+                    act = ACT_SAMPLE; a_dst = 2 * l + 1; a_store = l >= 1; a_src = 2 * l; a_ord = F->qq; // :139, :177
                     st = ST_SAMPLE_POST;
                 } else st = ST_SITE_END;
             } else {
                 // NoSampling: the K-loop re-evaluates f on identical arguments (:137-147, :210-216)
-                T term = f_eval<T>(pb, F.f2, (T)0, F.b2, (T)0);
-                if (l >= 2) term = term - f_eval<T>(pb, F.f2, (T)0, F.b4, (T)0);
+                T term = f_eval<T>(pb, F->f2, (T)0, F->b2, (T)0);
+                if (l >= 2) term = term - f_eval<T>(pb, F->f2, (T)0, F->b4, (T)0);
                 T b3 = (T)0;
                 for (int h = 0; h < K; ++h) b3 += term;
-                F.b3 = b3;
+                F->b3 = b3;
                 st = ST_SITE_END;
             }
-        } else if (st == ST_SAMPLE_POST) {
-            F.f3 = feat.ssq;
-            F.qq += 1;
-            if (l >= 1) {
-                push(l, 2 * l + 1, F.r, F.cc, F.rr, F.qq, cur);
-                F.cc += P.C[l]; F.rr += P.R[l]; F.qq += P.S[l];
-                F.phase = PH_V; cur = l; st = ST_LEVEL;
-            } else {
-                F.b3 += f_eval<T>(pb, F.f2, F.f3, (T)0, (T)0); // :140-146 with U_0 = 0
-                F.h += 1;
-                st = ST_SAMPLES;
-            }
-        } else if (st == ST_SITE_END) {
-            F.b += F.b3 / (T)K; // :148
-            F.k += 1;
-            F.co += P.cs[l]; F.ro += P.rs[l]; F.so += P.ss[l];
+        }
+        if (st == ST_SITE_END) {
+            F->b += F->b3 / (T)K; // :148
+            F->k += 1;
+            F->co += P.cs[l]; F->ro += P.rs[l]; F->so += P.ss[l];
             st = ST_LEVEL;
-        } else if (st == ST_G) {
-            if (F.k < F.gnum) { // :198-205
-                act = ACT_EM; a_src = F.xslot; a_store = false; a_s = F.s; a_t = t1; a_ord = F.co + F.k; // :202
+        }
+        if (st == ST_LEVEL) {
+            for (;;) {
+                if (l >= F->lend) { F->k = 0; F->b = (T)0; st = ST_G; break; }
+                if (F->k < F->num) { st = ST_SITE; break; }
+                if (cur == root && kind == UNIT_LEVEL) break; // the slice is done: result = b
+                F->a += ((t1 - F->s) * F->b) / (T)F->num; // :150, :195
+                l += 1;
+                F->l = l; F->k = 0; F->b = (T)0;
+                F->num = P.Mpow[F->lv - l];
+            }
+            if (st == ST_LEVEL) { result = F->b; break; }
+        }
+        if (st == ST_SITE) {
+            const T uu = time_uniform<T, G>(c, F->ro);
+            const T r = add_rn(F->s, mul_rn(sub_rn(t1, F->s), uu)); // :132
+            F->r = r;
+            act = ACT_EM; a_src = F->xslot; a_dst = 2 * l; a_store = (l >= 1) || shifted; a_s = F->s; a_t = r; a_ord = F->co; // :133
+            st = ST_SITE_POST;
+        }
+        if (st == ST_G) {
+            if (F->k < F->gnum) { // :198-205
+                act = ACT_EM; a_src = F->xslot; a_store = false; a_s = F->s; a_t = t1; a_ord = F->co + F->k; // :202
                 st = ST_G_POST;
             } else {
-                if (cur == root && kind == UNIT_G) { result = F.b; break; }
-                ret = F.a + F.b / (T)F.gnum; // :205, :207
+                if (cur == root && kind == UNIT_G) { result = F->b; break; }
+                ret = F->a + F->b / (T)F->gnum; // :205, :207
                 st = ST_RETURN;
-            }
-        } else if (st == ST_G_POST) {
-            F.b += g_eval<T>(pb, feat); // :203
-            F.k += 1;
-            st = ST_G;
-        } else { // ST_RETURN
-            if (cur == root) { result = ret; break; }
-            cur = F.parent;
-            Frame<T>& Pf = fr[cur];
-            const int pl = Pf.l;
-            if (Pf.phase == PH_B2) { Pf.b2 = ret; st = ST_AFTER_B2; }
-            else if (Pf.phase == PH_B4) { Pf.b4 = ret; st = ST_SAMPLES; }
-            else if (Pf.phase == PH_V) {
-                const T term = f_eval<T>(pb, Pf.f2, Pf.f3, Pf.b2, ret); // :140-146
-                if (pl >= 2) {
-                    Pf.term = term;
-                    push(pl - 1, 2 * pl + 1, Pf.r, Pf.cc, Pf.rr, Pf.qq, cur);
-                    Pf.cc += P.C[pl - 1]; Pf.rr += P.R[pl - 1]; Pf.qq += P.S[pl - 1];
-                    Pf.phase = PH_W; cur = pl - 1; st = ST_LEVEL;
-                } else { Pf.b3 += term; Pf.h += 1; st = ST_SAMPLES; }
-            } else {
-                Pf.b3 += Pf.term - f_eval<T>(pb, Pf.f2, Pf.f3, Pf.b4, ret); // :178-191
-                Pf.h += 1;
-                st = ST_SAMPLES;
             }
         }
         if (act == ACT_NONE) continue;
