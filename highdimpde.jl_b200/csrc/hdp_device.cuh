@@ -299,29 +299,30 @@ __device__ __forceinline__ double neg2log_unit(double u, const DrawK<double>& k)
     // ne = -(e + [idx >= HDP_LOG_SPLIT]) >= 0 as a double without I2F: (2^52 + ne) - 2^52
     const uint32_t ne = 1023u - (hi >> 20) - ((idx + (128u - HDP_LOG_SPLIT)) >> 7);
     const double ned = hilo2d(0x43300000u, ne) - 0x1p+52;
-    // log1p(r) = r + r^2 q(r)
-    double q = HDP_C7T;
-    q = xfma(q, r, -HDP_C6T);
-    q = xfma(q, r, HDP_C5T);
-    q = xfma(q, r, -0.25);
-    q = xfma(q, r, k.c3);
-    q = xfma(q, r, -0.5);
-    const double p = xfma(r * r, q, r);
-    double res = xfma(p, -2.0, lm2);
-    res = xfma(ned, HDP_TWO_LN2_LOT, res);
-    return xfma(ned, k.two_ln2, res);
+    // the large terms first (off the critical path: they do not need the polynomial)
+    double big = xfma(ned, k.two_ln2, lm2);
+    big = xfma(ned, HDP_TWO_LN2_LOT, big);
+    // log1p(r) = r + r^2 q(r), q = (-1/2 + r/3) + r^2 ((-1/4 + r/5) + r^2 (-1/6 + r/7)): three independent
+    // first-level terms, dependent depth 4 instead of Horner's 7
+    const double r2 = r * r;
+    const double qa = xfma(r, k.c3, -0.5);
+    const double qb = xfma(r, HDP_C5T, -0.25);
+    const double qc = xfma(r, HDP_C7T, -HDP_C6T);
+    const double q = xfma(r2, xfma(r2, qc, qb), qa);
+    const double p = xfma(r2, q, r);
+    return xfma(p, -2.0, big);
 }
 
+// sqrt of a positive normal double: MUFU.RSQ64H seed (≈2^-22), one coupled Goldschmidt step on
+// (g ≈ sqrt x, h ≈ 1/(2 sqrt x)) and a Heron correction; 7 operations, dependent depth 5
 __device__ __forceinline__ double sqrt_pos(double x)
 {
-    double y = rsqrt_approx(x);
-    const double h = 0.5 * x;
-    double t = y * y;
-    t = xfma(-h, t, 1.5);
-    y = y * t;
-    double sq = x * y;
-    const double er = xfma(-sq, sq, x);
-    return xfma(er, 0.5 * y, sq);
+    const double y = rsqrt_approx(x);
+    const double g = x * y, h = 0.5 * y;
+    const double r = xfma(-g, h, 0.5);
+    const double g1 = xfma(g, r, g), h1 = xfma(h, r, h);
+    const double e = xfma(-g1, g1, x);
+    return xfma(e, h1, g1);
 }
 
 // (sin, cos) of 2π k / 2^52 for the 52-bit integer k = (kh : kl), kh < 2^20
