@@ -76,6 +76,7 @@ template <typename T, int G> struct Ctx {
     int bad;
     int fast, fast_s; // em_step (EM_* mode, 0 = general form) / sample_step may take their fast specialisation
     int f_uses_z;     // f reads the sampled point itself (sum(z^2)), not only u(z)
+    void* frame_mem;  // units kernel: this lane group's Frame<T> in shared memory
     __device__ __forceinline__ XAcc<T> slot(int k) const
     {
         XAcc<T> a;
@@ -118,6 +119,14 @@ template <int G> __device__ __forceinline__ int gsumi(int v, unsigned mask)
     return v;
 }
 
+__device__ __forceinline__ void group_sync(unsigned mask)
+{
+#ifndef HDP_HOST_EMU
+    __syncwarp(mask);
+#else
+    (void)mask;
+#endif
+}
 template <typename T> __device__ __forceinline__ T big() { return (T)3.0e38; }
 
 // rand(tType)  (src/MLP.jl:132)
@@ -461,32 +470,33 @@ __device__ __forceinline__ T run_unit_iter(Ctx<T, G>& c, const MlpParams<T>& P, 
     const int lane = c.lane;
     const unsigned gmask = c.gmask;
     const DrawK<T> dk = draw_k_init<T>(P.zero & (lane + 1)); // 0, but neither constant nor uniform to the compiler
-    Frame<T> fr[kMaxL + 1];
+    // The frame of the innermost active call lives in shared memory (one per lane group: its
+    // lanes read and write the same cells with the same values); the frames of its callers are
+    // parked in local memory and only touched when a call starts or returns.
+    Frame<T> parked[kMaxL + 1];
+#ifdef HDP_HOST_EMU
+    Frame<T> frame0;
+    Frame<T>* const F = &frame0;
+#else
+    Frame<T>* const F = static_cast<Frame<T>*>(c.frame_mem);
+#endif
     int cur, root;
     {
         const u64 n = (u64)(u.k1 - u.k0);
         root = kind == UNIT_WHOLE ? nd.lv : (kind == UNIT_G ? 1 : u.l + 1);
-        Frame<T>& F = fr[root];
-        F.lv = root;
-        F.l = kind == UNIT_LEVEL ? u.l : 0;
-        F.lend = kind == UNIT_WHOLE ? nd.lv : (kind == UNIT_G ? 0 : u.l + 1);
-        F.k = 0;
-        F.num = kind == UNIT_LEVEL ? n : P.Mpow[root];
-        F.gnum = kind == UNIT_G ? n : P.Mpow[root];
-        F.a = (T)0; F.b = (T)0;
-        F.s = s0;
-        F.xslot = -1;
-        F.co = u.c; F.ro = u.r; F.so = u.s;
-        F.parent = -1;
+        F->lv = root;
+        F->l = kind == UNIT_LEVEL ? u.l : 0;
+        F->lend = kind == UNIT_WHOLE ? nd.lv : (kind == UNIT_G ? 0 : u.l + 1);
+        F->k = 0;
+        F->num = kind == UNIT_LEVEL ? n : P.Mpow[root];
+        F->gnum = kind == UNIT_G ? n : P.Mpow[root];
+        F->a = (T)0; F->b = (T)0;
+        F->s = s0;
+        F->xslot = -1;
+        F->co = u.c; F->ro = u.r; F->so = u.s;
+        F->parent = -1;
         cur = root;
     }
-    auto push = [&](int lvc, int xslot, T s, u64 co, u64 ro, u64 so, int parent) {
-        Frame<T>& Cf = fr[lvc];
-        Cf.lv = lvc; Cf.l = 0; Cf.lend = lvc; Cf.k = 0;
-        Cf.num = P.Mpow[lvc]; Cf.gnum = P.Mpow[lvc];
-        Cf.a = (T)0; Cf.b = (T)0; Cf.s = s; Cf.xslot = xslot;
-        Cf.co = co; Cf.ro = ro; Cf.so = so; Cf.parent = parent;
-    };
     int st = ST_LEVEL, nb = 0, bad = 0;
     T ret = (T)0, result = (T)0;
     Feat<T> feat;
@@ -495,7 +505,7 @@ __device__ __forceinline__ T run_unit_iter(Ctx<T, G>& c, const MlpParams<T>& P, 
         // One pass runs the bookkeeping from the result of the last action to the next one.  The
         // handlers are ordered so that every transition except "return to the parent" lands on a
         // handler further down the same pass.
-        Frame<T>* F = &fr[cur];
+        group_sync(gmask); // the lanes of a group update their shared frame in lockstep
         int l = F->l;
         int act = ACT_NONE;
         // action parameters
@@ -504,13 +514,21 @@ __device__ __forceinline__ T run_unit_iter(Ctx<T, G>& c, const MlpParams<T>& P, 
         T a_s = (T)0, a_t = (T)0;
         u64 a_ord = 0;
         auto enter = [&](int lvc, int xslot) { // start the call U_lvc(slot, r) of the current site
-            push(lvc, xslot, F->r, F->cc, F->rr, F->qq, cur);
-            F->cc += P.C[lvc]; F->rr += P.R[lvc]; F->qq += P.S[lvc];
-            cur = lvc; F = &fr[cur]; l = 0; st = ST_LEVEL;
+            const T s = F->r;
+            const u64 co = F->cc, ro = F->rr, so = F->qq;
+            F->cc = co + P.C[lvc]; F->rr = ro + P.R[lvc]; F->qq = so + P.S[lvc];
+            parked[cur] = *F;
+            F->lv = lvc; F->l = 0; F->lend = lvc; F->k = 0;
+            F->num = P.Mpow[lvc]; F->gnum = P.Mpow[lvc];
+            F->a = (T)0; F->b = (T)0; F->s = s; F->xslot = xslot;
+            F->co = co; F->ro = ro; F->so = so; F->parent = cur;
+            cur = lvc; l = 0; st = ST_LEVEL;
         };
         if (st == ST_RETURN) {
             if (cur == root) { result = ret; break; }
-            cur = F->parent; F = &fr[cur]; l = F->l;
+            cur = F->parent;
+            *F = parked[cur];
+            l = F->l;
             if (F->phase == PH_B2) { F->b2 = ret; st = ST_AFTER_B2; }
             else if (F->phase == PH_B4) { F->b4 = ret; st = ST_SAMPLES; }
             else if (F->phase == PH_V) {
@@ -646,6 +664,7 @@ __device__ __forceinline__ void ctx_init(Ctx<T, G>& c, const MlpParams<T>& P, u6
     c.nb = 0;
     c.bad = 0;
     c.seed = 0;
+    c.frame_mem = nullptr;
     c.fast = 0;
     if (P.pb.mu_kind == HDP_COEF_CONST && P.pb.sigma_kind == HDP_COEF_CONST && (!P.pb.has_bc || P.pb.bc_is_scalar) &&
         P.n_tape == nullptr && P.pb.g_kind != HDP_G_MIN && P.pb.g_kind != HDP_G_USER)
@@ -842,6 +861,7 @@ __device__ __forceinline__ void init_item(const MlpParams<T>& P, const T* x0, u6
 // ---------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------
+extern __shared__ double2 hdp_dyn_smem[]; // units kernel: (blockDim.x / G) * sizeof(Frame<T>) bytes
 template <typename T>
 __global__ void mlp_init_kernel(const __grid_constant__ MlpParams<T> P, const T* __restrict__ x0)
 {
@@ -874,6 +894,7 @@ __global__ void __launch_bounds__(128, HDP_MLP_MINBLOCKS) mlp_units_kernel(const
     Ctx<T, G> c;
     const int lane_w = threadIdx.x & 31;
     ctx_init<T, G>(c, P, (u64)blockIdx.x * blockDim.x + threadIdx.x, lane_w);
+    c.frame_mem = reinterpret_cast<Frame<T>*>(hdp_dyn_smem) + threadIdx.x / G; // blockDim.x / G frames
     const int sub = lane_w / G;
     const u64 n_work = (u64)P.n_units * (u64)P.n_solves;
     const u64 n_local = n_work > (u64)P.rank ? (n_work - (u64)P.rank + (u64)P.nranks - 1) / (u64)P.nranks : 0;

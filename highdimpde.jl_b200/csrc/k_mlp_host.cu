@@ -182,13 +182,15 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
     UserModule* um = nullptr;
     if (uses_user && (rc = get_user_module(h, prob, cfg->user, sizeof(T) == 4, G, &um)) != HDP_OK) return rc;
     const int block = 128;
+    // dynamic shared memory of the units kernel: one Frame<T> per lane group (k_mlp.cuh, run_unit_iter)
+    const size_t dyn_smem = (size_t)(block / G) * sizeof(Frame<T>);
     int bps = 0;
     if (um) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, (const void*)um->units, block, 0) != cudaSuccess) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, (const void*)um->units, block, dyn_smem) != cudaSuccess) {
             (void)cudaGetLastError();
             bps = 0;
         }
-    } else bps = LN.max_blocks_per_sm(block);
+    } else bps = LN.max_blocks_per_sm(block, dyn_smem);
     if (bps < 1) return set_err(h, HDP_ERR_CUDA, "occupancy query failed for the MLP kernel");
     const int sms = h->prop.multiProcessorCount;
     const int nranks = h->nccl_comm ? h->nccl_nranks : 1;
@@ -315,8 +317,8 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
     if (n_local > 0) {
         if (um) {
             void* args[1] = {(void*)&P};
-            HDP_CUDA(h, cudaLaunchKernel((const void*)um->units, dim3(grid), dim3(block), args, 0, h->stream));
-        } else HDP_CUDA(h, LN.units(P, grid, block, h->stream));
+            HDP_CUDA(h, cudaLaunchKernel((const void*)um->units, dim3(grid), dim3(block), args, dyn_smem, h->stream));
+        } else HDP_CUDA(h, LN.units(P, grid, block, dyn_smem, h->stream));
         h->launches++;
     }
     HDP_CUDA(h, cudaEventRecord(h->evp[1], h->stream));

@@ -12,18 +12,18 @@ namespace {
 typedef HDP_INST_T T_;
 constexpr int G_ = HDP_INST_G;
 
-static int inst_max_blocks(int block)
+static int inst_max_blocks(int block, size_t dyn_smem)
 {
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mlp_units_kernel<T_, G_>, block, 0) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mlp_units_kernel<T_, G_>, block, dyn_smem) != cudaSuccess) {
         (void)cudaGetLastError();
         return 0;
     }
     return nb;
 }
-static cudaError_t inst_units(const MlpParams<T_>& P, int grid, int block, cudaStream_t st)
+static cudaError_t inst_units(const MlpParams<T_>& P, int grid, int block, size_t dyn_smem, cudaStream_t st)
 {
-    mlp_units_kernel<T_, G_><<<grid, block, 0, st>>>(P);
+    mlp_units_kernel<T_, G_><<<grid, block, dyn_smem, st>>>(P);
     return cudaGetLastError();
 }
 static cudaError_t inst_expand(const MlpParams<T_>& P, int off, int count, int grid, int block, cudaStream_t st)
