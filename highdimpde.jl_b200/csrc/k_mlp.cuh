@@ -18,9 +18,22 @@
 
 namespace hdp {
 
-#ifndef HDP_EM_UNROLL
-#define HDP_EM_UNROLL 1
+// Launch tuning of the units kernel, per lane-group width (measured on B200, BASELINE C1/C2/C4/C5):
+// wide groups (d >= 100) run best with three vec-groups of a lane in flight per pass — three
+// independent Philox / Box–Muller chains — at 4 blocks per SM (128 registers); narrow groups
+// (d = 10: five vec-groups per lane) with one chain at 6 blocks per SM (80 registers).
+template <int G> struct Tune {
+#ifdef HDP_EM_UNROLL
+    static constexpr int U = HDP_EM_UNROLL;
+#else
+    static constexpr int U = G >= 4 ? 3 : 1;
 #endif
+#ifdef HDP_MLP_MINBLOCKS
+    static constexpr int MB = HDP_MLP_MINBLOCKS;
+#else
+    static constexpr int MB = G >= 4 ? 4 : 6;
+#endif
+};
 template <int N> struct IntTag { static constexpr int value = N; };
 struct FullTag { static constexpr bool value = true; };
 struct PartTag { static constexpr bool value = false; };
@@ -245,9 +258,9 @@ __device__ __forceinline__ T em_loop_fast(const MlpParams<T>& P, const DrawK<T>&
         dp0 = dp;
         p0 = p;
         const int pe = p + 32 * G < nfull ? p + 32 * G : nfull;
-#if HDP_EM_UNROLL > 1
-        for (; p + (HDP_EM_UNROLL - 1) * G < pe; p += HDP_EM_UNROLL * G) body(p, FullTag{}, IntTag<HDP_EM_UNROLL>{});
-#endif
+        constexpr int U = Tune<G>::U;
+        if (U > 1)
+            for (; p + (U - 1) * G < pe; p += U * G) body(p, FullTag{}, IntTag<U>{});
         for (; p < pe; p += G) body(p, FullTag{}, IntTag<1>{});
         if (p >= nfull && p < nvec && it < 32) { // the one partial vec-group (d % VEC != 0), if this lane owns it
             body(p, PartTag{}, IntTag<1>{});
@@ -883,11 +896,8 @@ __global__ void __launch_bounds__(128) mlp_expand_kernel(const __grid_constant__
 
 // the work units: dynamic fetch, one warp takes 32/G consecutive work items at a time
 // (lane groups of a warp then run equal-shaped units in lockstep)
-#ifndef HDP_MLP_MINBLOCKS
-#define HDP_MLP_MINBLOCKS 6
-#endif
 template <typename T, int G>
-__global__ void __launch_bounds__(128, HDP_MLP_MINBLOCKS) mlp_units_kernel(const __grid_constant__ MlpParams<T> P)
+__global__ void __launch_bounds__(128, Tune<G>::MB) mlp_units_kernel(const __grid_constant__ MlpParams<T> P)
 {
     constexpr int GPW = 32 / G;
     if constexpr (sizeof(T) == 8) tables_init();
