@@ -37,6 +37,9 @@ D, M, L, K = 100, 4, 4, 10
 SOLVES_PER_GPU = 4096
 PATH_STEPS_PER_SOLVE = 4916          # C(4) for M=4 local
 I64_PER_COORD_STEP = 39              # fp64 pipe-instr budget per reflected coordinate-step
+I64_EXECUTED = 30.8                  # what the kernel executes per coordinate-step (ncu fp64-pipe % x cycles, profiles/r1j)
+# dram__bytes_read.sum + dram__bytes_write.sum of one units launch on this workload (ncu --set full, profiles/r1j)
+DRAM_TRAFFIC_PER_LAUNCH = 167.3e6 + 604.6e6
 F_ALG_PER_COORD_STEP = 11            # algorithmic FLOP per reflected coordinate-step
 METRIC = "mlp_solves_per_sec"
 UNIT = "solves/s"
@@ -252,14 +255,20 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": WORKLOAD, "solves_per_gpu_per_step": n_local, "global_solves_per_step": n_total,
                        "parallelism": f"solves sharded over {world} rank(s), no data-path collective",
                        "l2": "256 MB flush between steps (untimed); the path is compute-bound, inputs are d doubles",
-                       "rng": "Philox4x32-10 + fp64 Box-Muller generated in registers"},
+                       "rng": "Philox4x32-10 (fixed key, seed and consumption ordinal in the counter) + table-driven fp64 Box-Muller, generated in registers"},
             "reflected_path_steps_per_sec": value * PATH_STEPS_PER_SOLVE,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": D * 8, "d2h_bytes_per_step": n_local * 8,
                     "ms_per_step": 1e3 * e2e_s / args.steps, "api": "hdpde_b200._ml_picard_batch -> hdp_mlp_solve_f64 (host buffers)"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": achieved / 1e12, "peak": peak64 / 1e12, "unit": "Tlane-instr/s",
-                         "frac": achieved / peak64, "traffic": None,
+                         "frac": achieved / peak64, "traffic": DRAM_TRAFFIC_PER_LAUNCH,
+                         "traffic_note": "bytes per units launch (4096 solves), ncu capture profiles/r1j_mlp_units_full.md: "
+                                         "scratch frames of the tree walk; 0.09 TB/s, not the bound",
+                         "executed": {"fp64_instr_per_coord_step": I64_EXECUTED,
+                                      "frac": coord_steps_per_s_gpu * I64_EXECUTED / peak64,
+                                      "note": "fp64-pipe utilisation actually reached (the table-driven Box-Muller "
+                                              "needs fewer fp64 instructions than the 8(d) budget)"},
                          "kernel": "mlp_units_kernel<double,G>",
                          "algorithmic": f"{I64_PER_COORD_STEP} fp64 pipe-instr per reflected coordinate-step x "
                                         f"{PATH_STEPS_PER_SOLVE * D} coordinate-steps per solve (SURVEY.md 8d)",

@@ -126,7 +126,11 @@ enum {
     HDP_NORMAL_BM32 = 2      /* Box-Muller, 32-bit uniforms, fp32 MUFU transcendentals */
 };
 
-/* random streams (one Philox stream id per consumer) */
+/* random streams (one Philox stream id per consumer).  Every draw is Philox4x32-10 with a fixed
+ * key at counter (w0, w1, seed_lo, seed_hi); (w0, w1) packs (stream, ordinal, group):
+ * TIME/STEP/SAMPLER: ordinal < 2^40 (the reference's consumption ordinal), group < 2^21
+ * (vec-group of a point); SDE/X0/MC: ordinal < 2^24 (step or sample index), group < 2^37
+ * (vec-group of the whole d×B array).  Larger requests return HDP_ERR_BAD_ARG. */
 enum {
     HDP_STREAM_TIME = 0,     /* uniforms r   (src/MLP.jl:132)          */
     HDP_STREAM_STEP = 1,     /* normals of `_mlt_sde_loop!` (:416)     */
