@@ -41,6 +41,7 @@ I64_EXECUTED = 30.8                  # what the kernel executes per coordinate-s
 # dram__bytes_read.sum + dram__bytes_write.sum of one units launch on this workload (ncu --set full, profiles/r1j)
 DRAM_TRAFFIC_PER_LAUNCH = 167.3e6 + 604.6e6
 F_ALG_PER_COORD_STEP = 11            # algorithmic FLOP per reflected coordinate-step
+print_line = print
 METRIC = "mlp_solves_per_sec"
 UNIT = "solves/s"
 WORKLOAD = "C2: MLP Allen-Cahn d=100, Neumann reflection [-1/2,1/2]^d, M=4 L=4 K=10, fp64, x0=0, tspan=(0,0.5)"
@@ -153,7 +154,7 @@ def run_reference(args, rank, world):
         "reflected_path_steps_per_sec": value * PATH_STEPS_PER_SOLVE,
         "u_mean": float(np.mean(us)),
     }
-    print(json.dumps(line), flush=True)
+    print_line(json.dumps(line))
 
 
 # --------------------------------------------------------------------------- our arm
@@ -281,7 +282,7 @@ def run_ours(args, rank, world, local_rank):
             "u_mean": float(np.mean(means)), "bounces_per_path_step": bounces / (n_total * args.steps * PATH_STEPS_PER_SOLVE),
             "extra": extra,
         }
-        print(json.dumps(line), flush=True)
+        print_line(json.dumps(line))
     h.close()
     if dist is not None:
         dist.destroy_process_group()
@@ -383,6 +384,17 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # The contract is ONE JSON line on stdout: park the real stdout and send everything that
+    # libraries print while the bench runs (NCCL's version banner, …) to stderr.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(real_stdout, (line + "\n").encode())
+
+    global print_line
+    print_line = emit
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
