@@ -231,6 +231,65 @@ def test_mlp_philox_mode_equals_its_own_tape(H, O, handle):
             assert rel_err(float(u[i]), uo) <= TOL[dt], (name, i)
 
 
+def _philox_tapes(H, handle, prob, alg, dt, seed):
+    nl = H._integrate(alg.mc_sample)
+    cn = H.mlp_counts(alg.M, alg.L, alg.K, nl)
+    r = handle.tape_fill(dt, H.capi.HDP_STREAM_TIME, False, seed, 0, cn["time_uniforms"], 1)
+    n = handle.tape_fill(dt, H.capi.HDP_STREAM_STEP, True, seed, 0, cn["path_steps"], prob.d)
+    s = None
+    if nl:
+        s = handle.tape_fill(dt, H.capi.HDP_STREAM_SAMPLER, isinstance(alg.mc_sample, H.NormalSampling), seed, 0,
+                             cn["sampler_calls"], prob.d)
+    return r, n, s
+
+
+def _fast_loop_cases(H):
+    """The specialised coordinate loops of the units kernel (em_loop_fast): no boundary, symmetric scalar box,
+    general scalar box; odd d (a partial vec-group), more than 32 vec-groups per lane (chunked fix-up mask),
+    steps far larger than the box (second and later wall hits, far excursions)."""
+    c = {}
+    c["sym_d5"] = (H.ParabolicPDEProblem(0.0, 1.0, np.zeros(5), (0.0, 0.5), g=H.ExpSumSq(0.25), f=H.FAllenCahn(1.0),
+                                         neumann_bc=(-0.5, 0.5)), H.MLP(M=3, L=3, K=2), np.float64)
+    c["box_d6"] = (H.ParabolicPDEProblem(0.0, 1.0, np.full(6, 0.1), (0.0, 0.5), g=H.ExpSumSq(0.25), f=H.FAllenCahn(1.0),
+                                         neumann_bc=(-0.3, 0.7)), H.MLP(M=3, L=3, K=2), np.float64)
+    c["box_d7_f32"] = (H.ParabolicPDEProblem(0.0, 1.0, np.full(7, 0.1, dtype=np.float32), (0.0, 0.5), g=H.ExpSumSq(0.25),
+                                             f=H.FAllenCahn(1.0), neumann_bc=(-0.3, 0.7)), H.MLP(M=3, L=3, K=2), np.float32)
+    c["nobc_d9"] = (H.ParabolicPDEProblem(0.05, 0.3, np.zeros(9), (0.0, 0.5), g=H.ExpSumSq(0.25), f=H.FAllenCahn(1.0)),
+                    H.MLP(M=3, L=3, K=2), np.float64)
+    c["wild_sym_d4"] = (H.ParabolicPDEProblem(0.0, 40.0, np.zeros(4), (0.0, 1.0), g=H.ExpSumSq(0.25), f=H.FAllenCahn(1.0),
+                                              neumann_bc=(-0.5, 0.5)), H.MLP(M=3, L=3, K=2), np.float64)
+    c["wild_far_d4"] = (H.ParabolicPDEProblem(0.0, 900.0, np.zeros(4), (0.0, 1.0), g=H.ExpSumSq(0.25), f=H.FAllenCahn(1.0),
+                                              neumann_bc=(-0.5, 0.5)), H.MLP(M=2, L=3, K=2), np.float64)
+    c["nonlocal_sym_d5"] = (H.PIDEProblem(0.0, 0.6, np.zeros(5), (0.0, 0.5), H.ExpSumSq(0.25), H.FNLAllenCahnDiff(),
+                                          neumann_bc=(-0.5, 0.5)),
+                            H.MLP(M=3, L=3, K=3, mc_sample=H.UniformSampling(-0.5, 0.5)), np.float64)
+    c["long_d2101"] = (H.ParabolicPDEProblem(0.0, 1.0, np.zeros(2101), (0.0, 0.5), g=H.ExpSumSq(1e-3), f=H.FAllenCahn(1.0),
+                                             neumann_bc=(-0.5, 0.5)), H.MLP(M=2, L=2, K=2), np.float64)
+    return c
+
+
+@pytest.mark.parametrize("name", ["sym_d5", "box_d6", "box_d7_f32", "nobc_d9", "wild_sym_d4", "wild_far_d4",
+                                  "nonlocal_sym_d5", "long_d2101"])
+def test_mlp_fast_loops_match_oracle_on_their_own_draws(H, O, handle, name, monkeypatch):
+    """RNG mode runs the specialised loops; the oracle is fed the very draws (hdp_tape_fill): values to tolerance,
+    wall-hit counts exact, whatever the lane-group width and the tree cut."""
+    prob, alg, dt = _fast_loop_cases(H)[name]
+    seed = 4242
+    tapes = _philox_tapes(H, handle, prob, alg, dt, seed)
+    uo, info = oracle_solve(H, O, prob, alg, dt, tapes)
+    assert info["rc"] == 0
+    groups = (None, 32) if name == "long_d2101" else (None, 1, 2, 8, 32)
+    for G in groups:
+        if G is None:
+            monkeypatch.delenv("HDP_MLP_GROUP", raising=False)
+        else:
+            monkeypatch.setenv("HDP_MLP_GROUP", str(G))
+        for target in (1, 50, 0):
+            u, st = H._ml_picard_batch(prob, alg, n_solves=1, seed=seed, target_units=target, handle=handle, dtype=dt)
+            assert rel_err(float(u[0]), uo) <= TOL[dt], (name, G, target, float(u[0]), uo)
+            assert st["bounces"] == info["bounces"], (name, G, target)
+
+
 def test_mlp_compat_mlt_partition(H, O, handle):
     """`_ml_picard_mlt` with Threads.nthreads()==NT (src/MLP.jl:218-404), quirk Q4."""
     prob, alg, dt = zoo(H)["allen_cahn_neumann_d5"]
