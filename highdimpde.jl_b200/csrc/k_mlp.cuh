@@ -18,20 +18,16 @@
 
 namespace hdp {
 
-// Launch tuning of the units kernel, per lane-group width (measured on B200, BASELINE C1/C2/C4/C5):
-// wide groups (d >= 100) run best with three vec-groups of a lane in flight per pass — three
-// independent Philox / Box–Muller chains — at 4 blocks per SM (128 registers); narrow groups
-// (d = 10: five vec-groups per lane) with one chain at 6 blocks per SM (80 registers).
-template <int G> struct Tune {
-#ifdef HDP_EM_UNROLL
-    static constexpr int U = HDP_EM_UNROLL;
-#else
-    static constexpr int U = G >= 4 ? 3 : 1;
-#endif
+// Launch tuning of the units kernel (measured on B200, BASELINE C1/C2/C4/C5): points with many
+// vec-groups per lane (d >= 100) run best with three of them in flight per pass — three
+// independent Philox / Box–Muller chains — at 4 blocks per SM (128 registers); short rows (d = 10:
+// five vec-groups per lane) with one chain at 6 blocks per SM (80 registers).  U is a template
+// parameter of the kernel; the host picks it from the row length.
+template <int U> struct Tune {
 #ifdef HDP_MLP_MINBLOCKS
     static constexpr int MB = HDP_MLP_MINBLOCKS;
 #else
-    static constexpr int MB = G >= 4 ? 4 : 6;
+    static constexpr int MB = U >= 2 ? 4 : 6;
 #endif
 };
 template <int N> struct IntTag { static constexpr int value = N; };
@@ -163,12 +159,12 @@ template <typename T, int G> __device__ __forceinline__ T time_uniform(const Ctx
 enum { EM_NOBC = 1, EM_SYM = 2, EM_BOX = 3 };
 
 // The coordinate loop itself; returns this lane's share of sum(x2^2).
-// With a boundary the loop always writes x2 (`dp` must be valid; callers that do not keep x2
-// pass a free scratch slot): a vec-group in which a coordinate is still outside after its
-// first mirror — a second wall hit in one step, ≈0.5 % of the coordinates of BASELINE C2 — is
-// only flagged in a bit mask, and finished after the loop from the stored values.  The loop
-// body therefore has no branch, no call and no convergence barrier.
-template <typename T, int G, int MODE>
+// A vec-group in which a coordinate is still outside after its first mirror — a second wall hit
+// in one step, ≈0.5 % of the coordinates of BASELINE C2 — is only flagged in a bit mask and
+// parked in a small per-thread stash (local memory: write-back cached, unlike a global store),
+// and finished after the loop.  The loop body therefore has no branch, no call and no
+// convergence barrier.
+template <typename T, int G, int MODE, int U = 1>
 __device__ __forceinline__ T em_loop_fast(const MlpParams<T>& P, const DrawK<T>& dk, u64 seed, int lane, const T* sp,
                                           uint32_t sstride, T* dp, uint32_t dstride, bool store, bool check_src, T s,
                                           T tend, u64 ord, int& nb, int& bad)
@@ -190,25 +186,25 @@ __device__ __forceinline__ T em_loop_fast(const MlpParams<T>& P, const DrawK<T>&
                 if (p * VEC + e < d && !(xv.v[e] >= lo_s && xv.v[e] <= hi_s)) bad = 1;
         }
     }
-    if (BC) store = true;
     T ssq = (T)0;
     unsigned fix = 0; // bit j: the j-th vec-group of the current chunk needs its reflection finished
+    Vec<T> stash[32]; // … and waits here
     int it = 0, p0 = lane;
     T* dp0 = dp;
     // U vec-groups of this lane (p, p+G, …) per pass
     auto body = [&](int p, auto full_tag, auto u_tag) {
         constexpr bool FULL = decltype(full_tag)::value;
-        constexpr int U = decltype(u_tag)::value;
-        Vec<T> xi[U], o[U];
+        constexpr int UU = decltype(u_tag)::value;
+        Vec<T> xi[UU], o[UU];
 #pragma unroll
-        for (int u = 0; u < U; ++u) xi[u] = draw_vec<T>(seed, HDP_STREAM_STEP, ord, (u64)(p + u * G), true, dk); // :416 randn!(x2)
+        for (int u = 0; u < UU; ++u) xi[u] = draw_vec<T>(seed, HDP_STREAM_STEP, ord, (u64)(p + u * G), true, dk); // :416 randn!(x2)
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
+        for (int u = 0; u < UU; ++u) {
             o[u] = ldv<T>(sp);
             sp += sstride;
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
+        for (int u = 0; u < UU; ++u) {
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
                 o[u].v[e] = add_rn(o[u].v[e], add_rn(mudt, mul_rn(sgsq, xi[u].v[e]))); // :417
@@ -224,7 +220,10 @@ __device__ __forceinline__ T em_loop_fast(const MlpParams<T>& P, const DrawK<T>&
                 q = xfma(o[u].v[e], o[u].v[e], q);
             }
             ssq = again ? ssq : q;
-            if (BC) fix |= (again ? 1u : 0u) << it;
+            if (BC) {
+                fix |= (again ? 1u : 0u) << it;
+                if (again) stash[it] = o[u];
+            }
             ++it;
             if (store) {
                 stv<T>(dp, o[u]);
@@ -232,7 +231,7 @@ __device__ __forceinline__ T em_loop_fast(const MlpParams<T>& P, const DrawK<T>&
             }
         }
     };
-    // second and later wall hits of the flagged vec-groups, from the values the loop stored
+    // second and later wall hits of the flagged vec-groups
     auto finish = [&]() {
         while (fix) {
 #ifdef HDP_HOST_EMU
@@ -241,14 +240,13 @@ __device__ __forceinline__ T em_loop_fast(const MlpParams<T>& P, const DrawK<T>&
             const int j = __ffs((int)fix) - 1;
 #endif
             fix &= fix - 1;
-            T* q = dp0 + (size_t)j * dstride;
-            Vec<T> o = ldv<T>(q);
+            Vec<T> o = stash[j];
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
                 if ((p0 + j * G) * VEC + e < d) o.v[e] = reflect_coord<T>(o.v[e], lo_s, hi_s, nb);
                 ssq = xfma(o.v[e], o.v[e], ssq);
             }
-            stv<T>(q, o);
+            if (store) stv<T>(dp0 + (size_t)j * dstride, o);
         }
     };
     int p = lane;
@@ -258,7 +256,6 @@ __device__ __forceinline__ T em_loop_fast(const MlpParams<T>& P, const DrawK<T>&
         dp0 = dp;
         p0 = p;
         const int pe = p + 32 * G < nfull ? p + 32 * G : nfull;
-        constexpr int U = Tune<G>::U;
         if (U > 1)
             for (; p + (U - 1) * G < pe; p += U * G) body(p, FullTag{}, IntTag<U>{});
         for (; p < pe; p += G) body(p, FullTag{}, IntTag<1>{});
@@ -468,7 +465,7 @@ enum { PH_B2 = 0, PH_B4 = 1, PH_V = 2, PH_W = 3 };
 enum { ST_LEVEL = 0, ST_SITE, ST_SITE_POST, ST_AFTER_B2, ST_SAMPLES, ST_SAMPLE_POST, ST_SITE_END, ST_G, ST_G_POST, ST_RETURN };
 enum { ACT_NONE = 0, ACT_EM = 1, ACT_SAMPLE = 2 };
 
-template <typename T, int G, int MODE>
+template <typename T, int G, int MODE, int U>
 __device__ __forceinline__ T run_unit_iter(Ctx<T, G>& c, const MlpParams<T>& P, const PlanUnit& u, const PlanNode& nd,
                                            const XAcc<T>& xp, T s0)
 {
@@ -648,10 +645,8 @@ __device__ __forceinline__ T run_unit_iter(Ctx<T, G>& c, const MlpParams<T>& P, 
                 const XAcc<T> xd = c.slot(a_dst);
                 feat = em_step_generic<T, G>(c, xs, a_store ? &xd : nullptr, a_s, a_t, a_ord);
             } else {
-                // steps that do not keep x2 (level-0 sites, the g term) write it to slot 0, which is
-                // free then: no level-0 site with a kept x2 is active during them
                 const XAcc<T> xd = c.slot(a_store ? a_dst : 0);
-                const T ssq = em_loop_fast<T, G, MODE>(P, dk, seed, lane, xs.base + xs.voff * VEC,
+                const T ssq = em_loop_fast<T, G, MODE, U>(P, dk, seed, lane, xs.base + xs.voff * VEC,
                                                        (uint32_t)xs.vstride * VEC, xd.base + xd.voff * VEC,
                                                        (uint32_t)xd.vstride * VEC, a_store, xs.unchecked != 0, a_s,
                                                        a_t, a_ord, nb, bad);
@@ -748,7 +743,7 @@ __device__ __forceinline__ void expand_item(Ctx<T, G>& c, const MlpParams<T>& P,
 }
 
 // one work item w = (unit, solve): evaluate and store the partial sum
-template <typename T, int G>
+template <typename T, int G, int U = 1>
 __device__ __forceinline__ void unit_item(Ctx<T, G>& c, const MlpParams<T>& P, u64 w)
 {
     const int solve = (int)(w % (u64)P.n_solves);
@@ -761,10 +756,10 @@ __device__ __forceinline__ void unit_item(Ctx<T, G>& c, const MlpParams<T>& P, u
     const XAcc<T> xp = c.point(solve, nd.point);
     T v;
     switch (c.fast) {
-    case EM_NOBC: v = run_unit_iter<T, G, EM_NOBC>(c, P, un, nd, xp, s); break;
-    case EM_SYM: v = run_unit_iter<T, G, EM_SYM>(c, P, un, nd, xp, s); break;
-    case EM_BOX: v = run_unit_iter<T, G, EM_BOX>(c, P, un, nd, xp, s); break;
-    default: v = run_unit_iter<T, G, 0>(c, P, un, nd, xp, s); break;
+    case EM_NOBC: v = run_unit_iter<T, G, EM_NOBC, U>(c, P, un, nd, xp, s); break;
+    case EM_SYM: v = run_unit_iter<T, G, EM_SYM, U>(c, P, un, nd, xp, s); break;
+    case EM_BOX: v = run_unit_iter<T, G, EM_BOX, U>(c, P, un, nd, xp, s); break;
+    default: v = run_unit_iter<T, G, 0, 1>(c, P, un, nd, xp, s); break;
     }
     const int nb = gsumi<G>(c.nb, c.gmask);
     if (c.lane == 0) {
@@ -896,8 +891,8 @@ __global__ void __launch_bounds__(128) mlp_expand_kernel(const __grid_constant__
 
 // the work units: dynamic fetch, one warp takes 32/G consecutive work items at a time
 // (lane groups of a warp then run equal-shaped units in lockstep)
-template <typename T, int G>
-__global__ void __launch_bounds__(128, Tune<G>::MB) mlp_units_kernel(const __grid_constant__ MlpParams<T> P)
+template <typename T, int G, int U>
+__global__ void __launch_bounds__(128, Tune<U>::MB) mlp_units_kernel(const __grid_constant__ MlpParams<T> P)
 {
     constexpr int GPW = 32 / G;
     if constexpr (sizeof(T) == 8) tables_init();
@@ -914,7 +909,7 @@ __global__ void __launch_bounds__(128, Tune<G>::MB) mlp_units_kernel(const __gri
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n_local) break;
         const u64 wl = base + (u64)sub;
-        if (wl < n_local) unit_item<T, G>(c, P, wl * (u64)P.nranks + (u64)P.rank);
+        if (wl < n_local) unit_item<T, G, U>(c, P, wl * (u64)P.nranks + (u64)P.rank);
     }
     if (c.bad) atomicExch(&P.flags[0], 1);
 }

@@ -29,19 +29,23 @@ template <typename T> MlpLaunchers<T> launchers_for(int G);
 template <> MlpLaunchers<double> launchers_for<double>(int G)
 {
     switch (G) { HDP_FOR_ALL_G(HDP_CASE, double, f64) }
-    return MlpLaunchers<double>{nullptr, nullptr, nullptr};
+    return MlpLaunchers<double>{};
 }
 template <> MlpLaunchers<float> launchers_for<float>(int G)
 {
     switch (G) { HDP_FOR_ALL_G(HDP_CASE, float, f32) }
-    return MlpLaunchers<float>{nullptr, nullptr, nullptr};
+    return MlpLaunchers<float>{};
 }
 
-// Lane-group width.  Throughput regime (plenty of work): the narrowest group with at most 16
-// vec-groups per lane — fewest idle lanes, fewest shuffles.  Latency regime (a single small
-// solve cannot fill the GPU with narrow groups): widen the group so that one path-step is
-// spread over more lanes.
-int pick_group(int nvec, double est_units, double resident_lanes)
+// Lane-group width (measured on B200, profiles/r1k_group_sweep.txt).
+// Throughput regime (a batch with plenty of work): the narrowest group with at most 64 vec-groups
+// per lane (d=100 → 1 lane, d=1000 → 8 lanes; C2 8.2 → 7.2 ms going from 4 lanes to 1, C5
+// 9.9 → 8.9 ms from 32 to 8): fewest idle lanes in the last pass, fewest shuffles, and the per-step
+// bookkeeping is spread over more coordinate work.
+// Latency regime: a narrow group makes every work unit take longer, so when there are few
+// path-steps per resident lane group (or only a handful of solves, whose trees cut into coarse
+// units) the group is widened until each resident group has about a dozen path-steps to do.
+int pick_group(int nvec, double path_steps_total, int n_solves, double sms)
 {
     const char* env = getenv("HDP_MLP_GROUP");
     if (env) {
@@ -49,8 +53,14 @@ int pick_group(int nvec, double est_units, double resident_lanes)
         if (g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32) return g;
     }
     int G = 1;
-    while (G < 32 && (nvec + G - 1) / G > 16) G *= 2;
-    while (G < 32 && G < nvec && est_units * G * 2 <= 0.5 * resident_lanes) G *= 2;
+    while (G < 32 && (nvec + G - 1) / G > (n_solves < 8 ? 16 : 64)) G *= 2;
+    auto resident_groups = [&](int g) {
+        const int npl = (nvec + g - 1) / g;
+        return sms * (npl >= 12 ? 4 : 6) * 128.0 / g; // blocks per SM of the two kernel variants
+    };
+    // (a batch never widens to the point where lanes of a group idle: 2 G <= nvec)
+    const int gmax = n_solves < 8 ? nvec : nvec / 2;
+    while (G < 32 && G < gmax && path_steps_total < 12.0 * resident_groups(G)) G *= 2;
     return G;
 }
 
@@ -175,22 +185,23 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
     const int d = prob->d;
     const int nvec = (d + VEC - 1) / VEC;
     const double min_unit = 8.0; // smallest work unit (path-steps + half the sampler calls)
-    const int G = pick_group(nvec, tab.W[L] * (double)n_solves / min_unit,
-                             (double)h->prop.multiProcessorCount * 768.0);
+    const int G = pick_group(nvec, tab.W[L] * (double)n_solves, n_solves, (double)h->prop.multiProcessorCount);
     const MlpLaunchers<T> LN = launchers_for<T>(G);
-    if (!LN.units) return set_err(h, HDP_ERR_UNSUPPORTED, "no kernel for group size %d", G);
+    if (!LN.units[0]) return set_err(h, HDP_ERR_UNSUPPORTED, "no kernel for group size %d", G);
     UserModule* um = nullptr;
     if (uses_user && (rc = get_user_module(h, prob, cfg->user, sizeof(T) == 4, G, &um)) != HDP_OK) return rc;
     const int block = 128;
     // dynamic shared memory of the units kernel: one Frame<T> per lane group (k_mlp.cuh, run_unit_iter)
     const size_t dyn_smem = (size_t)(block / G) * sizeof(Frame<T>);
+    // long rows: three vec-groups per pass (Tune<U>, k_mlp.cuh)
+    const int long_rows = (nvec + G - 1) / G >= 12 ? 1 : 0;
     int bps = 0;
     if (um) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, (const void*)um->units, block, dyn_smem) != cudaSuccess) {
             (void)cudaGetLastError();
             bps = 0;
         }
-    } else bps = LN.max_blocks_per_sm(block, dyn_smem);
+    } else bps = LN.max_blocks_per_sm[long_rows](block, dyn_smem);
     if (bps < 1) return set_err(h, HDP_ERR_CUDA, "occupancy query failed for the MLP kernel");
     const int sms = h->prop.multiProcessorCount;
     const int nranks = h->nccl_comm ? h->nccl_nranks : 1;
@@ -318,7 +329,7 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
         if (um) {
             void* args[1] = {(void*)&P};
             HDP_CUDA(h, cudaLaunchKernel((const void*)um->units, dim3(grid), dim3(block), args, dyn_smem, h->stream));
-        } else HDP_CUDA(h, LN.units(P, grid, block, dyn_smem, h->stream));
+        } else HDP_CUDA(h, LN.units[long_rows](P, grid, block, dyn_smem, h->stream));
         h->launches++;
     }
     HDP_CUDA(h, cudaEventRecord(h->evp[1], h->stream));

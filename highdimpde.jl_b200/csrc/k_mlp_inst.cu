@@ -12,18 +12,19 @@ namespace {
 typedef HDP_INST_T T_;
 constexpr int G_ = HDP_INST_G;
 
-static int inst_max_blocks(int block, size_t dyn_smem)
+template <int U> static int inst_max_blocks(int block, size_t dyn_smem)
 {
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mlp_units_kernel<T_, G_>, block, dyn_smem) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mlp_units_kernel<T_, G_, U>, block, dyn_smem) != cudaSuccess) {
         (void)cudaGetLastError();
         return 0;
     }
     return nb;
 }
+template <int U>
 static cudaError_t inst_units(const MlpParams<T_>& P, int grid, int block, size_t dyn_smem, cudaStream_t st)
 {
-    mlp_units_kernel<T_, G_><<<grid, block, dyn_smem, st>>>(P);
+    mlp_units_kernel<T_, G_, U><<<grid, block, dyn_smem, st>>>(P);
     return cudaGetLastError();
 }
 static cudaError_t inst_expand(const MlpParams<T_>& P, int off, int count, int grid, int block, cudaStream_t st)
@@ -36,8 +37,10 @@ static cudaError_t inst_expand(const MlpParams<T_>& P, int off, int count, int g
 MlpLaunchers<HDP_INST_T> HDP_INST_NAME()
 {
     MlpLaunchers<HDP_INST_T> l;
-    l.max_blocks_per_sm = inst_max_blocks;
-    l.units = inst_units;
+    l.max_blocks_per_sm[0] = inst_max_blocks<1>;
+    l.max_blocks_per_sm[1] = inst_max_blocks<3>;
+    l.units[0] = inst_units<1>;
+    l.units[1] = inst_units<3>;
     l.expand = inst_expand;
     return l;
 }

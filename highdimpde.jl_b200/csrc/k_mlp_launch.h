@@ -7,8 +7,9 @@
 namespace hdp {
 
 template <typename T> struct MlpLaunchers {
-    int (*max_blocks_per_sm)(int block, size_t dyn_smem);
-    cudaError_t (*units)(const MlpParams<T>& P, int grid, int block, size_t dyn_smem, cudaStream_t st);
+    // [0]: one vec-group per pass (short rows), [1]: three per pass (long rows)
+    int (*max_blocks_per_sm[2])(int block, size_t dyn_smem);
+    cudaError_t (*units[2])(const MlpParams<T>& P, int grid, int block, size_t dyn_smem, cudaStream_t st);
     cudaError_t (*expand)(const MlpParams<T>& P, int off, int count, int grid, int block, cudaStream_t st);
 };
 

@@ -117,7 +117,7 @@ int user_compile(const hdp_problem* p, const hdp_user_exprs* u, bool f32, int G,
     for (int i = 0; i < 4; ++i)
         if (needs[i].on) src += std::string("#define ") + macro[i] + " (" + needs[i].e + ")\n";
     src += "#include \"k_mlp.cuh\"\n";
-    const std::string n_units = "hdp::mlp_units_kernel<" + T + ", " + std::to_string(G) + ">";
+    const std::string n_units = "hdp::mlp_units_kernel<" + T + ", " + std::to_string(G) + ", 1>";
     const std::string n_expand = "hdp::mlp_expand_kernel<" + T + ", " + std::to_string(G) + ">";
     const std::string n_combine = "hdp::mlp_combine_kernel<" + T + ">";
     nvrtcProgram prog = nullptr;
