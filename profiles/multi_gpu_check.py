@@ -72,9 +72,12 @@ n_total = 1024 * world
 lo, hi = HD.shard_range(n_total, rank, world)
 u, st = H._ml_picard_batch(prob2, H.MLP(), n_solves=hi - lo, seed=HD.local_seed(50, rank, world, n_total), handle=h_solo)
 full = HD.gather_solves(u, n_total)
-# solve i must not depend on the rank count: compare the first solves with a local recomputation
+# solve i must not depend on the rank count: compare the first solves with a local recomputation.
+# The draws are identical (addressed by seed + solve index and consumption ordinal); a batch of 4 is
+# run with wider lane groups and another tree cut than a shard of 1024, so sums are associated
+# differently: equal to a few ulp, not bit for bit.
 chk, _ = H._ml_picard_batch(prob2, H.MLP(), n_solves=4, seed=50, handle=h_solo)
-assert np.array_equal(full[:4], chk)
+assert np.allclose(full[:4], chk, rtol=1e-13, atol=0.0), (full[:4], chk)
 if rank == 0:
     print(f"[multi] weak: {n_total} C2 solves over {world} ranks, mean u = {full.mean():.6f}, per-rank device_ms {st['device_ms']:.2f}")
 h.close()
