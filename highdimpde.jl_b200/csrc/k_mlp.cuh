@@ -30,6 +30,9 @@ template <int U> struct Tune {
     static constexpr int MB = U >= 2 ? 4 : 6;
 #endif
 };
+#ifndef HDP_EM_PRELOAD
+#define HDP_EM_PRELOAD 1
+#endif
 template <int N> struct IntTag { static constexpr int value = N; };
 struct FullTag { static constexpr bool value = true; };
 struct PartTag { static constexpr bool value = false; };
@@ -128,10 +131,14 @@ template <int G> __device__ __forceinline__ int gsumi(int v, unsigned mask)
     return v;
 }
 
-__device__ __forceinline__ void group_sync(unsigned mask)
+// the lanes of a group update their shared frame in lockstep.  A single-lane group needs no
+// synchronisation (and a per-lane mask would cost a MATCH.ANY per pass); a whole warp uses the
+// constant mask.
+template <int G> __device__ __forceinline__ void group_sync(unsigned mask)
 {
 #ifndef HDP_HOST_EMU
-    __syncwarp(mask);
+    if (G == 32) __syncwarp();
+    else if (G > 1) __syncwarp(mask);
 #else
     (void)mask;
 #endif
@@ -139,11 +146,10 @@ __device__ __forceinline__ void group_sync(unsigned mask)
 template <typename T> __device__ __forceinline__ T big() { return (T)3.0e38; }
 
 // rand(tType)  (src/MLP.jl:132)
-template <typename T, int G> __device__ __forceinline__ T time_uniform(const Ctx<T, G>& c, u64 ro)
+template <typename T> __device__ __forceinline__ T time_uniform(const MlpParams<T>& P, u64 seed, u64 ro)
 {
-    const MlpParams<T>& P = *c.P;
     if (P.r_tape) return P.r_tape[ro];
-    return draw_vec<T>(c.seed, HDP_STREAM_TIME, ro, 0, false).v[0];
+    return draw_vec<T>(seed, HDP_STREAM_TIME, ro, 0, false).v[0];
 }
 
 // `_mlt_sde_loop!(x2, x, s, t, prob, neumann_bc)`  (src/MLP.jl:406-421):
@@ -191,6 +197,13 @@ __device__ __forceinline__ T em_loop_fast(const MlpParams<T>& P, const DrawK<T>&
     Vec<T> stash[32]; // … and waits here
     int it = 0, p0 = lane;
     T* dp0 = dp;
+    Vec<T> xnext;
+    if (U == 1 && HDP_EM_PRELOAD) {
+        if (lane < nvec) xnext = ldv<T>(sp);
+        else
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) xnext.v[e] = (T)0;
+    }
     // U vec-groups of this lane (p, p+G, …) per pass
     auto body = [&](int p, auto full_tag, auto u_tag) {
         constexpr bool FULL = decltype(full_tag)::value;
@@ -198,10 +211,18 @@ __device__ __forceinline__ T em_loop_fast(const MlpParams<T>& P, const DrawK<T>&
         Vec<T> xi[UU], o[UU];
 #pragma unroll
         for (int u = 0; u < UU; ++u) xi[u] = draw_vec<T>(seed, HDP_STREAM_STEP, ord, (u64)(p + u * G), true, dk); // :416 randn!(x2)
-#pragma unroll
-        for (int u = 0; u < UU; ++u) {
-            o[u] = ldv<T>(sp);
+        if (U == 1 && HDP_EM_PRELOAD) {
+            // short rows, one vec-group per pass: the start point of the next pass is requested now,
+            // a whole pass before it is used (its address does not depend on the draws)
+            o[0] = xnext;
             sp += sstride;
+            if (p + G < nvec) xnext = ldv<T>(sp);
+        } else {
+#pragma unroll
+            for (int u = 0; u < UU; ++u) {
+                o[u] = ldv<T>(sp);
+                sp += sstride;
+            }
         }
 #pragma unroll
         for (int u = 0; u < UU; ++u) {
@@ -479,6 +500,7 @@ __device__ __forceinline__ T run_unit_iter(Ctx<T, G>& c, const MlpParams<T>& P, 
     const u64 seed = c.seed;
     const int lane = c.lane;
     const unsigned gmask = c.gmask;
+    const bool f_uses_z = pb.f_kind == HDP_F_NL_REPLICATOR || pb.f_kind == HDP_F_NL_USER;
     const DrawK<T> dk = draw_k_init<T>(P.zero & (lane + 1)); // 0, but neither constant nor uniform to the compiler
     // The frame of the innermost active call lives in shared memory (one per lane group: its
     // lanes read and write the same cells with the same values); the frames of its callers are
@@ -515,7 +537,7 @@ __device__ __forceinline__ T run_unit_iter(Ctx<T, G>& c, const MlpParams<T>& P, 
         // One pass runs the bookkeeping from the result of the last action to the next one.  The
         // handlers are ordered so that every transition except "return to the parent" lands on a
         // handler further down the same pass.
-        group_sync(gmask); // the lanes of a group update their shared frame in lockstep
+        group_sync<G>(gmask);
         int l = F->l;
         int act = ACT_NONE;
         // action parameters
@@ -587,7 +609,7 @@ __device__ __forceinline__ T run_unit_iter(Ctx<T, G>& c, const MlpParams<T>& P, 
             st = ST_G;
         }
         if (st == ST_SAMPLES) {
-            const bool dead_samples = (l == 0) && !c.f_uses_z;
+            const bool dead_samples = (l == 0) && !f_uses_z;
             if (has_samples && !dead_samples) {
                 if (F->h < K) { // :137, :176
                     act = ACT_SAMPLE; a_dst = 2 * l + 1; a_store = l >= 1; a_src = 2 * l; a_ord = F->qq; // :139, :177
@@ -622,7 +644,7 @@ __device__ __forceinline__ T run_unit_iter(Ctx<T, G>& c, const MlpParams<T>& P, 
             if (st == ST_LEVEL) { result = F->b; break; }
         }
         if (st == ST_SITE) {
-            const T uu = time_uniform<T, G>(c, F->ro);
+            const T uu = time_uniform<T>(P, seed, F->ro);
             const T r = add_rn(F->s, mul_rn(sub_rn(t1, F->s), uu)); // :132
             F->r = r;
             act = ACT_EM; a_src = F->xslot; a_dst = 2 * l; a_store = (l >= 1) || shifted; a_s = F->s; a_t = r; a_ord = F->co; // :133
@@ -714,7 +736,7 @@ __device__ __forceinline__ void expand_item(Ctx<T, G>& c, const MlpParams<T>& P,
     c.seed = P.seed0 + (u64)solve;
     const T s = nd.time_site < 0 ? P.pb.t0 : P.site_r[(u64)solve * P.n_sites + nd.time_site];
     const XAcc<T> xp = c.point(solve, nd.point);
-    const T u = time_uniform<T, G>(c, st.r);
+    const T u = time_uniform<T>(P, c.seed, st.r);
     const T r = add_rn(s, mul_rn(sub_rn(P.pb.t1, s), u));
     const XAcc<T> x2 = c.point(solve, st.x2_point);
     const Feat<T> f2 = em_step<T, G>(c, xp, x2, s, r, st.c);
