@@ -223,11 +223,20 @@ def run_ours(args, rank, world, local_rank):
             extra = bench_sde_loop(torch, H, h, local_rank)       # configs[2] (C3)
             extra.update(bench_other_configs(H, h))                # configs[0], [3], [4]
             p32 = h.measure_pipe_peak(32)
+            p64 = h.measure_pipe_peak(64)
             for k, v in extra.items():
                 if k.startswith("sde_loop_f32"):
-                    v["roofline"] = {"bound": "fp32", "achieved": v["fp32_pipe_lane_instr_per_s_at_I32_11"] / 1e12,
-                                     "peak": p32 / 1e12, "unit": "Tlane-instr/s",
-                                     "frac": v["fp32_pipe_lane_instr_per_s_at_I32_11"] / p32,
+                    cs = v["coord_steps_per_sec"]
+                    # 11 fp32 pipe-instructions per reflected coordinate-step, plus 20 INT32 ones for
+                    # Philox that share the issue port with them (the co-limiter the survey names)
+                    v["roofline"] = {"bound": "fp32", "achieved": cs * 11 / 1e12, "peak": p32 / 1e12,
+                                     "unit": "Tlane-instr/s", "frac": cs * 11 / p32,
+                                     "frac_with_philox_int32": cs * 31 / p32,
+                                     "hbm_frac_of_6542GBs": v["hbm_gbs"] / 6542.1}
+                if k.startswith("sde_loop_f64"):
+                    cs = v["coord_steps_per_sec"]
+                    v["roofline"] = {"bound": "fp64", "achieved": cs * I64_PER_COORD_STEP / 1e12, "peak": p64 / 1e12,
+                                     "unit": "Tlane-instr/s", "frac": cs * I64_PER_COORD_STEP / p64,
                                      "hbm_frac_of_6542GBs": v["hbm_gbs"] / 6542.1}
         except Exception as e:  # pragma: no cover
             extra["extra_error"] = repr(e)
@@ -289,36 +298,41 @@ def run_ours(args, rank, world, local_rank):
 
 
 def bench_sde_loop(torch, H, h, local_rank):
-    """C3: `sde_loop!` with reflection, fp32, B=8192 (the config) and B=1,048,576 (saturating)."""
+    """C3: `sde_loop!` with reflection, d=100, N=10: fp32 at B=8192 (the config) and B=1,048,576 (saturating),
+    and the fp64 instance of the same kernel at B=1,048,576."""
     import ctypes as C
     out = {}
     d, N = 100, 10
-    prob = H.ParabolicPDEProblem(0.0, 1.0, np.zeros(d, dtype=np.float32), (0.0, 1.0), g=H.SumSq(), f=H.FZero(),
-                                 neumann_bc=(-1.0, 1.0))
-    pb, _k = prob.to_c()
-    none, _k2 = H.NoSampling()._descriptor(d)
-    for B in (8192, 1 << 20):
-        y1 = torch.zeros(d * B, dtype=torch.float32, device="cuda")
-        y0 = torch.empty_like(y1)
-        torch.cuda.synchronize()
-        flags = H.capi.HDP_MEM_DEVICE | H.capi.HDP_ASYNC
-        reps = 20
-        best = None
-        for r in range(reps + 3):
-            y1.zero_()
+    for dtype, tdt, fn, tag, sizes in ((np.float32, torch.float32, "hdp_sde_loop_f32", "f32", (8192, 1 << 20)),
+                                       (np.float64, torch.float64, "hdp_sde_loop_f64", "f64", (1 << 20,))):
+        prob = H.ParabolicPDEProblem(0.0, 1.0, np.zeros(d, dtype=dtype), (0.0, 1.0), g=H.SumSq(), f=H.FZero(),
+                                     neumann_bc=(-1.0, 1.0))
+        pb, _k = prob.to_c()
+        none, _k2 = H.NoSampling()._descriptor(d)
+        esz = np.dtype(dtype).itemsize
+        for B in sizes:
+            y1 = torch.zeros(d * B, dtype=tdt, device="cuda")
+            y0 = torch.empty_like(y1)
             torch.cuda.synchronize()
-            rc = h.lib.hdp_sde_loop_f32(h.h, C.byref(pb), C.c_void_p(y0.data_ptr()), C.c_void_p(y1.data_ptr()), B, N,
-                                        C.c_float(0.1), None, C.byref(none), 7 + r, None, C.byref(none), None, 0,
+            flags = H.capi.HDP_MEM_DEVICE | H.capi.HDP_ASYNC
+            reps = 20
+            best = None
+            for r in range(reps + 3):
+                y1.zero_()
+                torch.cuda.synchronize()
+                dt = C.c_float(0.1) if tag == "f32" else C.c_double(0.1)
+                rc = getattr(h.lib, fn)(h.h, C.byref(pb), C.c_void_p(y0.data_ptr()), C.c_void_p(y1.data_ptr()), B, N,
+                                        dt, None, C.byref(none), 7 + r, None, C.byref(none), None, 0,
                                         H.capi.HDP_NORMAL_DEFAULT, flags)
-            H.capi.check(h.h, rc)
-            ms = h.last_device_ms()
-            if r >= 3:
-                best = ms if best is None else min(best, ms)
-        h.sync()
-        ps = B * N / (best * 1e-3)
-        out[f"sde_loop_f32_B{B}"] = {"path_steps_per_sec": ps, "coord_steps_per_sec": ps * d, "kernel_ms": best,
-                                     "hbm_bytes": 3 * d * B * 4, "hbm_gbs": 3 * d * B * 4 / (best * 1e-3) / 1e9,
-                                     "fp32_pipe_lane_instr_per_s_at_I32_11": ps * d * 11}
+                H.capi.check(h.h, rc)
+                ms = h.last_device_ms()
+                if r >= 3:
+                    best = ms if best is None else min(best, ms)
+            h.sync()
+            ps = B * N / (best * 1e-3)
+            out[f"sde_loop_{tag}_B{B}"] = {"path_steps_per_sec": ps, "coord_steps_per_sec": ps * d, "kernel_ms": best,
+                                           "hbm_bytes": 3 * d * B * esz, "hbm_gbs": 3 * d * B * esz / (best * 1e-3) / 1e9}
+            del y0, y1
     return out
 
 

@@ -126,6 +126,9 @@ mc_sample_kernel(T* __restrict__ z, const T* __restrict__ y1, const T* __restric
 //     K1_NOBC / K1_SYM — constant coefficients, DeepSplitting association, no boundary /
 //     symmetric scalar box (the BASELINE shape): nothing but the arithmetic is left in the loop.
 enum { K1_GENERIC = 0, K1_NOBC = 1, K1_SYM = 2 };
+#ifndef K1_STEP_UNROLL
+#define K1_STEP_UNROLL 2
+#endif
 
 template <typename T, bool ALIGNED, bool INJECT, int BC>
 __global__ void __launch_bounds__(128)
@@ -174,7 +177,22 @@ sde_loop_kernel(DevProblem<T> pb, T* __restrict__ y0, T* __restrict__ y1, size_t
             }
         }
         Vec<T> prev = cur;
-        for (int st = 0; st < nsteps; ++st) {
+        int st = 0;
+        if constexpr (BC != K1_GENERIC && !INJECT && K1_STEP_UNROLL == 2) {
+            // the normals of two steps are independent of the state: two Philox / Box–Muller chains in flight
+            for (; st + 1 < nsteps; st += 2) {
+                const Vec<T> xa = draw_vec<T>(seed, HDP_STREAM_SDE, (u64)st, (u64)v, true, dk);
+                const Vec<T> xb = draw_vec<T>(seed, HDP_STREAM_SDE, (u64)(st + 1), (u64)v, true, dk);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) cur.v[e] = add_rn(add_rn(cur.v[e], mudt_c), mul_rn(sgsq_c, xa.v[e])); // :160
+                if constexpr (BC == K1_SYM) reflect_vec_sym<T, false>(cur, pb.hi_s, nb_total); // :161-163
+                prev = cur; // y0 .= y1 (:159)
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) cur.v[e] = add_rn(add_rn(prev.v[e], mudt_c), mul_rn(sgsq_c, xb.v[e]));
+                if constexpr (BC == K1_SYM) reflect_vec_sym<T, false>(cur, pb.hi_s, nb_total);
+            }
+        }
+        for (; st < nsteps; ++st) {
             Vec<T> xi;
             if constexpr (INJECT) xi = load_el<T, ALIGNED>(dW + (size_t)st * n_el, q0, n_el);
             else xi = draw_vec<T>(seed, HDP_STREAM_SDE, (u64)st, (u64)v, true, dk);
