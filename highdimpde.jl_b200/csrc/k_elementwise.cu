@@ -178,18 +178,21 @@ sde_loop_kernel(DevProblem<T> pb, T* __restrict__ y0, T* __restrict__ y1, size_t
         }
         Vec<T> prev = cur;
         int st = 0;
-        if constexpr (BC != K1_GENERIC && !INJECT && K1_STEP_UNROLL == 2) {
-            // the normals of two steps are independent of the state: two Philox / Box–Muller chains in flight
-            for (; st + 1 < nsteps; st += 2) {
-                const Vec<T> xa = draw_vec<T>(seed, HDP_STREAM_SDE, (u64)st, (u64)v, true, dk);
-                const Vec<T> xb = draw_vec<T>(seed, HDP_STREAM_SDE, (u64)(st + 1), (u64)v, true, dk);
+        if constexpr (BC != K1_GENERIC && !INJECT && K1_STEP_UNROLL > 1) {
+            // the normals of consecutive steps do not depend on the state: several Philox / Box–Muller chains in flight
+            constexpr int SU = K1_STEP_UNROLL;
+            for (; st + SU - 1 < nsteps; st += SU) {
+                Vec<T> xs[SU];
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) cur.v[e] = add_rn(add_rn(cur.v[e], mudt_c), mul_rn(sgsq_c, xa.v[e])); // :160
-                if constexpr (BC == K1_SYM) reflect_vec_sym<T, false>(cur, pb.hi_s, nb_total); // :161-163
-                prev = cur; // y0 .= y1 (:159)
+                for (int u = 0; u < SU; ++u) xs[u] = draw_vec<T>(seed, HDP_STREAM_SDE, (u64)(st + u), (u64)v, true, dk);
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) cur.v[e] = add_rn(add_rn(prev.v[e], mudt_c), mul_rn(sgsq_c, xb.v[e]));
-                if constexpr (BC == K1_SYM) reflect_vec_sym<T, false>(cur, pb.hi_s, nb_total);
+                for (int u = 0; u < SU; ++u) {
+                    prev = cur; // y0 .= y1 (:159)
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e)
+                        cur.v[e] = add_rn(add_rn(prev.v[e], mudt_c), mul_rn(sgsq_c, xs[u].v[e])); // :160
+                    if constexpr (BC == K1_SYM) reflect_vec_sym<T, false>(cur, pb.hi_s, nb_total); // :161-163
+                }
             }
         }
         for (; st < nsteps; ++st) {
