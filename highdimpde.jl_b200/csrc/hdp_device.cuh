@@ -159,7 +159,6 @@ __device__ __forceinline__ double rsqrt_approx(double x)
 }
 __device__ __forceinline__ double xfma(double a, double b, double c) { return fma(a, b, c); }
 __device__ __forceinline__ float xfma(float a, float b, float c) { return fmaf(a, b, c); }
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.L1 [%0];" ::"l"(p)); }
 // MUFU approximations with flush-to-zero: the arguments are never denormal here, and the
 // non-ftz forms carry denormal fix-up code (extra FSETP/FMUL per call)
 __device__ __forceinline__ float rsq_approx(float x)

@@ -46,13 +46,11 @@ static inline uint32_t d2hi(double x) { uint64_t b; memcpy(&b, &x, 8); return (u
 static inline uint32_t d2lo(double x) { uint64_t b; memcpy(&b, &x, 8); return (uint32_t)b; }
 static inline float u2f(uint32_t b) { float f; memcpy(&f, &b, 4); return f; }
 static inline uint32_t f2u(float x) { uint32_t b; memcpy(&b, &x, 4); return b; }
-static inline double rcp_approx(double x) { return (double)(float)(1.0 / x); }     // ~24-bit seed, like MUFU.RCP64H
 static inline double rsqrt_approx(double x) { return (double)(float)(1.0 / sqrt(x)); }
 static inline float rsq_approx(float x) { return 1.0f / sqrtf(x); }
 static inline float lg2_approx(float x) { return log2f(x); }
 static inline float sin_approx(float x) { return sinf(x); }
 static inline float cos_approx(float x) { return cosf(x); }
-static inline void prefetch_l1(const void*) {}
 static inline double xfma(double a, double b, double c) { return fma(a, b, c); }
 static inline float xfma(float a, float b, float c) { return fmaf(a, b, c); }
 template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int) { return v; }
