@@ -263,13 +263,17 @@ def _fast_loop_cases(H):
     c["nonlocal_sym_d5"] = (H.PIDEProblem(0.0, 0.6, np.zeros(5), (0.0, 0.5), H.ExpSumSq(0.25), H.FNLAllenCahnDiff(),
                                           neumann_bc=(-0.5, 0.5)),
                             H.MLP(M=3, L=3, K=3, mc_sample=H.UniformSampling(-0.5, 0.5)), np.float64)
+    c["sym_d1"] = (H.ParabolicPDEProblem(0.0, 1.0, np.zeros(1), (0.0, 0.5), g=H.ExpSumSq(0.25), f=H.FAllenCahn(1.0),
+                                         neumann_bc=(-0.5, 0.5)), H.MLP(M=3, L=3, K=2), np.float64)
+    c["box_d1_f32"] = (H.ParabolicPDEProblem(0.0, 1.0, np.full(1, 0.2, dtype=np.float32), (0.0, 0.5), g=H.ExpSumSq(0.25),
+                                             f=H.FAllenCahn(1.0), neumann_bc=(-0.3, 0.7)), H.MLP(M=3, L=3, K=2), np.float32)
     c["long_d2101"] = (H.ParabolicPDEProblem(0.0, 1.0, np.zeros(2101), (0.0, 0.5), g=H.ExpSumSq(1e-3), f=H.FAllenCahn(1.0),
                                              neumann_bc=(-0.5, 0.5)), H.MLP(M=2, L=2, K=2), np.float64)
     return c
 
 
 @pytest.mark.parametrize("name", ["sym_d5", "box_d6", "box_d7_f32", "nobc_d9", "wild_sym_d4", "wild_far_d4",
-                                  "nonlocal_sym_d5", "long_d2101"])
+                                  "nonlocal_sym_d5", "sym_d1", "box_d1_f32", "long_d2101"])
 def test_mlp_fast_loops_match_oracle_on_their_own_draws(H, O, handle, name, monkeypatch):
     """RNG mode runs the specialised loops; the oracle is fed the very draws (hdp_tape_fill): values to tolerance,
     wall-hit counts exact, whatever the lane-group width and the tree cut."""

@@ -102,3 +102,24 @@ def test_start_outside_domain_is_reported(H, O, emu):
     assert info["rc"] == H.capi.HDP_ERR_START_OUTSIDE_DOMAIN
     u, rc, st = emu_solve(H, emu, prob, alg, np.float64, tapes=tapes)
     assert rc == H.capi.HDP_ERR_START_OUTSIDE_DOMAIN
+
+
+def test_product_generator_matches_its_definition(O, emu):
+    """The product's table-driven fp64 Box–Muller (hdp_device.cuh, compiled for the host) against the libm
+    evaluation of the same definition in the oracle: uniforms bit-equal, normals to a few ulp, over every
+    stream and over the whole range of the radius (including the entries of the log table next to u1 = 1)."""
+    import ctypes as C
+    emu.hdp_emu_draw_f64.argtypes = [C.c_uint64, C.c_int, C.c_uint64, C.c_uint32, C.c_int, C.POINTER(C.c_double)]
+    out = (C.c_double * 2)()
+    worst = 0.0
+    for stream in range(6):
+        for ord_ in range(0, 3000, 1 if stream == 1 else 37):
+            grp = (ord_ * 7) % 50
+            emu.hdp_emu_draw_f64(99, stream, ord_, grp, 0, out)
+            assert out[0] == O.draw(np.float64, 99, stream, ord_, 2 * grp, False)
+            assert out[1] == O.draw(np.float64, 99, stream, ord_, 2 * grp + 1, False)
+            emu.hdp_emu_draw_f64(99, stream, ord_, grp, 1, out)
+            a = O.draw(np.float64, 99, stream, ord_, 2 * grp, True)
+            b = O.draw(np.float64, 99, stream, ord_, 2 * grp + 1, True)
+            worst = max(worst, abs(out[0] - a) / max(1.0, abs(a)), abs(out[1] - b) / max(1.0, abs(b)))
+    assert worst <= 2e-15, worst

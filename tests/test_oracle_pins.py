@@ -33,6 +33,40 @@ def test_philox_known_answers(O):
         assert [int(v) for v in O.philox4x32_10(ctr, key)] == want
 
 
+def test_draw_addressing_layout(O):
+    """The library's draws: Philox4x32-10, fixed key, counter (w0, w1, seed_lo, seed_hi) with the documented
+    packing of (stream, ordinal, group) — include/hdpde.h, DESIGN.md section 3."""
+    key = [0xA4093822, 0x299F31D0]
+    seed = 0x0123456789ABCDEF
+
+    def words(stream, ord_, group):
+        if stream <= 2:  # TIME, STEP, SAMPLER: ordinal < 2^40, group < 2^21
+            w0 = ord_ & 0xFFFFFFFF
+            w1 = ((ord_ >> 32) | (group << 8) | (stream << 29)) & 0xFFFFFFFF
+        else:            # SDE, X0, MC: ordinal < 2^24, group < 2^37
+            w0 = group & 0xFFFFFFFF
+            w1 = ((group >> 32) | (ord_ << 5) | (stream << 29)) & 0xFFFFFFFF
+        return [int(v) for v in O.philox4x32_10([w0, w1, seed & 0xFFFFFFFF, seed >> 32], key)]
+
+    for stream, ord_, group in [(0, 5, 0), (1, (1 << 39) + 12345, (1 << 20) + 7), (2, 77, 3), (3, (1 << 23) + 9, (1 << 36) + 11),
+                                (4, 0, 123456789), (5, 31, 2)]:
+        w = words(stream, ord_, group)
+        # f64: two uniforms per call, u = ((w_hi >> 12) : w_lo) * 2^-52
+        u0 = O.draw(np.float64, seed, stream, ord_, 2 * group, False)
+        u1 = O.draw(np.float64, seed, stream, ord_, 2 * group + 1, False)
+        assert u0 == (((w[0] >> 12) << 32) | w[1]) * 2.0 ** -52 and u1 == (((w[2] >> 12) << 32) | w[3]) * 2.0 ** -52
+        # f32: four uniforms per call, u = (w >> 9) * 2^-23
+        for e in range(4):
+            assert O.draw(np.float32, seed, stream, ord_, 4 * group + e, False) == np.float32((w[e] >> 9) * 2.0 ** -23)
+        # f64 Box–Muller pair from the same words: u1 = (k1 | 1) 2^-52, angle 2 pi k2 / 2^52
+        k1 = (((w[0] >> 12) << 32) | w[1]) | 1
+        k2 = ((w[2] >> 12) << 32) | w[3]
+        r = math.sqrt(-2.0 * math.log(k1 * 2.0 ** -52))
+        th = 2.0 * math.pi * (k2 * 2.0 ** -52)
+        assert abs(O.draw(np.float64, seed, stream, ord_, 2 * group, True) - r * math.cos(th)) <= 1e-14
+        assert abs(O.draw(np.float64, seed, stream, ord_, 2 * group + 1, True) - r * math.sin(th)) <= 1e-14
+
+
 @pytest.mark.parametrize("kind", ["xoshiro", "philox"])
 def test_generators_are_standard(O, kind):
     rng = getattr(O.Rng, kind)(7)
