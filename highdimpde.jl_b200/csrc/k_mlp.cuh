@@ -30,6 +30,9 @@ template <int U> struct Tune {
     static constexpr int MB = U >= 2 ? 4 : 6;
 #endif
 };
+#ifndef HDP_MLP_BLOCK
+#define HDP_MLP_BLOCK 128 // threads per block of the expand and units kernels
+#endif
 #ifndef HDP_EM_PRELOAD
 #define HDP_EM_PRELOAD 1
 #endif
@@ -914,7 +917,7 @@ __global__ void __launch_bounds__(128) mlp_expand_kernel(const __grid_constant__
 // the work units: dynamic fetch, one warp takes 32/G consecutive work items at a time
 // (lane groups of a warp then run equal-shaped units in lockstep)
 template <typename T, int G, int U>
-__global__ void __launch_bounds__(128, Tune<U>::MB) mlp_units_kernel(const __grid_constant__ MlpParams<T> P)
+__global__ void __launch_bounds__(HDP_MLP_BLOCK, Tune<U>::MB) mlp_units_kernel(const __grid_constant__ MlpParams<T> P)
 {
     constexpr int GPW = 32 / G;
     if constexpr (sizeof(T) == 8) tables_init();

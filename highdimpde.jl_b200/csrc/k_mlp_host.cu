@@ -190,7 +190,7 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
     if (!LN.units[0]) return set_err(h, HDP_ERR_UNSUPPORTED, "no kernel for group size %d", G);
     UserModule* um = nullptr;
     if (uses_user && (rc = get_user_module(h, prob, cfg->user, sizeof(T) == 4, G, &um)) != HDP_OK) return rc;
-    const int block = 128;
+    const int block = HDP_MLP_BLOCK;
     // dynamic shared memory of the units kernel: one Frame<T> per lane group (k_mlp.cuh, run_unit_iter)
     const size_t dyn_smem = (size_t)(block / G) * sizeof(Frame<T>);
     // long rows: three vec-groups per pass (Tune<U>, k_mlp.cuh)
