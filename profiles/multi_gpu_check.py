@@ -1,6 +1,6 @@
 """Multi-GPU check (run under torchrun, one rank per GPU):
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
-      profiles/multi_gpu_check.py [L]
+      profiles/multi_gpu_check.py [L [M]]
 1. NCCL plumbing: hdp_nccl_unique_id -> broadcast -> hdp_comm_init_rank, allreduce self-test.
 2. Strong scaling of ONE solve (BASELINE C4 shape: non-local Fisher-KPP d=10, UniformSampling, M=4, K=10, level L):
    work units sharded over the ranks, one ncclAllReduce of the per-unit partial sums; the result must be
@@ -25,6 +25,7 @@ local = int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 Lv = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+Mv = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 
 h_solo = H.Handle(local)          # no communicator: the single-GPU reference
 h = H.Handle(local)
@@ -36,7 +37,7 @@ assert x[0] == world * (world + 1) / 2 and x[1] == world, x
 d = 10
 prob = H.PIDEProblem(0.0, 0.1, np.zeros(d), (0.0, 0.5), H.ExpSumSq(1.0), H.FNLFisher(),
                      neumann_bc=(np.full(d, -0.5), np.full(d, 0.5)))
-alg = H.MLP(M=4, L=Lv, K=10, mc_sample=H.UniformSampling(np.full(d, -0.5), np.full(d, 0.5)))
+alg = H.MLP(M=Mv, L=Lv, K=10, mc_sample=H.UniformSampling(np.full(d, -0.5), np.full(d, 0.5)))
 u1, s1 = H._ml_picard_batch(prob, alg, n_solves=1, seed=3, handle=h_solo)
 res = {}
 for it in range(3):
@@ -60,9 +61,9 @@ allu = HD.all_gather_object(float(uN[0]))
 assert all(v == allu[0] for v in allu), allu  # every rank holds the identical result
 dev = HD.max_over_ranks(min(v[1] for v in res.values()))
 if rank == 0:
-    print(f"[multi] world={world} C4-shape L={Lv}: u={uN[0]:.15g} rel_vs_1gpu={rel:.1e} bit_equal={same_bits} "
+    print(f"[multi] world={world} C4-shape M={Mv} L={Lv} ({sN['path_steps']} path-steps): u={uN[0]:.15g} rel_vs_1gpu={rel:.1e} bit_equal={same_bits} "
           f"units={sN['n_units']} (1 GPU: {s1['n_units']}) device_ms N-GPU={dev:.3f} 1-GPU={min(t_solo):.3f} "
-          f"speedup={min(t_solo) / dev:.2f}x bounces_rank0={sN['bounces']}")
+          f"speedup={min(t_solo) / dev:.2f}x bounces_rank0={sN['bounces']} phase_ms={ {k: round(v, 3) for k, v in sN['phase_ms'].items()} }")
 
 # weak scaling: independent C2 solves
 D = 100
