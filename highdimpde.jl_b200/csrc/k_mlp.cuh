@@ -798,7 +798,8 @@ __device__ __forceinline__ void unit_item(Ctx<T, G>& c, const MlpParams<T>& P, u
 // its units and over its explicit sites, then the per-level sums are butterfly-reduced — the
 // root of a deeply cut tree has thousands of children, one thread would walk them serially.
 template <typename T>
-__device__ __forceinline__ void combine_item(const MlpParams<T>& P, int off, u64 item, int lane, int nl)
+__device__ __forceinline__ void combine_item(const MlpParams<T>& P, int off, u64 item, int lane, int nl,
+                                             unsigned mask = 0xffffffffu)
 {
     const int solve = (int)(item % (u64)P.n_solves);
     const int nidx = P.nodes_by_depth[off + (int)(item / (u64)P.n_solves)];
@@ -860,10 +861,12 @@ __device__ __forceinline__ void combine_item(const MlpParams<T>& P, int off, u64
             for (int q = 0; q < kMaxL; ++q)
                 if (q == l) Bl[q] += add;
         }
-        if (nl > 1) {
+        if (nl > 1) { // butterfly over the nl lanes of this node (an aligned sub-warp group)
+            for (int o = nl >> 1; o > 0; o >>= 1) {
 #pragma unroll
-            for (int l = 0; l < kMaxL; ++l) Bl[l] = gsum<T, 32>(Bl[l], 0xffffffffu);
-            Gs = gsum<T, 32>(Gs, 0xffffffffu);
+                for (int l = 0; l < kMaxL; ++l) Bl[l] += __shfl_xor_sync(mask, Bl[l], o);
+                Gs += __shfl_xor_sync(mask, Gs, o);
+            }
         }
         T a = (T)0;
 #pragma unroll
@@ -939,12 +942,17 @@ __global__ void __launch_bounds__(HDP_MLP_BLOCK, Tune<U>::MB) mlp_units_kernel(c
     if (c.bad) atomicExch(&P.flags[0], 1);
 }
 
+// nl lanes (a power of two, 1..32) share one (node, solve): 32 where nodes have many children (the
+// root of a deeply cut tree has thousands), 4 where they have a handful
 template <typename T>
-__global__ void __launch_bounds__(128) mlp_combine_kernel(const __grid_constant__ MlpParams<T> P, int off, int count)
+__global__ void __launch_bounds__(128) mlp_combine_kernel(const __grid_constant__ MlpParams<T> P, int off, int count, int nl)
 {
-    const u64 gid = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; // one warp per (node, solve)
-    if (gid >= (u64)count * (u64)P.n_solves) return;
-    combine_item<T>(P, off, gid, threadIdx.x & 31, 32);
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 gid = t / (unsigned)nl;
+    const bool live = gid < (u64)count * (u64)P.n_solves;
+    const unsigned mask = __ballot_sync(0xffffffffu, live);
+    if (!live) return;
+    combine_item<T>(P, off, gid, (int)(t % (unsigned)nl), nl, mask);
 }
 #endif // HDP_HOST_EMU
 

@@ -343,13 +343,20 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
         const int off = plan->node_depth_off[dep];
         const int cnt = plan->node_depth_off[dep + 1] - off;
         if (cnt == 0) continue;
-        uint64_t tot = (uint64_t)cnt * n_solves * 32; // one warp per (node, solve)
+        // lanes per (node, solve): a warp where some node of this depth has many children, 4 lanes otherwise
+        int most = 0;
+        for (int q = off; q < off + cnt; ++q) {
+            const PlanNode& nd = plan->nodes[plan->nodes_by_depth[q]];
+            most = std::max(most, (nd.unit_end - nd.unit_begin) + (nd.site_end - nd.site_begin));
+        }
+        int nl = most > 16 ? 32 : 4;
+        uint64_t tot = (uint64_t)cnt * n_solves * nl;
         int gc = (int)((tot + 127) / 128);
         if (um) { // f is applied in the combine too: the user module's build of it
             int off_ = off, cnt_ = cnt;
-            void* args[3] = {(void*)&P, (void*)&off_, (void*)&cnt_};
+            void* args[4] = {(void*)&P, (void*)&off_, (void*)&cnt_, (void*)&nl};
             HDP_CUDA(h, cudaLaunchKernel((const void*)um->combine, dim3(gc), dim3(128), args, 0, h->stream));
-        } else mlp_combine_kernel<T><<<gc, 128, 0, h->stream>>>(P, off, cnt);
+        } else mlp_combine_kernel<T><<<gc, 128, 0, h->stream>>>(P, off, cnt, nl);
         h->launches++;
         HDP_CUDA(h, cudaGetLastError());
     }
