@@ -292,16 +292,22 @@ __device__ __forceinline__ T em_loop_fast(const MlpParams<T>& P, const DrawK<T>&
     return ssq;
 }
 
+// the stand-alone step of the expand pass (x2 is always kept); rows of >= 12 vec-groups per lane
+// take three per pass, like the units kernel
 template <typename T, int G, int MODE>
-__device__ HDP_NOINLINE Feat<T> em_step_fast(Ctx<T, G>& c, const XAcc<T>& src, const XAcc<T>& dst, T s, T tend, u64 ord)
+__device__ __forceinline__ Feat<T> em_step_fast(Ctx<T, G>& c, const MlpParams<T>& P, const XAcc<T>& src, const XAcc<T>& dst,
+                                                T s, T tend, u64 ord)
 {
     constexpr int VEC = Tr<T>::VEC;
-    const MlpParams<T>& P = *c.P;
     const DrawK<T> dk = draw_k_init<T>(P.zero & (c.lane + 1));
     int nb = 0, bad = 0;
-    const T ssq = em_loop_fast<T, G, MODE>(P, dk, c.seed, c.lane, src.base + src.voff * VEC, (uint32_t)src.vstride * VEC,
-                                           dst.base + dst.voff * VEC, (uint32_t)dst.vstride * VEC, true,
-                                           src.unchecked != 0, s, tend, ord, nb, bad);
+    const T* sp = src.base + src.voff * VEC;
+    T* dp = dst.base + dst.voff * VEC;
+    const uint32_t ss = (uint32_t)src.vstride * VEC, ds = (uint32_t)dst.vstride * VEC;
+    const T ssq = P.npl >= 12 ? em_loop_fast<T, G, MODE, 3>(P, dk, c.seed, c.lane, sp, ss, dp, ds, true, src.unchecked != 0,
+                                                           s, tend, ord, nb, bad)
+                              : em_loop_fast<T, G, MODE, 1>(P, dk, c.seed, c.lane, sp, ss, dp, ds, true, src.unchecked != 0,
+                                                           s, tend, ord, nb, bad);
     c.nb += nb;
     c.bad |= bad;
     Feat<T> f;
@@ -396,14 +402,15 @@ __device__ HDP_NOINLINE Feat<T> em_step_generic(Ctx<T, G>& c, const XAcc<T>& src
     return f;
 }
 
-// the stand-alone step (expand pass): dispatch on the mode of this launch; x2 is always kept
+// the stand-alone step (expand pass): dispatch on the mode of this launch
 template <typename T, int G>
-__device__ __forceinline__ Feat<T> em_step(Ctx<T, G>& c, const XAcc<T>& src, const XAcc<T>& dst, T s, T tend, u64 ord)
+__device__ __forceinline__ Feat<T> em_step(Ctx<T, G>& c, const MlpParams<T>& P, const XAcc<T>& src, const XAcc<T>& dst, T s,
+                                           T tend, u64 ord)
 {
     switch (c.fast) {
-    case EM_NOBC: return em_step_fast<T, G, EM_NOBC>(c, src, dst, s, tend, ord);
-    case EM_SYM: return em_step_fast<T, G, EM_SYM>(c, src, dst, s, tend, ord);
-    case EM_BOX: return em_step_fast<T, G, EM_BOX>(c, src, dst, s, tend, ord);
+    case EM_NOBC: return em_step_fast<T, G, EM_NOBC>(c, P, src, dst, s, tend, ord);
+    case EM_SYM: return em_step_fast<T, G, EM_SYM>(c, P, src, dst, s, tend, ord);
+    case EM_BOX: return em_step_fast<T, G, EM_BOX>(c, P, src, dst, s, tend, ord);
     }
     return em_step_generic<T, G>(c, src, &dst, s, tend, ord);
 }
@@ -742,7 +749,7 @@ __device__ __forceinline__ void expand_item(Ctx<T, G>& c, const MlpParams<T>& P,
     const T u = time_uniform<T>(P, c.seed, st.r);
     const T r = add_rn(s, mul_rn(sub_rn(P.pb.t1, s), u));
     const XAcc<T> x2 = c.point(solve, st.x2_point);
-    const Feat<T> f2 = em_step<T, G>(c, xp, x2, s, r, st.c);
+    const Feat<T> f2 = em_step<T, G>(c, P, xp, x2, s, r, st.c);
     if (c.lane == 0) {
         P.site_r[(u64)solve * P.n_sites + sidx] = r;
         P.feat[(u64)solve * P.n_points + st.x2_point] = f2.ssq;
