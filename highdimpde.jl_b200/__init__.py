@@ -10,12 +10,12 @@ calls raise.
 from . import _capi as capi
 from ._capi import Handle, HdpError, StartOutsideDomain, default_handle, load_library, set_default_handle
 from . import kinds
-from .kinds import (ConstCoef, LinearCoef, SumSq, InvSumSq, ExpSumSq, MinCoord, GaussDensity, FZero, FLinear,
+from .kinds import (ConstCoef, LinearCoef, QuadraticCoef, SumSq, InvSumSq, ExpSumSq, MinCoord, GaussDensity, FZero, FLinear,
                     FAllenCahn, FDefaultRisk, FFisherKPP, FNLAllenCahnDiff, FNLFisher, FNLReplicatorMutator,
                     UserCoef, UserG, UserF, UserFNL)
 from .sampling import UniformSampling, NormalSampling, NoSampling, _integrate
 from .problems import PIDEProblem, ParabolicPDEProblem, PIDESolution
 from .mlp import MLP, solve, mlp_counts, _ml_picard_batch
-from .sde import _reflect, sde_loop, _mlt_sde_loop
+from .sde import _reflect, sde_loop, _mlt_sde_loop, em_ensemble
 
 __all__ = [n for n in dir() if not n.startswith("__")]

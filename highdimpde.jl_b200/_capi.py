@@ -32,7 +32,7 @@ HDP_MEM_HOST = 0
 HDP_MEM_DEVICE = 1
 HDP_ASYNC = 2
 
-HDP_COEF_CONST, HDP_COEF_LINEAR, HDP_COEF_USER = 0, 1, 2
+HDP_COEF_CONST, HDP_COEF_LINEAR, HDP_COEF_USER, HDP_COEF_QUADRATIC = 0, 1, 2, 3
 HDP_G_USER, HDP_F_USER, HDP_F_NL_USER = 64, 64, 65
 HDP_G_SUMSQ, HDP_G_INV_SUMSQ, HDP_G_EXP_SUMSQ, HDP_G_MIN, HDP_G_GAUSS = 0, 1, 2, 3, 4
 HDP_F_ZERO, HDP_F_LINEAR, HDP_F_ALLEN_CAHN, HDP_F_DEFAULT_RISK, HDP_F_FISHER_KPP = 0, 1, 2, 3, 4
@@ -119,10 +119,14 @@ SYMBOLS = {
     "hdp_sde_loop_f32": (_i, [_H, _PP, _VP, _VP, _i, _i, C.c_float, _VP, _SP, _u64, _VP, _SP, _VP, _i, _i, _u]),
     "hdp_mlt_sde_loop_f64": (_i, [_H, _PP, _VP, _VP, _i, C.c_double, C.c_double, _u64, _VP, _u]),
     "hdp_mlt_sde_loop_f32": (_i, [_H, _PP, _VP, _VP, _i, C.c_float, C.c_float, _u64, _VP, _u]),
+    "hdp_set_user_exprs": (_i, [_H, C.POINTER(hdp_user_exprs)]),
+    "hdp_em_ensemble_f64": (_i, [_H, _PP, _VP, _i, _i, C.c_double, C.c_double, _VP, _u64, _VP, _u]),
+    "hdp_em_ensemble_f32": (_i, [_H, _PP, _VP, _i, _i, C.c_float, C.c_float, _VP, _u64, _VP, _u]),
     "hdp_mlp_counts_get": (_i, [_i, _i, _i, _i, _i, C.POINTER(hdp_mlp_counts)]),
     "hdp_mlp_solve_f64": (_i, [_H, _PP, C.POINTER(hdp_mlp_cfg), _VP, _VP, C.POINTER(hdp_mlp_stats)]),
     "hdp_mlp_solve_f32": (_i, [_H, _PP, C.POINTER(hdp_mlp_cfg), _VP, _VP, C.POINTER(hdp_mlp_stats)]),
     "hdp_user_kinds_check": (_i, [_PP, C.POINTER(hdp_user_exprs), _i, C.c_char_p, C.c_size_t]),
+    "hdp_user_coefs_check": (_i, [_PP, C.POINTER(hdp_user_exprs), _i, C.c_char_p, C.c_size_t]),
     "hdp_tape_fill_f64": (_i, [_H, _VP, _i, _i, _i, _u64, _u64, _u64, _i]),
     "hdp_tape_fill_f32": (_i, [_H, _VP, _i, _i, _i, _u64, _u64, _u64, _i]),
     "hdp_measure_pipe_peak": (_i, [_H, _i, C.POINTER(C.c_double)]),

@@ -116,6 +116,9 @@ extern "C" int hdp_destroy(hdp_handle h)
         for (auto& kv : h->user_modules)
             if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
         h->user_modules.clear();
+        for (auto& kv : h->sde_user_modules)
+            if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
+        h->sde_user_modules.clear();
         for (auto& b : h->buf)
             if (b.p) cudaFree(b.p);
         if (h->d_flags) cudaFree(h->d_flags);

@@ -26,6 +26,13 @@ struct UserModule {
     cudaKernel_t units = nullptr, expand = nullptr, combine = nullptr;
 };
 
+// K1 kernels (k_sde.cuh) compiled by NVRTC for one pair of user μ/σ expressions
+struct SdeUserModule {
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t sde[2][2] = {};    // [ALIGNED][INJECT], BC = K1_GENERIC
+    cudaKernel_t ens[2][2][2] = {}; // [ALIGNED][INJECT][TRAJ]
+};
+
 } // namespace hdp
 
 struct hdp_context {
@@ -47,6 +54,10 @@ struct hdp_context {
     // MLP plan cache
     std::map<std::string, std::shared_ptr<hdp::MlpPlan>> plans;
     std::map<std::string, hdp::UserModule> user_modules;
+    std::map<std::string, hdp::SdeUserModule> sde_user_modules;
+    // hdp_set_user_exprs: μ/σ expressions for the K1 entry points (copies)
+    std::string user_mu, user_sigma;
+    bool has_user_mu = false, has_user_sigma = false;
     int launches = 0;
 };
 

@@ -11,9 +11,11 @@ inline int validate_problem(hdp_context* h, const hdp_problem* p, bool allow_use
 {
     if (!p) return set_err(h, HDP_ERR_BAD_ARG, "problem is NULL");
     if (p->d <= 0) return set_err(h, HDP_ERR_BAD_ARG, "problem.d = %d", p->d);
-    const int max_coef = allow_user ? HDP_COEF_USER : HDP_COEF_LINEAR;
-    if (p->mu_kind < 0 || p->mu_kind > max_coef || p->sigma_kind < 0 || p->sigma_kind > max_coef)
-        return set_err(h, HDP_ERR_BAD_ARG, "unknown mu/sigma kind (user-defined coefficients are accepted by hdp_mlp_solve_* only)");
+    auto coef_ok = [&](int k) {
+        return k == HDP_COEF_CONST || k == HDP_COEF_LINEAR || k == HDP_COEF_QUADRATIC || (allow_user && k == HDP_COEF_USER);
+    };
+    if (!coef_ok(p->mu_kind) || !coef_ok(p->sigma_kind))
+        return set_err(h, HDP_ERR_BAD_ARG, "unknown mu/sigma kind%s", allow_user ? "" : " (this entry point takes no user-defined coefficients)");
     if (p->has_bc && !p->bc_is_scalar && (!p->lo || !p->hi))
         return set_err(h, HDP_ERR_BAD_ARG, "vector neumann_bc without lo/hi arrays");
     return HDP_OK;

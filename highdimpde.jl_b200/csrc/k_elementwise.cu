@@ -8,30 +8,12 @@
 // (src/MCSample.jl:28-33, 63-71).
 #include <string.h>
 #include "hdp_host_util.h"
+#include "k_sde.cuh"
+#include "user_kinds.h"
 
 using namespace hdp;
 
 namespace {
-
-template <typename T, bool ALIGNED>
-__device__ __forceinline__ Vec<T> load_el(const T* p, size_t q0, size_t n)
-{
-    constexpr int VEC = Tr<T>::VEC;
-    if constexpr (ALIGNED) return ldv<T>(p + q0);
-    Vec<T> r;
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) r.v[e] = (q0 + e < n) ? p[q0 + e] : (T)0;
-    return r;
-}
-template <typename T, bool ALIGNED>
-__device__ __forceinline__ void store_el(T* p, size_t q0, size_t n, const Vec<T>& r)
-{
-    constexpr int VEC = Tr<T>::VEC;
-    if constexpr (ALIGNED) { stv<T>(p + q0, r); return; }
-#pragma unroll
-    for (int e = 0; e < VEC; ++e)
-        if (q0 + e < n) p[q0 + e] = r.v[e];
-}
 
 template <typename T> struct Bounds {
     int scalar;
@@ -73,17 +55,6 @@ reflect_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__
 }
 
 // ------------------------------ K2 -----------------------------------
-template <typename T>
-__device__ __forceinline__ T sample_one(const DevSampler<T>& sm, T raw, int i, T xref)
-{
-    if (sm.kind == HDP_SAMPLER_UNIFORM) {
-        T a = sm.scalar ? sm.a_s : sm.a[i];
-        T b = sm.scalar ? sm.b_s : sm.b[i];
-        return uniform_map<T>(raw, a, b);
-    }
-    return normal_map<T>(raw, sm.sigma, sm.shifted != 0, xref);
-}
-
 template <typename T, bool ALIGNED>
 __global__ void __launch_bounds__(256)
 mc_sample_kernel(T* __restrict__ z, const T* __restrict__ y1, const T* __restrict__ inject,
@@ -115,130 +86,6 @@ mc_sample_kernel(T* __restrict__ z, const T* __restrict__ y1, const T* __restric
             store_el<T, ALIGNED>(z + (size_t)k * n_el, q0, n_el, o);
         }
     }
-}
-
-// ------------------------------ K1 -----------------------------------
-// N reflected EM steps per element; normals from dWall (INJECT) or Philox in
-// registers.  draw addressing: dWall[q + n_el*step] == draw(SDE, ordinal=step, i=q).
-// Bounds, coefficient products and validity flags are resolved into registers before
-// the step loop, so the loop body is: 1 Philox call, VEC x (Box–Muller, 3 flops, mirror).
-// BC: K1_GENERIC — any coefficient kind, any bounds, either association;
-//     K1_NOBC / K1_SYM — constant coefficients, DeepSplitting association, no boundary /
-//     symmetric scalar box (the BASELINE shape): nothing but the arithmetic is left in the loop.
-enum { K1_GENERIC = 0, K1_NOBC = 1, K1_SYM = 2 };
-#ifndef K1_STEP_UNROLL
-#define K1_STEP_UNROLL 2
-#endif
-
-template <typename T, bool ALIGNED, bool INJECT, int BC>
-__global__ void __launch_bounds__(128)
-sde_loop_kernel(DevProblem<T> pb, T* __restrict__ y0, T* __restrict__ y1, size_t n_el, int nsteps, T dt,
-                DevSampler<T> x0s, const T* __restrict__ x0_inject, u64 seed, const T* __restrict__ dW,
-                DevSampler<T> mc, T* __restrict__ z, int K, int* flags, unsigned long long* bounce_ctr,
-                int mlp_assoc, int zero)
-{
-    constexpr int VEC = Tr<T>::VEC;
-    if constexpr (sizeof(T) == 8) tables_init();
-    const int d = pb.d;
-    const size_t nv = (n_el + VEC - 1) / VEC;
-    const T sq = sqrt_rn(dt);
-    const bool has_bc = BC == K1_GENERIC ? pb.has_bc != 0 : BC == K1_SYM;
-    const bool mu_lin = pb.mu_kind == HDP_COEF_LINEAR, sg_lin = pb.sigma_kind == HDP_COEF_LINEAR;
-    const T mudt_c = mul_rn(pb.mu_c, dt), sgsq_c = mul_rn(pb.sigma_c, sq);
-    bool bad = false;
-    int nb_total = 0;
-    const DrawK<T> dk = draw_k_init<T>(BC != K1_GENERIC ? zero : 0);
-    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (size_t)gridDim.x * blockDim.x) {
-        const size_t q0 = v * VEC;
-        const int i0 = n_el <= 0xffffffffull ? (int)((uint32_t)q0 % (uint32_t)d) : (int)(q0 % (size_t)d);
-        Vec<T> cur = load_el<T, ALIGNED>(y1, q0, n_el);
-        // x0_sample!(y1), 1-argument sampler form (src/DeepSplitting.jl:155)
-        if (x0s.kind != HDP_SAMPLER_NONE) {
-            Vec<T> raw = x0_inject ? load_el<T, ALIGNED>(x0_inject, q0, n_el)
-                                   : draw_vec<T>(seed, HDP_STREAM_X0, 0, (u64)v, x0s.kind == HDP_SAMPLER_NORMAL);
-            int i = i0;
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) {
-                if (x0s.kind == HDP_SAMPLER_UNIFORM) cur.v[e] = sample_one<T>(x0s, raw.v[e], i, (T)0);
-                else cur.v[e] = normal_map<T>(raw.v[e], x0s.sigma, false, (T)0);
-                if (++i == d) i = 0;
-            }
-        }
-        Vec<T> lo, hi;
-        if (has_bc) {
-            int i = i0;
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) {
-                lo.v[e] = pb.bc_is_scalar ? pb.lo_s : pb.lo[i];
-                hi.v[e] = pb.bc_is_scalar ? pb.hi_s : pb.hi[i];
-                // @assert all((a .>= s) .& (a .<= e))  (src/reflect.jl:59): a = y0 of the first step
-                if (q0 + e < n_el && !(cur.v[e] >= lo.v[e] && cur.v[e] <= hi.v[e])) bad = true;
-                if (++i == d) i = 0;
-            }
-        }
-        Vec<T> prev = cur;
-        int st = 0;
-        if constexpr (BC != K1_GENERIC && !INJECT && K1_STEP_UNROLL > 1) {
-            // the normals of consecutive steps do not depend on the state: several Philox / Box–Muller chains in flight
-            constexpr int SU = K1_STEP_UNROLL;
-            for (; st + SU - 1 < nsteps; st += SU) {
-                Vec<T> xs[SU];
-#pragma unroll
-                for (int u = 0; u < SU; ++u) xs[u] = draw_vec<T>(seed, HDP_STREAM_SDE, (u64)(st + u), (u64)v, true, dk);
-#pragma unroll
-                for (int u = 0; u < SU; ++u) {
-                    prev = cur; // y0 .= y1 (:159)
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e)
-                        cur.v[e] = add_rn(add_rn(prev.v[e], mudt_c), mul_rn(sgsq_c, xs[u].v[e])); // :160
-                    if constexpr (BC == K1_SYM) reflect_vec_sym<T, false>(cur, pb.hi_s, nb_total); // :161-163
-                }
-            }
-        }
-        for (; st < nsteps; ++st) {
-            Vec<T> xi;
-            if constexpr (INJECT) xi = load_el<T, ALIGNED>(dW + (size_t)st * n_el, q0, n_el);
-            else xi = draw_vec<T>(seed, HDP_STREAM_SDE, (u64)st, (u64)v, true, dk);
-            prev = cur; // y0 .= y1 (:159)
-            if constexpr (BC == K1_GENERIC) {
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) {
-                    const T x = prev.v[e];
-                    const T mudt = mu_lin ? mul_rn(mul_rn(pb.mu_c, x), dt) : mudt_c;
-                    const T sgsq = sg_lin ? mul_rn(mul_rn(pb.sigma_c, x), sq) : sgsq_c;
-                    if (mlp_assoc) cur.v[e] = add_rn(x, add_rn(mudt, mul_rn(sgsq, xi.v[e]))); // src/MLP.jl:417
-                    else cur.v[e] = add_rn(add_rn(x, mudt), mul_rn(sgsq, xi.v[e])); // :160 (y0 + μ*dt) + (σ*sq)*dW
-                }
-                if (has_bc) reflect_vec<T, 1, false>(cur, lo, hi, 0u, nb_total); // :161-163
-            } else {
-#pragma unroll
-                for (int e = 0; e < VEC; ++e)
-                    cur.v[e] = add_rn(add_rn(prev.v[e], mudt_c), mul_rn(sgsq_c, xi.v[e])); // :160
-                if constexpr (BC == K1_SYM) reflect_vec_sym<T, false>(cur, pb.hi_s, nb_total); // :161-163
-            }
-        }
-        store_el<T, ALIGNED>(y0, q0, n_el, prev);
-        store_el<T, ALIGNED>(y1, q0, n_el, cur);
-        // fused epilogue mc_sample!(z, y1) (src/DeepSplitting.jl:186-189)
-        if (z != nullptr && mc.kind != HDP_SAMPLER_NONE) {
-            const bool normal = mc.kind == HDP_SAMPLER_NORMAL;
-            for (int k = 0; k < K; ++k) {
-                Vec<T> raw = draw_vec<T>(seed, HDP_STREAM_MC, (u64)k, (u64)v, normal);
-                int i = i0;
-                Vec<T> o;
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) {
-                    o.v[e] = sample_one<T>(mc, raw.v[e], i, cur.v[e]);
-                    if (++i == d) i = 0;
-                }
-                store_el<T, ALIGNED>(z + (size_t)k * n_el, q0, n_el, o);
-            }
-        }
-    }
-    if (bad) atomicExch(&flags[0], 1);
-    // one atomic per warp, not per thread: a single-address atomic serialises
-    nb_total = __reduce_add_sync(0xffffffffu, nb_total);
-    if (bounce_ctr && nb_total && (threadIdx.x & 31) == 0) atomicAdd(bounce_ctr, (unsigned long long)nb_total);
 }
 
 inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
@@ -380,23 +227,65 @@ int mc_sample_impl(hdp_handle h, T* z, const T* y1, int d, int B, int K, const h
 }
 
 // ------------------------------ K1 host ------------------------------
+inline bool uses_user_coef(const hdp_problem* p) { return p->mu_kind == HDP_COEF_USER || p->sigma_kind == HDP_COEF_USER; }
+
+// NVRTC-built K1 kernels for the expressions of hdp_set_user_exprs (once per handle and expression pair)
+int get_sde_user_module(hdp_context* h, const hdp_problem* prob, bool f32, SdeUserModule** out)
+{
+    hdp_user_exprs u{};
+    u.mu = h->has_user_mu ? h->user_mu.c_str() : nullptr;
+    u.sigma = h->has_user_sigma ? h->user_sigma.c_str() : nullptr;
+    std::string key = f32 ? "f32/" : "f64/";
+    key += (prob->mu_kind == HDP_COEF_USER && u.mu) ? u.mu : "-";
+    key += "\x1f";
+    key += (prob->sigma_kind == HDP_COEF_USER && u.sigma) ? u.sigma : "-";
+    auto it = h->sde_user_modules.find(key);
+    if (it != h->sde_user_modules.end()) { *out = &it->second; return HDP_OK; }
+    SdeUserBuild b;
+    int rc = user_compile_sde(prob, &u, f32, &b);
+    if (rc != HDP_OK) return set_err(h, rc, "%s", b.log.c_str());
+    SdeUserModule m;
+    HDP_CUDA(h, cudaLibraryLoadData(&m.lib, b.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+    int n = 0;
+    for (int al = 0; al < 2; ++al)
+        for (int inj = 0; inj < 2; ++inj) HDP_CUDA(h, cudaLibraryGetKernel(&m.sde[al][inj], m.lib, b.names[n++].c_str()));
+    for (int al = 0; al < 2; ++al)
+        for (int inj = 0; inj < 2; ++inj)
+            for (int tr = 0; tr < 2; ++tr) HDP_CUDA(h, cudaLibraryGetKernel(&m.ens[al][inj][tr], m.lib, b.names[n++].c_str()));
+    auto ins = h->sde_user_modules.emplace(key, m);
+    *out = &ins.first->second;
+    return HDP_OK;
+}
+
 template <typename T>
 int sde_loop_impl(hdp_handle h, const hdp_problem* prob, T* y0, T* y1, int B, int nsteps, T dt, const T* ts,
                   const hdp_sampler* x0_sampler, uint64_t seed, const T* dWall_inject,
                   const hdp_sampler* mc, T* z, int K, int normal_mode, unsigned mem_flags, int mlp_assoc = 0)
 {
-    (void)ts; // every supported coefficient kind is time-independent
     if (!h || !prob || !y0 || !y1 || B < 0 || nsteps < 0) return HDP_ERR_BAD_ARG;
     if (normal_mode != HDP_NORMAL_DEFAULT && normal_mode != (sizeof(T) == 8 ? HDP_NORMAL_BM64 : HDP_NORMAL_BM32))
         return set_err(h, HDP_ERR_UNSUPPORTED, "normal_mode %d not supported for this element type", normal_mode);
     std::lock_guard<std::mutex> lk(h->mu);
     DeviceGuard g(h->device);
     DevProblem<T> pb;
-    int rc = make_dev_problem<T>(h, prob, hdp_context::B_E, &pb);
+    int rc = make_dev_problem<T>(h, prob, hdp_context::B_E, &pb, /*allow_user=*/true);
     if (rc != HDP_OK) return rc;
     const int d = prob->d;
     const size_t n_el = (size_t)d * (size_t)B;
     if (n_el == 0) return HDP_OK;
+    // user μ/σ: the enumerated kinds are time-independent, expressions may read t = ts[step]
+    SdeUserModule* um = nullptr;
+    const T* dts = nullptr;
+    if (uses_user_coef(prob)) {
+        if (!ts && nsteps > 0) return set_err(h, HDP_ERR_BAD_ARG, "sde_loop!: user-defined mu/sigma need ts (t = ts[N+1-i])");
+        if ((rc = get_sde_user_module(h, prob, sizeof(T) == 4, &um)) != HDP_OK) return rc;
+        if (nsteps > 0) { // ts is a HOST array whatever mem_flags says (a Julia range, collected)
+            T* t = (T*)ensure(h, hdp_context::B_I, (size_t)nsteps * sizeof(T));
+            if (!t) return HDP_ERR_ALLOC;
+            HDP_CUDA(h, cudaMemcpyAsync(t, ts, (size_t)nsteps * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+            dts = t;
+        }
+    }
     DevSampler<T> x0s, mcs;
     if ((rc = make_dev_sampler<T>(h, x0_sampler, d, hdp_context::B_F, &x0s)) != HDP_OK) return rc;
     if ((rc = make_dev_sampler<T>(h, mc, d, hdp_context::B_G, &mcs)) != HDP_OK) return rc;
@@ -435,7 +324,7 @@ int sde_loop_impl(hdp_handle h, const hdp_problem* prob, T* y0, T* y1, int B, in
 #define LAUNCH3(AL, INJ, BC)                                                                              \
     sde_loop_kernel<T, AL, INJ, BC><<<grid, threads, 0, h->stream>>>(pb, dy0, dy1, n_el, nsteps, dt, x0s, \
                                                                      nullptr, seed, ddw, mcs, dz, K,       \
-                                                                     h->d_flags, h->d_ctr + 1, mlp_assoc, 0)
+                                                                     h->d_flags, h->d_ctr + 1, mlp_assoc, 0, dts)
 #define LAUNCH(AL, INJ)                                                                                   \
     do {                                                                                                  \
         if (bc == K1_SYM) LAUNCH3(AL, INJ, K1_SYM);                                                       \
@@ -443,7 +332,17 @@ int sde_loop_impl(hdp_handle h, const hdp_problem* prob, T* y0, T* y1, int B, in
         else LAUNCH3(AL, INJ, K1_GENERIC);                                                                \
     } while (0)
     HDP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-    if (al && ddw) LAUNCH(true, true);
+    if (um) {
+        const T* x0_inject = nullptr;
+        int* flags = h->d_flags;
+        unsigned long long* bctr = h->d_ctr + 1;
+        int zero = 0;
+        size_t n_el_ = n_el;
+        u64 seed_ = seed;
+        void* args[] = {&pb, &dy0, &dy1, &n_el_, &nsteps, &dt, &x0s, &x0_inject, &seed_, &ddw, &mcs, &dz, &K,
+                        &flags, &bctr, &mlp_assoc, &zero, &dts};
+        HDP_CUDA(h, cudaLaunchKernel((const void*)um->sde[al ? 1 : 0][ddw ? 1 : 0], dim3(grid), dim3(threads), args, 0, h->stream));
+    } else if (al && ddw) LAUNCH(true, true);
     else if (al) LAUNCH(true, false);
     else if (ddw) LAUNCH(false, true);
     else LAUNCH(false, false);
@@ -489,12 +388,114 @@ int mlt_sde_loop_impl(hdp_handle h, const hdp_problem* prob, T* x2, const T* x, 
         y0_host.resize(n_el);
         y0 = y0_host.data();
     }
-    return sde_loop_impl<T>(h, prob, y0, x2, B, 1, (T)(t - s), nullptr, nullptr, seed, inject, nullptr, nullptr, 0,
+    // μ(x, p, t), σ(x, p, t) take the END time of the step (src/MLP.jl:417)
+    return sde_loop_impl<T>(h, prob, y0, x2, B, 1, (T)(t - s), &t, nullptr, seed, inject, nullptr, nullptr, 0,
                             HDP_NORMAL_DEFAULT, mem_flags & ~(unsigned)HDP_ASYNC, /*mlp_assoc=*/1);
+}
+
+// ------------------------------ K1e host -----------------------------
+template <typename T>
+int em_ensemble_impl(hdp_handle h, const hdp_problem* prob, T* x, int B, int nsteps, T dt, T t0, T* traj,
+                     uint64_t seed, const T* inject, unsigned mem_flags)
+{
+    if (!h || !prob || !x || B < 0 || nsteps < 0) return HDP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    DevProblem<T> pb;
+    hdp_problem pr = *prob; // no reflection on this path: the solvers it serves have no neumann_bc
+    pr.has_bc = 0;
+    int rc = make_dev_problem<T>(h, &pr, hdp_context::B_E, &pb, /*allow_user=*/true);
+    if (rc != HDP_OK) return rc;
+    const int d = prob->d;
+    const size_t n_el = (size_t)d * (size_t)B;
+    if (n_el == 0) return HDP_OK;
+    SdeUserModule* um = nullptr;
+    if (uses_user_coef(prob) && (rc = get_sde_user_module(h, prob, sizeof(T) == 4, &um)) != HDP_OK) return rc;
+    const size_t n_traj = n_el * ((size_t)nsteps + 1);
+    T *dx, *dtraj = nullptr;
+    const T* ddw = nullptr;
+    if (mem_flags & HDP_MEM_DEVICE) { dx = x; dtraj = traj; ddw = inject; }
+    else {
+        dx = (T*)ensure(h, hdp_context::B_A, n_el * sizeof(T));
+        if (!dx) return HDP_ERR_ALLOC;
+        HDP_CUDA(h, cudaMemcpyAsync(dx, x, n_el * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+        if (inject) {
+            T* t = (T*)ensure(h, hdp_context::B_C, n_el * (size_t)nsteps * sizeof(T));
+            if (!t) return HDP_ERR_ALLOC;
+            HDP_CUDA(h, cudaMemcpyAsync(t, inject, n_el * (size_t)nsteps * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+            ddw = t;
+        }
+        if (traj) {
+            dtraj = (T*)ensure(h, hdp_context::B_D, n_traj * sizeof(T));
+            if (!dtraj) return HDP_ERR_ALLOC;
+        }
+    }
+    constexpr int VEC = Tr<T>::VEC;
+    const size_t nv = (n_el + VEC - 1) / VEC;
+    if (!draw_address_ok(HDP_STREAM_SDE, (u64)nsteps, (u64)nv))
+        return set_err(h, HDP_ERR_BAD_ARG, "em_ensemble: more than 2^24 steps or 2^37 vec-groups");
+    // vector accesses need whole vec-groups inside one column of the trajectory array
+    const bool al = (n_el % VEC == 0) && aligned16(dx) && aligned16(ddw) && (!dtraj || (d % VEC == 0 && aligned16(dtraj)));
+    const int threads = 128;
+    const int grid = grid_for(h, nv, threads, 64);
+    HDP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    if (um) {
+        size_t n_el_ = n_el;
+        u64 seed_ = seed;
+        void* args[] = {&pb, &dx, &n_el_, &nsteps, &dt, &t0, &dtraj, &seed_, &ddw};
+        HDP_CUDA(h, cudaLaunchKernel((const void*)um->ens[al ? 1 : 0][ddw ? 1 : 0][dtraj ? 1 : 0], dim3(grid), dim3(threads), args, 0, h->stream));
+    } else {
+#define LAUNCH_E(AL, INJ, TR) \
+    em_ensemble_kernel<T, AL, INJ, TR><<<grid, threads, 0, h->stream>>>(pb, dx, n_el, nsteps, dt, t0, dtraj, seed, ddw)
+#define LAUNCH_E2(AL, INJ)              \
+    do {                                \
+        if (dtraj) LAUNCH_E(AL, INJ, true); \
+        else LAUNCH_E(AL, INJ, false);  \
+    } while (0)
+        if (al && ddw) LAUNCH_E2(true, true);
+        else if (al) LAUNCH_E2(true, false);
+        else if (ddw) LAUNCH_E2(false, true);
+        else LAUNCH_E2(false, false);
+#undef LAUNCH_E2
+#undef LAUNCH_E
+    }
+    HDP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    h->launches++;
+    HDP_CUDA(h, cudaGetLastError());
+    if (mem_flags & HDP_MEM_DEVICE) {
+        if (!(mem_flags & HDP_ASYNC)) HDP_CUDA(h, cudaStreamSynchronize(h->stream));
+        return HDP_OK;
+    }
+    HDP_CUDA(h, cudaMemcpyAsync(x, dx, n_el * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+    if (traj) HDP_CUDA(h, cudaMemcpyAsync(traj, dtraj, n_traj * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+    HDP_CUDA(h, cudaStreamSynchronize(h->stream));
+    return HDP_OK;
 }
 
 } // namespace
 
+extern "C" int hdp_set_user_exprs(hdp_handle h, const hdp_user_exprs* user)
+{
+    if (!h) return HDP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->has_user_mu = user && user->mu;
+    h->has_user_sigma = user && user->sigma;
+    h->user_mu = h->has_user_mu ? user->mu : "";
+    h->user_sigma = h->has_user_sigma ? user->sigma : "";
+    return HDP_OK;
+}
+extern "C" int hdp_em_ensemble_f64(hdp_handle h, const hdp_problem* prob, double* x, int B, int nsteps, double dt,
+                                   double t0, double* traj, uint64_t seed, const double* normals_inject,
+                                   unsigned mem_flags)
+{
+    return em_ensemble_impl<double>(h, prob, x, B, nsteps, dt, t0, traj, seed, normals_inject, mem_flags);
+}
+extern "C" int hdp_em_ensemble_f32(hdp_handle h, const hdp_problem* prob, float* x, int B, int nsteps, float dt,
+                                   float t0, float* traj, uint64_t seed, const float* normals_inject,
+                                   unsigned mem_flags)
+{
+    return em_ensemble_impl<float>(h, prob, x, B, nsteps, dt, t0, traj, seed, normals_inject, mem_flags);
+}
 extern "C" int hdp_mlt_sde_loop_f64(hdp_handle h, const hdp_problem* prob, double* x2, const double* x, int B,
                                     double s, double t, uint64_t seed, const double* normals_inject, unsigned mem_flags)
 {

@@ -334,8 +334,8 @@ __device__ HDP_NOINLINE Feat<T> em_step_generic(Ctx<T, G>& c, const XAcc<T>& src
     const T lo_s = P.pb.lo_s, hi_s = P.pb.hi_s;
     const bool mu_lin = P.pb.mu_kind == HDP_COEF_LINEAR;
     const bool sg_lin = P.pb.sigma_kind == HDP_COEF_LINEAR;
-    const bool mu_usr = P.pb.mu_kind == HDP_COEF_USER;
-    const bool sg_usr = P.pb.sigma_kind == HDP_COEF_USER;
+    const bool mu_usr = P.pb.mu_kind == HDP_COEF_USER || P.pb.mu_kind == HDP_COEF_QUADRATIC;
+    const bool sg_usr = P.pb.sigma_kind == HDP_COEF_USER || P.pb.sigma_kind == HDP_COEF_QUADRATIC;
     const T mu_c = P.pb.mu_c, sg_c = P.pb.sigma_c;
     const bool want_min = P.pb.g_kind == HDP_G_MIN || P.pb.g_kind == HDP_G_USER;
     const T dt = sub_rn(tend, s);  // :415
@@ -365,8 +365,8 @@ __device__ HDP_NOINLINE Feat<T> em_step_generic(Ctx<T, G>& c, const XAcc<T>& src
             T mudt = mu_lin ? mul_rn(mul_rn(mu_c, x), dt) : mudt_c;
             T sgsq = sg_lin ? mul_rn(mul_rn(sg_c, x), sq) : sgsq_c;
             // μ(x,p,t), σ(x,p,t) are evaluated at the start point and the END time (:417)
-            if (mu_usr) mudt = mul_rn(user_mu<T>(x, p * VEC + e, tend, d, P.pb.mu_p), dt);
-            if (sg_usr) sgsq = mul_rn(user_sigma<T>(x, p * VEC + e, tend, d, P.pb.sigma_p), sq);
+            if (mu_usr) mudt = mul_rn(coef_any<T>(P.pb.mu_kind, P.pb.mu_p, x, p * VEC + e, tend, d, 0), dt);
+            if (sg_usr) sgsq = mul_rn(coef_any<T>(P.pb.sigma_kind, P.pb.sigma_p, x, p * VEC + e, tend, d, 1), sq);
             o.v[e] = add_rn(x, add_rn(mudt, mul_rn(sgsq, xi.v[e]))); // :417  x + (μ*dt + (σ*sq)*ξ)
         }
         if (has_bc) { // :418-420

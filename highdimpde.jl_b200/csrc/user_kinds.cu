@@ -153,6 +153,70 @@ int user_compile(const hdp_problem* p, const hdp_user_exprs* u, bool f32, int G,
     return HDP_OK;
 }
 
+int user_compile_sde(const hdp_problem* p, const hdp_user_exprs* u, bool f32, SdeUserBuild* out)
+{
+    out->cubin.clear();
+    out->log.clear();
+    out->names.clear();
+    if (!u) { out->log = "the problem uses HDP_COEF_USER but no expressions were set (hdp_set_user_exprs)"; return HDP_ERR_BAD_ARG; }
+    struct Need { bool on; const char* e; const char* what; const char* macro; } needs[2] = {
+        {p->mu_kind == HDP_COEF_USER, u->mu, "mu", "HDP_USER_MU_EXPR"},
+        {p->sigma_kind == HDP_COEF_USER, u->sigma, "sigma", "HDP_USER_SIGMA_EXPR"}};
+    for (auto& n : needs)
+        if (n.on && bad_expr(n.e)) {
+            out->log = std::string("user expression for ") + n.what +
+                       " is missing or not a plain C expression (no ';', braces, '#', newlines)";
+            return HDP_ERR_BAD_ARG;
+        }
+    NvrtcApi* a = nvrtc_api();
+    if (!a->err.empty()) { out->log = a->err; return HDP_ERR_NVRTC; }
+    const std::string T = f32 ? "float" : "double";
+    std::string src;
+    src += "typedef signed char int8_t; typedef unsigned char uint8_t; typedef int int32_t; typedef unsigned int uint32_t;\n"
+           "typedef long long int64_t; typedef unsigned long long uint64_t; typedef unsigned long uintptr_t;\n";
+    for (auto& n : needs)
+        if (n.on) src += std::string("#define ") + n.macro + " (" + n.e + ")\n";
+    src += "#include \"k_sde.cuh\"\n";
+    const char* tf[2] = {"false", "true"};
+    std::vector<std::string> exprs;
+    for (int al = 0; al < 2; ++al)
+        for (int inj = 0; inj < 2; ++inj)
+            exprs.push_back("hdp::sde_loop_kernel<" + T + ", " + tf[al] + ", " + tf[inj] + ", hdp::K1_GENERIC>");
+    for (int al = 0; al < 2; ++al)
+        for (int inj = 0; inj < 2; ++inj)
+            for (int tr = 0; tr < 2; ++tr)
+                exprs.push_back("hdp::em_ensemble_kernel<" + T + ", " + tf[al] + ", " + tf[inj] + ", " + tf[tr] + ">");
+    nvrtcProgram prog = nullptr;
+    int rc = a->CreateProgram(&prog, src.c_str(), "hdp_user_sde.cu", kEmbCount, kEmbSrc, kEmbNames);
+    if (rc != 0) { out->log = std::string("nvrtcCreateProgram: ") + a->GetErrorString(rc); return HDP_ERR_NVRTC; }
+    for (auto& e : exprs) a->AddNameExpression(prog, e.c_str());
+    const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-fmad=false", "-default-device"};
+    rc = a->CompileProgram(prog, 4, opts);
+    size_t ls = 0;
+    a->GetProgramLogSize(prog, &ls);
+    if (ls > 1) {
+        out->log.resize(ls);
+        a->GetProgramLog(prog, &out->log[0]);
+    }
+    if (rc != 0) {
+        out->log = std::string("NVRTC compilation of the user coefficients failed: ") + a->GetErrorString(rc) + "\n" + out->log;
+        a->DestroyProgram(&prog);
+        return HDP_ERR_BAD_ARG; // the expressions are the caller's
+    }
+    for (auto& e : exprs) {
+        const char* low = nullptr;
+        a->GetLoweredName(prog, e.c_str(), &low);
+        out->names.push_back(low ? low : "");
+    }
+    size_t cs = 0;
+    a->GetCUBINSize(prog, &cs);
+    out->cubin.resize(cs);
+    if (cs) a->GetCUBIN(prog, out->cubin.data());
+    a->DestroyProgram(&prog);
+    if (!cs || out->names[0].empty()) { out->log += "\nNVRTC produced no cubin"; return HDP_ERR_NVRTC; }
+    return HDP_OK;
+}
+
 } // namespace hdp
 
 extern "C" int hdp_user_kinds_check(const hdp_problem* prob, const hdp_user_exprs* user, int is_f32, char* log,
@@ -163,6 +227,21 @@ extern "C" int hdp_user_kinds_check(const hdp_problem* prob, const hdp_user_expr
     if (!hdp::user_needed(prob)) return HDP_OK;
     hdp::UserBuild b;
     int rc = hdp::user_compile(prob, user, is_f32 != 0, 4, &b);
+    if (log && log_cap) {
+        strncpy(log, b.log.c_str(), log_cap - 1);
+        log[log_cap - 1] = 0;
+    }
+    return rc;
+}
+
+extern "C" int hdp_user_coefs_check(const hdp_problem* prob, const hdp_user_exprs* user, int is_f32, char* log,
+                                    size_t log_cap)
+{
+    if (!prob) return HDP_ERR_BAD_ARG;
+    if (log && log_cap) log[0] = 0;
+    if (prob->mu_kind != HDP_COEF_USER && prob->sigma_kind != HDP_COEF_USER) return HDP_OK;
+    hdp::SdeUserBuild b;
+    int rc = hdp::user_compile_sde(prob, user, is_f32 != 0, &b);
     if (log && log_cap) {
         strncpy(log, b.log.c_str(), log_cap - 1);
         log[log_cap - 1] = 0;

@@ -43,6 +43,19 @@ class LinearCoef:
         return [self.c, 0.0]
 
 
+@dataclass(frozen=True)
+class QuadraticCoef:
+    """σ(x,p,t) = c * x .^ 2   (test/DeepSplitting.jl:355)"""
+    c: float
+    kind = capi.HDP_COEF_QUADRATIC
+
+    def __call__(self, x, p=None, t=None):
+        return self.c * np.asarray(x) ** 2
+
+    def params(self):
+        return [self.c, 0.0]
+
+
 _PY_ENV = {"exp": math.exp, "log": math.log, "sqrt": math.sqrt, "fabs": abs, "abs": abs, "pow": pow, "sin": math.sin,
            "cos": math.cos, "tanh": math.tanh, "fmax": max, "fmin": min, "max": max, "min": min, "floor": math.floor,
            "erf": math.erf, "M_PI": math.pi}
@@ -57,7 +70,8 @@ def _py_eval(expr, **names):
 @dataclass(frozen=True)
 class UserCoef:
     """μ(x,p,t)[i] / σ(x,p,t)[i] as a CUDA-C expression over `x` (the coordinate), `i`, `t` (the time the
-    reference passes: the end of the step), `d`, `p[0..1]` — compiled with NVRTC into the MLP kernels."""
+    reference passes: the end of the step in MLP, ts[N+1-i] in sde_loop!, t_k in an EM ensemble), `d`,
+    `p[0..1]` — compiled with NVRTC into the MLP / sde_loop! / ensemble kernels."""
     expr: str
     p: tuple = ()
     kind = capi.HDP_COEF_USER
@@ -72,7 +86,7 @@ class UserCoef:
 
 
 def as_coef(v):
-    if isinstance(v, (ConstCoef, LinearCoef, UserCoef)):
+    if isinstance(v, (ConstCoef, LinearCoef, QuadraticCoef, UserCoef)):
         return v
     if isinstance(v, (int, float, np.floating)):
         return ConstCoef(float(v))

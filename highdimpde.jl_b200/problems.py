@@ -74,6 +74,20 @@ class _Problem:
             raise capi.HdpError(rc, msg)
         return msg
 
+    def check_user_coefs(self, dtype=np.float64) -> str:
+        """The same for the sde_loop! / EM-ensemble kernels (user μ, σ only)."""
+        ue = self.user_exprs()
+        if ue is None:
+            return ""
+        lib = capi.load_library()
+        pb, keep = self.to_c()
+        log = C.create_string_buffer(1 << 16)
+        rc = lib.hdp_user_coefs_check(C.byref(pb), C.byref(ue), int(np.dtype(dtype) == np.float32), log, len(log))
+        msg = log.value.decode("utf-8", "replace")
+        if rc != capi.HDP_OK:
+            raise capi.HdpError(rc, msg)
+        return msg
+
     def to_c(self):
         """hdp_problem descriptor (+ the numpy arrays it points to, which must stay alive)."""
         pb = capi.hdp_problem()

@@ -39,13 +39,21 @@ def _reflect(a, b, s, e, *, return_bounces=False, handle=None):
     return (out, cnt) if return_bounces else out
 
 
+def _set_user_coefs(h, prob):
+    """hdp_set_user_exprs with the problem's μ/σ expressions (HDP_COEF_USER), cleared otherwise."""
+    ue = prob.user_exprs()
+    capi.check(h.h, h.lib.hdp_set_user_exprs(h.h, C.byref(ue) if ue is not None else None))
+    return ue
+
+
 def sde_loop(prob, y0, y1, nsteps, dt, *, ts=None, dWall=None, seed=0, mc_sample=None, z=None, handle=None):
     """sde_loop!(y0, y1, dWall) (src/DeepSplitting.jl:153-166): `nsteps` reflected
     Euler–Maruyama steps of the d×B batch.  y1 holds x0_batch on entry (:182); on
     return y0 is the state before the last step and y1 the final state.
     dWall: optional injected d×B×nsteps standard normals (the reference's array after
     randn!, :154); by default the normals are Philox draws generated in registers.
-    mc_sample / z: optional fused `mc_sample!(z, y1)` (:186-189), z is d×B×K."""
+    mc_sample / z: optional fused `mc_sample!(z, y1)` (:186-189), z is d×B×K.
+    ts: the time passed to μ, σ at each step (Julia's ts[N+1-i], :157); required for UserCoef kinds."""
     h = handle or capi.default_handle()
     dtp = y1.dtype
     if dtp not in (np.float32, np.float64) or y0.dtype != dtp:
@@ -70,6 +78,9 @@ def sde_loop(prob, y0, y1, nsteps, dt, *, ts=None, dWall=None, seed=0, mc_sample
         if dw.shape != (d, B, nsteps):
             raise ValueError("dWall must be d×B×nsteps")
     tsa = None if ts is None else np.ascontiguousarray(ts, dtype=dtp)
+    if tsa is not None and tsa.shape != (nsteps,):
+        raise ValueError("ts must hold nsteps times")
+    ue = _set_user_coefs(h, prob)
     if dtp == np.float64:
         fn, dtc = h.lib.hdp_sde_loop_f64, C.c_double(dt)
     else:
@@ -77,7 +88,7 @@ def sde_loop(prob, y0, y1, nsteps, dt, *, ts=None, dWall=None, seed=0, mc_sample
     capi.check(h.h, fn(h.h, C.byref(pb), capi.np_ptr(y0), capi.np_ptr(y1), B, int(nsteps), dtc,
                        capi.np_ptr(tsa), C.byref(x0s), int(seed), capi.np_ptr(dw), C.byref(mcs),
                        capi.np_ptr(z), K, capi.HDP_NORMAL_DEFAULT, capi.HDP_MEM_HOST))
-    del keep, keep2, keep3
+    del keep, keep2, keep3, ue
     return y0, y1
 
 
@@ -96,11 +107,51 @@ def _mlt_sde_loop(x2, x, s, t, prob, *, normals=None, seed=0, handle=None):
     B = 1 if x.ndim == 1 else int(np.prod(x.shape[1:]))
     pb, keep = prob.to_c()
     inj = None if normals is None else np.asarray(normals, dtype=dt_, order="F")
+    ue = _set_user_coefs(h, prob)
     if dt_ == np.float64:
         fn, a, b = h.lib.hdp_mlt_sde_loop_f64, C.c_double(s), C.c_double(t)
     else:
         fn, a, b = h.lib.hdp_mlt_sde_loop_f32, C.c_float(s), C.c_float(t)
     capi.check(h.h, fn(h.h, C.byref(pb), capi.np_ptr(x2), capi.np_ptr(xa), B, a, b, int(seed), capi.np_ptr(inj),
                        capi.HDP_MEM_HOST))
-    del keep
+    del keep, ue
     return x2
+
+
+def em_ensemble(prob, x0, dt, *, trajectories=None, saveat=False, normals=None, seed=0, handle=None):
+    """`solve(EnsembleProblem(SDEProblem(μ, σ, x0, tspan)), EM(); dt, trajectories, adaptive=false)` — the
+    pre-simulation stage of NNKolmogorov (src/NNKolmogorov.jl:81-112, final states only) and NNStopping
+    (src/NNStopping.jl:90-99, `saveat = dt`).  x0: a d-vector (every trajectory starts there; give
+    `trajectories`) or a d×B column-major matrix (trajectory b starts at x0[:, b], the `prob_func` of
+    NNKolmogorov).  Returns the d×B final states, or with saveat=True the d×(N+1)×B array `Array(sim)`.
+    normals: optional injected d×B×N standard normals."""
+    h = handle or capi.default_handle()
+    x0 = np.asarray(x0)
+    dtp = x0.dtype if x0.dtype in (np.float32, np.float64) else np.dtype(np.float64)
+    if x0.ndim == 1:
+        if trajectories is None:
+            raise ValueError("trajectories is required when x0 is a vector")
+        x = np.asfortranarray(np.repeat(np.asarray(x0, dtype=dtp)[:, None], int(trajectories), axis=1))
+    else:
+        x = np.array(x0, dtype=dtp, order="F")
+    d, B = x.shape
+    if d != prob.d:
+        raise ValueError("shape mismatch")
+    t0, t1 = prob.tspan
+    nsteps = int(round((t1 - t0) / dt))
+    pb, keep = prob.to_c()
+    inj = None
+    if normals is not None:
+        inj = np.asarray(normals, dtype=dtp, order="F")
+        if inj.shape != (d, B, nsteps):
+            raise ValueError("normals must be d×B×nsteps")
+    traj = np.empty((d, nsteps + 1, B), dtype=dtp, order="F") if saveat else None
+    ue = _set_user_coefs(h, prob)
+    if dtp == np.float64:
+        fn, dtc, t0c = h.lib.hdp_em_ensemble_f64, C.c_double(dt), C.c_double(t0)
+    else:
+        fn, dtc, t0c = h.lib.hdp_em_ensemble_f32, C.c_float(dt), C.c_float(t0)
+    capi.check(h.h, fn(h.h, C.byref(pb), capi.np_ptr(x), B, nsteps, dtc, t0c, capi.np_ptr(traj), int(seed),
+                       capi.np_ptr(inj), capi.HDP_MEM_HOST))
+    del keep, ue
+    return traj if saveat else x

@@ -77,9 +77,11 @@ enum {
 enum {
     HDP_COEF_CONST = 0,  /* c             p[0]=c   (test/MLP.jl:24-25)    */
     HDP_COEF_LINEAR = 1, /* c * x_i       p[0]=c   (test/MLP.jl:191-192)  */
-    HDP_COEF_USER = 2    /* hdp_user_exprs.mu / .sigma: a CUDA-C expression over
+    HDP_COEF_USER = 2,   /* hdp_user_exprs.mu / .sigma: a CUDA-C expression over
                             x (the coordinate), i (its index), t (the time the
-                            reference passes: the step's end time), d, p[0..1]  */
+                            reference passes: the step's end time in MLP, ts[N+1-i]
+                            in sde_loop!, t_k in an EM ensemble), d, p[0..1]    */
+    HDP_COEF_QUADRATIC = 3 /* c * x_i^2   p[0]=c   (test/DeepSplitting.jl:355: sigma * x .^ 2) */
 };
 
 /* g(x): terminal/initial condition prob.g, used at src/MLP.jl:203 */
@@ -177,7 +179,9 @@ typedef struct hdp_problem {
  * expressions compiled with NVRTC into the K3 kernels on first use and cached in the
  * handle.  Arbitrary Julia closures still cannot cross the ABI, but any g, f, μ, σ that
  * can be written as an expression of the quantities the hot path carries can.
- * NULL members are unused.  Only hdp_mlp_solve_* accepts USER kinds.                 */
+ * NULL members are unused.  hdp_mlp_solve_* takes them through hdp_mlp_cfg.user (all four
+ * kinds); hdp_sde_loop_*, hdp_mlt_sde_loop_* and hdp_em_ensemble_* take mu / sigma from
+ * hdp_set_user_exprs (their signatures mirror reference closures that have no such slot). */
 typedef struct hdp_user_exprs {
     const char* mu;
     const char* sigma;
@@ -328,6 +332,36 @@ int hdp_sde_loop_f32(hdp_handle h, const hdp_problem* prob, float* y0, float* y1
                      const hdp_sampler* mc, float* z, int K,
                      int normal_mode, unsigned mem_flags);
 
+/* User expressions for the K1 entry points (hdp_sde_loop_*, hdp_mlt_sde_loop_*,
+ * hdp_em_ensemble_*) when prob->mu_kind / sigma_kind is HDP_COEF_USER.  The strings are
+ * copied into the handle (the caller's pointers are not retained); NULL clears them.
+ * The kernels are built by NVRTC on first use and cached per handle and expression set.
+ * With a USER kind hdp_sde_loop_* requires `ts` (the reference passes t = ts[N+1-i] to
+ * μ and σ, src/DeepSplitting.jl:157-160). */
+int hdp_set_user_exprs(hdp_handle h, const hdp_user_exprs* user);
+
+/* ------------------------------------------------------------------ */
+/* K1e: plain Euler–Maruyama ensemble                 */
+/* replaces the pre-simulation stage of NNKolmogorov (src/NNKolmogorov.jl:81-112:
+ * `solve(EnsembleProblem(SDEProblem(μ, σ, xi[:,1], tspan), prob_func), EM(), ...;
+ * dt, trajectories, adaptive=false)`, only `sol.u[end]` kept) and of NNStopping
+ * (src/NNStopping.jl:90-99: the same with `saveat = dt`, `Array(sim)` kept).
+ * Step (StochasticDiffEq v7 `EM`, a dependency that is not vendored in the reference
+ * tree): dW = sqrt(dt)·ξ;  u = uprev + dt·μ(uprev,p,t_k) + σ(uprev,p,t_k)·dW, evaluated
+ * left to right, t_k = t0 + k·dt accumulated.  Diagonal noise, no reflection.
+ * x (in/out): d×B, column b = start point of trajectory b (NNKolmogorov: xi[:, b];
+ * NNStopping: prob.x repeated) → its final state.
+ * traj: nullable d×(nsteps+1)×B, `Array(sim)`'s layout, traj[:, 1, b] = start point.
+ * normals_inject: nullable d×B×nsteps standard normals ξ (parity mode); NULL =>
+ * Philox in registers (stream HDP_STREAM_SDE, ordinal = step, like hdp_sde_loop_*). */
+/* ------------------------------------------------------------------ */
+int hdp_em_ensemble_f64(hdp_handle h, const hdp_problem* prob, double* x, int B, int nsteps, double dt,
+                        double t0, double* traj, uint64_t seed, const double* normals_inject,
+                        unsigned mem_flags);
+int hdp_em_ensemble_f32(hdp_handle h, const hdp_problem* prob, float* x, int B, int nsteps, float dt,
+                        float t0, float* traj, uint64_t seed, const float* normals_inject,
+                        unsigned mem_flags);
+
 /* ------------------------------------------------------------------ */
 /* One Euler–Maruyama step of the MLP recursion, stand-alone              */
 /* replaces `_mlt_sde_loop!(x2, x, s, t, prob, neumann_bc)` (src/MLP.jl:406-421):
@@ -362,6 +396,9 @@ int hdp_mlp_solve_f32(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* 
  * touching a device: validation on a machine without a GPU.  is_f32: element type;
  * log (nullable) receives the compiler log.  Returns HDP_OK or HDP_ERR_BAD_ARG.          */
 int hdp_user_kinds_check(const hdp_problem* prob, const hdp_user_exprs* user, int is_f32,
+                         char* log, size_t log_cap);
+/* the same for the K1 entry points: compiles sde_loop! / EM-ensemble kernels with user mu / sigma */
+int hdp_user_coefs_check(const hdp_problem* prob, const hdp_user_exprs* user, int is_f32,
                          char* log, size_t log_cap);
 
 /* ------------------------------------------------------------------ */

@@ -65,7 +65,9 @@ void hdp_oracle_mlp_counts(int M, int L, int K, int nonlocal, int64_t out[5]);
                                       int parallel, REAL* u_out, int64_t* counts);                     \
     int hdp_oracle_sde_loop##SFX(const hdp_problem* pb, REAL* y0, REAL* y1, int B, int nsteps,         \
                                  REAL dt, const REAL* ts, const hdp_sampler* x0s, const REAL* x0_raw,  \
-                                 const REAL* dWall, int32_t* iters_per_step);
+                                 const REAL* dWall, int32_t* iters_per_step);                         \
+    int hdp_oracle_em_ensemble##SFX(const hdp_problem* pb, REAL* x, int B, int nsteps, REAL dt,        \
+                                    REAL t0, REAL* traj, const REAL* xi);
 
 HDP_ORACLE_DECL(double, _f64)
 HDP_ORACLE_DECL(float, _f32)

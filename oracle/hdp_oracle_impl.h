@@ -29,6 +29,7 @@
 static inline REAL FN(coef)(int kind, const double* p, REAL xi, int i, REAL t, int d, int which)
 {
     if (kind == HDP_COEF_LINEAR) return (REAL)p[0] * xi; /* test/MLP.jl:191-192: 0.02f0 * x */
+    if (kind == HDP_COEF_QUADRATIC) return (REAL)p[0] * (xi * xi); /* test/DeepSplitting.jl:355: sigma * x .^ 2 */
     if (kind == HDP_COEF_USER) {                        /* user μ(x,p,t)[i] / σ(x,p,t)[i] */
         hdp_oracle_user_coef fn = which ? hdp_oracle_user.sigma : hdp_oracle_user.mu;
         return (REAL)fn((double)xi, i, (double)t, d, p);
@@ -650,7 +651,6 @@ int FN(hdp_oracle_sde_loop)(const hdp_problem* pb, REAL* y0, REAL* y1, int B, in
 {
     const int d = pb->d;
     const size_t n_el = (size_t)d * (size_t)B;
-    (void)ts; /* supported kinds are time-independent */
     if (x0s && x0s->kind != HDP_SAMPLER_NONE) {
         if (!x0_raw) return HDP_ERR_BAD_ARG;
         /* x0_sample!(y1): 1-argument form (:155) — never shifted */
@@ -674,9 +674,10 @@ int FN(hdp_oracle_sde_loop)(const hdp_problem* pb, REAL* y0, REAL* y1, int B, in
     for (int st = 0; st < nsteps; ++st) {                       /* :156 */
         const REAL* dW = dWall + (size_t)st * n_el;             /* :158 */
         memcpy(y0, y1, sizeof(REAL) * n_el);                    /* :159 y0 .= y1 */
+        const REAL t = ts ? ts[st] : (REAL)0;                   /* :157 t = ts[N + 1 - i] */
         for (size_t q = 0; q < n_el; ++q) {
-            REAL mu = FN(coef)(pb->mu_kind, pb->mu_p, y0[q], (int)(q % (size_t)d), (REAL)0, d, 0);
-            REAL sg = FN(coef)(pb->sigma_kind, pb->sigma_p, y0[q], (int)(q % (size_t)d), (REAL)0, d, 1);
+            REAL mu = FN(coef)(pb->mu_kind, pb->mu_p, y0[q], (int)(q % (size_t)d), t, d, 0);
+            REAL sg = FN(coef)(pb->sigma_kind, pb->sigma_p, y0[q], (int)(q % (size_t)d), t, d, 1);
             /* :160 y1 .= y0 .+ μ .* dt .+ σ .* sqrt(dt) .* dW   →  (y0 + μ*dt) + ((σ*sqrt(dt))*dW) */
             y1[q] = (y0[q] + mu * dt) + ((sg * sq) * dW[q]);
         }
@@ -691,6 +692,46 @@ int FN(hdp_oracle_sde_loop)(const hdp_problem* pb, REAL* y0, REAL* y1, int B, in
     free(lo);
     free(tmp);
     return rc;
+}
+
+/* ---------------------------------------------------------------- */
+/* Plain Euler–Maruyama ensemble: the pre-simulation stage of          */
+/* NNKolmogorov (src/NNKolmogorov.jl:81-112) and NNStopping            */
+/* (src/NNStopping.jl:90-99):                                          */
+/*   solve(EnsembleProblem(SDEProblem(μ, σ, x0, tspan)), EM();         */
+/*         dt, trajectories, adaptive = false [, saveat = dt])         */
+/* The step is StochasticDiffEq.jl's `EM` (Project.toml compat "7";    */
+/* third-party, not vendored under /root/reference, so its published   */
+/* algorithm is restated): ΔW = sqrt(dt)·ξ (DiffEqNoiseProcess         */
+/* WHITE_NOISE_DIST), u = uprev + dt·f(uprev,p,t) + g(uprev,p,t)·ΔW    */
+/* for diagonal noise, evaluated left to right; t advances by dt.      */
+/* x: d×B start → final states; traj (nullable): d×(nsteps+1)×B as     */
+/* Array(sim); xi: d×B×nsteps standard normals.                        */
+/* ---------------------------------------------------------------- */
+int FN(hdp_oracle_em_ensemble)(const hdp_problem* pb, REAL* x, int B, int nsteps, REAL dt, REAL t0,
+                               REAL* traj, const REAL* xi)
+{
+    const int d = pb->d;
+    const size_t n_el = (size_t)d * (size_t)B;
+    REAL sq = sizeof(REAL) == sizeof(float) ? (REAL)sqrtf((float)dt) : (REAL)sqrt((double)dt);
+    for (int b = 0; b < B; ++b) {
+        REAL* u = x + (size_t)b * d;
+        REAL* tr = traj ? traj + (size_t)b * d * ((size_t)nsteps + 1) : NULL;
+        if (tr) memcpy(tr, u, sizeof(REAL) * (size_t)d);
+        REAL t = t0;
+        for (int st = 0; st < nsteps; ++st) {
+            const REAL* z = xi + (size_t)st * n_el + (size_t)b * d;
+            for (int i = 0; i < d; ++i) {
+                REAL dW = sq * z[i];
+                REAL mu = FN(coef)(pb->mu_kind, pb->mu_p, u[i], i, t, d, 0);
+                REAL sg = FN(coef)(pb->sigma_kind, pb->sigma_p, u[i], i, t, d, 1);
+                u[i] = (u[i] + dt * mu) + sg * dW;
+            }
+            t = t + dt;
+            if (tr) memcpy(tr + (size_t)(st + 1) * d, u, sizeof(REAL) * (size_t)d);
+        }
+    }
+    return HDP_OK;
 }
 
 #undef FN

@@ -259,7 +259,24 @@ def mlt_sde_loop(pb_struct, x, s, t, normals):
     return out
 
 
-def sde_loop(pb_struct, y1, nsteps, dt, dWall, x0_sampler_struct=None, x0_raw=None):
+def em_ensemble(pb_struct, x0, nsteps, dt, t0, xi, saveat=False):
+    """EM ensemble (src/NNKolmogorov.jl:81-112, src/NNStopping.jl:90-99; StochasticDiffEq's EM step).
+    x0: d×B; xi: d×B×nsteps standard normals.  Returns (x_end d×B, traj d×(nsteps+1)×B or None)."""
+    x = np.array(x0, order="F", copy=True)
+    dtp = x.dtype
+    d, B = x.shape
+    z = np.asfortranarray(xi, dtype=dtp)
+    traj = np.empty((d, nsteps + 1, B), dtype=dtp, order="F") if saveat else None
+    real = C.c_double if dtp == np.float64 else C.c_float
+    fn = getattr(lib(), "hdp_oracle_em_ensemble" + _sfx(dtp))
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, real, real, C.c_void_p, C.c_void_p]
+    rc = fn(C.byref(pb_struct), _p(x), B, nsteps, real(dt), real(t0), _p(traj), _p(z))
+    if rc != 0:
+        raise ValueError(f"oracle em_ensemble rc={rc}")
+    return x, traj
+
+
+def sde_loop(pb_struct, y1, nsteps, dt, dWall, x0_sampler_struct=None, x0_raw=None, ts=None):
     """sde_loop!(y0, y1, dWall) (src/DeepSplitting.jl:153-166). Returns (y0, y1, iters_per_step)."""
     y1 = np.array(y1, order="F", copy=True)
     dtp = y1.dtype
@@ -269,8 +286,9 @@ def sde_loop(pb_struct, y1, nsteps, dt, dWall, x0_sampler_struct=None, x0_raw=No
     its = np.zeros(max(nsteps, 1), dtype=np.int32)
     xr = None if x0_raw is None else np.asfortranarray(x0_raw, dtype=dtp)
     real = C.c_double if dtp == np.float64 else C.c_float
+    tsa = None if ts is None else np.ascontiguousarray(ts, dtype=dtp)
     rc = getattr(lib(), "hdp_oracle_sde_loop" + _sfx(dtp))(
-        C.byref(pb_struct), _p(y0), _p(y1), B, nsteps, real(dt), None,
+        C.byref(pb_struct), _p(y0), _p(y1), B, nsteps, real(dt), _p(tsa),
         C.byref(x0_sampler_struct) if x0_sampler_struct is not None else None, _p(xr), _p(dW), _p(its))
     if rc != 0:
         raise ValueError(f"oracle sde_loop rc={rc}")
