@@ -50,6 +50,10 @@ end
 # μ, σ (test/MLP.jl:24-25, 191-192)
 struct ConstCoef{T}; c::T; end;   (k::ConstCoef)(x, p, t) = k.c
 struct LinearCoef{T}; c::T; end;  (k::LinearCoef)(x, p, t) = k.c * x
+struct QuadraticCoef{T}; c::T; end;  (k::QuadraticCoef)(x, p, t) = k.c * x .^ 2   # test/DeepSplitting.jl:355
+# any other μ/σ: a CUDA-C expression over x, i, t, d, p[0..1] (compiled by NVRTC on first use) next to
+# the Julia closure that the host-side code paths keep calling
+struct UserCoef{F}; expr::String; p::NTuple{2, Float64}; fn::F; end;  (k::UserCoef)(x, p, t) = k.fn(x, p, t)
 # g (test/MLP.jl:28,118,146,174,199,265)
 struct SumSq{T}; c::T; end;            (k::SumSq)(x) = sum(x .^ 2) .+ k.c
 struct InvSumSq{T}; a::T; b::T; end;   (k::InvSumSq)(x) = 1 ./ (k.a .+ k.b * sum(x .^ 2))
@@ -80,6 +84,7 @@ function (k::FNLReplicatorMutator)(y, z, vy, vz, ∇vy, ∇vz, p, t)
 end
 
 kind_of(k::ConstCoef) = (Int32(0), (Float64(k.c), 0.0));  kind_of(k::LinearCoef) = (Int32(1), (Float64(k.c), 0.0))
+kind_of(k::UserCoef) = (Int32(2), k.p);                    kind_of(k::QuadraticCoef) = (Int32(3), (Float64(k.c), 0.0))
 gkind(k::SumSq) = (Int32(0), (Float64(k.c), 0.0, 0.0, 0.0))
 gkind(k::InvSumSq) = (Int32(1), (Float64(k.a), Float64(k.b), 0.0, 0.0))
 gkind(k::ExpSumSq) = (Int32(2), (Float64(k.c), 0.0, 0.0, 0.0))
@@ -92,7 +97,7 @@ fkind(k::FDefaultRisk) = (Int32(3), _p8(k.δ, k.R, k.vh, k.vl, k.γh, k.γl))
 fkind(::FNLAllenCahnDiff) = (Int32(16), _p8()); fkind(::FNLFisher) = (Int32(17), _p8())
 fkind(k::FNLReplicatorMutator) = (Int32(18), _p8(k.σs))
 
-const B200Coef = Union{ConstCoef, LinearCoef}
+const B200Coef = Union{ConstCoef, LinearCoef, QuadraticCoef, UserCoef}
 const B200G = Union{SumSq, InvSumSq, ExpSumSq, MinCoord, GaussDensity}
 const B200F = Union{FZero, FLinear, FAllenCahn, FFisherKPP, FDefaultRisk, FNLAllenCahnDiff, FNLFisher, FNLReplicatorMutator}
 
@@ -129,9 +134,9 @@ function sampler_desc(s::UniformSampling, keep)
 end
 sampler_desc(s::NormalSampling, keep) = HdpSampler(2, s.shifted, 1, 0, 0.0, 0.0, Float64(s.σ), C_NULL, C_NULL)
 
-function problem_desc(prob, f, bc, keep)
+function problem_desc(prob, f, bc, keep; g = prob.g)
     μk, μp = kind_of(prob.μ); σk, σp = kind_of(prob.σ)
-    gk, gp = gkind(prob.g);   fk, fp = fkind(f)
+    gk, gp = gkind(g);        fk, fp = fkind(f)
     d = Int32(length(prob.x))
     if isnothing(bc)
         has, scal, lo_s, hi_s, lo, hi = 0, 1, 0.0, 0.0, C_NULL, C_NULL
@@ -235,5 +240,38 @@ function sde_loop_b200!(y0::Array{T}, y1::Array{T}, nsteps, dt, prob, neumann_bc
     nothing
 end
 # CuArray arguments: same calls with `mem_flags = HDP_MEM_DEVICE (1)` and `pointer(::CuArray)`.
+
+# μ/σ expressions of UserCoef kinds for the K1 entry points (hdp_set_user_exprs copies the strings);
+# `ts` must then be passed to hdp_sde_loop_* (t = ts[N+1-i], src/DeepSplitting.jl:157).
+function set_user_coefs!(h::Handle, prob)
+    μ = prob.μ isa UserCoef ? prob.μ.expr : nothing;  σ = prob.σ isa UserCoef ? prob.σ.expr : nothing
+    if isnothing(μ) && isnothing(σ)
+        return check(h, ccall((:hdp_set_user_exprs, libhdp), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), h.ptr, C_NULL))
+    end
+    GC.@preserve μ σ begin
+        ue = HdpUserExprs(isnothing(μ) ? C_NULL : pointer(μ), isnothing(σ) ? C_NULL : pointer(σ), C_NULL, C_NULL)
+        check(h, ccall((:hdp_set_user_exprs, libhdp), Cint, (Ptr{Cvoid}, Ref{HdpUserExprs}), h.ptr, ue))
+    end
+end
+
+# ------------------------------------------------------------------ EM ensembles (src/NNKolmogorov.jl:81-112, src/NNStopping.jl:90-99)
+# Stands in for `solve(EnsembleProblem(SDEProblem(μ, σ, x0, tspan)[, prob_func]), EM(); dt, trajectories,
+# adaptive = false[, saveat = dt])`: x is d×trajectories (start points in, final states out); with
+# `saveat = true` returns `Array(sim)` (d × N+1 × trajectories), else x.
+function em_ensemble_b200!(x::Matrix{T}, prob, dt; saveat = false) where {T <: Union{Float32, Float64}}
+    keep = Any[]
+    pb = problem_desc(prob, FZero(), nothing, keep; g = SumSq(zero(T)))
+    N = Int(round((prob.tspan[2] - prob.tspan[1]) / dt)); d, B = size(x)
+    traj = saveat ? Array{T}(undef, d, N + 1, B) : nothing
+    h = handle(); set_user_coefs!(h, prob)
+    sym = T === Float64 ? :hdp_em_ensemble_f64 : :hdp_em_ensemble_f32
+    GC.@preserve keep begin
+        rc = ccall((sym, libhdp), Cint,
+                   (Ptr{Cvoid}, Ref{HdpProblem}, Ptr{T}, Cint, Cint, T, T, Ptr{T}, UInt64, Ptr{T}, Cuint),
+                   h.ptr, pb, x, B, N, T(dt), T(prob.tspan[1]), saveat ? pointer(traj) : C_NULL, rand(UInt64), C_NULL, 0)
+    end
+    check(h, rc)
+    saveat ? traj : x
+end
 
 end # module
