@@ -222,6 +222,7 @@ def run_ours(args, rank, world, local_rank):
         try:
             extra = bench_sde_loop(torch, H, h, local_rank)       # configs[2] (C3)
             extra.update(bench_other_configs(H, h))                # configs[0], [3], [4]
+            extra.update(bench_em_ensemble(torch, H, h))           # plain EM ensembles
             p32 = h.measure_pipe_peak(32)
             p64 = h.measure_pipe_peak(64)
             for k, v in extra.items():
@@ -232,6 +233,12 @@ def run_ours(args, rank, world, local_rank):
                     v["roofline"] = {"bound": "fp32", "achieved": cs * 11 / 1e12, "peak": p32 / 1e12,
                                      "unit": "Tlane-instr/s", "frac": cs * 11 / p32,
                                      "frac_with_philox_int32": cs * 31 / p32,
+                                     "hbm_frac_of_6542GBs": v["hbm_gbs"] / 6542.1}
+                if k.startswith("em_ensemble_f64"):
+                    cs = v["coord_steps_per_sec"]
+                    # the 8(d) budget without the 3 instructions of the reflection test + fold
+                    v["roofline"] = {"bound": "fp64", "achieved": cs * (I64_PER_COORD_STEP - 3) / 1e12, "peak": p64 / 1e12,
+                                     "unit": "Tlane-instr/s", "frac": cs * (I64_PER_COORD_STEP - 3) / p64,
                                      "hbm_frac_of_6542GBs": v["hbm_gbs"] / 6542.1}
                 if k.startswith("sde_loop_f64"):
                     cs = v["coord_steps_per_sec"]
@@ -333,6 +340,37 @@ def bench_sde_loop(torch, H, h, local_rank):
             out[f"sde_loop_{tag}_B{B}"] = {"path_steps_per_sec": ps, "coord_steps_per_sec": ps * d, "kernel_ms": best,
                                            "hbm_bytes": 3 * d * B * esz, "hbm_gbs": 3 * d * B * esz / (best * 1e-3) / 1e9}
             del y0, y1
+    return out
+
+
+def bench_em_ensemble(torch, H, h):
+    """the EM ensemble NNKolmogorov / NNStopping pre-simulate with (no reflection), fp64, d=100,
+    N=10, 2^18 trajectories: final states only, and with every step saved (`saveat = dt`, Array(sim) layout)."""
+    import ctypes as C
+    out = {}
+    d, N, B = 100, 10, 1 << 18
+    prob = H.ParabolicPDEProblem(H.LinearCoef(0.02), H.LinearCoef(0.2), np.zeros(d), (0.0, 1.0), g=H.SumSq(), f=H.FZero())
+    pb, _k = prob.to_c()
+    x = torch.empty(d * B, dtype=torch.float64, device="cuda")
+    traj = torch.empty(d * B * (N + 1), dtype=torch.float64, device="cuda")
+    flags = H.capi.HDP_MEM_DEVICE | H.capi.HDP_ASYNC
+    for tag, tp in (("final", None), ("saveat", C.c_void_p(traj.data_ptr()))):
+        best = None
+        for r in range(13):
+            x.fill_(100.0)
+            torch.cuda.synchronize()
+            rc = h.lib.hdp_em_ensemble_f64(h.h, C.byref(pb), C.c_void_p(x.data_ptr()), B, N, C.c_double(0.1), C.c_double(0.0),
+                                           tp, 11 + r, None, flags)
+            H.capi.check(h.h, rc)
+            ms = h.last_device_ms()
+            if r >= 3:
+                best = ms if best is None else min(best, ms)
+        h.sync()
+        ps = B * N / (best * 1e-3)
+        nbytes = d * B * 8 * (2 + ((N + 1) if tp is not None else 0))
+        out[f"em_ensemble_f64_B{B}_{tag}"] = {"path_steps_per_sec": ps, "coord_steps_per_sec": ps * d, "kernel_ms": best,
+                                             "hbm_bytes": nbytes, "hbm_gbs": nbytes / (best * 1e-3) / 1e9}
+    del x, traj
     return out
 
 

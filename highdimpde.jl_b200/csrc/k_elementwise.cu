@@ -235,7 +235,8 @@ int get_sde_user_module(hdp_context* h, const hdp_problem* prob, bool f32, SdeUs
     hdp_user_exprs u{};
     u.mu = h->has_user_mu ? h->user_mu.c_str() : nullptr;
     u.sigma = h->has_user_sigma ? h->user_sigma.c_str() : nullptr;
-    std::string key = f32 ? "f32/" : "f64/";
+    // the module is specialised to the pair of kinds as well as to the expressions
+    std::string key = (f32 ? "f32/" : "f64/") + std::to_string(prob->mu_kind) + "/" + std::to_string(prob->sigma_kind) + "/";
     key += (prob->mu_kind == HDP_COEF_USER && u.mu) ? u.mu : "-";
     key += "\x1f";
     key += (prob->sigma_kind == HDP_COEF_USER && u.sigma) ? u.sigma : "-";
@@ -442,11 +443,12 @@ int em_ensemble_impl(hdp_handle h, const hdp_problem* prob, T* x, int B, int nst
     if (um) {
         size_t n_el_ = n_el;
         u64 seed_ = seed;
-        void* args[] = {&pb, &dx, &n_el_, &nsteps, &dt, &t0, &dtraj, &seed_, &ddw};
+        int zero = 0;
+        void* args[] = {&pb, &dx, &n_el_, &nsteps, &dt, &t0, &dtraj, &seed_, &ddw, &zero};
         HDP_CUDA(h, cudaLaunchKernel((const void*)um->ens[al ? 1 : 0][ddw ? 1 : 0][dtraj ? 1 : 0], dim3(grid), dim3(threads), args, 0, h->stream));
     } else {
 #define LAUNCH_E(AL, INJ, TR) \
-    em_ensemble_kernel<T, AL, INJ, TR><<<grid, threads, 0, h->stream>>>(pb, dx, n_el, nsteps, dt, t0, dtraj, seed, ddw)
+    em_ensemble_kernel<T, AL, INJ, TR><<<grid, threads, 0, h->stream>>>(pb, dx, n_el, nsteps, dt, t0, dtraj, seed, ddw, 0)
 #define LAUNCH_E2(AL, INJ)              \
     do {                                \
         if (dtraj) LAUNCH_E(AL, INJ, true); \

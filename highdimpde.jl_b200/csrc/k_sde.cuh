@@ -186,55 +186,96 @@ sde_loop_kernel(DevProblem<T> pb, T* __restrict__ y0, T* __restrict__ y1, size_t
 // (uprev + dt μ) + σ (sqrt(dt) ξ) — a third association, next to :160 and src/MLP.jl:417.
 // x (in/out): d×B start → final states; traj (TRAJ): d×(nsteps+1)×B as `Array(sim)` lays it out.
 // Normals: dW_inject[q + n_el*step] (INJECT) or draw(SDE, ordinal = step, i = q) like sde_loop!.
+template <int N> struct KTag { static constexpr int value = N; };
+// μ or σ of a kind known at compile time (coef_any without the switch in the step loop)
+template <int KIND, typename T> __device__ __forceinline__ T coef_k(const T* p, T x, int i, T t, int d, int which)
+{
+    if constexpr (KIND == HDP_COEF_LINEAR) return mul_rn(p[0], x);
+    else if constexpr (KIND == HDP_COEF_QUADRATIC) return mul_rn(p[0], mul_rn(x, x));
+    else if constexpr (KIND == HDP_COEF_USER) return which ? user_sigma<T>(x, i, t, d, p) : user_mu<T>(x, i, t, d, p);
+    else return p[0];
+}
+// calls fn(KTag<kind>) for a run-time kind (once per thread, outside the step loop).  The NVRTC
+// build knows both kinds when it compiles (HDP_FIXED_MU_KIND / HDP_FIXED_SIGMA_KIND): one copy.
+template <int WHICH, typename F> __device__ __forceinline__ void with_kind(int kind, F&& fn)
+{
+#if defined(HDP_FIXED_MU_KIND) && defined(HDP_FIXED_SIGMA_KIND)
+    (void)kind;
+    if constexpr (WHICH) fn(KTag<HDP_FIXED_SIGMA_KIND>{});
+    else fn(KTag<HDP_FIXED_MU_KIND>{});
+#else
+    switch (kind) {
+    case HDP_COEF_LINEAR: fn(KTag<HDP_COEF_LINEAR>{}); break;
+    case HDP_COEF_QUADRATIC: fn(KTag<HDP_COEF_QUADRATIC>{}); break;
+    case HDP_COEF_USER: fn(KTag<HDP_COEF_USER>{}); break;
+    default: fn(KTag<HDP_COEF_CONST>{}); break;
+    }
+#endif
+}
+
 template <typename T, bool ALIGNED, bool INJECT, bool TRAJ>
 __global__ void __launch_bounds__(128)
 em_ensemble_kernel(DevProblem<T> pb, T* __restrict__ x, size_t n_el, int nsteps, T dt, T t0, T* __restrict__ traj,
-                   u64 seed, const T* __restrict__ dW)
+                   u64 seed, const T* __restrict__ dW, int zero)
 {
     constexpr int VEC = Tr<T>::VEC;
     if constexpr (sizeof(T) == 8) tables_init();
     const int d = pb.d;
     const size_t nv = (n_el + VEC - 1) / VEC;
     const T sq = sqrt_rn(dt);
-    const DrawK<T> dk = draw_k_init<T>(0);
-    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (size_t)gridDim.x * blockDim.x) {
-        const size_t q0 = v * VEC;
-        const int i0 = n_el <= 0xffffffffull ? (int)((uint32_t)q0 % (uint32_t)d) : (int)(q0 % (size_t)d);
-        Vec<T> cur = load_el<T, ALIGNED>(x, q0, n_el);
-        // element q = i + d b of the state sits at q + d (k + nsteps b) of the trajectory array
-        auto save = [&](int k) {
-            if constexpr (ALIGNED) { // d % VEC == 0: the VEC elements share their column
-                const size_t b = q0 / (size_t)d;
-                stv<T>(traj + q0 + (size_t)d * ((size_t)k + (size_t)nsteps * b), cur);
-            } else {
+    const DrawK<T> dk = draw_k_init<T>(zero);
+    // one copy of the step loop per (μ kind, σ kind): nothing but the arithmetic is left inside
+    with_kind<0>(pb.mu_kind, [&](auto mu_tag) {
+        with_kind<1>(pb.sigma_kind, [&](auto sg_tag) {
+            constexpr int MU = decltype(mu_tag)::value, SG = decltype(sg_tag)::value;
+            for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (size_t)gridDim.x * blockDim.x) {
+                const size_t q0 = v * VEC;
+                const int i0 = n_el <= 0xffffffffull ? (int)((uint32_t)q0 % (uint32_t)d) : (int)(q0 % (size_t)d);
+                Vec<T> cur = load_el<T, ALIGNED>(x, q0, n_el);
+                // element q = i + d b of the state sits at q + d (k + nsteps b) of the trajectory array
+                // (ALIGNED: d % VEC == 0, so the VEC elements share their column)
+                T* tp[ALIGNED ? 1 : VEC] = {};
+                if constexpr (TRAJ) {
 #pragma unroll
-                for (int e = 0; e < VEC; ++e)
-                    if (q0 + e < n_el) {
-                        const size_t b = (q0 + e) / (size_t)d;
-                        traj[q0 + e + (size_t)d * ((size_t)k + (size_t)nsteps * b)] = cur.v[e];
+                    for (int e = 0; e < (ALIGNED ? 1 : VEC); ++e) {
+                        const size_t q = q0 + e < n_el ? q0 + e : q0;
+                        tp[e] = traj + q + (size_t)d * (size_t)nsteps * (q / (size_t)d);
                     }
-            }
-        };
-        if constexpr (TRAJ) save(0);
-        T t = t0;
-        for (int st = 0; st < nsteps; ++st) {
-            Vec<T> xi;
-            if constexpr (INJECT) xi = load_el<T, ALIGNED>(dW + (size_t)st * n_el, q0, n_el);
-            else xi = draw_vec<T>(seed, HDP_STREAM_SDE, (u64)st, (u64)v, true, dk);
-            int i = i0;
+                }
+                auto save = [&]() {
+                    if constexpr (ALIGNED) {
+                        stv<T>(tp[0], cur);
+                        tp[0] += d;
+                    } else {
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) {
-                const T xe = cur.v[e];
-                const T mu = coef_any<T>(pb.mu_kind, pb.mu_p, xe, i, t, d, 0);
-                const T sg = coef_any<T>(pb.sigma_kind, pb.sigma_p, xe, i, t, d, 1);
-                cur.v[e] = add_rn(add_rn(xe, mul_rn(dt, mu)), mul_rn(sg, mul_rn(sq, xi.v[e])));
-                if (++i == d) i = 0;
+                        for (int e = 0; e < VEC; ++e) {
+                            if (q0 + e < n_el) *tp[e] = cur.v[e];
+                            tp[e] += d;
+                        }
+                    }
+                };
+                if constexpr (TRAJ) save();
+                T t = t0;
+                for (int st = 0; st < nsteps; ++st) {
+                    Vec<T> xi;
+                    if constexpr (INJECT) xi = load_el<T, ALIGNED>(dW + (size_t)st * n_el, q0, n_el);
+                    else xi = draw_vec<T>(seed, HDP_STREAM_SDE, (u64)st, (u64)v, true, dk);
+                    int i = i0;
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) {
+                        const T xe = cur.v[e];
+                        const T mu = coef_k<MU, T>(pb.mu_p, xe, i, t, d, 0);
+                        const T sg = coef_k<SG, T>(pb.sigma_p, xe, i, t, d, 1);
+                        cur.v[e] = add_rn(add_rn(xe, mul_rn(dt, mu)), mul_rn(sg, mul_rn(sq, xi.v[e])));
+                        if (++i == d) i = 0;
+                    }
+                    t = add_rn(t, dt);
+                    if constexpr (TRAJ) save();
+                }
+                store_el<T, ALIGNED>(x, q0, n_el, cur);
             }
-            t = add_rn(t, dt);
-            if constexpr (TRAJ) save(st + 1);
-        }
-        store_el<T, ALIGNED>(x, q0, n_el, cur);
-    }
+        });
+    });
 }
 
 } // namespace hdp

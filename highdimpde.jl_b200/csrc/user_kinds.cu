@@ -176,6 +176,8 @@ int user_compile_sde(const hdp_problem* p, const hdp_user_exprs* u, bool f32, Sd
            "typedef long long int64_t; typedef unsigned long long uint64_t; typedef unsigned long uintptr_t;\n";
     for (auto& n : needs)
         if (n.on) src += std::string("#define ") + n.macro + " (" + n.e + ")\n";
+    src += "#define HDP_FIXED_MU_KIND " + std::to_string(p->mu_kind) + "\n#define HDP_FIXED_SIGMA_KIND " +
+           std::to_string(p->sigma_kind) + "\n";
     src += "#include \"k_sde.cuh\"\n";
     const char* tf[2] = {"false", "true"};
     std::vector<std::string> exprs;

@@ -1,5 +1,5 @@
 """Small fixed workloads for ncu captures (see profiles/README.md).
-usage: python profiles/prof_workload.py mlp [n_solves] | sde [B] | c4 | c5"""
+usage: python profiles/prof_workload.py mlp [n_solves] | sde [B] | ens [B] | c4 | c5"""
 import ctypes as C
 import os
 import sys
@@ -37,6 +37,21 @@ elif what == "c5":
     for it in range(2):
         u, st = H._ml_picard_batch(prob, H.MLP(M=4, L=5, K=10), n_solves=n, seed=5 + it, handle=h)
         print(it, u.mean(), st)
+elif what == "ens":
+    import torch
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else (1 << 18)
+    d, N = 100, 10
+    prob = H.ParabolicPDEProblem(H.LinearCoef(0.02), H.LinearCoef(0.2), np.zeros(d), (0.0, 1.0), g=H.SumSq(), f=H.FZero())
+    pb, _k = prob.to_c()
+    x = torch.empty(d * B, dtype=torch.float64, device="cuda")
+    traj = torch.empty(d * B * (N + 1), dtype=torch.float64, device="cuda")
+    for it in range(3):
+        x.fill_(100.0)
+        torch.cuda.synchronize()
+        rc = h.lib.hdp_em_ensemble_f64(h.h, C.byref(pb), C.c_void_p(x.data_ptr()), B, N, C.c_double(0.1), C.c_double(0.0),
+                                       C.c_void_p(traj.data_ptr()), 7 + it, None, H.capi.HDP_MEM_DEVICE | H.capi.HDP_ASYNC)
+        H.capi.check(h.h, rc)
+        print(it, h.last_device_ms(), "ms")
 else:
     import torch
     B = int(sys.argv[2]) if len(sys.argv) > 2 else (1 << 20)
