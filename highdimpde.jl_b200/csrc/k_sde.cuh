@@ -47,6 +47,33 @@ __device__ __forceinline__ T sample_one(const DevSampler<T>& sm, T raw, int i, T
 }
 
 
+template <int N> struct KTag { static constexpr int value = N; };
+// μ or σ of a kind known at compile time (coef_any without the switch in the step loop)
+template <int KIND, typename T> __device__ __forceinline__ T coef_k(const T* p, T x, int i, T t, int d, int which)
+{
+    if constexpr (KIND == HDP_COEF_LINEAR) return mul_rn(p[0], x);
+    else if constexpr (KIND == HDP_COEF_QUADRATIC) return mul_rn(p[0], mul_rn(x, x));
+    else if constexpr (KIND == HDP_COEF_USER) return which ? user_sigma<T>(x, i, t, d, p) : user_mu<T>(x, i, t, d, p);
+    else return p[0];
+}
+// calls fn(KTag<kind>) for a run-time kind (once per thread, outside the step loop).  The NVRTC
+// build knows both kinds when it compiles (HDP_FIXED_MU_KIND / HDP_FIXED_SIGMA_KIND): one copy.
+template <int WHICH, typename F> __device__ __forceinline__ void with_kind(int kind, F&& fn)
+{
+#if defined(HDP_FIXED_MU_KIND) && defined(HDP_FIXED_SIGMA_KIND)
+    (void)kind;
+    if constexpr (WHICH) fn(KTag<HDP_FIXED_SIGMA_KIND>{});
+    else fn(KTag<HDP_FIXED_MU_KIND>{});
+#else
+    switch (kind) {
+    case HDP_COEF_LINEAR: fn(KTag<HDP_COEF_LINEAR>{}); break;
+    case HDP_COEF_QUADRATIC: fn(KTag<HDP_COEF_QUADRATIC>{}); break;
+    case HDP_COEF_USER: fn(KTag<HDP_COEF_USER>{}); break;
+    default: fn(KTag<HDP_COEF_CONST>{}); break;
+    }
+#endif
+}
+
 // ------------------------------ K1 -----------------------------------
 // N reflected EM steps per element; normals from dWall (INJECT) or Philox in
 // registers.  draw addressing: dWall[q + n_el*step] == draw(SDE, ordinal=step, i=q).
@@ -76,7 +103,7 @@ sde_loop_kernel(DevProblem<T> pb, T* __restrict__ y0, T* __restrict__ y1, size_t
     const T mudt_c = mul_rn(pb.mu_c, dt), sgsq_c = mul_rn(pb.sigma_c, sq);
     bool bad = false;
     int nb_total = 0;
-    const DrawK<T> dk = draw_k_init<T>(BC != K1_GENERIC ? zero : 0);
+    const DrawK<T> dk = draw_k_init<T>(zero);
     for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (size_t)gridDim.x * blockDim.x) {
         const size_t q0 = v * VEC;
         const int i0 = n_el <= 0xffffffffull ? (int)((uint32_t)q0 % (uint32_t)d) : (int)(q0 % (size_t)d);
@@ -124,33 +151,42 @@ sde_loop_kernel(DevProblem<T> pb, T* __restrict__ y0, T* __restrict__ y1, size_t
                 }
             }
         }
-        for (; st < nsteps; ++st) {
-            Vec<T> xi;
-            if constexpr (INJECT) xi = load_el<T, ALIGNED>(dW + (size_t)st * n_el, q0, n_el);
-            else xi = draw_vec<T>(seed, HDP_STREAM_SDE, (u64)st, (u64)v, true, dk);
-            prev = cur; // y0 .= y1 (:159)
-            if constexpr (BC == K1_GENERIC) {
-                // μ(y0, p, t), σ(y0, p, t) with t = ts[N + 1 - i] (:157), or the end time of the one
-                // `_mlt_sde_loop!` step (src/MLP.jl:417)
-                const T t = ts ? ts[st] : (T)0;
-                int i = i0;
+        // the remaining steps (all of them in the generic mode: one copy of the loop per pair of
+        // coefficient kinds, so that no kind is decided inside it)
+        auto steps = [&](auto mu_tag, auto sg_tag) {
+            [[maybe_unused]] constexpr int MU = decltype(mu_tag)::value;
+            [[maybe_unused]] constexpr int SG = decltype(sg_tag)::value;
+            for (; st < nsteps; ++st) {
+                Vec<T> xi;
+                if constexpr (INJECT) xi = load_el<T, ALIGNED>(dW + (size_t)st * n_el, q0, n_el);
+                else xi = draw_vec<T>(seed, HDP_STREAM_SDE, (u64)st, (u64)v, true, dk);
+                prev = cur; // y0 .= y1 (:159)
+                if constexpr (BC == K1_GENERIC) {
+                    // μ(y0, p, t), σ(y0, p, t) with t = ts[N + 1 - i] (:157), or the end time of the one
+                    // `_mlt_sde_loop!` step (src/MLP.jl:417)
+                    const T t = ts ? ts[st] : (T)0;
+                    int i = i0;
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) {
-                    const T x = prev.v[e];
-                    const T mudt = mul_rn(coef_any<T>(pb.mu_kind, pb.mu_p, x, i, t, d, 0), dt);
-                    const T sgsq = mul_rn(coef_any<T>(pb.sigma_kind, pb.sigma_p, x, i, t, d, 1), sq);
-                    if (++i == d) i = 0;
-                    if (mlp_assoc) cur.v[e] = add_rn(x, add_rn(mudt, mul_rn(sgsq, xi.v[e]))); // src/MLP.jl:417
-                    else cur.v[e] = add_rn(add_rn(x, mudt), mul_rn(sgsq, xi.v[e])); // :160 (y0 + μ*dt) + (σ*sq)*dW
+                    for (int e = 0; e < VEC; ++e) {
+                        const T x = prev.v[e];
+                        const T mudt = mul_rn(coef_k<MU, T>(pb.mu_p, x, i, t, d, 0), dt);
+                        const T sgsq = mul_rn(coef_k<SG, T>(pb.sigma_p, x, i, t, d, 1), sq);
+                        if (++i == d) i = 0;
+                        if (mlp_assoc) cur.v[e] = add_rn(x, add_rn(mudt, mul_rn(sgsq, xi.v[e]))); // src/MLP.jl:417
+                        else cur.v[e] = add_rn(add_rn(x, mudt), mul_rn(sgsq, xi.v[e])); // :160 (y0 + μ*dt) + (σ*sq)*dW
+                    }
+                    if (has_bc) reflect_vec<T, 1, false>(cur, lo, hi, 0u, nb_total); // :161-163
+                } else {
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e)
+                        cur.v[e] = add_rn(add_rn(prev.v[e], mudt_c), mul_rn(sgsq_c, xi.v[e])); // :160
+                    if constexpr (BC == K1_SYM) reflect_vec_sym<T, false>(cur, pb.hi_s, nb_total); // :161-163
                 }
-                if (has_bc) reflect_vec<T, 1, false>(cur, lo, hi, 0u, nb_total); // :161-163
-            } else {
-#pragma unroll
-                for (int e = 0; e < VEC; ++e)
-                    cur.v[e] = add_rn(add_rn(prev.v[e], mudt_c), mul_rn(sgsq_c, xi.v[e])); // :160
-                if constexpr (BC == K1_SYM) reflect_vec_sym<T, false>(cur, pb.hi_s, nb_total); // :161-163
             }
-        }
+        };
+        if constexpr (BC == K1_GENERIC)
+            with_kind<0>(pb.mu_kind, [&](auto m) { with_kind<1>(pb.sigma_kind, [&](auto sg) { steps(m, sg); }); });
+        else steps(KTag<HDP_COEF_CONST>{}, KTag<HDP_COEF_CONST>{});
         store_el<T, ALIGNED>(y0, q0, n_el, prev);
         store_el<T, ALIGNED>(y1, q0, n_el, cur);
         // fused epilogue mc_sample!(z, y1) (src/DeepSplitting.jl:186-189)
@@ -186,33 +222,6 @@ sde_loop_kernel(DevProblem<T> pb, T* __restrict__ y0, T* __restrict__ y1, size_t
 // (uprev + dt μ) + σ (sqrt(dt) ξ) — a third association, next to :160 and src/MLP.jl:417.
 // x (in/out): d×B start → final states; traj (TRAJ): d×(nsteps+1)×B as `Array(sim)` lays it out.
 // Normals: dW_inject[q + n_el*step] (INJECT) or draw(SDE, ordinal = step, i = q) like sde_loop!.
-template <int N> struct KTag { static constexpr int value = N; };
-// μ or σ of a kind known at compile time (coef_any without the switch in the step loop)
-template <int KIND, typename T> __device__ __forceinline__ T coef_k(const T* p, T x, int i, T t, int d, int which)
-{
-    if constexpr (KIND == HDP_COEF_LINEAR) return mul_rn(p[0], x);
-    else if constexpr (KIND == HDP_COEF_QUADRATIC) return mul_rn(p[0], mul_rn(x, x));
-    else if constexpr (KIND == HDP_COEF_USER) return which ? user_sigma<T>(x, i, t, d, p) : user_mu<T>(x, i, t, d, p);
-    else return p[0];
-}
-// calls fn(KTag<kind>) for a run-time kind (once per thread, outside the step loop).  The NVRTC
-// build knows both kinds when it compiles (HDP_FIXED_MU_KIND / HDP_FIXED_SIGMA_KIND): one copy.
-template <int WHICH, typename F> __device__ __forceinline__ void with_kind(int kind, F&& fn)
-{
-#if defined(HDP_FIXED_MU_KIND) && defined(HDP_FIXED_SIGMA_KIND)
-    (void)kind;
-    if constexpr (WHICH) fn(KTag<HDP_FIXED_SIGMA_KIND>{});
-    else fn(KTag<HDP_FIXED_MU_KIND>{});
-#else
-    switch (kind) {
-    case HDP_COEF_LINEAR: fn(KTag<HDP_COEF_LINEAR>{}); break;
-    case HDP_COEF_QUADRATIC: fn(KTag<HDP_COEF_QUADRATIC>{}); break;
-    case HDP_COEF_USER: fn(KTag<HDP_COEF_USER>{}); break;
-    default: fn(KTag<HDP_COEF_CONST>{}); break;
-    }
-#endif
-}
-
 template <typename T, bool ALIGNED, bool INJECT, bool TRAJ>
 __global__ void __launch_bounds__(128)
 em_ensemble_kernel(DevProblem<T> pb, T* __restrict__ x, size_t n_el, int nsteps, T dt, T t0, T* __restrict__ traj,
