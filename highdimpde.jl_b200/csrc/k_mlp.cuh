@@ -334,8 +334,8 @@ __device__ HDP_NOINLINE Feat<T> em_step_generic(Ctx<T, G>& c, const XAcc<T>& src
     const T lo_s = P.pb.lo_s, hi_s = P.pb.hi_s;
     const bool mu_lin = P.pb.mu_kind == HDP_COEF_LINEAR;
     const bool sg_lin = P.pb.sigma_kind == HDP_COEF_LINEAR;
-    const bool mu_usr = P.pb.mu_kind == HDP_COEF_USER || P.pb.mu_kind == HDP_COEF_QUADRATIC;
-    const bool sg_usr = P.pb.sigma_kind == HDP_COEF_USER || P.pb.sigma_kind == HDP_COEF_QUADRATIC;
+    const bool mu_usr = P.pb.mu_kind == HDP_COEF_USER;
+    const bool sg_usr = P.pb.sigma_kind == HDP_COEF_USER;
     const T mu_c = P.pb.mu_c, sg_c = P.pb.sigma_c;
     const bool want_min = P.pb.g_kind == HDP_G_MIN || P.pb.g_kind == HDP_G_USER;
     const T dt = sub_rn(tend, s);  // :415
@@ -365,8 +365,8 @@ __device__ HDP_NOINLINE Feat<T> em_step_generic(Ctx<T, G>& c, const XAcc<T>& src
             T mudt = mu_lin ? mul_rn(mul_rn(mu_c, x), dt) : mudt_c;
             T sgsq = sg_lin ? mul_rn(mul_rn(sg_c, x), sq) : sgsq_c;
             // μ(x,p,t), σ(x,p,t) are evaluated at the start point and the END time (:417)
-            if (mu_usr) mudt = mul_rn(coef_any<T>(P.pb.mu_kind, P.pb.mu_p, x, p * VEC + e, tend, d, 0), dt);
-            if (sg_usr) sgsq = mul_rn(coef_any<T>(P.pb.sigma_kind, P.pb.sigma_p, x, p * VEC + e, tend, d, 1), sq);
+            if (mu_usr) mudt = mul_rn(user_mu<T>(x, p * VEC + e, tend, d, P.pb.mu_p), dt);
+            if (sg_usr) sgsq = mul_rn(user_sigma<T>(x, p * VEC + e, tend, d, P.pb.sigma_p), sq);
             o.v[e] = add_rn(x, add_rn(mudt, mul_rn(sgsq, xi.v[e]))); // :417  x + (μ*dt + (σ*sq)*ξ)
         }
         if (has_bc) { // :418-420
@@ -694,6 +694,17 @@ __device__ __forceinline__ T run_unit_iter(Ctx<T, G>& c, const MlpParams<T>& P, 
     return result;
 }
 
+// which specialisation of the coordinate loop a launch takes: EM_* for constant coefficients, in-register
+// RNG, g without min(x) and no / a scalar boundary, else 0 (the general form).  The host picks the units
+// kernel compiled for exactly this mode (k_mlp_host.cu), the device uses it for everything else.
+template <typename T> __host__ __device__ inline int em_mode_of(const DevProblem<T>& pb, bool normals_injected)
+{
+    if (pb.mu_kind == HDP_COEF_CONST && pb.sigma_kind == HDP_COEF_CONST && (!pb.has_bc || pb.bc_is_scalar) &&
+        !normals_injected && pb.g_kind != HDP_G_MIN && pb.g_kind != HDP_G_USER)
+        return !pb.has_bc ? EM_NOBC : (pb.lo_s == -pb.hi_s ? EM_SYM : EM_BOX);
+    return 0;
+}
+
 template <typename T, int G>
 __device__ __forceinline__ void ctx_init(Ctx<T, G>& c, const MlpParams<T>& P, u64 tid, int lane_w)
 {
@@ -705,10 +716,7 @@ __device__ __forceinline__ void ctx_init(Ctx<T, G>& c, const MlpParams<T>& P, u6
     c.bad = 0;
     c.seed = 0;
     c.frame_mem = nullptr;
-    c.fast = 0;
-    if (P.pb.mu_kind == HDP_COEF_CONST && P.pb.sigma_kind == HDP_COEF_CONST && (!P.pb.has_bc || P.pb.bc_is_scalar) &&
-        P.n_tape == nullptr && P.pb.g_kind != HDP_G_MIN && P.pb.g_kind != HDP_G_USER)
-        c.fast = !P.pb.has_bc ? EM_NOBC : (P.pb.lo_s == -P.pb.hi_s ? EM_SYM : EM_BOX);
+    c.fast = em_mode_of<T>(P.pb, P.n_tape != nullptr);
     c.fast_s = P.s_tape == nullptr && (P.sm.kind != HDP_SAMPLER_UNIFORM || P.sm.scalar);
     c.f_uses_z = P.pb.f_kind == HDP_F_NL_REPLICATOR || P.pb.f_kind == HDP_F_NL_USER;
 }
@@ -775,7 +783,7 @@ __device__ __forceinline__ void expand_item(Ctx<T, G>& c, const MlpParams<T>& P,
 }
 
 // one work item w = (unit, solve): evaluate and store the partial sum
-template <typename T, int G, int U = 1>
+template <typename T, int G, int U = 1, int FM = -1>
 __device__ __forceinline__ void unit_item(Ctx<T, G>& c, const MlpParams<T>& P, u64 w)
 {
     const int solve = (int)(w % (u64)P.n_solves);
@@ -787,11 +795,19 @@ __device__ __forceinline__ void unit_item(Ctx<T, G>& c, const MlpParams<T>& P, u
     const T s = nd.time_site < 0 ? P.pb.t0 : P.site_r[(u64)solve * P.n_sites + nd.time_site];
     const XAcc<T> xp = c.point(solve, nd.point);
     T v;
-    switch (c.fast) {
-    case EM_NOBC: v = run_unit_iter<T, G, EM_NOBC, U>(c, P, un, nd, xp, s); break;
-    case EM_SYM: v = run_unit_iter<T, G, EM_SYM, U>(c, P, un, nd, xp, s); break;
-    case EM_BOX: v = run_unit_iter<T, G, EM_BOX, U>(c, P, un, nd, xp, s); break;
-    default: v = run_unit_iter<T, G, 0, 1>(c, P, un, nd, xp, s); break;
+    // FM >= 0: a kernel compiled for one mode (the host launched it because em_mode_of says so) carries
+    // only that copy of the walk; FM < 0 (NVRTC build, host emulation): decided here
+    if constexpr (FM == EM_NOBC) v = run_unit_iter<T, G, EM_NOBC, U>(c, P, un, nd, xp, s);
+    else if constexpr (FM == EM_SYM) v = run_unit_iter<T, G, EM_SYM, U>(c, P, un, nd, xp, s);
+    else if constexpr (FM == EM_BOX) v = run_unit_iter<T, G, EM_BOX, U>(c, P, un, nd, xp, s);
+    else if constexpr (FM == 0) v = run_unit_iter<T, G, 0, 1>(c, P, un, nd, xp, s);
+    else {
+        switch (c.fast) {
+        case EM_NOBC: v = run_unit_iter<T, G, EM_NOBC, U>(c, P, un, nd, xp, s); break;
+        case EM_SYM: v = run_unit_iter<T, G, EM_SYM, U>(c, P, un, nd, xp, s); break;
+        case EM_BOX: v = run_unit_iter<T, G, EM_BOX, U>(c, P, un, nd, xp, s); break;
+        default: v = run_unit_iter<T, G, 0, 1>(c, P, un, nd, xp, s); break;
+        }
     }
     const int nb = gsumi<G>(c.nb, c.gmask);
     if (c.lane == 0) {
@@ -926,7 +942,7 @@ __global__ void __launch_bounds__(128) mlp_expand_kernel(const __grid_constant__
 
 // the work units: dynamic fetch, one warp takes 32/G consecutive work items at a time
 // (lane groups of a warp then run equal-shaped units in lockstep)
-template <typename T, int G, int U>
+template <typename T, int G, int U, int FM = -1>
 __global__ void __launch_bounds__(HDP_MLP_BLOCK, Tune<U>::MB) mlp_units_kernel(const __grid_constant__ MlpParams<T> P)
 {
     constexpr int GPW = 32 / G;
@@ -934,6 +950,10 @@ __global__ void __launch_bounds__(HDP_MLP_BLOCK, Tune<U>::MB) mlp_units_kernel(c
     Ctx<T, G> c;
     const int lane_w = threadIdx.x & 31;
     ctx_init<T, G>(c, P, (u64)blockIdx.x * blockDim.x + threadIdx.x, lane_w);
+    if (FM >= 0 && c.fast != FM) { // the host and the device disagree about the mode: never compute with the wrong loop
+        if (threadIdx.x == 0) atomicExch(&P.flags[1], 1);
+        return;
+    }
     c.frame_mem = reinterpret_cast<Frame<T>*>(hdp_dyn_smem) + threadIdx.x / G; // blockDim.x / G frames
     const int sub = lane_w / G;
     const u64 n_work = (u64)P.n_units * (u64)P.n_solves;
@@ -944,7 +964,7 @@ __global__ void __launch_bounds__(HDP_MLP_BLOCK, Tune<U>::MB) mlp_units_kernel(c
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n_local) break;
         const u64 wl = base + (u64)sub;
-        if (wl < n_local) unit_item<T, G, U>(c, P, wl * (u64)P.nranks + (u64)P.rank);
+        if (wl < n_local) unit_item<T, G, U, FM>(c, P, wl * (u64)P.nranks + (u64)P.rank);
     }
     if (c.bad) atomicExch(&P.flags[0], 1);
 }

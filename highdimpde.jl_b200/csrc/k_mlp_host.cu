@@ -187,7 +187,8 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
     const double min_unit = 8.0; // smallest work unit (path-steps + half the sampler calls)
     const int G = pick_group(nvec, tab.W[L] * (double)n_solves, n_solves, (double)h->prop.multiProcessorCount);
     const MlpLaunchers<T> LN = launchers_for<T>(G);
-    if (!LN.units[0]) return set_err(h, HDP_ERR_UNSUPPORTED, "no kernel for group size %d", G);
+    if (!LN.units[0][0]) return set_err(h, HDP_ERR_UNSUPPORTED, "no kernel for group size %d", G);
+    const int mode = em_mode_of<T>(P.pb, cfg->n_tape != nullptr); // the units kernel compiled for this mode
     UserModule* um = nullptr;
     if (uses_user && (rc = get_user_module(h, prob, cfg->user, sizeof(T) == 4, G, &um)) != HDP_OK) return rc;
     const int block = HDP_MLP_BLOCK;
@@ -201,7 +202,7 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
             (void)cudaGetLastError();
             bps = 0;
         }
-    } else bps = LN.max_blocks_per_sm[long_rows](block, dyn_smem);
+    } else bps = LN.max_blocks_per_sm[long_rows][mode](block, dyn_smem);
     if (bps < 1) return set_err(h, HDP_ERR_CUDA, "occupancy query failed for the MLP kernel");
     const int sms = h->prop.multiProcessorCount;
     const int nranks = h->nccl_comm ? h->nccl_nranks : 1;
@@ -329,7 +330,7 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
         if (um) {
             void* args[1] = {(void*)&P};
             HDP_CUDA(h, cudaLaunchKernel((const void*)um->units, dim3(grid), dim3(block), args, dyn_smem, h->stream));
-        } else HDP_CUDA(h, LN.units[long_rows](P, grid, block, dyn_smem, h->stream));
+        } else HDP_CUDA(h, LN.units[long_rows][mode](P, grid, block, dyn_smem, h->stream));
         h->launches++;
     }
     HDP_CUDA(h, cudaEventRecord(h->evp[1], h->stream));
@@ -364,9 +365,10 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
     // root values: value[solve][0]
     HDP_CUDA(h, cudaMemcpy2DAsync(u_out, sizeof(T), d_value, (size_t)P.n_nodes * sizeof(T), sizeof(T), n_solves,
                                   cudaMemcpyDeviceToHost, h->stream));
-    int flag = 0;
+    int flags2[2] = {0, 0}; // [0] start point outside the box, [1] kernel / mode mismatch (internal)
+    int& flag = flags2[0];
     unsigned long long ctr[2] = {0, 0};
-    HDP_CUDA(h, cudaMemcpyAsync(&flag, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    HDP_CUDA(h, cudaMemcpyAsync(flags2, h->d_flags, sizeof(flags2), cudaMemcpyDeviceToHost, h->stream));
     HDP_CUDA(h, cudaMemcpyAsync(ctr, h->d_ctr, sizeof(ctr), cudaMemcpyDeviceToHost, h->stream));
     HDP_CUDA(h, cudaStreamSynchronize(h->stream));
     if (stats) {
@@ -385,6 +387,10 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
         stats->n_sites = P.n_sites;
         stats->group_size = G;
         stats->n_launches = h->launches - launches0;
+    }
+    if (flags2[1]) {
+        cudaMemsetAsync(h->d_flags, 0, sizeof(flags2), h->stream);
+        return set_err(h, HDP_ERR_UNSUPPORTED, "internal: the units kernel launched does not match the mode of the problem");
     }
     if (flag) {
         cudaMemsetAsync(h->d_flags, 0, sizeof(int), h->stream);
@@ -410,13 +416,30 @@ extern "C" int hdp_mlp_counts_get(int M, int L, int K, int nonlocal, int compat_
     return HDP_OK;
 }
 
+// HDP_COEF_QUADRATIC inside the recursion: served as the user expression c*(x*x) through the NVRTC build, so
+// the statically compiled kernels stay exactly as they are (the reference's MLP tests never use this kind)
+template <typename T>
+int mlp_solve_entry(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg, const T* x0, T* u_out,
+                    hdp_mlp_stats* stats)
+{
+    if (!h || !prob || !cfg || (prob->mu_kind != HDP_COEF_QUADRATIC && prob->sigma_kind != HDP_COEF_QUADRATIC))
+        return mlp_solve_impl<T>(h, prob, cfg, x0, u_out, stats);
+    hdp_problem p2 = *prob;
+    hdp_mlp_cfg c2 = *cfg;
+    hdp_user_exprs ue = cfg->user ? *cfg->user : hdp_user_exprs{nullptr, nullptr, nullptr, nullptr};
+    if (prob->mu_kind == HDP_COEF_QUADRATIC) { p2.mu_kind = HDP_COEF_USER; ue.mu = "p[0]*(x*x)"; }
+    if (prob->sigma_kind == HDP_COEF_QUADRATIC) { p2.sigma_kind = HDP_COEF_USER; ue.sigma = "p[0]*(x*x)"; }
+    c2.user = &ue;
+    return mlp_solve_impl<T>(h, &p2, &c2, x0, u_out, stats);
+}
+
 extern "C" int hdp_mlp_solve_f64(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg, const double* x0,
                                  double* u_out, hdp_mlp_stats* stats)
 {
-    return mlp_solve_impl<double>(h, prob, cfg, x0, u_out, stats);
+    return mlp_solve_entry<double>(h, prob, cfg, x0, u_out, stats);
 }
 extern "C" int hdp_mlp_solve_f32(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg, const float* x0,
                                  float* u_out, hdp_mlp_stats* stats)
 {
-    return mlp_solve_impl<float>(h, prob, cfg, x0, u_out, stats);
+    return mlp_solve_entry<float>(h, prob, cfg, x0, u_out, stats);
 }

@@ -12,19 +12,19 @@ namespace {
 typedef HDP_INST_T T_;
 constexpr int G_ = HDP_INST_G;
 
-template <int U> static int inst_max_blocks(int block, size_t dyn_smem)
+template <int U, int FM> static int inst_max_blocks(int block, size_t dyn_smem)
 {
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mlp_units_kernel<T_, G_, U>, block, dyn_smem) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mlp_units_kernel<T_, G_, U, FM>, block, dyn_smem) != cudaSuccess) {
         (void)cudaGetLastError();
         return 0;
     }
     return nb;
 }
-template <int U>
+template <int U, int FM>
 static cudaError_t inst_units(const MlpParams<T_>& P, int grid, int block, size_t dyn_smem, cudaStream_t st)
 {
-    mlp_units_kernel<T_, G_, U><<<grid, block, dyn_smem, st>>>(P);
+    mlp_units_kernel<T_, G_, U, FM><<<grid, block, dyn_smem, st>>>(P);
     return cudaGetLastError();
 }
 static cudaError_t inst_expand(const MlpParams<T_>& P, int off, int count, int grid, int block, cudaStream_t st)
@@ -37,10 +37,14 @@ static cudaError_t inst_expand(const MlpParams<T_>& P, int off, int count, int g
 MlpLaunchers<HDP_INST_T> HDP_INST_NAME()
 {
     MlpLaunchers<HDP_INST_T> l;
-    l.max_blocks_per_sm[0] = inst_max_blocks<1>;
-    l.max_blocks_per_sm[1] = inst_max_blocks<3>;
-    l.units[0] = inst_units<1>;
-    l.units[1] = inst_units<3>;
+    static_assert(EM_NOBC == 1 && EM_SYM == 2 && EM_BOX == 3, "mode index");
+#define HDP_SET(LONG, U, FM)                           \
+    l.max_blocks_per_sm[LONG][FM] = inst_max_blocks<U, FM>; \
+    l.units[LONG][FM] = inst_units<U, FM>;
+    HDP_SET(0, 1, 0) HDP_SET(0, 1, 1) HDP_SET(0, 1, 2) HDP_SET(0, 1, 3)
+    // the general form always walks one vec-group per pass: long rows only change its launch bounds
+    HDP_SET(1, 3, 0) HDP_SET(1, 3, 1) HDP_SET(1, 3, 2) HDP_SET(1, 3, 3)
+#undef HDP_SET
     l.expand = inst_expand;
     return l;
 }

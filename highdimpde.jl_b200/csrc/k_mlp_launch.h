@@ -7,9 +7,10 @@
 namespace hdp {
 
 template <typename T> struct MlpLaunchers {
-    // [0]: one vec-group per pass (short rows), [1]: three per pass (long rows)
-    int (*max_blocks_per_sm[2])(int block, size_t dyn_smem);
-    cudaError_t (*units[2])(const MlpParams<T>& P, int grid, int block, size_t dyn_smem, cudaStream_t st);
+    // [0]: one vec-group per pass (short rows), [1]: three per pass (long rows); second index: the mode of
+    // the coordinate loop the kernel was compiled for (em_mode_of: 0 general, EM_NOBC, EM_SYM, EM_BOX)
+    int (*max_blocks_per_sm[2][4])(int block, size_t dyn_smem);
+    cudaError_t (*units[2][4])(const MlpParams<T>& P, int grid, int block, size_t dyn_smem, cudaStream_t st);
     cudaError_t (*expand)(const MlpParams<T>& P, int off, int count, int grid, int block, cudaStream_t st);
 };
 

@@ -207,3 +207,42 @@ def test_user_coefficients_on_the_k1_paths_match_oracle(H, O, handle, dtype):
     pbp, _k = plain.to_c()
     wx, _ = O.em_ensemble(pbp, x0, N, dtype(0.1), dtype(0.0), xiN)
     assert np.array_equal(H.em_ensemble(plain, x0, 0.1, normals=xiN, handle=handle), wx)
+
+
+@pytest.mark.gpu
+def test_em_ensemble_edges(H, handle):
+    """Empty ensembles, zero steps, a vector start point without `trajectories`, wrong shapes."""
+    prob = _prob(H, H.LinearCoef(0.1), 0.3, 4, tspan=(0.0, 0.5))
+    assert H.em_ensemble(prob, np.zeros((4, 0), order="F"), 0.1, handle=handle).shape == (4, 0)
+    x0 = np.asfortranarray(np.arange(12.0).reshape(4, 3))
+    tr = H.em_ensemble(prob, x0, 1.0, saveat=True, handle=handle)  # dt > T - t0 rounds to zero steps
+    assert tr.shape == (4, 1, 3) and np.array_equal(tr[:, 0, :], x0)
+    with pytest.raises(ValueError):
+        H.em_ensemble(prob, np.zeros(4), 0.1, handle=handle)
+    with pytest.raises(ValueError):
+        H.em_ensemble(prob, np.zeros((5, 2), order="F"), 0.1, handle=handle)
+    with pytest.raises(ValueError):
+        H.em_ensemble(prob, x0, 0.1, normals=np.zeros((4, 3, 4)), handle=handle)
+    # a user kind without expressions on the handle is the caller's error, reported as such
+    lib = handle.lib
+    pb, _k = _prob(H, H.UserCoef("x"), 1.0, 4).to_c()
+    H.capi.check(handle.h, lib.hdp_set_user_exprs(handle.h, None))
+    x = np.zeros((4, 2), order="F")
+    import ctypes as C
+    rc = lib.hdp_em_ensemble_f64(handle.h, C.byref(pb), H.capi.np_ptr(x), 2, 3, C.c_double(0.1), C.c_double(0.0), None, 1,
+                                 None, H.capi.HDP_MEM_HOST)
+    assert rc == H.capi.HDP_ERR_BAD_ARG
+
+
+@pytest.mark.gpu
+def test_mlp_with_quadratic_sigma_matches_oracle(H, O, handle):
+    """QuadraticCoef inside the MLP recursion (served as the user expression c*(x*x) through NVRTC) against the
+    oracle's native kind, on injected tapes."""
+    from helpers import oracle_solve, random_tapes, rel_err
+    prob = H.ParabolicPDEProblem(H.LinearCoef(0.02), H.QuadraticCoef(0.4), np.full(6, 0.7), (0.0, 0.5), g=H.SumSq(),
+                                 f=H.FAllenCahn(1.0), neumann_bc=(-2.0, 2.0))
+    alg = H.MLP(M=3, L=3, K=2)
+    tapes = random_tapes(H, prob, alg, np.float64, seed=4)
+    want, _ = oracle_solve(H, O, prob, alg, np.float64, tapes)
+    u, st = H._ml_picard_batch(prob, alg, n_solves=1, seed=0, handle=handle, tapes=tapes)
+    assert rel_err(float(u[0]), float(want)) <= 1e-12
