@@ -37,9 +37,9 @@ D, M, L, K = 100, 4, 4, 10
 SOLVES_PER_GPU = 4096
 PATH_STEPS_PER_SOLVE = 4916          # C(4) for M=4 local
 I64_PER_COORD_STEP = 39              # fp64 pipe-instr budget per reflected coordinate-step
-I64_EXECUTED = 28.1                  # what the kernel executes per coordinate-step (ncu fp64-pipe % x cycles, profiles/r1m)
-# dram__bytes_read.sum + dram__bytes_write.sum of one units launch on this workload (ncu --set full, profiles/r1m)
-DRAM_TRAFFIC_PER_LAUNCH = 2.28e6 + 1.48e6
+I64_EXECUTED = 28.0                  # what the kernel executes per coordinate-step (ncu fp64-pipe % x cycles, profiles/r1o_summary.md)
+# dram__bytes_read.sum + dram__bytes_write.sum of one units launch on this workload (ncu --set full, profiles/r1o_summary.md)
+DRAM_TRAFFIC_PER_LAUNCH = 2.24e6 + 1.47e6
 F_ALG_PER_COORD_STEP = 11            # algorithmic FLOP per reflected coordinate-step
 print_line = print
 METRIC = "mlp_solves_per_sec"
@@ -280,7 +280,7 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": achieved / 1e12, "peak": peak64 / 1e12, "unit": "Tlane-instr/s",
                          "frac": achieved / peak64, "traffic": DRAM_TRAFFIC_PER_LAUNCH,
-                         "traffic_note": "bytes per units launch (4096 solves), ncu capture profiles/r1m_mlp_units_full.md: "
+                         "traffic_note": "bytes per units launch (4096 solves), ncu capture profiles/r1o_summary.md: "
                                          "the scratch of the tree walk stays in L2; HBM is idle, the fp64 pipe is the bound",
                          "executed": {"fp64_instr_per_coord_step": I64_EXECUTED,
                                       "frac": coord_steps_per_s_gpu * I64_EXECUTED / peak64,
