@@ -449,17 +449,6 @@ template <typename T> __device__ __forceinline__ T user_sigma(T x, int i, T t, i
     return (T)(HDP_USER_SIGMA_EXPR);
 }
 
-// μ(x,p,t)[i] (which = 0) or σ(x,p,t)[i] (which = 1) of any kind
-template <typename T> __device__ __forceinline__ T coef_any(int kind, const T* p, T x, int i, T t, int d, int which)
-{
-    switch (kind) {
-    case HDP_COEF_LINEAR: return mul_rn(p[0], x);
-    case HDP_COEF_QUADRATIC: return mul_rn(p[0], mul_rn(x, x)); // c * x .^ 2
-    case HDP_COEF_USER: return which ? user_sigma<T>(x, i, t, d, p) : user_mu<T>(x, i, t, d, p);
-    }
-    return p[0];
-}
-
 // MLP step, src/MLP.jl:417:  x + ((μ*dt) + ((σ*sq)*ξ))
 template <typename T> __device__ __forceinline__ T em_mlp(T x, T mu, T sg, T dt, T sq, T xi)
 {

@@ -48,7 +48,7 @@ __device__ __forceinline__ T sample_one(const DevSampler<T>& sm, T raw, int i, T
 
 
 template <int N> struct KTag { static constexpr int value = N; };
-// μ or σ of a kind known at compile time (coef_any without the switch in the step loop)
+// μ(x,p,t)[i] (which = 0) or σ(x,p,t)[i] (which = 1) of a kind known at compile time: no switch in the step loop
 template <int KIND, typename T> __device__ __forceinline__ T coef_k(const T* p, T x, int i, T t, int d, int which)
 {
     if constexpr (KIND == HDP_COEF_LINEAR) return mul_rn(p[0], x);
