@@ -77,3 +77,39 @@ def test_gpu_reproduces_golden_elementwise(H, handle):
     assert np.array_equal(z, G["mc_uniform"])
     H.NormalSampling(0.3, True)(z, G["mc_y1"], inject=G["mc_raw_n"], handle=handle)
     assert np.array_equal(z, G["mc_normal_shifted"])
+
+
+# ------------------------------ golden_v2: EM ensembles, state-dependent coefficients ------------------------------
+from make_golden_v2 import ensemble_cases, prob_of, sde_cases  # noqa: E402
+
+G2 = np.load(os.path.join(HERE, "golden", "golden_v2.npz"))
+DT = {"f64": np.float64, "f32": np.float32}
+
+
+def test_oracle_reproduces_golden_v2(H, O):
+    for tag, dt in DT.items():
+        for name, (mu, sg, d, B, N, tspan) in ensemble_cases().items():
+            h = (tspan[1] - tspan[0]) / N
+            xe, traj = O.em_ensemble(prob_of(mu, sg, d, dt, tspan).to_c()[0], G2[f"ens_{tag}_{name}_x0"], N, dt(h),
+                                     dt(tspan[0]), G2[f"ens_{tag}_{name}_xi"], saveat=True)
+            assert np.array_equal(traj, G2[f"ens_{tag}_{name}_traj"]) and np.array_equal(xe, traj[:, -1, :])
+        for name, (mu, sg, bc) in sde_cases().items():
+            y0, y1, _ = O.sde_loop(prob_of(mu, sg, 5, dt, (0.0, 1.0), bc).to_c()[0], G2[f"sde_{tag}_{name}_start"], 6, 0.1,
+                                   G2[f"sde_{tag}_{name}_dW"])
+            assert np.array_equal(y0, G2[f"sde_{tag}_{name}_y0"]) and np.array_equal(y1, G2[f"sde_{tag}_{name}_y1"])
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_golden_v2(H, handle):
+    for tag, dt in DT.items():
+        for name, (mu, sg, d, B, N, tspan) in ensemble_cases().items():
+            h = (tspan[1] - tspan[0]) / N
+            traj = H.em_ensemble(prob_of(mu, sg, d, dt, tspan), G2[f"ens_{tag}_{name}_x0"], h, normals=G2[f"ens_{tag}_{name}_xi"],
+                                 saveat=True, handle=handle)
+            assert np.array_equal(traj, G2[f"ens_{tag}_{name}_traj"])  # the same IEEE operations in the same order
+        for name, (mu, sg, bc) in sde_cases().items():
+            y1 = np.array(G2[f"sde_{tag}_{name}_start"], order="F")
+            y0 = np.empty_like(y1, order="F")
+            H.sde_loop(prob_of(mu, sg, 5, dt, (0.0, 1.0), bc), y0, y1, 6, 0.1, dWall=G2[f"sde_{tag}_{name}_dW"], handle=handle)
+            tol = TOL[dt] if bc is not None else 0.0
+            assert np.max(np.abs(y1 - G2[f"sde_{tag}_{name}_y1"])) <= tol and np.max(np.abs(y0 - G2[f"sde_{tag}_{name}_y0"])) <= tol
