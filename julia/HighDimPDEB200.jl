@@ -134,10 +134,10 @@ function sampler_desc(s::UniformSampling, keep)
 end
 sampler_desc(s::NormalSampling, keep) = HdpSampler(2, s.shifted, 1, 0, 0.0, 0.0, Float64(s.σ), C_NULL, C_NULL)
 
-function problem_desc(prob, f, bc, keep; g = prob.g)
+function problem_desc(prob, f, bc, keep; g = prob.g, d = length(prob.x))
     μk, μp = kind_of(prob.μ); σk, σp = kind_of(prob.σ)
     gk, gp = gkind(g);        fk, fp = fkind(f)
-    d = Int32(length(prob.x))
+    d = Int32(d)
     if isnothing(bc)
         has, scal, lo_s, hi_s, lo, hi = 0, 1, 0.0, 0.0, C_NULL, C_NULL
     elseif bc[1] isa Number
@@ -260,8 +260,9 @@ end
 # `saveat = true` returns `Array(sim)` (d × N+1 × trajectories), else x.
 function em_ensemble_b200!(x::Matrix{T}, prob, dt; saveat = false) where {T <: Union{Float32, Float64}}
     keep = Any[]
-    pb = problem_desc(prob, FZero(), nothing, keep; g = SumSq(zero(T)))
-    N = Int(round((prob.tspan[2] - prob.tspan[1]) / dt)); d, B = size(x)
+    d, B = size(x)                      # prob.x is `nothing` for NNKolmogorov problems (src/NNKolmogorov.jl:19)
+    pb = problem_desc(prob, FZero(), nothing, keep; g = SumSq(zero(T)), d = d)
+    N = Int(round((prob.tspan[2] - prob.tspan[1]) / dt))
     traj = saveat ? Array{T}(undef, d, N + 1, B) : nothing
     h = handle(); set_user_coefs!(h, prob)
     sym = T === Float64 ? :hdp_em_ensemble_f64 : :hdp_em_ensemble_f32
