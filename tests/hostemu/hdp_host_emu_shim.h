@@ -1,8 +1,8 @@
 // hdp_host_emu_shim.h — TEST INFRASTRUCTURE ONLY.
-// Lets g++ compile the product's device code (hdp_device.cuh, k_mlp.cuh) for the
-// host with a single-lane group (G = 1), so the tree planner, the consumption-
-// ordinal arithmetic and the combine logic can be checked against the oracle on
-// a machine without a GPU.  Never compiled into libhdpde_b200.so.
+// Lets g++ compile the product's device code (hdp_device.cuh, k_mlp.cuh, k_sde.cuh) for the
+// host with a single-lane group (G = 1) / a single thread, so the tree planner, the
+// consumption-ordinal arithmetic, the combine logic and the K1 step loops can be checked
+// against the oracle on a machine without a GPU.  Never compiled into libhdpde_b200.so.
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -18,6 +18,11 @@
 
 struct alignas(16) double2 { double x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
+
+// launch geometry of the emulated K1 kernels (k_sde.cuh): one block of one thread walks the whole grid-stride loop
+struct hdp_emu_dim3 { unsigned x, y, z; };
+static const hdp_emu_dim3 blockIdx = {0, 0, 0}, threadIdx = {0, 0, 0}, blockDim = {1, 1, 1}, gridDim = {1, 1, 1};
+static inline int __reduce_add_sync(unsigned, int v) { return v; }
 
 // IEEE round-to-nearest primitives (the emulation is built with -ffp-contract=off)
 static inline double __dmul_rn(double a, double b) { return a * b; }

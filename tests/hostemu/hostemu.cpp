@@ -7,6 +7,7 @@
 #include <vector>
 #include <algorithm>
 #include "k_mlp.cuh"
+#include "k_sde.cuh"
 #include "mlp_plan.h"
 #include "hdp_convert.h"
 
@@ -130,3 +131,82 @@ extern "C" void hdp_emu_plan_summary(int M, int L, int K, int nonlocal, double t
     out[3] = plan.n_points; out[4] = plan.max_depth;
     out[5] = (int64_t)plan.tab.C[L]; out[6] = (int64_t)plan.tab.R[L]; out[7] = (int64_t)plan.tab.S[L];
 }
+
+// ------------------------------------------------------------------------------------------
+// K1 (k_sde.cuh): the `sde_loop!` / `_mlt_sde_loop!` kernel and the EM-ensemble kernel, one emulated
+// thread walking the whole grid-stride loop.  The mode is chosen as sde_loop_impl (k_elementwise.cu) does.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+static int emu_sde_loop(const hdp_problem* prob, T* y0, T* y1, int B, int nsteps, T dt, const T* ts,
+                        const hdp_sampler* x0s_, uint64_t seed, const T* dW, const hdp_sampler* mc_, T* z, int K,
+                        int mlp_assoc, int force_generic, unsigned long long* bounces)
+{
+    DevProblem<T> pb;
+    fill_dev_problem<T>(prob, &pb);
+    const int d = prob->d;
+    std::vector<T> lohi, ab0, ab1;
+    if (prob->has_bc && !prob->bc_is_scalar) {
+        lohi.resize(2 * d);
+        for (int i = 0; i < d; ++i) { lohi[i] = (T)prob->lo[i]; lohi[d + i] = (T)prob->hi[i]; }
+        pb.lo = lohi.data(); pb.hi = lohi.data() + d;
+    }
+    DevSampler<T> x0s, mcs;
+    fill_dev_sampler<T>(x0s_, &x0s);
+    fill_dev_sampler<T>(mc_, &mcs);
+    auto vec_bounds = [&](const hdp_sampler* s, DevSampler<T>& q, std::vector<T>& ab) {
+        if (s && s->kind == HDP_SAMPLER_UNIFORM && !s->bounds_are_scalar) {
+            ab.resize(2 * d);
+            for (int i = 0; i < d; ++i) { ab[i] = (T)s->a[i]; ab[d + i] = (T)s->b[i]; }
+            q.a = ab.data(); q.b = ab.data() + d;
+        }
+    };
+    vec_bounds(x0s_, x0s, ab0);
+    vec_bounds(mc_, mcs, ab1);
+    const size_t n_el = (size_t)d * (size_t)B;
+    if (n_el == 0) return HDP_OK;
+    int flags[2] = {0, 0};
+    unsigned long long ctr = 0;
+    const bool const_coef = prob->mu_kind == HDP_COEF_CONST && prob->sigma_kind == HDP_COEF_CONST && !mlp_assoc && !force_generic;
+    const int bc = !const_coef ? K1_GENERIC : !pb.has_bc ? K1_NOBC : (pb.bc_is_scalar && pb.lo_s == -pb.hi_s) ? K1_SYM : K1_GENERIC;
+    T* zz = (z && mcs.kind != HDP_SAMPLER_NONE && K > 0) ? z : nullptr;
+#define EMU_K1(INJ, BC) sde_loop_kernel<T, false, INJ, BC>(pb, y0, y1, n_el, nsteps, dt, x0s, nullptr, seed, dW, mcs, zz, K, flags, &ctr, mlp_assoc, 0, ts)
+    if (dW) { if (bc == K1_SYM) EMU_K1(true, K1_SYM); else if (bc == K1_NOBC) EMU_K1(true, K1_NOBC); else EMU_K1(true, K1_GENERIC); }
+    else { if (bc == K1_SYM) EMU_K1(false, K1_SYM); else if (bc == K1_NOBC) EMU_K1(false, K1_NOBC); else EMU_K1(false, K1_GENERIC); }
+#undef EMU_K1
+    if (bounces) *bounces = ctr;
+    return flags[0] ? HDP_ERR_START_OUTSIDE_DOMAIN : HDP_OK;
+}
+
+template <typename T>
+static int emu_em_ensemble(const hdp_problem* prob, T* x, int B, int nsteps, T dt, T t0, T* traj, uint64_t seed, const T* xi)
+{
+    DevProblem<T> pb;
+    hdp_problem pr = *prob;
+    pr.has_bc = 0;
+    fill_dev_problem<T>(&pr, &pb);
+    const size_t n_el = (size_t)prob->d * (size_t)B;
+    if (n_el == 0) return HDP_OK;
+    if (xi) { if (traj) em_ensemble_kernel<T, false, true, true>(pb, x, n_el, nsteps, dt, t0, traj, seed, xi, 0);
+              else em_ensemble_kernel<T, false, true, false>(pb, x, n_el, nsteps, dt, t0, traj, seed, xi, 0); }
+    else { if (traj) em_ensemble_kernel<T, false, false, true>(pb, x, n_el, nsteps, dt, t0, traj, seed, xi, 0);
+           else em_ensemble_kernel<T, false, false, false>(pb, x, n_el, nsteps, dt, t0, traj, seed, xi, 0); }
+    return HDP_OK;
+}
+
+#define EMU_K1_EXPORT(REAL, SFX)                                                                                     \
+    extern "C" int hdp_emu_sde_loop##SFX(const hdp_problem* prob, REAL* y0, REAL* y1, int B, int nsteps, REAL dt,    \
+                                         const REAL* ts, const hdp_sampler* x0s, uint64_t seed, const REAL* dW,      \
+                                         const hdp_sampler* mc, REAL* z, int K, int mlp_assoc, int force_generic,    \
+                                         unsigned long long* bounces)                                                \
+    {                                                                                                                \
+        return emu_sde_loop<REAL>(prob, y0, y1, B, nsteps, dt, ts, x0s, seed, dW, mc, z, K, mlp_assoc, force_generic, \
+                                  bounces);                                                                          \
+    }                                                                                                                \
+    extern "C" int hdp_emu_em_ensemble##SFX(const hdp_problem* prob, REAL* x, int B, int nsteps, REAL dt, REAL t0,   \
+                                            REAL* traj, uint64_t seed, const REAL* xi)                               \
+    {                                                                                                                \
+        return emu_em_ensemble<REAL>(prob, x, B, nsteps, dt, t0, traj, seed, xi);                                    \
+    }
+EMU_K1_EXPORT(double, _f64)
+EMU_K1_EXPORT(float, _f32)
+
