@@ -310,8 +310,9 @@ int hdp_mc_sample_f32(hdp_handle h, float* z, const float* y1, int d, int B, int
  * caller's: y1 holds the start points on entry).
  * y0 (out): state before the last step; y1 (in/out): start → final state.
  * nsteps = size(dWall,3); ts[i] (i=0..nsteps-1) is the time passed to
- * μ,σ at step i, i.e. Julia's ts[N+1-i] (:157).  May be NULL for
- * time-independent kinds.
+ * μ,σ at step i, i.e. Julia's ts[N+1-i] (:157).  Always a HOST array (a
+ * collected Julia range), whatever mem_flags says.  May be NULL for the
+ * enumerated kinds (all time-independent); required for HDP_COEF_USER.
  * x0_sampler: prob.x0_sample, applied to y1 before the loop (:155);
  * NULL or kind NONE leaves y1 untouched.
  * dWall_inject: nullable d×B×nsteps standard normals (the reference's
