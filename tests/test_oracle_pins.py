@@ -304,3 +304,71 @@ def test_sde_loop_oracle_matches_numpy(O, H):
         prev = want
         want = (prev + 0.5 * 0.1) + (2.0 * math.sqrt(0.1)) * dW[:, :, i]
     assert np.array_equal(y1, want) and np.array_equal(y0, prev)
+
+
+# ------------------------------ a second, independent restatement ------------------------------
+def _seq_sumsq(x):
+    s = 0.0
+    for v in x:
+        s += float(v) * float(v)
+    return s
+
+
+def _closure_cases(H):
+    """name -> (kinds problem, alg, python closures mu, sigma, g, f, python sampler) — the closures are the
+    reference's test functions transcribed literally (test/MLP.jl, docs/src/tutorials/mlp.md)."""
+    from oracle import ml_picard_py as P
+    mx = lambda u: u if u > 0 else 0.0  # noqa: E731
+    d = 4
+    c = {}
+    c["heat"] = (H.ParabolicPDEProblem(0.0, 0.1, np.full(d, 2.0), (0.0, 0.5), g=H.SumSq(), f=H.FZero()), H.MLP(M=3, L=3, K=2),
+                 lambda x, p, t: 0.0, lambda x, p, t: 0.1, lambda x: _seq_sumsq(x),
+                 lambda y, z, vy, vz, dy, dz, p, t: 0.0 * vy, P.NoSampling())                              # test/MLP.jl:24-35
+    bc = (np.full(d, -0.5), np.full(d, 0.5))
+    c["allen_cahn_neumann"] = (H.ParabolicPDEProblem(0.0, 1.0, np.zeros(d), (0.0, 0.5), g=H.ExpSumSq(0.25), f=H.FAllenCahn(1.0),
+                                                     neumann_bc=bc), H.MLP(M=3, L=4, K=2),
+                               lambda x, p, t: 0.0, lambda x, p, t: 1.0, lambda x: math.exp(-0.25 * _seq_sumsq(x)),
+                               lambda y, z, vy, vz, dy, dz, p, t: 1.0 * (vy - vy * vy * vy), P.NoSampling())  # :162-186
+    c["black_scholes"] = (H.ParabolicPDEProblem(H.LinearCoef(0.02), H.LinearCoef(0.2), np.full(d, 100.0), (0.0, 1.0),
+                                                g=H.MinCoord(), f=H.FDefaultRisk()), H.MLP(M=3, L=3, K=2),
+                          lambda x, p, t: 0.02 * x, lambda x, p, t: 0.2 * x, lambda x: float(np.min(x)),
+                          None, P.NoSampling())                                                            # :188-230
+    dr = H.FDefaultRisk()
+
+    def f_risk(y, z, vy, vz, dy, dz, p, t):                                                                # :209-215
+        Q = (vy < dr.vh) * dr.gh + (vy >= dr.vl) * dr.gl + ((vy >= dr.vh) and (vy < dr.vl)) * (
+            ((dr.gh - dr.gl) / (dr.vh - dr.vl)) * (vy - dr.vh) + dr.gh)
+        return -(1.0 - dr.delta) * Q * vy - dr.R * vy
+    c["black_scholes"] = c["black_scholes"][:5] + (f_risk,) + c["black_scholes"][6:]
+    c["fisher_nonlocal_neumann"] = (H.PIDEProblem(0.0, 0.1, np.zeros(d), (0.0, 0.5), H.ExpSumSq(1.0), H.FNLFisher(), neumann_bc=bc),
+                                    H.MLP(M=2, L=4, K=2, mc_sample=H.UniformSampling(np.full(d, -0.5), np.full(d, 0.5))),
+                                    lambda x, p, t: 0.0, lambda x, p, t: 0.1, lambda x: math.exp(-_seq_sumsq(x)),
+                                    lambda y, z, vy, vz, dy, dz, p, t: mx(vy) * (1.0 - mx(vz)),
+                                    P.UniformSampling(np.full(d, -0.5), np.full(d, 0.5)))                  # tutorials/mlp.md:45-58
+    c["allen_cahn_diff_shifted_normal"] = (H.PIDEProblem(0.0, 0.1, np.zeros(d), (0.0, 0.5), H.ExpSumSq(0.25), H.FNLAllenCahnDiff()),
+                                           H.MLP(M=2, L=4, K=2, mc_sample=H.NormalSampling(0.2, True)),
+                                           lambda x, p, t: 0.0, lambda x, p, t: 0.1, lambda x: math.exp(-0.25 * _seq_sumsq(x)),
+                                           lambda y, z, vy, vz, dy, dz, p, t: (vy - vy * vy * vy) - (vz - vz * vz * vz),
+                                           P.NormalSampling(0.2, True))                                    # test/MLP.jl:288-317
+    return c
+
+
+@pytest.mark.parametrize("name", ["heat", "allen_cahn_neumann", "black_scholes", "fisher_nonlocal_neumann",
+                                  "allen_cahn_diff_shifted_normal"])
+def test_c_oracle_equals_independent_python_restatement(O, H, name):
+    """oracle/ml_picard_py.py was written from src/MLP.jl, src/reflect.jl and src/MCSample.jl on its own and runs
+    real closures; the C oracle (enumerated kinds) must give the same bits on the same tapes, consume exactly the
+    same number of random numbers and count the same wall hits."""
+    from helpers import oracle_solve, random_tapes
+    from oracle import ml_picard_py as P
+    prob, alg, mu, sigma, g, f, sampler = _closure_cases(H)[name]
+    tapes = random_tapes(H, prob, alg, np.float64, seed=sum(map(ord, name)))
+    want, info = oracle_solve(H, O, prob, alg, np.float64, tapes)
+    pp = P.Problem(mu, sigma, g, f, prob.tspan, neumann_bc=prob.neumann_bc)
+    tape = P.Tape(*tapes)
+    got, st = P.solve(pp, alg.M, alg.L, alg.K, prob.x, sampler, tape)
+    assert got == want, (got, want)                                   # bit for bit
+    assert st["bounces"] == info["bounces"]
+    assert tape.ir == len(tapes[0]) and tape.in_ == len(tapes[1])     # every draw consumed, in the same order
+    if tapes[2] is not None:
+        assert tape.is_ == len(tapes[2])
