@@ -7,6 +7,7 @@ it bit for bit on shared random tapes, so a misreading of the recursion would ha
 languages, to go unnoticed.  (The reference itself is pure Julia and cannot run in this image.)
 
     _ml_picard       src/MLP.jl:102-208   (and :210-216 for x === nothing)
+    _ml_picard_mlt   src/MLP.jl:218-260, _ml_picard_call :262-388, _get_loop_num :391-404
     _mlt_sde_loop!   src/MLP.jl:406-421
     _reflect         src/reflect.jl:8-55  (Vector method, the literal sequential billiard)
     samplers         src/MCSample.jl:28-33, 63-71, 86
@@ -191,3 +192,77 @@ def solve(prob, M, L, K, x, mc_sample, tape):
     stats = {"steps": 0, "bounces": 0}
     u = ml_picard(M, L, K, np.asarray(x, dtype=np.float64), prob.tspan[0], prob.tspan[1], mc_sample, tape, prob, stats)
     return u, stats
+
+
+# ------------------------------ the threaded variant, src/MLP.jl:218-404 ------------------------------
+def get_loop_num(M, num, thread_id, nthreads):
+    """src/MLP.jl:391-404, literally: float division, `M % num`; `for k in 1:loop_num` runs floor(loop_num) times."""
+    if num < nthreads:
+        return 0 if thread_id > num else 1
+    remainder = M % num
+    if remainder > 0 and thread_id <= remainder:
+        loop_num = num / nthreads + 1
+    else:
+        loop_num = num / nthreads
+    return int(math.floor(loop_num))
+
+
+def ml_picard_call(M, L, K, x, s, t, mc_sample, tape, nthreads, thread_id, prob, stats):
+    """src/MLP.jl:262-388: the level loops of one task; the sums are still divided by `num`, not by the number of
+    iterations actually run (quirk Q4 of SURVEY.md)."""
+    d = x.shape[0]
+    x2 = np.empty(d)
+    x3 = np.empty(d) if mc_sample.integrate else None
+    p, f = prob.p, prob.f
+    a = 0.0
+    for l in range(0, min(L - 1, 1) + 1):                             # :284
+        b = 0.0
+        num = M ** (L - l)
+        for _k in range(get_loop_num(M, num, thread_id, nthreads)):   # :287-288
+            r = s + (t - s) * tape.rand()
+            mlt_sde_loop(tape, x2, x, s, r, prob, stats)
+            b2 = ml_picard(M, l, K, x2, r, t, mc_sample, tape, prob, stats)
+            b3 = 0.0
+            for _h in range(K):
+                z = mc_sample(tape, x3, x2)
+                b3 += f(x2, z, b2, ml_picard(M, l, K, z, r, t, mc_sample, tape, prob, stats), None, None, p, t)
+            b += b3 / K
+        a += (t - s) * b / num                                        # :307
+    for l in range(2, L):                                             # :310
+        b = 0.0
+        num = M ** (L - l)
+        for _k in range(get_loop_num(M, num, thread_id, nthreads)):
+            r = s + (t - s) * tape.rand()
+            mlt_sde_loop(tape, x2, x, s, r, prob, stats)
+            b2 = ml_picard(M, l, K, x2, r, t, mc_sample, tape, prob, stats)
+            b4 = ml_picard(M, l - 1, K, x2, r, t, mc_sample, tape, prob, stats)
+            b3 = 0.0
+            for _h in range(K):
+                z = mc_sample(tape, x3, x2)
+                first = f(x2, z, b2, ml_picard(M, l, K, z, r, t, mc_sample, tape, prob, stats), None, None, p, t)
+                second = f(x2, z, b4, ml_picard(M, l - 1, K, z, r, t, mc_sample, tape, prob, stats), None, None, p, t)
+                b3 += first - second
+            b += b3 / K
+        a += (t - s) * b / num                                        # :384
+    return a
+
+
+def solve_mlt(prob, M, L, K, x, mc_sample, tape, nthreads):
+    """`_ml_picard_mlt` (src/MLP.jl:218-260) with Threads.nthreads() == nthreads, the tasks run one after the other
+    on ONE shared tape (tasks 1..NT, then the g-term of the main task) — the order the C oracle uses when it is
+    given a single sequential tape.  (With task-local RNGs the reference's draws are not ordered across tasks.)"""
+    stats = {"steps": 0, "bounces": 0}
+    x = np.asarray(x, dtype=np.float64)
+    s, t = prob.tspan
+    parts = [ml_picard_call(M, L, K, x, s, t, mc_sample, tape, nthreads, tid, prob, stats) for tid in range(1, nthreads + 1)]
+    num = M ** L                                                      # :246
+    x2 = np.empty(x.shape[0])
+    a2 = 0.0
+    for _k in range(num):
+        mlt_sde_loop(tape, x2, x, s, t, prob, stats)                  # :251
+        a2 += prob.g(x2)
+    a2 /= num                                                         # :254
+    a = 0.0
+    for v in parts:                                                   # :257 sum([fetch(t) for t in tasks])
+        a += v
+    return a + a2, stats                                              # :259

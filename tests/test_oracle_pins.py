@@ -372,3 +372,26 @@ def test_c_oracle_equals_independent_python_restatement(O, H, name):
     assert tape.ir == len(tapes[0]) and tape.in_ == len(tapes[1])     # every draw consumed, in the same order
     if tapes[2] is not None:
         assert tape.is_ == len(tapes[2])
+
+
+@pytest.mark.parametrize("nt", [1, 3, 8])
+@pytest.mark.parametrize("name", ["allen_cahn_neumann", "fisher_nonlocal_neumann"])
+def test_c_oracle_threaded_variant_equals_independent_python_restatement(O, H, name, nt):
+    """`_ml_picard_mlt` / `_ml_picard_call` / `_get_loop_num` (src/MLP.jl:218-404, quirk Q4), tasks run one after the
+    other on one shared tape: both restatements give the same bits and consume the same draws."""
+    from helpers import random_tapes
+    from oracle import ml_picard_py as P
+    prob, alg, mu, sigma, g, f, sampler = _closure_cases(H)[name]
+    tapes = random_tapes(H, prob, alg, np.float64, seed=nt + sum(map(ord, name)), compat=nt)
+    pb, _k = prob.to_c()
+    sm, _k2 = alg.mc_sample._descriptor(prob.d)
+    rng = O.Rng.tape(np.float64, *tapes)
+    want, info = O.ml_picard_mlt(pb, sm, alg.M, alg.L, alg.K, prob.x, nt, [rng] * (nt + 1), parallel=False)
+    assert info["rc"] == 0
+    tape = P.Tape(*tapes)
+    got, st = P.solve_mlt(P.Problem(mu, sigma, g, f, prob.tspan, neumann_bc=prob.neumann_bc), alg.M, alg.L, alg.K, prob.x,
+                          sampler, tape, nt)
+    assert got == want and st["bounces"] == info["bounces"] and st["steps"] == info["path_steps"]
+    assert tape.ir == len(tapes[0]) and tape.in_ == len(tapes[1])
+    for M, num, tid, n in [(4, 256, 1, 8), (4, 4, 3, 8), (4, 16, 2, 3), (4, 1, 1, 1), (4, 4, 1, 1), (3, 27, 5, 4)]:
+        assert P.get_loop_num(M, num, tid, n) == O.get_loop_num(M, num, tid, n)
