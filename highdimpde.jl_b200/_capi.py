@@ -28,6 +28,7 @@ HDP_ERR_ALLOC = -7
 HDP_ERR_UNSUPPORTED = -8
 HDP_ERR_NVRTC = -9
 
+HDP_MAX_LEVELS = 6
 HDP_MEM_HOST = 0
 HDP_MEM_DEVICE = 1
 HDP_ASYNC = 2
@@ -72,7 +73,9 @@ class hdp_mlp_cfg(C.Structure):
                 ("n_x0", C.c_int32), ("normal_mode", C.c_int32), ("compat_mlt_threads", C.c_int32),
                 ("target_units", C.c_int32), ("seed", C.c_uint64), ("sampler", hdp_sampler),
                 ("r_tape", C.c_void_p), ("n_tape", C.c_void_p), ("s_tape", C.c_void_p),
-                ("user", C.POINTER(hdp_user_exprs))]
+                ("user", C.POINTER(hdp_user_exprs)),
+                ("group_size", C.c_int32), ("mem_flags", C.c_uint32), ("unit_oversub", C.c_double),
+                ("std_err_out", C.c_void_p)]
 
 
 class hdp_mlp_counts(C.Structure):
@@ -84,7 +87,10 @@ class hdp_mlp_stats(C.Structure):
     _fields_ = [("per_solve", hdp_mlp_counts), ("bounces", C.c_uint64), ("n_units", C.c_uint64),
                 ("n_nodes", C.c_uint64), ("n_sites", C.c_uint64), ("device_ms", C.c_double),
                 ("group_size", C.c_int32), ("n_launches", C.c_int32),
-                ("phase_ms", C.c_double * 4)]
+                ("phase_ms", C.c_double * 4),
+                ("level_n", C.c_uint64 * (HDP_MAX_LEVELS + 1)), ("level_sum", C.c_double * (HDP_MAX_LEVELS + 1)),
+                ("level_sumsq", C.c_double * (HDP_MAX_LEVELS + 1)), ("std_error", C.c_double),
+                ("exchange_bytes", C.c_uint64)]
 
 
 class hdp_devinfo(C.Structure):

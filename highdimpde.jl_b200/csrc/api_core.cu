@@ -112,6 +112,7 @@ extern "C" int hdp_destroy(hdp_handle h)
         DeviceGuard g(h->device);
         cudaStreamSynchronize(h->stream);
         hdp_comm_destroy(h);
+        h->shardings.clear();
         h->plans.clear();
         for (auto& kv : h->user_modules)
             if (kv.second.lib) cudaLibraryUnload(kv.second.lib);

@@ -18,7 +18,8 @@ struct DevBuf {
     size_t cap = 0;
 };
 
-struct MlpPlan; // mlp_plan.h
+struct MlpPlan;     // mlp_plan.h
+struct MlpSharding; // mlp_plan.h
 
 // K3 kernels compiled by NVRTC for one set of user expressions (user_kinds.cu)
 struct UserModule {
@@ -44,7 +45,7 @@ struct hdp_context {
     std::mutex mu;
     std::string err;
     // grow-only scratch, indexed by role
-    enum { B_A = 0, B_B, B_C, B_D, B_E, B_F, B_G, B_H, B_I, B_J, B_K, B_L, B_N };
+    enum { B_A = 0, B_B, B_C, B_D, B_E, B_F, B_G, B_H, B_I, B_J, B_K, B_L, B_M, B_O, B_P, B_Q, B_N };
     hdp::DevBuf buf[B_N];
     int* d_flags = nullptr;          // [0] error flag, [1..] spare
     unsigned long long* d_ctr = nullptr; // [0] work counter, [1] bounce counter
@@ -53,6 +54,7 @@ struct hdp_context {
     int nccl_rank = 0, nccl_nranks = 1;
     // MLP plan cache
     std::map<std::string, std::shared_ptr<hdp::MlpPlan>> plans;
+    std::map<std::string, std::shared_ptr<hdp::MlpSharding>> shardings; // per (plan, nranks, rank)
     std::map<std::string, hdp::UserModule> user_modules;
     std::map<std::string, hdp::SdeUserModule> sde_user_modules;
     // hdp_set_user_exprs: μ/σ expressions for the K1 entry points (copies)

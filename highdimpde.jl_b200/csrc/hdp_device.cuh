@@ -93,7 +93,10 @@ __device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, 
 __device__ __forceinline__ float sqrt_rn(float a) { return __fsqrt_rn(a); }
 
 // ---------------------------------------------------------------------
-// Philox4x32-10 with a FIXED key; the 64-bit seed travels in the counter:
+// Philox4x32-R with a FIXED key (R = HDP_PHILOX_ROUNDS, include/hdpde.h: 7, the fewest rounds
+// Salmon et al. (SC'11) report as Crush-resistant; their default of 10 buys margin the Monte-Carlo
+// estimators here do not need and costs 12 of the ~147 instructions of a vec-group); the 64-bit
+// seed travels in the counter:
 //   ctr = (w0, w1, seed_lo, seed_hi),   (w0, w1) = draw_address(stream, ordinal, group)
 // Addressing by consumption ordinal — never by thread id — makes every draw independent of
 // launch geometry and GPU count.  The fixed key makes the ten round keys immediates of the
@@ -106,10 +109,10 @@ struct Philox4 { uint32_t w[4]; };
 
 constexpr uint32_t kPhiloxKey0 = 0xA4093822u, kPhiloxKey1 = 0x299F31D0u; // fractional digits of pi
 
-__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3)
+__device__ __forceinline__ Philox4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3)
 {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < HDP_PHILOX_ROUNDS; ++r) {
         const uint32_t k0 = kPhiloxKey0 + (uint32_t)r * 0x9E3779B9u, k1 = kPhiloxKey1 + (uint32_t)r * 0xBB67AE85u;
         const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
@@ -350,7 +353,7 @@ __device__ __forceinline__ Philox4 draw_words(u64 seed, int stream, u64 ord, u64
 {
     uint32_t w0, w1;
     draw_address(stream, ord, group, w0, w1);
-    return philox4x32_10(w0, w1, (uint32_t)seed, (uint32_t)(seed >> 32));
+    return philox4x32(w0, w1, (uint32_t)seed, (uint32_t)(seed >> 32));
 }
 template <typename T> __device__ __forceinline__ Vec<T> normals_from_words(const Philox4& p, const DrawK<T>& k);
 template <> __device__ __forceinline__ Vec<double> normals_from_words<double>(const Philox4& p, const DrawK<double>& k)
@@ -542,28 +545,43 @@ __device__ __forceinline__ bool reflect_first(Vec<T>& x, T lo, T hi, int& nb)
     return again;
 }
 // Symmetric scalar box [-h, h] (every BASELINE configuration with a boundary): |x| > h is the
-// same decision as (x < -h) | (x > h), and the wall that was hit is copysign(h, x).  Same
-// mirror arithmetic, fewer compares and selects.
+// same decision as (x < -h) | (x > h), and the wall that was hit is copysign(h, x).
+// With m = h - |x| (negative exactly when the coordinate is outside: x - x rounds to +0, so the
+// sign bit of m IS the decision) the mirror b - 2*(b - wall) of src/reflect.jl:34 is
+// sign(b) * (|b| + 2 m): |b| - h = -m exactly (rounding is symmetric), 2*(.) is exact, so the one
+// fma below rounds like the reference's subtract, double, subtract.  Everything that follows the
+// two fp64 operations is integer work on the high word of m: the select predicate, the hit count
+// (one LEA.HI) and the test for a second hit — fp64 compares hold the dispatch port twice as long.
+// `far` = sym_far_bits(h): a coordinate whose first mirror image is still outside has
+// m <= -2h (up to one rounding), i.e. high word of m >= high word of -2h as unsigned integers;
+// the test below is that comparison with a margin, so it may report a few coordinates that are
+// in fact inside — its callers re-check with reflect_coord, which decides exactly.
+__device__ __forceinline__ uint32_t top_bits(double x) { return d2hi(x); }
+__device__ __forceinline__ uint32_t top_bits(float x) { return f2u(x); }
+template <typename T> __device__ __forceinline__ uint32_t sym_far_bits(T h)
+{
+    return top_bits(mul_rn((T)-2, h)) - (sizeof(T) == 8 ? 1u : 16u);
+}
+// First wall hit of VEC coordinates, branch-free.  Returns the largest top_bits(m) of the group:
+// >= `far` (sym_far_bits) means some coordinate may still be outside after its first mirror.
+// (Predicated fmas written in PTX come back from ptxas as fma + select, so the select is written here.)
 template <typename T, bool COUNT = true>
-__device__ __forceinline__ bool reflect_first_sym(Vec<T>& x, T h, int& nb)
+__device__ __forceinline__ uint32_t reflect_first_sym(Vec<T>& x, T h, int& nb)
 {
     constexpr int VEC = Tr<T>::VEC;
-    bool again = false;
+    uint32_t top = 0;
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
         const T v = x.v[e];
         const T a = fabs(v);
-        const bool o = a > h;
-        // b - 2*(b - wall) with wall = copysign(h, b) is sign(b) * (|b| - 2*(|b| - h)): rounding is
-        // symmetric and 2*(.) is exact, so the single fma below rounds exactly like the
-        // reference's subtract, double, subtract (src/reflect.jl:34)
-        const T ta = xfma((T)-2, sub_rn(a, h), a);
-        const T t = xor_sign(ta, v);
-        x.v[e] = o ? t : v;
-        if (COUNT) nb += o ? 1 : 0;
-        again |= o && (fabs(ta) > h);
+        const T m = sub_rn(h, a);
+        const T ta = xfma((T)2, m, a);
+        const uint32_t mb = top_bits(m);
+        x.v[e] = (int32_t)mb < 0 ? xor_sign(ta, v) : v;
+        if (COUNT) nb += (int)(mb >> 31);
+        top = mb > top ? mb : top;
     }
-    return again;
+    return top;
 }
 template <typename T, int G, bool COUNT = true>
 __device__ __forceinline__ void reflect_vec(Vec<T>& x, const Vec<T>& lo, const Vec<T>& hi, unsigned gmask, int& nb)
@@ -587,9 +605,9 @@ __device__ __forceinline__ void reflect_vec(Vec<T>& x, const Vec<T>& lo, const V
     }
 }
 template <typename T, bool COUNT = true>
-__device__ __forceinline__ void reflect_vec_sym(Vec<T>& x, T h, int& nb)
+__device__ __forceinline__ void reflect_vec_sym(Vec<T>& x, T h, uint32_t far, int& nb)
 {
-    if (reflect_first_sym<T, COUNT>(x, h, nb)) {
+    if (reflect_first_sym<T, COUNT>(x, h, nb) >= far) {
 #pragma unroll
         for (int e = 0; e < Tr<T>::VEC; ++e) x.v[e] = reflect_coord<T>(x.v[e], -h, h, nb);
     }

@@ -52,7 +52,8 @@ template <typename T> struct MlpParams {
     u64 seed0;
     int n_solves, n_x0;
     const PlanUnit* units;
-    const int32_t* exec;
+    const int32_t* exec;      // the units this rank evaluates, most expensive first
+    int n_exec;
     const int8_t* unit_tag;
     const PlanNode* nodes;
     const PlanSite* sites;
@@ -68,6 +69,18 @@ template <typename T> struct MlpParams {
     T* scratch;
     u64 total_threads;
     int rank, nranks;
+    // one solve sharded over several ranks (mlp_plan.h: MlpSharding); all null on one GPU
+    const int8_t* unit_mine;  // per unit: evaluated on this rank
+    const int8_t* site_cls;   // per site: SITE_UPPER (replicated), SITE_MINE, SITE_OTHER (bottom sites)
+    const int32_t* node_slot; // per node: slot of a crown node in xbuf, else -1
+    double* xbuf;             // [n_solves][xstride] crown partial values, then the root statistics;
+                              // followed by kXTail doubles for the whole call.  The only buffer all-reduced.
+    int xstride, n_slots;
+    // Monte-Carlo error bar of the root call (cfg->std_err_out); all null when not asked for
+    double* rootsq;           // [n_solves][rootsq_stride]: (sum, sum of squares) per root unit, or per root level
+    int rootsq_stride;        //   when the whole solve is one unit
+    double* lvstat;           // [n_solves][3*(kMaxL+1)]: n, sum, sum of squares per root level (entry L: g-term)
+    T* std_err;               // [n_solves]
     int zero;        // 0, opaque to the compiler (draw_k_init)
     unsigned long long* work_ctr;
     unsigned long long* bounce_ctr;
@@ -134,18 +147,6 @@ template <int G> __device__ __forceinline__ int gsumi(int v, unsigned mask)
     return v;
 }
 
-// the lanes of a group update their shared frame in lockstep.  A single-lane group needs no
-// synchronisation (and a per-lane mask would cost a MATCH.ANY per pass); a whole warp uses the
-// constant mask.
-template <int G> __device__ __forceinline__ void group_sync(unsigned mask)
-{
-#ifndef HDP_HOST_EMU
-    if (G == 32) __syncwarp();
-    else if (G > 1) __syncwarp(mask);
-#else
-    (void)mask;
-#endif
-}
 template <typename T> __device__ __forceinline__ T big() { return (T)3.0e38; }
 
 // rand(tType)  (src/MLP.jl:132)
@@ -186,6 +187,7 @@ __device__ __forceinline__ T em_loop_fast(const MlpParams<T>& P, const DrawK<T>&
     const T sq = sqrt_rn(dt);
     const T mudt = mul_rn(P.pb.mu_c, dt), sgsq = mul_rn(P.pb.sigma_c, sq);
     const int nfull = d / VEC;
+    [[maybe_unused]] const uint32_t far = sym_far_bits<T>(hi_s);
     if (BC && check_src) { // src/reflect.jl:12
         const T* q = sp;
         for (int p = lane; p < nvec; p += G, q += sstride) {
@@ -227,6 +229,7 @@ __device__ __forceinline__ T em_loop_fast(const MlpParams<T>& P, const DrawK<T>&
                 sp += sstride;
             }
         }
+        const unsigned bit0 = 1u << it; // this pass's first bit of `fix`
 #pragma unroll
         for (int u = 0; u < UU; ++u) {
 #pragma unroll
@@ -235,7 +238,7 @@ __device__ __forceinline__ T em_loop_fast(const MlpParams<T>& P, const DrawK<T>&
                 if (!FULL && !((p + u * G) * VEC + e < d)) o[u].v[e] = MODE == EM_BOX ? lo_s : (T)0; // padding never reflects
             }
             bool again = false;
-            if (MODE == EM_SYM) again = reflect_first_sym<T>(o[u], hi_s, nb);    // :418-420
+            if (MODE == EM_SYM) again = reflect_first_sym<T>(o[u], hi_s, nb) >= far; // :418-420
             if (MODE == EM_BOX) again = reflect_first<T>(o[u], lo_s, hi_s, nb);
             T q = ssq;
 #pragma unroll
@@ -244,16 +247,15 @@ __device__ __forceinline__ T em_loop_fast(const MlpParams<T>& P, const DrawK<T>&
                 q = xfma(o[u].v[e], o[u].v[e], q);
             }
             ssq = again ? ssq : q;
-            if (BC) {
-                fix |= (again ? 1u : 0u) << it;
-                if (again) stash[it] = o[u];
+            if (BC && again) {
+                fix |= bit0 << u;
+                stash[it + u] = o[u];
             }
-            ++it;
-            if (store) {
-                stv<T>(dp, o[u]);
-                dp += dstride;
-            }
+            // the stride of a scratch row is the same for every lane: one pointer bump per pass, below
+            if (store) stv<T>(dp + (size_t)u * dstride, o[u]);
         }
+        it += UU;
+        dp += (size_t)UU * dstride; // (never dereferenced when !store)
     };
     // second and later wall hits of the flagged vec-groups
     auto finish = [&]() {
@@ -489,16 +491,24 @@ __device__ __forceinline__ Feat<T> sample_step(Ctx<T, G>& c, const XAcc<T>* dst,
 // ---------------------------------------------------------------------
 template <typename T> struct Frame {
     T s, r, a, b, b3, b2, b4, f2, f3, term;
+    double sq; // sum of squares of the samples of the current level (only tracked for the root call of a solve)
     u64 k, num, gnum, co, ro, so, cc, rr, qq;
-    int lv, l, lend, h, phase, xslot, parent, pad_;
+    int lv, l, lend, h, phase, xslot, parent, pad_[sizeof(T) == 8 ? 3 : 1];
 };
+// one frame per thread, side by side in shared memory: an odd number of 8-byte words per frame keeps a
+// warp's accesses to one field on 16 distinct bank pairs (two wavefronts for a 64-bit field: the minimum)
+static_assert(sizeof(Frame<double>) % 8 == 0 && (sizeof(Frame<double>) / 8) % 2 == 1, "Frame<double> stride");
+static_assert(sizeof(Frame<float>) % 8 == 0 && (sizeof(Frame<float>) / 8) % 2 == 1, "Frame<float> stride");
+enum { SITE_UPPER = 0, SITE_MINE = 1, SITE_OTHER = 2 };
+enum { CMB_ALL = 0, CMB_PARTIAL = 1, CMB_FINAL = 2 };
+constexpr int kXTail = 8; // xbuf tail: [0..3] 16-bit chunks of the call hash, [4] wall hits, [5..7] spare
 enum { PH_B2 = 0, PH_B4 = 1, PH_V = 2, PH_W = 3 };
 enum { ST_LEVEL = 0, ST_SITE, ST_SITE_POST, ST_AFTER_B2, ST_SAMPLES, ST_SAMPLE_POST, ST_SITE_END, ST_G, ST_G_POST, ST_RETURN };
 enum { ACT_NONE = 0, ACT_EM = 1, ACT_SAMPLE = 2 };
 
 template <typename T, int G, int MODE, int U>
 __device__ __forceinline__ T run_unit_iter(Ctx<T, G>& c, const MlpParams<T>& P, const PlanUnit& u, const PlanNode& nd,
-                                           const XAcc<T>& xp, T s0)
+                                           const XAcc<T>& xp, T s0, double* rsq)
 {
     constexpr int VEC = Tr<T>::VEC;
     const DevProblem<T>& pb = P.pb;
@@ -512,9 +522,13 @@ __device__ __forceinline__ T run_unit_iter(Ctx<T, G>& c, const MlpParams<T>& P, 
     const unsigned gmask = c.gmask;
     const bool f_uses_z = pb.f_kind == HDP_F_NL_REPLICATOR || pb.f_kind == HDP_F_NL_USER;
     const DrawK<T> dk = draw_k_init<T>(P.zero & (lane + 1)); // 0, but neither constant nor uniform to the compiler
-    // The frame of the innermost active call lives in shared memory (one per lane group: its
-    // lanes read and write the same cells with the same values); the frames of its callers are
-    // parked in local memory and only touched when a call starts or returns.
+    // The frame of the innermost active call lives in shared memory, one private copy per thread
+    // (the lanes of a group keep identical copies: no cell is shared, so nothing depends on the
+    // lanes running in lockstep); the frames of its callers are parked in local memory and only
+    // touched when a call starts or returns.
+    // rsq (nullable): where this unit reports (sum, sum of squares) of the samples it takes for the
+    // root call of its solve — the error bar of cfg->std_err_out.  A slice unit reports one pair, a
+    // unit that is the whole solve one pair per level and one for the g-term.
     Frame<T> parked[kMaxL + 1];
 #ifdef HDP_HOST_EMU
     Frame<T> frame0;
@@ -533,6 +547,7 @@ __device__ __forceinline__ T run_unit_iter(Ctx<T, G>& c, const MlpParams<T>& P, 
         F->num = kind == UNIT_LEVEL ? n : P.Mpow[root];
         F->gnum = kind == UNIT_G ? n : P.Mpow[root];
         F->a = (T)0; F->b = (T)0;
+        F->sq = 0.0;
         F->s = s0;
         F->xslot = -1;
         F->co = u.c; F->ro = u.r; F->so = u.s;
@@ -547,7 +562,6 @@ __device__ __forceinline__ T run_unit_iter(Ctx<T, G>& c, const MlpParams<T>& P, 
         // One pass runs the bookkeeping from the result of the last action to the next one.  The
         // handlers are ordered so that every transition except "return to the parent" lands on a
         // handler further down the same pass.
-        group_sync<G>(gmask);
         int l = F->l;
         int act = ACT_NONE;
         // action parameters
@@ -614,7 +628,9 @@ __device__ __forceinline__ T run_unit_iter(Ctx<T, G>& c, const MlpParams<T>& P, 
             }
         }
         if (st == ST_G_POST) {
-            F->b += g_eval<T>(pb, feat); // :203
+            const T gv = g_eval<T>(pb, feat);
+            F->b += gv; // :203
+            if (rsq && cur == root) F->sq += (double)gv * (double)gv;
             F->k += 1;
             st = ST_G;
         }
@@ -636,7 +652,9 @@ __device__ __forceinline__ T run_unit_iter(Ctx<T, G>& c, const MlpParams<T>& P, 
             }
         }
         if (st == ST_SITE_END) {
-            F->b += F->b3 / (T)K; // :148
+            const T sv = F->b3 / (T)K;
+            F->b += sv; // :148
+            if (rsq && cur == root) F->sq += (double)sv * (double)sv;
             F->k += 1;
             F->co += P.cs[l]; F->ro += P.rs[l]; F->so += P.ss[l];
             st = ST_LEVEL;
@@ -646,12 +664,20 @@ __device__ __forceinline__ T run_unit_iter(Ctx<T, G>& c, const MlpParams<T>& P, 
                 if (l >= F->lend) { F->k = 0; F->b = (T)0; st = ST_G; break; }
                 if (F->k < F->num) { st = ST_SITE; break; }
                 if (cur == root && kind == UNIT_LEVEL) break; // the slice is done: result = b
+                if (rsq && cur == root) { // a whole solve: one pair per level
+                    if (lane == 0) { rsq[2 * l] = (double)F->b; rsq[2 * l + 1] = F->sq; }
+                    F->sq = 0.0;
+                }
                 F->a += ((t1 - F->s) * F->b) / (T)F->num; // :150, :195
                 l += 1;
                 F->l = l; F->k = 0; F->b = (T)0;
                 F->num = P.Mpow[F->lv - l];
             }
-            if (st == ST_LEVEL) { result = F->b; break; }
+            if (st == ST_LEVEL) {
+                result = F->b;
+                if (rsq && lane == 0) { rsq[0] = (double)result; rsq[1] = F->sq; }
+                break;
+            }
         }
         if (st == ST_SITE) {
             const T uu = time_uniform<T>(P, seed, F->ro);
@@ -665,7 +691,12 @@ __device__ __forceinline__ T run_unit_iter(Ctx<T, G>& c, const MlpParams<T>& P, 
                 act = ACT_EM; a_src = F->xslot; a_store = false; a_s = F->s; a_t = t1; a_ord = F->co + F->k; // :202
                 st = ST_G_POST;
             } else {
-                if (cur == root && kind == UNIT_G) { result = F->b; break; }
+                if (cur == root && kind == UNIT_G) {
+                    result = F->b;
+                    if (rsq && lane == 0) { rsq[0] = (double)result; rsq[1] = F->sq; }
+                    break;
+                }
+                if (rsq && cur == root && lane == 0) { rsq[2 * P.L] = (double)F->b; rsq[2 * P.L + 1] = F->sq; }
                 ret = F->a + F->b / (T)F->gnum; // :205, :207
                 st = ST_RETURN;
             }
@@ -744,11 +775,14 @@ __device__ __forceinline__ void assert_in_box(Ctx<T, G>& c, const MlpParams<T>& 
 }
 
 // geometry of one explicit site: r, x2, x3_h
+// (`list`: the explicit sites of one depth — or, when a solve is sharded, the replicated upper sites of one
+// depth / the bottom sites this rank owns)
 template <typename T, int G>
-__device__ __forceinline__ void expand_item(Ctx<T, G>& c, const MlpParams<T>& P, int off, u64 item)
+__device__ __forceinline__ void expand_item(Ctx<T, G>& c, const MlpParams<T>& P, const int32_t* list, u64 item,
+                                            bool count_hits = true)
 {
     const int solve = (int)(item % (u64)P.n_solves);
-    const int sidx = P.sites_by_depth[off + (int)(item / (u64)P.n_solves)];
+    const int sidx = list[item / (u64)P.n_solves];
     const PlanSite st = P.sites[sidx];
     const PlanNode nd = P.nodes[st.node];
     c.seed = P.seed0 + (u64)solve;
@@ -777,7 +811,7 @@ __device__ __forceinline__ void expand_item(Ctx<T, G>& c, const MlpParams<T>& P,
     const int nb = gsumi<G>(c.nb, c.gmask);
     const int bad = gsumi<G>(c.bad, c.gmask);
     if (c.lane == 0) {
-        if (nb) atomicAdd(P.bounce_ctr, (unsigned long long)nb);
+        if (nb && count_hits) atomicAdd(P.bounce_ctr, (unsigned long long)nb);
         if (bad) atomicExch(&P.flags[0], 1);
     }
 }
@@ -794,19 +828,22 @@ __device__ __forceinline__ void unit_item(Ctx<T, G>& c, const MlpParams<T>& P, u
     c.nb = 0;
     const T s = nd.time_site < 0 ? P.pb.t0 : P.site_r[(u64)solve * P.n_sites + nd.time_site];
     const XAcc<T> xp = c.point(solve, nd.point);
+    // units of the root call report their samples' sum of squares when an error bar is wanted
+    double* rsq = nullptr;
+    if (P.rootsq && un.node == 0) rsq = P.rootsq + (u64)solve * P.rootsq_stride + (un.kind == UNIT_WHOLE ? 0 : 2 * uid);
     T v;
     // FM >= 0: a kernel compiled for one mode (the host launched it because em_mode_of says so) carries
     // only that copy of the walk; FM < 0 (NVRTC build, host emulation): decided here
-    if constexpr (FM == EM_NOBC) v = run_unit_iter<T, G, EM_NOBC, U>(c, P, un, nd, xp, s);
-    else if constexpr (FM == EM_SYM) v = run_unit_iter<T, G, EM_SYM, U>(c, P, un, nd, xp, s);
-    else if constexpr (FM == EM_BOX) v = run_unit_iter<T, G, EM_BOX, U>(c, P, un, nd, xp, s);
-    else if constexpr (FM == 0) v = run_unit_iter<T, G, 0, 1>(c, P, un, nd, xp, s);
+    if constexpr (FM == EM_NOBC) v = run_unit_iter<T, G, EM_NOBC, U>(c, P, un, nd, xp, s, rsq);
+    else if constexpr (FM == EM_SYM) v = run_unit_iter<T, G, EM_SYM, U>(c, P, un, nd, xp, s, rsq);
+    else if constexpr (FM == EM_BOX) v = run_unit_iter<T, G, EM_BOX, U>(c, P, un, nd, xp, s, rsq);
+    else if constexpr (FM == 0) v = run_unit_iter<T, G, 0, 1>(c, P, un, nd, xp, s, rsq);
     else {
         switch (c.fast) {
-        case EM_NOBC: v = run_unit_iter<T, G, EM_NOBC, U>(c, P, un, nd, xp, s); break;
-        case EM_SYM: v = run_unit_iter<T, G, EM_SYM, U>(c, P, un, nd, xp, s); break;
-        case EM_BOX: v = run_unit_iter<T, G, EM_BOX, U>(c, P, un, nd, xp, s); break;
-        default: v = run_unit_iter<T, G, 0, 1>(c, P, un, nd, xp, s); break;
+        case EM_NOBC: v = run_unit_iter<T, G, EM_NOBC, U>(c, P, un, nd, xp, s, rsq); break;
+        case EM_SYM: v = run_unit_iter<T, G, EM_SYM, U>(c, P, un, nd, xp, s, rsq); break;
+        case EM_BOX: v = run_unit_iter<T, G, EM_BOX, U>(c, P, un, nd, xp, s, rsq); break;
+        default: v = run_unit_iter<T, G, 0, 1>(c, P, un, nd, xp, s, rsq); break;
         }
     }
     const int nb = gsumi<G>(c.nb, c.gmask);
@@ -820,38 +857,78 @@ __device__ __forceinline__ void unit_item(Ctx<T, G>& c, const MlpParams<T>& P, u
 // `nl` lanes (a warp on the device, 1 in the host emulation) share the node: they stride over
 // its units and over its explicit sites, then the per-level sums are butterfly-reduced — the
 // root of a deeply cut tree has thousands of children, one thread would walk them serially.
+//
+// mode (one solve sharded over several ranks, MlpSharding in mlp_plan.h):
+//   CMB_ALL      every unit and every site of the node -> value[node]            (one GPU; owned nodes)
+//   CMB_PARTIAL  this rank's units and bottom sites of a crown node -> xbuf slot (summed by the all-reduce)
+//   CMB_FINAL    the all-reduced slot + the node's upper sites (replicated)  -> value[node]
+// A node's value is linear in its units and in the f-terms of its sites, so the three add up.
+// The root node also gathers n, sum and sum of squares of its samples per level (the error bar).
 template <typename T>
-__device__ __forceinline__ void combine_item(const MlpParams<T>& P, int off, u64 item, int lane, int nl,
-                                             unsigned mask = 0xffffffffu)
+__device__ __forceinline__ void combine_item(const MlpParams<T>& P, const int32_t* list, u64 item, int lane, int nl,
+                                             unsigned mask = 0xffffffffu, int mode = CMB_ALL)
 {
     const int solve = (int)(item % (u64)P.n_solves);
-    const int nidx = P.nodes_by_depth[off + (int)(item / (u64)P.n_solves)];
+    const int nidx = list[item / (u64)P.n_solves];
     const PlanNode nd = P.nodes[nidx];
     const DevProblem<T>& pb = P.pb;
     const double* part = P.partial + (u64)solve * P.n_units;
     const T* val = P.value + (u64)solve * P.n_nodes;
     const T* feat = P.feat + (u64)solve * P.n_points;
+    double* xb = P.xbuf ? P.xbuf + (u64)solve * P.xstride : nullptr;
+    const int slot = P.node_slot ? P.node_slot[nidx] : -1;
+    const bool leaf = nd.unit_end - nd.unit_begin == 1 && nd.site_end == nd.site_begin &&
+                      (P.unit_tag[nd.unit_begin] >> 4) == UNIT_WHOLE;
+    const bool stats = nidx == 0 && P.lvstat != nullptr;
+    double* lv = stats ? P.lvstat + (u64)solve * (3 * (kMaxL + 1)) : nullptr;
+    const double* rsq = stats ? P.rootsq + (u64)solve * P.rootsq_stride : nullptr;
     T result;
-    if (nd.unit_end - nd.unit_begin == 1 && nd.site_end == nd.site_begin &&
-        (P.unit_tag[nd.unit_begin] >> 4) == UNIT_WHOLE) {
-        result = (T)part[nd.unit_begin];
+    double Ns[kMaxL + 1], Sm[kMaxL + 1], Sq[kMaxL + 1];
+#pragma unroll
+    for (int l = 0; l <= kMaxL; ++l) { Ns[l] = 0.0; Sm[l] = 0.0; Sq[l] = 0.0; }
+    if (leaf) {
+        // a whole-call leaf in the crown (below an upper site, or the root of a solve that is one unit): in a
+        // sharded solve its owner contributes the value, the scatter pass hands the sum back through partial[]
+        const bool have = mode == CMB_ALL || (mode == CMB_PARTIAL && P.unit_mine[nd.unit_begin]);
+        result = (mode == CMB_FINAL || have) ? (T)part[nd.unit_begin] : (T)0;
+        if (stats && have && lane == 0) { // the whole solve was one unit: it reported a pair per level
+            for (int l = 0; l <= P.L; ++l) {
+                Ns[l] = (double)P.Mpow[l < P.L ? P.L - l : P.L];
+                Sm[l] = rsq[2 * l];
+                Sq[l] = rsq[2 * l + 1];
+            }
+        }
     } else {
         const T s = nd.time_site < 0 ? pb.t0 : P.site_r[(u64)solve * P.n_sites + nd.time_site];
         T Bl[kMaxL];
 #pragma unroll
         for (int l = 0; l < kMaxL; ++l) Bl[l] = (T)0;
         T Gs = (T)0;
-        for (int u = nd.unit_begin + lane; u < nd.unit_end; u += nl) {
-            const int tag = P.unit_tag[u];
-            const T v = (T)part[u];
-            if ((tag >> 4) == UNIT_G) Gs += v;
-            else {
+        if (mode != CMB_FINAL) {
+            for (int u = nd.unit_begin + lane; u < nd.unit_end; u += nl) {
+                if (mode == CMB_PARTIAL && !P.unit_mine[u]) continue;
+                const int tag = P.unit_tag[u];
+                const T v = (T)part[u];
+                const int sl = (tag >> 4) == UNIT_G ? P.L : (tag & 15);
+                if ((tag >> 4) == UNIT_G) Gs += v;
+                else {
 #pragma unroll
-                for (int l = 0; l < kMaxL; ++l)
-                    if (l == (tag & 15)) Bl[l] += v;
+                    for (int l = 0; l < kMaxL; ++l)
+                        if (l == (tag & 15)) Bl[l] += v;
+                }
+                if (stats) {
+                    const PlanUnit un = P.units[u];
+#pragma unroll
+                    for (int l = 0; l <= kMaxL; ++l)
+                        if (l == sl) { Ns[l] += (double)(un.k1 - un.k0); Sm[l] += rsq[2 * u]; Sq[l] += rsq[2 * u + 1]; }
+                }
             }
         }
         for (int si = nd.site_begin + lane; si < nd.site_end; si += nl) {
+            if (mode != CMB_ALL) {
+                const int cls = P.site_cls[si];
+                if (mode == CMB_PARTIAL ? cls != SITE_MINE : cls != SITE_UPPER) continue;
+            }
             const PlanSite st = P.sites[si];
             const int l = st.l;
             const int32_t* ch = P.children + st.child0;
@@ -882,13 +959,24 @@ __device__ __forceinline__ void combine_item(const MlpParams<T>& P, int off, u64
             const T add = b3 / (T)P.K;
 #pragma unroll
             for (int q = 0; q < kMaxL; ++q)
-                if (q == l) Bl[q] += add;
+                if (q == l) {
+                    Bl[q] += add;
+                    if (stats) { Ns[q] += 1.0; Sm[q] += (double)add; Sq[q] += (double)add * (double)add; }
+                }
         }
         if (nl > 1) { // butterfly over the nl lanes of this node (an aligned sub-warp group)
             for (int o = nl >> 1; o > 0; o >>= 1) {
 #pragma unroll
                 for (int l = 0; l < kMaxL; ++l) Bl[l] += __shfl_xor_sync(mask, Bl[l], o);
                 Gs += __shfl_xor_sync(mask, Gs, o);
+                if (stats) {
+#pragma unroll
+                    for (int l = 0; l <= kMaxL; ++l) {
+                        Ns[l] += __shfl_xor_sync(mask, Ns[l], o);
+                        Sm[l] += __shfl_xor_sync(mask, Sm[l], o);
+                        Sq[l] += __shfl_xor_sync(mask, Sq[l], o);
+                    }
+                }
             }
         }
         T a = (T)0;
@@ -898,7 +986,30 @@ __device__ __forceinline__ void combine_item(const MlpParams<T>& P, int off, u64
         const T a2 = Gs / (T)P.Mpow[nd.lv];
         result = a + a2;
     }
-    if (lane == 0) P.value[(u64)solve * P.n_nodes + nidx] = result;
+    if (lane != 0) return;
+    if (mode == CMB_PARTIAL) xb[slot] = (double)result;
+    else P.value[(u64)solve * P.n_nodes + nidx] = (mode == CMB_FINAL && !leaf) ? (T)(xb[slot] + (double)result) : result;
+    if (stats) {
+        double* xs = xb ? xb + P.n_slots : nullptr; // the root statistics travel behind the crown slots
+        if (mode == CMB_PARTIAL) {
+            for (int l = 0; l <= kMaxL; ++l) { xs[3 * l] = Ns[l]; xs[3 * l + 1] = Sm[l]; xs[3 * l + 2] = Sq[l]; }
+            return;
+        }
+        // standard error of the root value: the samples of a level are i.i.d., the levels independent
+        double var = 0.0;
+        for (int l = 0; l <= P.L; ++l) {
+            if (mode == CMB_FINAL) { Ns[l] += xs[3 * l]; Sm[l] += xs[3 * l + 1]; Sq[l] += xs[3 * l + 2]; }
+            lv[3 * l] = Ns[l]; lv[3 * l + 1] = Sm[l]; lv[3 * l + 2] = Sq[l];
+            const double n = Ns[l];
+            const double w = l < P.L ? (double)(pb.t1 - pb.t0) : 1.0;
+            if (n > 1.5) {
+                double v1 = (Sq[l] - Sm[l] * Sm[l] / n) / (n - 1.0); // sample variance of the level
+                if (v1 < 0.0) v1 = 0.0;
+                var += w * w * v1 / n;
+            }
+        }
+        if (P.std_err) P.std_err[solve] = (T)sqrt(var);
+    }
 }
 
 // points[solve][0] <- x0 (padded with zeros)
@@ -920,7 +1031,7 @@ __device__ __forceinline__ void init_item(const MlpParams<T>& P, const T* x0, u6
 // ---------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------
-extern __shared__ double2 hdp_dyn_smem[]; // units kernel: (blockDim.x / G) * sizeof(Frame<T>) bytes
+extern __shared__ double2 hdp_dyn_smem[]; // units kernel: blockDim.x * sizeof(Frame<T>) bytes
 template <typename T>
 __global__ void mlp_init_kernel(const __grid_constant__ MlpParams<T> P, const T* __restrict__ x0)
 {
@@ -930,14 +1041,15 @@ __global__ void mlp_init_kernel(const __grid_constant__ MlpParams<T> P, const T*
 }
 
 template <typename T, int G>
-__global__ void __launch_bounds__(128) mlp_expand_kernel(const __grid_constant__ MlpParams<T> P, int off, int count)
+__global__ void __launch_bounds__(128) mlp_expand_kernel(const __grid_constant__ MlpParams<T> P, const int32_t* list, int count,
+                                                         int count_hits)
 {
     if constexpr (sizeof(T) == 8) tables_init();
     Ctx<T, G> c;
     ctx_init<T, G>(c, P, (u64)blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31);
     const u64 gid = c.tid / G;
     if (gid >= (u64)count * (u64)P.n_solves) return;
-    expand_item<T, G>(c, P, off, gid);
+    expand_item<T, G>(c, P, list, gid, count_hits != 0);
 }
 
 // the work units: dynamic fetch, one warp takes 32/G consecutive work items at a time
@@ -954,17 +1066,16 @@ __global__ void __launch_bounds__(HDP_MLP_BLOCK, Tune<U>::MB) mlp_units_kernel(c
         if (threadIdx.x == 0) atomicExch(&P.flags[1], 1);
         return;
     }
-    c.frame_mem = reinterpret_cast<Frame<T>*>(hdp_dyn_smem) + threadIdx.x / G; // blockDim.x / G frames
+    c.frame_mem = reinterpret_cast<Frame<T>*>(hdp_dyn_smem) + threadIdx.x; // one private frame per thread
     const int sub = lane_w / G;
-    const u64 n_work = (u64)P.n_units * (u64)P.n_solves;
-    const u64 n_local = n_work > (u64)P.rank ? (n_work - (u64)P.rank + (u64)P.nranks - 1) / (u64)P.nranks : 0;
+    const u64 n_work = (u64)P.n_exec * (u64)P.n_solves; // this rank's units (all of them on one GPU)
     for (;;) {
         unsigned long long base = 0;
         if (lane_w == 0) base = atomicAdd(P.work_ctr, (unsigned long long)GPW);
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n_local) break;
+        if (base >= n_work) break;
         const u64 wl = base + (u64)sub;
-        if (wl < n_local) unit_item<T, G, U, FM>(c, P, wl * (u64)P.nranks + (u64)P.rank);
+        if (wl < n_work) unit_item<T, G, U, FM>(c, P, wl);
     }
     if (c.bad) atomicExch(&P.flags[0], 1);
 }
@@ -972,14 +1083,34 @@ __global__ void __launch_bounds__(HDP_MLP_BLOCK, Tune<U>::MB) mlp_units_kernel(c
 // nl lanes (a power of two, 1..32) share one (node, solve): 32 where nodes have many children (the
 // root of a deeply cut tree has thousands), 4 where they have a handful
 template <typename T>
-__global__ void __launch_bounds__(128) mlp_combine_kernel(const __grid_constant__ MlpParams<T> P, int off, int count, int nl)
+__global__ void __launch_bounds__(128) mlp_combine_kernel(const __grid_constant__ MlpParams<T> P, const int32_t* list, int count,
+                                                          int nl, int mode)
 {
     const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    // the call-wide tail of the exchange buffer: wall hits of this rank out, the all-reduced total back
+    if (t == 0 && P.xbuf) {
+        double* tail = P.xbuf + (u64)P.n_solves * P.xstride;
+        if (mode == CMB_PARTIAL) tail[4] = (double)*P.bounce_ctr;
+        if (mode == CMB_FINAL && list[0] == 0) *P.bounce_ctr = (unsigned long long)tail[4];
+    }
     const u64 gid = t / (unsigned)nl;
-    const bool live = gid < (u64)count * (u64)P.n_solves;
-    const unsigned mask = __ballot_sync(0xffffffffu, live);
-    if (!live) return;
-    combine_item<T>(P, off, gid, (int)(t % (unsigned)nl), nl, mask);
+    if (gid >= (u64)count * (u64)P.n_solves) return; // (the nl lanes of a node leave together)
+    // the shuffles of a node stay inside its own nl lanes: the root's statistics are reduced by its group alone
+    const int lane = (int)(t % (unsigned)nl);
+    const unsigned mask = nl >= 32 ? 0xffffffffu : (((1u << nl) - 1u) << ((threadIdx.x & 31) - lane));
+    combine_item<T>(P, list, gid, lane, nl, mask, mode);
+}
+
+// sharded solve: the all-reduced values of the whole-call leaves below upper sites go back to partial[],
+// where the sites read their children
+template <typename T>
+__global__ void __launch_bounds__(128) mlp_scatter_kernel(const __grid_constant__ MlpParams<T> P, const int32_t* list, int count)
+{
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (u64)count * (u64)P.n_solves) return;
+    const int solve = (int)(t % (u64)P.n_solves);
+    const int nidx = list[t / (u64)P.n_solves];
+    P.partial[(u64)solve * P.n_units + P.nodes[nidx].unit_begin] = P.xbuf[(u64)solve * P.xstride + P.node_slot[nidx]];
 }
 #endif // HDP_HOST_EMU
 

@@ -20,6 +20,13 @@ MlpPlan::~MlpPlan()
     for (void* p : ps)
         if (p) cudaFree(p);
 }
+MlpSharding::~MlpSharding()
+{
+    void* ps[] = {d_exec_own, d_upper_sites, d_own_bottom_sites, d_owned_nodes, d_crown_nodes, d_crown_leaves,
+                  d_crown_final, d_unit_mine, d_site_cls, d_node_slot};
+    for (void* p : ps)
+        if (p) cudaFree(p);
+}
 } // namespace hdp
 
 namespace {
@@ -45,13 +52,10 @@ template <> MlpLaunchers<float> launchers_for<float>(int G)
 // Latency regime: a narrow group makes every work unit take longer, so when there are few
 // path-steps per resident lane group (or only a handful of solves, whose trees cut into coarse
 // units) the group is widened until each resident group has about a dozen path-steps to do.
-int pick_group(int nvec, double path_steps_total, int n_solves, double sms)
+// `forced` (cfg->group_size) overrides the rule; results never depend on the width.
+int pick_group(int forced, int nvec, double path_steps_total, int n_solves, double sms)
 {
-    const char* env = getenv("HDP_MLP_GROUP");
-    if (env) {
-        int g = atoi(env);
-        if (g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32) return g;
-    }
+    if (forced > 0) return forced;
     int G = 1;
     while (G < 32 && (nvec + G - 1) / G > (n_solves < 8 ? 16 : 64)) G *= 2;
     auto resident_groups = [&](int g) {
@@ -72,15 +76,30 @@ template <typename V> int upload(hdp_context* h, const std::vector<V>& v, void**
     return HDP_OK;
 }
 
+// The planner materialises every unit (56 bytes each on host and device): a cut finer than kMaxPlanUnits
+// units per solve is refused and retried with twice the threshold (a plan that failed is remembered as an
+// alias of the one that replaced it).
+constexpr size_t kMaxPlanUnits = 3u << 20;
 int get_plan(hdp_context* h, int M, int L, int K, bool nonlocal, double thresh, int compat,
-             std::shared_ptr<MlpPlan>* out)
+             std::shared_ptr<MlpPlan>* out, std::string* key_out)
 {
     char key[160];
     snprintf(key, sizeof(key), "%d/%d/%d/%d/%.6g/%d", M, L, K, (int)nonlocal, thresh, compat);
+    *key_out = key;
     auto it = h->plans.find(key);
-    if (it != h->plans.end()) { *out = it->second; return HDP_OK; }
+    if (it != h->plans.end()) {
+        *out = it->second;
+        snprintf(key, sizeof(key), "%d/%d/%d/%d/%.6g/%d", M, L, K, (int)nonlocal, it->second->thresh, compat);
+        *key_out = key; // (the key of the plan actually built: shardings hang off it)
+        return HDP_OK;
+    }
+    const std::string asked = key;
     auto plan = std::make_shared<MlpPlan>();
-    mlp_build_plan(M, L, K, nonlocal, thresh, compat, plan.get());
+    while (!mlp_build_plan(M, L, K, nonlocal, thresh, compat, plan.get(), kMaxPlanUnits)) thresh *= 2.0;
+    snprintf(key, sizeof(key), "%d/%d/%d/%d/%.6g/%d", M, L, K, (int)nonlocal, thresh, compat);
+    *key_out = key;
+    it = h->plans.find(key);
+    if (it != h->plans.end()) { h->plans[asked] = it->second; *out = it->second; return HDP_OK; }
     int rc;
     if ((rc = upload(h, plan->nodes, &plan->d_nodes)) != HDP_OK) return rc;
     if ((rc = upload(h, plan->sites, &plan->d_sites)) != HDP_OK) return rc;
@@ -90,9 +109,34 @@ int get_plan(hdp_context* h, int M, int L, int K, bool nonlocal, double thresh, 
     if ((rc = upload(h, plan->unit_tag, &plan->d_unit_tag)) != HDP_OK) return rc;
     if ((rc = upload(h, plan->sites_by_depth, &plan->d_sites_by_depth)) != HDP_OK) return rc;
     if ((rc = upload(h, plan->nodes_by_depth, &plan->d_nodes_by_depth)) != HDP_OK) return rc;
-    if (h->plans.size() > 64) h->plans.clear();
+    if (h->plans.size() > 64) { h->shardings.clear(); h->plans.clear(); }
     h->plans[key] = plan;
+    h->plans[asked] = plan;
     *out = plan;
+    return HDP_OK;
+}
+
+int get_sharding(hdp_context* h, const std::string& plan_key, const MlpPlan& plan, int nranks, int rank,
+                 std::shared_ptr<MlpSharding>* out)
+{
+    const std::string key = plan_key + "#" + std::to_string(nranks) + "/" + std::to_string(rank);
+    auto it = h->shardings.find(key);
+    if (it != h->shardings.end()) { *out = it->second; return HDP_OK; }
+    auto sh = std::make_shared<MlpSharding>();
+    mlp_build_sharding(plan, nranks, rank, sh.get());
+    int rc;
+    if ((rc = upload(h, sh->exec_own, &sh->d_exec_own)) != HDP_OK) return rc;
+    if ((rc = upload(h, sh->upper_sites, &sh->d_upper_sites)) != HDP_OK) return rc;
+    if ((rc = upload(h, sh->own_bottom_sites, &sh->d_own_bottom_sites)) != HDP_OK) return rc;
+    if ((rc = upload(h, sh->owned_nodes, &sh->d_owned_nodes)) != HDP_OK) return rc;
+    if ((rc = upload(h, sh->crown_nodes, &sh->d_crown_nodes)) != HDP_OK) return rc;
+    if ((rc = upload(h, sh->crown_leaves, &sh->d_crown_leaves)) != HDP_OK) return rc;
+    if ((rc = upload(h, sh->crown_final, &sh->d_crown_final)) != HDP_OK) return rc;
+    if ((rc = upload(h, sh->unit_mine, &sh->d_unit_mine)) != HDP_OK) return rc;
+    if ((rc = upload(h, sh->site_cls, &sh->d_site_cls)) != HDP_OK) return rc;
+    if ((rc = upload(h, sh->node_slot, &sh->d_node_slot)) != HDP_OK) return rc;
+    h->shardings[key] = sh;
+    *out = sh;
     return HDP_OK;
 }
 
@@ -128,6 +172,37 @@ void compat_counts(const MlpCountTables& t, int NT, uint64_t* C, uint64_t* R, ui
     *C = c + t.Mpow[t.L]; *R = r; *S = s;
 }
 
+// What the ranks of a sharded solve must agree on: the configuration, the problem and (a sample of) the start
+// points.  FNV-1a; the four 16-bit chunks travel as doubles in the tail of the exchange buffer.
+uint64_t fnv(uint64_t hsh, const void* p, size_t n)
+{
+    const unsigned char* b = (const unsigned char*)p;
+    for (size_t i = 0; i < n; ++i) { hsh ^= b[i]; hsh *= 0x100000001b3ull; }
+    return hsh;
+}
+template <typename T>
+uint64_t call_hash(const hdp_problem* prob, const hdp_mlp_cfg* cfg, const T* x0_host, int n_units, double thresh)
+{
+    uint64_t hsh = 0xcbf29ce484222325ull;
+    const int32_t ints[] = {cfg->M, cfg->L, cfg->K, cfg->n_solves, cfg->n_x0, cfg->compat_mlt_threads, cfg->sampler.kind,
+                            cfg->sampler.shifted, prob->d, prob->mu_kind, prob->sigma_kind, prob->g_kind, prob->f_kind,
+                            prob->has_bc, n_units, (int32_t)sizeof(T)};
+    hsh = fnv(hsh, ints, sizeof(ints));
+    hsh = fnv(hsh, &cfg->seed, sizeof(cfg->seed));
+    hsh = fnv(hsh, &thresh, sizeof(thresh));
+    hsh = fnv(hsh, &prob->t0, 2 * sizeof(double));
+    hsh = fnv(hsh, prob->mu_p, sizeof(prob->mu_p));
+    hsh = fnv(hsh, prob->sigma_p, sizeof(prob->sigma_p));
+    hsh = fnv(hsh, prob->g_p, sizeof(prob->g_p));
+    hsh = fnv(hsh, prob->f_p, sizeof(prob->f_p));
+    if (x0_host) { // host start points: the first and the last 4 KB
+        const size_t nb = (size_t)cfg->n_x0 * prob->d * sizeof(T), cap = 4096;
+        hsh = fnv(hsh, x0_host, std::min(nb, cap));
+        if (nb > cap) hsh = fnv(hsh, (const char*)x0_host + nb - cap, cap);
+    }
+    return hsh;
+}
+
 template <typename T>
 int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg, const T* x0, T* u_out,
                    hdp_mlp_stats* stats)
@@ -145,6 +220,13 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
     if (cfg->normal_mode != HDP_NORMAL_DEFAULT &&
         cfg->normal_mode != (sizeof(T) == 8 ? HDP_NORMAL_BM64 : HDP_NORMAL_BM32))
         return set_err(h, HDP_ERR_UNSUPPORTED, "normal_mode %d not supported for this element type", cfg->normal_mode);
+    const int gs = cfg->group_size;
+    if (gs != 0 && gs != 1 && gs != 2 && gs != 4 && gs != 8 && gs != 16 && gs != 32)
+        return set_err(h, HDP_ERR_BAD_ARG, "group_size = %d: must be 0 (automatic), 1, 2, 4, 8, 16 or 32", gs);
+    if (cfg->mem_flags & ~(unsigned)(HDP_MEM_DEVICE | HDP_ASYNC))
+        return set_err(h, HDP_ERR_BAD_ARG, "mem_flags = %u", cfg->mem_flags);
+    const bool on_device = (cfg->mem_flags & HDP_MEM_DEVICE) != 0;
+    const bool async = on_device && (cfg->mem_flags & HDP_ASYNC) != 0;
     const bool nonlocal = cfg->sampler.kind != HDP_SAMPLER_NONE;
     const bool f_nonlocal = (prob->f_kind >= HDP_F_NL_FIRST && prob->f_kind < HDP_F_USER) || prob->f_kind == HDP_F_NL_USER;
     if (f_nonlocal && !nonlocal)
@@ -176,8 +258,17 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
         if (compat) compat_counts(tab, compat, &stats->per_solve.path_steps, &stats->per_solve.time_uniforms,
                                   &stats->per_solve.sampler_calls);
     }
+    T* se_out = (T*)cfg->std_err_out;
     if (L == 0) { // `_ml_picard` returns zero(elxType) (src/MLP.jl:117-119)
-        for (int i = 0; i < n_solves; ++i) u_out[i] = (T)0;
+        if (on_device) {
+            HDP_CUDA(h, cudaMemsetAsync(u_out, 0, (size_t)n_solves * sizeof(T), h->stream));
+            if (se_out) HDP_CUDA(h, cudaMemsetAsync(se_out, 0, (size_t)n_solves * sizeof(T), h->stream));
+            if (!async) HDP_CUDA(h, cudaStreamSynchronize(h->stream));
+        } else
+            for (int i = 0; i < n_solves; ++i) {
+                u_out[i] = (T)0;
+                if (se_out) se_out[i] = (T)0;
+            }
         return HDP_OK;
     }
 
@@ -185,15 +276,19 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
     const int d = prob->d;
     const int nvec = (d + VEC - 1) / VEC;
     const double min_unit = 8.0; // smallest work unit (path-steps + half the sampler calls)
-    const int G = pick_group(nvec, tab.W[L] * (double)n_solves, n_solves, (double)h->prop.multiProcessorCount);
+    const int sms = h->prop.multiProcessorCount;
+    const int nranks = h->nccl_comm ? h->nccl_nranks : 1;
+    const int rank = h->nccl_comm ? h->nccl_rank : 0;
+    // a sharded solve is in the latency regime by construction: the work of one rank decides the lane-group width
+    const int G = pick_group(gs, nvec, tab.W[L] * (double)n_solves / nranks, n_solves, (double)sms);
     const MlpLaunchers<T> LN = launchers_for<T>(G);
     if (!LN.units[0][0]) return set_err(h, HDP_ERR_UNSUPPORTED, "no kernel for group size %d", G);
     const int mode = em_mode_of<T>(P.pb, cfg->n_tape != nullptr); // the units kernel compiled for this mode
     UserModule* um = nullptr;
     if (uses_user && (rc = get_user_module(h, prob, cfg->user, sizeof(T) == 4, G, &um)) != HDP_OK) return rc;
     const int block = HDP_MLP_BLOCK;
-    // dynamic shared memory of the units kernel: one Frame<T> per lane group (k_mlp.cuh, run_unit_iter)
-    const size_t dyn_smem = (size_t)(block / G) * sizeof(Frame<T>);
+    // dynamic shared memory of the units kernel: one private Frame<T> per thread (k_mlp.cuh, run_unit_iter)
+    const size_t dyn_smem = (size_t)block * sizeof(Frame<T>);
     // long rows: three vec-groups per pass (Tune<U>, k_mlp.cuh)
     const int long_rows = (nvec + G - 1) / G >= 12 ? 1 : 0;
     int bps = 0;
@@ -204,18 +299,13 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
         }
     } else bps = LN.max_blocks_per_sm[long_rows][mode](block, dyn_smem);
     if (bps < 1) return set_err(h, HDP_ERR_CUDA, "occupancy query failed for the MLP kernel");
-    const int sms = h->prop.multiProcessorCount;
-    const int nranks = h->nccl_comm ? h->nccl_nranks : 1;
-    const int rank = h->nccl_comm ? h->nccl_rank : 0;
 
     // ---- cut the tree: at most `thresh` work per unit ----
     const double resident_groups = (double)sms * bps * block / G;
-    // units per resident lane group: enough for the LPT-ordered dynamic fetch to balance, few
-    // enough that the replicated expand/combine passes and the all-reduce stay small
-    // (measured, C4 L=5: 1 GPU best at 8; 8 GPUs: 2 per rank gives 0.9 M units and 3.7x, 8 per rank
-    // cuts one level deeper — 16 M units — and the all-reduce + combine then dominate)
-    double oversub = nranks > 1 ? 2.0 : 8.0;
-    if (const char* ev = getenv("HDP_MLP_OVERSUB")) oversub = std::max(1.0, atof(ev));
+    // units per resident lane group (cfg->unit_oversub): enough for the LPT-ordered dynamic fetch to balance.
+    // On one GPU 8 (measured, C4 L=5).  A sharded solve exchanges one double per crown node, whatever the
+    // number of units below, so it can afford the same fine cut per rank.
+    double oversub = cfg->unit_oversub > 0 ? std::max(1.0, cfg->unit_oversub) : 8.0;
     double target = cfg->target_units > 0 ? (double)cfg->target_units : resident_groups * oversub * nranks;
     const double total_work = tab.W[L] * (double)n_solves;
     double thresh = total_work / target;
@@ -227,7 +317,10 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
         thresh = thresh >= tab.W[L] ? tab.W[L] : std::max(min_unit, q);
     }
     std::shared_ptr<MlpPlan> plan;
-    if ((rc = get_plan(h, M, L, K, nonlocal, thresh, compat, &plan)) != HDP_OK) return rc;
+    std::string plan_key;
+    if ((rc = get_plan(h, M, L, K, nonlocal, thresh, compat, &plan, &plan_key)) != HDP_OK) return rc;
+    std::shared_ptr<MlpSharding> sh;
+    if (nranks > 1 && (rc = get_sharding(h, plan_key, *plan, nranks, rank, &sh)) != HDP_OK) return rc;
 
     if (!draw_address_ok(HDP_STREAM_STEP, tab.C[L] + 1, (u64)nvec) || !draw_address_ok(HDP_STREAM_SAMPLER, tab.S[L] + 1, (u64)nvec))
         return set_err(h, HDP_ERR_BAD_ARG, "MLP: more than 2^40 path-steps per solve or 2^21 vec-groups per point");
@@ -244,7 +337,8 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
     P.n_solves = n_solves;
     P.n_x0 = cfg->n_x0;
     P.units = (const PlanUnit*)plan->d_units;
-    P.exec = (const int32_t*)plan->d_exec;
+    P.exec = sh ? (const int32_t*)sh->d_exec_own : (const int32_t*)plan->d_exec;
+    P.n_exec = sh ? (int)sh->exec_own.size() : (int)plan->units.size();
     P.unit_tag = (const int8_t*)plan->d_unit_tag;
     P.nodes = (const PlanNode*)plan->d_nodes;
     P.sites = (const PlanSite*)plan->d_sites;
@@ -262,12 +356,10 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
     P.flags = h->d_flags;
 
     // ---- launch geometry of the unit kernel ----
-    const uint64_t n_work = (uint64_t)P.n_units * (uint64_t)n_solves;
-    const uint64_t n_local = n_work > (uint64_t)rank ? (n_work - rank + nranks - 1) / nranks : 0;
+    const uint64_t n_local = (uint64_t)P.n_exec * (uint64_t)n_solves;
     const uint64_t groups_per_block = block / G;
     uint64_t want_blocks = (n_local + groups_per_block - 1) / groups_per_block;
     int grid = (int)std::min<uint64_t>(std::max<uint64_t>(want_blocks, 1), (uint64_t)sms * bps);
-    // the expand kernel is launched with one group per (site, solve); size scratch for the larger
     P.total_threads = (uint64_t)grid * block;
 
     // ---- per-call device state ----
@@ -278,30 +370,72 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
     double* d_partial = (double*)ensure(h, hdp_context::B_D, (size_t)n_solves * P.n_units * sizeof(double));
     T* d_value = (T*)ensure(h, hdp_context::B_G, (size_t)n_solves * P.n_nodes * sizeof(T));
     T* d_scratch = (T*)ensure(h, hdp_context::B_H, (size_t)(2 * L) * P.npl * P.total_threads * VEC * sizeof(T));
-    T* d_x0 = (T*)ensure(h, hdp_context::B_I, (size_t)cfg->n_x0 * d * sizeof(T));
-    if (!d_points || !d_feat || !d_site_r || !d_partial || !d_value || !d_scratch || !d_x0) return HDP_ERR_ALLOC;
+    if (!d_points || !d_feat || !d_site_r || !d_partial || !d_value || !d_scratch) return HDP_ERR_ALLOC;
+    const T* d_x0 = x0;
+    if (!on_device) {
+        T* buf = (T*)ensure(h, hdp_context::B_I, (size_t)cfg->n_x0 * d * sizeof(T));
+        if (!buf) return HDP_ERR_ALLOC;
+        d_x0 = buf;
+    }
     P.points = d_points; P.feat = d_feat; P.site_r = d_site_r; P.partial = d_partial; P.value = d_value;
     P.scratch = d_scratch;
+
+    // error bar: per root unit (or per root level when the solve is one unit) a (sum, sum of squares) pair
+    const bool want_se = se_out != nullptr;
+    T* d_se = nullptr;
+    if (want_se) {
+        const PlanNode& root = plan->nodes[0];
+        P.rootsq_stride = 2 * std::max(root.unit_end - root.unit_begin, L + 1);
+        P.rootsq = (double*)ensure(h, hdp_context::B_M, (size_t)n_solves * P.rootsq_stride * sizeof(double));
+        P.lvstat = (double*)ensure(h, hdp_context::B_O, (size_t)n_solves * 3 * (kMaxL + 1) * sizeof(double));
+        d_se = on_device ? se_out : (T*)ensure(h, hdp_context::B_P, (size_t)n_solves * sizeof(T));
+        if (!P.rootsq || !P.lvstat || !d_se) return HDP_ERR_ALLOC;
+        P.std_err = d_se;
+    }
+    // exchange buffer of a sharded solve: one double per crown node and solve, the root statistics, the call tail
+    size_t x_count = 0;
+    uint64_t my_hash = 0;
+    if (sh) {
+        P.unit_mine = (const int8_t*)sh->d_unit_mine;
+        P.site_cls = (const int8_t*)sh->d_site_cls;
+        P.node_slot = (const int32_t*)sh->d_node_slot;
+        P.n_slots = sh->n_slots;
+        P.xstride = sh->n_slots + 3 * (kMaxL + 1);
+        x_count = (size_t)n_solves * P.xstride + kXTail;
+        P.xbuf = (double*)ensure(h, hdp_context::B_Q, x_count * sizeof(double));
+        if (!P.xbuf) return HDP_ERR_ALLOC;
+        my_hash = call_hash<T>(prob, cfg, on_device ? nullptr : x0, P.n_units, thresh);
+    }
 
     if (taped) {
         uint64_t nC = tab.C[L], nR = tab.R[L], nS = tab.S[L];
         if (compat) compat_counts(tab, compat, &nC, &nR, &nS);
-        T* tr = (T*)ensure(h, hdp_context::B_J, std::max<size_t>(nR, 1) * sizeof(T));
-        T* tn = (T*)ensure(h, hdp_context::B_K, (size_t)nC * d * sizeof(T));
-        T* ts = (T*)ensure(h, hdp_context::B_L, std::max<size_t>((size_t)nS * d, 1) * sizeof(T));
-        if (!tr || !tn || !ts) return HDP_ERR_ALLOC;
-        HDP_CUDA(h, cudaMemcpyAsync(tr, cfg->r_tape, (size_t)nR * sizeof(T), cudaMemcpyHostToDevice, h->stream));
-        HDP_CUDA(h, cudaMemcpyAsync(tn, cfg->n_tape, (size_t)nC * d * sizeof(T), cudaMemcpyHostToDevice, h->stream));
-        if (nonlocal)
-            HDP_CUDA(h, cudaMemcpyAsync(ts, cfg->s_tape, (size_t)nS * d * sizeof(T), cudaMemcpyHostToDevice, h->stream));
-        P.r_tape = tr; P.n_tape = tn; P.s_tape = nonlocal ? ts : nullptr;
+        if (on_device) {
+            P.r_tape = (const T*)cfg->r_tape; P.n_tape = (const T*)cfg->n_tape;
+            P.s_tape = nonlocal ? (const T*)cfg->s_tape : nullptr;
+        } else {
+            T* tr = (T*)ensure(h, hdp_context::B_J, std::max<size_t>(nR, 1) * sizeof(T));
+            T* tn = (T*)ensure(h, hdp_context::B_K, (size_t)nC * d * sizeof(T));
+            T* ts = (T*)ensure(h, hdp_context::B_L, std::max<size_t>((size_t)nS * d, 1) * sizeof(T));
+            if (!tr || !tn || !ts) return HDP_ERR_ALLOC;
+            HDP_CUDA(h, cudaMemcpyAsync(tr, cfg->r_tape, (size_t)nR * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+            HDP_CUDA(h, cudaMemcpyAsync(tn, cfg->n_tape, (size_t)nC * d * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+            if (nonlocal)
+                HDP_CUDA(h, cudaMemcpyAsync(ts, cfg->s_tape, (size_t)nS * d * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+            P.r_tape = tr; P.n_tape = tn; P.s_tape = nonlocal ? ts : nullptr;
+        }
     }
 
     const int launches0 = h->launches;
-    HDP_CUDA(h, cudaMemcpyAsync(d_x0, x0, (size_t)cfg->n_x0 * d * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    double tail_host[kXTail] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (!on_device)
+        HDP_CUDA(h, cudaMemcpyAsync((void*)d_x0, x0, (size_t)cfg->n_x0 * d * sizeof(T), cudaMemcpyHostToDevice, h->stream));
     HDP_CUDA(h, cudaMemsetAsync(h->d_ctr, 0, 2 * sizeof(unsigned long long), h->stream));
-    if (nranks > 1)
-        HDP_CUDA(h, cudaMemsetAsync(d_partial, 0, (size_t)n_solves * P.n_units * sizeof(double), h->stream));
+    if (sh) {
+        for (int q = 0; q < 4; ++q) tail_host[q] = (double)((my_hash >> (16 * q)) & 0xffffu);
+        HDP_CUDA(h, cudaMemcpyAsync(P.xbuf + (size_t)n_solves * P.xstride, tail_host, sizeof(tail_host),
+                                    cudaMemcpyHostToDevice, h->stream));
+    }
     HDP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     {
         uint64_t tot = (uint64_t)n_solves * P.dpad;
@@ -310,22 +444,54 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
         h->launches++;
         HDP_CUDA(h, cudaGetLastError());
     }
-    // top-down geometry of the explicit sites
-    for (int dep = 0; dep <= plan->max_depth; ++dep) {
-        const int off = plan->site_depth_off[dep];
-        const int cnt = plan->site_depth_off[dep + 1] - off;
-        if (cnt == 0) continue;
+    auto launch_expand = [&](const int32_t* list, int cnt, int count_hits) -> int {
+        if (cnt == 0) return HDP_OK;
         uint64_t groups = (uint64_t)cnt * n_solves;
         int ge = (int)((groups * G + block - 1) / block);
         if (um) {
-            int off_ = off, cnt_ = cnt;
-            void* args[3] = {(void*)&P, (void*)&off_, (void*)&cnt_};
+            void* args[4] = {(void*)&P, (void*)&list, (void*)&cnt, (void*)&count_hits};
             HDP_CUDA(h, cudaLaunchKernel((const void*)um->expand, dim3(ge), dim3(block), args, 0, h->stream));
-        } else HDP_CUDA(h, LN.expand(P, off, cnt, ge, block, h->stream));
+        } else HDP_CUDA(h, LN.expand(P, list, cnt, count_hits, ge, block, h->stream));
         h->launches++;
+        return HDP_OK;
+    };
+    // lanes per (node, solve) of a combine launch: a warp where some node has many children, 4 lanes otherwise
+    auto launch_combine = [&](const int32_t* list, const int32_t* host_list, int cnt, int cmode) -> int {
+        if (cnt == 0) return HDP_OK;
+        int most = 0;
+        for (int q = 0; q < cnt; ++q) {
+            const PlanNode& nd = plan->nodes[host_list[q]];
+            most = std::max(most, (nd.unit_end - nd.unit_begin) + (nd.site_end - nd.site_begin));
+        }
+        int nl = most > 16 ? 32 : 4;
+        uint64_t tot = (uint64_t)cnt * n_solves * nl;
+        int gc = (int)((tot + 127) / 128);
+        if (um) { // f is applied in the combine too: the user module's build of it
+            void* args[5] = {(void*)&P, (void*)&list, (void*)&cnt, (void*)&nl, (void*)&cmode};
+            HDP_CUDA(h, cudaLaunchKernel((const void*)um->combine, dim3(gc), dim3(128), args, 0, h->stream));
+        } else mlp_combine_kernel<T><<<gc, 128, 0, h->stream>>>(P, list, cnt, nl, cmode);
+        h->launches++;
+        HDP_CUDA(h, cudaGetLastError());
+        return HDP_OK;
+    };
+    // ---- top-down geometry of the explicit sites ----
+    if (!sh) {
+        for (int dep = 0; dep <= plan->max_depth; ++dep) {
+            const int off = plan->site_depth_off[dep];
+            if ((rc = launch_expand(P.sites_by_depth + off, plan->site_depth_off[dep + 1] - off, 1)) != HDP_OK) return rc;
+        }
+    } else {
+        // the upper sites on every rank (rank 0 counts their wall hits), then the bottom sites this rank owns
+        for (int dep = 0; dep <= plan->max_depth; ++dep) {
+            const int off = sh->upper_depth_off[dep];
+            if ((rc = launch_expand((const int32_t*)sh->d_upper_sites + off, sh->upper_depth_off[dep + 1] - off,
+                                    rank == 0 ? 1 : 0)) != HDP_OK)
+                return rc;
+        }
+        if ((rc = launch_expand((const int32_t*)sh->d_own_bottom_sites, (int)sh->own_bottom_sites.size(), 1)) != HDP_OK) return rc;
     }
     HDP_CUDA(h, cudaEventRecord(h->evp[0], h->stream));
-    // the work units
+    // ---- the work units ----
     if (n_local > 0) {
         if (um) {
             void* args[1] = {(void*)&P};
@@ -334,42 +500,70 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
         h->launches++;
     }
     HDP_CUDA(h, cudaEventRecord(h->evp[1], h->stream));
-    if (nranks > 1) {
-        rc = nccl_allreduce_f64_device(h, d_partial, (size_t)n_solves * P.n_units);
-        if (rc != HDP_OK) return rc;
-    }
-    HDP_CUDA(h, cudaEventRecord(h->evp[2], h->stream));
-    // bottom-up combine
-    for (int dep = plan->max_depth; dep >= 0; --dep) {
-        const int off = plan->node_depth_off[dep];
-        const int cnt = plan->node_depth_off[dep + 1] - off;
-        if (cnt == 0) continue;
-        // lanes per (node, solve): a warp where some node of this depth has many children, 4 lanes otherwise
-        int most = 0;
-        for (int q = off; q < off + cnt; ++q) {
-            const PlanNode& nd = plan->nodes[plan->nodes_by_depth[q]];
-            most = std::max(most, (nd.unit_end - nd.unit_begin) + (nd.site_end - nd.site_begin));
+    if (!sh) {
+        HDP_CUDA(h, cudaEventRecord(h->evp[2], h->stream));
+        // ---- bottom-up combine ----
+        for (int dep = plan->max_depth; dep >= 0; --dep) {
+            const int off = plan->node_depth_off[dep];
+            if ((rc = launch_combine(P.nodes_by_depth + off, plan->nodes_by_depth.data() + off,
+                                     plan->node_depth_off[dep + 1] - off, CMB_ALL)) != HDP_OK)
+                return rc;
         }
-        int nl = most > 16 ? 32 : 4;
-        uint64_t tot = (uint64_t)cnt * n_solves * nl;
-        int gc = (int)((tot + 127) / 128);
-        if (um) { // f is applied in the combine too: the user module's build of it
-            int off_ = off, cnt_ = cnt;
-            void* args[4] = {(void*)&P, (void*)&off_, (void*)&cnt_, (void*)&nl};
-            HDP_CUDA(h, cudaLaunchKernel((const void*)um->combine, dim3(gc), dim3(128), args, 0, h->stream));
-        } else mlp_combine_kernel<T><<<gc, 128, 0, h->stream>>>(P, off, cnt, nl);
-        h->launches++;
-        HDP_CUDA(h, cudaGetLastError());
+    } else {
+        // the calls below this rank's bottom sites, then this rank's share of every crown node
+        if ((rc = launch_combine((const int32_t*)sh->d_owned_nodes, sh->owned_nodes.data(), (int)sh->owned_nodes.size(),
+                                 CMB_ALL)) != HDP_OK)
+            return rc;
+        if ((rc = launch_combine((const int32_t*)sh->d_crown_nodes, sh->crown_nodes.data(), (int)sh->crown_nodes.size(),
+                                 CMB_PARTIAL)) != HDP_OK)
+            return rc;
+        HDP_CUDA(h, cudaEventRecord(h->evp[1], h->stream)); // (the local combine counts as unit work)
+        rc = nccl_allreduce_f64_device(h, P.xbuf, x_count);
+        if (rc != HDP_OK) return rc;
+        HDP_CUDA(h, cudaEventRecord(h->evp[2], h->stream));
+        if (!sh->crown_leaves.empty()) {
+            const int cnt = (int)sh->crown_leaves.size();
+            const uint64_t tot = (uint64_t)cnt * n_solves;
+            mlp_scatter_kernel<T><<<(int)((tot + 127) / 128), 128, 0, h->stream>>>(P, (const int32_t*)sh->d_crown_leaves, cnt);
+            h->launches++;
+            HDP_CUDA(h, cudaGetLastError());
+        }
+        for (int dep = plan->max_depth; dep >= 0; --dep) {
+            const int off = sh->crown_final_off[dep];
+            if ((rc = launch_combine((const int32_t*)sh->d_crown_final + off, sh->crown_final.data() + off,
+                                     sh->crown_final_off[dep + 1] - off, CMB_FINAL)) != HDP_OK)
+                return rc;
+        }
     }
     HDP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
-    // root values: value[solve][0]
+    // ---- results: value[solve][0] ----
     HDP_CUDA(h, cudaMemcpy2DAsync(u_out, sizeof(T), d_value, (size_t)P.n_nodes * sizeof(T), sizeof(T), n_solves,
-                                  cudaMemcpyDeviceToHost, h->stream));
+                                  on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+    if (want_se && !on_device)
+        HDP_CUDA(h, cudaMemcpyAsync(se_out, d_se, (size_t)n_solves * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+    if (stats) {
+        stats->n_units = P.n_units;
+        stats->n_nodes = P.n_nodes;
+        stats->n_sites = P.n_sites;
+        stats->group_size = G;
+        stats->n_launches = h->launches - launches0;
+        stats->exchange_bytes = x_count * sizeof(double);
+    }
+    if (async) return HDP_OK; // a start point outside the box surfaces at hdp_sync
     int flags2[2] = {0, 0}; // [0] start point outside the box, [1] kernel / mode mismatch (internal)
     int& flag = flags2[0];
     unsigned long long ctr[2] = {0, 0};
+    double lv0[3 * (kMaxL + 1)];
+    T se0 = (T)0;
     HDP_CUDA(h, cudaMemcpyAsync(flags2, h->d_flags, sizeof(flags2), cudaMemcpyDeviceToHost, h->stream));
     HDP_CUDA(h, cudaMemcpyAsync(ctr, h->d_ctr, sizeof(ctr), cudaMemcpyDeviceToHost, h->stream));
+    if (sh)
+        HDP_CUDA(h, cudaMemcpyAsync(tail_host, P.xbuf + (size_t)n_solves * P.xstride, sizeof(tail_host),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    if (want_se && stats) {
+        HDP_CUDA(h, cudaMemcpyAsync(lv0, P.lvstat, sizeof(lv0), cudaMemcpyDeviceToHost, h->stream));
+        HDP_CUDA(h, cudaMemcpyAsync(&se0, d_se, sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+    }
     HDP_CUDA(h, cudaStreamSynchronize(h->stream));
     if (stats) {
         float ms = 0;
@@ -382,15 +576,25 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
             stats->phase_ms[i] = pm;
         }
         stats->bounces = ctr[1];
-        stats->n_units = P.n_units;
-        stats->n_nodes = P.n_nodes;
-        stats->n_sites = P.n_sites;
-        stats->group_size = G;
-        stats->n_launches = h->launches - launches0;
+        if (want_se) {
+            for (int l = 0; l <= L; ++l) {
+                stats->level_n[l] = (uint64_t)(lv0[3 * l] + 0.5);
+                stats->level_sum[l] = lv0[3 * l + 1];
+                stats->level_sumsq[l] = lv0[3 * l + 2];
+            }
+            stats->std_error = (double)se0;
+        }
     }
     if (flags2[1]) {
         cudaMemsetAsync(h->d_flags, 0, sizeof(flags2), h->stream);
         return set_err(h, HDP_ERR_UNSUPPORTED, "internal: the units kernel launched does not match the mode of the problem");
+    }
+    if (sh) { // every rank must have described the same call: the all-reduced hash is nranks times mine
+        for (int q = 0; q < 4; ++q)
+            if (tail_host[q] != (double)nranks * (double)((my_hash >> (16 * q)) & 0xffffu))
+                return set_err(h, HDP_ERR_BAD_ARG,
+                               "sharded MLP solve: the ranks disagree on seed, configuration, problem or start points "
+                               "(every rank must pass the same arguments; draw the seed once and broadcast it)");
     }
     if (flag) {
         cudaMemsetAsync(h->d_flags, 0, sizeof(int), h->stream);

@@ -104,6 +104,7 @@ sde_loop_kernel(DevProblem<T> pb, T* __restrict__ y0, T* __restrict__ y1, size_t
     bool bad = false;
     int nb_total = 0;
     const DrawK<T> dk = draw_k_init<T>(zero);
+    [[maybe_unused]] const uint32_t far = sym_far_bits<T>(pb.hi_s);
     for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (size_t)gridDim.x * blockDim.x) {
         const size_t q0 = v * VEC;
         const int i0 = n_el <= 0xffffffffull ? (int)((uint32_t)q0 % (uint32_t)d) : (int)(q0 % (size_t)d);
@@ -147,7 +148,7 @@ sde_loop_kernel(DevProblem<T> pb, T* __restrict__ y0, T* __restrict__ y1, size_t
 #pragma unroll
                     for (int e = 0; e < VEC; ++e)
                         cur.v[e] = add_rn(add_rn(prev.v[e], mudt_c), mul_rn(sgsq_c, xs[u].v[e])); // :160
-                    if constexpr (BC == K1_SYM) reflect_vec_sym<T, false>(cur, pb.hi_s, nb_total); // :161-163
+                    if constexpr (BC == K1_SYM) reflect_vec_sym<T, false>(cur, pb.hi_s, far, nb_total); // :161-163
                 }
             }
         }
@@ -180,7 +181,7 @@ sde_loop_kernel(DevProblem<T> pb, T* __restrict__ y0, T* __restrict__ y1, size_t
 #pragma unroll
                     for (int e = 0; e < VEC; ++e)
                         cur.v[e] = add_rn(add_rn(prev.v[e], mudt_c), mul_rn(sgsq_c, xi.v[e])); // :160
-                    if constexpr (BC == K1_SYM) reflect_vec_sym<T, false>(cur, pb.hi_s, nb_total); // :161-163
+                    if constexpr (BC == K1_SYM) reflect_vec_sym<T, false>(cur, pb.hi_s, far, nb_total); // :161-163
                 }
             }
         };

@@ -69,9 +69,12 @@ struct Builder {
     double thresh;
     int compat;
     std::vector<double> unit_cost;
+    size_t max_units = 0; // 0: no limit
+    bool overflow = false;
 
     void add_unit(int node, int kind, int l, int64_t k0, int64_t k1, uint64_t c, uint64_t r, uint64_t s, double cost)
     {
+        if (max_units && p->units.size() >= max_units) { overflow = true; return; }
         PlanUnit u{};
         u.node = node; u.kind = kind; u.l = l; u.k0 = k0; u.k1 = k1; u.c = c; u.r = r; u.s = s;
         p->units.push_back(u);
@@ -157,7 +160,7 @@ struct Builder {
         p->nodes[id].site_begin = site_begin; p->nodes[id].site_end = site_end;
         // children of the explicit sites (consumption order inside a site:
         // r, step, U_l(x2), [U_{l-1}(x2)], then per h: sample, U_l(x3), [U_{l-1}(x3)])
-        for (int si = site_begin; si < site_end; ++si) {
+        for (int si = site_begin; si < site_end && !overflow; ++si) {
             const PlanSite st = p->sites[si];
             const int l = st.l;
             uint64_t c = st.c + 1, r = st.r + 1, s = st.s;
@@ -187,7 +190,7 @@ struct Builder {
 };
 } // namespace
 
-void mlp_build_plan(int M, int L, int K, bool nonlocal, double thresh, int compat_threads, MlpPlan* plan)
+bool mlp_build_plan(int M, int L, int K, bool nonlocal, double thresh, int compat_threads, MlpPlan* plan, size_t max_units)
 {
     mlp_count_tables(M, L, K, nonlocal, &plan->tab);
     plan->thresh = thresh;
@@ -196,7 +199,10 @@ void mlp_build_plan(int M, int L, int K, bool nonlocal, double thresh, int compa
     plan->n_points = 1;
     plan->max_depth = 0;
     Builder b{plan, plan->tab, thresh, compat_threads, {}};
+    b.max_units = max_units;
     b.build_node(L, 0, -1, 0, 0, 0, 0, true);
+    if (b.overflow) return false; // the cut is finer than the caller can hold: try a coarser one
+    plan->unit_cost.assign(b.unit_cost.begin(), b.unit_cost.end());
     plan->unit_tag.resize(plan->units.size());
     for (size_t i = 0; i < plan->units.size(); ++i)
         plan->unit_tag[i] = (int8_t)((plan->units[i].kind << 4) | (plan->units[i].l & 15));
@@ -230,6 +236,113 @@ void mlp_build_plan(int M, int L, int K, bool nonlocal, double thresh, int compa
     for (size_t i = 0; i < plan->sites.size(); ++i) plan->sites_by_depth[so[plan->sites[i].depth]++] = (int32_t)i;
     for (size_t i = 0; i < plan->nodes.size(); ++i)
         if (needs_combine(i)) plan->nodes_by_depth[no[plan->nodes[i].depth]++] = (int32_t)i;
+    return true;
+}
+
+
+// ---------------------------------------------------------------------
+// sharding of one plan over several ranks (see MlpSharding in mlp_plan.h)
+// ---------------------------------------------------------------------
+void mlp_build_sharding(const MlpPlan& plan, int nranks, int rank, MlpSharding* out)
+{
+    const int n_nodes = (int)plan.nodes.size(), n_sites = (int)plan.sites.size(), n_units = (int)plan.units.size();
+    const int Kp = plan.tab.Kp;
+    const int nch = 2 * (1 + Kp);
+    out->nranks = nranks; out->rank = rank;
+    auto is_leaf = [&](int n) {
+        const PlanNode& nd = plan.nodes[n];
+        return nd.unit_end - nd.unit_begin == 1 && nd.site_end == nd.site_begin && plan.units[nd.unit_begin].kind == UNIT_WHOLE;
+    };
+    // explicit child nodes of a site: the entries of children[] that name a node; a whole-call leaf is named by
+    // its unit there (-2 - unit), so map units of leaves back to their node
+    std::vector<int32_t> leaf_of_unit(n_units, -1);
+    for (int n = 0; n < n_nodes; ++n)
+        if (is_leaf(n)) leaf_of_unit[plan.nodes[n].unit_begin] = n;
+    auto child_node = [&](int32_t code) -> int { return code >= 0 ? code : (code == -1 ? -1 : leaf_of_unit[-2 - code]); };
+    // bottom site: no child call has explicit sites of its own
+    std::vector<int8_t> bottom(n_sites, 1);
+    for (int si = 0; si < n_sites; ++si)
+        for (int q = 0; q < nch; ++q) {
+            const int32_t code = plan.children[plan.sites[si].child0 + q];
+            if (code >= 0 && plan.nodes[code].site_end > plan.nodes[code].site_begin) bottom[si] = 0;
+        }
+    // crown nodes: the root, and every child of an upper site
+    std::vector<int8_t> crown(n_nodes, 0);
+    std::vector<int32_t> owner_site(n_nodes, -1); // for nodes below a bottom site: that site
+    crown[0] = 1;
+    for (int si = 0; si < n_sites; ++si) // sites are created parent-first, so crown[] of the parent is final here
+        for (int q = 0; q < nch; ++q) {
+            const int cn = child_node(plan.children[plan.sites[si].child0 + q]);
+            if (cn < 0) continue;
+            if (bottom[si]) owner_site[cn] = si;
+            else crown[cn] = 1;
+        }
+    // items to balance: bottom sites (with everything below them) and the units attached to crown nodes
+    struct Item { double cost; int kind, id; }; // kind 0: bottom site, 1: crown-attached unit
+    std::vector<Item> items;
+    for (int si = 0; si < n_sites; ++si)
+        if (bottom[si]) items.push_back({plan.tab.Ws[plan.sites[si].l], 0, si});
+    std::vector<int32_t> node_of_unit(n_units, 0);
+    for (int n = 0; n < n_nodes; ++n)
+        for (int u = plan.nodes[n].unit_begin; u < plan.nodes[n].unit_end; ++u) node_of_unit[u] = n;
+    for (int u = 0; u < n_units; ++u)
+        if (crown[node_of_unit[u]]) items.push_back({(double)plan.unit_cost[u], 1, u});
+    std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.cost > b.cost; });
+    std::vector<double> load(nranks, 0.0);
+    std::vector<int32_t> site_owner(n_sites, -1), unit_owner(n_units, -1);
+    int rr = 0;
+    for (const Item& it : items) { // longest first, each to the least loaded rank (ties: round robin)
+        int best = rr % nranks;
+        for (int q = 0; q < nranks; ++q) {
+            const int r = (rr + q) % nranks;
+            if (load[r] < load[best]) best = r;
+        }
+        ++rr;
+        load[best] += it.cost;
+        if (it.kind == 0) site_owner[it.id] = best;
+        else unit_owner[it.id] = best;
+    }
+    for (int u = 0; u < n_units; ++u)
+        if (unit_owner[u] < 0) unit_owner[u] = site_owner[owner_site[node_of_unit[u]]];
+    out->load_max = *std::max_element(load.begin(), load.end());
+    out->load_mean = std::accumulate(load.begin(), load.end(), 0.0) / nranks;
+    // per-rank lists
+    out->unit_mine.assign(n_units, 0);
+    out->exec_own.clear();
+    for (int32_t u : plan.exec_order)
+        if (unit_owner[u] == rank) { out->exec_own.push_back(u); out->unit_mine[u] = 1; }
+    out->site_cls.assign(n_sites, 0);
+    out->own_bottom_sites.clear();
+    for (int si = 0; si < n_sites; ++si) {
+        out->site_cls[si] = !bottom[si] ? 0 : (site_owner[si] == rank ? 1 : 2);
+        if (bottom[si] && site_owner[si] == rank) out->own_bottom_sites.push_back(si);
+    }
+    const int nd = plan.max_depth + 1;
+    out->upper_depth_off.assign(nd + 1, 0);
+    out->upper_sites.clear();
+    for (int dep = 0; dep < nd; ++dep) {
+        for (int q = plan.site_depth_off[dep]; q < plan.site_depth_off[dep + 1]; ++q)
+            if (!bottom[plan.sites_by_depth[q]]) out->upper_sites.push_back(plan.sites_by_depth[q]);
+        out->upper_depth_off[dep + 1] = (int32_t)out->upper_sites.size();
+    }
+    out->node_slot.assign(n_nodes, -1);
+    out->crown_nodes.clear(); out->crown_leaves.clear(); out->owned_nodes.clear();
+    out->n_slots = 0;
+    std::vector<std::vector<int32_t>> fin(nd);
+    for (int n = 0; n < n_nodes; ++n) {
+        if (crown[n]) {
+            out->node_slot[n] = out->n_slots++;
+            out->crown_nodes.push_back(n);
+            if (is_leaf(n)) out->crown_leaves.push_back(n);
+            if (!is_leaf(n) || n == 0) fin[plan.nodes[n].depth].push_back(n); // (a root that is one unit still gets its value)
+        } else if (!is_leaf(n) && site_owner[owner_site[n]] == rank) out->owned_nodes.push_back(n);
+    }
+    out->crown_final.clear();
+    out->crown_final_off.assign(nd + 1, 0);
+    for (int dep = 0; dep < nd; ++dep) {
+        out->crown_final.insert(out->crown_final.end(), fin[dep].begin(), fin[dep].end());
+        out->crown_final_off[dep + 1] = (int32_t)out->crown_final.size();
+    }
 }
 
 } // namespace hdp

@@ -38,6 +38,7 @@ struct MlpPlan {
     std::vector<PlanSite> sites;
     std::vector<PlanUnit> units;
     std::vector<int32_t> children;
+    std::vector<float> unit_cost;       // work model of each unit (path-steps + half the sampler calls)
     std::vector<int8_t> unit_tag;       // (kind << 4) | level, the only unit fields the combine pass reads
     std::vector<int32_t> exec_order;    // unit ids, most expensive first
     std::vector<int32_t> sites_by_depth;  // site ids grouped by depth
@@ -61,8 +62,45 @@ struct MlpPlan {
 // thresh: maximum work (path-steps + sampler calls) of one unit.
 // compat_threads > 0 reproduces the `_ml_picard_mlt` / `_get_loop_num`
 // enumeration of the root call (src/MLP.jl:218-404).
-void mlp_build_plan(int M, int L, int K, bool nonlocal, double thresh, int compat_threads, MlpPlan* plan);
+// max_units > 0: give up (return false, plan unusable) as soon as the cut needs more units than that.
+bool mlp_build_plan(int M, int L, int K, bool nonlocal, double thresh, int compat_threads, MlpPlan* plan,
+                    size_t max_units = 0);
 
 int64_t mlp_get_loop_num(int M, int64_t num, int thread_id, int nthreads);
+
+// One solve (or a small batch) sharded over `nranks` GPUs — the analogue of the reference's
+// `Threads.@spawn` / `fetch` / `sum` (src/MLP.jl:235-259), cut where a GPU needs it.
+//
+// f is nonlinear, so a site can only be finished where all its child values are complete.  The plan is
+// therefore split into a *crown* — the root, the *upper* sites (those with a child call that itself has
+// explicit sites) and the calls below them — which every rank holds, and the subtrees below the *bottom*
+// sites (all children whole-call leaves or calls made of slice units only), each of which belongs to ONE
+// rank: that rank generates its geometry, evaluates its units, combines its calls and applies f.  What
+// crosses the wire is linear: per crown node, this rank's share of the node's value (its slice units, the
+// f-terms of its bottom sites; the value of a whole-call leaf below an upper site) — one double per crown
+// node and solve, summed by a single ncclAllReduce.  The upper sites are then finished redundantly.
+struct MlpSharding {
+    int nranks = 1, rank = 0;
+    std::vector<int32_t> exec_own;            // units this rank evaluates, most expensive first
+    std::vector<int32_t> upper_sites;         // replicated sites grouped by depth
+    std::vector<int32_t> upper_depth_off;     // size max_depth+2
+    std::vector<int32_t> own_bottom_sites;    // this rank's bottom sites (any depth; one expand launch)
+    std::vector<int32_t> owned_nodes;         // slice-only calls below this rank's bottom sites (combine: CMB_ALL)
+    std::vector<int32_t> crown_nodes;         // every crown node, leaves included (combine: CMB_PARTIAL)
+    std::vector<int32_t> crown_leaves;        // whole-call leaves below upper sites (scatter after the all-reduce)
+    std::vector<int32_t> crown_final;         // crown nodes that are not leaves, grouped by depth (combine: CMB_FINAL)
+    std::vector<int32_t> crown_final_off;     // size max_depth+2
+    std::vector<int8_t> unit_mine;            // per unit
+    std::vector<int8_t> site_cls;             // per site: 0 upper, 1 bottom and mine, 2 bottom of another rank
+    std::vector<int32_t> node_slot;           // per node: slot in the exchange buffer, -1 below a bottom site
+    int n_slots = 0;
+    double load_max = 0, load_mean = 0;       // modelled work of the busiest rank / the mean
+    // device copies (owned by the handle's cache; freed in the destructor)
+    void *d_exec_own = nullptr, *d_upper_sites = nullptr, *d_own_bottom_sites = nullptr, *d_owned_nodes = nullptr,
+         *d_crown_nodes = nullptr, *d_crown_leaves = nullptr, *d_crown_final = nullptr, *d_unit_mine = nullptr,
+         *d_site_cls = nullptr, *d_node_slot = nullptr;
+    ~MlpSharding();
+};
+void mlp_build_sharding(const MlpPlan& plan, int nranks, int rank, MlpSharding* out);
 
 } // namespace hdp

@@ -7,7 +7,7 @@
 
 namespace hdp {
 
-constexpr int kMaxL = 6;
+constexpr int kMaxL = 6; // == HDP_MAX_LEVELS (include/hdpde.h)
 
 enum { UNIT_LEVEL = 0, UNIT_G = 1, UNIT_WHOLE = 2 };
 

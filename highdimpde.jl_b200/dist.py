@@ -50,6 +50,12 @@ def broadcast_bytes(data: bytes | None, n: int, src: int = 0) -> bytes:
     return bytes(t.cpu().tolist())
 
 
+def broadcast_int(v: int, src: int = 0) -> int:
+    """The same 64-bit integer on every rank (rank `src`'s) — e.g. the seed of a sharded solve."""
+    data = int(v).to_bytes(8, "little") if _dist().get_rank() == src else None
+    return int.from_bytes(broadcast_bytes(data, 8, src), "little")
+
+
 def gather_solves(local: np.ndarray, n: int) -> np.ndarray:
     """All ranks' per-solve results, concatenated in solve order."""
     parts = all_gather_object(np.asarray(local))

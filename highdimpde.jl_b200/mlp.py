@@ -33,10 +33,13 @@ def mlp_counts(M, L, K, nonlocal_=False, compat_mlt_threads=0) -> dict:
 
 
 def _ml_picard_batch(prob: _Problem, alg: MLP, *, n_solves=1, x0=None, seed=0, tapes=None,
-                     compat_mlt_threads=0, target_units=0, handle=None, dtype=None):
+                     compat_mlt_threads=0, target_units=0, handle=None, dtype=None, group_size=0,
+                     unit_oversub=0.0, std_err=False):
     """Runs n_solves independent MLP solves (seeds seed, seed+1, …) on the GPU.
     x0: None (prob.x), a d-vector, or a d×n_solves column-major matrix.
     tapes: optional (r_tape, n_tape, s_tape) in the reference's consumption order.
+    group_size / unit_oversub: launch tuning (0 = automatic; results do not depend on them).
+    std_err: also estimate the Monte-Carlo standard error of every solve (stats["std_err"]).
     Returns (u[n_solves], stats dict)."""
     h = handle or capi.default_handle()
     if not isinstance(prob.x0_sample, NoSampling):
@@ -61,6 +64,9 @@ def _ml_picard_batch(prob: _Problem, alg: MLP, *, n_solves=1, x0=None, seed=0, t
     cfg.normal_mode = capi.HDP_NORMAL_DEFAULT
     cfg.compat_mlt_threads = int(compat_mlt_threads)
     cfg.target_units = int(target_units)
+    cfg.group_size = int(group_size)
+    cfg.unit_oversub = float(unit_oversub)
+    cfg.mem_flags = capi.HDP_MEM_HOST
     cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     sm, keep2 = alg.mc_sample._descriptor(d)
     cfg.sampler = sm
@@ -80,6 +86,10 @@ def _ml_picard_batch(prob: _Problem, alg: MLP, *, n_solves=1, x0=None, seed=0, t
             tp.append(s_t)
             cfg.s_tape = s_t.ctypes.data
     u = np.empty(int(n_solves), dtype=dt)
+    se = None
+    if std_err:
+        se = np.zeros(int(n_solves), dtype=dt)
+        cfg.std_err_out = se.ctypes.data
     st = capi.hdp_mlp_stats()
     fn = h.lib.hdp_mlp_solve_f64 if dt == np.float64 else h.lib.hdp_mlp_solve_f32
     rc = fn(h.h, C.byref(pb), C.byref(cfg), capi.np_ptr(x), capi.np_ptr(u), C.byref(st))
@@ -90,7 +100,12 @@ def _ml_picard_batch(prob: _Problem, alg: MLP, *, n_solves=1, x0=None, seed=0, t
              "n_nodes": st.n_nodes, "n_sites": st.n_sites, "device_ms": st.device_ms,
              "group_size": st.group_size, "n_launches": st.n_launches,
              "phase_ms": {"expand": st.phase_ms[0], "units": st.phase_ms[1], "allreduce": st.phase_ms[2],
-                          "combine": st.phase_ms[3]}}
+                          "combine": st.phase_ms[3]},
+             "exchange_bytes": st.exchange_bytes}
+    if std_err:
+        L1 = alg.L + 1
+        stats.update({"std_err": se, "level_n": list(st.level_n[:L1]), "level_sum": list(st.level_sum[:L1]),
+                      "level_sumsq": list(st.level_sumsq[:L1])})
     del keep, keep2, tp
     return u, stats
 
@@ -111,6 +126,11 @@ def solve(prob, alg, *args, multithreading=True, verbose=False, seed=None, **kw)
     nt = int(kw.pop("julia_threads", 0))
     if seed is None:
         seed = int.from_bytes(os.urandom(8), "little")
+        h = kw.get("handle") or capi.default_handle()
+        if h.info()["nccl_nranks"] > 1:
+            # a solve sharded over several ranks: every rank must walk the same random tree
+            from . import dist
+            seed = dist.broadcast_int(seed)
     u, stats = _ml_picard_batch(prob, alg, n_solves=1, seed=seed,
                                 compat_mlt_threads=nt if multithreading else 0, **kw)
     usol = u[0].item()

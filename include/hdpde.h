@@ -128,7 +128,16 @@ enum {
     HDP_NORMAL_BM32 = 2      /* Box-Muller, 32-bit uniforms, fp32 MUFU transcendentals */
 };
 
-/* random streams (one Philox stream id per consumer).  Every draw is Philox4x32-10 with a fixed
+/* Rounds of the counter-based generator.  The reference draws from Julia's task-local
+ * Xoshiro256++ (`rand`, `randn!`: src/MLP.jl:132,416, src/DeepSplitting.jl:154), whose bit
+ * stream no reference test pins; the library's own stream is Philox4x32 with 7 rounds — the
+ * fewest that Salmon, Moraes, Dror, Shaw (SC'11, "Parallel random numbers: as easy as 1, 2, 3",
+ * table 2) report as passing BigCrush.  The oracle's Philox twin reads the same constant. */
+#ifndef HDP_PHILOX_ROUNDS
+#define HDP_PHILOX_ROUNDS 7
+#endif
+
+/* random streams (one Philox stream id per consumer).  Every draw is Philox4x32-R (R above) with a fixed
  * key at counter (w0, w1, seed_lo, seed_hi); (w0, w1) packs (stream, ordinal, group):
  * TIME/STEP/SAMPLER: ordinal < 2^40 (the reference's consumption ordinal), group < 2^21
  * (vec-group of a point); SDE/X0/MC: ordinal < 2^24 (step or sample index), group < 2^37
@@ -189,6 +198,8 @@ typedef struct hdp_user_exprs {
     const char* f;
 } hdp_user_exprs;
 
+#define HDP_MAX_LEVELS 6 /* largest L of MLP(M, L, K) the kernels are built for */
+
 /* MLP(M, L, K, mc_sample) (src/MLP.jl:24-32) plus the knobs a GPU needs. */
 typedef struct hdp_mlp_cfg {
     int32_t M, L, K;
@@ -207,6 +218,17 @@ typedef struct hdp_mlp_cfg {
      * All three NULL => counter-based Philox generated in registers. */
     const void *r_tape, *n_tape, *s_tape;
     const hdp_user_exprs* user; /* required iff the problem uses a *_USER kind, else NULL */
+    /* --- launch tuning (0 = automatic; results never depend on either) --- */
+    int32_t group_size;        /* lanes that own one path: 1, 2, 4, 8, 16 or 32                    */
+    uint32_t mem_flags;        /* HDP_MEM_DEVICE: x0, u_out, std_err_out and the tapes are device
+                                  pointers (CuArray); | HDP_ASYNC: enqueue only — stats then carry
+                                  only the host-side fields and errors surface at hdp_sync        */
+    double unit_oversub;       /* work units per resident lane group the tree is cut into          */
+    /* --- Monte-Carlo error bar (the reference returns none) --- */
+    void* std_err_out;         /* nullable, n_solves values of the entry point's element type: the
+                                  standard error of each solve, sqrt(sum_l Var_l / n_l) over the
+                                  root call's level sums and its g-term (their samples are i.i.d.
+                                  within a level, levels are independent)                          */
 } hdp_mlp_cfg;
 
 typedef struct hdp_mlp_counts {
@@ -228,6 +250,14 @@ typedef struct hdp_mlp_stats {
     int32_t n_launches;        /* kernels launched by this call                     */
     double phase_ms[4];        /* device time of: expand (top-down geometry), units,
                                   all-reduce of the partial sums, combine (bottom-up) */
+    /* root call of solve 0, filled when cfg->std_err_out is given: entry l < L is level l of
+     * `_ml_picard`'s outer loops (src/MLP.jl:126-196; samples b3/K, weight (t-s)/M^(L-l)), entry L
+     * the g-term (:198-205; samples g(x2), weight 1/M^L)                                         */
+    uint64_t level_n[HDP_MAX_LEVELS + 1];     /* samples taken                                     */
+    double level_sum[HDP_MAX_LEVELS + 1];     /* sum of the samples                                */
+    double level_sumsq[HDP_MAX_LEVELS + 1];   /* sum of their squares                              */
+    double std_error;                         /* of solve 0                                        */
+    uint64_t exchange_bytes;   /* bytes each rank hands to the all-reduce (0 on one GPU)           */
 } hdp_mlp_stats;
 
 typedef struct hdp_devinfo {

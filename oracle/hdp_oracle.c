@@ -40,17 +40,17 @@
 #endif
 
 /* ================================================================ */
-/* Philox4x32-10 (Salmon et al., SC'11), generic in counter and key.   */
+/* Philox4x32-R (Salmon et al., SC'11), generic in counter, key, rounds. */
 /* The CUDA library's draws use a FIXED key and carry the 64-bit seed   */
 /* in the counter: ctr = (w0, w1, seed_lo, seed_hi) with (w0, w1) the   */
 /* packed address (stream, ordinal, group) — see draw_address() in      */
 /* highdimpde.jl_b200/csrc/hdp_device.cuh.                              */
 /* ================================================================ */
-void hdp_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+void hdp_oracle_philox4x32(const uint32_t ctr[4], const uint32_t key[2], int rounds, uint32_t out[4])
 {
     uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
     uint32_t k0 = key[0], k1 = key[1];
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < rounds; ++r) {
         uint64_t p0 = (uint64_t)0xD2511F53u * c0;
         uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
         uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
@@ -62,6 +62,12 @@ void hdp_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint
         k1 += 0xBB67AE85u;
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+int hdp_oracle_philox_rounds(void) { return HDP_PHILOX_ROUNDS; }
+/* the 10-round member of the family: the one Random123 publishes known-answer vectors for */
+void hdp_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    hdp_oracle_philox4x32(ctr, key, 10, out);
 }
 
 /* the library's draw: streams TIME/STEP/SAMPLER pack (ordinal < 2^40, group < 2^21),
@@ -79,7 +85,7 @@ static void draw_words(uint64_t seed, int stream, uint64_t ord, uint64_t group, 
     }
     ctr[2] = (uint32_t)seed;
     ctr[3] = (uint32_t)(seed >> 32);
-    hdp_oracle_philox4x32_10(ctr, key, w);
+    hdp_oracle_philox4x32(ctr, key, HDP_PHILOX_ROUNDS, w); /* the library's round count (include/hdpde.h) */
 }
 
 static inline uint64_t k52(uint32_t hi, uint32_t lo)

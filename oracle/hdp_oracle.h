@@ -44,6 +44,8 @@ hdp_oracle_rng* hdp_oracle_rng_xoshiro(uint64_t seed, int is_f32, int sampler_no
 void hdp_oracle_rng_free(hdp_oracle_rng* g);
 void hdp_oracle_rng_fill(hdp_oracle_rng* g, int what, double* out, int n);
 
+void hdp_oracle_philox4x32(const uint32_t ctr[4], const uint32_t key[2], int rounds, uint32_t out[4]);
+int hdp_oracle_philox_rounds(void);
 void hdp_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 double hdp_oracle_draw_f64(uint64_t seed, int stream, uint64_t ord, uint64_t i, int want_normal);
 float hdp_oracle_draw_f32(uint64_t seed, int stream, uint64_t ord, uint64_t i, int want_normal);

@@ -48,6 +48,8 @@ def lib():
         L.hdp_oracle_rng_free.argtypes = [vp]
         L.hdp_oracle_rng_fill.argtypes = [vp, i, vp, i]
         L.hdp_oracle_philox4x32_10.argtypes = [vp, vp, vp]
+        L.hdp_oracle_philox4x32.argtypes = [vp, vp, i, vp]
+        L.hdp_oracle_philox_rounds.restype = i
         L.hdp_oracle_draw_f64.restype = C.c_double
         L.hdp_oracle_draw_f64.argtypes = [u64, i, u64, u64, i]
         L.hdp_oracle_draw_f32.restype = C.c_float
@@ -131,6 +133,19 @@ def philox4x32_10(ctr, key):
     out = np.zeros(4, dtype=np.uint32)
     lib().hdp_oracle_philox4x32_10(_p(c), _p(k), _p(out))
     return out
+
+
+def philox4x32(ctr, key, rounds=None):
+    """Philox4x32-R; rounds=None: the library's round count (HDP_PHILOX_ROUNDS, include/hdpde.h)."""
+    c = np.asarray(ctr, dtype=np.uint32)
+    k = np.asarray(key, dtype=np.uint32)
+    out = np.zeros(4, dtype=np.uint32)
+    lib().hdp_oracle_philox4x32(_p(c), _p(k), philox_rounds() if rounds is None else int(rounds), _p(out))
+    return out
+
+
+def philox_rounds():
+    return int(lib().hdp_oracle_philox_rounds())
 
 
 def draw(dtype, seed, stream, ord_, i, normal):

@@ -6,10 +6,9 @@ h = H.Handle(0)
 def run(name, prob, alg, n, gs):
     out = []
     for g in gs:
-        os.environ["HDP_MLP_GROUP"] = str(g)
         best = 1e30
         for r in range(4):
-            u, st = H._ml_picard_batch(prob, alg, n_solves=n, seed=100 + r * n, handle=h)
+            u, st = H._ml_picard_batch(prob, alg, n_solves=n, seed=100 + r * n, handle=h, group_size=g)
             if r: best = min(best, st["device_ms"])
         out.append(f"G={g}:{best:.3f}ms/{st['n_units']}u")
     print(f"{name:28s} n={n:5d}  " + "  ".join(out), flush=True)

@@ -68,7 +68,8 @@ def random_tapes(H, prob, alg, dtype, seed=1, compat=0):
     return r, n, s
 
 
-def emu_solve(H, emu, prob, alg, dtype=np.float64, seed=0, tapes=None, target_units=0, compat=0, n_solves=1):
+def emu_solve(H, emu, prob, alg, dtype=np.float64, seed=0, tapes=None, target_units=0, compat=0, n_solves=1, nranks=1,
+              std_err=False):
     pb, keep = prob.to_c()
     cfg = H.capi.hdp_mlp_cfg()
     cfg.M, cfg.L, cfg.K = alg.M, alg.L, alg.K
@@ -85,9 +86,14 @@ def emu_solve(H, emu, prob, alg, dtype=np.float64, seed=0, tapes=None, target_un
             cfg.s_tape = ts[2].ctypes.data
     x = np.ascontiguousarray(prob.x, dtype=dtype)
     u = np.zeros(n_solves, dtype=dtype)
+    se = np.zeros(n_solves, dtype=dtype)
+    if std_err:
+        cfg.std_err_out = se.ctypes.data
     st = H.capi.hdp_mlp_stats()
-    fn = emu.hdp_emu_mlp_solve_f64 if dtype == np.float64 else emu.hdp_emu_mlp_solve_f32
-    rc = fn(C.byref(pb), C.byref(cfg), x.ctypes.data_as(C.c_void_p), u.ctypes.data_as(C.c_void_p), C.byref(st))
+    fn = emu.hdp_emu_mlp_solve_sharded_f64 if dtype == np.float64 else emu.hdp_emu_mlp_solve_sharded_f32
+    rc = fn(C.byref(pb), C.byref(cfg), x.ctypes.data_as(C.c_void_p), u.ctypes.data_as(C.c_void_p), C.byref(st), int(nranks))
+    if std_err:
+        st.se = se
     return u, rc, st
 
 

@@ -17,11 +17,19 @@ namespace hdp {
 MlpPlan::~MlpPlan() {} // no device copies in the emulation
 }
 
+namespace hdp {
+MlpSharding::~MlpSharding() {}
+}
+
+// nranks > 1 emulates a solve sharded over several GPUs (MlpSharding): the ranks run one after the other on
+// private copies of the per-call state, their exchange buffers are summed as the all-reduce would, and every
+// rank finishes the crown; the results of all ranks must agree bit for bit (checked here), rank 0's is returned.
 template <typename T>
-static int emu_solve(const hdp_problem* prob, const hdp_mlp_cfg* cfg, const T* x0, T* u_out, hdp_mlp_stats* stats)
+static int emu_solve(const hdp_problem* prob, const hdp_mlp_cfg* cfg, const T* x0, T* u_out, hdp_mlp_stats* stats,
+                     int nranks = 1)
 {
     const int M = cfg->M, L = cfg->L, K = cfg->K, n_solves = cfg->n_solves;
-    if (M < 1 || K < 1 || L < 1 || L > kMaxL || n_solves < 1) return HDP_ERR_BAD_ARG;
+    if (M < 1 || K < 1 || L < 1 || L > kMaxL || n_solves < 1 || nranks < 1) return HDP_ERR_BAD_ARG;
     const bool nonlocal = cfg->sampler.kind != HDP_SAMPLER_NONE;
     constexpr int VEC = Tr<T>::VEC;
     constexpr int G = 1;
@@ -59,40 +67,123 @@ static int emu_solve(const hdp_problem* prob, const hdp_mlp_cfg* cfg, const T* x
     }
     for (int i = 0; i <= kMaxL + 1; ++i) P.Mpow[i] = tab.Mpow[i];
     P.seed0 = cfg->seed; P.n_solves = n_solves; P.n_x0 = cfg->n_x0;
-    P.units = plan.units.data(); P.exec = plan.exec_order.data(); P.unit_tag = plan.unit_tag.data(); P.nodes = plan.nodes.data();
+    P.units = plan.units.data(); P.unit_tag = plan.unit_tag.data(); P.nodes = plan.nodes.data();
     P.sites = plan.sites.data(); P.children = plan.children.data();
     P.sites_by_depth = plan.sites_by_depth.data(); P.nodes_by_depth = plan.nodes_by_depth.data();
     P.n_units = (int)plan.units.size(); P.n_nodes = (int)plan.nodes.size();
     P.n_sites = (int)plan.sites.size(); P.n_points = plan.n_points;
-    P.rank = 0; P.nranks = 1;
+    P.nranks = nranks;
     P.r_tape = (const T*)cfg->r_tape; P.n_tape = (const T*)cfg->n_tape; P.s_tape = (const T*)cfg->s_tape;
-    std::vector<T> points((size_t)n_solves * P.n_points * P.dpad + VEC), feat((size_t)n_solves * P.n_points);
-    std::vector<T> site_r((size_t)n_solves * std::max(P.n_sites, 1)), value((size_t)n_solves * P.n_nodes);
-    std::vector<double> partial((size_t)n_solves * P.n_units);
-    // 16-byte aligned scratch
-    std::vector<double2> scratch_raw((size_t)(2 * L) * P.npl * VEC * sizeof(T) / sizeof(double2) + 2);
-    unsigned long long ctr[2] = {0, 0};
-    int flags[2] = {0, 0};
-    // align points to 16 B
-    std::vector<double2> points_raw(((size_t)n_solves * P.n_points * P.dpad * sizeof(T)) / sizeof(double2) + 2);
-    P.points = (T*)points_raw.data(); P.feat = feat.data(); P.site_r = site_r.data();
-    P.partial = partial.data(); P.value = value.data(); P.scratch = (T*)scratch_raw.data();
-    P.total_threads = 1; P.work_ctr = &ctr[0]; P.bounce_ctr = &ctr[1]; P.flags = flags;
+    const bool want_se = cfg->std_err_out != nullptr;
+    const PlanNode& root = plan.nodes[0];
+    P.rootsq_stride = 2 * std::max(root.unit_end - root.unit_begin, L + 1);
 
-    for (u64 q = 0; q < (u64)n_solves * P.dpad; ++q) init_item<T>(P, x0, q);
+    struct RankState {
+        std::vector<T> feat, site_r, value, se;
+        std::vector<double> partial, rootsq, lvstat, xbuf;
+        std::vector<double2> scratch_raw, points_raw;
+        unsigned long long ctr[2] = {0, 0};
+        int flags[2] = {0, 0};
+        MlpSharding sh;
+    };
+    std::vector<RankState> rs(nranks);
+    int xstride = 0;
+    auto bind = [&](int r) {
+        RankState& S = rs[r];
+        P.rank = r;
+        P.points = (T*)S.points_raw.data(); P.feat = S.feat.data(); P.site_r = S.site_r.data();
+        P.partial = S.partial.data(); P.value = S.value.data(); P.scratch = (T*)S.scratch_raw.data();
+        P.total_threads = 1; P.work_ctr = &S.ctr[0]; P.bounce_ctr = &S.ctr[1]; P.flags = S.flags;
+        P.rootsq = want_se ? S.rootsq.data() : nullptr;
+        P.lvstat = want_se ? S.lvstat.data() : nullptr;
+        P.std_err = want_se ? S.se.data() : nullptr;
+        if (nranks > 1) {
+            P.exec = S.sh.exec_own.data(); P.n_exec = (int)S.sh.exec_own.size();
+            P.unit_mine = S.sh.unit_mine.data(); P.site_cls = S.sh.site_cls.data(); P.node_slot = S.sh.node_slot.data();
+            P.n_slots = S.sh.n_slots; P.xstride = S.sh.n_slots + 3 * (kMaxL + 1);
+            P.xbuf = S.xbuf.data();
+        } else {
+            P.exec = plan.exec_order.data(); P.n_exec = P.n_units;
+        }
+    };
+    for (int r = 0; r < nranks; ++r) {
+        RankState& S = rs[r];
+        S.feat.resize((size_t)n_solves * P.n_points);
+        S.site_r.resize((size_t)n_solves * std::max(P.n_sites, 1));
+        S.value.resize((size_t)n_solves * P.n_nodes);
+        S.se.resize(n_solves);
+        S.partial.assign((size_t)n_solves * P.n_units, 0.0);
+        S.rootsq.assign((size_t)n_solves * P.rootsq_stride, 0.0);
+        S.lvstat.assign((size_t)n_solves * 3 * (kMaxL + 1), 0.0);
+        S.scratch_raw.resize((size_t)(2 * L) * P.npl * VEC * sizeof(T) / sizeof(double2) + 2); // 16-byte aligned
+        S.points_raw.resize(((size_t)n_solves * P.n_points * P.dpad * sizeof(T)) / sizeof(double2) + 2);
+        if (nranks > 1) {
+            mlp_build_sharding(plan, nranks, r, &S.sh);
+            xstride = S.sh.n_slots + 3 * (kMaxL + 1);
+            S.xbuf.assign((size_t)n_solves * xstride + kXTail, 0.0);
+        }
+    }
     Ctx<T, G> c;
-    ctx_init<T, G>(c, P, 0, 0);
-    for (int dep = 0; dep <= plan.max_depth; ++dep) {
-        int off = plan.site_depth_off[dep], cnt = plan.site_depth_off[dep + 1] - off;
-        for (u64 it = 0; it < (u64)cnt * n_solves; ++it) { c.nb = 0; expand_item<T, G>(c, P, off, it); }
+    auto expand_list = [&](const int32_t* list, int cnt, bool hits) {
+        for (u64 it = 0; it < (u64)cnt * n_solves; ++it) { c.nb = 0; expand_item<T, G>(c, P, list, it, hits); }
+    };
+    auto combine_list = [&](const int32_t* list, int cnt, int mode) {
+        for (u64 it = 0; it < (u64)cnt * n_solves; ++it) combine_item<T>(P, list, it, 0, 1, 0xffffffffu, mode);
+    };
+    // phase 1 (per rank): geometry, units, local combine
+    for (int r = 0; r < nranks; ++r) {
+        bind(r);
+        RankState& S = rs[r];
+        for (u64 q = 0; q < (u64)n_solves * P.dpad; ++q) init_item<T>(P, x0, q);
+        ctx_init<T, G>(c, P, 0, 0);
+        if (nranks == 1) {
+            for (int dep = 0; dep <= plan.max_depth; ++dep)
+                expand_list(P.sites_by_depth + plan.site_depth_off[dep], plan.site_depth_off[dep + 1] - plan.site_depth_off[dep], true);
+        } else {
+            for (int dep = 0; dep <= plan.max_depth; ++dep)
+                expand_list(S.sh.upper_sites.data() + S.sh.upper_depth_off[dep],
+                            S.sh.upper_depth_off[dep + 1] - S.sh.upper_depth_off[dep], r == 0);
+            expand_list(S.sh.own_bottom_sites.data(), (int)S.sh.own_bottom_sites.size(), true);
+        }
+        for (u64 w = 0; w < (u64)P.n_exec * n_solves; ++w) unit_item<T, G>(c, P, w);
+        if (c.bad) S.flags[0] = 1;
+        if (nranks == 1) {
+            for (int dep = plan.max_depth; dep >= 0; --dep)
+                combine_list(P.nodes_by_depth + plan.node_depth_off[dep], plan.node_depth_off[dep + 1] - plan.node_depth_off[dep], CMB_ALL);
+        } else {
+            combine_list(S.sh.owned_nodes.data(), (int)S.sh.owned_nodes.size(), CMB_ALL);
+            combine_list(S.sh.crown_nodes.data(), (int)S.sh.crown_nodes.size(), CMB_PARTIAL);
+            S.xbuf[(size_t)n_solves * xstride + 4] = (double)S.ctr[1];
+        }
     }
-    for (u64 w = 0; w < (u64)P.n_units * n_solves; ++w) unit_item<T, G>(c, P, w);
-    if (c.bad) flags[0] = 1;
-    for (int dep = plan.max_depth; dep >= 0; --dep) {
-        int off = plan.node_depth_off[dep], cnt = plan.node_depth_off[dep + 1] - off;
-        for (u64 it = 0; it < (u64)cnt * n_solves; ++it) combine_item<T>(P, off, it, 0, 1);
+    if (nranks > 1) {
+        // the all-reduce
+        std::vector<double> sum(rs[0].xbuf.size(), 0.0);
+        for (int r = 0; r < nranks; ++r)
+            for (size_t i = 0; i < sum.size(); ++i) sum[i] += rs[r].xbuf[i];
+        // phase 2 (per rank): scatter the crown leaves, finish the crown
+        for (int r = 0; r < nranks; ++r) {
+            bind(r);
+            RankState& S = rs[r];
+            S.xbuf = sum;
+            P.xbuf = S.xbuf.data();
+            for (int32_t nidx : S.sh.crown_leaves)
+                for (int sv = 0; sv < n_solves; ++sv)
+                    S.partial[(size_t)sv * P.n_units + plan.nodes[nidx].unit_begin] = S.xbuf[(size_t)sv * xstride + S.sh.node_slot[nidx]];
+            for (int dep = plan.max_depth; dep >= 0; --dep)
+                combine_list(S.sh.crown_final.data() + S.sh.crown_final_off[dep],
+                             S.sh.crown_final_off[dep + 1] - S.sh.crown_final_off[dep], CMB_FINAL);
+            S.ctr[1] = (unsigned long long)sum[(size_t)n_solves * xstride + 4];
+        }
+        for (int r = 1; r < nranks; ++r)
+            for (int i = 0; i < n_solves; ++i)
+                if (rs[r].value[(size_t)i * P.n_nodes] != rs[0].value[(size_t)i * P.n_nodes]) return HDP_ERR_UNSUPPORTED;
     }
-    for (int i = 0; i < n_solves; ++i) u_out[i] = value[(size_t)i * P.n_nodes];
+    int bad = 0;
+    for (int r = 0; r < nranks; ++r) bad |= rs[r].flags[0];
+    for (int i = 0; i < n_solves; ++i) u_out[i] = rs[0].value[(size_t)i * P.n_nodes];
+    if (want_se)
+        for (int i = 0; i < n_solves; ++i) ((T*)cfg->std_err_out)[i] = rs[0].se[i];
     if (stats) {
         memset(stats, 0, sizeof(*stats));
         stats->per_solve.path_steps = tab.C[L];
@@ -100,11 +191,45 @@ static int emu_solve(const hdp_problem* prob, const hdp_mlp_cfg* cfg, const T* x
         stats->per_solve.sampler_calls = tab.S[L];
         stats->per_solve.f_evals = tab.F[L];
         stats->per_solve.g_evals = tab.G[L];
-        stats->bounces = ctr[1];
+        stats->bounces = rs[0].ctr[1];
         stats->n_units = P.n_units; stats->n_nodes = P.n_nodes; stats->n_sites = P.n_sites;
         stats->group_size = 1;
+        stats->exchange_bytes = nranks > 1 ? rs[0].xbuf.size() * sizeof(double) : 0;
+        if (want_se) {
+            for (int l = 0; l <= L; ++l) {
+                stats->level_n[l] = (uint64_t)(rs[0].lvstat[3 * l] + 0.5);
+                stats->level_sum[l] = rs[0].lvstat[3 * l + 1];
+                stats->level_sumsq[l] = rs[0].lvstat[3 * l + 2];
+            }
+            stats->std_error = (double)rs[0].se[0];
+        }
     }
-    return flags[0] ? HDP_ERR_START_OUTSIDE_DOMAIN : HDP_OK;
+    return bad ? HDP_ERR_START_OUTSIDE_DOMAIN : HDP_OK;
+}
+
+extern "C" int hdp_emu_mlp_solve_sharded_f64(const hdp_problem* prob, const hdp_mlp_cfg* cfg, const double* x0,
+                                             double* u_out, hdp_mlp_stats* stats, int nranks)
+{
+    return emu_solve<double>(prob, cfg, x0, u_out, stats, nranks);
+}
+extern "C" int hdp_emu_mlp_solve_sharded_f32(const hdp_problem* prob, const hdp_mlp_cfg* cfg, const float* x0,
+                                             float* u_out, hdp_mlp_stats* stats, int nranks)
+{
+    return emu_solve<float>(prob, cfg, x0, u_out, stats, nranks);
+}
+// the sharding of a plan, summarised: [n_slots, crown nodes, crown leaves, upper sites, bottom sites (all ranks),
+// owned nodes (this rank), units (this rank), 1000 * busiest rank's modelled load / mean load]
+extern "C" void hdp_emu_sharding_summary(int M, int L, int K, int nonlocal, double thresh, int nranks, int rank, int64_t out[8])
+{
+    MlpPlan plan;
+    mlp_build_plan(M, L, K, nonlocal != 0, thresh, 0, &plan);
+    MlpSharding sh;
+    mlp_build_sharding(plan, nranks, rank, &sh);
+    int64_t bottoms = 0;
+    for (int8_t c : sh.site_cls) bottoms += c != 0;
+    out[0] = sh.n_slots; out[1] = (int64_t)sh.crown_nodes.size(); out[2] = (int64_t)sh.crown_leaves.size();
+    out[3] = (int64_t)sh.upper_sites.size(); out[4] = bottoms; out[5] = (int64_t)sh.owned_nodes.size();
+    out[6] = (int64_t)sh.exec_own.size(); out[7] = (int64_t)(1000.0 * sh.load_max / std::max(sh.load_mean, 1e-300));
 }
 
 extern "C" int hdp_emu_mlp_solve_f64(const hdp_problem* prob, const hdp_mlp_cfg* cfg, const double* x0,

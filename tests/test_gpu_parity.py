@@ -199,15 +199,14 @@ def test_mlp_injected_tapes_match_oracle(H, O, handle, name):
 
 
 @pytest.mark.parametrize("G", [1, 2, 4, 8, 16, 32])
-def test_mlp_every_group_size(H, O, handle, G, monkeypatch):
+def test_mlp_every_group_size(H, O, handle, G):
     """Results do not depend on how many lanes own a path."""
-    monkeypatch.setenv("HDP_MLP_GROUP", str(G))
     for name in ("allen_cahn_neumann_d5", "nonlocal_ac_neumann_d5", "black_scholes_d20", "allen_cahn_neumann_f32_d7"):
         prob, alg, dt = zoo(H)[name]
         tapes = random_tapes(H, prob, alg, dt, seed=8)
         uo, info = oracle_solve(H, O, prob, alg, dt, tapes)
         for target in (1, 300):
-            u, st = H._ml_picard_batch(prob, alg, tapes=tapes, target_units=target, handle=handle, dtype=dt)
+            u, st = H._ml_picard_batch(prob, alg, tapes=tapes, target_units=target, handle=handle, dtype=dt, group_size=G)
             assert st["group_size"] == G
             assert rel_err(float(u[0]), uo) <= TOL[dt] and st["bounces"] == info["bounces"]
 
@@ -274,7 +273,7 @@ def _fast_loop_cases(H):
 
 @pytest.mark.parametrize("name", ["sym_d5", "box_d6", "box_d7_f32", "nobc_d9", "wild_sym_d4", "wild_far_d4",
                                   "nonlocal_sym_d5", "sym_d1", "box_d1_f32", "long_d2101"])
-def test_mlp_fast_loops_match_oracle_on_their_own_draws(H, O, handle, name, monkeypatch):
+def test_mlp_fast_loops_match_oracle_on_their_own_draws(H, O, handle, name):
     """RNG mode runs the specialised loops; the oracle is fed the very draws (hdp_tape_fill): values to tolerance,
     wall-hit counts exact, whatever the lane-group width and the tree cut."""
     prob, alg, dt = _fast_loop_cases(H)[name]
@@ -284,12 +283,9 @@ def test_mlp_fast_loops_match_oracle_on_their_own_draws(H, O, handle, name, monk
     assert info["rc"] == 0
     groups = (None, 32) if name == "long_d2101" else (None, 1, 2, 8, 32)
     for G in groups:
-        if G is None:
-            monkeypatch.delenv("HDP_MLP_GROUP", raising=False)
-        else:
-            monkeypatch.setenv("HDP_MLP_GROUP", str(G))
         for target in (1, 50, 0):
-            u, st = H._ml_picard_batch(prob, alg, n_solves=1, seed=seed, target_units=target, handle=handle, dtype=dt)
+            u, st = H._ml_picard_batch(prob, alg, n_solves=1, seed=seed, target_units=target, handle=handle, dtype=dt,
+                                       group_size=G or 0)
             assert rel_err(float(u[0]), uo) <= TOL[dt], (name, G, target, float(u[0]), uo)
             assert st["bounces"] == info["bounces"], (name, G, target)
 

@@ -123,3 +123,98 @@ def test_product_generator_matches_its_definition(O, emu):
             b = O.draw(np.float64, 99, stream, ord_, 2 * grp + 1, True)
             worst = max(worst, abs(out[0] - a) / max(1.0, abs(a)), abs(out[1] - b) / max(1.0, abs(b)))
     assert worst <= 2e-15, worst
+
+
+# ---------------------------------------------------------------------------------------------
+# one solve sharded over several ranks (MlpSharding): the emulation runs the ranks one after the
+# other, sums their exchange buffers as the all-reduce would and lets every rank finish the crown
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["allen_cahn_neumann_d5", "nonlocal_ac_neumann_d5", "replicator_d2", "black_scholes_d20",
+                                  "shifted_normal_d3_L5", "heat_neumann_f32_d3"])
+def test_sharded_solve_matches_oracle_for_any_rank_count(H, O, emu, name):
+    prob, alg, dt = zoo(H)[name]
+    tapes = random_tapes(H, prob, alg, dt, seed=13)
+    uo, info = oracle_solve(H, O, prob, alg, dt, tapes)
+    for target in (0, 40, 800, 100000):
+        u1, rc, st1 = emu_solve(H, emu, prob, alg, dt, tapes=tapes, target_units=target)
+        assert rc == 0
+        for nranks in (2, 3, 8):
+            u, rc, st = emu_solve(H, emu, prob, alg, dt, tapes=tapes, target_units=target, nranks=nranks)
+            assert rc == 0, (name, target, nranks)  # (also: every rank finished with the same bits)
+            assert rel_err(float(u[0]), uo) <= TOL[dt], (name, target, nranks, u[0], uo)
+            assert abs(float(u[0]) - float(u1[0])) <= 4 * TOL[dt] * 1e-3 * max(1.0, abs(uo))  # summation order only
+            assert st.bounces == info["bounces"], (name, target, nranks)  # every wall hit counted once
+            assert st.exchange_bytes > 0
+
+
+def test_sharded_batch_and_compat_partition(H, O, emu):
+    prob, alg, dt = zoo(H)["heat_neumann_d5"]
+    pb, keep = prob.to_c()
+    sm, k2 = alg.mc_sample._descriptor(prob.d)
+    u, rc, st = emu_solve(H, emu, prob, alg, dt, seed=40, n_solves=3, target_units=300, nranks=4)
+    assert rc == 0
+    for i in range(3):
+        uo, _ = O.ml_picard(pb, sm, alg.M, alg.L, alg.K, prob.x, O.Rng.philox(40 + i, dt, False))
+        assert rel_err(float(u[i]), uo) <= 1e-11
+    # the threaded variant's partition of the root call, sharded
+    prob, alg, dt = zoo(H)["allen_cahn_neumann_d5"]
+    nt = 3
+    tapes = random_tapes(H, prob, alg, dt, seed=5, compat=nt)
+    pb, keep = prob.to_c()
+    sm, k2 = alg.mc_sample._descriptor(prob.d)
+    rng = O.Rng.tape(dt, *tapes)
+    uo, info = O.ml_picard_mlt(pb, sm, alg.M, alg.L, alg.K, prob.x, nt, [rng] * (nt + 1), parallel=False)
+    u, rc, st = emu_solve(H, emu, prob, alg, dt, tapes=tapes, target_units=64, compat=nt, nranks=2)
+    assert rc == 0 and rel_err(float(u[0]), uo) <= 1e-12 and st.bounces == info["bounces"]
+
+
+def test_sharding_exchanges_one_double_per_crown_node(H, emu):
+    """BASELINE C4 (M=4, L=5, K=10, non-local) cut as finely as 8 GPUs need: hundreds of thousands of units, a few
+    thousand crown nodes — the all-reduce carries the latter — and a balanced split of the modelled work."""
+    import ctypes as C
+    out = (C.c_int64 * 8)()
+    plan = (C.c_int64 * 8)()
+    for thresh in (400.0, 90.0):
+        emu.hdp_emu_plan_summary(4, 5, 10, 1, C.c_double(thresh), 0, plan)
+        n_units = plan[2]
+        units = 0
+        for rank in range(8):
+            emu.hdp_emu_sharding_summary(4, 5, 10, 1, C.c_double(thresh), 8, rank, out)
+            units += out[6]
+            assert out[0] == out[1] and out[0] < n_units // 20, (thresh, list(out), n_units)
+            assert out[7] <= 1020, (thresh, list(out))  # busiest rank within 2 % of the mean
+        assert units == n_units  # every unit has exactly one owner
+
+
+# ---------------------------------------------------------------------------------------------
+# Monte-Carlo error bar (cfg.std_err_out)
+# ---------------------------------------------------------------------------------------------
+def test_error_bar_is_the_level_statistics_of_the_root(H, O, emu):
+    """Heat equation (f = 0): only the g-term contributes; its sample statistics can be recomputed from the tape."""
+    prob, alg, dt = zoo(H)["heat_d10"]
+    tapes = random_tapes(H, prob, alg, dt, seed=3)
+    cn = H.mlp_counts(alg.M, alg.L, alg.K)
+    ng = alg.M ** alg.L
+    # the g-term steps are the last M^L path-steps of the root call: x2 = x + sigma*sqrt(T)*xi, g = sum(x2^2)
+    xi = tapes[1][cn["path_steps"] - ng:]
+    g = np.sum((prob.x[None, :] + 0.1 * np.sqrt(0.5) * xi) ** 2, axis=1)
+    se_want = np.sqrt(g.var(ddof=1) / ng)
+    ref = None
+    for target, nranks in ((0, 1), (30, 1), (3000, 1), (30, 2), (3000, 8)):
+        u, rc, st = emu_solve(H, emu, prob, alg, dt, tapes=tapes, target_units=target, nranks=nranks, std_err=True)
+        assert rc == 0
+        assert st.level_n[alg.L] == ng and abs(st.level_sum[alg.L] - g.sum()) <= 1e-9 * g.sum()
+        assert abs(st.level_sumsq[alg.L] - np.sum(g * g)) <= 1e-9 * np.sum(g * g)
+        assert [st.level_n[l] for l in range(alg.L)] == [alg.M ** (alg.L - l) for l in range(alg.L)]
+        assert abs(st.std_error - se_want) <= 1e-6 * se_want and abs(float(st.se[0]) - se_want) <= 1e-6 * se_want
+        ref = ref or st.std_error
+
+
+def test_error_bar_covers_the_scatter_of_independent_solves(H, emu):
+    """Allen–Cahn with reflection: the reported standard error matches the empirical spread over seeds."""
+    prob, alg, dt = zoo(H)["allen_cahn_neumann_d5"]
+    u, rc, st = emu_solve(H, emu, prob, alg, dt, seed=7, n_solves=48, target_units=48 * 40, std_err=True)
+    assert rc == 0
+    sd = float(np.std(u, ddof=1))
+    se = float(np.sqrt(np.mean(st.se ** 2)))
+    assert 0.6 * sd <= se <= 1.6 * sd, (sd, se)

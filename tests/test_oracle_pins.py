@@ -31,10 +31,19 @@ def test_philox_known_answers(O):
             [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1])]
     for ctr, key, want in kat:
         assert [int(v) for v in O.philox4x32_10(ctr, key)] == want
+        assert [int(v) for v in O.philox4x32(ctr, key, 10)] == want
+    # the library draws with HDP_PHILOX_ROUNDS rounds of the same round function and key schedule:
+    # R rounds followed by 10 - R more from the bumped key are the 10-round vector
+    R = O.philox_rounds()
+    assert R == 7
+    for ctr, key, want in kat:
+        mid = O.philox4x32(ctr, key, R)
+        key2 = [(key[0] + R * 0x9E3779B9) & 0xFFFFFFFF, (key[1] + R * 0xBB67AE85) & 0xFFFFFFFF]
+        assert [int(v) for v in O.philox4x32(mid, key2, 10 - R)] == want
 
 
 def test_draw_addressing_layout(O):
-    """The library's draws: Philox4x32-10, fixed key, counter (w0, w1, seed_lo, seed_hi) with the documented
+    """The library's draws: Philox4x32-7 (HDP_PHILOX_ROUNDS), fixed key, counter (w0, w1, seed_lo, seed_hi) with the documented
     packing of (stream, ordinal, group) — include/hdpde.h, DESIGN.md section 3."""
     key = [0xA4093822, 0x299F31D0]
     seed = 0x0123456789ABCDEF
@@ -46,7 +55,7 @@ def test_draw_addressing_layout(O):
         else:            # SDE, X0, MC: ordinal < 2^24, group < 2^37
             w0 = group & 0xFFFFFFFF
             w1 = ((group >> 32) | (ord_ << 5) | (stream << 29)) & 0xFFFFFFFF
-        return [int(v) for v in O.philox4x32_10([w0, w1, seed & 0xFFFFFFFF, seed >> 32], key)]
+        return [int(v) for v in O.philox4x32([w0, w1, seed & 0xFFFFFFFF, seed >> 32], key)]
 
     for stream, ord_, group in [(0, 5, 0), (1, (1 << 39) + 12345, (1 << 20) + 7), (2, 77, 3), (3, (1 << 23) + 9, (1 << 36) + 11),
                                 (4, 0, 123456789), (5, 31, 2)]:
