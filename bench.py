@@ -36,11 +36,32 @@ import numpy as np  # noqa: E402
 D, M, L, K = 100, 4, 4, 10
 SOLVES_PER_GPU = 4096
 PATH_STEPS_PER_SOLVE = 4916          # C(4) for M=4 local
-I64_PER_COORD_STEP = 39              # fp64 pipe-instr budget per reflected coordinate-step
-I64_EXECUTED = 28.0                  # what the kernel executes per coordinate-step (ncu fp64-pipe % x cycles, profiles/r1o_summary.md)
-# dram__bytes_read.sum + dram__bytes_write.sum of one units launch on this workload (ncu --set full, profiles/r1o_summary.md)
-DRAM_TRAFFIC_PER_LAUNCH = 2.24e6 + 1.47e6
+I64_PER_COORD_STEP = 39              # fp64 pipe-instr budget per reflected coordinate-step (the v0 budget)
 F_ALG_PER_COORD_STEP = 11            # algorithmic FLOP per reflected coordinate-step
+
+
+def units_profile():
+    """What the committed `ncu --set full` capture of the units kernel on THIS workload (4096 C2 solves) says:
+    DRAM bytes per launch (with the CSV's units applied) and the fp64 instructions the kernel executes per
+    coordinate-step (fp64-pipe utilisation x active cycles x 64 fp64 lanes per SM x SMs / coordinate-steps).
+    Nothing is typed in by hand: profiles/tools/ncu_metrics.py reads the newest r2*_mlp_units_full_metrics.csv."""
+    sys.path.insert(0, os.path.join(ROOT, "profiles", "tools"))
+    try:
+        import ncu_metrics as NM
+        path = NM.latest("r2*_mlp_units_full_metrics.csv") or NM.latest("r1o_mlp_units_full_metrics.csv")
+        m = NM.load(path)
+        coord_steps = SOLVES_PER_GPU * PATH_STEPS_PER_SOLVE * D
+        fp64_lane_instr = (m["sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"] / 100.0 *
+                           m["sm__cycles_active.avg"] * 64 * 148)
+        return {"traffic": m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"],
+                "dram_read": m["dram__bytes_read.sum"], "dram_write": m["dram__bytes_write.sum"],
+                "fp64_instr_per_coord_step": fp64_lane_instr / coord_steps,
+                "warp_instr_per_vec_group": m["smsp__inst_executed.sum"] / (coord_steps / 64.0),
+                "fp64_pipe_pct": m["sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"],
+                "kernel_ms_under_ncu": 1e3 * m["gpu__time_duration.sum"],
+                "source": os.path.relpath(path, ROOT)}
+    except Exception as e:  # pragma: no cover
+        return {"traffic": None, "fp64_instr_per_coord_step": None, "source": f"unavailable: {e!r}"}
 print_line = print
 METRIC = "mlp_solves_per_sec"
 UNIT = "solves/s"
@@ -251,6 +272,11 @@ def run_ours(args, rank, world, local_rank):
     peak64 = h.measure_pipe_peak(64)
     peak32 = h.measure_pipe_peak(32)
 
+    # ---- strong scaling of ONE solve over the ranks (every rank takes part; N > 1 only) ----
+    strong = bench_strong(torch, dist, H, HD, local_rank, rank, world) if dist is not None else None
+    if strong is not None and rank == 0:
+        extra["strong"] = strong
+
     if dist is not None:
         dev_ms = HD.max_over_ranks(dev_ms)
         e2e_s = HD.max_over_ranks(e2e_s)
@@ -263,6 +289,8 @@ def run_ours(args, rank, world, local_rank):
         e2e = n_total * args.steps / e2e_s
         coord_steps_per_s_gpu = (n_local * args.steps * PATH_STEPS_PER_SOLVE * D) / (dev_ms * 1e-3)
         achieved = coord_steps_per_s_gpu * I64_PER_COORD_STEP
+        prof = units_profile()
+        i_exec = prof.get("fp64_instr_per_coord_step")
         # reported baseline, rank 0 at N=1 only (keeps multi-GPU runs short)
         cpu = cpu_baseline(H, prob, alg) if world == 1 else None
         line = {
@@ -270,7 +298,8 @@ def run_ours(args, rank, world, local_rank):
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "solves_per_gpu_per_step": n_local, "global_solves_per_step": n_total,
-                       "parallelism": f"solves sharded over {world} rank(s), no data-path collective",
+                       "parallelism": f"headline: independent solves sharded over {world} rank(s), no data-path collective; "
+                                      "extra.strong (N > 1): ONE solve sharded by subtree, one ncclAllReduce of a double per crown node",
                        "l2": "256 MB flush between steps (untimed); the path is compute-bound, inputs are d doubles",
                        "rng": "Philox4x32-10 (fixed key, seed and consumption ordinal in the counter) + table-driven fp64 Box-Muller, generated in registers"},
             "reflected_path_steps_per_sec": value * PATH_STEPS_PER_SOLVE,
@@ -279,14 +308,17 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": achieved / 1e12, "peak": peak64 / 1e12, "unit": "Tlane-instr/s",
-                         "frac": achieved / peak64, "traffic": DRAM_TRAFFIC_PER_LAUNCH,
-                         "traffic_note": "bytes per units launch (4096 solves), ncu capture profiles/r1o_summary.md: "
-                                         "the scratch of the tree walk stays in L2; HBM is idle, the fp64 pipe is the bound",
-                         "executed": {"fp64_instr_per_coord_step": I64_EXECUTED,
-                                      "frac": coord_steps_per_s_gpu * I64_EXECUTED / peak64,
-                                      "note": "fp64-pipe utilisation actually reached (the table-driven Box-Muller "
-                                              "needs fewer fp64 instructions than the 8(d) budget)"},
-                         "kernel": "mlp_units_kernel<double,1,3>",
+                         "frac": achieved / peak64, "traffic": prof.get("traffic"),
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one units launch (4096 solves), read "
+                                         "with its units from " + str(prof.get("source")) + ": the per-lane scratch rows of the "
+                                         "tree walk spill past L2; algorithmic bytes per launch are ~33 KB, the fp64 pipe and "
+                                         "the issue port are the bound, not HBM",
+                         "executed": {"fp64_instr_per_coord_step": i_exec,
+                                      "frac": (coord_steps_per_s_gpu * i_exec / peak64) if i_exec else None,
+                                      "profile": prof,
+                                      "note": "fp64-pipe utilisation actually reached: the instructions the kernel executes "
+                                              "(ncu capture) at the live rate; `frac` above uses the SURVEY 8(d) budget"},
+                         "kernel": "mlp_units_kernel<double,1,3,EM_SYM>",
                          "algorithmic": f"{I64_PER_COORD_STEP} fp64 pipe-instr per reflected coordinate-step x "
                                         f"{PATH_STEPS_PER_SOLVE * D} coordinate-steps per solve (SURVEY.md 8d)",
                          "peak_source": "hdp_measure_pipe_peak(64): DFMA saturation microbenchmark, measured live",
@@ -302,6 +334,61 @@ def run_ours(args, rank, world, local_rank):
     h.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+def strong_workloads(H):
+    """One solve large enough to occupy several GPUs: Allen-Cahn d=100 with Neumann reflection at
+    M=8, L=5 (1,184,968 path-steps) and BASELINE configs[3] (C4: non-local Fisher-KPP d=10, M=4, L=5, K=10,
+    45.4 M path-steps)."""
+    d = 100
+    ac = H.ParabolicPDEProblem(0.0, 1.0, np.zeros(d), (0.0, 0.5), g=H.ExpSumSq(0.25), f=H.FAllenCahn(1.0),
+                               neumann_bc=(np.full(d, -0.5), np.full(d, 0.5)))
+    d = 10
+    c4 = H.PIDEProblem(0.0, 0.1, np.zeros(d), (0.0, 0.5), H.ExpSumSq(1.0), H.FNLFisher(),
+                       neumann_bc=(np.full(d, -0.5), np.full(d, 0.5)))
+    a4 = H.MLP(M=4, L=5, K=10, mc_sample=H.UniformSampling(np.full(d, -0.5), np.full(d, 0.5)))
+    return {"allen_cahn_d100_M8_L5_one_solve": (ac, H.MLP(M=8, L=5, K=10)),
+            "c4_nonlocal_fisher_d10_L5_one_solve": (c4, a4)}
+
+
+def bench_strong(torch, dist, H, HD, local_rank, rank, world, reps=5):
+    """One solve sharded over all ranks through the library's own NCCL communicator (hdp_comm_init_rank): bottom
+    subtrees owned by one rank each, ONE ncclAllReduce of a double per crown node, the crown finished redundantly.
+    Time = CUDA events on the library's stream around the whole call (all-reduce included), max over ranks, best
+    of `reps`; the 1-GPU time is the same solve on a handle without communicator (rank 0).  Results must agree
+    to 1e-12 (they differ only in the order of a few sums)."""
+    hc = H.Handle(local_rank)
+    HD.attach_nccl(hc)
+    hs = H.Handle(local_rank)
+    out = {}
+    for name, (prob, alg) in strong_workloads(H).items():
+        seed = 31
+        best1, u1, st1 = None, None, None
+        for r in range(reps + 1):
+            u, st = H._ml_picard_batch(prob, alg, n_solves=1, seed=seed, handle=hs)
+            if r > 0 and (best1 is None or st["device_ms"] < best1):
+                best1, u1, st1 = st["device_ms"], float(u[0]), st
+        bestn, un, stn = None, None, None
+        for r in range(reps + 1):
+            dist.barrier()
+            torch.cuda.synchronize()
+            u, st = H._ml_picard_batch(prob, alg, n_solves=1, seed=seed, handle=hc, std_err=True)
+            ms = HD.max_over_ranks(st["device_ms"])
+            if r > 0 and (bestn is None or ms < bestn):
+                bestn, un, stn = ms, float(u[0]), st
+        ms1 = HD.min_over_ranks(best1)  # (every rank timed the 1-GPU solve; identical GPUs)
+        alln = HD.all_gather_object(un)
+        out[name] = {"path_steps": st1["path_steps"], "ms_1gpu": ms1, "ms_sharded": bestn, "speedup": ms1 / bestn,
+                     "n_gpus": world, "u_1gpu": u1, "u_sharded": un, "rel_vs_1gpu": abs(un - u1) / abs(u1),
+                     "identical_on_all_ranks": all(v == alln[0] for v in alln),
+                     "std_err": float(stn["std_err"][0]),
+                     "units_1gpu": st1["n_units"], "units_sharded": stn["n_units"], "group_1gpu": st1["group_size"],
+                     "group_sharded": stn["group_size"], "exchange_bytes": stn["exchange_bytes"],
+                     "phase_ms_1gpu": st1["phase_ms"], "phase_ms_sharded_rank0": stn["phase_ms"],
+                     "launches_sharded": stn["n_launches"]}
+    hc.close()
+    hs.close()
+    return out
 
 
 def bench_sde_loop(torch, H, h, local_rank):
@@ -340,6 +427,27 @@ def bench_sde_loop(torch, H, h, local_rank):
             out[f"sde_loop_{tag}_B{B}"] = {"path_steps_per_sec": ps, "coord_steps_per_sec": ps * d, "kernel_ms": best,
                                            "hbm_bytes": 3 * d * B * esz, "hbm_gbs": 3 * d * B * esz / (best * 1e-3) / 1e9}
             del y0, y1
+            if B == 8192:
+                # the named C3 shape, E epochs of paths per launch (hdp_sde_loop_epochs_*): one epoch alone is a
+                # single partial wave of 1600 blocks
+                for E in (16, 64):
+                    y1 = torch.zeros(d * B * E, dtype=tdt, device="cuda")
+                    y0 = torch.empty_like(y1)
+                    best = None
+                    for r in range(13):
+                        y1.zero_()
+                        torch.cuda.synchronize()
+                        H.sde_loop_epochs(prob, None, None, N, 0.1, seed=7 + r * E, device_ptrs=(y0.data_ptr(), y1.data_ptr(), 0),
+                                          B=B, n_epochs=E, dtype=dtype, async_=True, handle=h)
+                        ms = h.last_device_ms()
+                        if r >= 3:
+                            best = ms if best is None else min(best, ms)
+                    h.sync()
+                    ps = B * N * E / (best * 1e-3)
+                    out[f"sde_loop_{tag}_B{B}_x{E}_epochs"] = {
+                        "path_steps_per_sec": ps, "coord_steps_per_sec": ps * d, "kernel_ms": best, "us_per_epoch": 1e3 * best / E,
+                        "hbm_bytes": 3 * d * B * E * esz, "hbm_gbs": 3 * d * B * E * esz / (best * 1e-3) / 1e9}
+                    del y0, y1
     return out
 
 

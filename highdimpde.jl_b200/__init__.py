@@ -15,7 +15,7 @@ from .kinds import (ConstCoef, LinearCoef, QuadraticCoef, SumSq, InvSumSq, ExpSu
                     UserCoef, UserG, UserF, UserFNL)
 from .sampling import UniformSampling, NormalSampling, NoSampling, _integrate
 from .problems import PIDEProblem, ParabolicPDEProblem, PIDESolution
-from .mlp import MLP, solve, mlp_counts, _ml_picard_batch
-from .sde import _reflect, sde_loop, _mlt_sde_loop, em_ensemble
+from .mlp import MLP, solve, mlp_counts, _ml_picard_batch, _ml_picard_device
+from .sde import _reflect, sde_loop, sde_loop_device, sde_loop_epochs, _mlt_sde_loop, em_ensemble
 
 __all__ = [n for n in dir() if not n.startswith("__")]

@@ -123,6 +123,8 @@ SYMBOLS = {
     "hdp_mc_sample_f32": (_i, [_H, _VP, _VP, _i, _i, _i, _SP, _u64, _VP, _u]),
     "hdp_sde_loop_f64": (_i, [_H, _PP, _VP, _VP, _i, _i, C.c_double, _VP, _SP, _u64, _VP, _SP, _VP, _i, _i, _u]),
     "hdp_sde_loop_f32": (_i, [_H, _PP, _VP, _VP, _i, _i, C.c_float, _VP, _SP, _u64, _VP, _SP, _VP, _i, _i, _u]),
+    "hdp_sde_loop_epochs_f64": (_i, [_H, _PP, _VP, _VP, _i, _i, C.c_double, _VP, _SP, _u64, _i, _SP, _VP, _i, _u]),
+    "hdp_sde_loop_epochs_f32": (_i, [_H, _PP, _VP, _VP, _i, _i, C.c_float, _VP, _SP, _u64, _i, _SP, _VP, _i, _u]),
     "hdp_mlt_sde_loop_f64": (_i, [_H, _PP, _VP, _VP, _i, C.c_double, C.c_double, _u64, _VP, _u]),
     "hdp_mlt_sde_loop_f32": (_i, [_H, _PP, _VP, _VP, _i, C.c_float, C.c_float, _u64, _VP, _u]),
     "hdp_set_user_exprs": (_i, [_H, C.POINTER(hdp_user_exprs)]),

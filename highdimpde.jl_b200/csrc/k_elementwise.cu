@@ -261,9 +261,9 @@ int get_sde_user_module(hdp_context* h, const hdp_problem* prob, bool f32, SdeUs
 template <typename T>
 int sde_loop_impl(hdp_handle h, const hdp_problem* prob, T* y0, T* y1, int B, int nsteps, T dt, const T* ts,
                   const hdp_sampler* x0_sampler, uint64_t seed, const T* dWall_inject,
-                  const hdp_sampler* mc, T* z, int K, int normal_mode, unsigned mem_flags, int mlp_assoc = 0)
+                  const hdp_sampler* mc, T* z, int K, int normal_mode, unsigned mem_flags, int mlp_assoc = 0, int n_epochs = 1)
 {
-    if (!h || !prob || !y0 || !y1 || B < 0 || nsteps < 0) return HDP_ERR_BAD_ARG;
+    if (!h || !prob || !y0 || !y1 || B < 0 || nsteps < 0 || n_epochs < 1 || n_epochs > 65535) return HDP_ERR_BAD_ARG;
     if (normal_mode != HDP_NORMAL_DEFAULT && normal_mode != (sizeof(T) == 8 ? HDP_NORMAL_BM64 : HDP_NORMAL_BM32))
         return set_err(h, HDP_ERR_UNSUPPORTED, "normal_mode %d not supported for this element type", normal_mode);
     std::lock_guard<std::mutex> lk(h->mu);
@@ -272,7 +272,8 @@ int sde_loop_impl(hdp_handle h, const hdp_problem* prob, T* y0, T* y1, int B, in
     int rc = make_dev_problem<T>(h, prob, hdp_context::B_E, &pb, /*allow_user=*/true);
     if (rc != HDP_OK) return rc;
     const int d = prob->d;
-    const size_t n_el = (size_t)d * (size_t)B;
+    const size_t n_el = (size_t)d * (size_t)B; // per epoch
+    const size_t E = (size_t)n_epochs;
     if (n_el == 0) return HDP_OK;
     // user μ/σ: the enumerated kinds are time-independent, expressions may read t = ts[step]
     SdeUserModule* um = nullptr;
@@ -295,18 +296,18 @@ int sde_loop_impl(hdp_handle h, const hdp_problem* prob, T* y0, T* y1, int B, in
     const T* ddw = nullptr;
     if (mem_flags & HDP_MEM_DEVICE) { dy0 = y0; dy1 = y1; dz = z; ddw = dWall_inject; }
     else {
-        dy0 = (T*)ensure(h, hdp_context::B_A, n_el * sizeof(T));
-        dy1 = (T*)ensure(h, hdp_context::B_B, n_el * sizeof(T));
+        dy0 = (T*)ensure(h, hdp_context::B_A, E * n_el * sizeof(T));
+        dy1 = (T*)ensure(h, hdp_context::B_B, E * n_el * sizeof(T));
         if (!dy0 || !dy1) return HDP_ERR_ALLOC;
-        HDP_CUDA(h, cudaMemcpyAsync(dy1, y1, n_el * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+        HDP_CUDA(h, cudaMemcpyAsync(dy1, y1, E * n_el * sizeof(T), cudaMemcpyHostToDevice, h->stream));
         if (dWall_inject) {
-            T* t = (T*)ensure(h, hdp_context::B_C, n_el * (size_t)nsteps * sizeof(T));
+            T* t = (T*)ensure(h, hdp_context::B_C, E * n_el * (size_t)nsteps * sizeof(T));
             if (!t) return HDP_ERR_ALLOC;
-            HDP_CUDA(h, cudaMemcpyAsync(t, dWall_inject, n_el * (size_t)nsteps * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+            HDP_CUDA(h, cudaMemcpyAsync(t, dWall_inject, E * n_el * (size_t)nsteps * sizeof(T), cudaMemcpyHostToDevice, h->stream));
             ddw = t;
         }
         if (want_z) {
-            dz = (T*)ensure(h, hdp_context::B_D, n_el * (size_t)K * sizeof(T));
+            dz = (T*)ensure(h, hdp_context::B_D, E * n_el * (size_t)K * sizeof(T));
             if (!dz) return HDP_ERR_ALLOC;
         }
     }
@@ -317,7 +318,8 @@ int sde_loop_impl(hdp_handle h, const hdp_problem* prob, T* y0, T* y1, int B, in
         return set_err(h, HDP_ERR_BAD_ARG, "sde_loop!: more than 2^24 steps/samples or 2^37 vec-groups");
     const bool al = (n_el % VEC == 0) && aligned16(dy0) && aligned16(dy1) && aligned16(dz) && aligned16(ddw);
     const int threads = 128;
-    const int grid = grid_for(h, nv, threads, 64);
+    const int grid_x = grid_for(h, nv, threads, 64);
+    const dim3 grid((unsigned)grid_x, (unsigned)n_epochs); // blockIdx.y = epoch (k_sde.cuh)
     const bool const_coef = prob->mu_kind == HDP_COEF_CONST && prob->sigma_kind == HDP_COEF_CONST && !mlp_assoc;
     const int bc = !const_coef ? K1_GENERIC
                    : !pb.has_bc ? K1_NOBC
@@ -342,7 +344,7 @@ int sde_loop_impl(hdp_handle h, const hdp_problem* prob, T* y0, T* y1, int B, in
         u64 seed_ = seed;
         void* args[] = {&pb, &dy0, &dy1, &n_el_, &nsteps, &dt, &x0s, &x0_inject, &seed_, &ddw, &mcs, &dz, &K,
                         &flags, &bctr, &mlp_assoc, &zero, &dts};
-        HDP_CUDA(h, cudaLaunchKernel((const void*)um->sde[al ? 1 : 0][ddw ? 1 : 0], dim3(grid), dim3(threads), args, 0, h->stream));
+        HDP_CUDA(h, cudaLaunchKernel((const void*)um->sde[al ? 1 : 0][ddw ? 1 : 0], grid, dim3(threads), args, 0, h->stream));
     } else if (al && ddw) LAUNCH(true, true);
     else if (al) LAUNCH(true, false);
     else if (ddw) LAUNCH(false, true);
@@ -353,9 +355,9 @@ int sde_loop_impl(hdp_handle h, const hdp_problem* prob, T* y0, T* y1, int B, in
     h->launches++;
     HDP_CUDA(h, cudaGetLastError());
     if (!(mem_flags & HDP_MEM_DEVICE)) {
-        HDP_CUDA(h, cudaMemcpyAsync(y0, dy0, n_el * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
-        HDP_CUDA(h, cudaMemcpyAsync(y1, dy1, n_el * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
-        if (want_z) HDP_CUDA(h, cudaMemcpyAsync(z, dz, n_el * (size_t)K * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+        HDP_CUDA(h, cudaMemcpyAsync(y0, dy0, E * n_el * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+        HDP_CUDA(h, cudaMemcpyAsync(y1, dy1, E * n_el * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+        if (want_z) HDP_CUDA(h, cudaMemcpyAsync(z, dz, E * n_el * (size_t)K * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
     }
     if ((mem_flags & HDP_MEM_DEVICE) && (mem_flags & HDP_ASYNC)) return HDP_OK;
     if (prob->has_bc || !(mem_flags & HDP_MEM_DEVICE)) return check_flag(h, "sde_loop!");
@@ -546,4 +548,18 @@ extern "C" int hdp_sde_loop_f32(hdp_handle h, const hdp_problem* prob, float* y0
 {
     return sde_loop_impl<float>(h, prob, y0, y1, B, nsteps, dt, ts, x0_sampler, seed, dWall_inject, mc, z, K,
                                 normal_mode, mem_flags);
+}
+extern "C" int hdp_sde_loop_epochs_f64(hdp_handle h, const hdp_problem* prob, double* y0, double* y1, int B, int nsteps,
+                                       double dt, const double* ts, const hdp_sampler* x0_sampler, uint64_t seed,
+                                       int n_epochs, const hdp_sampler* mc, double* z, int K, unsigned mem_flags)
+{
+    return sde_loop_impl<double>(h, prob, y0, y1, B, nsteps, dt, ts, x0_sampler, seed, nullptr, mc, z, K,
+                                 HDP_NORMAL_DEFAULT, mem_flags, 0, n_epochs);
+}
+extern "C" int hdp_sde_loop_epochs_f32(hdp_handle h, const hdp_problem* prob, float* y0, float* y1, int B, int nsteps,
+                                       float dt, const float* ts, const hdp_sampler* x0_sampler, uint64_t seed,
+                                       int n_epochs, const hdp_sampler* mc, float* z, int K, unsigned mem_flags)
+{
+    return sde_loop_impl<float>(h, prob, y0, y1, B, nsteps, dt, ts, x0_sampler, seed, nullptr, mc, z, K,
+                                HDP_NORMAL_DEFAULT, mem_flags, 0, n_epochs);
 }

@@ -19,22 +19,26 @@
 namespace hdp {
 
 // Launch tuning of the units kernel (measured on B200, BASELINE C1/C2/C4/C5): points with many
-// vec-groups per lane (d >= 100) run best with three of them in flight per pass — three
-// independent Philox / Box–Muller chains — at 4 blocks per SM (128 registers); short rows (d = 10:
-// five vec-groups per lane) with one chain at 6 blocks per SM (80 registers).  U is a template
+// vec-groups per lane run best with three or four of them in flight per pass — independent
+// Philox / Box–Muller chains — at 4 blocks per SM (128 registers): four for rows of >= 48 vec-groups
+// per lane (d = 100 with one lane per point, d = 1000 with eight), three for rows of 12..47 (wide
+// lane groups in the latency regime; a fourth chain lost 5-20 % there); short rows (d = 10: five
+// vec-groups per lane) with one chain at 6 blocks per SM (80 registers).  U is a template
 // parameter of the kernel; the host picks it from the row length.
-template <int U> struct Tune {
-#ifdef HDP_MLP_MINBLOCKS
-    static constexpr int MB = HDP_MLP_MINBLOCKS;
-#else
-    static constexpr int MB = U >= 2 ? 4 : 6;
+#ifndef HDP_MLP_LONG_MINBLOCKS
+#define HDP_MLP_LONG_MINBLOCKS 4
 #endif
+template <int U> struct Tune {
+    static constexpr int MB = U >= 2 ? HDP_MLP_LONG_MINBLOCKS : 6;
 };
 #ifndef HDP_MLP_BLOCK
 #define HDP_MLP_BLOCK 128 // threads per block of the expand and units kernels
 #endif
 #ifndef HDP_EM_PRELOAD
 #define HDP_EM_PRELOAD 1
+#endif
+#ifndef HDP_EM_PREFETCH
+#define HDP_EM_PREFETCH 0 // long rows: 1 / 2 = prefetch the start points of the next pass into L1 / L2 (measured: profiles/r2a_*)
 #endif
 template <int N> struct IntTag { static constexpr int value = N; };
 struct FullTag { static constexpr bool value = true; };
@@ -174,13 +178,19 @@ enum { EM_NOBC = 1, EM_SYM = 2, EM_BOX = 3 };
 // parked in a small per-thread stash (local memory: write-back cached, unlike a global store),
 // and finished after the loop.  The loop body therefore has no branch, no call and no
 // convergence barrier.
-template <typename T, int G, int MODE, int U = 1>
+template <typename T, int G, int MODE, int U = 1, bool MU0 = false>
 __device__ __forceinline__ T em_loop_fast(const MlpParams<T>& P, const DrawK<T>& dk, u64 seed, int lane, const T* sp,
                                           uint32_t sstride, T* dp, uint32_t dstride, bool store, bool check_src, T s,
                                           T tend, u64 ord, int& nb, int& bad)
 {
     constexpr int VEC = Tr<T>::VEC;
     constexpr bool BC = MODE != EM_NOBC;
+#ifndef HDP_HOST_EMU
+    // points and scratch rows are cudaMalloc'ed: keep the compiler on LDG/STG (it falls back to generic
+    // LD/ST when it loses track of the address space across the two copies of this loop)
+    __builtin_assume(__isGlobal(sp));
+    __builtin_assume(__isGlobal(dp));
+#endif
     const int d = P.pb.d, nvec = P.nvec;
     const T lo_s = MODE == EM_SYM ? -P.pb.hi_s : P.pb.lo_s, hi_s = P.pb.hi_s;
     const T dt = sub_rn(tend, s);  // :415
@@ -228,13 +238,25 @@ __device__ __forceinline__ T em_loop_fast(const MlpParams<T>& P, const DrawK<T>&
                 o[u] = ldv<T>(sp);
                 sp += sstride;
             }
+#if HDP_EM_PREFETCH && !defined(HDP_HOST_EMU)
+            if (UU > 1) {
+#pragma unroll
+                for (int u = 0; u < UU; ++u) {
+                    if (p + (UU + u) * G >= nvec) continue; // only vec-groups of this row
+                    if (HDP_EM_PREFETCH == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(sp + (size_t)u * sstride));
+                    else asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + (size_t)u * sstride));
+                }
+            }
+#endif
         }
         const unsigned bit0 = 1u << it; // this pass's first bit of `fix`
 #pragma unroll
         for (int u = 0; u < UU; ++u) {
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
-                o[u].v[e] = add_rn(o[u].v[e], add_rn(mudt, mul_rn(sgsq, xi[u].v[e]))); // :417
+                // :417  x + (μ dt + (σ sq) ξ); with μ = 0 the inner sum is its second term (0 + y = y), one rounding less to issue
+                const T dx = mul_rn(sgsq, xi[u].v[e]);
+                o[u].v[e] = add_rn(o[u].v[e], MU0 ? dx : add_rn(mudt, dx));
                 if (!FULL && !((p + u * G) * VEC + e < d)) o[u].v[e] = MODE == EM_BOX ? lo_s : (T)0; // padding never reflects
             }
             bool again = false;
@@ -275,16 +297,26 @@ __device__ __forceinline__ T em_loop_fast(const MlpParams<T>& P, const DrawK<T>&
             if (store) stv<T>(dp0 + (size_t)j * dstride, o);
         }
     };
+    const int nrag = (nvec % G) ? (nvec / G) * G : nvec; // vec-groups below this index form rows that every lane owns
     int p = lane;
     while (p < nvec) {
         // at most 32 vec-groups per chunk: one bit each in `fix`
         it = 0;
         dp0 = dp;
         p0 = p;
-        const int pe = p + 32 * G < nfull ? p + 32 * G : nfull;
+        // rows every lane of the group owns first: all lanes then run the same passes (a lane with one vec-group
+        // more than its neighbours would drag the whole warp through its own tail passes)
+        const int lim = nfull < nrag ? nfull : nrag;
+        const int pe = p + 32 * G < lim ? p + 32 * G : lim;
         if (U > 1)
             for (; p + (U - 1) * G < pe; p += U * G) body(p, FullTag{}, IntTag<U>{});
+        if (U > 2) // what is left of the chunk, still two at a time (d = 100: 50 vec-groups = 12 passes of four + one of two)
+            for (; p + G < pe; p += 2 * G) body(p, FullTag{}, IntTag<2>{});
         for (; p < pe; p += G) body(p, FullTag{}, IntTag<1>{});
+        if (p >= nrag && p < nfull && it < 32) { // the ragged last row: only some lanes own a vec-group there
+            body(p, FullTag{}, IntTag<1>{});
+            p += G;
+        }
         if (p >= nfull && p < nvec && it < 32) { // the one partial vec-group (d % VEC != 0), if this lane owns it
             body(p, PartTag{}, IntTag<1>{});
             p += G;
@@ -521,6 +553,7 @@ __device__ __forceinline__ T run_unit_iter(Ctx<T, G>& c, const MlpParams<T>& P, 
     const int lane = c.lane;
     const unsigned gmask = c.gmask;
     const bool f_uses_z = pb.f_kind == HDP_F_NL_REPLICATOR || pb.f_kind == HDP_F_NL_USER;
+    const bool mu0 = MODE != 0 && pb.mu_c == (T)0;
     const DrawK<T> dk = draw_k_init<T>(P.zero & (lane + 1)); // 0, but neither constant nor uniform to the compiler
     // The frame of the innermost active call lives in shared memory, one private copy per thread
     // (the lanes of a group keep identical copies: no cell is shared, so nothing depends on the
@@ -562,6 +595,9 @@ __device__ __forceinline__ T run_unit_iter(Ctx<T, G>& c, const MlpParams<T>& P, 
         // One pass runs the bookkeeping from the result of the last action to the next one.  The
         // handlers are ordered so that every transition except "return to the parent" lands on a
         // handler further down the same pass.
+#ifdef HDP_FRAME_SHARED_EXPERIMENT
+        if (G > 1) __syncwarp(gmask);
+#endif
         int l = F->l;
         int act = ACT_NONE;
         // action parameters
@@ -709,10 +745,15 @@ __device__ __forceinline__ T run_unit_iter(Ctx<T, G>& c, const MlpParams<T>& P, 
                 feat = em_step_generic<T, G>(c, xs, a_store ? &xd : nullptr, a_s, a_t, a_ord);
             } else {
                 const XAcc<T> xd = c.slot(a_store ? a_dst : 0);
-                const T ssq = em_loop_fast<T, G, MODE, U>(P, dk, seed, lane, xs.base + xs.voff * VEC,
-                                                       (uint32_t)xs.vstride * VEC, xd.base + xd.voff * VEC,
-                                                       (uint32_t)xd.vstride * VEC, a_store, xs.unchecked != 0, a_s,
-                                                       a_t, a_ord, nb, bad);
+                // (μ = 0 — every BASELINE configuration — is a property of the launch: no lane ever takes the other copy)
+                const T ssq = mu0 ? em_loop_fast<T, G, MODE, U, true>(P, dk, seed, lane, xs.base + xs.voff * VEC,
+                                                                    (uint32_t)xs.vstride * VEC, xd.base + xd.voff * VEC,
+                                                                    (uint32_t)xd.vstride * VEC, a_store, xs.unchecked != 0,
+                                                                    a_s, a_t, a_ord, nb, bad)
+                                  : em_loop_fast<T, G, MODE, U, false>(P, dk, seed, lane, xs.base + xs.voff * VEC,
+                                                                     (uint32_t)xs.vstride * VEC, xd.base + xd.voff * VEC,
+                                                                     (uint32_t)xd.vstride * VEC, a_store, xs.unchecked != 0,
+                                                                     a_s, a_t, a_ord, nb, bad);
                 feat.ssq = gsum<T, G>(ssq, gmask);
             }
         } else {
@@ -864,9 +905,13 @@ __device__ __forceinline__ void unit_item(Ctx<T, G>& c, const MlpParams<T>& P, u
 //   CMB_FINAL    the all-reduced slot + the node's upper sites (replicated)  -> value[node]
 // A node's value is linear in its units and in the f-terms of its sites, so the three add up.
 // The root node also gathers n, sum and sum of squares of its samples per level (the error bar).
+// nl > 32 (device only): a whole block shares the node — the root of a finely cut tree has ten thousand
+// children, and a single warp walking them through dependent loads was 0.4 ms of a 1.2 ms solve; `xwarp`
+// is then the block's shared staging area (kCmbStage doubles per warp) for the fixed-order sum over its warps.
+constexpr int kCmbStage = kMaxL + 1 + 3 * (kMaxL + 1);
 template <typename T>
 __device__ __forceinline__ void combine_item(const MlpParams<T>& P, const int32_t* list, u64 item, int lane, int nl,
-                                             unsigned mask = 0xffffffffu, int mode = CMB_ALL)
+                                             unsigned mask = 0xffffffffu, int mode = CMB_ALL, double* xwarp = nullptr)
 {
     const int solve = (int)(item % (u64)P.n_solves);
     const int nidx = list[item / (u64)P.n_solves];
@@ -964,8 +1009,8 @@ __device__ __forceinline__ void combine_item(const MlpParams<T>& P, const int32_
                     if (stats) { Ns[q] += 1.0; Sm[q] += (double)add; Sq[q] += (double)add * (double)add; }
                 }
         }
-        if (nl > 1) { // butterfly over the nl lanes of this node (an aligned sub-warp group)
-            for (int o = nl >> 1; o > 0; o >>= 1) {
+        if (nl > 1) { // butterfly over the lanes of this node inside a warp (an aligned group of min(nl, 32) lanes)
+            for (int o = (nl > 32 ? 32 : nl) >> 1; o > 0; o >>= 1) {
 #pragma unroll
                 for (int l = 0; l < kMaxL; ++l) Bl[l] += __shfl_xor_sync(mask, Bl[l], o);
                 Gs += __shfl_xor_sync(mask, Gs, o);
@@ -979,6 +1024,30 @@ __device__ __forceinline__ void combine_item(const MlpParams<T>& P, const int32_
                 }
             }
         }
+#ifndef HDP_HOST_EMU
+        if (nl > 32) { // then over the warps of the block, in warp order
+            const int w = lane >> 5, nw = nl >> 5;
+            if ((lane & 31) == 0) {
+                double* q = xwarp + w * kCmbStage;
+                for (int l = 0; l < kMaxL; ++l) q[l] = (double)Bl[l];
+                q[kMaxL] = (double)Gs;
+                for (int l = 0; l <= kMaxL; ++l) {
+                    q[kMaxL + 1 + 3 * l] = Ns[l]; q[kMaxL + 2 + 3 * l] = Sm[l]; q[kMaxL + 3 + 3 * l] = Sq[l];
+                }
+            }
+            __syncthreads();
+            if (lane == 0) {
+                for (int ww = 1; ww < nw; ++ww) {
+                    const double* q = xwarp + ww * kCmbStage;
+                    for (int l = 0; l < kMaxL; ++l) Bl[l] += (T)q[l];
+                    Gs += (T)q[kMaxL];
+                    for (int l = 0; l <= kMaxL; ++l) {
+                        Ns[l] += q[kMaxL + 1 + 3 * l]; Sm[l] += q[kMaxL + 2 + 3 * l]; Sq[l] += q[kMaxL + 3 + 3 * l];
+                    }
+                }
+            }
+        }
+#endif
         T a = (T)0;
 #pragma unroll
         for (int l = 0; l < kMaxL; ++l)
@@ -1066,7 +1135,11 @@ __global__ void __launch_bounds__(HDP_MLP_BLOCK, Tune<U>::MB) mlp_units_kernel(c
         if (threadIdx.x == 0) atomicExch(&P.flags[1], 1);
         return;
     }
+#ifdef HDP_FRAME_SHARED_EXPERIMENT
+    c.frame_mem = reinterpret_cast<Frame<T>*>(hdp_dyn_smem) + threadIdx.x / G;
+#else
     c.frame_mem = reinterpret_cast<Frame<T>*>(hdp_dyn_smem) + threadIdx.x; // one private frame per thread
+#endif
     const int sub = lane_w / G;
     const u64 n_work = (u64)P.n_exec * (u64)P.n_solves; // this rank's units (all of them on one GPU)
     for (;;) {
@@ -1083,7 +1156,7 @@ __global__ void __launch_bounds__(HDP_MLP_BLOCK, Tune<U>::MB) mlp_units_kernel(c
 // nl lanes (a power of two, 1..32) share one (node, solve): 32 where nodes have many children (the
 // root of a deeply cut tree has thousands), 4 where they have a handful
 template <typename T>
-__global__ void __launch_bounds__(128) mlp_combine_kernel(const __grid_constant__ MlpParams<T> P, const int32_t* list, int count,
+__global__ void __launch_bounds__(512) mlp_combine_kernel(const __grid_constant__ MlpParams<T> P, const int32_t* list, int count,
                                                           int nl, int mode)
 {
     const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1093,12 +1166,13 @@ __global__ void __launch_bounds__(128) mlp_combine_kernel(const __grid_constant_
         if (mode == CMB_PARTIAL) tail[4] = (double)*P.bounce_ctr;
         if (mode == CMB_FINAL && list[0] == 0) *P.bounce_ctr = (unsigned long long)tail[4];
     }
+    __shared__ double xwarp[16 * kCmbStage]; // nl > 32: one node per block of nl <= 512 threads
     const u64 gid = t / (unsigned)nl;
     if (gid >= (u64)count * (u64)P.n_solves) return; // (the nl lanes of a node leave together)
     // the shuffles of a node stay inside its own nl lanes: the root's statistics are reduced by its group alone
     const int lane = (int)(t % (unsigned)nl);
     const unsigned mask = nl >= 32 ? 0xffffffffu : (((1u << nl) - 1u) << ((threadIdx.x & 31) - lane));
-    combine_item<T>(P, list, gid, lane, nl, mask, mode);
+    combine_item<T>(P, list, gid, lane, nl, mask, mode, xwarp);
 }
 
 // sharded solve: the all-reduced values of the whole-call leaves below upper sites go back to partial[],

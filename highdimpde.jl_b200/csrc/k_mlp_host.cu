@@ -289,8 +289,9 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
     const int block = HDP_MLP_BLOCK;
     // dynamic shared memory of the units kernel: one private Frame<T> per thread (k_mlp.cuh, run_unit_iter)
     const size_t dyn_smem = (size_t)block * sizeof(Frame<T>);
-    // long rows: three vec-groups per pass (Tune<U>, k_mlp.cuh)
-    const int long_rows = (nvec + G - 1) / G >= 12 ? 1 : 0;
+    // long rows: three vec-groups per pass, very long rows four (Tune<U>, k_mlp.cuh)
+    const int npl_ = (nvec + G - 1) / G;
+    const int long_rows = npl_ >= 48 ? 2 : (npl_ >= 12 ? 1 : 0);
     int bps = 0;
     if (um) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, (const void*)um->units, block, dyn_smem) != cudaSuccess) {
@@ -463,13 +464,15 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
             const PlanNode& nd = plan->nodes[host_list[q]];
             most = std::max(most, (nd.unit_end - nd.unit_begin) + (nd.site_end - nd.site_begin));
         }
-        int nl = most > 16 ? 32 : 4;
+        // a handful of children: 4 lanes; many: a warp; thousands (the root of a finely cut tree): a block of 512
+        const int nl = most > 2048 ? 512 : (most > 16 ? 32 : 4);
+        const int cb = nl > 128 ? nl : 128; // threads per block (one node per block when nl > 32)
         uint64_t tot = (uint64_t)cnt * n_solves * nl;
-        int gc = (int)((tot + 127) / 128);
+        int gc = (int)((tot + cb - 1) / cb);
         if (um) { // f is applied in the combine too: the user module's build of it
             void* args[5] = {(void*)&P, (void*)&list, (void*)&cnt, (void*)&nl, (void*)&cmode};
-            HDP_CUDA(h, cudaLaunchKernel((const void*)um->combine, dim3(gc), dim3(128), args, 0, h->stream));
-        } else mlp_combine_kernel<T><<<gc, 128, 0, h->stream>>>(P, list, cnt, nl, cmode);
+            HDP_CUDA(h, cudaLaunchKernel((const void*)um->combine, dim3(gc), dim3(cb), args, 0, h->stream));
+        } else mlp_combine_kernel<T><<<gc, cb, 0, h->stream>>>(P, list, cnt, nl, cmode);
         h->launches++;
         HDP_CUDA(h, cudaGetLastError());
         return HDP_OK;

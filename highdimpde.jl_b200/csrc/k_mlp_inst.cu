@@ -45,6 +45,7 @@ MlpLaunchers<HDP_INST_T> HDP_INST_NAME()
     HDP_SET(0, 1, 0) HDP_SET(0, 1, 1) HDP_SET(0, 1, 2) HDP_SET(0, 1, 3)
     // the general form always walks one vec-group per pass: long rows only change its launch bounds
     HDP_SET(1, 3, 0) HDP_SET(1, 3, 1) HDP_SET(1, 3, 2) HDP_SET(1, 3, 3)
+    HDP_SET(2, 4, 0) HDP_SET(2, 4, 1) HDP_SET(2, 4, 2) HDP_SET(2, 4, 3)
 #undef HDP_SET
     l.expand = inst_expand;
     return l;

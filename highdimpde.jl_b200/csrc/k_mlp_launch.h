@@ -7,10 +7,11 @@
 namespace hdp {
 
 template <typename T> struct MlpLaunchers {
-    // [0]: one vec-group per pass (short rows), [1]: three per pass (long rows); second index: the mode of
-    // the coordinate loop the kernel was compiled for (em_mode_of: 0 general, EM_NOBC, EM_SYM, EM_BOX)
-    int (*max_blocks_per_sm[2][4])(int block, size_t dyn_smem);
-    cudaError_t (*units[2][4])(const MlpParams<T>& P, int grid, int block, size_t dyn_smem, cudaStream_t st);
+    // [0]: one vec-group per pass (short rows), [1]: three per pass (long rows), [2]: four per pass (very long
+    // rows: >= 48 vec-groups per lane, measured in profiles/r2c_*, r2j_*); second index: the mode of the
+    // coordinate loop the kernel was compiled for (em_mode_of: 0 general, EM_NOBC, EM_SYM, EM_BOX)
+    int (*max_blocks_per_sm[3][4])(int block, size_t dyn_smem);
+    cudaError_t (*units[3][4])(const MlpParams<T>& P, int grid, int block, size_t dyn_smem, cudaStream_t st);
     cudaError_t (*expand)(const MlpParams<T>& P, const int32_t* list, int count, int count_hits, int grid, int block, cudaStream_t st);
 };
 

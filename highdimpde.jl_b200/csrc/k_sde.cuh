@@ -96,6 +96,16 @@ sde_loop_kernel(DevProblem<T> pb, T* __restrict__ y0, T* __restrict__ y1, size_t
 {
     constexpr int VEC = Tr<T>::VEC;
     if constexpr (sizeof(T) == 8) tables_init();
+    // blockIdx.y: the epoch of a multi-epoch launch (hdp_sde_loop_epochs_*): epoch e works on slice e of every
+    // array with seed + e, exactly as a call of its own would — DeepSplitting's paths do not depend on the
+    // network, so several training epochs' worth are simulated per launch (src/DeepSplitting.jl:181-195)
+    if (const size_t ep = blockIdx.y) {
+        y0 += ep * n_el; y1 += ep * n_el;
+        if (dW) dW += ep * n_el * (size_t)nsteps;
+        if (x0_inject) x0_inject += ep * n_el;
+        if (z) z += ep * n_el * (size_t)K;
+        seed += ep;
+    }
     const int d = pb.d;
     const size_t nv = (n_el + VEC - 1) / VEC;
     const T sq = sqrt_rn(dt);

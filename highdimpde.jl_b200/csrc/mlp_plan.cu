@@ -63,6 +63,7 @@ int64_t mlp_get_loop_num(int M, int64_t num, int thread_id, int nthreads)
 }
 
 namespace {
+constexpr double kMinExplicitCall = 64.0, kMinExplicitCallNonlocal = 16.0;
 struct Builder {
     MlpPlan* p;
     const MlpCountTables& t;
@@ -85,7 +86,13 @@ struct Builder {
     void do_level(int id, int depth, int l, int64_t nsites, uint64_t& c, uint64_t& r, uint64_t& s)
     {
         if (nsites <= 0) return;
-        if (l >= 1 && t.W[l] > thresh) {
+        // Sites become explicit (their child calls separate units, f applied in the combine pass) only where the
+        // child call is worth a launch-level detour: below kMinExplicitCall path-steps (U_1: 2M steps) the
+        // geometry and combine passes cost more than the finer units buy (measured: Allen-Cahn d=100, M=8, L=5
+        // one solve 0.99 -> 0.73 ms; and the C4 plan one level deeper has 16 M units), so such sites stay in
+        // slice units, one site per unit at the finest.  A non-local site fans out into 1 + K child calls per
+        // level, so there the detour pays from smaller calls on (replicator-mutator d=10, L=4: 1.16 vs 2.69 ms).
+        if (l >= 1 && t.W[l] > thresh && t.W[l] >= (t.Kp > 0 ? kMinExplicitCallNonlocal : kMinExplicitCall)) {
             for (int64_t k = 0; k < nsites; ++k) {
                 PlanSite st{};
                 st.node = id; st.l = l; st.depth = depth;

@@ -73,6 +73,15 @@ def max_over_ranks(x: float) -> float:
     return float(t.item())
 
 
+def min_over_ranks(x: float) -> float:
+    import torch
+    dist = _dist()
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return float(t.item())
+
+
 def attach_nccl(handle):
     """Join this rank's handle to an NCCL communicator over all ranks."""
     dist = _dist()

@@ -110,6 +110,34 @@ def _ml_picard_batch(prob: _Problem, alg: MLP, *, n_solves=1, x0=None, seed=0, t
     return u, stats
 
 
+def _ml_picard_device(prob: _Problem, alg: MLP, x0_ptr: int, u_ptr: int, *, n_solves=1, n_x0=1, seed=0, dtype=np.float64,
+                      std_err_ptr: int = 0, async_=False, group_size=0, handle=None):
+    """The same solve with device-resident arguments (Julia: `CuArray`s handed over as `CuPtr`): x0 (d×n_x0),
+    u (n_solves) and the optional standard errors are raw device addresses; with async_=True the call only
+    enqueues (finish with handle.sync(), which also reports a start point outside the box)."""
+    h = handle or capi.default_handle()
+    dt = np.dtype(dtype)
+    pb, keep = prob.to_c()
+    cfg = capi.hdp_mlp_cfg()
+    cfg.M, cfg.L, cfg.K = alg.M, alg.L, alg.K
+    cfg.n_solves, cfg.n_x0 = int(n_solves), int(n_x0)
+    cfg.normal_mode = capi.HDP_NORMAL_DEFAULT
+    cfg.group_size = int(group_size)
+    cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    cfg.mem_flags = capi.HDP_MEM_DEVICE | (capi.HDP_ASYNC if async_ else 0)
+    cfg.std_err_out = int(std_err_ptr) or None
+    sm, keep2 = alg.mc_sample._descriptor(prob.d)
+    cfg.sampler = sm
+    ue = prob.user_exprs()
+    if ue is not None:
+        cfg.user = C.pointer(ue)
+    st = capi.hdp_mlp_stats()
+    fn = h.lib.hdp_mlp_solve_f64 if dt == np.float64 else h.lib.hdp_mlp_solve_f32
+    capi.check(h.h, fn(h.h, C.byref(pb), C.byref(cfg), C.c_void_p(int(x0_ptr)), C.c_void_p(int(u_ptr)), C.byref(st)))
+    del keep, keep2
+    return st
+
+
 def solve(prob, alg, *args, multithreading=True, verbose=False, seed=None, **kw):
     """SciMLBase.solve(prob, alg::MLP; multithreading = true, verbose = false) (src/MLP.jl:43-100).
 

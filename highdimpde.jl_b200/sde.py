@@ -92,6 +92,60 @@ def sde_loop(prob, y0, y1, nsteps, dt, *, ts=None, dWall=None, seed=0, mc_sample
     return y0, y1
 
 
+def sde_loop_epochs(prob, y0, y1, nsteps, dt, *, seed=0, mc_sample=None, z=None, device_ptrs=None, B=None, n_epochs=None,
+                    dtype=None, async_=False, handle=None):
+    """E epochs of `y1 .= x0_batch; sde_loop!(y0, y1, dWall)` (src/DeepSplitting.jl:181-184) in one launch: y0, y1 are
+    d×B×E column-major (y1 holds every epoch's start points), z optionally d×B×K×E; slice e is what
+    sde_loop(..., seed=seed + e) returns.  With device_ptrs=(y0_ptr, y1_ptr, z_ptr) the arrays are device-resident
+    (give B, n_epochs, dtype) and nothing crosses PCIe."""
+    h = handle or capi.default_handle()
+    pb, keep = prob.to_c()
+    x0s, keep2 = prob.x0_sample._descriptor(prob.d)
+    mcs, keep3 = (mc_sample or NoSampling())._descriptor(prob.d)
+    ue = _set_user_coefs(h, prob)
+    if device_ptrs is None:
+        dtp = y1.dtype
+        if y1.ndim != 3 or not y1.flags.f_contiguous or y0.shape != y1.shape or y0.dtype != dtp or not y0.flags.f_contiguous:
+            raise ValueError("y0, y1 must be d×B×E column-major arrays of one element type")
+        d, B, n_epochs = y1.shape
+        K = 0
+        if z is not None:
+            if z.dtype != dtp or not z.flags.f_contiguous or z.ndim != 4 or z.shape[:2] != (d, B) or z.shape[3] != n_epochs:
+                raise ValueError("z must be d×B×K×E column-major")
+            K = z.shape[2]
+        p0, p1, pz, flags = capi.np_ptr(y0), capi.np_ptr(y1), capi.np_ptr(z), capi.HDP_MEM_HOST
+    else:
+        dtp = np.dtype(dtype)
+        vp = lambda a: C.c_void_p(int(a)) if a else None
+        p0, p1, pz = (vp(a) for a in device_ptrs)
+        K = int(z or 0)  # with device pointers `z` carries K
+        flags = capi.HDP_MEM_DEVICE | (capi.HDP_ASYNC if async_ else 0)
+    fn, dtc = (h.lib.hdp_sde_loop_epochs_f64, C.c_double(dt)) if dtp == np.float64 else (h.lib.hdp_sde_loop_epochs_f32, C.c_float(dt))
+    capi.check(h.h, fn(h.h, C.byref(pb), p0, p1, int(B), int(nsteps), dtc, None, C.byref(x0s), int(seed), int(n_epochs),
+                       C.byref(mcs), pz, K, flags))
+    del keep, keep2, keep3, ue
+    return y0, y1
+
+
+def sde_loop_device(prob, y0_ptr: int, y1_ptr: int, B: int, nsteps: int, dt, *, dtype=np.float32, seed=0, dWall_ptr: int = 0,
+                    mc_sample=None, z_ptr: int = 0, K: int = 0, async_=False, handle=None):
+    """`sde_loop!` on device-resident arrays (Julia: `CuArray`s handed over as `CuPtr`): y0, y1 (d×B), the optional
+    injected dWall (d×B×nsteps) and z (d×B×K) are raw device addresses; nothing crosses PCIe.  With async_=True
+    the call only enqueues on the handle's stream (finish with handle.sync())."""
+    h = handle or capi.default_handle()
+    dtp = np.dtype(dtype)
+    pb, keep = prob.to_c()
+    x0s, keep2 = prob.x0_sample._descriptor(prob.d)
+    mcs, keep3 = (mc_sample or NoSampling())._descriptor(prob.d)
+    ue = _set_user_coefs(h, prob)
+    fn, dtc = (h.lib.hdp_sde_loop_f64, C.c_double(dt)) if dtp == np.float64 else (h.lib.hdp_sde_loop_f32, C.c_float(dt))
+    flags = capi.HDP_MEM_DEVICE | (capi.HDP_ASYNC if async_ else 0)
+    vp = lambda a: C.c_void_p(int(a)) if a else None
+    capi.check(h.h, fn(h.h, C.byref(pb), vp(y0_ptr), vp(y1_ptr), int(B), int(nsteps), dtc, None, C.byref(x0s), int(seed),
+                       vp(dWall_ptr), C.byref(mcs), vp(z_ptr), int(K), capi.HDP_NORMAL_DEFAULT, flags))
+    del keep, keep2, keep3, ue
+
+
 def _mlt_sde_loop(x2, x, s, t, prob, *, normals=None, seed=0, handle=None):
     """_mlt_sde_loop!(x2, x, s, t, prob, neumann_bc) (src/MLP.jl:406-421): one Euler–Maruyama step
     s -> t of the MLP recursion (x2 = x + (μ*dt + σ*sqrt(dt)*ξ), then `_reflect`), mutating x2.

@@ -363,6 +363,21 @@ int hdp_sde_loop_f32(hdp_handle h, const hdp_problem* prob, float* y0, float* y1
                      const hdp_sampler* mc, float* z, int K,
                      int normal_mode, unsigned mem_flags);
 
+/* Several epochs of paths per launch.  In DeepSplitting's training loop
+ * (src/DeepSplitting.jl:181-195) every epoch calls `y1 .= x0_batch; sde_loop!(y0, y1, dWall)` and
+ * then takes one gradient step; the paths do not depend on the network, so E epochs' worth can be
+ * simulated by one launch and consumed one slice per epoch.  y0, y1: d×B×E (y1 holds the start
+ * points of every epoch on entry), z: d×B×K×E.  Slice e is bit for bit what
+ * hdp_sde_loop_*(…, seed + e, dWall_inject = NULL, …) returns for it.  1 <= n_epochs <= 65535. */
+int hdp_sde_loop_epochs_f64(hdp_handle h, const hdp_problem* prob, double* y0, double* y1,
+                            int B, int nsteps, double dt, const double* ts,
+                            const hdp_sampler* x0_sampler, uint64_t seed, int n_epochs,
+                            const hdp_sampler* mc, double* z, int K, unsigned mem_flags);
+int hdp_sde_loop_epochs_f32(hdp_handle h, const hdp_problem* prob, float* y0, float* y1,
+                            int B, int nsteps, float dt, const float* ts,
+                            const hdp_sampler* x0_sampler, uint64_t seed, int n_epochs,
+                            const hdp_sampler* mc, float* z, int K, unsigned mem_flags);
+
 /* User expressions for the K1 entry points (hdp_sde_loop_*, hdp_mlt_sde_loop_*,
  * hdp_em_ensemble_*) when prob->mu_kind / sigma_kind is HDP_COEF_USER.  The strings are
  * copied into the handle (the caller's pointers are not retained); NULL clears them.

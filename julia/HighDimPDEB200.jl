@@ -3,21 +3,29 @@
 # NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no Julia toolchain.
 # The Python package `highdimpde.jl_b200/` is the 1:1 twin of this file (same
 # descriptors, same entry points, same argument order) and IS exercised by
-# `tests/`; keep the two in step.  See INTEGRATION.md.
+# `tests/`; keep the two in step.  `julia/test/runtests.jl` is what a maintainer
+# with Julia runs; INTEGRATION.md lists every method added here next to the
+# reference method it sits beside, and why the pair is unambiguous.
 #
 # What it does: user-visible `solve(prob, MLP(...))` is unchanged.  When μ, σ, g, f
 # are the callable *kind* structs below (ordinary Julia callables, so the stock CPU
 # path keeps working), `HighDimPDE._ml_picard` / `_ml_picard_mlt`
-# (src/MLP.jl:102-260) are overlaid by one `ccall` into `hdp_mlp_solve_f64/_f32`;
-# `_reflect` (src/reflect.jl) and the samplers' call operators (src/MCSample.jl)
-# get `ccall` methods for `Array`/`CuArray` arguments, and `sde_loop_b200!`
-# replaces the `sde_loop!` closure of src/DeepSplitting.jl:153-166.
+# (src/MLP.jl:102-260) are overlaid by one `ccall` into `hdp_mlp_solve_f64/_f32`.
+# `solve(prob, DeepSplitting(...), dt)`: the Euler–Maruyama loop of that solver is a
+# closure (src/DeepSplitting.jl:153-166) and cannot be overlaid from outside; with
+# the two-line hook of `julia/patches/deepsplitting_sde_loop_hook.patch` applied it
+# calls `HighDimPDE._sde_loop!`, for which this file (Array) and
+# `ext/HighDimPDEB200CUDAExt.jl` (CuArray, no PCIe copy) add `ccall` methods.
+# The Matrix method of `_reflect` (src/reflect.jl:58-82) gets a `ccall` method too.
 module HighDimPDEB200
 
 using HighDimPDE
+using Random
 import HighDimPDE: _ml_picard, _ml_picard_mlt, _reflect, UniformSampling, NormalSampling, NoSampling
 
 const libhdp = get(ENV, "HDPDE_B200_LIB", joinpath(@__DIR__, "..", "highdimpde.jl_b200", "libhdpde_b200.so"))
+const HDP_MEM_HOST, HDP_MEM_DEVICE, HDP_ASYNC = UInt32(0), UInt32(1), UInt32(2)
+const HDP_MAX_LEVELS = 6
 
 # ------------------------------------------------------------------ POD mirrors of include/hdpde.h
 struct HdpSampler
@@ -34,16 +42,34 @@ struct HdpProblem
     lo_scalar::Float64; hi_scalar::Float64
     lo::Ptr{Float64}; hi::Ptr{Float64}
 end
+struct HdpUserExprs                # CUDA-C expressions compiled by NVRTC (include/hdpde.h: hdp_user_exprs)
+    mu::Cstring; sigma::Cstring; g::Cstring; f::Cstring
+end
 struct HdpMlpCfg
     M::Int32; L::Int32; K::Int32; n_solves::Int32; n_x0::Int32; normal_mode::Int32
     compat_mlt_threads::Int32; target_units::Int32
     seed::UInt64
     sampler::HdpSampler
     r_tape::Ptr{Cvoid}; n_tape::Ptr{Cvoid}; s_tape::Ptr{Cvoid}
-    user::Ptr{Cvoid}             # Ptr{HdpUserExprs} for the *_USER kinds, else C_NULL
+    user::Ptr{HdpUserExprs}      # for the *_USER kinds, else C_NULL
+    group_size::Int32; mem_flags::UInt32
+    unit_oversub::Float64
+    std_err_out::Ptr{Cvoid}      # nullable: standard error per solve
 end
-struct HdpUserExprs                # CUDA-C expressions compiled by NVRTC (include/hdpde.h: hdp_user_exprs)
-    mu::Cstring; sigma::Cstring; g::Cstring; f::Cstring
+struct HdpMlpCounts
+    path_steps::UInt64; time_uniforms::UInt64; sampler_calls::UInt64; f_evals::UInt64; g_evals::UInt64
+end
+struct HdpMlpStats
+    per_solve::HdpMlpCounts
+    bounces::UInt64; n_units::UInt64; n_nodes::UInt64; n_sites::UInt64
+    device_ms::Float64
+    group_size::Int32; n_launches::Int32
+    phase_ms::NTuple{4, Float64}
+    level_n::NTuple{HDP_MAX_LEVELS + 1, UInt64}
+    level_sum::NTuple{HDP_MAX_LEVELS + 1, Float64}
+    level_sumsq::NTuple{HDP_MAX_LEVELS + 1, Float64}
+    std_error::Float64
+    exchange_bytes::UInt64
 end
 
 # ------------------------------------------------------------------ kinds: callable structs
@@ -51,9 +77,14 @@ end
 struct ConstCoef{T}; c::T; end;   (k::ConstCoef)(x, p, t) = k.c
 struct LinearCoef{T}; c::T; end;  (k::LinearCoef)(x, p, t) = k.c * x
 struct QuadraticCoef{T}; c::T; end;  (k::QuadraticCoef)(x, p, t) = k.c * x .^ 2   # test/DeepSplitting.jl:355
-# any other μ/σ: a CUDA-C expression over x, i, t, d, p[0..1] (compiled by NVRTC on first use) next to
-# the Julia closure that the host-side code paths keep calling
+# Anything else: a CUDA-C expression (compiled by NVRTC on first use) next to the Julia closure that the
+# host-side code paths keep calling.  μ, σ read x, i, t, d, p[0..1]; g reads ssq, mn, d, p[0..3];
+# f reads vy, vz, ssq_y, ssq_z, t, d, p[0..7] (include/hdpde.h, hdp_user_exprs).
 struct UserCoef{F}; expr::String; p::NTuple{2, Float64}; fn::F; end;  (k::UserCoef)(x, p, t) = k.fn(x, p, t)
+struct UserG{F}; expr::String; p::NTuple{4, Float64}; fn::F; end;     (k::UserG)(x) = k.fn(x)
+struct UserF{F}; expr::String; p::NTuple{8, Float64}; fn::F; end;     (k::UserF)(y, v, ∇v, p, t) = k.fn(y, v, ∇v, p, t)
+struct UserFNL{F}; expr::String; p::NTuple{8, Float64}; fn::F; end
+(k::UserFNL)(y, z, vy, vz, ∇vy, ∇vz, p, t) = k.fn(y, z, vy, vz, ∇vy, ∇vz, p, t)
 # g (test/MLP.jl:28,118,146,174,199,265)
 struct SumSq{T}; c::T; end;            (k::SumSq)(x) = sum(x .^ 2) .+ k.c
 struct InvSumSq{T}; a::T; b::T; end;   (k::InvSumSq)(x) = 1 ./ (k.a .+ k.b * sum(x .^ 2))
@@ -90,16 +121,23 @@ gkind(k::InvSumSq) = (Int32(1), (Float64(k.a), Float64(k.b), 0.0, 0.0))
 gkind(k::ExpSumSq) = (Int32(2), (Float64(k.c), 0.0, 0.0, 0.0))
 gkind(::MinCoord) = (Int32(3), (0.0, 0.0, 0.0, 0.0))
 gkind(k::GaussDensity) = (Int32(4), (Float64(k.ss0), 0.0, 0.0, 0.0))
+gkind(k::UserG) = (Int32(64), k.p)
 _p8(v...) = ntuple(i -> i <= length(v) ? Float64(v[i]) : 0.0, 8)
 fkind(::FZero) = (Int32(0), _p8());            fkind(k::FLinear) = (Int32(1), _p8(k.r))
 fkind(k::FAllenCahn) = (Int32(2), _p8(k.c));   fkind(::FFisherKPP) = (Int32(4), _p8())
 fkind(k::FDefaultRisk) = (Int32(3), _p8(k.δ, k.R, k.vh, k.vl, k.γh, k.γl))
 fkind(::FNLAllenCahnDiff) = (Int32(16), _p8()); fkind(::FNLFisher) = (Int32(17), _p8())
 fkind(k::FNLReplicatorMutator) = (Int32(18), _p8(k.σs))
+fkind(k::UserF) = (Int32(64), k.p);            fkind(k::UserFNL) = (Int32(65), k.p)
 
 const B200Coef = Union{ConstCoef, LinearCoef, QuadraticCoef, UserCoef}
-const B200G = Union{SumSq, InvSumSq, ExpSumSq, MinCoord, GaussDensity}
-const B200F = Union{FZero, FLinear, FAllenCahn, FFisherKPP, FDefaultRisk, FNLAllenCahnDiff, FNLFisher, FNLReplicatorMutator}
+const B200G = Union{SumSq, InvSumSq, ExpSumSq, MinCoord, GaussDensity, UserG}
+const B200F = Union{FZero, FLinear, FAllenCahn, FFisherKPP, FDefaultRisk, FNLAllenCahnDiff, FNLFisher,
+                    FNLReplicatorMutator, UserF, UserFNL}
+const HdpFloat = Union{Float32, Float64}
+
+user_expr(k) = nothing
+user_expr(k::Union{UserCoef, UserG, UserF, UserFNL}) = k.expr
 
 # ------------------------------------------------------------------ handle
 mutable struct Handle
@@ -112,8 +150,11 @@ mutable struct Handle
         finalizer(x -> ccall((:hdp_destroy, libhdp), Cint, (Ptr{Cvoid},), x.ptr), h)
     end
 end
-const _handles = Dict{Int, Handle}()          # one handle per Julia thread
-handle() = get!(() -> Handle(), _handles, Threads.threadid())
+# one handle per Julia thread; the table is shared, so it is only touched under a lock
+const _handles = Dict{Int, Handle}()
+const _handles_lock = ReentrantLock()
+handle() = lock(() -> get!(() -> Handle(), _handles, Threads.threadid()), _handles_lock)
+sync(h::Handle = handle()) = check(h, ccall((:hdp_sync, libhdp), Cint, (Ptr{Cvoid},), h.ptr))
 
 function check(h::Handle, rc::Cint)
     rc == 0 && return
@@ -129,65 +170,103 @@ function sampler_desc(s::UniformSampling, keep)
     if s.a isa Number
         return HdpSampler(1, 0, 1, 0, Float64(s.a), Float64(s.b), 0.0, C_NULL, C_NULL)
     end
-    a = Vector{Float64}(s.a); b = Vector{Float64}(s.b); push!(keep, a, b)
+    a = Vector{Float64}(Array(s.a)); b = Vector{Float64}(Array(s.b)); push!(keep, a, b)
     HdpSampler(1, 0, 0, 0, 0.0, 0.0, 0.0, pointer(a), pointer(b))
 end
 sampler_desc(s::NormalSampling, keep) = HdpSampler(2, s.shifted, 1, 0, 0.0, 0.0, Float64(s.σ), C_NULL, C_NULL)
 
-function problem_desc(prob, f, bc, keep; g = prob.g, d = length(prob.x))
-    μk, μp = kind_of(prob.μ); σk, σp = kind_of(prob.σ)
-    gk, gp = gkind(g);        fk, fp = fkind(f)
-    d = Int32(d)
+function problem_desc(μ, σ, g, f, tspan, bc, d, keep)
+    μk, μp = kind_of(μ); σk, σp = kind_of(σ)
+    gk, gp = gkind(g);   fk, fp = fkind(f)
     if isnothing(bc)
         has, scal, lo_s, hi_s, lo, hi = 0, 1, 0.0, 0.0, C_NULL, C_NULL
     elseif bc[1] isa Number
         has, scal, lo_s, hi_s, lo, hi = 1, 1, Float64(bc[1]), Float64(bc[2]), C_NULL, C_NULL
     else
-        l = Vector{Float64}(bc[1]); u = Vector{Float64}(bc[2]); push!(keep, l, u)
+        l = Vector{Float64}(Array(bc[1])); u = Vector{Float64}(Array(bc[2])); push!(keep, l, u)
         has, scal, lo_s, hi_s, lo, hi = 1, 0, 0.0, 0.0, pointer(l), pointer(u)
     end
-    HdpProblem(d, μk, σk, gk, fk, has, scal, 0, Float64(prob.tspan[1]), Float64(prob.tspan[2]),
+    HdpProblem(Int32(d), μk, σk, gk, fk, has, scal, 0, Float64(tspan[1]), Float64(tspan[2]),
                μp, σp, gp, fp, lo_s, hi_s, lo, hi)
+end
+problem_desc(prob, f, bc, keep; g = prob.g, d = length(prob.x)) =
+    problem_desc(prob.μ, prob.σ, g, f, prob.tspan, bc, d, keep)
+
+# the expressions of the *_USER kinds as a C struct (strings kept alive in `keep`); C_NULL when none is used
+function user_exprs_ref(μ, σ, g, f, keep)
+    es = map(user_expr, (μ, σ, g, f))
+    all(isnothing, es) && return nothing
+    cs = map(e -> isnothing(e) ? nothing : Base.cconvert(Cstring, e), es)
+    push!(keep, cs...)
+    ptrs = map(c -> isnothing(c) ? Cstring(C_NULL) : Base.unsafe_convert(Cstring, c), cs)
+    r = Ref(HdpUserExprs(ptrs...))
+    push!(keep, r)
+    r
 end
 
 # ------------------------------------------------------------------ MLP overlay (src/MLP.jl:68-98)
 accelerated(prob) = prob.μ isa B200Coef && prob.σ isa B200Coef && prob.g isa B200G && prob.f isa B200F
 
-function _mlp_b200(M, L, K, x::Vector{T}, mc_sample!, prob, neumann_bc, compat_threads) where {T <: Union{Float32, Float64}}
+"""
+    mlp_b200(M, L, K, x, mc_sample!, prob, neumann_bc; compat_threads = 0, seed = rand(UInt64), std_err = false)
+
+One `hdp_mlp_solve_*` call.  Returns `u`, or `(u, standard_error, stats)` with `std_err = true`.
+"""
+function mlp_b200(M, L, K, x::Vector{T}, mc_sample!, prob, neumann_bc; compat_threads = 0, seed = rand(UInt64),
+                  std_err = false) where {T <: HdpFloat}
     keep = Any[]
     pb = problem_desc(prob, prob.f, neumann_bc, keep)
-    cfg = HdpMlpCfg(M, L, K, 1, 1, 0, compat_threads, 0, rand(UInt64), sampler_desc(mc_sample!, keep),
-                    C_NULL, C_NULL, C_NULL, C_NULL)
+    ue = user_exprs_ref(prob.μ, prob.σ, prob.g, prob.f, keep)
+    se = Vector{T}(undef, 1)
     u = Vector{T}(undef, 1)
+    st = Ref{HdpMlpStats}()
     h = handle()
     sym = T === Float64 ? :hdp_mlp_solve_f64 : :hdp_mlp_solve_f32
-    GC.@preserve keep x u begin
+    GC.@preserve keep x u se begin
+        cfg = HdpMlpCfg(M, L, K, 1, 1, 0, compat_threads, 0, seed, sampler_desc(mc_sample!, keep),
+                        C_NULL, C_NULL, C_NULL,
+                        isnothing(ue) ? Ptr{HdpUserExprs}(C_NULL) : Base.unsafe_convert(Ptr{HdpUserExprs}, ue),
+                        0, HDP_MEM_HOST, 0.0, std_err ? Ptr{Cvoid}(pointer(se)) : C_NULL)
         rc = ccall((sym, libhdp), Cint,
-                   (Ptr{Cvoid}, Ref{HdpProblem}, Ref{HdpMlpCfg}, Ptr{T}, Ptr{T}, Ptr{Cvoid}),
-                   h.ptr, pb, cfg, x, u, C_NULL)
+                   (Ptr{Cvoid}, Ref{HdpProblem}, Ref{HdpMlpCfg}, Ptr{T}, Ptr{T}, Ref{HdpMlpStats}),
+                   h.ptr, pb, cfg, x, u, st)
     end
     check(h, rc)
-    u[1]
+    std_err ? (u[1], se[1], st[]) : u[1]
 end
 
 # `_ml_picard(M, L, K, x, s, t, mc_sample!, g, f, verbose, prob, neumann_bc)` at the top of the
 # recursion (s == tspan[1], t == tspan[2]) — the calls made by solve(::MLP), src/MLP.jl:68-98.
-function _ml_picard(M, L, K, x::Vector{T}, s, t, mc_sample!, g::B200G, f, verbose, prob, neumann_bc) where {T}
+# Signature: `x::Vector{T}` and `g::B200G` are strictly narrower than the reference's untyped
+# positional arguments (src/MLP.jl:102-115) and than its `x::Nothing` method (:210), so the methods
+# below are more specific than both and ambiguous with neither.
+function _ml_picard(M, L, K, x::Vector{T}, s, t, mc_sample!, g::B200G, f, verbose, prob, neumann_bc) where {T <: HdpFloat}
     if accelerated(prob) && s == prob.tspan[1] && t == prob.tspan[2]
-        return _mlp_b200(M, L, K, x, mc_sample!, prob, neumann_bc, 0)
+        return mlp_b200(M, L, K, x, mc_sample!, prob, neumann_bc)
     end
-    invoke(_ml_picard, Tuple{Any, Any, Any, typeof(x), Any, Any, Any, Any, Any, Any, Any, Any},
+    invoke(_ml_picard, Tuple{Any, Any, Any, Any, Any, Any, Any, Any, Any, Any, Any, Any},
            M, L, K, x, s, t, mc_sample!, g, f, verbose, prob, neumann_bc)
 end
-function _ml_picard_mlt(M, L, K, x::Vector{T}, s, t, mc_sample!, g::B200G, f, verbose, prob, neumann_bc) where {T}
-    accelerated(prob) || return invoke(_ml_picard_mlt, Tuple{Any, Any, Any, typeof(x), Any, Any, Any, Any, Any, Any, Any, Any},
+function _ml_picard_mlt(M, L, K, x::Vector{T}, s, t, mc_sample!, g::B200G, f, verbose, prob, neumann_bc) where {T <: HdpFloat}
+    accelerated(prob) || return invoke(_ml_picard_mlt, Tuple{Any, Any, Any, Any, Any, Any, Any, Any, Any, Any, Any, Any},
                                        M, L, K, x, s, t, mc_sample!, g, f, verbose, prob, neumann_bc)
     # reproduce the `_get_loop_num` partition of the threaded estimator (src/MLP.jl:391-404)
-    _mlp_b200(M, L, K, x, mc_sample!, prob, neumann_bc, Threads.nthreads())
+    mlp_b200(M, L, K, x, mc_sample!, prob, neumann_bc; compat_threads = Threads.nthreads())
 end
 
-# ------------------------------------------------------------------ _reflect (src/reflect.jl:8-82)
-function _reflect(a::Array{T}, b::Array{T}, s, e) where {T <: Union{Float32, Float64}}
+# ------------------------------------------------------------------ _reflect, batched method (src/reflect.jl:58-82)
+# Only the Matrix method is overlaid.  The reference has
+#   (A) _reflect(a::T, b::T, s::T, e::T) where {T <: Vector}        src/reflect.jl:8
+#   (B) _reflect(a::T, b::T, s, e)       where {T <: AbstractArray}  src/reflect.jl:58
+# `Matrix{T}` is not a `Vector`, so the method below is disjoint from (A) and a strict subset of (B):
+# more specific than (B), ambiguous with nothing.  The Vector method (A) — called once per path-step
+# by the CPU recursion, src/MLP.jl:419 — is deliberately left alone: it stays the stock code on the
+# `invoke` fall-back path, and a kernel launch per d-vector would serve nobody.
+const REFLECT_MIN_ELEMENTS = 1 << 14   # below this the stock broadcast is faster than a round trip
+function _reflect(a::Matrix{T}, b::Matrix{T}, s, e) where {T <: HdpFloat}
+    if length(a) < REFLECT_MIN_ELEMENTS
+        return invoke(_reflect, Tuple{AbstractArray, AbstractArray, Any, Any}, a, b, s, e)
+    end
     size(a) == size(b) || error("a not same dim as b")
     d = size(a, 1); B = length(a) ÷ d
     out = similar(b)
@@ -197,21 +276,22 @@ function _reflect(a::Array{T}, b::Array{T}, s, e) where {T <: Union{Float32, Flo
     sym = T === Float64 ? :hdp_reflect_f64 : :hdp_reflect_f32
     rc = ccall((sym, libhdp), Cint,
                (Ptr{Cvoid}, Ptr{T}, Ptr{T}, Ptr{T}, Cint, Cint, Ptr{T}, Ptr{T}, Cint, Ptr{Int32}, Cuint),
-               h.ptr, a, b, out, d, B, lo, hi, scalar, C_NULL, 0)
+               h.ptr, a, b, out, d, B, lo, hi, scalar, C_NULL, HDP_MEM_HOST)
     check(h, rc)
     out
 end
 
 # ------------------------------------------------------------------ samplers (src/MCSample.jl:28-33, 63-71)
-function _mc_sample!(s, x_mc::Array{T}, x) where {T <: Union{Float32, Float64}}
+function _mc_sample!(s, x_mc::Array{T}, x) where {T <: HdpFloat}
     keep = Any[]
     d = size(x_mc, 1); B = size(x_mc, 2); K = length(x_mc) ÷ (d * B)
     h = handle()
     sym = T === Float64 ? :hdp_mc_sample_f64 : :hdp_mc_sample_f32
-    GC.@preserve keep begin
+    GC.@preserve keep x begin
         rc = ccall((sym, libhdp), Cint,
                    (Ptr{Cvoid}, Ptr{T}, Ptr{T}, Cint, Cint, Cint, Ref{HdpSampler}, UInt64, Ptr{T}, Cuint),
-                   h.ptr, x_mc, isnothing(x) ? C_NULL : pointer(x), d, B, K, sampler_desc(s, keep), rand(UInt64), C_NULL, 0)
+                   h.ptr, x_mc, isnothing(x) ? C_NULL : pointer(x), d, B, K, sampler_desc(s, keep), rand(UInt64), C_NULL,
+                   HDP_MEM_HOST)
     end
     check(h, rc)
     x_mc
@@ -220,56 +300,111 @@ b200_sample!(s::UniformSampling, x_mc, x = nothing) = _mc_sample!(s, x_mc, nothi
 b200_sample!(s::NormalSampling, x_mc, x = nothing) = _mc_sample!(s, x_mc, s.shifted ? x : nothing)
 
 # ------------------------------------------------------------------ sde_loop! (src/DeepSplitting.jl:153-166)
-# y1 holds x0_batch on entry (:182).  With `z` and `mc_sample!` the call also performs
-# `mc_sample!(z, y1)` (:186-189) in the same kernel.
-function sde_loop_b200!(y0::Array{T}, y1::Array{T}, nsteps, dt, prob, neumann_bc, x0_sample!;
-                        mc_sample! = NoSampling(), z = nothing) where {T <: Union{Float32, Float64}}
+# μ/σ expressions of UserCoef kinds for the K1 entry points (hdp_set_user_exprs copies the strings)
+function set_user_coefs!(h::Handle, μ, σ)
+    em = user_expr(μ); es = user_expr(σ)
+    if isnothing(em) && isnothing(es)
+        return check(h, ccall((:hdp_set_user_exprs, libhdp), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), h.ptr, C_NULL))
+    end
+    GC.@preserve em es begin
+        ue = HdpUserExprs(isnothing(em) ? C_NULL : pointer(em), isnothing(es) ? C_NULL : pointer(es), C_NULL, C_NULL)
+        check(h, ccall((:hdp_set_user_exprs, libhdp), Cint, (Ptr{Cvoid}, Ref{HdpUserExprs}), h.ptr, ue))
+    end
+end
+
+# The raw call: pointers are host or device addresses according to `mem_flags`.  y1 holds x0_batch on
+# entry (:182); with `z` it also performs `mc_sample!(z, y1)` (:186-189) in the same kernel.
+function sde_loop_ccall!(::Type{T}, y0, y1, B, nsteps, dt, ts, μ, σ, tspan, d, neumann_bc, x0_sample!, mc_sample!, z, K,
+                         mem_flags; seed = rand(UInt64)) where {T <: HdpFloat}
     keep = Any[]
-    pb = problem_desc(prob, prob.f, neumann_bc, keep)
-    K = isnothing(z) ? 0 : size(z, 3)
+    pb = problem_desc(μ, σ, SumSq(0.0), FZero(), tspan, neumann_bc, d, keep)
     h = handle()
+    set_user_coefs!(h, μ, σ)
+    tsv = isnothing(ts) ? nothing : T[ts[length(ts) - i] for i in 1:nsteps]   # t = ts[N + 1 - i] (:157), 1-based
     sym = T === Float64 ? :hdp_sde_loop_f64 : :hdp_sde_loop_f32
-    GC.@preserve keep begin
+    GC.@preserve keep tsv begin
         rc = ccall((sym, libhdp), Cint,
                    (Ptr{Cvoid}, Ref{HdpProblem}, Ptr{T}, Ptr{T}, Cint, Cint, T, Ptr{T}, Ref{HdpSampler}, UInt64, Ptr{T},
                     Ref{HdpSampler}, Ptr{T}, Cint, Cint, Cuint),
-                   h.ptr, pb, y0, y1, size(y1, 2), nsteps, T(dt), C_NULL, sampler_desc(x0_sample!, keep), rand(UInt64),
-                   C_NULL, sampler_desc(mc_sample!, keep), isnothing(z) ? C_NULL : pointer(z), K, 0, 0)
+                   h.ptr, pb, y0, y1, B, nsteps, T(dt), isnothing(tsv) ? C_NULL : pointer(tsv),
+                   sampler_desc(x0_sample!, keep), seed, C_NULL, sampler_desc(mc_sample!, keep), z, K, 0, mem_flags)
     end
     check(h, rc)
     nothing
 end
-# CuArray arguments: same calls with `mem_flags = HDP_MEM_DEVICE (1)` and `pointer(::CuArray)`.
 
-# μ/σ expressions of UserCoef kinds for the K1 entry points (hdp_set_user_exprs copies the strings);
-# `ts` must then be passed to hdp_sde_loop_* (t = ts[N+1-i], src/DeepSplitting.jl:157).
-function set_user_coefs!(h::Handle, prob)
-    μ = prob.μ isa UserCoef ? prob.μ.expr : nothing;  σ = prob.σ isa UserCoef ? prob.σ.expr : nothing
-    if isnothing(μ) && isnothing(σ)
-        return check(h, ccall((:hdp_set_user_exprs, libhdp), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), h.ptr, C_NULL))
+"""
+    _sde_loop!(y0, y1, dWall, μ, σ, p, dt, ts, N, neumann_bc, x0_sample!)
+
+The method `HighDimPDE._sde_loop!` gets once `julia/patches/deepsplitting_sde_loop_hook.patch` is applied to
+src/DeepSplitting.jl (the patch moves the body of the `sde_loop!` closure, :153-166, into a generic method of
+that name and leaves a one-line closure that forwards to it).  `Matrix{T}` states and kind coefficients are
+narrower than the generic method's untyped arguments: more specific, unambiguous.  `dWall` is not filled —
+the normals are generated in registers — only its third dimension (the number of steps) is read.
+"""
+function sde_loop_b200!(y0::Matrix{T}, y1::Matrix{T}, dWall::Array{T, 3}, μ::B200Coef, σ::B200Coef, p, dt, ts, N, neumann_bc,
+                        x0_sample!) where {T <: HdpFloat}
+    GC.@preserve y0 y1 begin
+        sde_loop_ccall!(T, pointer(y0), pointer(y1), size(y1, 2), size(dWall, 3), dt, ts, μ, σ, (first(ts), last(ts)),
+                        size(y1, 1), neumann_bc, x0_sample!, NoSampling(), Ptr{T}(C_NULL), 0, HDP_MEM_HOST)
     end
-    GC.@preserve μ σ begin
-        ue = HdpUserExprs(isnothing(μ) ? C_NULL : pointer(μ), isnothing(σ) ? C_NULL : pointer(σ), C_NULL, C_NULL)
-        check(h, ccall((:hdp_set_user_exprs, libhdp), Cint, (Ptr{Cvoid}, Ref{HdpUserExprs}), h.ptr, ue))
+end
+if isdefined(HighDimPDE, :_sde_loop!)   # the hook patch is applied: drop in
+    @eval HighDimPDE._sde_loop!(y0::Matrix{T}, y1::Matrix{T}, dWall::Array{T, 3}, μ::B200Coef, σ::B200Coef, p, dt, ts, N,
+                                neumann_bc, x0_sample!) where {T <: HdpFloat} =
+        sde_loop_b200!(y0, y1, dWall, μ, σ, p, dt, ts, N, neumann_bc, x0_sample!)
+end
+
+# convenience form without the reference's calling convention (what the tests and the epoch batching use)
+function sde_loop_b200!(y0::Matrix{T}, y1::Matrix{T}, nsteps::Integer, dt, prob, neumann_bc, x0_sample!;
+                        mc_sample! = NoSampling(), z = nothing, seed = rand(UInt64)) where {T <: HdpFloat}
+    K = isnothing(z) ? 0 : size(z, 3)
+    GC.@preserve y0 y1 z begin
+        sde_loop_ccall!(T, pointer(y0), pointer(y1), size(y1, 2), nsteps, dt, nothing, prob.μ, prob.σ, prob.tspan, size(y1, 1),
+                        neumann_bc, x0_sample!, mc_sample!, isnothing(z) ? Ptr{T}(C_NULL) : pointer(z), K, HDP_MEM_HOST; seed)
     end
+end
+
+# E epochs of paths per launch (hdp_sde_loop_epochs_*): y0, y1 are d×B×E, z optionally d×B×K×E; slice e is
+# what sde_loop_b200!(…; seed = seed + e) returns.  DeepSplitting's paths do not depend on the network, so a
+# training loop can simulate E epochs' worth at once and consume one slice per epoch (INTEGRATION.md §5).
+function sde_loop_epochs_b200!(y0::Array{T, 3}, y1::Array{T, 3}, nsteps::Integer, dt, prob, neumann_bc, x0_sample!;
+                               mc_sample! = NoSampling(), z = nothing, seed = rand(UInt64), mem_flags = HDP_MEM_HOST,
+                               ptrs = nothing) where {T <: HdpFloat}
+    keep = Any[]
+    d, B, E = size(y1)
+    pb = problem_desc(prob.μ, prob.σ, SumSq(0.0), FZero(), prob.tspan, neumann_bc, d, keep)
+    K = isnothing(z) ? 0 : size(z, 3)
+    h = handle(); set_user_coefs!(h, prob.μ, prob.σ)
+    p0, p1, pz = isnothing(ptrs) ? (pointer(y0), pointer(y1), isnothing(z) ? Ptr{T}(C_NULL) : pointer(z)) : ptrs
+    sym = T === Float64 ? :hdp_sde_loop_epochs_f64 : :hdp_sde_loop_epochs_f32
+    GC.@preserve keep y0 y1 z begin
+        rc = ccall((sym, libhdp), Cint,
+                   (Ptr{Cvoid}, Ref{HdpProblem}, Ptr{T}, Ptr{T}, Cint, Cint, T, Ptr{T}, Ref{HdpSampler}, UInt64, Cint,
+                    Ref{HdpSampler}, Ptr{T}, Cint, Cuint),
+                   h.ptr, pb, p0, p1, B, nsteps, T(dt), C_NULL, sampler_desc(x0_sample!, keep), seed, E,
+                   sampler_desc(mc_sample!, keep), pz, K, mem_flags)
+    end
+    check(h, rc)
+    nothing
 end
 
 # ------------------------------------------------------------------ EM ensembles (src/NNKolmogorov.jl:81-112, src/NNStopping.jl:90-99)
 # Stands in for `solve(EnsembleProblem(SDEProblem(μ, σ, x0, tspan)[, prob_func]), EM(); dt, trajectories,
 # adaptive = false[, saveat = dt])`: x is d×trajectories (start points in, final states out); with
 # `saveat = true` returns `Array(sim)` (d × N+1 × trajectories), else x.
-function em_ensemble_b200!(x::Matrix{T}, prob, dt; saveat = false) where {T <: Union{Float32, Float64}}
+function em_ensemble_b200!(x::Matrix{T}, prob, dt; saveat = false, seed = rand(UInt64)) where {T <: HdpFloat}
     keep = Any[]
     d, B = size(x)                      # prob.x is `nothing` for NNKolmogorov problems (src/NNKolmogorov.jl:19)
-    pb = problem_desc(prob, FZero(), nothing, keep; g = SumSq(zero(T)), d = d)
+    pb = problem_desc(prob.μ, prob.σ, SumSq(zero(T)), FZero(), prob.tspan, nothing, d, keep)
     N = Int(round((prob.tspan[2] - prob.tspan[1]) / dt))
     traj = saveat ? Array{T}(undef, d, N + 1, B) : nothing
-    h = handle(); set_user_coefs!(h, prob)
+    h = handle(); set_user_coefs!(h, prob.μ, prob.σ)
     sym = T === Float64 ? :hdp_em_ensemble_f64 : :hdp_em_ensemble_f32
-    GC.@preserve keep begin
+    GC.@preserve keep x traj begin
         rc = ccall((sym, libhdp), Cint,
                    (Ptr{Cvoid}, Ref{HdpProblem}, Ptr{T}, Cint, Cint, T, T, Ptr{T}, UInt64, Ptr{T}, Cuint),
-                   h.ptr, pb, x, B, N, T(dt), T(prob.tspan[1]), saveat ? pointer(traj) : C_NULL, rand(UInt64), C_NULL, 0)
+                   h.ptr, pb, x, B, N, T(dt), T(prob.tspan[1]), saveat ? pointer(traj) : C_NULL, seed, C_NULL, HDP_MEM_HOST)
     end
     check(h, rc)
     saveat ? traj : x

@@ -3,8 +3,9 @@
       profiles/multi_gpu_check.py [L [M]]
 1. NCCL plumbing: hdp_nccl_unique_id -> broadcast -> hdp_comm_init_rank, allreduce self-test.
 2. Strong scaling of ONE solve (BASELINE C4 shape: non-local Fisher-KPP d=10, UniformSampling, M=4, K=10, level L):
-   work units sharded over the ranks, one ncclAllReduce of the per-unit partial sums; the result must be
-   bit-identical to the single-GPU solve (each slot is written by exactly one rank).
+   bottom subtrees owned by one rank each, one ncclAllReduce of a double per crown node, the crown finished on
+   every rank; the result must agree with the single-GPU solve to 1e-12 (a few sums are associated differently),
+   be bit-identical on all ranks, count every wall hit once, and a rank that passes another seed must be caught.
 3. Weak scaling of independent solves (C2): shards of the solve index, no collective."""
 import os
 import sys
@@ -59,11 +60,18 @@ assert rel <= 1e-12, (uN, u1)
 same_bits = bool(uN[0] == u1[0])
 allu = HD.all_gather_object(float(uN[0]))
 assert all(v == allu[0] for v in allu), allu  # every rank holds the identical result
+assert sN["bounces"] == s1["bounces"], (sN["bounces"], s1["bounces"])  # all-reduced total == the single-GPU count
+# ranks that describe different calls (here: another seed) are refused instead of summed into one number
+try:
+    H._ml_picard_batch(prob, alg, n_solves=1, seed=3 + (rank == world - 1), handle=h)
+    raise SystemExit("a seed mismatch across ranks went unnoticed")
+except H.HdpError as e:
+    assert "disagree" in str(e), e
 dev = HD.max_over_ranks(min(v[1] for v in res.values()))
 if rank == 0:
     print(f"[multi] world={world} C4-shape M={Mv} L={Lv} ({sN['path_steps']} path-steps): u={uN[0]:.15g} rel_vs_1gpu={rel:.1e} bit_equal={same_bits} "
           f"units={sN['n_units']} (1 GPU: {s1['n_units']}) device_ms N-GPU={dev:.3f} 1-GPU={min(t_solo):.3f} "
-          f"speedup={min(t_solo) / dev:.2f}x bounces_rank0={sN['bounces']} phase_ms={ {k: round(v, 3) for k, v in sN['phase_ms'].items()} }")
+          f"speedup={min(t_solo) / dev:.2f}x bounces={sN['bounces']} exchange_bytes={sN['exchange_bytes']} phase_ms={ {k: round(v, 3) for k, v in sN['phase_ms'].items()} }")
 
 # weak scaling: independent C2 solves
 D = 100

@@ -50,6 +50,11 @@ def emu():
 
 @pytest.fixture(scope="session")
 def handle(H):
-    h = H.Handle(0)
+    try:
+        h = H.Handle(0)
+    except H.HdpError as e:
+        if e.code == H.capi.HDP_ERR_NO_DEVICE:  # plain `pytest tests` on a machine without a B200: skip, don't error
+            pytest.skip("no sm_100 device: the hot path has no CPU fallback (run with -m gpu on a B200)")
+        raise
     yield h
     h.close()

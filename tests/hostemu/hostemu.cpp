@@ -21,63 +21,14 @@ namespace hdp {
 MlpSharding::~MlpSharding() {}
 }
 
-// nranks > 1 emulates a solve sharded over several GPUs (MlpSharding): the ranks run one after the other on
-// private copies of the per-call state, their exchange buffers are summed as the all-reduce would, and every
-// rank finishes the crown; the results of all ranks must agree bit for bit (checked here), rank 0's is returned.
-template <typename T>
-static int emu_solve(const hdp_problem* prob, const hdp_mlp_cfg* cfg, const T* x0, T* u_out, hdp_mlp_stats* stats,
-                     int nranks = 1)
-{
-    const int M = cfg->M, L = cfg->L, K = cfg->K, n_solves = cfg->n_solves;
-    if (M < 1 || K < 1 || L < 1 || L > kMaxL || n_solves < 1 || nranks < 1) return HDP_ERR_BAD_ARG;
-    const bool nonlocal = cfg->sampler.kind != HDP_SAMPLER_NONE;
-    constexpr int VEC = Tr<T>::VEC;
-    constexpr int G = 1;
-    MlpParams<T> P;
-    memset(&P, 0, sizeof(P));
-    fill_dev_problem<T>(prob, &P.pb);
-    fill_dev_sampler<T>(&cfg->sampler, &P.sm);
-    const int d = prob->d;
-    std::vector<T> lohi, ab;
-    if (prob->has_bc && !prob->bc_is_scalar) {
-        lohi.resize(2 * d);
-        for (int i = 0; i < d; ++i) { lohi[i] = (T)prob->lo[i]; lohi[d + i] = (T)prob->hi[i]; }
-        P.pb.lo = lohi.data(); P.pb.hi = lohi.data() + d;
-    }
-    if (cfg->sampler.kind == HDP_SAMPLER_UNIFORM && !cfg->sampler.bounds_are_scalar) {
-        ab.resize(2 * d);
-        for (int i = 0; i < d; ++i) { ab[i] = (T)cfg->sampler.a[i]; ab[d + i] = (T)cfg->sampler.b[i]; }
-        P.sm.a = ab.data(); P.sm.b = ab.data() + d;
-    }
-    MlpCountTables tab;
-    mlp_count_tables(M, L, K, nonlocal, &tab);
-    const int compat = cfg->compat_mlt_threads > 0 ? cfg->compat_mlt_threads : 0;
-    double thresh = tab.W[L];
-    if (cfg->target_units > 0) thresh = std::max(1.0, tab.W[L] * n_solves / (double)cfg->target_units);
-    if (thresh > tab.W[L]) thresh = tab.W[L];
-    MlpPlan plan;
-    mlp_build_plan(M, L, K, nonlocal, thresh, compat, &plan);
-
-    const int nvec = (d + VEC - 1) / VEC;
-    P.M = M; P.K = K; P.L = L; P.Kp = tab.Kp;
-    P.nvec = nvec; P.npl = nvec; P.dpad = nvec * VEC;
-    for (int i = 0; i <= kMaxL; ++i) {
-        P.C[i] = tab.C[i]; P.R[i] = tab.R[i]; P.S[i] = tab.S[i];
-        P.cs[i] = tab.cs[i]; P.rs[i] = tab.rs[i]; P.ss[i] = tab.ss[i];
-    }
-    for (int i = 0; i <= kMaxL + 1; ++i) P.Mpow[i] = tab.Mpow[i];
-    P.seed0 = cfg->seed; P.n_solves = n_solves; P.n_x0 = cfg->n_x0;
-    P.units = plan.units.data(); P.unit_tag = plan.unit_tag.data(); P.nodes = plan.nodes.data();
-    P.sites = plan.sites.data(); P.children = plan.children.data();
-    P.sites_by_depth = plan.sites_by_depth.data(); P.nodes_by_depth = plan.nodes_by_depth.data();
-    P.n_units = (int)plan.units.size(); P.n_nodes = (int)plan.nodes.size();
-    P.n_sites = (int)plan.sites.size(); P.n_points = plan.n_points;
-    P.nranks = nranks;
-    P.r_tape = (const T*)cfg->r_tape; P.n_tape = (const T*)cfg->n_tape; P.s_tape = (const T*)cfg->s_tape;
-    const bool want_se = cfg->std_err_out != nullptr;
-    const PlanNode& root = plan.nodes[0];
-    P.rootsq_stride = 2 * std::max(root.unit_end - root.unit_begin, L + 1);
-
+// nranks > 1 emulates a solve sharded over several GPUs (MlpSharding).  In one process the ranks run one after
+// the other on private copies of the per-call state, their exchange buffers are summed as the all-reduce would,
+// and every rank finishes the crown; the results of all ranks must agree bit for bit (checked), rank 0's is
+// returned.  The two phases are also exported separately (hdp_emu_shard_*), so that a world_size-2 `gloo` test can
+// run one rank per process and do the all-reduce with torch.distributed.
+template <typename T> struct EmuSolve {
+    static constexpr int VEC = Tr<T>::VEC;
+    static constexpr int G = 1;
     struct RankState {
         std::vector<T> feat, site_r, value, se;
         std::vector<double> partial, rootsq, lvstat, xbuf;
@@ -86,9 +37,85 @@ static int emu_solve(const hdp_problem* prob, const hdp_mlp_cfg* cfg, const T* x
         int flags[2] = {0, 0};
         MlpSharding sh;
     };
-    std::vector<RankState> rs(nranks);
-    int xstride = 0;
-    auto bind = [&](int r) {
+    MlpParams<T> P;
+    MlpCountTables tab;
+    MlpPlan plan;
+    std::vector<T> lohi, ab, x0v;
+    std::vector<RankState> rs; // indexed by rank (only the ranks this process emulates are sized)
+    Ctx<T, G> c;
+    int nranks = 1, n_solves = 1, L = 1, xstride = 0;
+    bool want_se = false;
+
+    int setup(const hdp_problem* prob, const hdp_mlp_cfg* cfg, const T* x0, int nranks_, int only_rank)
+    {
+        const int M = cfg->M, K = cfg->K;
+        L = cfg->L; n_solves = cfg->n_solves; nranks = nranks_;
+        if (M < 1 || K < 1 || L < 1 || L > kMaxL || n_solves < 1 || nranks < 1) return HDP_ERR_BAD_ARG;
+        const bool nonlocal = cfg->sampler.kind != HDP_SAMPLER_NONE;
+        memset(&P, 0, sizeof(P));
+        fill_dev_problem<T>(prob, &P.pb);
+        fill_dev_sampler<T>(&cfg->sampler, &P.sm);
+        const int d = prob->d;
+        x0v.assign(x0, x0 + (size_t)cfg->n_x0 * d);
+        if (prob->has_bc && !prob->bc_is_scalar) {
+            lohi.resize(2 * d);
+            for (int i = 0; i < d; ++i) { lohi[i] = (T)prob->lo[i]; lohi[d + i] = (T)prob->hi[i]; }
+            P.pb.lo = lohi.data(); P.pb.hi = lohi.data() + d;
+        }
+        if (cfg->sampler.kind == HDP_SAMPLER_UNIFORM && !cfg->sampler.bounds_are_scalar) {
+            ab.resize(2 * d);
+            for (int i = 0; i < d; ++i) { ab[i] = (T)cfg->sampler.a[i]; ab[d + i] = (T)cfg->sampler.b[i]; }
+            P.sm.a = ab.data(); P.sm.b = ab.data() + d;
+        }
+        mlp_count_tables(M, L, K, nonlocal, &tab);
+        const int compat = cfg->compat_mlt_threads > 0 ? cfg->compat_mlt_threads : 0;
+        double thresh = tab.W[L];
+        if (cfg->target_units > 0) thresh = std::max(1.0, tab.W[L] * n_solves / (double)cfg->target_units);
+        if (thresh > tab.W[L]) thresh = tab.W[L];
+        mlp_build_plan(M, L, K, nonlocal, thresh, compat, &plan);
+        const int nvec = (d + VEC - 1) / VEC;
+        P.M = M; P.K = K; P.L = L; P.Kp = tab.Kp;
+        P.nvec = nvec; P.npl = nvec; P.dpad = nvec * VEC;
+        for (int i = 0; i <= kMaxL; ++i) {
+            P.C[i] = tab.C[i]; P.R[i] = tab.R[i]; P.S[i] = tab.S[i];
+            P.cs[i] = tab.cs[i]; P.rs[i] = tab.rs[i]; P.ss[i] = tab.ss[i];
+        }
+        for (int i = 0; i <= kMaxL + 1; ++i) P.Mpow[i] = tab.Mpow[i];
+        P.seed0 = cfg->seed; P.n_solves = n_solves; P.n_x0 = cfg->n_x0;
+        P.units = plan.units.data(); P.unit_tag = plan.unit_tag.data(); P.nodes = plan.nodes.data();
+        P.sites = plan.sites.data(); P.children = plan.children.data();
+        P.sites_by_depth = plan.sites_by_depth.data(); P.nodes_by_depth = plan.nodes_by_depth.data();
+        P.n_units = (int)plan.units.size(); P.n_nodes = (int)plan.nodes.size();
+        P.n_sites = (int)plan.sites.size(); P.n_points = plan.n_points;
+        P.nranks = nranks;
+        P.r_tape = (const T*)cfg->r_tape; P.n_tape = (const T*)cfg->n_tape; P.s_tape = (const T*)cfg->s_tape;
+        want_se = cfg->std_err_out != nullptr;
+        const PlanNode& root = plan.nodes[0];
+        P.rootsq_stride = 2 * std::max(root.unit_end - root.unit_begin, L + 1);
+        rs.resize(nranks);
+        for (int r = 0; r < nranks; ++r) {
+            if (only_rank >= 0 && r != only_rank) continue;
+            RankState& S = rs[r];
+            S.feat.resize((size_t)n_solves * P.n_points);
+            S.site_r.resize((size_t)n_solves * std::max(P.n_sites, 1));
+            S.value.resize((size_t)n_solves * P.n_nodes);
+            S.se.resize(n_solves);
+            S.partial.assign((size_t)n_solves * P.n_units, 0.0);
+            S.rootsq.assign((size_t)n_solves * P.rootsq_stride, 0.0);
+            S.lvstat.assign((size_t)n_solves * 3 * (kMaxL + 1), 0.0);
+            S.scratch_raw.resize((size_t)(2 * L) * P.npl * VEC * sizeof(T) / sizeof(double2) + 2); // 16-byte aligned
+            S.points_raw.resize(((size_t)n_solves * P.n_points * P.dpad * sizeof(T)) / sizeof(double2) + 2);
+            if (nranks > 1) {
+                mlp_build_sharding(plan, nranks, r, &S.sh);
+                xstride = S.sh.n_slots + 3 * (kMaxL + 1);
+                S.xbuf.assign((size_t)n_solves * xstride + kXTail, 0.0);
+            }
+        }
+        return HDP_OK;
+    }
+    size_t xcount() const { return (size_t)n_solves * xstride + kXTail; }
+    void bind(int r)
+    {
         RankState& S = rs[r];
         P.rank = r;
         P.points = (T*)S.points_raw.data(); P.feat = S.feat.data(); P.site_r = S.site_r.data();
@@ -100,41 +127,26 @@ static int emu_solve(const hdp_problem* prob, const hdp_mlp_cfg* cfg, const T* x
         if (nranks > 1) {
             P.exec = S.sh.exec_own.data(); P.n_exec = (int)S.sh.exec_own.size();
             P.unit_mine = S.sh.unit_mine.data(); P.site_cls = S.sh.site_cls.data(); P.node_slot = S.sh.node_slot.data();
-            P.n_slots = S.sh.n_slots; P.xstride = S.sh.n_slots + 3 * (kMaxL + 1);
+            P.n_slots = S.sh.n_slots; P.xstride = xstride;
             P.xbuf = S.xbuf.data();
         } else {
             P.exec = plan.exec_order.data(); P.n_exec = P.n_units;
         }
-    };
-    for (int r = 0; r < nranks; ++r) {
-        RankState& S = rs[r];
-        S.feat.resize((size_t)n_solves * P.n_points);
-        S.site_r.resize((size_t)n_solves * std::max(P.n_sites, 1));
-        S.value.resize((size_t)n_solves * P.n_nodes);
-        S.se.resize(n_solves);
-        S.partial.assign((size_t)n_solves * P.n_units, 0.0);
-        S.rootsq.assign((size_t)n_solves * P.rootsq_stride, 0.0);
-        S.lvstat.assign((size_t)n_solves * 3 * (kMaxL + 1), 0.0);
-        S.scratch_raw.resize((size_t)(2 * L) * P.npl * VEC * sizeof(T) / sizeof(double2) + 2); // 16-byte aligned
-        S.points_raw.resize(((size_t)n_solves * P.n_points * P.dpad * sizeof(T)) / sizeof(double2) + 2);
-        if (nranks > 1) {
-            mlp_build_sharding(plan, nranks, r, &S.sh);
-            xstride = S.sh.n_slots + 3 * (kMaxL + 1);
-            S.xbuf.assign((size_t)n_solves * xstride + kXTail, 0.0);
-        }
     }
-    Ctx<T, G> c;
-    auto expand_list = [&](const int32_t* list, int cnt, bool hits) {
+    void expand_list(const int32_t* list, int cnt, bool hits)
+    {
         for (u64 it = 0; it < (u64)cnt * n_solves; ++it) { c.nb = 0; expand_item<T, G>(c, P, list, it, hits); }
-    };
-    auto combine_list = [&](const int32_t* list, int cnt, int mode) {
+    }
+    void combine_list(const int32_t* list, int cnt, int mode)
+    {
         for (u64 it = 0; it < (u64)cnt * n_solves; ++it) combine_item<T>(P, list, it, 0, 1, 0xffffffffu, mode);
-    };
-    // phase 1 (per rank): geometry, units, local combine
-    for (int r = 0; r < nranks; ++r) {
+    }
+    // geometry, units and the local combine of one rank; fills its exchange buffer
+    void phase1(int r)
+    {
         bind(r);
         RankState& S = rs[r];
-        for (u64 q = 0; q < (u64)n_solves * P.dpad; ++q) init_item<T>(P, x0, q);
+        for (u64 q = 0; q < (u64)n_solves * P.dpad; ++q) init_item<T>(P, x0v.data(), q);
         ctx_init<T, G>(c, P, 0, 0);
         if (nranks == 1) {
             for (int dep = 0; dep <= plan.max_depth; ++dep)
@@ -154,57 +166,97 @@ static int emu_solve(const hdp_problem* prob, const hdp_mlp_cfg* cfg, const T* x
             combine_list(S.sh.owned_nodes.data(), (int)S.sh.owned_nodes.size(), CMB_ALL);
             combine_list(S.sh.crown_nodes.data(), (int)S.sh.crown_nodes.size(), CMB_PARTIAL);
             S.xbuf[(size_t)n_solves * xstride + 4] = (double)S.ctr[1];
+            S.xbuf[(size_t)n_solves * xstride + 5] = (double)S.flags[0]; // (the library reads its flag per rank; here it rides along)
         }
     }
-    if (nranks > 1) {
-        // the all-reduce
-        std::vector<double> sum(rs[0].xbuf.size(), 0.0);
-        for (int r = 0; r < nranks; ++r)
-            for (size_t i = 0; i < sum.size(); ++i) sum[i] += rs[r].xbuf[i];
-        // phase 2 (per rank): scatter the crown leaves, finish the crown
-        for (int r = 0; r < nranks; ++r) {
-            bind(r);
-            RankState& S = rs[r];
-            S.xbuf = sum;
-            P.xbuf = S.xbuf.data();
-            for (int32_t nidx : S.sh.crown_leaves)
-                for (int sv = 0; sv < n_solves; ++sv)
-                    S.partial[(size_t)sv * P.n_units + plan.nodes[nidx].unit_begin] = S.xbuf[(size_t)sv * xstride + S.sh.node_slot[nidx]];
-            for (int dep = plan.max_depth; dep >= 0; --dep)
-                combine_list(S.sh.crown_final.data() + S.sh.crown_final_off[dep],
-                             S.sh.crown_final_off[dep + 1] - S.sh.crown_final_off[dep], CMB_FINAL);
-            S.ctr[1] = (unsigned long long)sum[(size_t)n_solves * xstride + 4];
-        }
-        for (int r = 1; r < nranks; ++r)
-            for (int i = 0; i < n_solves; ++i)
-                if (rs[r].value[(size_t)i * P.n_nodes] != rs[0].value[(size_t)i * P.n_nodes]) return HDP_ERR_UNSUPPORTED;
+    // after the all-reduce: scatter the crown leaves, finish the crown
+    void phase2(int r, const double* sum)
+    {
+        bind(r);
+        RankState& S = rs[r];
+        S.xbuf.assign(sum, sum + xcount());
+        P.xbuf = S.xbuf.data();
+        for (int32_t nidx : S.sh.crown_leaves)
+            for (int sv = 0; sv < n_solves; ++sv)
+                S.partial[(size_t)sv * P.n_units + plan.nodes[nidx].unit_begin] = S.xbuf[(size_t)sv * xstride + S.sh.node_slot[nidx]];
+        for (int dep = plan.max_depth; dep >= 0; --dep)
+            combine_list(S.sh.crown_final.data() + S.sh.crown_final_off[dep],
+                         S.sh.crown_final_off[dep + 1] - S.sh.crown_final_off[dep], CMB_FINAL);
+        S.ctr[1] = (unsigned long long)sum[(size_t)n_solves * xstride + 4];
+        if (sum[(size_t)n_solves * xstride + 5] > 0.0) S.flags[0] = 1;
     }
-    int bad = 0;
-    for (int r = 0; r < nranks; ++r) bad |= rs[r].flags[0];
-    for (int i = 0; i < n_solves; ++i) u_out[i] = rs[0].value[(size_t)i * P.n_nodes];
-    if (want_se)
-        for (int i = 0; i < n_solves; ++i) ((T*)cfg->std_err_out)[i] = rs[0].se[i];
-    if (stats) {
-        memset(stats, 0, sizeof(*stats));
-        stats->per_solve.path_steps = tab.C[L];
-        stats->per_solve.time_uniforms = tab.R[L];
-        stats->per_solve.sampler_calls = tab.S[L];
-        stats->per_solve.f_evals = tab.F[L];
-        stats->per_solve.g_evals = tab.G[L];
-        stats->bounces = rs[0].ctr[1];
-        stats->n_units = P.n_units; stats->n_nodes = P.n_nodes; stats->n_sites = P.n_sites;
-        stats->group_size = 1;
-        stats->exchange_bytes = nranks > 1 ? rs[0].xbuf.size() * sizeof(double) : 0;
-        if (want_se) {
-            for (int l = 0; l <= L; ++l) {
-                stats->level_n[l] = (uint64_t)(rs[0].lvstat[3 * l] + 0.5);
-                stats->level_sum[l] = rs[0].lvstat[3 * l + 1];
-                stats->level_sumsq[l] = rs[0].lvstat[3 * l + 2];
+    int finish(int r, const hdp_mlp_cfg* cfg, T* u_out, hdp_mlp_stats* stats)
+    {
+        RankState& S = rs[r];
+        for (int i = 0; i < n_solves; ++i) u_out[i] = S.value[(size_t)i * P.n_nodes];
+        if (want_se)
+            for (int i = 0; i < n_solves; ++i) ((T*)cfg->std_err_out)[i] = S.se[i];
+        if (stats) {
+            memset(stats, 0, sizeof(*stats));
+            stats->per_solve.path_steps = tab.C[L];
+            stats->per_solve.time_uniforms = tab.R[L];
+            stats->per_solve.sampler_calls = tab.S[L];
+            stats->per_solve.f_evals = tab.F[L];
+            stats->per_solve.g_evals = tab.G[L];
+            stats->bounces = S.ctr[1];
+            stats->n_units = P.n_units; stats->n_nodes = P.n_nodes; stats->n_sites = P.n_sites;
+            stats->group_size = 1;
+            stats->exchange_bytes = nranks > 1 ? xcount() * sizeof(double) : 0;
+            if (want_se) {
+                for (int l = 0; l <= L; ++l) {
+                    stats->level_n[l] = (uint64_t)(S.lvstat[3 * l] + 0.5);
+                    stats->level_sum[l] = S.lvstat[3 * l + 1];
+                    stats->level_sumsq[l] = S.lvstat[3 * l + 2];
+                }
+                stats->std_error = (double)S.se[0];
             }
-            stats->std_error = (double)rs[0].se[0];
         }
+        return S.flags[0] ? HDP_ERR_START_OUTSIDE_DOMAIN : HDP_OK;
     }
-    return bad ? HDP_ERR_START_OUTSIDE_DOMAIN : HDP_OK;
+};
+
+template <typename T>
+static int emu_solve(const hdp_problem* prob, const hdp_mlp_cfg* cfg, const T* x0, T* u_out, hdp_mlp_stats* stats,
+                     int nranks = 1)
+{
+    EmuSolve<T> E;
+    int rc = E.setup(prob, cfg, x0, nranks, -1);
+    if (rc != HDP_OK) return rc;
+    for (int r = 0; r < nranks; ++r) E.phase1(r);
+    if (nranks > 1) {
+        std::vector<double> sum(E.xcount(), 0.0); // the all-reduce
+        for (int r = 0; r < nranks; ++r)
+            for (size_t i = 0; i < sum.size(); ++i) sum[i] += E.rs[r].xbuf[i];
+        for (int r = 0; r < nranks; ++r) E.phase2(r, sum.data());
+        for (int r = 1; r < nranks; ++r)
+            for (int i = 0; i < E.n_solves; ++i)
+                if (E.rs[r].value[(size_t)i * E.P.n_nodes] != E.rs[0].value[(size_t)i * E.P.n_nodes]) return HDP_ERR_UNSUPPORTED;
+    }
+    return E.finish(0, cfg, u_out, stats);
+}
+
+// one rank per process (f64): create + phase 1 -> exchange buffer; all-reduce it outside; phase 2 -> result
+extern "C" void* hdp_emu_shard_begin(const hdp_problem* prob, const hdp_mlp_cfg* cfg, const double* x0, int nranks, int rank,
+                                     int64_t* xcount)
+{
+    auto* E = new EmuSolve<double>();
+    if (nranks < 2 || rank < 0 || rank >= nranks || E->setup(prob, cfg, x0, nranks, rank) != HDP_OK) { delete E; return nullptr; }
+    E->phase1(rank);
+    *xcount = (int64_t)E->xcount();
+    return E;
+}
+extern "C" void hdp_emu_shard_xbuf(void* e, int rank, double* out)
+{
+    auto* E = (EmuSolve<double>*)e;
+    std::copy(E->rs[rank].xbuf.begin(), E->rs[rank].xbuf.end(), out);
+}
+extern "C" int hdp_emu_shard_end(void* e, int rank, const hdp_mlp_cfg* cfg, const double* xsum, double* u_out, hdp_mlp_stats* stats)
+{
+    auto* E = (EmuSolve<double>*)e;
+    E->phase2(rank, xsum);
+    int rc = E->finish(rank, cfg, u_out, stats);
+    delete E;
+    return rc;
 }
 
 extern "C" int hdp_emu_mlp_solve_sharded_f64(const hdp_problem* prob, const hdp_mlp_cfg* cfg, const double* x0,

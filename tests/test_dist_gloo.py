@@ -44,13 +44,66 @@ def _worker(rank, world, port, q):
         full = D.gather_solves(local, n)
         assert np.array_equal(full, np.arange(n) * 2.0)
         assert D.local_seed(100, rank, world, n) == 100 + lo
-        # 4. max-over-ranks timing reduction
-        assert D.max_over_ranks(float(rank + 1)) == float(world)
+        # 4. max-over-ranks timing reduction; the seed of a sharded solve is rank 0's
+        assert D.max_over_ranks(float(rank + 1)) == float(world) and D.min_over_ranks(float(rank + 1)) == 1.0
+        assert D.broadcast_int(0xFEDCBA9876543210 + rank) == 0xFEDCBA9876543210
+        # 5. ONE solve sharded over the two ranks — the library's N > 1 data path with the product's device code
+        #    compiled for the host (tests/hostemu): each process runs its rank's geometry, units and local combine,
+        #    the exchange buffers are summed by a real all-reduce, each rank finishes the crown.
+        _sharded_solve(rank, world, H, D)
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))
     finally:
         dist.destroy_process_group()
+
+
+def _sharded_solve(rank, world, H, D):
+    import ctypes as C
+    import subprocess
+    sys_path = os.path.dirname(os.path.abspath(__file__))
+    import sys
+    sys.path.insert(0, sys_path)
+    from helpers import zoo, random_tapes
+    from oracle import oracle as O
+    O.build()
+    emu_dir = os.path.join(sys_path, "hostemu")
+    if rank == 0:
+        subprocess.run(["make", "-C", emu_dir], check=True, capture_output=True)
+    dist.barrier()
+    emu = C.CDLL(os.path.join(emu_dir, "_build", "libhdp_hostemu.so"))
+    emu.hdp_emu_shard_begin.restype = C.c_void_p
+    for name, target in (("nonlocal_ac_neumann_d5", 400), ("allen_cahn_neumann_d5", 60)):
+        prob, alg, dt = zoo(H)[name]
+        tapes = random_tapes(H, prob, alg, dt, seed=29)
+        pb, keep = prob.to_c()
+        sm, k2 = alg.mc_sample._descriptor(prob.d)
+        uo, info = O.ml_picard(pb, sm, alg.M, alg.L, alg.K, np.asarray(prob.x, dtype=dt), O.Rng.tape(dt, *tapes))
+        cfg = H.capi.hdp_mlp_cfg()
+        cfg.M, cfg.L, cfg.K, cfg.n_solves, cfg.n_x0, cfg.seed, cfg.target_units = alg.M, alg.L, alg.K, 1, 1, 0, target
+        cfg.sampler = sm
+        ts = [np.ascontiguousarray(t, dtype=dt) if t is not None else None for t in tapes]
+        cfg.r_tape, cfg.n_tape = ts[0].ctypes.data, ts[1].ctypes.data
+        if ts[2] is not None:
+            cfg.s_tape = ts[2].ctypes.data
+        x = np.ascontiguousarray(prob.x, dtype=dt)
+        n = C.c_int64(0)
+        e = emu.hdp_emu_shard_begin(C.byref(pb), C.byref(cfg), x.ctypes.data_as(C.c_void_p), world, rank, C.byref(n))
+        assert e
+        xb = np.zeros(n.value)
+        emu.hdp_emu_shard_xbuf(C.c_void_p(e), rank, xb.ctypes.data_as(C.c_void_p))
+        t = torch.from_numpy(xb)
+        dist.all_reduce(t)  # the one collective of the path (ncclAllReduce(double, sum) on the GPUs)
+        u = np.zeros(1)
+        st = H.capi.hdp_mlp_stats()
+        rc = emu.hdp_emu_shard_end(C.c_void_p(e), rank, C.byref(cfg), xb.ctypes.data_as(C.c_void_p), u.ctypes.data_as(C.c_void_p),
+                                   C.byref(st))
+        assert rc == 0
+        assert abs(u[0] - uo) <= 1e-12 * abs(uo), (name, u[0], uo)
+        assert st.bounces == info["bounces"]          # every wall hit counted once across the ranks
+        both = D.all_gather_object(float(u[0]))
+        assert both[0] == both[1]                     # the ranks finish with identical bits
+        assert n.value * 8 < 64 * 1024                # the exchange is a double per crown node, not per unit
 
 
 def test_world_size_2_gloo():
