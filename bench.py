@@ -338,8 +338,8 @@ def run_ours(args, rank, world, local_rank):
 
 def strong_workloads(H):
     """One solve large enough to occupy several GPUs: Allen-Cahn d=100 with Neumann reflection at
-    M=8, L=5 (1,184,968 path-steps) and BASELINE configs[3] (C4: non-local Fisher-KPP d=10, M=4, L=5, K=10,
-    45.4 M path-steps)."""
+    M=8, L=5 (1,184,968 path-steps), the same at d=1000 (1.18 G coordinate-steps, the strong-scaling case of
+    BASELINE configs[4]) and BASELINE configs[3] (C4: non-local Fisher-KPP d=10, M=4, L=5, K=10, 45.4 M path-steps)."""
     d = 100
     ac = H.ParabolicPDEProblem(0.0, 1.0, np.zeros(d), (0.0, 0.5), g=H.ExpSumSq(0.25), f=H.FAllenCahn(1.0),
                                neumann_bc=(np.full(d, -0.5), np.full(d, 0.5)))
@@ -347,7 +347,11 @@ def strong_workloads(H):
     c4 = H.PIDEProblem(0.0, 0.1, np.zeros(d), (0.0, 0.5), H.ExpSumSq(1.0), H.FNLFisher(),
                        neumann_bc=(np.full(d, -0.5), np.full(d, 0.5)))
     a4 = H.MLP(M=4, L=5, K=10, mc_sample=H.UniformSampling(np.full(d, -0.5), np.full(d, 0.5)))
+    d = 1000
+    ac1000 = H.ParabolicPDEProblem(0.0, 1.0, np.zeros(d), (0.0, 0.5), g=H.ExpSumSq(0.25), f=H.FAllenCahn(1.0),
+                                   neumann_bc=(np.full(d, -0.5), np.full(d, 0.5)))
     return {"allen_cahn_d100_M8_L5_one_solve": (ac, H.MLP(M=8, L=5, K=10)),
+            "allen_cahn_d1000_M8_L5_one_solve": (ac1000, H.MLP(M=8, L=5, K=10)),   # SURVEY 8d, C5 strong scaling
             "c4_nonlocal_fisher_d10_L5_one_solve": (c4, a4)}
 
 

@@ -170,6 +170,12 @@ __device__ __forceinline__ float rsq_approx(float x)
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ float sqrt_approx(float x)
+{
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float lg2_approx(float x)
 {
     float y;
@@ -374,11 +380,12 @@ template <> __device__ __forceinline__ Vec<float> normals_from_words<float>(cons
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const float u1 = u2f(0x3f800000u | (p.w[2 * h] >> 9)) - 0.99999994f; // (k + 1/2) 2^-23 in (0,1)
-        const float u2 = u2f(0x3f800000u | (p.w[2 * h + 1] >> 9)) - 1.0f;
+        // 2π u2 with u2 = m - 1, m in [1,2) built from the bits: the product 2π (m - 1) is formed exactly inside the fma
+        // and rounded once — the same value as fl(2π * u2), one instruction less
+        const float th = xfma(u2f(0x3f800000u | (p.w[2 * h + 1] >> 9)), 6.283185307179586f, -6.283185307179586f);
         // -2 ln u1 = -2 ln2 * log2(u1)
         const float tt = -1.3862943611198906f * lg2_approx(u1); // > 0: u1 < 1
-        const float rad = tt * rsq_approx(tt);
-        const float th = 6.283185307179586f * u2;
+        const float rad = sqrt_approx(tt);
         r.v[2 * h] = rad * cos_approx(th);
         r.v[2 * h + 1] = rad * sin_approx(th);
     }

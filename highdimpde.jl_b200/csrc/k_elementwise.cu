@@ -321,9 +321,10 @@ int sde_loop_impl(hdp_handle h, const hdp_problem* prob, T* y0, T* y1, int B, in
     const int grid_x = grid_for(h, nv, threads, 64);
     const dim3 grid((unsigned)grid_x, (unsigned)n_epochs); // blockIdx.y = epoch (k_sde.cuh)
     const bool const_coef = prob->mu_kind == HDP_COEF_CONST && prob->sigma_kind == HDP_COEF_CONST && !mlp_assoc;
-    const int bc = !const_coef ? K1_GENERIC
-                   : !pb.has_bc ? K1_NOBC
-                   : (pb.bc_is_scalar && pb.lo_s == -pb.hi_s) ? K1_SYM : K1_GENERIC;
+    int bc = !const_coef ? K1_GENERIC
+             : !pb.has_bc ? K1_NOBC
+             : (pb.bc_is_scalar && pb.lo_s == -pb.hi_s) ? K1_SYM : K1_GENERIC;
+    if (bc != K1_GENERIC && pb.mu_c == (T)0) bc += 2; // K1_NOBC0 / K1_SYM0
 #define LAUNCH3(AL, INJ, BC)                                                                              \
     sde_loop_kernel<T, AL, INJ, BC><<<grid, threads, 0, h->stream>>>(pb, dy0, dy1, n_el, nsteps, dt, x0s, \
                                                                      nullptr, seed, ddw, mcs, dz, K,       \
@@ -332,6 +333,8 @@ int sde_loop_impl(hdp_handle h, const hdp_problem* prob, T* y0, T* y1, int B, in
     do {                                                                                                  \
         if (bc == K1_SYM) LAUNCH3(AL, INJ, K1_SYM);                                                       \
         else if (bc == K1_NOBC) LAUNCH3(AL, INJ, K1_NOBC);                                                \
+        else if (bc == K1_SYM0) LAUNCH3(AL, INJ, K1_SYM0);                                                \
+        else if (bc == K1_NOBC0) LAUNCH3(AL, INJ, K1_NOBC0);                                              \
         else LAUNCH3(AL, INJ, K1_GENERIC);                                                                \
     } while (0)
     HDP_CUDA(h, cudaEventRecord(h->ev0, h->stream));

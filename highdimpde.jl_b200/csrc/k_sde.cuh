@@ -82,12 +82,14 @@ template <int WHICH, typename F> __device__ __forceinline__ void with_kind(int k
 // BC: K1_GENERIC — any coefficient kind, any bounds, either association;
 //     K1_NOBC / K1_SYM — constant coefficients, DeepSplitting association, no boundary /
 //     symmetric scalar box (the BASELINE shape): nothing but the arithmetic is left in the loop.
-enum { K1_GENERIC = 0, K1_NOBC = 1, K1_SYM = 2 };
+//     K1_NOBC0 / K1_SYM0 — the same with μ = 0 (every BASELINE configuration): `y0 + μ*dt` is y0, one addition
+//     per coordinate-step less to issue, the same value.
+enum { K1_GENERIC = 0, K1_NOBC = 1, K1_SYM = 2, K1_NOBC0 = 3, K1_SYM0 = 4 };
 #ifndef K1_STEP_UNROLL
 #define K1_STEP_UNROLL 2
 #endif
 
-template <typename T, bool ALIGNED, bool INJECT, int BC>
+template <typename T, bool ALIGNED, bool INJECT, int BCX>
 __global__ void __launch_bounds__(128)
 sde_loop_kernel(DevProblem<T> pb, T* __restrict__ y0, T* __restrict__ y1, size_t n_el, int nsteps, T dt,
                 DevSampler<T> x0s, const T* __restrict__ x0_inject, u64 seed, const T* __restrict__ dW,
@@ -95,6 +97,8 @@ sde_loop_kernel(DevProblem<T> pb, T* __restrict__ y0, T* __restrict__ y1, size_t
                 int mlp_assoc, int zero, const T* __restrict__ ts)
 {
     constexpr int VEC = Tr<T>::VEC;
+    constexpr bool MU0 = BCX == K1_NOBC0 || BCX == K1_SYM0;
+    constexpr int BC = MU0 ? BCX - 2 : BCX;
     if constexpr (sizeof(T) == 8) tables_init();
     // blockIdx.y: the epoch of a multi-epoch launch (hdp_sde_loop_epochs_*): epoch e works on slice e of every
     // array with seed + e, exactly as a call of its own would — DeepSplitting's paths do not depend on the
@@ -157,7 +161,7 @@ sde_loop_kernel(DevProblem<T> pb, T* __restrict__ y0, T* __restrict__ y1, size_t
                     prev = cur; // y0 .= y1 (:159)
 #pragma unroll
                     for (int e = 0; e < VEC; ++e)
-                        cur.v[e] = add_rn(add_rn(prev.v[e], mudt_c), mul_rn(sgsq_c, xs[u].v[e])); // :160
+                        cur.v[e] = add_rn(MU0 ? prev.v[e] : add_rn(prev.v[e], mudt_c), mul_rn(sgsq_c, xs[u].v[e])); // :160
                     if constexpr (BC == K1_SYM) reflect_vec_sym<T, false>(cur, pb.hi_s, far, nb_total); // :161-163
                 }
             }
@@ -190,7 +194,7 @@ sde_loop_kernel(DevProblem<T> pb, T* __restrict__ y0, T* __restrict__ y1, size_t
                 } else {
 #pragma unroll
                     for (int e = 0; e < VEC; ++e)
-                        cur.v[e] = add_rn(add_rn(prev.v[e], mudt_c), mul_rn(sgsq_c, xi.v[e])); // :160
+                        cur.v[e] = add_rn(MU0 ? prev.v[e] : add_rn(prev.v[e], mudt_c), mul_rn(sgsq_c, xi.v[e])); // :160
                     if constexpr (BC == K1_SYM) reflect_vec_sym<T, false>(cur, pb.hi_s, far, nb_total); // :161-163
                 }
             }

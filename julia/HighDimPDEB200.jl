@@ -208,13 +208,23 @@ end
 accelerated(prob) = prob.μ isa B200Coef && prob.σ isa B200Coef && prob.g isa B200G && prob.f isa B200F
 
 """
-    mlp_b200(M, L, K, x, mc_sample!, prob, neumann_bc; compat_threads = 0, seed = rand(UInt64), std_err = false)
+    mlp_b200(M, L, K, x, mc_sample!, prob, neumann_bc; compat_threads = 0, seed = rand(UInt64), std_err = false,
+             tapes = nothing)
 
 One `hdp_mlp_solve_*` call.  Returns `u`, or `(u, standard_error, stats)` with `std_err = true`.
+`tapes = (r, n, s)`: injected random tapes in the reference's consumption order (parity mode; `s === nothing`
+without a sampler) — `n` and `s` are d×count matrices or flat vectors, coordinate fastest.
 """
 function mlp_b200(M, L, K, x::Vector{T}, mc_sample!, prob, neumann_bc; compat_threads = 0, seed = rand(UInt64),
-                  std_err = false) where {T <: HdpFloat}
+                  std_err = false, tapes = nothing) where {T <: HdpFloat}
     keep = Any[]
+    tr = tn = ts = Ptr{Cvoid}(C_NULL)
+    if !isnothing(tapes)
+        r, n, s = map(t -> isnothing(t) ? nothing : Vector{T}(vec(t)), tapes)
+        push!(keep, r, n, s)
+        tr, tn = Ptr{Cvoid}(pointer(r)), Ptr{Cvoid}(pointer(n))
+        isnothing(s) || (ts = Ptr{Cvoid}(pointer(s)))
+    end
     pb = problem_desc(prob, prob.f, neumann_bc, keep)
     ue = user_exprs_ref(prob.μ, prob.σ, prob.g, prob.f, keep)
     se = Vector{T}(undef, 1)
@@ -224,7 +234,7 @@ function mlp_b200(M, L, K, x::Vector{T}, mc_sample!, prob, neumann_bc; compat_th
     sym = T === Float64 ? :hdp_mlp_solve_f64 : :hdp_mlp_solve_f32
     GC.@preserve keep x u se begin
         cfg = HdpMlpCfg(M, L, K, 1, 1, 0, compat_threads, 0, seed, sampler_desc(mc_sample!, keep),
-                        C_NULL, C_NULL, C_NULL,
+                        tr, tn, ts,
                         isnothing(ue) ? Ptr{HdpUserExprs}(C_NULL) : Base.unsafe_convert(Ptr{HdpUserExprs}, ue),
                         0, HDP_MEM_HOST, 0.0, std_err ? Ptr{Cvoid}(pointer(se)) : C_NULL)
         rc = ccall((sym, libhdp), Cint,
@@ -315,7 +325,7 @@ end
 # The raw call: pointers are host or device addresses according to `mem_flags`.  y1 holds x0_batch on
 # entry (:182); with `z` it also performs `mc_sample!(z, y1)` (:186-189) in the same kernel.
 function sde_loop_ccall!(::Type{T}, y0, y1, B, nsteps, dt, ts, μ, σ, tspan, d, neumann_bc, x0_sample!, mc_sample!, z, K,
-                         mem_flags; seed = rand(UInt64)) where {T <: HdpFloat}
+                         mem_flags; seed = rand(UInt64), dWall_inject = Ptr{T}(C_NULL)) where {T <: HdpFloat}
     keep = Any[]
     pb = problem_desc(μ, σ, SumSq(0.0), FZero(), tspan, neumann_bc, d, keep)
     h = handle()
@@ -327,7 +337,7 @@ function sde_loop_ccall!(::Type{T}, y0, y1, B, nsteps, dt, ts, μ, σ, tspan, d,
                    (Ptr{Cvoid}, Ref{HdpProblem}, Ptr{T}, Ptr{T}, Cint, Cint, T, Ptr{T}, Ref{HdpSampler}, UInt64, Ptr{T},
                     Ref{HdpSampler}, Ptr{T}, Cint, Cint, Cuint),
                    h.ptr, pb, y0, y1, B, nsteps, T(dt), isnothing(tsv) ? C_NULL : pointer(tsv),
-                   sampler_desc(x0_sample!, keep), seed, C_NULL, sampler_desc(mc_sample!, keep), z, K, 0, mem_flags)
+                   sampler_desc(x0_sample!, keep), seed, dWall_inject, sampler_desc(mc_sample!, keep), z, K, 0, mem_flags)
     end
     check(h, rc)
     nothing
@@ -357,11 +367,12 @@ end
 
 # convenience form without the reference's calling convention (what the tests and the epoch batching use)
 function sde_loop_b200!(y0::Matrix{T}, y1::Matrix{T}, nsteps::Integer, dt, prob, neumann_bc, x0_sample!;
-                        mc_sample! = NoSampling(), z = nothing, seed = rand(UInt64)) where {T <: HdpFloat}
+                        mc_sample! = NoSampling(), z = nothing, seed = rand(UInt64), dWall = nothing) where {T <: HdpFloat}
     K = isnothing(z) ? 0 : size(z, 3)
-    GC.@preserve y0 y1 z begin
+    GC.@preserve y0 y1 z dWall begin
         sde_loop_ccall!(T, pointer(y0), pointer(y1), size(y1, 2), nsteps, dt, nothing, prob.μ, prob.σ, prob.tspan, size(y1, 1),
-                        neumann_bc, x0_sample!, mc_sample!, isnothing(z) ? Ptr{T}(C_NULL) : pointer(z), K, HDP_MEM_HOST; seed)
+                        neumann_bc, x0_sample!, mc_sample!, isnothing(z) ? Ptr{T}(C_NULL) : pointer(z), K, HDP_MEM_HOST; seed,
+                        dWall_inject = isnothing(dWall) ? Ptr{T}(C_NULL) : pointer(dWall))   # parity mode: the array after randn!
     end
 end
 

@@ -53,6 +53,7 @@ static inline float u2f(uint32_t b) { float f; memcpy(&f, &b, 4); return f; }
 static inline uint32_t f2u(float x) { uint32_t b; memcpy(&b, &x, 4); return b; }
 static inline double rsqrt_approx(double x) { return (double)(float)(1.0 / sqrt(x)); }
 static inline float rsq_approx(float x) { return 1.0f / sqrtf(x); }
+static inline float sqrt_approx(float x) { return sqrtf(x); }
 static inline float lg2_approx(float x) { return log2f(x); }
 static inline float sin_approx(float x) { return sinf(x); }
 static inline float cos_approx(float x) { return cosf(x); }

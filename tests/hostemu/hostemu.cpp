@@ -344,11 +344,12 @@ static int emu_sde_loop(const hdp_problem* prob, T* y0, T* y1, int B, int nsteps
     int flags[2] = {0, 0};
     unsigned long long ctr = 0;
     const bool const_coef = prob->mu_kind == HDP_COEF_CONST && prob->sigma_kind == HDP_COEF_CONST && !mlp_assoc && !force_generic;
-    const int bc = !const_coef ? K1_GENERIC : !pb.has_bc ? K1_NOBC : (pb.bc_is_scalar && pb.lo_s == -pb.hi_s) ? K1_SYM : K1_GENERIC;
+    int bc = !const_coef ? K1_GENERIC : !pb.has_bc ? K1_NOBC : (pb.bc_is_scalar && pb.lo_s == -pb.hi_s) ? K1_SYM : K1_GENERIC;
+    if (bc != K1_GENERIC && pb.mu_c == (T)0) bc += 2;
     T* zz = (z && mcs.kind != HDP_SAMPLER_NONE && K > 0) ? z : nullptr;
 #define EMU_K1(INJ, BC) sde_loop_kernel<T, false, INJ, BC>(pb, y0, y1, n_el, nsteps, dt, x0s, nullptr, seed, dW, mcs, zz, K, flags, &ctr, mlp_assoc, 0, ts)
-    if (dW) { if (bc == K1_SYM) EMU_K1(true, K1_SYM); else if (bc == K1_NOBC) EMU_K1(true, K1_NOBC); else EMU_K1(true, K1_GENERIC); }
-    else { if (bc == K1_SYM) EMU_K1(false, K1_SYM); else if (bc == K1_NOBC) EMU_K1(false, K1_NOBC); else EMU_K1(false, K1_GENERIC); }
+    if (dW) { if (bc == K1_SYM) EMU_K1(true, K1_SYM); else if (bc == K1_NOBC) EMU_K1(true, K1_NOBC); else if (bc == K1_SYM0) EMU_K1(true, K1_SYM0); else if (bc == K1_NOBC0) EMU_K1(true, K1_NOBC0); else EMU_K1(true, K1_GENERIC); }
+    else { if (bc == K1_SYM) EMU_K1(false, K1_SYM); else if (bc == K1_NOBC) EMU_K1(false, K1_NOBC); else if (bc == K1_SYM0) EMU_K1(false, K1_SYM0); else if (bc == K1_NOBC0) EMU_K1(false, K1_NOBC0); else EMU_K1(false, K1_GENERIC); }
 #undef EMU_K1
     if (bounces) *bounces = ctr;
     return flags[0] ? HDP_ERR_START_OUTSIDE_DOMAIN : HDP_OK;
