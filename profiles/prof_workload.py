@@ -1,5 +1,5 @@
 """Small fixed workloads for ncu captures (see profiles/README.md).
-usage: python profiles/prof_workload.py mlp [n_solves] | sde [B] | ens [B] | c4 | c5"""
+usage: python profiles/prof_workload.py mlp [n_solves] | c1 [n_solves] | sde [B] | ens [B] | c4 | c5"""
 import ctypes as C
 import os
 import sys
@@ -16,6 +16,13 @@ if what == "mlp":
     d = 100
     prob = H.ParabolicPDEProblem(0.0, 1.0, np.zeros(d), (0.0, 0.5), g=H.ExpSumSq(0.25), f=H.FAllenCahn(1.0),
                                  neumann_bc=(np.full(d, -0.5), np.full(d, 0.5)))
+    for it in range(3):
+        u, st = H._ml_picard_batch(prob, H.MLP(), n_solves=n, seed=11 + it, handle=h)
+        print(it, u.mean(), st)
+elif what == "c1":
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+    d = 10
+    prob = H.ParabolicPDEProblem(0.0, 0.1, np.zeros(d), (0.0, 0.5), g=H.SumSq(), f=H.FZero())
     for it in range(3):
         u, st = H._ml_picard_batch(prob, H.MLP(), n_solves=n, seed=11 + it, handle=h)
         print(it, u.mean(), st)

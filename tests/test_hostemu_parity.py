@@ -218,3 +218,51 @@ def test_error_bar_covers_the_scatter_of_independent_solves(H, emu):
     sd = float(np.std(u, ddof=1))
     se = float(np.sqrt(np.mean(st.se ** 2)))
     assert 0.6 * sd <= se <= 1.6 * sd, (sd, se)
+
+
+# ---------------------------------------------------------------------------------------------
+# the specialised coordinate loops in RNG mode with an even d (no partial vec-group), on the CPU
+# ---------------------------------------------------------------------------------------------
+def _leaf_cases(H):
+    c = {}
+    c["sym_d6"] = (H.ParabolicPDEProblem(0.0, 1.0, np.zeros(6), (0.0, 0.5), g=H.ExpSumSq(0.25), f=H.FAllenCahn(1.0),
+                                         neumann_bc=(-0.5, 0.5)), H.MLP(M=3, L=3, K=2), np.float64)     # partial last batches (M = 3)
+    c["sym_d4_M4"] = (H.ParabolicPDEProblem(0.0, 1.0, np.zeros(4), (0.0, 0.5), g=H.ExpSumSq(0.25), f=H.FAllenCahn(1.0),
+                                            neumann_bc=(-0.5, 0.5)), H.MLP(M=4, L=3, K=3), np.float64)
+    c["box_mu_d4"] = (H.ParabolicPDEProblem(0.3, 0.8, np.full(4, 0.1), (0.0, 0.5), g=H.SumSq(1.0), f=H.FLinear(0.3),
+                                            neumann_bc=(-0.3, 0.7)), H.MLP(M=3, L=3, K=2), np.float64)  # mu != 0, general scalar box
+    c["nobc_d8"] = (H.ParabolicPDEProblem(0.05, 0.3, np.zeros(8), (0.0, 0.5), g=H.InvSumSq(2.0, 0.4), f=H.FAllenCahn(-1.0)),
+                    H.MLP(M=5, L=2, K=2), np.float64)
+    c["wild_sym_d2"] = (H.ParabolicPDEProblem(0.0, 30.0, np.zeros(2), (0.0, 1.0), g=H.ExpSumSq(0.25), f=H.FAllenCahn(1.0),
+                                              neumann_bc=(-0.5, 0.5)), H.MLP(M=3, L=3, K=2), np.float64)  # many double hits, far excursions
+    c["nonlocal_dead_d4"] = (H.PIDEProblem(0.0, 0.6, np.zeros(4), (0.0, 0.5), H.ExpSumSq(0.25), H.FNLAllenCahnDiff(),
+                                           neumann_bc=(-0.5, 0.5)),
+                             H.MLP(M=3, L=3, K=3, mc_sample=H.UniformSampling(-0.5, 0.5)), np.float64)  # level-0 samples are dead draws
+    c["replicator_live_d2"] = (H.PIDEProblem(0.0, 0.1, np.zeros(2), (0.0, 0.5), H.GaussDensity(1e-2), H.FNLReplicatorMutator(1.0)),
+                               H.MLP(M=3, L=3, K=2, mc_sample=H.NormalSampling(1.0)), np.float64)       # f reads z: sites not batched, g-term is
+    c["sym_d8_f32"] = (H.ParabolicPDEProblem(0.0, 1.0, np.zeros(8, dtype=np.float32), (0.0, 0.5), g=H.ExpSumSq(0.25),
+                                             f=H.FAllenCahn(1.0), neumann_bc=(-0.5, 0.5)), H.MLP(M=3, L=3, K=2), np.float32)
+    return c
+
+
+@pytest.mark.parametrize("name", ["sym_d6", "sym_d4_M4", "box_mu_d4", "nobc_d8", "wild_sym_d2", "nonlocal_dead_d4",
+                                  "replicator_live_d2", "sym_d8_f32"])
+def test_fast_loops_match_the_oracle_on_the_same_philox_draws(H, O, emu, name):
+    """RNG mode takes the specialised loops (no boundary / symmetric box / scalar box, mu = 0 or not, dead sampler draws);
+    the oracle draws the same Philox numbers by ordinal.  Values to the generator's accuracy (libm vs the product's
+    tables), wall hits exact, for every cut and for a sharded run.  (These cases were written for the leaf-batch
+    experiment of profiles/r2p_leaf_batch_experiment.md, which they passed; it was slower and is not in the product.)"""
+    prob, alg, dt = _leaf_cases(H)[name]
+    pb, keep = prob.to_c()
+    sm, k2 = alg.mc_sample._descriptor(prob.d)
+    normal = isinstance(alg.mc_sample, H.NormalSampling)
+    for seed in (3, 1234567):
+        uo, info = O.ml_picard(pb, sm, alg.M, alg.L, alg.K, np.asarray(prob.x, dtype=dt), O.Rng.philox(seed, dt, normal))
+        assert info["rc"] == 0
+        tol = 1e-11 if dt == np.float64 else 2e-5
+        for target, nranks in ((0, 1), (7, 1), (200, 1), (100000, 1), (200, 3)):
+            u, rc, st = emu_solve(H, emu, prob, alg, dt, seed=seed, target_units=target, nranks=nranks)
+            assert rc == 0
+            assert rel_err(float(u[0]), uo) <= tol, (name, seed, target, nranks, float(u[0]), uo)
+            if dt == np.float64 and name != "wild_sym_d2":
+                assert st.bounces == info["bounces"], (name, seed, target, nranks)
