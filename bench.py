@@ -301,7 +301,7 @@ def run_ours(args, rank, world, local_rank):
                        "parallelism": f"headline: independent solves sharded over {world} rank(s), no data-path collective; "
                                       "extra.strong (N > 1): ONE solve sharded by subtree, one ncclAllReduce of a double per crown node",
                        "l2": "256 MB flush between steps (untimed); the path is compute-bound, inputs are d doubles",
-                       "rng": "Philox4x32-10 (fixed key, seed and consumption ordinal in the counter) + table-driven fp64 Box-Muller, generated in registers"},
+                       "rng": "Philox4x32-7 (fixed key, seed and consumption ordinal in the counter) + table-driven fp64 Box-Muller, generated in registers"},
             "reflected_path_steps_per_sec": value * PATH_STEPS_PER_SOLVE,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": D * 8, "d2h_bytes_per_step": n_local * 8,
                     "ms_per_step": 1e3 * e2e_s / args.steps, "api": "hdpde_b200._ml_picard_batch -> hdp_mlp_solve_f64 (host buffers)"},
@@ -338,7 +338,7 @@ def run_ours(args, rank, world, local_rank):
 
 def strong_workloads(H):
     """One solve large enough to occupy several GPUs: Allen-Cahn d=100 with Neumann reflection at
-    M=8, L=5 (1,184,968 path-steps), the same at d=1000 (1.18 G coordinate-steps, the strong-scaling case of
+    M=8, L=5 (1,184,968 path-steps) and M=8, L=6 (19.5 M path-steps), the L=5 one at d=1000 (1.18 G coordinate-steps, the strong-scaling case of
     BASELINE configs[4]) and BASELINE configs[3] (C4: non-local Fisher-KPP d=10, M=4, L=5, K=10, 45.4 M path-steps)."""
     d = 100
     ac = H.ParabolicPDEProblem(0.0, 1.0, np.zeros(d), (0.0, 0.5), g=H.ExpSumSq(0.25), f=H.FAllenCahn(1.0),
@@ -351,6 +351,9 @@ def strong_workloads(H):
     ac1000 = H.ParabolicPDEProblem(0.0, 1.0, np.zeros(d), (0.0, 0.5), g=H.ExpSumSq(0.25), f=H.FAllenCahn(1.0),
                                    neumann_bc=(np.full(d, -0.5), np.full(d, 0.5)))
     return {"allen_cahn_d100_M8_L5_one_solve": (ac, H.MLP(M=8, L=5, K=10)),
+            # one level more: 19,534,536 path-steps (1.95 G coordinate-steps, ~6 ms on one B200) — the d=100 solve that is
+            # large enough for "7x at 8 GPUs" to be measurable on ONE solve (SURVEY 8e caveat (b))
+            "allen_cahn_d100_M8_L6_one_solve": (ac, H.MLP(M=8, L=6, K=10)),
             "allen_cahn_d1000_M8_L5_one_solve": (ac1000, H.MLP(M=8, L=5, K=10)),   # SURVEY 8d, C5 strong scaling
             "c4_nonlocal_fisher_d10_L5_one_solve": (c4, a4)}
 

@@ -45,7 +45,7 @@ struct hdp_context {
     std::mutex mu;
     std::string err;
     // grow-only scratch, indexed by role
-    enum { B_A = 0, B_B, B_C, B_D, B_E, B_F, B_G, B_H, B_I, B_J, B_K, B_L, B_M, B_O, B_P, B_Q, B_N };
+    enum { B_A = 0, B_B, B_C, B_D, B_E, B_F, B_G, B_H, B_I, B_J, B_K, B_L, B_M, B_O, B_P, B_Q, B_R, B_N };
     hdp::DevBuf buf[B_N];
     int* d_flags = nullptr;          // [0] error flag, [1..] spare
     unsigned long long* d_ctr = nullptr; // [0] work counter, [1] bounce counter

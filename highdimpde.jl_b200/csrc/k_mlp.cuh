@@ -86,6 +86,10 @@ template <typename T> struct MlpParams {
     double* lvstat;           // [n_solves][3*(kMaxL+1)]: n, sum, sum of squares per root level (entry L: g-term)
     T* std_err;               // [n_solves]
     int zero;        // 0, opaque to the compiler (draw_k_init)
+    // combine pass, nodes with more than kBigNode units (the root of a finely cut tree has 10^4..10^5): their
+    // units are summed by stage_nb blocks each first (mlp_prereduce_kernel), stage[launch item][block][kCmbStage]
+    const double* stage;
+    int stage_nb;
     unsigned long long* work_ctr;
     unsigned long long* bounce_ctr;
     int* flags;
@@ -817,37 +821,45 @@ __device__ __forceinline__ void assert_in_box(Ctx<T, G>& c, const MlpParams<T>& 
 
 // geometry of one explicit site: r, x2, x3_h
 // (`list`: the explicit sites of one depth — or, when a solve is sharded, the replicated upper sites of one
-// depth / the bottom sites this rank owns)
+// depth / the sites of one depth at and below this rank's ownership roots)
+// One item per (site, solve, point): point 0 is x2, point 1 + h is x3_h.  A pass over a depth is a link in a
+// chain of dependent launches and rarely fills the GPU, so its duration is the latency of one item: a site
+// walked by a single lane group (x2, then K sampled points one after the other) held every launch at 25-30 us
+// for a non-local problem.  A shifted sampler starts from x2: its items recompute x2 (the same bits, stored by
+// all of them) instead of waiting for the first; only point 0 reports r, the feature and the wall hits of x2.
 template <typename T, int G>
 __device__ __forceinline__ void expand_item(Ctx<T, G>& c, const MlpParams<T>& P, const int32_t* list, u64 item,
                                             bool count_hits = true)
 {
+    const int npt = 1 + P.Kp;
+    const int j = (int)(item % (u64)npt);
+    item /= (u64)npt;
     const int solve = (int)(item % (u64)P.n_solves);
     const int sidx = list[item / (u64)P.n_solves];
     const PlanSite st = P.sites[sidx];
     const PlanNode nd = P.nodes[st.node];
     c.seed = P.seed0 + (u64)solve;
-    const T s = nd.time_site < 0 ? P.pb.t0 : P.site_r[(u64)solve * P.n_sites + nd.time_site];
-    const XAcc<T> xp = c.point(solve, nd.point);
-    const T u = time_uniform<T>(P, c.seed, st.r);
-    const T r = add_rn(s, mul_rn(sub_rn(P.pb.t1, s), u));
     const XAcc<T> x2 = c.point(solve, st.x2_point);
-    const Feat<T> f2 = em_step<T, G>(c, P, xp, x2, s, r, st.c);
-    if (c.lane == 0) {
-        P.site_r[(u64)solve * P.n_sites + sidx] = r;
-        P.feat[(u64)solve * P.n_points + st.x2_point] = f2.ssq;
-    }
-    if (P.Kp > 0) {
-        const int l = st.l;
-        const u64 sub = P.S[l] + (l >= 2 ? P.S[l - 1] : 0);
-        u64 qq = st.s + sub;
-        for (int h = 0; h < P.Kp; ++h) {
-            const XAcc<T> x3 = c.point(solve, st.x3_point0 + h);
-            const Feat<T> f3 = sample_step<T, G>(c, &x3, x2, qq);
-            if (c.lane == 0) P.feat[(u64)solve * P.n_points + st.x3_point0 + h] = f3.ssq;
-            if (P.pb.has_bc && l >= 1) assert_in_box<T, G>(c, P, x3); // U_l(x3) steps from x3 (a level-0 site never does)
-            qq += 1 + sub;
+    if (j == 0 || (P.sm.kind == HDP_SAMPLER_NORMAL && P.sm.shifted)) {
+        const T s = nd.time_site < 0 ? P.pb.t0 : P.site_r[(u64)solve * P.n_sites + nd.time_site];
+        const XAcc<T> xp = c.point(solve, nd.point);
+        const T u = time_uniform<T>(P, c.seed, st.r);
+        const T r = add_rn(s, mul_rn(sub_rn(P.pb.t1, s), u));
+        const Feat<T> f2 = em_step<T, G>(c, P, xp, x2, s, r, st.c);
+        if (j == 0 && c.lane == 0) {
+            P.site_r[(u64)solve * P.n_sites + sidx] = r;
+            P.feat[(u64)solve * P.n_points + st.x2_point] = f2.ssq;
         }
+        if (j != 0) c.nb = 0; // (point 0 counts the wall hits of the step)
+    }
+    if (j > 0) {
+        const int l = st.l, h = j - 1;
+        const u64 sub = P.S[l] + (l >= 2 ? P.S[l - 1] : 0);
+        const u64 qq = st.s + sub + (u64)h * (1 + sub);
+        const XAcc<T> x3 = c.point(solve, st.x3_point0 + h);
+        const Feat<T> f3 = sample_step<T, G>(c, &x3, x2, qq);
+        if (c.lane == 0) P.feat[(u64)solve * P.n_points + st.x3_point0 + h] = f3.ssq;
+        if (P.pb.has_bc && l >= 1) assert_in_box<T, G>(c, P, x3); // U_l(x3) steps from x3 (a level-0 site never does)
     }
     const int nb = gsumi<G>(c.nb, c.gmask);
     const int bad = gsumi<G>(c.bad, c.gmask);
@@ -909,6 +921,8 @@ __device__ __forceinline__ void unit_item(Ctx<T, G>& c, const MlpParams<T>& P, u
 // children, and a single warp walking them through dependent loads was 0.4 ms of a 1.2 ms solve; `xwarp`
 // is then the block's shared staging area (kCmbStage doubles per warp) for the fixed-order sum over its warps.
 constexpr int kCmbStage = kMaxL + 1 + 3 * (kMaxL + 1);
+constexpr int kBigNode = 4096;   // units of one node above which several blocks share the sum
+constexpr int kStageBlocks = 64; // blocks per such node
 template <typename T>
 __device__ __forceinline__ void combine_item(const MlpParams<T>& P, const int32_t* list, u64 item, int lane, int nl,
                                              unsigned mask = 0xffffffffu, int mode = CMB_ALL, double* xwarp = nullptr)
@@ -949,7 +963,21 @@ __device__ __forceinline__ void combine_item(const MlpParams<T>& P, const int32_
 #pragma unroll
         for (int l = 0; l < kMaxL; ++l) Bl[l] = (T)0;
         T Gs = (T)0;
-        if (mode != CMB_FINAL) {
+        if (mode != CMB_FINAL && P.stage != nullptr && nd.unit_end - nd.unit_begin > kBigNode) {
+            // the units were summed by mlp_prereduce_kernel: one record per block
+            for (int b = lane; b < P.stage_nb; b += nl) {
+                const double* q = P.stage + (item * (u64)P.stage_nb + (u64)b) * kCmbStage;
+#pragma unroll
+                for (int l = 0; l < kMaxL; ++l) Bl[l] += (T)q[l];
+                Gs += (T)q[kMaxL];
+                if (stats) {
+#pragma unroll
+                    for (int l = 0; l <= kMaxL; ++l) {
+                        Ns[l] += q[kMaxL + 1 + 3 * l]; Sm[l] += q[kMaxL + 2 + 3 * l]; Sq[l] += q[kMaxL + 3 + 3 * l];
+                    }
+                }
+            }
+        } else if (mode != CMB_FINAL) {
             for (int u = nd.unit_begin + lane; u < nd.unit_end; u += nl) {
                 if (mode == CMB_PARTIAL && !P.unit_mine[u]) continue;
                 const int tag = P.unit_tag[u];
@@ -986,6 +1014,9 @@ __device__ __forceinline__ void combine_item(const MlpParams<T>& P, const int32_
             const T b4 = cv(ch[1]);
             T b3 = (T)0;
             if (P.Kp > 0) {
+                // (unrolled: the loads of four sampled points are in flight together — a combine pass is a link in a
+                // chain of dependent launches and lasts as long as one site's chain of dependent loads)
+#pragma unroll 4
                 for (int h = 0; h < P.K; ++h) {
                     const T f3 = feat[st.x3_point0 + h];
                     const T v = cv(ch[2 + 2 * h]);
@@ -1109,16 +1140,20 @@ __global__ void mlp_init_kernel(const __grid_constant__ MlpParams<T> P, const T*
         init_item<T>(P, x0, q);
 }
 
+// (two lists per launch: a sharded solve expands the replicated upper sites of a depth and its own sites of
+// that depth together — they do not depend on each other, and every launch of the chain costs 10-20 us)
 template <typename T, int G>
 __global__ void __launch_bounds__(128) mlp_expand_kernel(const __grid_constant__ MlpParams<T> P, const int32_t* list, int count,
-                                                         int count_hits)
+                                                         int count_hits, const int32_t* list2, int count2, int count_hits2)
 {
     if constexpr (sizeof(T) == 8) tables_init();
     Ctx<T, G> c;
     ctx_init<T, G>(c, P, (u64)blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31);
     const u64 gid = c.tid / G;
-    if (gid >= (u64)count * (u64)P.n_solves) return;
-    expand_item<T, G>(c, P, list, gid, count_hits != 0);
+    const u64 per = (u64)P.n_solves * (u64)(1 + P.Kp);
+    const u64 n1 = (u64)count * per;
+    if (gid < n1) expand_item<T, G>(c, P, list, gid, count_hits != 0);
+    else if (gid < n1 + (u64)count2 * per) expand_item<T, G>(c, P, list2, gid - n1, count_hits2 != 0);
 }
 
 // the work units: dynamic fetch, one warp takes 32/G consecutive work items at a time
@@ -1151,6 +1186,86 @@ __global__ void __launch_bounds__(HDP_MLP_BLOCK, Tune<U>::MB) mlp_units_kernel(c
         if (wl < n_work) unit_item<T, G, U, FM>(c, P, wl);
     }
     if (c.bad) atomicExch(&P.flags[0], 1);
+}
+
+// First stage of the combine pass for nodes with more than kBigNode units: grid (kStageBlocks, items); block b of
+// an item sums its share of the node's unit partials (this rank's, when the solve is sharded: mode CMB_PARTIAL)
+// per level — and, for the root, the sample statistics of the error bar — in a fixed order, and leaves one
+// kCmbStage record.  A single block of 512 lanes walking the 10^5 units of the root of Allen-Cahn d=100, M=8, L=6
+// through dependent loads took 0.23 ms of a 1.6 ms sharded solve.
+template <typename T>
+__global__ void __launch_bounds__(256) mlp_prereduce_kernel(const __grid_constant__ MlpParams<T> P, const int32_t* list, int mode,
+                                                            double* stage)
+{
+    const u64 item = blockIdx.y;
+    const int solve = (int)(item % (u64)P.n_solves);
+    const int nidx = list[item / (u64)P.n_solves];
+    const PlanNode nd = P.nodes[nidx];
+    const int nu = nd.unit_end - nd.unit_begin;
+    if (nu <= kBigNode) return;
+    const double* part = P.partial + (u64)solve * P.n_units;
+    const bool stats = nidx == 0 && P.lvstat != nullptr;
+    const double* rsq = stats ? P.rootsq + (u64)solve * P.rootsq_stride : nullptr;
+    const int per = (nu + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int u0 = nd.unit_begin + (int)blockIdx.x * per;
+    const int u1 = u0 + per < nd.unit_end ? u0 + per : nd.unit_end;
+    T Bl[kMaxL];
+    T Gs = (T)0;
+    double Ns[kMaxL + 1], Sm[kMaxL + 1], Sq[kMaxL + 1];
+#pragma unroll
+    for (int l = 0; l < kMaxL; ++l) Bl[l] = (T)0;
+#pragma unroll
+    for (int l = 0; l <= kMaxL; ++l) { Ns[l] = 0.0; Sm[l] = 0.0; Sq[l] = 0.0; }
+    for (int u = u0 + (int)threadIdx.x; u < u1; u += (int)blockDim.x) {
+        if (mode == CMB_PARTIAL && !P.unit_mine[u]) continue;
+        const int tag = P.unit_tag[u];
+        const T v = (T)part[u];
+        const int sl = (tag >> 4) == UNIT_G ? P.L : (tag & 15);
+        if ((tag >> 4) == UNIT_G) Gs += v;
+        else {
+#pragma unroll
+            for (int l = 0; l < kMaxL; ++l)
+                if (l == (tag & 15)) Bl[l] += v;
+        }
+        if (stats) {
+            const PlanUnit un = P.units[u];
+#pragma unroll
+            for (int l = 0; l <= kMaxL; ++l)
+                if (l == sl) { Ns[l] += (double)(un.k1 - un.k0); Sm[l] += rsq[2 * u]; Sq[l] += rsq[2 * u + 1]; }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int l = 0; l < kMaxL; ++l) Bl[l] += __shfl_xor_sync(0xffffffffu, Bl[l], o);
+        Gs += __shfl_xor_sync(0xffffffffu, Gs, o);
+        if (stats) {
+#pragma unroll
+            for (int l = 0; l <= kMaxL; ++l) {
+                Ns[l] += __shfl_xor_sync(0xffffffffu, Ns[l], o);
+                Sm[l] += __shfl_xor_sync(0xffffffffu, Sm[l], o);
+                Sq[l] += __shfl_xor_sync(0xffffffffu, Sq[l], o);
+            }
+        }
+    }
+    __shared__ double xw[8 * kCmbStage];
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        double* q = xw + w * kCmbStage;
+        for (int l = 0; l < kMaxL; ++l) q[l] = (double)Bl[l];
+        q[kMaxL] = (double)Gs;
+        for (int l = 0; l <= kMaxL; ++l) { q[kMaxL + 1 + 3 * l] = Ns[l]; q[kMaxL + 2 + 3 * l] = Sm[l]; q[kMaxL + 3 + 3 * l] = Sq[l]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < kCmbStage) { // entry by entry, the warps in order
+        double a = 0.0;
+        bool as_t = threadIdx.x <= kMaxL; // level sums and the g-term are sums of T values
+        T at = (T)0;
+        for (int ww = 0; ww < (int)(blockDim.x >> 5); ++ww) {
+            const double v = xw[ww * kCmbStage + threadIdx.x];
+            if (as_t) at += (T)v; else a += v;
+        }
+        stage[(item * (u64)gridDim.x + blockIdx.x) * kCmbStage + threadIdx.x] = as_t ? (double)at : a;
+    }
 }
 
 // nl lanes (a power of two, 1..32) share one (node, solve): 32 where nodes have many children (the

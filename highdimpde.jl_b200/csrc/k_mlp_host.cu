@@ -22,7 +22,7 @@ MlpPlan::~MlpPlan()
 }
 MlpSharding::~MlpSharding()
 {
-    void* ps[] = {d_exec_own, d_upper_sites, d_own_bottom_sites, d_owned_nodes, d_crown_nodes, d_crown_leaves,
+    void* ps[] = {d_exec_own, d_upper_sites, d_own_sites, d_owned_nodes, d_crown_nodes, d_crown_leaves,
                   d_crown_final, d_unit_mine, d_site_cls, d_node_slot};
     for (void* p : ps)
         if (p) cudaFree(p);
@@ -56,12 +56,15 @@ template <> MlpLaunchers<float> launchers_for<float>(int G)
 int pick_group(int forced, int nvec, double path_steps_total, int n_solves, double sms)
 {
     if (forced > 0) return forced;
-    int G = 1;
-    while (G < 32 && (nvec + G - 1) / G > (n_solves < 8 ? 16 : 64)) G *= 2;
     auto resident_groups = [&](int g) {
         const int npl = (nvec + g - 1) / g;
         return sms * (npl >= 12 ? 4 : 6) * 128.0 / g; // blocks per SM of the two kernel variants
     };
+    // (a handful of solves that are each large — Allen-Cahn d=100, M=8, L=6: 19.5 M path-steps, 257 per resident
+    // lane — are in the throughput regime like a batch: 7.85 ms with one lane per point against 9.29 ms with four)
+    const bool few_small = n_solves < 8 && path_steps_total < 64.0 * resident_groups(1);
+    int G = 1;
+    while (G < 32 && (nvec + G - 1) / G > (few_small ? 16 : 64)) G *= 2;
     // (a batch never widens to the point where lanes of a group idle: 2 G <= nvec)
     const int gmax = n_solves < 8 ? nvec : nvec / 2;
     while (G < 32 && G < gmax && path_steps_total < 12.0 * resident_groups(G)) G *= 2;
@@ -79,8 +82,10 @@ template <typename V> int upload(hdp_context* h, const std::vector<V>& v, void**
 // The planner materialises every unit (56 bytes each on host and device): a cut finer than kMaxPlanUnits
 // units per solve is refused and retried with twice the threshold (a plan that failed is remembered as an
 // alias of the one that replaced it).
-constexpr size_t kMaxPlanUnits = 3u << 20;
-int get_plan(hdp_context* h, int M, int L, int K, bool nonlocal, double thresh, int compat,
+// A sharded solve holds the whole plan on every rank but works on 1/nranks of it: it may be cut finer (and so
+// may a caller who names the number of units, cfg->target_units).
+constexpr size_t kMaxPlanUnits = 3u << 20, kMaxPlanUnitsSharded = 8u << 20;
+int get_plan(hdp_context* h, int M, int L, int K, bool nonlocal, double thresh, int compat, size_t max_units,
              std::shared_ptr<MlpPlan>* out, std::string* key_out)
 {
     char key[160];
@@ -95,7 +100,7 @@ int get_plan(hdp_context* h, int M, int L, int K, bool nonlocal, double thresh, 
     }
     const std::string asked = key;
     auto plan = std::make_shared<MlpPlan>();
-    while (!mlp_build_plan(M, L, K, nonlocal, thresh, compat, plan.get(), kMaxPlanUnits)) thresh *= 2.0;
+    while (!mlp_build_plan(M, L, K, nonlocal, thresh, compat, plan.get(), max_units)) thresh *= 2.0;
     snprintf(key, sizeof(key), "%d/%d/%d/%d/%.6g/%d", M, L, K, (int)nonlocal, thresh, compat);
     *key_out = key;
     it = h->plans.find(key);
@@ -127,7 +132,7 @@ int get_sharding(hdp_context* h, const std::string& plan_key, const MlpPlan& pla
     int rc;
     if ((rc = upload(h, sh->exec_own, &sh->d_exec_own)) != HDP_OK) return rc;
     if ((rc = upload(h, sh->upper_sites, &sh->d_upper_sites)) != HDP_OK) return rc;
-    if ((rc = upload(h, sh->own_bottom_sites, &sh->d_own_bottom_sites)) != HDP_OK) return rc;
+    if ((rc = upload(h, sh->own_sites, &sh->d_own_sites)) != HDP_OK) return rc;
     if ((rc = upload(h, sh->owned_nodes, &sh->d_owned_nodes)) != HDP_OK) return rc;
     if ((rc = upload(h, sh->crown_nodes, &sh->d_crown_nodes)) != HDP_OK) return rc;
     if ((rc = upload(h, sh->crown_leaves, &sh->d_crown_leaves)) != HDP_OK) return rc;
@@ -319,7 +324,8 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
     }
     std::shared_ptr<MlpPlan> plan;
     std::string plan_key;
-    if ((rc = get_plan(h, M, L, K, nonlocal, thresh, compat, &plan, &plan_key)) != HDP_OK) return rc;
+    if ((rc = get_plan(h, M, L, K, nonlocal, thresh, compat, (nranks > 1 || cfg->target_units > 0) ? kMaxPlanUnitsSharded : kMaxPlanUnits, &plan,
+                       &plan_key)) != HDP_OK) return rc;
     std::shared_ptr<MlpSharding> sh;
     if (nranks > 1 && (rc = get_sharding(h, plan_key, *plan, nranks, rank, &sh)) != HDP_OK) return rc;
 
@@ -428,6 +434,22 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
     }
 
     const int launches0 = h->launches;
+#ifdef HDP_PHASE_TRACE
+    // debugging build (make EXTRA=-DHDP_PHASE_TRACE): an event after every launch, the per-launch times on stderr
+    static cudaEvent_t tr_ev[64];
+    static const char* tr_name[64];
+    static int tr_cnt[64];
+    int tr_n = 0;
+    auto trace = [&](const char* name, int cnt) {
+        if (tr_n >= 64) return;
+        if (!tr_ev[tr_n]) cudaEventCreate(&tr_ev[tr_n]);
+        cudaEventRecord(tr_ev[tr_n], h->stream);
+        tr_name[tr_n] = name; tr_cnt[tr_n] = cnt;
+        ++tr_n;
+    };
+#else
+    auto trace = [](const char*, int) {};
+#endif
     double tail_host[kXTail] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (!on_device)
         HDP_CUDA(h, cudaMemcpyAsync((void*)d_x0, x0, (size_t)cfg->n_x0 * d * sizeof(T), cudaMemcpyHostToDevice, h->stream));
@@ -441,39 +463,63 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
     {
         uint64_t tot = (uint64_t)n_solves * P.dpad;
         int gi = (int)std::min<uint64_t>((tot + 255) / 256, (uint64_t)sms * 8);
+        trace("start", 0);
         mlp_init_kernel<T><<<gi, 256, 0, h->stream>>>(P, d_x0);
         h->launches++;
+        trace("init", gi);
         HDP_CUDA(h, cudaGetLastError());
     }
-    auto launch_expand = [&](const int32_t* list, int cnt, int count_hits) -> int {
-        if (cnt == 0) return HDP_OK;
-        uint64_t groups = (uint64_t)cnt * n_solves;
+    auto launch_expand = [&](const int32_t* list, int cnt, int count_hits, const int32_t* list2 = nullptr, int cnt2 = 0,
+                             int count_hits2 = 0) -> int {
+        if (cnt + cnt2 == 0) return HDP_OK;
+        uint64_t groups = (uint64_t)(cnt + cnt2) * n_solves * (uint64_t)(1 + tab.Kp); // one lane group per (site, solve, point)
         int ge = (int)((groups * G + block - 1) / block);
         if (um) {
-            void* args[4] = {(void*)&P, (void*)&list, (void*)&cnt, (void*)&count_hits};
+            void* args[7] = {(void*)&P, (void*)&list, (void*)&cnt, (void*)&count_hits, (void*)&list2, (void*)&cnt2, (void*)&count_hits2};
             HDP_CUDA(h, cudaLaunchKernel((const void*)um->expand, dim3(ge), dim3(block), args, 0, h->stream));
-        } else HDP_CUDA(h, LN.expand(P, list, cnt, count_hits, ge, block, h->stream));
+        } else HDP_CUDA(h, LN.expand(P, list, cnt, count_hits, list2, cnt2, count_hits2, ge, block, h->stream));
         h->launches++;
+        trace("expand", cnt + cnt2);
         return HDP_OK;
     };
     // lanes per (node, solve) of a combine launch: a warp where some node has many children, 4 lanes otherwise
     auto launch_combine = [&](const int32_t* list, const int32_t* host_list, int cnt, int cmode) -> int {
         if (cnt == 0) return HDP_OK;
-        int most = 0;
+        int most = 0, most_units = 0;
+        for (int q = 0; q < cnt; ++q) most_units = std::max(most_units, plan->nodes[host_list[q]].unit_end - plan->nodes[host_list[q]].unit_begin);
+        // nodes with very many units: several blocks each sum a share first (mlp_prereduce_kernel)
+        const uint64_t items = (uint64_t)cnt * n_solves;
+        const bool staged = cmode != CMB_FINAL && most_units > kBigNode && items <= 1024;
+        MlpParams<T> Pc = P;
+        if (staged) {
+            double* stage = (double*)ensure(h, hdp_context::B_R, items * kStageBlocks * kCmbStage * sizeof(double));
+            if (!stage) return HDP_ERR_ALLOC;
+            mlp_prereduce_kernel<T><<<dim3(kStageBlocks, (unsigned)items), 256, 0, h->stream>>>(P, list, cmode, stage);
+            h->launches++;
+            HDP_CUDA(h, cudaGetLastError());
+            trace("prereduce", cnt);
+            Pc.stage = stage;
+            Pc.stage_nb = kStageBlocks;
+        }
         for (int q = 0; q < cnt; ++q) {
             const PlanNode& nd = plan->nodes[host_list[q]];
-            most = std::max(most, (nd.unit_end - nd.unit_begin) + (nd.site_end - nd.site_begin));
+            const int nu = nd.unit_end - nd.unit_begin;
+            most = std::max(most, ((staged && nu > kBigNode) ? kStageBlocks : nu) + (nd.site_end - nd.site_begin));
         }
-        // a handful of children: 4 lanes; many: a warp; thousands (the root of a finely cut tree): a block of 512
-        const int nl = most > 2048 ? 512 : (most > 16 ? 32 : 4);
+        // a handful of children: 4 lanes; many: a warp; thousands (the root of a finely cut tree): a block of 512 —
+        // but only where the list is too short to fill the GPU with warps (Allen-Cahn d=100, M=8, L=6: 5264 calls of
+        // depth 1 with a few thousand slice units each took 310 us as blocks of 512, a warp each is plenty)
+        const bool few = (uint64_t)cnt * n_solves <= 2 * (uint64_t)sms;
+        const int nl = (most > 2048 && few) ? 512 : (most > 16 ? 32 : 4);
         const int cb = nl > 128 ? nl : 128; // threads per block (one node per block when nl > 32)
         uint64_t tot = (uint64_t)cnt * n_solves * nl;
         int gc = (int)((tot + cb - 1) / cb);
         if (um) { // f is applied in the combine too: the user module's build of it
-            void* args[5] = {(void*)&P, (void*)&list, (void*)&cnt, (void*)&nl, (void*)&cmode};
+            void* args[5] = {(void*)&Pc, (void*)&list, (void*)&cnt, (void*)&nl, (void*)&cmode};
             HDP_CUDA(h, cudaLaunchKernel((const void*)um->combine, dim3(gc), dim3(cb), args, 0, h->stream));
-        } else mlp_combine_kernel<T><<<gc, cb, 0, h->stream>>>(P, list, cnt, nl, cmode);
+        } else mlp_combine_kernel<T><<<gc, cb, 0, h->stream>>>(Pc, list, cnt, nl, cmode);
         h->launches++;
+        trace(cmode == CMB_ALL ? "combine_all" : (cmode == CMB_PARTIAL ? "combine_partial" : "combine_final"), cnt);
         HDP_CUDA(h, cudaGetLastError());
         return HDP_OK;
     };
@@ -484,14 +530,14 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
             if ((rc = launch_expand(P.sites_by_depth + off, plan->site_depth_off[dep + 1] - off, 1)) != HDP_OK) return rc;
         }
     } else {
-        // the upper sites on every rank (rank 0 counts their wall hits), then the bottom sites this rank owns
+        // depth by depth: the upper sites on every rank (rank 0 counts their wall hits) together with the sites at
+        // and below this rank's ownership roots (a site's start point comes from a site one depth up)
         for (int dep = 0; dep <= plan->max_depth; ++dep) {
-            const int off = sh->upper_depth_off[dep];
-            if ((rc = launch_expand((const int32_t*)sh->d_upper_sites + off, sh->upper_depth_off[dep + 1] - off,
-                                    rank == 0 ? 1 : 0)) != HDP_OK)
+            const int off = sh->upper_depth_off[dep], off2 = sh->own_depth_off[dep];
+            if ((rc = launch_expand((const int32_t*)sh->d_upper_sites + off, sh->upper_depth_off[dep + 1] - off, rank == 0 ? 1 : 0,
+                                    (const int32_t*)sh->d_own_sites + off2, sh->own_depth_off[dep + 1] - off2, 1)) != HDP_OK)
                 return rc;
         }
-        if ((rc = launch_expand((const int32_t*)sh->d_own_bottom_sites, (int)sh->own_bottom_sites.size(), 1)) != HDP_OK) return rc;
     }
     HDP_CUDA(h, cudaEventRecord(h->evp[0], h->stream));
     // ---- the work units ----
@@ -501,6 +547,7 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
             HDP_CUDA(h, cudaLaunchKernel((const void*)um->units, dim3(grid), dim3(block), args, dyn_smem, h->stream));
         } else HDP_CUDA(h, LN.units[long_rows][mode](P, grid, block, dyn_smem, h->stream));
         h->launches++;
+        trace("units", (int)n_local);
     }
     HDP_CUDA(h, cudaEventRecord(h->evp[1], h->stream));
     if (!sh) {
@@ -513,22 +560,30 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
                 return rc;
         }
     } else {
-        // the calls below this rank's bottom sites, then this rank's share of every crown node
-        if ((rc = launch_combine((const int32_t*)sh->d_owned_nodes, sh->owned_nodes.data(), (int)sh->owned_nodes.size(),
-                                 CMB_ALL)) != HDP_OK)
-            return rc;
-        if ((rc = launch_combine((const int32_t*)sh->d_crown_nodes, sh->crown_nodes.data(), (int)sh->crown_nodes.size(),
-                                 CMB_PARTIAL)) != HDP_OK)
+        // the calls below this rank's ownership roots, bottom-up, then this rank's share of every crown node
+        for (int dep = plan->max_depth; dep >= 0; --dep) {
+            const int off = sh->owned_depth_off[dep];
+            if ((rc = launch_combine((const int32_t*)sh->d_owned_nodes + off, sh->owned_nodes.data() + off,
+                                     sh->owned_depth_off[dep + 1] - off, CMB_ALL)) != HDP_OK)
+                return rc;
+        }
+        // (the root first and alone: it has thousands of children and takes a block of lanes, the other crown
+        // nodes a few lanes each — one launch sized for the root spent 95 us on 4313 blocks of 512 threads)
+        if ((rc = launch_combine((const int32_t*)sh->d_crown_nodes, sh->crown_nodes.data(), 1, CMB_PARTIAL)) != HDP_OK) return rc;
+        if ((rc = launch_combine((const int32_t*)sh->d_crown_nodes + 1, sh->crown_nodes.data() + 1,
+                                 (int)sh->crown_nodes.size() - 1, CMB_PARTIAL)) != HDP_OK)
             return rc;
         HDP_CUDA(h, cudaEventRecord(h->evp[1], h->stream)); // (the local combine counts as unit work)
         rc = nccl_allreduce_f64_device(h, P.xbuf, x_count);
         if (rc != HDP_OK) return rc;
+        trace("allreduce", (int)x_count);
         HDP_CUDA(h, cudaEventRecord(h->evp[2], h->stream));
         if (!sh->crown_leaves.empty()) {
             const int cnt = (int)sh->crown_leaves.size();
             const uint64_t tot = (uint64_t)cnt * n_solves;
             mlp_scatter_kernel<T><<<(int)((tot + 127) / 128), 128, 0, h->stream>>>(P, (const int32_t*)sh->d_crown_leaves, cnt);
             h->launches++;
+            trace("scatter", cnt);
             HDP_CUDA(h, cudaGetLastError());
         }
         for (int dep = plan->max_depth; dep >= 0; --dep) {
@@ -568,6 +623,17 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
         HDP_CUDA(h, cudaMemcpyAsync(&se0, d_se, sizeof(T), cudaMemcpyDeviceToHost, h->stream));
     }
     HDP_CUDA(h, cudaStreamSynchronize(h->stream));
+#ifdef HDP_PHASE_TRACE
+    if (getenv("HDP_PHASE_TRACE")) {
+        fprintf(stderr, "[trace rank %d]", rank);
+        for (int i = 1; i < tr_n; ++i) {
+            float pm = 0;
+            cudaEventElapsedTime(&pm, tr_ev[i - 1], tr_ev[i]);
+            fprintf(stderr, " %s(%d)=%.1fus", tr_name[i], tr_cnt[i], pm * 1e3f);
+        }
+        fprintf(stderr, "\n");
+    }
+#endif
     if (stats) {
         float ms = 0;
         cudaEventElapsedTime(&ms, h->ev0, h->ev1);

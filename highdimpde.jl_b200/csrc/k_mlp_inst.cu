@@ -27,10 +27,10 @@ static cudaError_t inst_units(const MlpParams<T_>& P, int grid, int block, size_
     mlp_units_kernel<T_, G_, U, FM><<<grid, block, dyn_smem, st>>>(P);
     return cudaGetLastError();
 }
-static cudaError_t inst_expand(const MlpParams<T_>& P, const int32_t* list, int count, int count_hits, int grid, int block,
-                               cudaStream_t st)
+static cudaError_t inst_expand(const MlpParams<T_>& P, const int32_t* list, int count, int count_hits, const int32_t* list2,
+                               int count2, int count_hits2, int grid, int block, cudaStream_t st)
 {
-    mlp_expand_kernel<T_, G_><<<grid, block, 0, st>>>(P, list, count, count_hits);
+    mlp_expand_kernel<T_, G_><<<grid, block, 0, st>>>(P, list, count, count_hits, list2, count2, count_hits2);
     return cudaGetLastError();
 }
 } // namespace

@@ -12,7 +12,8 @@ template <typename T> struct MlpLaunchers {
     // coordinate loop the kernel was compiled for (em_mode_of: 0 general, EM_NOBC, EM_SYM, EM_BOX)
     int (*max_blocks_per_sm[3][4])(int block, size_t dyn_smem);
     cudaError_t (*units[3][4])(const MlpParams<T>& P, int grid, int block, size_t dyn_smem, cudaStream_t st);
-    cudaError_t (*expand)(const MlpParams<T>& P, const int32_t* list, int count, int count_hits, int grid, int block, cudaStream_t st);
+    cudaError_t (*expand)(const MlpParams<T>& P, const int32_t* list, int count, int count_hits, const int32_t* list2, int count2,
+                          int count_hits2, int grid, int block, cudaStream_t st);
 };
 
 #define HDP_DECL_INST(T, TN, G) MlpLaunchers<T> mlp_launchers_##TN##_g##G();

@@ -63,7 +63,8 @@ int64_t mlp_get_loop_num(int M, int64_t num, int thread_id, int nthreads)
 }
 
 namespace {
-constexpr double kMinExplicitCall = 64.0, kMinExplicitCallNonlocal = 16.0;
+constexpr double kMinExplicitCall = 64.0, kMinExplicitCallNonlocal = 16.0, kLongSite = 4.0;
+constexpr double kOwnItems = 64.0; // ownership roots per rank a sharded solve aims for (at least)
 struct Builder {
     MlpPlan* p;
     const MlpCountTables& t;
@@ -92,7 +93,14 @@ struct Builder {
         // one solve 0.99 -> 0.73 ms; and the C4 plan one level deeper has 16 M units), so such sites stay in
         // slice units, one site per unit at the finest.  A non-local site fans out into 1 + K child calls per
         // level, so there the detour pays from smaller calls on (replicator-mutator d=10, L=4: 1.16 vs 2.69 ms).
-        if (l >= 1 && t.W[l] > thresh && t.W[l] >= (t.Kp > 0 ? kMinExplicitCallNonlocal : kMinExplicitCall)) {
+        // A site whose child calls each fit a unit can still be far too long for one lane to walk: a non-local site
+        // is 1 + K' (or twice that) child calls, and with fewer such sites than resident lanes the units phase lasts
+        // as long as one of them however many GPUs share the solve (C4 on 8 ranks: 57 k level-1 sites of 89
+        // path-steps per rank, 0.7 ms each, for 114 k lanes).  Such a site becomes explicit too; its children are
+        // then whole-call units, read straight from partial[] by the combine pass.
+        const bool long_site = t.Ws[l] > kLongSite * thresh;
+        if (l >= 1 && (t.W[l] > thresh || long_site) &&
+            t.W[l] >= (t.Kp > 0 ? kMinExplicitCallNonlocal : kMinExplicitCall)) {
             for (int64_t k = 0; k < nsites; ++k) {
                 PlanSite st{};
                 st.node = id; st.l = l; st.depth = depth;
@@ -250,7 +258,7 @@ bool mlp_build_plan(int M, int L, int K, bool nonlocal, double thresh, int compa
 // ---------------------------------------------------------------------
 // sharding of one plan over several ranks (see MlpSharding in mlp_plan.h)
 // ---------------------------------------------------------------------
-void mlp_build_sharding(const MlpPlan& plan, int nranks, int rank, MlpSharding* out)
+void mlp_build_sharding(const MlpPlan& plan, int nranks, int rank, MlpSharding* out, double own_items)
 {
     const int n_nodes = (int)plan.nodes.size(), n_sites = (int)plan.sites.size(), n_units = (int)plan.units.size();
     const int Kp = plan.tab.Kp;
@@ -266,37 +274,42 @@ void mlp_build_sharding(const MlpPlan& plan, int nranks, int rank, MlpSharding* 
     for (int n = 0; n < n_nodes; ++n)
         if (is_leaf(n)) leaf_of_unit[plan.nodes[n].unit_begin] = n;
     auto child_node = [&](int32_t code) -> int { return code >= 0 ? code : (code == -1 ? -1 : leaf_of_unit[-2 - code]); };
-    // bottom site: no child call has explicit sites of its own
-    std::vector<int8_t> bottom(n_sites, 1);
+    // Ownership roots: walking down from the root, the first site that is small enough to be one item of the
+    // balance (at most 1/kOwnItems of a rank's share: the longest-first assignment below is then within a
+    // few per cent of even), or below which no call has explicit sites.  Everything under such a site —
+    // deeper explicit sites included — belongs to its owner; the sites above are the upper sites.
+    const double own_cap = plan.tab.W[plan.tab.L] / ((double)nranks * (own_items > 0 ? own_items : kOwnItems));
+    std::vector<int8_t> structural_bottom(n_sites, 1);
     for (int si = 0; si < n_sites; ++si)
         for (int q = 0; q < nch; ++q) {
             const int32_t code = plan.children[plan.sites[si].child0 + q];
-            if (code >= 0 && plan.nodes[code].site_end > plan.nodes[code].site_begin) bottom[si] = 0;
+            if (code >= 0 && plan.nodes[code].site_end > plan.nodes[code].site_begin) structural_bottom[si] = 0;
         }
-    // crown nodes: the root, and every child of an upper site
-    std::vector<int8_t> crown(n_nodes, 0);
-    std::vector<int32_t> owner_site(n_nodes, -1); // for nodes below a bottom site: that site
-    crown[0] = 1;
-    for (int si = 0; si < n_sites; ++si) // sites are created parent-first, so crown[] of the parent is final here
+    std::vector<int32_t> root_of_node(n_nodes, -1); // ownership root above a node; -1: crown node
+    std::vector<int32_t> root_of_site(n_sites, -1); // ownership root of a site (itself for a root); -1: upper site
+    for (int si = 0; si < n_sites; ++si) { // sites are created parent-first: root_of_node[] of the parent call is final here
+        const PlanSite& st = plan.sites[si];
+        const int above = root_of_node[st.node];
+        if (above >= 0) root_of_site[si] = above;
+        else if (structural_bottom[si] || plan.tab.Ws[st.l] <= own_cap) root_of_site[si] = si;
         for (int q = 0; q < nch; ++q) {
-            const int cn = child_node(plan.children[plan.sites[si].child0 + q]);
-            if (cn < 0) continue;
-            if (bottom[si]) owner_site[cn] = si;
-            else crown[cn] = 1;
+            const int cn = child_node(plan.children[st.child0 + q]);
+            if (cn >= 0) root_of_node[cn] = root_of_site[si];
         }
-    // items to balance: bottom sites (with everything below them) and the units attached to crown nodes
-    struct Item { double cost; int kind, id; }; // kind 0: bottom site, 1: crown-attached unit
+    }
+    // items to balance: ownership roots (with everything below them) and the units attached to crown nodes
+    struct Item { double cost; int kind, id; }; // kind 0: ownership root, 1: crown-attached unit
     std::vector<Item> items;
     for (int si = 0; si < n_sites; ++si)
-        if (bottom[si]) items.push_back({plan.tab.Ws[plan.sites[si].l], 0, si});
+        if (root_of_site[si] == si) items.push_back({plan.tab.Ws[plan.sites[si].l], 0, si});
     std::vector<int32_t> node_of_unit(n_units, 0);
     for (int n = 0; n < n_nodes; ++n)
         for (int u = plan.nodes[n].unit_begin; u < plan.nodes[n].unit_end; ++u) node_of_unit[u] = n;
     for (int u = 0; u < n_units; ++u)
-        if (crown[node_of_unit[u]]) items.push_back({(double)plan.unit_cost[u], 1, u});
+        if (root_of_node[node_of_unit[u]] < 0) items.push_back({(double)plan.unit_cost[u], 1, u});
     std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.cost > b.cost; });
     std::vector<double> load(nranks, 0.0);
-    std::vector<int32_t> site_owner(n_sites, -1), unit_owner(n_units, -1);
+    std::vector<int32_t> root_owner(n_sites, -1), unit_owner(n_units, -1);
     int rr = 0;
     for (const Item& it : items) { // longest first, each to the least loaded rank (ties: round robin)
         int best = rr % nranks;
@@ -306,11 +319,11 @@ void mlp_build_sharding(const MlpPlan& plan, int nranks, int rank, MlpSharding* 
         }
         ++rr;
         load[best] += it.cost;
-        if (it.kind == 0) site_owner[it.id] = best;
+        if (it.kind == 0) root_owner[it.id] = best;
         else unit_owner[it.id] = best;
     }
     for (int u = 0; u < n_units; ++u)
-        if (unit_owner[u] < 0) unit_owner[u] = site_owner[owner_site[node_of_unit[u]]];
+        if (unit_owner[u] < 0) unit_owner[u] = root_owner[root_of_node[node_of_unit[u]]];
     out->load_max = *std::max_element(load.begin(), load.end());
     out->load_mean = std::accumulate(load.begin(), load.end(), 0.0) / nranks;
     // per-rank lists
@@ -318,37 +331,44 @@ void mlp_build_sharding(const MlpPlan& plan, int nranks, int rank, MlpSharding* 
     out->exec_own.clear();
     for (int32_t u : plan.exec_order)
         if (unit_owner[u] == rank) { out->exec_own.push_back(u); out->unit_mine[u] = 1; }
-    out->site_cls.assign(n_sites, 0);
-    out->own_bottom_sites.clear();
-    for (int si = 0; si < n_sites; ++si) {
-        out->site_cls[si] = !bottom[si] ? 0 : (site_owner[si] == rank ? 1 : 2);
-        if (bottom[si] && site_owner[si] == rank) out->own_bottom_sites.push_back(si);
-    }
     const int nd = plan.max_depth + 1;
+    out->site_cls.assign(n_sites, 0);
     out->upper_depth_off.assign(nd + 1, 0);
+    out->own_depth_off.assign(nd + 1, 0);
     out->upper_sites.clear();
+    out->own_sites.clear();
     for (int dep = 0; dep < nd; ++dep) {
-        for (int q = plan.site_depth_off[dep]; q < plan.site_depth_off[dep + 1]; ++q)
-            if (!bottom[plan.sites_by_depth[q]]) out->upper_sites.push_back(plan.sites_by_depth[q]);
+        for (int q = plan.site_depth_off[dep]; q < plan.site_depth_off[dep + 1]; ++q) {
+            const int si = plan.sites_by_depth[q];
+            const int root = root_of_site[si];
+            out->site_cls[si] = root < 0 ? 0 : (root_owner[root] == rank ? 1 : 2);
+            if (root < 0) out->upper_sites.push_back(si);
+            else if (root_owner[root] == rank) out->own_sites.push_back(si);
+        }
         out->upper_depth_off[dep + 1] = (int32_t)out->upper_sites.size();
+        out->own_depth_off[dep + 1] = (int32_t)out->own_sites.size();
     }
     out->node_slot.assign(n_nodes, -1);
-    out->crown_nodes.clear(); out->crown_leaves.clear(); out->owned_nodes.clear();
+    out->crown_nodes.clear(); out->crown_leaves.clear();
     out->n_slots = 0;
-    std::vector<std::vector<int32_t>> fin(nd);
+    std::vector<std::vector<int32_t>> fin(nd), own(nd);
     for (int n = 0; n < n_nodes; ++n) {
-        if (crown[n]) {
+        if (root_of_node[n] < 0) {
             out->node_slot[n] = out->n_slots++;
             out->crown_nodes.push_back(n);
             if (is_leaf(n)) out->crown_leaves.push_back(n);
             if (!is_leaf(n) || n == 0) fin[plan.nodes[n].depth].push_back(n); // (a root that is one unit still gets its value)
-        } else if (!is_leaf(n) && site_owner[owner_site[n]] == rank) out->owned_nodes.push_back(n);
+        } else if (!is_leaf(n) && root_owner[root_of_node[n]] == rank) own[plan.nodes[n].depth].push_back(n);
     }
     out->crown_final.clear();
+    out->owned_nodes.clear();
     out->crown_final_off.assign(nd + 1, 0);
+    out->owned_depth_off.assign(nd + 1, 0);
     for (int dep = 0; dep < nd; ++dep) {
         out->crown_final.insert(out->crown_final.end(), fin[dep].begin(), fin[dep].end());
         out->crown_final_off[dep + 1] = (int32_t)out->crown_final.size();
+        out->owned_nodes.insert(out->owned_nodes.end(), own[dep].begin(), own[dep].end());
+        out->owned_depth_off[dep + 1] = (int32_t)out->owned_nodes.size();
     }
 }
 

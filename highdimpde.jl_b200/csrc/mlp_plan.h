@@ -72,35 +72,39 @@ int64_t mlp_get_loop_num(int M, int64_t num, int thread_id, int nthreads);
 // `Threads.@spawn` / `fetch` / `sum` (src/MLP.jl:235-259), cut where a GPU needs it.
 //
 // f is nonlinear, so a site can only be finished where all its child values are complete.  The plan is
-// therefore split into a *crown* — the root, the *upper* sites (those with a child call that itself has
-// explicit sites) and the calls below them — which every rank holds, and the subtrees below the *bottom*
-// sites (all children whole-call leaves or calls made of slice units only), each of which belongs to ONE
-// rank: that rank generates its geometry, evaluates its units, combines its calls and applies f.  What
-// crosses the wire is linear: per crown node, this rank's share of the node's value (its slice units, the
-// f-terms of its bottom sites; the value of a whole-call leaf below an upper site) — one double per crown
-// node and solve, summed by a single ncclAllReduce.  The upper sites are then finished redundantly.
+// therefore split into a *crown* — the root, the *upper* sites and the calls directly below them — which every
+// rank holds, and the subtrees below the *ownership roots*: walking down from the root, the first site whose
+// modelled cost is at most 1/64 of a rank's share (or below which no call has explicit sites).  Each ownership
+// root belongs to ONE rank: that rank generates the geometry of everything below it (deeper explicit sites
+// included), evaluates its units, combines its calls and applies f.  What crosses the wire is linear: per crown
+// node, this rank's share of the node's value (its slice units, the f-terms of its ownership roots; the value of
+// a whole-call leaf below an upper site) — one double per crown node and solve, summed by a single
+// ncclAllReduce.  The upper sites are then finished redundantly.
 struct MlpSharding {
     int nranks = 1, rank = 0;
     std::vector<int32_t> exec_own;            // units this rank evaluates, most expensive first
     std::vector<int32_t> upper_sites;         // replicated sites grouped by depth
     std::vector<int32_t> upper_depth_off;     // size max_depth+2
-    std::vector<int32_t> own_bottom_sites;    // this rank's bottom sites (any depth; one expand launch)
-    std::vector<int32_t> owned_nodes;         // slice-only calls below this rank's bottom sites (combine: CMB_ALL)
+    std::vector<int32_t> own_sites;           // this rank's ownership roots and the explicit sites below them, grouped by depth
+    std::vector<int32_t> own_depth_off;       // size max_depth+2
+    std::vector<int32_t> owned_nodes;         // calls below this rank's ownership roots, grouped by depth (combine: CMB_ALL)
+    std::vector<int32_t> owned_depth_off;     // size max_depth+2
     std::vector<int32_t> crown_nodes;         // every crown node, leaves included (combine: CMB_PARTIAL)
     std::vector<int32_t> crown_leaves;        // whole-call leaves below upper sites (scatter after the all-reduce)
     std::vector<int32_t> crown_final;         // crown nodes that are not leaves, grouped by depth (combine: CMB_FINAL)
     std::vector<int32_t> crown_final_off;     // size max_depth+2
     std::vector<int8_t> unit_mine;            // per unit
-    std::vector<int8_t> site_cls;             // per site: 0 upper, 1 bottom and mine, 2 bottom of another rank
-    std::vector<int32_t> node_slot;           // per node: slot in the exchange buffer, -1 below a bottom site
+    std::vector<int8_t> site_cls;             // per site: 0 upper, 1 at or below an ownership root of mine, 2 of another rank
+    std::vector<int32_t> node_slot;           // per node: slot in the exchange buffer, -1 below an ownership root
     int n_slots = 0;
     double load_max = 0, load_mean = 0;       // modelled work of the busiest rank / the mean
     // device copies (owned by the handle's cache; freed in the destructor)
-    void *d_exec_own = nullptr, *d_upper_sites = nullptr, *d_own_bottom_sites = nullptr, *d_owned_nodes = nullptr,
+    void *d_exec_own = nullptr, *d_upper_sites = nullptr, *d_own_sites = nullptr, *d_owned_nodes = nullptr,
          *d_crown_nodes = nullptr, *d_crown_leaves = nullptr, *d_crown_final = nullptr, *d_unit_mine = nullptr,
          *d_site_cls = nullptr, *d_node_slot = nullptr;
     ~MlpSharding();
 };
-void mlp_build_sharding(const MlpPlan& plan, int nranks, int rank, MlpSharding* out);
+// own_items: ownership roots per rank to aim for (0: the default, 64; tests lower it to nest explicit sites below a root)
+void mlp_build_sharding(const MlpPlan& plan, int nranks, int rank, MlpSharding* out, double own_items = 0);
 
 } // namespace hdp

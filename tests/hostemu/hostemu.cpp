@@ -20,6 +20,10 @@ MlpPlan::~MlpPlan() {} // no device copies in the emulation
 namespace hdp {
 MlpSharding::~MlpSharding() {}
 }
+// ownership roots per rank the emulated shardings aim for (0: the library's default); tests lower it so that
+// explicit sites nest below an ownership root on small trees
+static double g_own_items = 0;
+extern "C" void hdp_emu_set_own_items(double v) { g_own_items = v; }
 
 // nranks > 1 emulates a solve sharded over several GPUs (MlpSharding).  In one process the ranks run one after
 // the other on private copies of the per-call state, their exchange buffers are summed as the all-reduce would,
@@ -106,7 +110,7 @@ template <typename T> struct EmuSolve {
             S.scratch_raw.resize((size_t)(2 * L) * P.npl * VEC * sizeof(T) / sizeof(double2) + 2); // 16-byte aligned
             S.points_raw.resize(((size_t)n_solves * P.n_points * P.dpad * sizeof(T)) / sizeof(double2) + 2);
             if (nranks > 1) {
-                mlp_build_sharding(plan, nranks, r, &S.sh);
+                mlp_build_sharding(plan, nranks, r, &S.sh, g_own_items);
                 xstride = S.sh.n_slots + 3 * (kMaxL + 1);
                 S.xbuf.assign((size_t)n_solves * xstride + kXTail, 0.0);
             }
@@ -135,7 +139,7 @@ template <typename T> struct EmuSolve {
     }
     void expand_list(const int32_t* list, int cnt, bool hits)
     {
-        for (u64 it = 0; it < (u64)cnt * n_solves; ++it) { c.nb = 0; expand_item<T, G>(c, P, list, it, hits); }
+        for (u64 it = 0; it < (u64)cnt * n_solves * (u64)(1 + P.Kp); ++it) { c.nb = 0; expand_item<T, G>(c, P, list, it, hits); }
     }
     void combine_list(const int32_t* list, int cnt, int mode)
     {
@@ -155,7 +159,8 @@ template <typename T> struct EmuSolve {
             for (int dep = 0; dep <= plan.max_depth; ++dep)
                 expand_list(S.sh.upper_sites.data() + S.sh.upper_depth_off[dep],
                             S.sh.upper_depth_off[dep + 1] - S.sh.upper_depth_off[dep], r == 0);
-            expand_list(S.sh.own_bottom_sites.data(), (int)S.sh.own_bottom_sites.size(), true);
+            for (int dep = 0; dep <= plan.max_depth; ++dep)
+                expand_list(S.sh.own_sites.data() + S.sh.own_depth_off[dep], S.sh.own_depth_off[dep + 1] - S.sh.own_depth_off[dep], true);
         }
         for (u64 w = 0; w < (u64)P.n_exec * n_solves; ++w) unit_item<T, G>(c, P, w);
         if (c.bad) S.flags[0] = 1;
@@ -163,7 +168,9 @@ template <typename T> struct EmuSolve {
             for (int dep = plan.max_depth; dep >= 0; --dep)
                 combine_list(P.nodes_by_depth + plan.node_depth_off[dep], plan.node_depth_off[dep + 1] - plan.node_depth_off[dep], CMB_ALL);
         } else {
-            combine_list(S.sh.owned_nodes.data(), (int)S.sh.owned_nodes.size(), CMB_ALL);
+            for (int dep = plan.max_depth; dep >= 0; --dep)
+                combine_list(S.sh.owned_nodes.data() + S.sh.owned_depth_off[dep],
+                             S.sh.owned_depth_off[dep + 1] - S.sh.owned_depth_off[dep], CMB_ALL);
             combine_list(S.sh.crown_nodes.data(), (int)S.sh.crown_nodes.size(), CMB_PARTIAL);
             S.xbuf[(size_t)n_solves * xstride + 4] = (double)S.ctr[1];
             S.xbuf[(size_t)n_solves * xstride + 5] = (double)S.flags[0]; // (the library reads its flag per rank; here it rides along)
@@ -269,14 +276,14 @@ extern "C" int hdp_emu_mlp_solve_sharded_f32(const hdp_problem* prob, const hdp_
 {
     return emu_solve<float>(prob, cfg, x0, u_out, stats, nranks);
 }
-// the sharding of a plan, summarised: [n_slots, crown nodes, crown leaves, upper sites, bottom sites (all ranks),
+// the sharding of a plan, summarised: [n_slots, crown nodes, crown leaves, upper sites, sites at or below an ownership root (all ranks),
 // owned nodes (this rank), units (this rank), 1000 * busiest rank's modelled load / mean load]
 extern "C" void hdp_emu_sharding_summary(int M, int L, int K, int nonlocal, double thresh, int nranks, int rank, int64_t out[8])
 {
     MlpPlan plan;
     mlp_build_plan(M, L, K, nonlocal != 0, thresh, 0, &plan);
     MlpSharding sh;
-    mlp_build_sharding(plan, nranks, rank, &sh);
+    mlp_build_sharding(plan, nranks, rank, &sh, g_own_items);
     int64_t bottoms = 0;
     for (int8_t c : sh.site_cls) bottoms += c != 0;
     out[0] = sh.n_slots; out[1] = (int64_t)sh.crown_nodes.size(); out[2] = (int64_t)sh.crown_leaves.size();

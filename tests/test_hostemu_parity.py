@@ -3,6 +3,8 @@ mlp_plan.cu are compiled for the host (tests/hostemu, single-lane group) and com
 with the oracle on identical injected tapes.  This validates, without a GPU, the
 consumption-ordinal arithmetic ("bit-exact indexing"), the tree cut at any threshold,
 the bottom-up combine, the kinds, and the per-coordinate reflection."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -174,7 +176,7 @@ def test_sharding_exchanges_one_double_per_crown_node(H, emu):
     import ctypes as C
     out = (C.c_int64 * 8)()
     plan = (C.c_int64 * 8)()
-    for thresh in (400.0, 90.0):
+    for thresh in (400.0, 90.0, 45.0):   # (45: the level-1 sites explicit, 5.6 M units)
         emu.hdp_emu_plan_summary(4, 5, 10, 1, C.c_double(thresh), 0, plan)
         n_units = plan[2]
         units = 0
@@ -266,3 +268,40 @@ def test_fast_loops_match_the_oracle_on_the_same_philox_draws(H, O, emu, name):
             assert rel_err(float(u[0]), uo) <= tol, (name, seed, target, nranks, float(u[0]), uo)
             if dt == np.float64 and name != "wild_sym_d2":
                 assert st.bounces == info["bounces"], (name, seed, target, nranks)
+
+
+# ---------------------------------------------------------------------------------------------
+# long non-local sites made explicit (whole-call children), ownership roots with explicit sites below them
+# ---------------------------------------------------------------------------------------------
+def test_long_sites_and_nested_ownership_match_the_oracle(H, O, emu):
+    """thresh between W[1] and Ws[1] / 4: a level-1 site of a non-local problem (1 + K child calls) is far longer than a
+    unit although each child call fits one — the planner makes such sites explicit, their children whole-call units.
+    Sharded, with few ownership roots per rank asked for, the level-2 sites become the roots and the explicit level-1
+    sites nest below them: geometry and combine of the owner run depth by depth.  Same tapes, every cut and rank count:
+    the oracle's value, and its wall-hit count."""
+    prob = H.PIDEProblem(0.0, 0.4, np.zeros(2), (0.0, 0.5), H.ExpSumSq(0.25), H.FNLFisher(), neumann_bc=(-0.5, 0.5))
+    alg = H.MLP(M=3, L=3, K=8, mc_sample=H.UniformSampling(-0.5, 0.5))
+    dt = np.float64
+    tapes = random_tapes(H, prob, alg, dt, seed=5)
+    uo, info = oracle_solve(H, O, prob, alg, dt, tapes)
+    plan = (C.c_int64 * 8)()
+    # W[1] = 18, Ws[1] = 167 (M = 3, K = 8): a 29-unit cut target keeps whole U_1 calls and splits the sites
+    emu.hdp_emu_plan_summary(3, 3, 8, 1, C.c_double(20.0), 0, plan)
+    n_units, n_sites = plan[2], plan[1]
+    assert n_sites >= 9 * 3 and n_units > 5 * n_sites, list(plan)   # level-1 sites explicit, 1 + K whole calls each
+    target = int(alg_work(H, alg) / 20.0)
+    try:
+        for own_items, nranks in ((0, 1), (0, 2), (0, 3), (1.0, 2), (0.5, 3), (2.0, 8)):
+            emu.hdp_emu_set_own_items(C.c_double(own_items))
+            u, rc, st = emu_solve(H, emu, prob, alg, dt, tapes=tapes, target_units=target, nranks=nranks)
+            assert rc == 0
+            assert rel_err(float(u[0]), uo) <= 1e-12, (own_items, nranks, float(u[0]), uo)
+            assert st.bounces == info["bounces"], (own_items, nranks)
+            assert st.n_sites == n_sites
+    finally:
+        emu.hdp_emu_set_own_items(C.c_double(0.0))
+
+
+def alg_work(H, alg):
+    cn = H.mlp_counts(alg.M, alg.L, alg.K, nonlocal_=True)
+    return cn["path_steps"] + 0.5 * cn["sampler_calls"]
