@@ -201,19 +201,20 @@ __device__ __forceinline__ float cos_approx(float x)
 // f64: 52-bit uniforms.  Words (w_hi, w_lo) -> k = (w_hi >> 12) : w_lo in [0, 2^52);
 //      the double with exponent field 0x3ff and mantissa k is 1 + k*2^-52, so
 //      u = that - 1 in [0,1)                       (one exact DADD, no I2F)
-//      u1 = that - (1 - 2^-53) = (k + 1/2)*2^-52 in (0,1)   (Box–Muller radius)
+//      u1 = (k | 1)*2^-52 in (0,1)                 (Box–Muller radius; k | 1 converted by one I2F.F64.U64)
 // Box–Muller: z0 = R cos(T), z1 = R sin(T), R = sqrt(-2 ln u1), T = 2π k2 / 2^52.
-//   Both transcendentals are table driven; the tables (6 KB, hdp_tables.h) are staged in
+//   Both transcendentals are table driven; the tables (12 KB, hdp_tables.h) are staged in
 //   shared memory by tables_init() at kernel start.
-//   -2 ln u1: u1 = 2^e * m, m in [1,2).  idx = m rounded to 7 fraction bits (0..128) selects
-//      rc ≈ 1/(1 + idx/128) and lm2 = -2 ln(1/rc) (shifted by ln 2 for idx >= 54, so the
+//   -2 ln u1: u1 = 2^e * m, m in [1,2).  idx = m rounded to 8 fraction bits (0..256) selects
+//      rc ≈ 1/(1 + idx/256) and lm2 = -2 ln(1/rc) (shifted by ln 2 for idx >= 107, so the
 //      entries next to u1 = 1 are exactly zero and nothing cancels there); r = fma(m, rc, -1),
-//      |r| <= 2^-8, log1p(r) by its degree-7 Taylor polynomial.  No special cases: u1 is a
+//      |r| <= 2^-9, log1p(r) by its degree-6 Taylor polynomial.  No special cases: u1 is a
 //      normal number in (0,1).  Agrees with glibc's log to 2 ulp.
-//   sqrt: MUFU.RSQ64H seed + 1 Newton step + Heron correction.
-//   sin/cos: the top 8 bits of k2 select (sin, cos) at the centre of a 1/256 turn, the other
-//      44 bits give the offset |δ| <= π/256 exactly; sin δ, cos δ − 1 by degree-5/6 Taylor
-//      polynomials and the angle-sum formulas.  No octant logic.
+//   sqrt: MUFU.RSQ64H seed + 1 Goldschmidt step + Heron correction.
+//   sin/cos: the top 9 bits of k2 select (sin, cos) at the centre of a 1/512 turn, the other
+//      43 bits give the offset |δ| <= π/512 exactly; sin δ by its degree-5, cos δ − 1 by its degree-4
+//      Taylor polynomial, and the angle-sum formulas.  No octant logic.
+//   32 fp64 instructions and two I2F per pair of normals (round 1: 38).
 // f32: 23-bit uniforms by the same trick; Box–Muller on the MUFU pipe.
 // ---------------------------------------------------------------------
 #ifndef HDP_HOST_EMU
@@ -230,10 +231,7 @@ __device__ __forceinline__ float cos_approx(float x)
 // encode as 32-bit immediates of DFMA.
 #define HDP_C5T 0x1.9999ap-3    /* 1/5   */
 #define HDP_C6T 0x1.55555p-3    /* 1/6   */
-#define HDP_C7T 0x1.24925p-3    /* 1/7   */
 #define HDP_C120T 0x1.11111p-7  /* 1/120 */
-#define HDP_C720T 0x1.6c16cp-10 /* 1/720 */
-#define HDP_TWO_LN2_LOT 0x1.abc9ep-55
 
 template <typename T> struct DrawK {};
 template <> struct DrawK<double> {
@@ -242,13 +240,13 @@ template <> struct DrawK<double> {
 };
 
 #ifndef HDP_HOST_EMU
-__shared__ double2 s_log_tab[129];
-__shared__ double2 s_sincos_tab[256];
+__shared__ double2 s_log_tab[HDP_LOG_N + 1];
+__shared__ double2 s_sincos_tab[HDP_SINCOS_N];
 // every kernel that draws fp64 normals calls this first, with all threads of the block
 __device__ __forceinline__ void tables_init()
 {
-    for (int i = threadIdx.x; i < 129; i += blockDim.x) s_log_tab[i] = make_double2(kLogTab[i][0], kLogTab[i][1]);
-    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+    for (int i = threadIdx.x; i < HDP_LOG_N + 1; i += blockDim.x) s_log_tab[i] = make_double2(kLogTab[i][0], kLogTab[i][1]);
+    for (int i = threadIdx.x; i < HDP_SINCOS_N; i += blockDim.x)
         s_sincos_tab[i] = make_double2(kSinCosTab[i][0], kSinCosTab[i][1]);
     __syncthreads();
 }
@@ -295,59 +293,79 @@ template <typename T> static inline DrawK<T> draw_k_init(int)
 }
 #endif
 
-// -2 ln(u) for a normal double u in (0,1)
-__device__ __forceinline__ double neg2log_unit(double u, const DrawK<double>& k)
+// -2 ln(u1) for u1 = k 2^-52, k = (kh : kl) an integer in [1, 2^52)
+// (k is converted exactly by one I2F.F64.U64 — the conversion pipe, one dispatch cycle — and only the mantissa
+// and the exponent of the result are used, so the scaling by 2^-52 is a constant in the exponent arithmetic;
+// building u1 = (1 + k 2^-52) - (1 - 2^-53) from the bits took an OR and a DADD)
+__device__ __forceinline__ double neg2log_k52(uint32_t kh, uint32_t kl, const DrawK<double>& k)
 {
+#ifndef HDP_GEN_I2F
+#define HDP_GEN_I2F 1 // 0: the bit-built conversions (A/B: profiles/r2t_generator_ab.txt)
+#endif
+#if HDP_GEN_I2F
+    const double u = (double)(((u64)kh << 32) | (u64)kl); // k, exactly
+#else
+    const double u = (hilo2d(0x3ff00000u | kh, kl) - 1.0) * 0x1p+52;
+#endif
     const uint32_t hi = d2hi(u), lo = d2lo(u);
     const uint32_t mh = (hi & 0x000fffffu) | 0x3ff00000u;   // m = 1.f in [1,2)
-    const uint32_t idx = (mh - 0x3feff800u) >> 13;          // f rounded to 7 bits: 0..128
+    static_assert(HDP_LOG_N == 256 && HDP_SINCOS_N == 512, "the index arithmetic below is written for these table sizes");
+    const uint32_t idx = (mh - 0x3feff800u) >> 12;          // f rounded to 8 bits (to nearest): 0..256
     double rc, lm2;
     tab_entry(k.log_tab, idx, rc, lm2);
-    const double r = xfma(hilo2d(mh, lo), rc, -1.0);        // |r| <= 2^-8
-    // ne = -(e + [idx >= HDP_LOG_SPLIT]) >= 0 as a double without I2F: (2^52 + ne) - 2^52
-    const uint32_t ne = 1023u - (hi >> 20) - ((idx + (128u - HDP_LOG_SPLIT)) >> 7);
+    const double r = xfma(hilo2d(mh, lo), rc, -1.0);        // |r| <= 2^-9
+    // ne = -(e + [idx >= HDP_LOG_SPLIT]) >= 0
+    const uint32_t ne = (1023u + 52u) - (hi >> 20) - ((idx + (256u - HDP_LOG_SPLIT)) >> 8);
+#if HDP_GEN_I2F
+    const double ned = (double)ne; // I2F.F64.U32 on the conversion pipe: one dispatch cycle, where (2^52 + ne) - 2^52 was a DADD
+#else
     const double ned = hilo2d(0x43300000u, ne) - 0x1p+52;
+#endif
     // the large terms first (off the critical path: they do not need the polynomial)
-    double big = xfma(ned, k.two_ln2, lm2);
-    big = xfma(ned, HDP_TWO_LN2_LOT, big);
-    // log1p(r) = r + r^2 q(r), q = (-1/2 + r/3) + r^2 ((-1/4 + r/5) + r^2 (-1/6 + r/7)): three independent
-    // first-level terms, dependent depth 4 instead of Horner's 7
+    // (the low part of 2 ln 2, 2^-54, times ne <= 52 is at most 0.3 ulp of the result anywhere: not worth an fp64 issue slot)
+    const double big = xfma(ned, k.two_ln2, lm2);
+    // log1p(r) = r + r^2 q(r), q = (-1/2 + r/3) + r^2 ((-1/4 + r/5) - r^2/6); the next term, r^7/7, is below
+    // 2^-56 of the result for |r| <= 2^-9.  Two independent first-level terms: dependent depth 4.
     const double r2 = r * r;
     const double qa = xfma(r, k.c3, -0.5);
     const double qb = xfma(r, HDP_C5T, -0.25);
-    const double qc = xfma(r, HDP_C7T, -HDP_C6T);
-    const double q = xfma(r2, xfma(r2, qc, qb), qa);
+    const double q = xfma(r2, xfma(r2, -HDP_C6T, qb), qa);
     const double p = xfma(r2, q, r);
     return xfma(p, -2.0, big);
 }
 
-// sqrt of a positive normal double: MUFU.RSQ64H seed (≈2^-22), one coupled Goldschmidt step on
-// (g ≈ sqrt x, h ≈ 1/(2 sqrt x)) and a Heron correction; 7 operations, dependent depth 5
+// sqrt of a positive normal double: MUFU.RSQ64H seed (≈2^-22), one Goldschmidt step on g ≈ sqrt x with
+// h ≈ 1/(2 sqrt x) and a Heron correction; 6 operations, dependent depth 5; within 1 ulp of sqrt
 __device__ __forceinline__ double sqrt_pos(double x)
 {
     const double y = rsqrt_approx(x);
-    const double g = x * y, h = 0.5 * y;
+    const double g = x * y;
+    // h = y / 2 by one integer subtraction from the exponent field (y is a normal number in [0.1, 2^27]: x is
+    // -2 ln u1 in [2^-52, 73]): an ALU instruction holds the dispatch port for one cycle, a DMUL for two
+    const double h = hilo2d(d2hi(y) - 0x00100000u, d2lo(y));
     const double r = xfma(-g, h, 0.5);
-    const double g1 = xfma(g, r, g), h1 = xfma(h, r, h);
-    const double e = xfma(-g1, g1, x);
-    return xfma(e, h1, g1);
+    const double g1 = xfma(g, r, g);       // relative error 2^-43
+    const double e = xfma(-g1, g1, x);     // exact residual
+    return xfma(e, h, g1);                 // h is good to 2^-22: the correction term is off by 2^-65 of the result
+                                           // (refining h as well, as a full Goldschmidt step would, buys nothing)
 }
 
 // (sin, cos) of 2π k / 2^52 for the 52-bit integer k = (kh : kl), kh < 2^20
 __device__ __forceinline__ void sincos_turn52(uint32_t kh, uint32_t kl, double& sn, double& cs, const DrawK<double>& k)
 {
     double sj, cj;
-    tab_entry(k.sincos_tab, kh >> 12, sj, cj);
-    // offset from the centre of the 1/256 turn: (f - 2^43) * 2π/2^52, f = low 44 bits of k
-    const double dl = (hilo2d(0x43300000u | (kh & 0xfffu), kl) - 0x1.008p+52 /* 2^52 + 2^43 */) * k.turn;
+    tab_entry(k.sincos_tab, kh >> 11, sj, cj);
+    // offset from the centre of the 1/512 turn: (f - 2^42) * 2π/2^52, f = low 43 bits of k
+    const double dl = (hilo2d(0x43300000u | (kh & 0x7ffu), kl) - 0x1.004p+52 /* 2^52 + 2^42 */) * k.turn;
     const double t = dl * dl;
     const double ps = xfma(t, HDP_C120T, -k.c6);
     const double sd = xfma(dl * t, ps, dl);                 // sin δ
-    double pc = xfma(t, -HDP_C720T, k.c24);
-    pc = xfma(t, pc, -0.5);
+    const double pc = xfma(t, k.c24, -0.5);                 // (δ^6/720 <= 7e-17 for |δ| <= π/512)
     const double cd1 = t * pc;                              // cos δ − 1
-    sn = sj + xfma(cj, sd, sj * cd1);
-    cs = cj + xfma(-sj, sd, cj * cd1);
+    // sin(a + δ) = sj + (cj sin δ + sj (cos δ - 1)) as two chained fmas (one rounding more than summing the two
+    // corrections first, one fp64 instruction less per output: <= 1 ulp)
+    sn = xfma(sj, cd1, xfma(cj, sd, sj));
+    cs = xfma(cj, cd1, xfma(-sj, sd, cj));
 }
 
 template <typename T>
@@ -366,8 +384,7 @@ template <> __device__ __forceinline__ Vec<double> normals_from_words<double>(co
 {
     Vec<double> r;
     const uint32_t h1 = p.w[0] >> 12, h2 = p.w[2] >> 12;
-    const double u1 = hilo2d(0x3ff00000u | h1, p.w[1] | 1u) - 1.0; // (k1 | 1) 2^-52 in (0,1)
-    const double rad = sqrt_pos(neg2log_unit(u1, k));
+    const double rad = sqrt_pos(neg2log_k52(h1, p.w[1] | 1u, k)); // u1 = (k1 | 1) 2^-52 in (0,1)
     double sn, cs;
     sincos_turn52(h2, p.w[3], sn, cs, k);
     r.v[0] = rad * cs;

@@ -527,9 +527,8 @@ __device__ __forceinline__ Feat<T> sample_step(Ctx<T, G>& c, const XAcc<T>* dst,
 // ---------------------------------------------------------------------
 template <typename T> struct Frame {
     T s, r, a, b, b3, b2, b4, f2, f3, term;
-    double sq; // sum of squares of the samples of the current level (only tracked for the root call of a solve)
     u64 k, num, gnum, co, ro, so, cc, rr, qq;
-    int lv, l, lend, h, phase, xslot, parent, pad_[sizeof(T) == 8 ? 3 : 1];
+    int lv, l, lend, h, phase, xslot, parent, pad_[sizeof(T) == 8 ? 1 : 3];
 };
 // one frame per thread, side by side in shared memory: an odd number of 8-byte words per frame keeps a
 // warp's accesses to one field on 16 distinct bank pairs (two wavefronts for a 64-bit field: the minimum)
@@ -574,6 +573,9 @@ __device__ __forceinline__ T run_unit_iter(Ctx<T, G>& c, const MlpParams<T>& P, 
     Frame<T>* const F = static_cast<Frame<T>*>(c.frame_mem);
 #endif
     int cur, root;
+    // sum of squares of the samples of the current level of the unit's root call (the error bar, cfg->std_err_out):
+    // one per unit, so it need not travel with the frames
+    double root_sq = 0.0;
     {
         const u64 n = (u64)(u.k1 - u.k0);
         root = kind == UNIT_WHOLE ? nd.lv : (kind == UNIT_G ? 1 : u.l + 1);
@@ -584,7 +586,6 @@ __device__ __forceinline__ T run_unit_iter(Ctx<T, G>& c, const MlpParams<T>& P, 
         F->num = kind == UNIT_LEVEL ? n : P.Mpow[root];
         F->gnum = kind == UNIT_G ? n : P.Mpow[root];
         F->a = (T)0; F->b = (T)0;
-        F->sq = 0.0;
         F->s = s0;
         F->xslot = -1;
         F->co = u.c; F->ro = u.r; F->so = u.s;
@@ -670,7 +671,7 @@ __device__ __forceinline__ T run_unit_iter(Ctx<T, G>& c, const MlpParams<T>& P, 
         if (st == ST_G_POST) {
             const T gv = g_eval<T>(pb, feat);
             F->b += gv; // :203
-            if (rsq && cur == root) F->sq += (double)gv * (double)gv;
+            if (rsq && cur == root) root_sq += (double)gv * (double)gv;
             F->k += 1;
             st = ST_G;
         }
@@ -694,7 +695,7 @@ __device__ __forceinline__ T run_unit_iter(Ctx<T, G>& c, const MlpParams<T>& P, 
         if (st == ST_SITE_END) {
             const T sv = F->b3 / (T)K;
             F->b += sv; // :148
-            if (rsq && cur == root) F->sq += (double)sv * (double)sv;
+            if (rsq && cur == root) root_sq += (double)sv * (double)sv;
             F->k += 1;
             F->co += P.cs[l]; F->ro += P.rs[l]; F->so += P.ss[l];
             st = ST_LEVEL;
@@ -705,8 +706,8 @@ __device__ __forceinline__ T run_unit_iter(Ctx<T, G>& c, const MlpParams<T>& P, 
                 if (F->k < F->num) { st = ST_SITE; break; }
                 if (cur == root && kind == UNIT_LEVEL) break; // the slice is done: result = b
                 if (rsq && cur == root) { // a whole solve: one pair per level
-                    if (lane == 0) { rsq[2 * l] = (double)F->b; rsq[2 * l + 1] = F->sq; }
-                    F->sq = 0.0;
+                    if (lane == 0) { rsq[2 * l] = (double)F->b; rsq[2 * l + 1] = root_sq; }
+                    root_sq = 0.0;
                 }
                 F->a += ((t1 - F->s) * F->b) / (T)F->num; // :150, :195
                 l += 1;
@@ -715,7 +716,7 @@ __device__ __forceinline__ T run_unit_iter(Ctx<T, G>& c, const MlpParams<T>& P, 
             }
             if (st == ST_LEVEL) {
                 result = F->b;
-                if (rsq && lane == 0) { rsq[0] = (double)result; rsq[1] = F->sq; }
+                if (rsq && lane == 0) { rsq[0] = (double)result; rsq[1] = root_sq; }
                 break;
             }
         }
@@ -733,10 +734,10 @@ __device__ __forceinline__ T run_unit_iter(Ctx<T, G>& c, const MlpParams<T>& P, 
             } else {
                 if (cur == root && kind == UNIT_G) {
                     result = F->b;
-                    if (rsq && lane == 0) { rsq[0] = (double)result; rsq[1] = F->sq; }
+                    if (rsq && lane == 0) { rsq[0] = (double)result; rsq[1] = root_sq; }
                     break;
                 }
-                if (rsq && cur == root && lane == 0) { rsq[2 * P.L] = (double)F->b; rsq[2 * P.L + 1] = F->sq; }
+                if (rsq && cur == root && lane == 0) { rsq[2 * P.L] = (double)F->b; rsq[2 * P.L + 1] = root_sq; }
                 ret = F->a + F->b / (T)F->gnum; // :205, :207
                 st = ST_RETURN;
             }
@@ -1149,11 +1150,16 @@ __global__ void __launch_bounds__(128) mlp_expand_kernel(const __grid_constant__
     if constexpr (sizeof(T) == 8) tables_init();
     Ctx<T, G> c;
     ctx_init<T, G>(c, P, (u64)blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31);
-    const u64 gid = c.tid / G;
     const u64 per = (u64)P.n_solves * (u64)(1 + P.Kp);
-    const u64 n1 = (u64)count * per;
-    if (gid < n1) expand_item<T, G>(c, P, list, gid, count_hits != 0);
-    else if (gid < n1 + (u64)count2 * per) expand_item<T, G>(c, P, list2, gid - n1, count_hits2 != 0);
+    const u64 n1 = (u64)count * per, n12 = n1 + (u64)count2 * per;
+    // grid-stride: a large pass runs on a resident grid, so that staging the generator tables (6 KB per block)
+    // is paid once per resident block and not once per 128 items
+    const u64 stride = (u64)gridDim.x * blockDim.x / G;
+    for (u64 gid = c.tid / G; gid < n12; gid += stride) {
+        c.nb = 0;
+        if (gid < n1) expand_item<T, G>(c, P, list, gid, count_hits != 0);
+        else expand_item<T, G>(c, P, list2, gid - n1, count_hits2 != 0);
+    }
 }
 
 // the work units: dynamic fetch, one warp takes 32/G consecutive work items at a time

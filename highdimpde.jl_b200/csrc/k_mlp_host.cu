@@ -473,7 +473,7 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
                              int count_hits2 = 0) -> int {
         if (cnt + cnt2 == 0) return HDP_OK;
         uint64_t groups = (uint64_t)(cnt + cnt2) * n_solves * (uint64_t)(1 + tab.Kp); // one lane group per (site, solve, point)
-        int ge = (int)((groups * G + block - 1) / block);
+        int ge = (int)std::min<uint64_t>((groups * G + block - 1) / block, (uint64_t)sms * 12);
         if (um) {
             void* args[7] = {(void*)&P, (void*)&list, (void*)&cnt, (void*)&count_hits, (void*)&list2, (void*)&cnt2, (void*)&count_hits2};
             HDP_CUDA(h, cudaLaunchKernel((const void*)um->expand, dim3(ge), dim3(block), args, 0, h->stream));
@@ -485,7 +485,7 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
     // lanes per (node, solve) of a combine launch: a warp where some node has many children, 4 lanes otherwise
     auto launch_combine = [&](const int32_t* list, const int32_t* host_list, int cnt, int cmode) -> int {
         if (cnt == 0) return HDP_OK;
-        int most = 0, most_units = 0;
+        int most = 0, most_units = 0, most_weight = 0;
         for (int q = 0; q < cnt; ++q) most_units = std::max(most_units, plan->nodes[host_list[q]].unit_end - plan->nodes[host_list[q]].unit_begin);
         // nodes with very many units: several blocks each sum a share first (mlp_prereduce_kernel)
         const uint64_t items = (uint64_t)cnt * n_solves;
@@ -504,13 +504,18 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
         for (int q = 0; q < cnt; ++q) {
             const PlanNode& nd = plan->nodes[host_list[q]];
             const int nu = nd.unit_end - nd.unit_begin;
-            most = std::max(most, ((staged && nu > kBigNode) ? kStageBlocks : nu) + (nd.site_end - nd.site_begin));
+            const int nus = (staged && nu > kBigNode) ? kStageBlocks : nu, ns = nd.site_end - nd.site_begin;
+            most = std::max(most, nus + ns);
+            most_weight = std::max(most_weight, nus + ns * (1 + tab.Kp));
         }
         // a handful of children: 4 lanes; many: a warp; thousands (the root of a finely cut tree): a block of 512 —
         // but only where the list is too short to fill the GPU with warps (Allen-Cahn d=100, M=8, L=6: 5264 calls of
         // depth 1 with a few thousand slice units each took 310 us as blocks of 512, a warp each is plenty)
+        // In a short list — the root, alone — lanes are free, and a non-local site costs 1 + K evaluations of f with
+        // their dependent loads: the root of C4 (300 units, 340 explicit sites) walked by one warp, eleven sites
+        // per lane, held the chain for 90 us.
         const bool few = (uint64_t)cnt * n_solves <= 2 * (uint64_t)sms;
-        const int nl = (most > 2048 && few) ? 512 : (most > 16 ? 32 : 4);
+        const int nl = few ? (most_weight > 256 ? 512 : (most_weight > 16 ? 32 : 4)) : (most > 16 ? 32 : 4);
         const int cb = nl > 128 ? nl : 128; // threads per block (one node per block when nl > 32)
         uint64_t tot = (uint64_t)cnt * n_solves * nl;
         int gc = (int)((tot + cb - 1) / cb);
