@@ -62,9 +62,12 @@ int pick_group(int forced, int nvec, double path_steps_total, int n_solves, doub
     };
     // (a handful of solves that are each large — Allen-Cahn d=100, M=8, L=6: 19.5 M path-steps, 257 per resident
     // lane — are in the throughput regime like a batch: 7.85 ms with one lane per point against 9.29 ms with four)
-    const bool few_small = n_solves < 8 && path_steps_total < 64.0 * resident_groups(1);
+    // In between (8..64 path-steps per resident lane: the same solve on 8 GPUs, 2.4 M path-steps per rank) rows of
+    // up to 32 vec-groups per lane: 1.40 ms with two lanes per point, 1.54 with four, 1.66 with one.
+    const double per_lane = path_steps_total / resident_groups(1);
+    const int cap = n_solves >= 8 || per_lane >= 64.0 ? 64 : (per_lane >= 8.0 ? 32 : 16);
     int G = 1;
-    while (G < 32 && (nvec + G - 1) / G > (few_small ? 16 : 64)) G *= 2;
+    while (G < 32 && (nvec + G - 1) / G > cap) G *= 2;
     // (a batch never widens to the point where lanes of a group idle: 2 G <= nvec)
     const int gmax = n_solves < 8 ? nvec : nvec / 2;
     while (G < 32 && G < gmax && path_steps_total < 12.0 * resident_groups(G)) G *= 2;
