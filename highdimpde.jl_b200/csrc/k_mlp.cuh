@@ -283,22 +283,47 @@ __device__ __forceinline__ T em_loop_fast(const MlpParams<T>& P, const DrawK<T>&
         it += UU;
         dp += (size_t)UU * dstride; // (never dereferenced when !store)
     };
-    // second and later wall hits of the flagged vec-groups
+    // second and later wall hits of the flagged vec-groups.  The stash lives in local memory: the entry of the next
+    // flagged vec-group is requested before this one is worked on (waiting for the load at the first compare of
+    // reflect_coord was 7 % of the kernel's stall samples, r2u capture).
     auto finish = [&]() {
-        while (fix) {
+        if (!fix) return;
+        auto lowest = [](unsigned m) {
 #ifdef HDP_HOST_EMU
-            const int j = __builtin_ctz(fix);
+            return __builtin_ctz(m);
 #else
-            const int j = __ffs((int)fix) - 1;
+            return __ffs((int)m) - 1;
 #endif
+        };
+        if constexpr (U == 1) { // short rows (d = 10): one or two flagged vec-groups at most, the plain loop is faster (A/B: r2v)
+            while (fix) {
+                const int j = lowest(fix);
+                fix &= fix - 1;
+                Vec<T> o = stash[j];
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    if ((p0 + j * G) * VEC + e < d) o.v[e] = reflect_coord<T>(o.v[e], lo_s, hi_s, nb);
+                    ssq = xfma(o.v[e], o.v[e], ssq);
+                }
+                if (store) stv<T>(dp0 + (size_t)j * dstride, o);
+            }
+            return;
+        }
+        int j = lowest(fix);
+        Vec<T> o = stash[j];
+        for (;;) {
             fix &= fix - 1;
-            Vec<T> o = stash[j];
+            const int jn = fix ? lowest(fix) : j;
+            const Vec<T> on = stash[jn];
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
                 if ((p0 + j * G) * VEC + e < d) o.v[e] = reflect_coord<T>(o.v[e], lo_s, hi_s, nb);
                 ssq = xfma(o.v[e], o.v[e], ssq);
             }
             if (store) stv<T>(dp0 + (size_t)j * dstride, o);
+            if (!fix) break;
+            o = on;
+            j = jn;
         }
     };
     const int nrag = (nvec % G) ? (nvec / G) * G : nvec; // vec-groups below this index form rows that every lane owns
