@@ -853,39 +853,44 @@ __device__ __forceinline__ void assert_in_box(Ctx<T, G>& c, const MlpParams<T>& 
 // walked by a single lane group (x2, then K sampled points one after the other) held every launch at 25-30 us
 // for a non-local problem.  A shifted sampler starts from x2: its items recompute x2 (the same bits, stored by
 // all of them) instead of waiting for the first; only point 0 reports r, the feature and the wall hits of x2.
+// (`split` = false: one item per (site, solve), the points one after the other — a pass over tens of thousands of
+// sites fills the GPU either way, and then the shared per-site loads and index arithmetic are paid once, not 1 + K times.)
 template <typename T, int G>
 __device__ __forceinline__ void expand_item(Ctx<T, G>& c, const MlpParams<T>& P, const int32_t* list, u64 item,
-                                            bool count_hits = true)
+                                            bool count_hits = true, bool split = true)
 {
     const int npt = 1 + P.Kp;
-    const int j = (int)(item % (u64)npt);
-    item /= (u64)npt;
+    const int j = split ? (int)(item % (u64)npt) : -1; // -1: every point of the site
+    if (split) item /= (u64)npt;
     const int solve = (int)(item % (u64)P.n_solves);
     const int sidx = list[item / (u64)P.n_solves];
     const PlanSite st = P.sites[sidx];
     const PlanNode nd = P.nodes[st.node];
     c.seed = P.seed0 + (u64)solve;
     const XAcc<T> x2 = c.point(solve, st.x2_point);
-    if (j == 0 || (P.sm.kind == HDP_SAMPLER_NORMAL && P.sm.shifted)) {
+    if (j <= 0 || (P.sm.kind == HDP_SAMPLER_NORMAL && P.sm.shifted)) {
         const T s = nd.time_site < 0 ? P.pb.t0 : P.site_r[(u64)solve * P.n_sites + nd.time_site];
         const XAcc<T> xp = c.point(solve, nd.point);
         const T u = time_uniform<T>(P, c.seed, st.r);
         const T r = add_rn(s, mul_rn(sub_rn(P.pb.t1, s), u));
         const Feat<T> f2 = em_step<T, G>(c, P, xp, x2, s, r, st.c);
-        if (j == 0 && c.lane == 0) {
+        if (j <= 0 && c.lane == 0) {
             P.site_r[(u64)solve * P.n_sites + sidx] = r;
             P.feat[(u64)solve * P.n_points + st.x2_point] = f2.ssq;
         }
-        if (j != 0) c.nb = 0; // (point 0 counts the wall hits of the step)
+        if (j > 0) c.nb = 0; // (point 0 counts the wall hits of the step)
     }
-    if (j > 0) {
-        const int l = st.l, h = j - 1;
+    if (j != 0 && P.Kp > 0) {
+        const int l = st.l;
         const u64 sub = P.S[l] + (l >= 2 ? P.S[l - 1] : 0);
-        const u64 qq = st.s + sub + (u64)h * (1 + sub);
-        const XAcc<T> x3 = c.point(solve, st.x3_point0 + h);
-        const Feat<T> f3 = sample_step<T, G>(c, &x3, x2, qq);
-        if (c.lane == 0) P.feat[(u64)solve * P.n_points + st.x3_point0 + h] = f3.ssq;
-        if (P.pb.has_bc && l >= 1) assert_in_box<T, G>(c, P, x3); // U_l(x3) steps from x3 (a level-0 site never does)
+        const int h0 = j > 0 ? j - 1 : 0, h1 = j > 0 ? j : P.Kp;
+        for (int h = h0; h < h1; ++h) {
+            const u64 qq = st.s + sub + (u64)h * (1 + sub);
+            const XAcc<T> x3 = c.point(solve, st.x3_point0 + h);
+            const Feat<T> f3 = sample_step<T, G>(c, &x3, x2, qq);
+            if (c.lane == 0) P.feat[(u64)solve * P.n_points + st.x3_point0 + h] = f3.ssq;
+            if (P.pb.has_bc && l >= 1) assert_in_box<T, G>(c, P, x3); // U_l(x3) steps from x3 (a level-0 site never does)
+        }
     }
     const int nb = gsumi<G>(c.nb, c.gmask);
     const int bad = gsumi<G>(c.bad, c.gmask);
@@ -948,6 +953,7 @@ __device__ __forceinline__ void unit_item(Ctx<T, G>& c, const MlpParams<T>& P, u
 // is then the block's shared staging area (kCmbStage doubles per warp) for the fixed-order sum over its warps.
 constexpr int kCmbStage = kMaxL + 1 + 3 * (kMaxL + 1);
 constexpr int kBigNode = 4096;   // units of one node above which several blocks share the sum
+constexpr unsigned long long kExpandSplitBelow = 32768; // (sites x solves) of a geometry pass below which its points are spread over lane groups
 constexpr int kStageBlocks = 64; // blocks per such node
 template <typename T>
 __device__ __forceinline__ void combine_item(const MlpParams<T>& P, const int32_t* list, u64 item, int lane, int nl,
@@ -1175,15 +1181,17 @@ __global__ void __launch_bounds__(128) mlp_expand_kernel(const __grid_constant__
     if constexpr (sizeof(T) == 8) tables_init();
     Ctx<T, G> c;
     ctx_init<T, G>(c, P, (u64)blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31);
-    const u64 per = (u64)P.n_solves * (u64)(1 + P.Kp);
+    // a short pass (a link of the launch chain that cannot fill the GPU) takes one lane group per (site, point)
+    const bool split = (u64)(count + count2) * (u64)P.n_solves < kExpandSplitBelow;
+    const u64 per = (u64)P.n_solves * (u64)(split ? 1 + P.Kp : 1);
     const u64 n1 = (u64)count * per, n12 = n1 + (u64)count2 * per;
     // grid-stride: a large pass runs on a resident grid, so that staging the generator tables (6 KB per block)
     // is paid once per resident block and not once per 128 items
     const u64 stride = (u64)gridDim.x * blockDim.x / G;
     for (u64 gid = c.tid / G; gid < n12; gid += stride) {
         c.nb = 0;
-        if (gid < n1) expand_item<T, G>(c, P, list, gid, count_hits != 0);
-        else expand_item<T, G>(c, P, list2, gid - n1, count_hits2 != 0);
+        if (gid < n1) expand_item<T, G>(c, P, list, gid, count_hits != 0, split);
+        else expand_item<T, G>(c, P, list2, gid - n1, count_hits2 != 0, split);
     }
 }
 

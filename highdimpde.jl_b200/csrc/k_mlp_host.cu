@@ -475,7 +475,9 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
     auto launch_expand = [&](const int32_t* list, int cnt, int count_hits, const int32_t* list2 = nullptr, int cnt2 = 0,
                              int count_hits2 = 0) -> int {
         if (cnt + cnt2 == 0) return HDP_OK;
-        uint64_t groups = (uint64_t)(cnt + cnt2) * n_solves * (uint64_t)(1 + tab.Kp); // one lane group per (site, solve, point)
+        const uint64_t site_items = (uint64_t)(cnt + cnt2) * n_solves;
+        // one lane group per (site, solve, point) in a short pass, per (site, solve) in a long one (mlp_expand_kernel)
+        uint64_t groups = site_items * (uint64_t)(site_items < kExpandSplitBelow ? 1 + tab.Kp : 1);
         int ge = (int)std::min<uint64_t>((groups * G + block - 1) / block, (uint64_t)sms * 12);
         if (um) {
             void* args[7] = {(void*)&P, (void*)&list, (void*)&cnt, (void*)&count_hits, (void*)&list2, (void*)&cnt2, (void*)&count_hits2};

@@ -139,7 +139,10 @@ template <typename T> struct EmuSolve {
     }
     void expand_list(const int32_t* list, int cnt, bool hits)
     {
-        for (u64 it = 0; it < (u64)cnt * n_solves * (u64)(1 + P.Kp); ++it) { c.nb = 0; expand_item<T, G>(c, P, list, it, hits); }
+        // both forms of the geometry pass (mlp_expand_kernel picks by the size of the pass): short lists one item per
+        // (site, point), longer ones one item per site
+        const bool split = cnt < 8;
+        for (u64 it = 0; it < (u64)cnt * n_solves * (u64)(split ? 1 + P.Kp : 1); ++it) { c.nb = 0; expand_item<T, G>(c, P, list, it, hits, split); }
     }
     void combine_list(const int32_t* list, int cnt, int mode)
     {

@@ -226,3 +226,54 @@ def test_sde_loop_epochs_equal_separate_calls(H, handle, dtype, d, B):
     handle.sync()
     assert np.array_equal(t1.cpu().numpy(), y1.ravel(order="F")) and np.array_equal(t0.cpu().numpy(), y0.ravel(order="F"))
     assert np.array_equal(tz.cpu().numpy(), z.ravel(order="F"))
+
+
+def test_wide_root_multi_block_combine_and_nonlocal_fine_cut(H, O, handle):
+    """Code paths of the launch chain that only large single solves reach, against the oracle on the solve's own draws:
+    (a) a root with more than 4096 units — its partial sums go through mlp_prereduce_kernel (64 blocks) before the
+    combine, and the error bar with them; (b) a non-local problem cut so finely that level-1 sites become explicit
+    with whole-call children, and its geometry passes run both as one lane group per (site, point) (short passes) and
+    per site (passes of >= 32768 sites).  Every cut must give the oracle's value and wall-hit count."""
+    # (a) Allen-Cahn d=6, M=8, L=5 (1,184,968 path-steps): 32768 level-0 sites, 32768 g-samples and 4096 level-1 sites at
+    # the root — 4096 + 4096 + 4096 units of it at the finest cut (8 path-steps per unit)
+    d = 6
+    prob = H.ParabolicPDEProblem(0.0, 1.0, np.zeros(d), (0.0, 0.5), g=H.ExpSumSq(0.25), f=H.FAllenCahn(1.0),
+                                 neumann_bc=(np.full(d, -0.5), np.full(d, 0.5)))
+    alg = H.MLP(M=8, L=5, K=3)
+    seed = 9
+    uo, info = oracle_solve(H, O, prob, alg, np.float64, _tapes(H, handle, prob, alg, seed))
+    assert info["rc"] == 0
+    ses = []
+    for target in (1, 3000, 10 ** 7):
+        u, st = H._ml_picard_batch(prob, alg, seed=seed, handle=handle, target_units=target, std_err=True)
+        assert rel_err(float(u[0]), uo) <= 1e-12 and st["bounces"] == info["bounces"], (target, float(u[0]), uo)
+        ses.append(float(st["std_err"][0]))
+    assert st["n_units"] > 8192                      # the finest cut: the root alone holds more than 4096 units
+    assert max(ses) - min(ses) <= 1e-9 * max(ses)    # the same error bar through one unit, a warp, and 64 blocks
+
+    # (b) non-local Fisher-KPP d=4, M=3, L=4, K=8 (174,594 path-steps, 709,872 sampler calls per solve), 16 solves per
+    # call so that the deepest geometry pass of the fine cut (2874 sites x 16) takes the per-site form
+    d = 4
+    prob = H.PIDEProblem(0.0, 0.3, np.zeros(d), (0.0, 0.5), H.ExpSumSq(1.0), H.FNLFisher(),
+                         neumann_bc=(np.full(d, -0.5), np.full(d, 0.5)))
+    alg = H.MLP(M=3, L=4, K=8, mc_sample=H.UniformSampling(np.full(d, -0.5), np.full(d, 0.5)))
+    cn = H.mlp_counts(alg.M, alg.L, alg.K, True)
+    seed, n = 5, 16
+    want = {}
+    for i in (0, 11):
+        r = handle.tape_fill(np.float64, H.capi.HDP_STREAM_TIME, False, seed + i, 0, cn["time_uniforms"], 1)
+        nn = handle.tape_fill(np.float64, H.capi.HDP_STREAM_STEP, True, seed + i, 0, cn["path_steps"], d)
+        ss = handle.tape_fill(np.float64, H.capi.HDP_STREAM_SAMPLER, False, seed + i, 0, cn["sampler_calls"], d)
+        want[i] = oracle_solve(H, O, prob, alg, np.float64, (r, nn, ss))
+        assert want[i][1]["rc"] == 0
+    work = cn["path_steps"] + 0.5 * cn["sampler_calls"]
+    sites = []
+    for target in (0, int(n * work / 2000.0), int(n * work / 30.0)):   # thresh = W[L], 2000, 30 (W[1] = 18 < 30 < Ws[1] / 4)
+        u, st = H._ml_picard_batch(prob, alg, n_solves=n, seed=seed, handle=handle, target_units=target)
+        for i, (uo, info) in want.items():
+            assert rel_err(float(u[i]), uo) <= 1e-12, (target, i, float(u[i]), uo)
+        sites.append(st["n_sites"])
+        u1, st1 = H._ml_picard_batch(prob, alg, n_solves=1, seed=seed + 11, handle=handle,
+                                     target_units=max(1, target // n))
+        assert rel_err(float(u1[0]), want[11][0]) <= 1e-12 and st1["bounces"] == want[11][1]["bounces"], target
+    assert sites[-1] >= 2000 and sites[-1] * n >= 32768   # the finest cut made the level-1 sites explicit
