@@ -63,7 +63,7 @@ int64_t mlp_get_loop_num(int M, int64_t num, int thread_id, int nthreads)
 }
 
 namespace {
-constexpr double kMinExplicitCall = 64.0, kMinExplicitCallNonlocal = 16.0, kLongSite = 4.0;
+constexpr double kMinExplicitCall = 64.0, kMinExplicitCallNonlocal = 16.0, kLongSite = 6.0;
 constexpr double kOwnItems = 64.0; // ownership roots per rank a sharded solve aims for (at least)
 struct Builder {
     MlpPlan* p;

@@ -268,7 +268,7 @@ def test_wide_root_multi_block_combine_and_nonlocal_fine_cut(H, O, handle):
         assert want[i][1]["rc"] == 0
     work = cn["path_steps"] + 0.5 * cn["sampler_calls"]
     sites = []
-    for target in (0, int(n * work / 2000.0), int(n * work / 30.0)):   # thresh = W[L], 2000, 30 (W[1] = 18 < 30 < Ws[1] / 4)
+    for target in (0, int(n * work / 2000.0), int(n * work / 24.0)):   # thresh = W[L], 2000, 22.6 (W[1] = 18 < 22.6 < Ws[1] / 6)
         u, st = H._ml_picard_batch(prob, alg, n_solves=n, seed=seed, handle=handle, target_units=target)
         for i, (uo, info) in want.items():
             assert rel_err(float(u[i]), uo) <= 1e-12, (target, i, float(u[i]), uo)

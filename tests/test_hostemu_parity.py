@@ -274,7 +274,7 @@ def test_fast_loops_match_the_oracle_on_the_same_philox_draws(H, O, emu, name):
 # long non-local sites made explicit (whole-call children), ownership roots with explicit sites below them
 # ---------------------------------------------------------------------------------------------
 def test_long_sites_and_nested_ownership_match_the_oracle(H, O, emu):
-    """thresh between W[1] and Ws[1] / 4: a level-1 site of a non-local problem (1 + K child calls) is far longer than a
+    """thresh between W[1] and Ws[1] / 6: a level-1 site of a non-local problem (1 + K child calls) is far longer than a
     unit although each child call fits one — the planner makes such sites explicit, their children whole-call units.
     Sharded, with few ownership roots per rank asked for, the level-2 sites become the roots and the explicit level-1
     sites nest below them: geometry and combine of the owner run depth by depth.  Same tapes, every cut and rank count:
