@@ -406,6 +406,7 @@ def bench_strong(torch, dist, H, HD, local_rank, rank, world, reps=5):
                      "std_err": float(stn["std_err"][0]),
                      "units_1gpu": st1["n_units"], "units_sharded": stn["n_units"], "group_1gpu": st1["group_size"],
                      "group_sharded": stn["group_size"], "exchange_bytes": stn["exchange_bytes"],
+                     "exchange": stn["exchange_kind"],
                      "phase_ms_1gpu": st1["phase_ms"], "phase_ms_sharded_rank0": stn["phase_ms"],
                      "launches_sharded": stn["n_launches"]}
     hc.close()

@@ -29,6 +29,7 @@ HDP_ERR_UNSUPPORTED = -8
 HDP_ERR_NVRTC = -9
 
 HDP_MAX_LEVELS = 6
+HDP_PEER_HANDLE_BYTES, HDP_PEER_MAX_RANKS, HDP_PEER_SLOT_DOUBLES = 64, 16, 8192
 HDP_MEM_HOST = 0
 HDP_MEM_DEVICE = 1
 HDP_ASYNC = 2
@@ -90,7 +91,7 @@ class hdp_mlp_stats(C.Structure):
                 ("phase_ms", C.c_double * 4),
                 ("level_n", C.c_uint64 * (HDP_MAX_LEVELS + 1)), ("level_sum", C.c_double * (HDP_MAX_LEVELS + 1)),
                 ("level_sumsq", C.c_double * (HDP_MAX_LEVELS + 1)), ("std_error", C.c_double),
-                ("exchange_bytes", C.c_uint64)]
+                ("exchange_bytes", C.c_uint64), ("exchange_kind", C.c_int32), ("_pad", C.c_int32)]
 
 
 class hdp_devinfo(C.Structure):
@@ -117,6 +118,9 @@ SYMBOLS = {
     "hdp_comm_init_rank": (_i, [_H, C.POINTER(C.c_uint8), _i, _i]),
     "hdp_comm_destroy": (_i, [_H]),
     "hdp_comm_allreduce_f64": (_i, [_H, _VP, C.c_size_t]),
+    "hdp_peer_window_export": (_i, [_H, C.POINTER(C.c_uint8)]),
+    "hdp_peer_window_attach": (_i, [_H, C.POINTER(C.c_uint8), _i, _i]),
+    "hdp_peer_window_detach": (_i, [_H]),
     "hdp_reflect_f64": (_i, [_H, _VP, _VP, _VP, _i, _i, _VP, _VP, _i, _VP, _u]),
     "hdp_reflect_f32": (_i, [_H, _VP, _VP, _VP, _i, _i, _VP, _VP, _i, _VP, _u]),
     "hdp_mc_sample_f64": (_i, [_H, _VP, _VP, _i, _i, _i, _SP, _u64, _VP, _u]),
@@ -243,6 +247,20 @@ class Handle:
 
     def comm_destroy(self):
         check(self.h, self.lib.hdp_comm_destroy(self.h))
+
+    # ---- peer exchange windows (hdp_peer_window_*) ----
+    def peer_window_export(self) -> bytes:
+        buf = (C.c_uint8 * HDP_PEER_HANDLE_BYTES)()
+        check(self.h, self.lib.hdp_peer_window_export(self.h, buf))
+        return bytes(buf)
+
+    def peer_window_attach(self, handles: bytes, nranks: int, rank: int):
+        assert len(handles) == nranks * HDP_PEER_HANDLE_BYTES
+        buf = (C.c_uint8 * len(handles)).from_buffer_copy(handles)
+        check(self.h, self.lib.hdp_peer_window_attach(self.h, buf, nranks, rank))
+
+    def peer_window_detach(self):
+        check(self.h, self.lib.hdp_peer_window_detach(self.h))
 
     def allreduce_f64(self, a: np.ndarray) -> np.ndarray:
         a = np.ascontiguousarray(a, dtype=np.float64)

@@ -104,6 +104,7 @@ extern "C" int hdp_create(hdp_handle* out, int device)
 }
 
 extern "C" int hdp_comm_destroy(hdp_handle h);
+static void peer_close_all(hdp_context* h);
 
 extern "C" int hdp_destroy(hdp_handle h)
 {
@@ -112,6 +113,8 @@ extern "C" int hdp_destroy(hdp_handle h)
         DeviceGuard g(h->device);
         cudaStreamSynchronize(h->stream);
         hdp_comm_destroy(h);
+        peer_close_all(h);
+        if (h->peer_win) cudaFree(h->peer_win);
         h->shardings.clear();
         h->plans.clear();
         for (auto& kv : h->user_modules)
@@ -265,6 +268,84 @@ extern "C" int hdp_comm_destroy(hdp_handle h)
     }
     h->nccl_rank = 0;
     h->nccl_nranks = 1;
+    return HDP_OK;
+}
+
+// ---------------------------------------------------------------------
+// peer exchange windows (include/hdpde.h; the kernel: mlp_exchange_kernel, k_mlp.cuh)
+// ---------------------------------------------------------------------
+static_assert(sizeof(cudaIpcMemHandle_t) == HDP_PEER_HANDLE_BYTES, "IPC handle size");
+static const size_t kPeerWindowBytesHost = (size_t)2 * HDP_PEER_MAX_RANKS * HDP_PEER_SLOT_DOUBLES * sizeof(double) +
+                                           (size_t)2 * HDP_PEER_MAX_RANKS * sizeof(unsigned long long);
+
+static void peer_close_all(hdp_context* h)
+{
+    for (int r = 0; r < HDP_PEER_MAX_RANKS; ++r) {
+        if (h->peer_base[r] && h->peer_base[r] != h->peer_win) cudaIpcCloseMemHandle(h->peer_base[r]);
+        h->peer_base[r] = nullptr;
+    }
+    h->peer_nranks = 0;
+    h->peer_rank = 0;
+    (void)cudaGetLastError();
+}
+
+extern "C" int hdp_peer_window_export(hdp_handle h, uint8_t handle_out[HDP_PEER_HANDLE_BYTES])
+{
+    if (!h || !handle_out) return HDP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    if (h->peer_nranks) return set_err(h, HDP_ERR_BAD_ARG, "peer windows are attached: detach before exporting again");
+    HDP_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (!h->peer_win) {
+        HDP_CUDA(h, cudaMalloc(&h->peer_win, kPeerWindowBytesHost));
+    }
+    // (flags and exchange counter restart together: a window is only ever re-exported with all ranks detached)
+    HDP_CUDA(h, cudaMemset(h->peer_win, 0, kPeerWindowBytesHost));
+    HDP_CUDA(h, cudaDeviceSynchronize());
+    h->peer_epoch = 0;
+    cudaIpcMemHandle_t ipc;
+    HDP_CUDA(h, cudaIpcGetMemHandle(&ipc, h->peer_win));
+    memcpy(handle_out, &ipc, sizeof(ipc));
+    return HDP_OK;
+}
+
+extern "C" int hdp_peer_window_attach(hdp_handle h, const uint8_t* handles, int nranks, int rank)
+{
+    if (!h || !handles) return HDP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    if (nranks < 2 || nranks > HDP_PEER_MAX_RANKS || rank < 0 || rank >= nranks)
+        return set_err(h, HDP_ERR_BAD_ARG, "peer windows: 2..%d ranks, got rank %d of %d", HDP_PEER_MAX_RANKS, rank, nranks);
+    if (!h->nccl_comm || h->nccl_nranks != nranks || h->nccl_rank != rank)
+        return set_err(h, HDP_ERR_BAD_ARG, "peer windows follow the communicator: call hdp_comm_init_rank with the same rank / nranks first");
+    if (!h->peer_win) return set_err(h, HDP_ERR_BAD_ARG, "hdp_peer_window_export has not been called on this handle");
+    peer_close_all(h);
+    for (int r = 0; r < nranks; ++r) {
+        if (r == rank) { h->peer_base[r] = h->peer_win; continue; }
+        cudaIpcMemHandle_t ipc;
+        memcpy(&ipc, handles + (size_t)r * HDP_PEER_HANDLE_BYTES, sizeof(ipc));
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            peer_close_all(h);
+            return set_err(h, HDP_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s (no peer path: sharded solves keep the ncclAllReduce)", r,
+                           cudaGetErrorString(e));
+        }
+        h->peer_base[r] = p;
+    }
+    h->peer_nranks = nranks;
+    h->peer_rank = rank;
+    return HDP_OK;
+}
+
+extern "C" int hdp_peer_window_detach(hdp_handle h)
+{
+    if (!h) return HDP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    cudaStreamSynchronize(h->stream);
+    peer_close_all(h);
     return HDP_OK;
 }
 

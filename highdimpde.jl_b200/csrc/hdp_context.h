@@ -47,11 +47,16 @@ struct hdp_context {
     // grow-only scratch, indexed by role
     enum { B_A = 0, B_B, B_C, B_D, B_E, B_F, B_G, B_H, B_I, B_J, B_K, B_L, B_M, B_O, B_P, B_Q, B_R, B_N };
     hdp::DevBuf buf[B_N];
-    int* d_flags = nullptr;          // [0] error flag, [1..] spare
+    int* d_flags = nullptr;          // [0] start point outside the box, [1] kernel/mode mismatch, [2] peer exchange timed out
     unsigned long long* d_ctr = nullptr; // [0] work counter, [1] bounce counter
     // NCCL (optional)
     void* nccl_comm = nullptr;
     int nccl_rank = 0, nccl_nranks = 1;
+    // peer exchange window (optional, hdp_peer_window_*): this rank's window and every rank's as mapped here
+    void* peer_win = nullptr;
+    void* peer_base[HDP_PEER_MAX_RANKS] = {};
+    int peer_nranks = 0, peer_rank = 0;
+    unsigned long long peer_epoch = 0; // one per exchange, in step on all ranks (every exchange is collective)
     // MLP plan cache
     std::map<std::string, std::shared_ptr<hdp::MlpPlan>> plans;
     std::map<std::string, std::shared_ptr<hdp::MlpSharding>> shardings; // per (plan, nranks, rank)

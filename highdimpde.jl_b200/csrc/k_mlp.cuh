@@ -1010,22 +1010,38 @@ __device__ __forceinline__ void combine_item(const MlpParams<T>& P, const int32_
                 }
             }
         } else if (mode != CMB_FINAL) {
-            for (int u = nd.unit_begin + lane; u < nd.unit_end; u += nl) {
-                if (mode == CMB_PARTIAL && !P.unit_mine[u]) continue;
-                const int tag = P.unit_tag[u];
-                const T v = (T)part[u];
-                const int sl = (tag >> 4) == UNIT_G ? P.L : (tag & 15);
-                if ((tag >> 4) == UNIT_G) Gs += v;
-                else {
+            // four units of this lane per pass, their loads in flight together (a node of a finely cut tree has
+            // thousands of units, and a pass of the combine chain lasts as long as its longest lane: walking them one
+            // load round-trip at a time was 160 us of a 7.3 ms solve); each lane still adds in ascending unit order
+            constexpr int UB = 4;
+            for (int u0 = nd.unit_begin + lane; u0 < nd.unit_end; u0 += UB * nl) {
+                int tg[UB];
+                T vv[UB];
 #pragma unroll
-                    for (int l = 0; l < kMaxL; ++l)
-                        if (l == (tag & 15)) Bl[l] += v;
+                for (int q = 0; q < UB; ++q) {
+                    const int u = u0 + q * nl;
+                    const bool ok = u < nd.unit_end && !(mode == CMB_PARTIAL && !P.unit_mine[u]);
+                    tg[q] = ok ? (int)P.unit_tag[u] : -1;
+                    vv[q] = ok ? (T)part[u] : (T)0;
                 }
-                if (stats) {
-                    const PlanUnit un = P.units[u];
 #pragma unroll
-                    for (int l = 0; l <= kMaxL; ++l)
-                        if (l == sl) { Ns[l] += (double)(un.k1 - un.k0); Sm[l] += rsq[2 * u]; Sq[l] += rsq[2 * u + 1]; }
+                for (int q = 0; q < UB; ++q) {
+                    if (tg[q] < 0) continue;
+                    const int u = u0 + q * nl, tag = tg[q];
+                    const T v = vv[q];
+                    const int sl = (tag >> 4) == UNIT_G ? P.L : (tag & 15);
+                    if ((tag >> 4) == UNIT_G) Gs += v;
+                    else {
+#pragma unroll
+                        for (int l = 0; l < kMaxL; ++l)
+                            if (l == (tag & 15)) Bl[l] += v;
+                    }
+                    if (stats) {
+                        const PlanUnit un = P.units[u];
+#pragma unroll
+                        for (int l = 0; l <= kMaxL; ++l)
+                            if (l == sl) { Ns[l] += (double)(un.k1 - un.k0); Sm[l] += rsq[2 * u]; Sq[l] += rsq[2 * u + 1]; }
+                    }
                 }
             }
         }
@@ -1164,9 +1180,25 @@ __device__ __forceinline__ void init_item(const MlpParams<T>& P, const T* x0, u6
 // kernels
 // ---------------------------------------------------------------------
 extern __shared__ double2 hdp_dyn_smem[]; // units kernel: blockDim.x * sizeof(Frame<T>) bytes
+
+// A solve is a chain of ten to twenty dependent launches (geometry by depth, units, combine by depth) and a
+// single solve — sharded or not — lasts 0.3-7 ms, so the gaps between the links count.  Every kernel of the
+// chain is launched with programmatic stream serialisation (k_mlp_host.cu: launch_chained) and opens with this
+// pair: `launch_dependents` lets the next link's blocks be scheduled onto whatever SM capacity this grid leaves
+// free (its launch latency, parameter load and — fp64 — the staging of the generator tables then overlap this
+// grid); `wait` blocks until every grid before this one has completed and its writes are visible.  All threads
+// of all blocks execute the pair first thing, unconditionally: a grid that exits without `wait` would be taken as
+// complete before its predecessors are.  Launched without the attribute (NVRTC-built kernels, host emulation)
+// both instructions do nothing.
+__device__ __forceinline__ void chain_enter()
+{
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 template <typename T>
 __global__ void mlp_init_kernel(const __grid_constant__ MlpParams<T> P, const T* __restrict__ x0)
 {
+    chain_enter();
     const u64 total = (u64)P.n_solves * (u64)P.dpad;
     for (u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (u64)gridDim.x * blockDim.x)
         init_item<T>(P, x0, q);
@@ -1178,7 +1210,9 @@ template <typename T, int G>
 __global__ void __launch_bounds__(128) mlp_expand_kernel(const __grid_constant__ MlpParams<T> P, const int32_t* list, int count,
                                                          int count_hits, const int32_t* list2, int count2, int count_hits2)
 {
-    if constexpr (sizeof(T) == 8) tables_init();
+    asm volatile("griddepcontrol.launch_dependents;");
+    if constexpr (sizeof(T) == 8) tables_init(); // (constant tables: staged while the previous link still runs)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     Ctx<T, G> c;
     ctx_init<T, G>(c, P, (u64)blockIdx.x * blockDim.x + threadIdx.x, threadIdx.x & 31);
     // a short pass (a link of the launch chain that cannot fill the GPU) takes one lane group per (site, point)
@@ -1201,7 +1235,9 @@ template <typename T, int G, int U, int FM = -1>
 __global__ void __launch_bounds__(HDP_MLP_BLOCK, Tune<U>::MB) mlp_units_kernel(const __grid_constant__ MlpParams<T> P)
 {
     constexpr int GPW = 32 / G;
+    asm volatile("griddepcontrol.launch_dependents;");
     if constexpr (sizeof(T) == 8) tables_init();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     Ctx<T, G> c;
     const int lane_w = threadIdx.x & 31;
     ctx_init<T, G>(c, P, (u64)blockIdx.x * blockDim.x + threadIdx.x, lane_w);
@@ -1236,6 +1272,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) mlp_prereduce_kernel(const __grid_constant__ MlpParams<T> P, const int32_t* list, int mode,
                                                             double* stage)
 {
+    chain_enter();
     const u64 item = blockIdx.y;
     const int solve = (int)(item % (u64)P.n_solves);
     const int nidx = list[item / (u64)P.n_solves];
@@ -1313,6 +1350,7 @@ template <typename T>
 __global__ void __launch_bounds__(512) mlp_combine_kernel(const __grid_constant__ MlpParams<T> P, const int32_t* list, int count,
                                                           int nl, int mode)
 {
+    chain_enter();
     const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     // the call-wide tail of the exchange buffer: wall hits of this rank out, the all-reduced total back
     if (t == 0 && P.xbuf) {
@@ -1334,11 +1372,88 @@ __global__ void __launch_bounds__(512) mlp_combine_kernel(const __grid_constant_
 template <typename T>
 __global__ void __launch_bounds__(128) mlp_scatter_kernel(const __grid_constant__ MlpParams<T> P, const int32_t* list, int count)
 {
+    chain_enter();
     const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (u64)count * (u64)P.n_solves) return;
     const int solve = (int)(t % (u64)P.n_solves);
     const int nidx = list[t / (u64)P.n_solves];
     P.partial[(u64)solve * P.n_units + P.nodes[nidx].unit_begin] = P.xbuf[(u64)solve * P.xstride + P.node_slot[nidx]];
+}
+
+// ---------------------------------------------------------------------
+// The exchange of a sharded solve over peer memory (hdp_peer_window_*, include/hdpde.h): push — flag — sum —
+// scatter in ONE single-block launch, in place of ncclAllReduce + mlp_scatter_kernel.
+// Window of a rank: double data[2][kPeerMax][kPeerSlot], then u64 flag[2][kPeerMax]; slot [p][r] and flag [p][r]
+// are written by rank r alone, in the exchanges of parity p.  Rank r's flag is the number of its latest exchange
+// (they only grow), stored with release semantics after its doubles; a reader takes it with acquire semantics
+// and then reads the slot past L1.  Two parities suffice: a rank can only be one exchange ahead of a peer (it
+// cannot finish exchange n + 1 without the peer's flag n + 1, which the peer publishes after it has finished
+// reading exchange n), and an exchange ahead writes the other parity.
+// The sum runs over the slots in rank order on every rank: identical bits everywhere, no dependence on arrival.
+// ---------------------------------------------------------------------
+constexpr int kPeerMax = 16;       // == HDP_PEER_MAX_RANKS
+constexpr int kPeerSlot = 8192;    // == HDP_PEER_SLOT_DOUBLES
+constexpr unsigned long long kPeerTimeoutNs = 20ull * 1000000000ull;
+constexpr size_t kPeerWindowBytes = (size_t)2 * kPeerMax * kPeerSlot * sizeof(double) + (size_t)2 * kPeerMax * sizeof(unsigned long long);
+struct PeerWin {
+    double* base[kPeerMax]; // every rank's window as mapped on this device
+    int nranks, rank;
+    unsigned long long epoch;
+};
+__device__ __forceinline__ unsigned long long* peer_flag(double* base, int par, int r)
+{
+    return reinterpret_cast<unsigned long long*>(base + (size_t)2 * kPeerMax * kPeerSlot) + par * kPeerMax + r;
+}
+template <typename T>
+__global__ void __launch_bounds__(1024) mlp_exchange_kernel(const __grid_constant__ MlpParams<T> P, const __grid_constant__ PeerWin W,
+                                                            int n, const int32_t* leaves, int n_leaves)
+{
+    chain_enter();
+    const int par = (int)(W.epoch & 1ull);
+    const size_t slot = ((size_t)par * kPeerMax + (size_t)W.rank) * kPeerSlot;
+    // push: this rank's doubles into its slot of every window (the peers' over NVLink, its own locally)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double v = P.xbuf[i];
+        for (int q = 0; q < W.nranks; ++q) {
+            int r = W.rank + q; // (each rank starts with a different peer)
+            if (r >= W.nranks) r -= W.nranks;
+            W.base[r][slot + i] = v;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < W.nranks) {
+        const int r = threadIdx.x;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flag(W.base[r], par, W.rank)), "l"(W.epoch) : "memory");
+        const unsigned long long* f = peer_flag(W.base[W.rank], par, r);
+        unsigned long long v, t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+            if (v >= W.epoch) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > kPeerTimeoutNs) { // the peer never arrived: fail the call, do not hang the GPU
+                atomicExch(&P.flags[2], 1);
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    // sum of the slots of this rank's window, in rank order
+    const double* mine = W.base[W.rank] + (size_t)par * kPeerMax * kPeerSlot;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double a = 0.0;
+        for (int r = 0; r < W.nranks; ++r) a += __ldcg(mine + (size_t)r * kPeerSlot + i);
+        P.xbuf[i] = a;
+    }
+    __syncthreads();
+    // whole-call leaves below upper sites: their summed values go back to partial[], where the sites read them
+    const u64 tot = (u64)n_leaves * (u64)P.n_solves;
+    for (u64 t = threadIdx.x; t < tot; t += blockDim.x) {
+        const int solve = (int)(t % (u64)P.n_solves);
+        const int nidx = leaves[t / (u64)P.n_solves];
+        P.partial[(u64)solve * P.n_units + P.nodes[nidx].unit_begin] = P.xbuf[(u64)solve * P.xstride + P.node_slot[nidx]];
+    }
 }
 #endif // HDP_HOST_EMU
 

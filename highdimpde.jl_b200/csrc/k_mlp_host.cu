@@ -13,6 +13,8 @@
 
 using namespace hdp;
 
+static_assert(kPeerMax == HDP_PEER_MAX_RANKS && kPeerSlot == HDP_PEER_SLOT_DOUBLES, "peer window constants (include/hdpde.h)");
+
 namespace hdp {
 MlpPlan::~MlpPlan()
 {
@@ -337,7 +339,14 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
     P.M = M; P.K = K; P.L = L; P.Kp = tab.Kp;
     P.nvec = nvec;
     P.npl = (nvec + G - 1) / G;
-    P.dpad = P.npl * G * VEC; // every lane may load its full vec-group
+    // Geometry passes that cannot fill the GPU (every pass of a single Allen-Cahn solve: a few hundred to a few
+    // thousand sites per depth) last as long as ONE path-step of one lane group, and the chain has one such pass
+    // per depth: they run a warp per (site, point) whatever the width of the units kernel — d = 100 with two lanes
+    // per point is 25 dependent passes over the row (11-13 us per launch), with a warp it is two.  Rows are plain
+    // arrays of vec-groups, so only their padding depends on the width.  Short rows (d = 10) keep one width.
+    const int Ge = (!um && nvec >= 16 && G < 32) ? 32 : G;
+    const int npl_e = (nvec + Ge - 1) / Ge;
+    P.dpad = std::max(P.npl * G, npl_e * Ge) * VEC; // every lane may load its full vec-group
     for (int i = 0; i <= kMaxL; ++i) {
         P.C[i] = tab.C[i]; P.R[i] = tab.R[i]; P.S[i] = tab.S[i];
         P.cs[i] = tab.cs[i]; P.rs[i] = tab.rs[i]; P.ss[i] = tab.ss[i];
@@ -416,6 +425,8 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
         if (!P.xbuf) return HDP_ERR_ALLOC;
         my_hash = call_hash<T>(prob, cfg, on_device ? nullptr : x0, P.n_units, thresh);
     }
+    // peer windows attached on every rank and the exchange fits a slot: the library's own exchange kernel
+    const bool use_peer = sh && h->peer_nranks == nranks && h->peer_rank == rank && x_count <= (size_t)kPeerSlot;
 
     if (taped) {
         uint64_t nC = tab.C[L], nR = tab.R[L], nS = tab.S[L];
@@ -472,17 +483,24 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
         trace("init", gi);
         HDP_CUDA(h, cudaGetLastError());
     }
+    const MlpLaunchers<T> LNe = launchers_for<T>(Ge);
+    MlpParams<T> Pe = P; // the wide geometry pass: the same state, its own row partition
+    Pe.npl = npl_e;
     auto launch_expand = [&](const int32_t* list, int cnt, int count_hits, const int32_t* list2 = nullptr, int cnt2 = 0,
                              int count_hits2 = 0) -> int {
         if (cnt + cnt2 == 0) return HDP_OK;
         const uint64_t site_items = (uint64_t)(cnt + cnt2) * n_solves;
         // one lane group per (site, solve, point) in a short pass, per (site, solve) in a long one (mlp_expand_kernel)
         uint64_t groups = site_items * (uint64_t)(site_items < kExpandSplitBelow ? 1 + tab.Kp : 1);
-        int ge = (int)std::min<uint64_t>((groups * G + block - 1) / block, (uint64_t)sms * 12);
+        // a warp per item while all of them are resident at once
+        const bool wide = Ge != G && groups * (uint64_t)Ge <= (uint64_t)sms * 12 * block;
+        const int Gx = wide ? Ge : G;
+        int ge = (int)std::min<uint64_t>((groups * Gx + block - 1) / block, (uint64_t)sms * 12);
         if (um) {
             void* args[7] = {(void*)&P, (void*)&list, (void*)&cnt, (void*)&count_hits, (void*)&list2, (void*)&cnt2, (void*)&count_hits2};
-            HDP_CUDA(h, cudaLaunchKernel((const void*)um->expand, dim3(ge), dim3(block), args, 0, h->stream));
-        } else HDP_CUDA(h, LN.expand(P, list, cnt, count_hits, list2, cnt2, count_hits2, ge, block, h->stream));
+            HDP_CUDA(h, launch_chained_module((const void*)um->expand, dim3(ge), dim3(block), 0, h->stream, args));
+        } else if (wide) HDP_CUDA(h, LNe.expand(Pe, list, cnt, count_hits, list2, cnt2, count_hits2, ge, block, h->stream));
+        else HDP_CUDA(h, LN.expand(P, list, cnt, count_hits, list2, cnt2, count_hits2, ge, block, h->stream));
         h->launches++;
         trace("expand", cnt + cnt2);
         return HDP_OK;
@@ -499,9 +517,9 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
         if (staged) {
             double* stage = (double*)ensure(h, hdp_context::B_R, items * kStageBlocks * kCmbStage * sizeof(double));
             if (!stage) return HDP_ERR_ALLOC;
-            mlp_prereduce_kernel<T><<<dim3(kStageBlocks, (unsigned)items), 256, 0, h->stream>>>(P, list, cmode, stage);
+            HDP_CUDA(h, launch_chained(mlp_prereduce_kernel<T>, dim3(kStageBlocks, (unsigned)items), dim3(256), 0, h->stream, P, list,
+                                       cmode, stage));
             h->launches++;
-            HDP_CUDA(h, cudaGetLastError());
             trace("prereduce", cnt);
             Pc.stage = stage;
             Pc.stage_nb = kStageBlocks;
@@ -526,8 +544,8 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
         int gc = (int)((tot + cb - 1) / cb);
         if (um) { // f is applied in the combine too: the user module's build of it
             void* args[5] = {(void*)&Pc, (void*)&list, (void*)&cnt, (void*)&nl, (void*)&cmode};
-            HDP_CUDA(h, cudaLaunchKernel((const void*)um->combine, dim3(gc), dim3(cb), args, 0, h->stream));
-        } else mlp_combine_kernel<T><<<gc, cb, 0, h->stream>>>(Pc, list, cnt, nl, cmode);
+            HDP_CUDA(h, launch_chained_module((const void*)um->combine, dim3(gc), dim3(cb), 0, h->stream, args));
+        } else HDP_CUDA(h, launch_chained(mlp_combine_kernel<T>, dim3(gc), dim3(cb), 0, h->stream, Pc, list, cnt, nl, cmode));
         h->launches++;
         trace(cmode == CMB_ALL ? "combine_all" : (cmode == CMB_PARTIAL ? "combine_partial" : "combine_final"), cnt);
         HDP_CUDA(h, cudaGetLastError());
@@ -554,7 +572,7 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
     if (n_local > 0) {
         if (um) {
             void* args[1] = {(void*)&P};
-            HDP_CUDA(h, cudaLaunchKernel((const void*)um->units, dim3(grid), dim3(block), args, dyn_smem, h->stream));
+            HDP_CUDA(h, launch_chained_module((const void*)um->units, dim3(grid), dim3(block), dyn_smem, h->stream, args));
         } else HDP_CUDA(h, LN.units[long_rows][mode](P, grid, block, dyn_smem, h->stream));
         h->launches++;
         trace("units", (int)n_local);
@@ -584,17 +602,33 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
                                  (int)sh->crown_nodes.size() - 1, CMB_PARTIAL)) != HDP_OK)
             return rc;
         HDP_CUDA(h, cudaEventRecord(h->evp[1], h->stream)); // (the local combine counts as unit work)
-        rc = nccl_allreduce_f64_device(h, P.xbuf, x_count);
-        if (rc != HDP_OK) return rc;
-        trace("allreduce", (int)x_count);
-        HDP_CUDA(h, cudaEventRecord(h->evp[2], h->stream));
-        if (!sh->crown_leaves.empty()) {
-            const int cnt = (int)sh->crown_leaves.size();
-            const uint64_t tot = (uint64_t)cnt * n_solves;
-            mlp_scatter_kernel<T><<<(int)((tot + 127) / 128), 128, 0, h->stream>>>(P, (const int32_t*)sh->d_crown_leaves, cnt);
+        if (use_peer) {
+            // the library's own exchange over peer memory: push, flag, sum in rank order and the scatter of the
+            // whole-call leaves in one launch (mlp_exchange_kernel)
+            PeerWin W;
+            memset(&W, 0, sizeof(W));
+            for (int r = 0; r < nranks; ++r) W.base[r] = (double*)h->peer_base[r];
+            W.nranks = nranks;
+            W.rank = rank;
+            W.epoch = ++h->peer_epoch;
+            HDP_CUDA(h, launch_chained(mlp_exchange_kernel<T>, dim3(1), dim3(1024), 0, h->stream, P, W, (int)x_count,
+                                       (const int32_t*)sh->d_crown_leaves, (int)sh->crown_leaves.size()));
             h->launches++;
-            trace("scatter", cnt);
-            HDP_CUDA(h, cudaGetLastError());
+            trace("exchange", (int)x_count);
+            HDP_CUDA(h, cudaEventRecord(h->evp[2], h->stream));
+        } else {
+            rc = nccl_allreduce_f64_device(h, P.xbuf, x_count);
+            if (rc != HDP_OK) return rc;
+            trace("allreduce", (int)x_count);
+            HDP_CUDA(h, cudaEventRecord(h->evp[2], h->stream));
+            if (!sh->crown_leaves.empty()) {
+                const int cnt = (int)sh->crown_leaves.size();
+                const uint64_t tot = (uint64_t)cnt * n_solves;
+                HDP_CUDA(h, launch_chained(mlp_scatter_kernel<T>, dim3((unsigned)((tot + 127) / 128)), dim3(128), 0, h->stream, P,
+                                           (const int32_t*)sh->d_crown_leaves, cnt));
+                h->launches++;
+                trace("scatter", cnt);
+            }
         }
         for (int dep = plan->max_depth; dep >= 0; --dep) {
             const int off = sh->crown_final_off[dep];
@@ -610,6 +644,7 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
     if (want_se && !on_device)
         HDP_CUDA(h, cudaMemcpyAsync(se_out, d_se, (size_t)n_solves * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
     if (stats) {
+        stats->exchange_kind = sh ? (use_peer ? 2 : 1) : 0;
         stats->n_units = P.n_units;
         stats->n_nodes = P.n_nodes;
         stats->n_sites = P.n_sites;
@@ -618,7 +653,7 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
         stats->exchange_bytes = x_count * sizeof(double);
     }
     if (async) return HDP_OK; // a start point outside the box surfaces at hdp_sync
-    int flags2[2] = {0, 0}; // [0] start point outside the box, [1] kernel / mode mismatch (internal)
+    int flags2[3] = {0, 0, 0}; // [0] start point outside the box, [1] kernel / mode mismatch (internal), [2] peer exchange timed out
     int& flag = flags2[0];
     unsigned long long ctr[2] = {0, 0};
     double lv0[3 * (kMaxL + 1)];
@@ -663,6 +698,11 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
             }
             stats->std_error = (double)se0;
         }
+    }
+    if (flags2[2]) {
+        cudaMemsetAsync(h->d_flags, 0, sizeof(flags2), h->stream);
+        return set_err(h, HDP_ERR_NCCL, "sharded MLP solve: a peer did not reach the exchange within 20 s (every rank must make the "
+                                        "same sequence of sharded calls; detach the peer windows to fall back to NCCL)");
     }
     if (flags2[1]) {
         cudaMemsetAsync(h->d_flags, 0, sizeof(flags2), h->stream);

@@ -24,14 +24,13 @@ template <int U, int FM> static int inst_max_blocks(int block, size_t dyn_smem)
 template <int U, int FM>
 static cudaError_t inst_units(const MlpParams<T_>& P, int grid, int block, size_t dyn_smem, cudaStream_t st)
 {
-    mlp_units_kernel<T_, G_, U, FM><<<grid, block, dyn_smem, st>>>(P);
-    return cudaGetLastError();
+    return launch_chained(mlp_units_kernel<T_, G_, U, FM>, dim3(grid), dim3(block), dyn_smem, st, P);
 }
 static cudaError_t inst_expand(const MlpParams<T_>& P, const int32_t* list, int count, int count_hits, const int32_t* list2,
                                int count2, int count_hits2, int grid, int block, cudaStream_t st)
 {
-    mlp_expand_kernel<T_, G_><<<grid, block, 0, st>>>(P, list, count, count_hits, list2, count2, count_hits2);
-    return cudaGetLastError();
+    return launch_chained(mlp_expand_kernel<T_, G_>, dim3(grid), dim3(block), 0, st, P, list, count, count_hits, list2, count2,
+                          count_hits2);
 }
 } // namespace
 

@@ -2,9 +2,45 @@
 // Each (T, G) pair is compiled in its own translation unit (k_mlp_inst.cu with
 // -DHDP_INST_T / -DHDP_INST_G) so the build parallelises.
 #pragma once
+#include <string.h>
+#include <utility>
 #include "k_mlp.cuh"
 
 namespace hdp {
+
+// Launch of one link of a solve's chain: programmatic stream serialisation, so that the link's blocks may be
+// scheduled while the previous link still runs and wait at `griddepcontrol.wait` (chain_enter, k_mlp.cuh)
+// instead of being launched only after it has drained.  (-DHDP_NO_CHAIN_PDL: plain launches, for A/B runs.)
+inline void chained_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* at, dim3 grid, dim3 block, size_t smem, cudaStream_t st)
+{
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->gridDim = grid;
+    cfg->blockDim = block;
+    cfg->dynamicSmemBytes = smem;
+    cfg->stream = st;
+#ifndef HDP_NO_CHAIN_PDL
+    at->id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at->val.programmaticStreamSerializationAllowed = 1;
+    cfg->attrs = at;
+    cfg->numAttrs = 1;
+#endif
+}
+template <typename... KA, typename... A>
+inline cudaError_t launch_chained(void (*kernel)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args)
+{
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute at;
+    chained_config(&cfg, &at, grid, block, smem, st);
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<A>(args)...);
+}
+// the same for a kernel of an NVRTC-built module
+inline cudaError_t launch_chained_module(const void* kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st, void** args)
+{
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute at;
+    chained_config(&cfg, &at, grid, block, smem, st);
+    return cudaLaunchKernelExC(&cfg, kernel, args);
+}
 
 template <typename T> struct MlpLaunchers {
     // [0]: one vec-group per pass (short rows), [1]: three per pass (long rows), [2]: four per pass (very long

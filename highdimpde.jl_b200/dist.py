@@ -82,11 +82,43 @@ def min_over_ranks(x: float) -> float:
     return float(t.item())
 
 
-def attach_nccl(handle):
-    """Join this rank's handle to an NCCL communicator over all ranks."""
+def attach_nccl(handle, peer_windows: bool = True):
+    """Join this rank's handle to an NCCL communicator over all ranks and — ranks of one node with a peer path —
+    attach the peer exchange windows (`attach_peer_windows`), so that the exchange of a sharded solve is the
+    library's own kernel over NVLink peer memory; NCCL stays for exchanges larger than a window slot."""
     dist = _dist()
     rank, world = dist.get_rank(), dist.get_world_size()
     uid = handle.nccl_unique_id() if rank == 0 else None
     uid = broadcast_bytes(uid, 128)
     handle.comm_init_rank(uid, world, rank)
+    if peer_windows and world > 1:
+        attach_peer_windows(handle)
     return rank, world
+
+
+def attach_peer_windows(handle) -> bool:
+    """hdp_peer_window_export on every rank, the 64-byte IPC handles gathered in rank order, hdp_peer_window_attach.
+    All or nothing: if any rank cannot map a peer (different nodes, no P2P path, more than 16 ranks) every rank
+    detaches and sharded solves keep the ncclAllReduce.  Returns whether the windows are attached."""
+    from . import _capi
+    dist = _dist()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ok, mine = True, b""
+    if world > _capi.HDP_PEER_MAX_RANKS:
+        ok = False
+    else:
+        try:
+            mine = handle.peer_window_export()
+        except _capi.HdpError:
+            ok = False
+    parts = all_gather_object((ok, mine))
+    ok = all(p[0] for p in parts)
+    if ok:
+        try:
+            handle.peer_window_attach(b"".join(p[1] for p in parts), world, rank)
+        except _capi.HdpError:
+            ok = False
+    ok = all(all_gather_object(ok))
+    if not ok:
+        handle.peer_window_detach()
+    return ok

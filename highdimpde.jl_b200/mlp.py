@@ -101,7 +101,8 @@ def _ml_picard_batch(prob: _Problem, alg: MLP, *, n_solves=1, x0=None, seed=0, t
              "group_size": st.group_size, "n_launches": st.n_launches,
              "phase_ms": {"expand": st.phase_ms[0], "units": st.phase_ms[1], "allreduce": st.phase_ms[2],
                           "combine": st.phase_ms[3]},
-             "exchange_bytes": st.exchange_bytes}
+             "exchange_bytes": st.exchange_bytes,
+             "exchange_kind": ("none", "nccl", "peer")[st.exchange_kind]}
     if std_err:
         L1 = alg.L + 1
         stats.update({"std_err": se, "level_n": list(st.level_n[:L1]), "level_sum": list(st.level_sum[:L1]),

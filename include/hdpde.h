@@ -258,6 +258,9 @@ typedef struct hdp_mlp_stats {
     double level_sumsq[HDP_MAX_LEVELS + 1];   /* sum of their squares                              */
     double std_error;                         /* of solve 0                                        */
     uint64_t exchange_bytes;   /* bytes each rank hands to the all-reduce (0 on one GPU)           */
+    int32_t exchange_kind;     /* 0 none (one GPU), 1 ncclAllReduce, 2 the library's exchange kernel
+                                  over peer windows (hdp_peer_window_*)                            */
+    int32_t _pad;
 } hdp_mlp_stats;
 
 typedef struct hdp_devinfo {
@@ -300,6 +303,25 @@ int hdp_comm_init_rank(hdp_handle h, const uint8_t id[128], int nranks, int rank
 int hdp_comm_destroy(hdp_handle h);
 /* sum-allreduce of n doubles in place (host buffer) — plumbing check */
 int hdp_comm_allreduce_f64(hdp_handle h, double* buf, size_t n);
+
+/* Peer exchange window (ranks on ONE node, after hdp_comm_init_rank): the exchange of a sharded solve is a few
+ * KB — one double per crown node — and a solve lasts 0.3-1.5 ms, so the 35-50 us an ncclAllReduce of that size
+ * takes is all latency.  With windows attached the library's own exchange kernel does it instead: every rank
+ * stores its doubles straight into a slot of every peer's window over NVLink (P2P stores through a CUDA-IPC
+ * mapping), publishes a release flag per peer, waits for the peers' flags and sums the slots of its own window in
+ * rank order — the same bits on every rank — and hands whole-call leaves back to their parent sites in the same
+ * launch.  hdp_peer_window_export allocates this rank's window and returns its 64-byte IPC handle; the host
+ * language gathers the handles of all ranks (rank order) and every rank attaches.  Collective: either all
+ * ranks attach or all detach (hdp_peer_window_detach) — a rank that cannot map a peer (no P2P path) returns an
+ * error and the caller must detach everywhere; solves then use the ncclAllReduce.  Exchanges larger than the
+ * window slot (HDP_PEER_SLOT_DOUBLES per solve call) use NCCL as well.  A peer that does not arrive within
+ * 20 s fails the call with HDP_ERR_NCCL instead of hanging the GPU. */
+#define HDP_PEER_HANDLE_BYTES 64
+#define HDP_PEER_MAX_RANKS 16
+#define HDP_PEER_SLOT_DOUBLES 8192
+int hdp_peer_window_export(hdp_handle h, uint8_t handle_out[HDP_PEER_HANDLE_BYTES]);
+int hdp_peer_window_attach(hdp_handle h, const uint8_t* handles /* nranks x 64 bytes, rank order */, int nranks, int rank);
+int hdp_peer_window_detach(hdp_handle h);
 
 /* ------------------------------------------------------------------ */
 /* K4: reflection operator                                             */

@@ -70,6 +70,7 @@ struct HdpMlpStats
     level_sumsq::NTuple{HDP_MAX_LEVELS + 1, Float64}
     std_error::Float64
     exchange_bytes::UInt64
+    exchange_kind::Int32; _pad::Int32   # 0 none, 1 ncclAllReduce, 2 exchange kernel over peer windows
 end
 
 # ------------------------------------------------------------------ kinds: callable structs

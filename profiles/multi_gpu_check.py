@@ -3,8 +3,8 @@
       profiles/multi_gpu_check.py [L [M]]
 1. NCCL plumbing: hdp_nccl_unique_id -> broadcast -> hdp_comm_init_rank, allreduce self-test.
 2. Strong scaling of ONE solve (BASELINE C4 shape: non-local Fisher-KPP d=10, UniformSampling, M=4, K=10, level L):
-   bottom subtrees owned by one rank each, one ncclAllReduce of a double per crown node, the crown finished on
-   every rank; the result must agree with the single-GPU solve to 1e-12 (a few sums are associated differently),
+   bottom subtrees owned by one rank each, one exchange of a double per crown node (the library's kernel over peer
+   windows, and the ncclAllReduce it replaces: both are run and compared), the crown finished on every rank; the result must agree with the single-GPU solve to 1e-12 (a few sums are associated differently),
    be bit-identical on all ranks, count every wall hit once, and a rank that passes another seed must be caught.
 3. Weak scaling of independent solves (C2): shards of the solve index, no collective."""
 import os
@@ -30,8 +30,10 @@ Mv = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 
 h_solo = H.Handle(local)          # no communicator: the single-GPU reference
 h = H.Handle(local)
-r, w = HD.attach_nccl(h)
+r, w = HD.attach_nccl(h)        # communicator + peer exchange windows (the library's own exchange kernel)
 assert (r, w) == (rank, world)
+h_nccl = H.Handle(local)        # communicator only: the exchange is an ncclAllReduce
+HD.attach_nccl(h_nccl, peer_windows=False)
 x = h.allreduce_f64(np.array([rank + 1.0, 1.0]))
 assert x[0] == world * (world + 1) / 2 and x[1] == world, x
 
@@ -57,6 +59,13 @@ for it in range(3):
 # so compare values to 1e-12 and, when the unit counts agree, bit for bit.
 rel = abs(uN[0] - u1[0]) / abs(u1[0])
 assert rel <= 1e-12, (uN, u1)
+# the two exchanges: the same crown sums up to the order of nranks additions
+uC, sC = H._ml_picard_batch(prob, alg, n_solves=1, seed=3, handle=h_nccl)
+assert sC["exchange_kind"] == "nccl", sC["exchange_kind"]
+assert abs(uC[0] - uN[0]) <= 1e-14 * abs(uN[0]), (uC, uN)
+assert sC["bounces"] == sN["bounces"]
+peer_ok = sN["exchange_kind"] == "peer"
+assert all(HD.all_gather_object(peer_ok)) or not any(HD.all_gather_object(peer_ok))
 same_bits = bool(uN[0] == u1[0])
 allu = HD.all_gather_object(float(uN[0]))
 assert all(v == allu[0] for v in allu), allu  # every rank holds the identical result
@@ -71,7 +80,7 @@ dev = HD.max_over_ranks(min(v[1] for v in res.values()))
 if rank == 0:
     print(f"[multi] world={world} C4-shape M={Mv} L={Lv} ({sN['path_steps']} path-steps): u={uN[0]:.15g} rel_vs_1gpu={rel:.1e} bit_equal={same_bits} "
           f"units={sN['n_units']} (1 GPU: {s1['n_units']}) device_ms N-GPU={dev:.3f} 1-GPU={min(t_solo):.3f} "
-          f"speedup={min(t_solo) / dev:.2f}x bounces={sN['bounces']} exchange_bytes={sN['exchange_bytes']} phase_ms={ {k: round(v, 3) for k, v in sN['phase_ms'].items()} }")
+          f"speedup={min(t_solo) / dev:.2f}x bounces={sN['bounces']} exchange={sN['exchange_kind']} exchange_bytes={sN['exchange_bytes']} (nccl: {sC['device_ms']:.3f} ms, allreduce {sC['phase_ms']['allreduce']:.3f}) phase_ms={ {k: round(v, 3) for k, v in sN['phase_ms'].items()} }")
 
 # weak scaling: independent C2 solves
 D = 100
@@ -90,5 +99,6 @@ assert np.allclose(full[:4], chk, rtol=1e-13, atol=0.0), (full[:4], chk)
 if rank == 0:
     print(f"[multi] weak: {n_total} C2 solves over {world} ranks, mean u = {full.mean():.6f}, per-rank device_ms {st['device_ms']:.2f}")
 h.close()
+h_nccl.close()
 h_solo.close()
 dist.destroy_process_group()
