@@ -90,6 +90,11 @@ template <typename T> struct MlpParams {
     // units are summed by stage_nb blocks each first (mlp_prereduce_kernel), stage[launch item][block][kCmbStage]
     const double* stage;
     int stage_nb;
+    // ... or, for a list with per-node shares (the crown of a sharded solve: the root has 10^5 units and thousands of
+    // sites, most crown nodes a handful): job j = (list index, share) sums that share of the node's units AND of
+    // its sites into stage[solve][j]; stage_off[k] .. stage_off[k + 1] are the jobs of list entry k
+    const int32_t* stage_off;
+    int stage_jobs;
     unsigned long long* work_ctr;
     unsigned long long* bounce_ctr;
     int* flags;
@@ -937,6 +942,46 @@ __device__ __forceinline__ void unit_item(Ctx<T, G>& c, const MlpParams<T>& P, u
     }
 }
 
+// The f-term of one explicit site from its children's values: b3 / K of src/MLP.jl:139-194 (`val`, `part`, `feat`:
+// the solve's node values, unit partial sums and point features; *l_out: the site's level)
+template <typename T>
+__device__ __forceinline__ T site_term(const MlpParams<T>& P, int si, const T* val, const double* part, const T* feat, int* l_out)
+{
+    const DevProblem<T>& pb = P.pb;
+    const PlanSite st = P.sites[si];
+    const int l = st.l;
+    const int32_t* ch = P.children + st.child0;
+    const T f2 = feat[st.x2_point];
+    // child value: explicit node, whole-call leaf (straight from its unit's partial), or 0
+    auto cv = [&](int32_t code) -> T {
+        return code >= 0 ? val[code] : (code == -1 ? (T)0 : (T)part[-2 - code]);
+    };
+    const T b2 = cv(ch[0]);
+    const T b4 = cv(ch[1]);
+    T b3 = (T)0;
+    if (P.Kp > 0) {
+        // (unrolled: the loads of four sampled points are in flight together — a combine pass is a link in a
+        // chain of dependent launches and lasts as long as one site's chain of dependent loads)
+#pragma unroll 4
+        for (int h = 0; h < P.K; ++h) {
+            const T f3 = feat[st.x3_point0 + h];
+            const T v = cv(ch[2 + 2 * h]);
+            T term = f_eval<T>(pb, f2, f3, b2, v);
+            if (l >= 2) {
+                const T w = cv(ch[3 + 2 * h]);
+                term = term - f_eval<T>(pb, f2, f3, b4, w);
+            }
+            b3 += term;
+        }
+    } else {
+        T term = f_eval<T>(pb, f2, (T)0, b2, (T)0);
+        if (l >= 2) term = term - f_eval<T>(pb, f2, (T)0, b4, (T)0);
+        for (int h = 0; h < P.K; ++h) b3 += term;
+    }
+    *l_out = l;
+    return b3 / (T)P.K;
+}
+
 // value of one explicit node from its units' partial sums and its explicit sites.
 // `nl` lanes (a warp on the device, 1 in the host emulation) share the node: they stride over
 // its units and over its explicit sites, then the per-level sums are butterfly-reduced — the
@@ -995,10 +1040,15 @@ __device__ __forceinline__ void combine_item(const MlpParams<T>& P, const int32_
 #pragma unroll
         for (int l = 0; l < kMaxL; ++l) Bl[l] = (T)0;
         T Gs = (T)0;
-        if (mode != CMB_FINAL && P.stage != nullptr && nd.unit_end - nd.unit_begin > kBigNode) {
-            // the units were summed by mlp_prereduce_kernel: one record per block
-            for (int b = lane; b < P.stage_nb; b += nl) {
-                const double* q = P.stage + (item * (u64)P.stage_nb + (u64)b) * kCmbStage;
+        // (a list with per-node shares: a node without jobs is light and is walked here like any other)
+        const int k = (int)(item / (u64)P.n_solves);
+        const bool by_jobs = mode != CMB_FINAL && P.stage != nullptr && P.stage_off != nullptr && P.stage_off[k + 1] > P.stage_off[k];
+        if (by_jobs || (mode != CMB_FINAL && P.stage != nullptr && P.stage_off == nullptr && nd.unit_end - nd.unit_begin > kBigNode)) {
+            // the units (by_jobs: and the sites) were summed by mlp_prereduce_kernel: one record per block
+            const int nb = by_jobs ? P.stage_off[k + 1] - P.stage_off[k] : P.stage_nb;
+            const u64 rec0 = by_jobs ? (u64)solve * (u64)P.stage_jobs + (u64)P.stage_off[k] : item * (u64)P.stage_nb;
+            for (int b = lane; b < nb; b += nl) {
+                const double* q = P.stage + (rec0 + (u64)b) * kCmbStage;
 #pragma unroll
                 for (int l = 0; l < kMaxL; ++l) Bl[l] += (T)q[l];
                 Gs += (T)q[kMaxL];
@@ -1045,42 +1095,13 @@ __device__ __forceinline__ void combine_item(const MlpParams<T>& P, const int32_
                 }
             }
         }
-        for (int si = nd.site_begin + lane; si < nd.site_end; si += nl) {
+        for (int si = nd.site_begin + lane; si < nd.site_end && !by_jobs; si += nl) {
             if (mode != CMB_ALL) {
                 const int cls = P.site_cls[si];
                 if (mode == CMB_PARTIAL ? cls != SITE_MINE : cls != SITE_UPPER) continue;
             }
-            const PlanSite st = P.sites[si];
-            const int l = st.l;
-            const int32_t* ch = P.children + st.child0;
-            const T f2 = feat[st.x2_point];
-            // child value: explicit node, whole-call leaf (straight from its unit's partial), or 0
-            auto cv = [&](int32_t code) -> T {
-                return code >= 0 ? val[code] : (code == -1 ? (T)0 : (T)part[-2 - code]);
-            };
-            const T b2 = cv(ch[0]);
-            const T b4 = cv(ch[1]);
-            T b3 = (T)0;
-            if (P.Kp > 0) {
-                // (unrolled: the loads of four sampled points are in flight together — a combine pass is a link in a
-                // chain of dependent launches and lasts as long as one site's chain of dependent loads)
-#pragma unroll 4
-                for (int h = 0; h < P.K; ++h) {
-                    const T f3 = feat[st.x3_point0 + h];
-                    const T v = cv(ch[2 + 2 * h]);
-                    T term = f_eval<T>(pb, f2, f3, b2, v);
-                    if (l >= 2) {
-                        const T w = cv(ch[3 + 2 * h]);
-                        term = term - f_eval<T>(pb, f2, f3, b4, w);
-                    }
-                    b3 += term;
-                }
-            } else {
-                T term = f_eval<T>(pb, f2, (T)0, b2, (T)0);
-                if (l >= 2) term = term - f_eval<T>(pb, f2, (T)0, b4, (T)0);
-                for (int h = 0; h < P.K; ++h) b3 += term;
-            }
-            const T add = b3 / (T)P.K;
+            int l;
+            const T add = site_term<T>(P, si, val, part, feat, &l);
 #pragma unroll
             for (int q = 0; q < kMaxL; ++q)
                 if (q == l) {
@@ -1268,22 +1289,40 @@ __global__ void __launch_bounds__(HDP_MLP_BLOCK, Tune<U>::MB) mlp_units_kernel(c
 // per level — and, for the root, the sample statistics of the error bar — in a fixed order, and leaves one
 // kCmbStage record.  A single block of 512 lanes walking the 10^5 units of the root of Allen-Cahn d=100, M=8, L=6
 // through dependent loads took 0.23 ms of a 1.6 ms sharded solve.
+// With `jobs` (crown of a sharded solve, P.stage_off): grid (jobs, solves); job j = (list index k, share b of the
+// stage_off[k + 1] - stage_off[k] shares of that node) sums its share of the node's units and of its sites (the
+// f-terms of this rank's ownership roots) — the combine launch that follows only adds the records up, so the
+// root, whose thousands of sites one block walked through dependent loads in 33 us, costs what any node costs.
 template <typename T>
-__global__ void __launch_bounds__(256) mlp_prereduce_kernel(const __grid_constant__ MlpParams<T> P, const int32_t* list, int mode,
-                                                            double* stage)
+__global__ void __launch_bounds__(256, 3) mlp_prereduce_kernel(const __grid_constant__ MlpParams<T> P, const int32_t* list, int mode,
+                                                            double* stage, const int2* jobs)
 {
     chain_enter();
-    const u64 item = blockIdx.y;
-    const int solve = (int)(item % (u64)P.n_solves);
-    const int nidx = list[item / (u64)P.n_solves];
+    int share, nshare, solve, nidx;
+    u64 rec;
+    if (jobs) {
+        const int2 jb = jobs[blockIdx.x];
+        share = jb.y;
+        nshare = P.stage_off[jb.x + 1] - P.stage_off[jb.x];
+        solve = (int)blockIdx.y;
+        nidx = list[jb.x];
+        rec = (u64)solve * (u64)P.stage_jobs + (u64)blockIdx.x;
+    } else {
+        const u64 item = blockIdx.y;
+        share = (int)blockIdx.x;
+        nshare = (int)gridDim.x;
+        solve = (int)(item % (u64)P.n_solves);
+        nidx = list[item / (u64)P.n_solves];
+        rec = item * (u64)gridDim.x + blockIdx.x;
+    }
     const PlanNode nd = P.nodes[nidx];
     const int nu = nd.unit_end - nd.unit_begin;
-    if (nu <= kBigNode) return;
+    if (!jobs && nu <= kBigNode) return;
     const double* part = P.partial + (u64)solve * P.n_units;
     const bool stats = nidx == 0 && P.lvstat != nullptr;
     const double* rsq = stats ? P.rootsq + (u64)solve * P.rootsq_stride : nullptr;
-    const int per = (nu + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int u0 = nd.unit_begin + (int)blockIdx.x * per;
+    const int per = (nu + nshare - 1) / nshare;
+    const int u0 = nd.unit_begin + share * per;
     const int u1 = u0 + per < nd.unit_end ? u0 + per : nd.unit_end;
     T Bl[kMaxL];
     T Gs = (T)0;
@@ -1308,6 +1347,27 @@ __global__ void __launch_bounds__(256) mlp_prereduce_kernel(const __grid_constan
 #pragma unroll
             for (int l = 0; l <= kMaxL; ++l)
                 if (l == sl) { Ns[l] += (double)(un.k1 - un.k0); Sm[l] += rsq[2 * u]; Sq[l] += rsq[2 * u + 1]; }
+        }
+    }
+    if (jobs) { // this share of the node's sites
+        const T* val = P.value + (u64)solve * P.n_nodes;
+        const T* feat = P.feat + (u64)solve * P.n_points;
+        const int ns = nd.site_end - nd.site_begin, sper = (ns + nshare - 1) / nshare;
+        const int s0 = nd.site_begin + share * sper;
+        const int s1 = s0 + sper < nd.site_end ? s0 + sper : nd.site_end;
+        for (int si = s0 + (int)threadIdx.x; si < s1; si += (int)blockDim.x) {
+            if (mode != CMB_ALL) {
+                const int cls = P.site_cls[si];
+                if (mode == CMB_PARTIAL ? cls != SITE_MINE : cls != SITE_UPPER) continue;
+            }
+            int l;
+            const T add = site_term<T>(P, si, val, part, feat, &l);
+#pragma unroll
+            for (int q = 0; q < kMaxL; ++q)
+                if (q == l) {
+                    Bl[q] += add;
+                    if (stats) { Ns[q] += 1.0; Sm[q] += (double)add; Sq[q] += (double)add * (double)add; }
+                }
         }
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -1340,7 +1400,7 @@ __global__ void __launch_bounds__(256) mlp_prereduce_kernel(const __grid_constan
             const double v = xw[ww * kCmbStage + threadIdx.x];
             if (as_t) at += (T)v; else a += v;
         }
-        stage[(item * (u64)gridDim.x + blockIdx.x) * kCmbStage + threadIdx.x] = as_t ? (double)at : a;
+        stage[rec * kCmbStage + threadIdx.x] = as_t ? (double)at : a;
     }
 }
 

@@ -25,7 +25,7 @@ MlpPlan::~MlpPlan()
 MlpSharding::~MlpSharding()
 {
     void* ps[] = {d_exec_own, d_upper_sites, d_own_sites, d_owned_nodes, d_crown_nodes, d_crown_leaves,
-                  d_crown_final, d_unit_mine, d_site_cls, d_node_slot};
+                  d_crown_final, d_unit_mine, d_site_cls, d_node_slot, d_crown_jobs, d_crown_job_off};
     for (void* p : ps)
         if (p) cudaFree(p);
 }
@@ -145,6 +145,27 @@ int get_sharding(hdp_context* h, const std::string& plan_key, const MlpPlan& pla
     if ((rc = upload(h, sh->unit_mine, &sh->d_unit_mine)) != HDP_OK) return rc;
     if ((rc = upload(h, sh->site_cls, &sh->d_site_cls)) != HDP_OK) return rc;
     if ((rc = upload(h, sh->node_slot, &sh->d_node_slot)) != HDP_OK) return rc;
+    // shares of the crown partial pass: about two thousand units (a site of this rank counts as sixteen: 1 + K
+    // evaluations of f behind three dependent loads) per block of 256 threads, at most kStageBlocks per node; a
+    // light node (C4: 4312 crown nodes of a few dozen sites) gets none and is walked by its warp of the combine launch
+    sh->crown_job_off.assign(1, 0);
+    for (size_t k = 0; k < sh->crown_nodes.size(); ++k) {
+        const PlanNode& nd = plan.nodes[sh->crown_nodes[k]];
+        const int nu = nd.unit_end - nd.unit_begin;
+        const bool leaf = nu == 1 && nd.site_end == nd.site_begin && (plan.unit_tag[nd.unit_begin] >> 4) == UNIT_WHOLE;
+        int nb = 0;
+        if (!leaf) {
+            long work = nu;
+            for (int si = nd.site_begin; si < nd.site_end; ++si)
+                if (sh->site_cls[si] == SITE_MINE) work += 16;
+            nb = work <= 512 ? 0 : (int)std::min<long>(std::max<long>((work + 2047) / 2048, 1), kStageBlocks);
+        }
+        sh->crown_heavy += nb > 0;
+        for (int b = 0; b < nb; ++b) { sh->crown_jobs.push_back((int32_t)k); sh->crown_jobs.push_back(b); }
+        sh->crown_job_off.push_back((int32_t)(sh->crown_jobs.size() / 2));
+    }
+    if ((rc = upload(h, sh->crown_jobs, &sh->d_crown_jobs)) != HDP_OK) return rc;
+    if ((rc = upload(h, sh->crown_job_off, &sh->d_crown_job_off)) != HDP_OK) return rc;
     h->shardings[key] = sh;
     *out = sh;
     return HDP_OK;
@@ -287,8 +308,17 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
     const int nvec = (d + VEC - 1) / VEC;
     const double min_unit = 8.0; // smallest work unit (path-steps + half the sampler calls)
     const int sms = h->prop.multiProcessorCount;
-    const int nranks = h->nccl_comm ? h->nccl_nranks : 1;
-    const int rank = h->nccl_comm ? h->nccl_rank : 0;
+    int nranks = h->nccl_comm ? h->nccl_nranks : 1;
+    int rank = h->nccl_comm ? h->nccl_rank : 0;
+#ifdef HDP_PHASE_TRACE
+    // debugging build only: the launch chain of rank r of n on ONE GPU, the exchange left out (the value is then
+    // this rank's share, not the solution) — per-launch times of an 8-rank chain at the price of one GPU
+    bool fake_shard = false;
+    if (const char* fr = getenv("HDP_TRACE_FAKE_RANKS")) {
+        int n = 1, r = 0;
+        if (!h->nccl_comm && sscanf(fr, "%d/%d", &r, &n) == 2 && n > 1 && r >= 0 && r < n) { nranks = n; rank = r; fake_shard = true; }
+    }
+#endif
     // a sharded solve is in the latency regime by construction: the work of one rank decides the lane-group width
     const int G = pick_group(gs, nvec, tab.W[L] * (double)n_solves / nranks, n_solves, (double)sms);
     const MlpLaunchers<T> LN = launchers_for<T>(G);
@@ -339,12 +369,12 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
     P.M = M; P.K = K; P.L = L; P.Kp = tab.Kp;
     P.nvec = nvec;
     P.npl = (nvec + G - 1) / G;
-    // Geometry passes that cannot fill the GPU (every pass of a single Allen-Cahn solve: a few hundred to a few
-    // thousand sites per depth) last as long as ONE path-step of one lane group, and the chain has one such pass
-    // per depth: they run a warp per (site, point) whatever the width of the units kernel — d = 100 with two lanes
-    // per point is 25 dependent passes over the row (11-13 us per launch), with a warp it is two.  Rows are plain
-    // arrays of vec-groups, so only their padding depends on the width.  Short rows (d = 10) keep one width.
-    const int Ge = (!um && nvec >= 16 && G < 32) ? 32 : G;
+    // Geometry passes: a pass of the chain that does not fill the GPU lasts as long as ONE path-step of one lane
+    // group — d = 100 with one lane per point is 50 dependent passes over the row (25 us per launch), with a warp
+    // it is two — so every pass picks its own width (launch_expand below), whatever the width of the units kernel.
+    // Rows are plain arrays of vec-groups: only their padding depends on the width.  Short rows (d = 10) and
+    // NVRTC-built modules (compiled for one width) keep the units kernel's.
+    const int Ge = (!um && nvec >= 16 && G < 32) ? 32 : G; // the widest a pass may take
     const int npl_e = (nvec + Ge - 1) / Ge;
     P.dpad = std::max(P.npl * G, npl_e * Ge) * VEC; // every lane may load its full vec-group
     for (int i = 0; i <= kMaxL; ++i) {
@@ -483,24 +513,33 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
         trace("init", gi);
         HDP_CUDA(h, cudaGetLastError());
     }
-    const MlpLaunchers<T> LNe = launchers_for<T>(Ge);
-    MlpParams<T> Pe = P; // the wide geometry pass: the same state, its own row partition
-    Pe.npl = npl_e;
     auto launch_expand = [&](const int32_t* list, int cnt, int count_hits, const int32_t* list2 = nullptr, int cnt2 = 0,
                              int count_hits2 = 0) -> int {
         if (cnt + cnt2 == 0) return HDP_OK;
         const uint64_t site_items = (uint64_t)(cnt + cnt2) * n_solves;
         // one lane group per (site, solve, point) in a short pass, per (site, solve) in a long one (mlp_expand_kernel)
         uint64_t groups = site_items * (uint64_t)(site_items < kExpandSplitBelow ? 1 + tab.Kp : 1);
-        // a warp per item while all of them are resident at once
-        const bool wide = Ge != G && groups * (uint64_t)Ge <= (uint64_t)sms * 12 * block;
-        const int Gx = wide ? Ge : G;
+        // width of this pass: waves of resident lane groups x passes over a lane's share of the row (three
+        // vec-groups per pass on long shares), the narrower on a tie
+        int Gx = G;
+        {
+            const double cap = (double)sms * 12 * block;
+            double best = 0;
+            for (int g = G; g <= Ge; g *= 2) {
+                const int npl_g = (nvec + g - 1) / g;
+                const double cost = ceil((double)groups * g / cap) * (npl_g >= 12 ? (npl_g + 2) / 3 * 1.5 : (double)npl_g);
+                if (g == G || cost < best) { best = cost; Gx = g; }
+            }
+        }
         int ge = (int)std::min<uint64_t>((groups * Gx + block - 1) / block, (uint64_t)sms * 12);
         if (um) {
             void* args[7] = {(void*)&P, (void*)&list, (void*)&cnt, (void*)&count_hits, (void*)&list2, (void*)&cnt2, (void*)&count_hits2};
             HDP_CUDA(h, launch_chained_module((const void*)um->expand, dim3(ge), dim3(block), 0, h->stream, args));
-        } else if (wide) HDP_CUDA(h, LNe.expand(Pe, list, cnt, count_hits, list2, cnt2, count_hits2, ge, block, h->stream));
-        else HDP_CUDA(h, LN.expand(P, list, cnt, count_hits, list2, cnt2, count_hits2, ge, block, h->stream));
+        } else if (Gx != G) {
+            MlpParams<T> Px = P; // the same state, its own partition of the rows
+            Px.npl = (nvec + Gx - 1) / Gx;
+            HDP_CUDA(h, launchers_for<T>(Gx).expand(Px, list, cnt, count_hits, list2, cnt2, count_hits2, ge, block, h->stream));
+        } else HDP_CUDA(h, LN.expand(P, list, cnt, count_hits, list2, cnt2, count_hits2, ge, block, h->stream));
         h->launches++;
         trace("expand", cnt + cnt2);
         return HDP_OK;
@@ -518,7 +557,7 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
             double* stage = (double*)ensure(h, hdp_context::B_R, items * kStageBlocks * kCmbStage * sizeof(double));
             if (!stage) return HDP_ERR_ALLOC;
             HDP_CUDA(h, launch_chained(mlp_prereduce_kernel<T>, dim3(kStageBlocks, (unsigned)items), dim3(256), 0, h->stream, P, list,
-                                       cmode, stage));
+                                       cmode, stage, (const int2*)nullptr));
             h->launches++;
             trace("prereduce", cnt);
             Pc.stage = stage;
@@ -527,6 +566,9 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
         for (int q = 0; q < cnt; ++q) {
             const PlanNode& nd = plan->nodes[host_list[q]];
             const int nu = nd.unit_end - nd.unit_begin;
+            // (CMB_FINAL walks only the replicated upper sites of a node, but sizing its lanes by those alone was
+            // slower — Allen-Cahn M=8, L=6 on 8 ranks: 18 -> 36 us and 20 -> 50 us for the last two passes: these
+            // passes are latency-bound walks, lanes are free)
             const int nus = (staged && nu > kBigNode) ? kStageBlocks : nu, ns = nd.site_end - nd.site_begin;
             most = std::max(most, nus + ns);
             most_weight = std::max(most_weight, nus + ns * (1 + tab.Kp));
@@ -597,10 +639,35 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
         }
         // (the root first and alone: it has thousands of children and takes a block of lanes, the other crown
         // nodes a few lanes each — one launch sized for the root spent 95 us on 4313 blocks of 512 threads)
-        if ((rc = launch_combine((const int32_t*)sh->d_crown_nodes, sh->crown_nodes.data(), 1, CMB_PARTIAL)) != HDP_OK) return rc;
-        if ((rc = launch_combine((const int32_t*)sh->d_crown_nodes + 1, sh->crown_nodes.data() + 1,
-                                 (int)sh->crown_nodes.size() - 1, CMB_PARTIAL)) != HDP_OK)
-            return rc;
+        const int n_jobs = (int)(sh->crown_jobs.size() / 2);
+        // (one heavy node only — the root of C4, its other 4312 crown nodes are light — gains nothing over root first, rest after)
+        if (!um && n_solves <= 65535 && sh->crown_heavy >= 2) {
+            // every crown node in one pass: its units and this rank's sites summed by the node's share of blocks
+            // (crown_jobs), then a warp per node adds the records up and writes the node's slot of the exchange buffer
+            double* stage = (double*)ensure(h, hdp_context::B_R, (size_t)n_solves * n_jobs * kCmbStage * sizeof(double));
+            if (!stage) return HDP_ERR_ALLOC;
+            MlpParams<T> Pj = P;
+            Pj.stage = stage;
+            Pj.stage_off = (const int32_t*)sh->d_crown_job_off;
+            Pj.stage_jobs = n_jobs;
+            const int32_t* clist = (const int32_t*)sh->d_crown_nodes;
+            const int cnt = (int)sh->crown_nodes.size();
+            HDP_CUDA(h, launch_chained(mlp_prereduce_kernel<T>, dim3((unsigned)n_jobs, (unsigned)n_solves), dim3(256), 0, h->stream, Pj,
+                                       clist, (int)CMB_PARTIAL, stage, (const int2*)sh->d_crown_jobs));
+            h->launches++;
+            trace("prereduce_jobs", n_jobs);
+            const int nl = 32, cb = 128;
+            const uint64_t tot = (uint64_t)cnt * n_solves * nl;
+            HDP_CUDA(h, launch_chained(mlp_combine_kernel<T>, dim3((unsigned)((tot + cb - 1) / cb)), dim3(cb), 0, h->stream, Pj, clist, cnt,
+                                       nl, (int)CMB_PARTIAL));
+            h->launches++;
+            trace("combine_partial", cnt);
+        } else {
+            if ((rc = launch_combine((const int32_t*)sh->d_crown_nodes, sh->crown_nodes.data(), 1, CMB_PARTIAL)) != HDP_OK) return rc;
+            if ((rc = launch_combine((const int32_t*)sh->d_crown_nodes + 1, sh->crown_nodes.data() + 1,
+                                     (int)sh->crown_nodes.size() - 1, CMB_PARTIAL)) != HDP_OK)
+                return rc;
+        }
         HDP_CUDA(h, cudaEventRecord(h->evp[1], h->stream)); // (the local combine counts as unit work)
         if (use_peer) {
             // the library's own exchange over peer memory: push, flag, sum in rank order and the scatter of the
@@ -617,6 +684,9 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
             trace("exchange", (int)x_count);
             HDP_CUDA(h, cudaEventRecord(h->evp[2], h->stream));
         } else {
+#ifdef HDP_PHASE_TRACE
+            if (!fake_shard)
+#endif
             rc = nccl_allreduce_f64_device(h, P.xbuf, x_count);
             if (rc != HDP_OK) return rc;
             trace("allreduce", (int)x_count);
@@ -708,6 +778,9 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
         cudaMemsetAsync(h->d_flags, 0, sizeof(flags2), h->stream);
         return set_err(h, HDP_ERR_UNSUPPORTED, "internal: the units kernel launched does not match the mode of the problem");
     }
+#ifdef HDP_PHASE_TRACE
+    if (fake_shard) return HDP_OK;
+#endif
     if (sh) { // every rank must have described the same call: the all-reduced hash is nranks times mine
         for (int q = 0; q < 4; ++q)
             if (tail_host[q] != (double)nranks * (double)((my_hash >> (16 * q)) & 0xffffu))

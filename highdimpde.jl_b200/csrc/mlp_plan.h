@@ -97,11 +97,16 @@ struct MlpSharding {
     std::vector<int8_t> site_cls;             // per site: 0 upper, 1 at or below an ownership root of mine, 2 of another rank
     std::vector<int32_t> node_slot;           // per node: slot in the exchange buffer, -1 below an ownership root
     int n_slots = 0;
+    // crown partial pass: node crown_nodes[k] is summed by crown_job_off[k + 1] - crown_job_off[k] blocks (its units
+    // and this rank's sites shared out among them; 0 for a whole-call leaf), job j = (k, share) — k_mlp_host.cu
+    std::vector<int32_t> crown_job_off;       // size crown_nodes.size() + 1
+    std::vector<int32_t> crown_jobs;          // pairs (k, share)
+    int crown_heavy = 0;                      // crown nodes with jobs
     double load_max = 0, load_mean = 0;       // modelled work of the busiest rank / the mean
     // device copies (owned by the handle's cache; freed in the destructor)
     void *d_exec_own = nullptr, *d_upper_sites = nullptr, *d_own_sites = nullptr, *d_owned_nodes = nullptr,
          *d_crown_nodes = nullptr, *d_crown_leaves = nullptr, *d_crown_final = nullptr, *d_unit_mine = nullptr,
-         *d_site_cls = nullptr, *d_node_slot = nullptr;
+         *d_site_cls = nullptr, *d_node_slot = nullptr, *d_crown_jobs = nullptr, *d_crown_job_off = nullptr;
     ~MlpSharding();
 };
 // own_items: ownership roots per rank to aim for (0: the default, 64; tests lower it to nest explicit sites below a root)
