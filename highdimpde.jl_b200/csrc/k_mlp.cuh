@@ -1000,7 +1000,9 @@ constexpr int kCmbStage = kMaxL + 1 + 3 * (kMaxL + 1);
 constexpr int kBigNode = 4096;   // units of one node above which several blocks share the sum
 constexpr unsigned long long kExpandSplitBelow = 32768; // (sites x solves) of a geometry pass below which its points are spread over lane groups
 constexpr int kStageBlocks = 64; // blocks per such node
-template <typename T>
+// STATS = false: a launch that cannot contain the root of a solve that wants an error bar — the 21 doubles of the
+// level statistics then never exist (they cost the kernel 42 registers and a stack frame whoever the node is).
+template <typename T, bool STATS = true>
 __device__ __forceinline__ void combine_item(const MlpParams<T>& P, const int32_t* list, u64 item, int lane, int nl,
                                              unsigned mask = 0xffffffffu, int mode = CMB_ALL, double* xwarp = nullptr)
 {
@@ -1015,7 +1017,7 @@ __device__ __forceinline__ void combine_item(const MlpParams<T>& P, const int32_
     const int slot = P.node_slot ? P.node_slot[nidx] : -1;
     const bool leaf = nd.unit_end - nd.unit_begin == 1 && nd.site_end == nd.site_begin &&
                       (P.unit_tag[nd.unit_begin] >> 4) == UNIT_WHOLE;
-    const bool stats = nidx == 0 && P.lvstat != nullptr;
+    const bool stats = STATS && nidx == 0 && P.lvstat != nullptr;
     double* lv = stats ? P.lvstat + (u64)solve * (3 * (kMaxL + 1)) : nullptr;
     const double* rsq = stats ? P.rootsq + (u64)solve * P.rootsq_stride : nullptr;
     T result;
@@ -1293,7 +1295,7 @@ __global__ void __launch_bounds__(HDP_MLP_BLOCK, Tune<U>::MB) mlp_units_kernel(c
 // stage_off[k + 1] - stage_off[k] shares of that node) sums its share of the node's units and of its sites (the
 // f-terms of this rank's ownership roots) — the combine launch that follows only adds the records up, so the
 // root, whose thousands of sites one block walked through dependent loads in 33 us, costs what any node costs.
-template <typename T>
+template <typename T, bool STATS = true>
 __global__ void __launch_bounds__(256, 3) mlp_prereduce_kernel(const __grid_constant__ MlpParams<T> P, const int32_t* list, int mode,
                                                             double* stage, const int2* jobs)
 {
@@ -1319,7 +1321,7 @@ __global__ void __launch_bounds__(256, 3) mlp_prereduce_kernel(const __grid_cons
     const int nu = nd.unit_end - nd.unit_begin;
     if (!jobs && nu <= kBigNode) return;
     const double* part = P.partial + (u64)solve * P.n_units;
-    const bool stats = nidx == 0 && P.lvstat != nullptr;
+    const bool stats = STATS && nidx == 0 && P.lvstat != nullptr;
     const double* rsq = stats ? P.rootsq + (u64)solve * P.rootsq_stride : nullptr;
     const int per = (nu + nshare - 1) / nshare;
     const int u0 = nd.unit_begin + share * per;
@@ -1406,7 +1408,7 @@ __global__ void __launch_bounds__(256, 3) mlp_prereduce_kernel(const __grid_cons
 
 // nl lanes (a power of two, 1..32) share one (node, solve): 32 where nodes have many children (the
 // root of a deeply cut tree has thousands), 4 where they have a handful
-template <typename T>
+template <typename T, bool STATS = true>
 __global__ void __launch_bounds__(512) mlp_combine_kernel(const __grid_constant__ MlpParams<T> P, const int32_t* list, int count,
                                                           int nl, int mode)
 {
@@ -1424,7 +1426,7 @@ __global__ void __launch_bounds__(512) mlp_combine_kernel(const __grid_constant_
     // the shuffles of a node stay inside its own nl lanes: the root's statistics are reduced by its group alone
     const int lane = (int)(t % (unsigned)nl);
     const unsigned mask = nl >= 32 ? 0xffffffffu : (((1u << nl) - 1u) << ((threadIdx.x & 31) - lane));
-    combine_item<T>(P, list, gid, lane, nl, mask, mode, xwarp);
+    combine_item<T, STATS>(P, list, gid, lane, nl, mask, mode, xwarp);
 }
 
 // sharded solve: the all-reduced values of the whole-call leaves below upper sites go back to partial[],

@@ -374,9 +374,12 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
     // it is two — so every pass picks its own width (launch_expand below), whatever the width of the units kernel.
     // Rows are plain arrays of vec-groups: only their padding depends on the width.  Short rows (d = 10) and
     // NVRTC-built modules (compiled for one width) keep the units kernel's.
-    const int Ge = (!um && nvec >= 16 && G < 32) ? 32 : G; // the widest a pass may take
+    // (a batch keeps its rows as they were — its geometry passes fill the GPU at any width, and padding d = 100 to
+    // 128 put the start points of the 32 units of a warp 1024 bytes apart, one L1 set: C2 lost 6 %)
+    const int Ge = (!um && nvec >= 16 && G < 32 && n_solves < 8) ? 32 : G; // the widest a pass may take
     const int npl_e = (nvec + Ge - 1) / Ge;
     P.dpad = std::max(P.npl * G, npl_e * Ge) * VEC; // every lane may load its full vec-group
+    if (Ge != G && ((size_t)P.dpad * sizeof(T)) % 512 == 0) P.dpad += 16 / (int)sizeof(T); // rows never a power of two apart
     for (int i = 0; i <= kMaxL; ++i) {
         P.C[i] = tab.C[i]; P.R[i] = tab.R[i]; P.S[i] = tab.S[i];
         P.cs[i] = tab.cs[i]; P.rs[i] = tab.rs[i]; P.ss[i] = tab.ss[i];
@@ -547,6 +550,10 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
     // lanes per (node, solve) of a combine launch: a warp where some node has many children, 4 lanes otherwise
     auto launch_combine = [&](const int32_t* list, const int32_t* host_list, int cnt, int cmode) -> int {
         if (cnt == 0) return HDP_OK;
+        // the error bar is gathered at the root: only a launch that holds node 0 carries the level statistics
+        bool with_stats = false;
+        if (want_se)
+            for (int q = 0; q < cnt; ++q) with_stats |= host_list[q] == 0;
         int most = 0, most_units = 0, most_weight = 0;
         for (int q = 0; q < cnt; ++q) most_units = std::max(most_units, plan->nodes[host_list[q]].unit_end - plan->nodes[host_list[q]].unit_begin);
         // nodes with very many units: several blocks each sum a share first (mlp_prereduce_kernel)
@@ -556,8 +563,12 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
         if (staged) {
             double* stage = (double*)ensure(h, hdp_context::B_R, items * kStageBlocks * kCmbStage * sizeof(double));
             if (!stage) return HDP_ERR_ALLOC;
-            HDP_CUDA(h, launch_chained(mlp_prereduce_kernel<T>, dim3(kStageBlocks, (unsigned)items), dim3(256), 0, h->stream, P, list,
-                                       cmode, stage, (const int2*)nullptr));
+            if (with_stats)
+                HDP_CUDA(h, launch_chained(mlp_prereduce_kernel<T, true>, dim3(kStageBlocks, (unsigned)items), dim3(256), 0, h->stream, P,
+                                           list, cmode, stage, (const int2*)nullptr));
+            else
+                HDP_CUDA(h, launch_chained(mlp_prereduce_kernel<T, false>, dim3(kStageBlocks, (unsigned)items), dim3(256), 0, h->stream, P,
+                                           list, cmode, stage, (const int2*)nullptr));
             h->launches++;
             trace("prereduce", cnt);
             Pc.stage = stage;
@@ -587,7 +598,8 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
         if (um) { // f is applied in the combine too: the user module's build of it
             void* args[5] = {(void*)&Pc, (void*)&list, (void*)&cnt, (void*)&nl, (void*)&cmode};
             HDP_CUDA(h, launch_chained_module((const void*)um->combine, dim3(gc), dim3(cb), 0, h->stream, args));
-        } else HDP_CUDA(h, launch_chained(mlp_combine_kernel<T>, dim3(gc), dim3(cb), 0, h->stream, Pc, list, cnt, nl, cmode));
+        } else if (with_stats) HDP_CUDA(h, launch_chained(mlp_combine_kernel<T, true>, dim3(gc), dim3(cb), 0, h->stream, Pc, list, cnt, nl, cmode));
+        else HDP_CUDA(h, launch_chained(mlp_combine_kernel<T, false>, dim3(gc), dim3(cb), 0, h->stream, Pc, list, cnt, nl, cmode));
         h->launches++;
         trace(cmode == CMB_ALL ? "combine_all" : (cmode == CMB_PARTIAL ? "combine_partial" : "combine_final"), cnt);
         HDP_CUDA(h, cudaGetLastError());
@@ -652,14 +664,22 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
             Pj.stage_jobs = n_jobs;
             const int32_t* clist = (const int32_t*)sh->d_crown_nodes;
             const int cnt = (int)sh->crown_nodes.size();
-            HDP_CUDA(h, launch_chained(mlp_prereduce_kernel<T>, dim3((unsigned)n_jobs, (unsigned)n_solves), dim3(256), 0, h->stream, Pj,
-                                       clist, (int)CMB_PARTIAL, stage, (const int2*)sh->d_crown_jobs));
+            if (want_se)
+                HDP_CUDA(h, launch_chained(mlp_prereduce_kernel<T, true>, dim3((unsigned)n_jobs, (unsigned)n_solves), dim3(256), 0, h->stream,
+                                           Pj, clist, (int)CMB_PARTIAL, stage, (const int2*)sh->d_crown_jobs));
+            else
+                HDP_CUDA(h, launch_chained(mlp_prereduce_kernel<T, false>, dim3((unsigned)n_jobs, (unsigned)n_solves), dim3(256), 0, h->stream,
+                                           Pj, clist, (int)CMB_PARTIAL, stage, (const int2*)sh->d_crown_jobs));
             h->launches++;
             trace("prereduce_jobs", n_jobs);
             const int nl = 32, cb = 128;
             const uint64_t tot = (uint64_t)cnt * n_solves * nl;
-            HDP_CUDA(h, launch_chained(mlp_combine_kernel<T>, dim3((unsigned)((tot + cb - 1) / cb)), dim3(cb), 0, h->stream, Pj, clist, cnt,
-                                       nl, (int)CMB_PARTIAL));
+            if (want_se)
+                HDP_CUDA(h, launch_chained(mlp_combine_kernel<T, true>, dim3((unsigned)((tot + cb - 1) / cb)), dim3(cb), 0, h->stream, Pj, clist,
+                                           cnt, nl, (int)CMB_PARTIAL));
+            else
+                HDP_CUDA(h, launch_chained(mlp_combine_kernel<T, false>, dim3((unsigned)((tot + cb - 1) / cb)), dim3(cb), 0, h->stream, Pj, clist,
+                                           cnt, nl, (int)CMB_PARTIAL));
             h->launches++;
             trace("combine_partial", cnt);
         } else {
