@@ -306,7 +306,7 @@ def run_ours(args, rank, world, local_rank):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "solves_per_gpu_per_step": n_local, "global_solves_per_step": n_total,
                        "parallelism": f"headline: independent solves sharded over {world} rank(s), no data-path collective; "
-                                      "extra.strong (N > 1): ONE solve sharded by subtree, one ncclAllReduce of a double per crown node",
+                                      "extra.strong (N > 1): ONE solve sharded by subtree, one exchange of a double per crown node (the library's kernel over NVLink peer windows; ncclAllReduce as fallback)",
                        "l2": "256 MB flush between steps (untimed); the path is compute-bound, inputs are d doubles",
                        "rng": "Philox4x32-7 (fixed key, seed and consumption ordinal in the counter) + table-driven fp64 Box-Muller, generated in registers"},
             "reflected_path_steps_per_sec": value * PATH_STEPS_PER_SOLVE,
@@ -374,8 +374,9 @@ def strong_workloads(H):
 
 
 def bench_strong(torch, dist, H, HD, local_rank, rank, world, reps=5):
-    """One solve sharded over all ranks through the library's own NCCL communicator (hdp_comm_init_rank): bottom
-    subtrees owned by one rank each, ONE ncclAllReduce of a double per crown node, the crown finished redundantly.
+    """One solve sharded over all ranks of the library's communicator (hdp_comm_init_rank + hdp_peer_window_*): bottom
+    subtrees owned by one rank each, ONE exchange of a double per crown node — the library's exchange kernel over
+    NVLink peer memory (`exchange: "peer"`; ncclAllReduce where no peer path exists) —, the crown finished redundantly.
     Time = CUDA events on the library's stream around the whole call (all-reduce included), max over ranks, best
     of `reps`; the 1-GPU time is the same solve on a handle without communicator (rank 0).  Results must agree
     to 1e-12 (they differ only in the order of a few sums)."""
@@ -394,10 +395,16 @@ def bench_strong(torch, dist, H, HD, local_rank, rank, world, reps=5):
         for r in range(reps + 1):
             dist.barrier()
             torch.cuda.synchronize()
-            u, st = H._ml_picard_batch(prob, alg, n_solves=1, seed=seed, handle=hc, std_err=True)
+            u, st = H._ml_picard_batch(prob, alg, n_solves=1, seed=seed, handle=hc)
             ms = HD.max_over_ranks(st["device_ms"])
             if r > 0 and (bestn is None or ms < bestn):
                 bestn, un, stn = ms, float(u[0]), st
+        # (the error bar is an optional output — cfg.std_err_out — and neither timed solve asks for it; one more
+        # sharded call does, so that the line carries the Monte-Carlo standard error of the value)
+        dist.barrier()
+        use, stse = H._ml_picard_batch(prob, alg, n_solves=1, seed=seed, handle=hc, std_err=True)
+        assert abs(float(use[0]) - un) <= 1e-13 * abs(un)
+        stn = dict(stn, std_err=stse["std_err"])
         ms1 = HD.min_over_ranks(best1)  # (every rank timed the 1-GPU solve; identical GPUs)
         alln = HD.all_gather_object(un)
         out[name] = {"path_steps": st1["path_steps"], "ms_1gpu": ms1, "ms_sharded": bestn, "speedup": ms1 / bestn,

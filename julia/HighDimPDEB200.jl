@@ -165,6 +165,30 @@ function check(h::Handle, rc::Cint)
     error("libhdpde_b200 error $rc: $msg")
 end
 
+# ------------------------------------------------------------------ one solve over several GPUs
+# (include/hdpde.h: hdp_nccl_unique_id / hdp_comm_init_rank / hdp_peer_window_*; the bytes travel by whatever the
+# host program uses between its processes — MPI.jl, Distributed.jl — see INTEGRATION.md §3)
+function nccl_unique_id()
+    id = Vector{UInt8}(undef, 128)
+    rc = ccall((:hdp_nccl_unique_id, libhdp), Cint, (Ptr{UInt8},), id)
+    rc == 0 || error("hdp_nccl_unique_id: " * unsafe_string(ccall((:hdp_last_error, libhdp), Cstring, (Ptr{Cvoid},), C_NULL)))
+    id
+end
+comm_init_rank!(h::Handle, id::Vector{UInt8}, nranks::Integer, rank::Integer) =
+    check(h, ccall((:hdp_comm_init_rank, libhdp), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Cint, Cint), h.ptr, id, nranks, rank))
+"64-byte CUDA-IPC handle of this rank's exchange window (gather them in rank order, then `peer_window_attach!`)"
+function peer_window_export(h::Handle)
+    out = Vector{UInt8}(undef, 64)
+    check(h, ccall((:hdp_peer_window_export, libhdp), Cint, (Ptr{Cvoid}, Ptr{UInt8}), h.ptr, out))
+    out
+end
+"`handles`: nranks × 64 bytes in rank order.  Returns false (instead of throwing) when a peer cannot be mapped: the caller then detaches on every rank."
+function peer_window_attach!(h::Handle, handles::Vector{UInt8}, nranks::Integer, rank::Integer)
+    length(handles) == 64 * nranks || error("peer_window_attach!: expected $(64 * nranks) bytes")
+    ccall((:hdp_peer_window_attach, libhdp), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Cint, Cint), h.ptr, handles, nranks, rank) == 0
+end
+peer_window_detach!(h::Handle) = check(h, ccall((:hdp_peer_window_detach, libhdp), Cint, (Ptr{Cvoid},), h.ptr))
+
 # ------------------------------------------------------------------ descriptors
 sampler_desc(::NoSampling, keep) = HdpSampler(0, 0, 1, 0, 0.0, 0.0, 0.0, C_NULL, C_NULL)
 function sampler_desc(s::UniformSampling, keep)

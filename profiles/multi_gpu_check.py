@@ -82,6 +82,28 @@ if rank == 0:
           f"units={sN['n_units']} (1 GPU: {s1['n_units']}) device_ms N-GPU={dev:.3f} 1-GPU={min(t_solo):.3f} "
           f"speedup={min(t_solo) / dev:.2f}x bounces={sN['bounces']} exchange={sN['exchange_kind']} exchange_bytes={sN['exchange_bytes']} (nccl: {sC['device_ms']:.3f} ms, allreduce {sC['phase_ms']['allreduce']:.3f}) phase_ms={ {k: round(v, 3) for k, v in sN['phase_ms'].items()} }")
 
+# 2b. a local problem whose crown holds many heavy nodes (Allen-Cahn d=100, M=8, L=5: the crown partial pass runs by
+# per-node shares, mlp_prereduce_kernel with jobs), with the error bar: value and standard error against one GPU
+Dh = 100
+probh = H.ParabolicPDEProblem(0.0, 1.0, np.zeros(Dh), (0.0, 0.5), g=H.ExpSumSq(0.25), f=H.FAllenCahn(1.0),
+                              neumann_bc=(np.full(Dh, -0.5), np.full(Dh, 0.5)))
+algh = H.MLP(M=8, L=5, K=10)
+for se in (False, True):
+    ua, sa = H._ml_picard_batch(probh, algh, n_solves=1, seed=31, handle=h_solo, std_err=se)
+    ub, sb = H._ml_picard_batch(probh, algh, n_solves=1, seed=31, handle=h, std_err=se)
+    uc, sc = H._ml_picard_batch(probh, algh, n_solves=1, seed=31, handle=h_nccl, std_err=se)
+    assert abs(ub[0] - ua[0]) <= 1e-12 * abs(ua[0]), (ub, ua)
+    assert abs(uc[0] - ub[0]) <= 1e-14 * abs(ub[0]), (uc, ub)
+    assert sb["bounces"] == sa["bounces"] == sc["bounces"]
+    allh = HD.all_gather_object(float(ub[0]))
+    assert all(v == allh[0] for v in allh), allh
+    if se:
+        assert abs(sb["std_err"][0] - sa["std_err"][0]) <= 1e-10 * sa["std_err"][0], (sb["std_err"], sa["std_err"])
+        assert sb["level_n"] == sa["level_n"], (sb["level_n"], sa["level_n"])
+if rank == 0:
+    print(f"[multi] Allen-Cahn d=100 M=8 L=5 sharded: u={ub[0]:.15g} (1 GPU {ua[0]:.15g}) std_err={sb['std_err'][0]:.3e} exchange={sb['exchange_kind']} "
+          f"device_ms {sb['device_ms']:.3f} (1 GPU {sa['device_ms']:.3f})")
+
 # weak scaling: independent C2 solves
 D = 100
 prob2 = H.ParabolicPDEProblem(0.0, 1.0, np.zeros(D), (0.0, 0.5), g=H.ExpSumSq(0.25), f=H.FAllenCahn(1.0),

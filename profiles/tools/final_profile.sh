@@ -1,13 +1,14 @@
 #!/bin/bash
 # final captures of the round (one GPU).  Plain runs first, ncu after each has exited 0.
 set -x
-R=r2u
+R=r2z
 python -m pytest tests -m gpu -x -q > gpurun_out/${R}_pytest.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/${R}_pytest.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${R}_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/${R}_smoke.log
 python bench.py --steps 10 --warmup 3 > gpurun_out/${R}_bench_1gpu.json 2> gpurun_out/${R}_bench.err; echo "bench rc=$?"
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${R}_bench_reference_arm.json 2>> gpurun_out/${R}_bench.err; echo "ref rc=$?"
 python profiles/sweep.py > gpurun_out/${R}_sweep.txt 2>&1
 python profiles/sde_sweep.py > gpurun_out/${R}_sde_sweep.txt 2>&1
+python profiles/tools/single_solve_ab.py 15 > gpurun_out/${R}_single_solves.txt 2>&1
 for w in "mlp 4096" "c5 64" "c1 4096" "sde" "ens"; do
   tag=$(echo $w | cut -d' ' -f1)
   python profiles/prof_workload.py $w > gpurun_out/${R}_plain_$tag.log 2>&1 || { echo "plain $tag failed"; continue; }
