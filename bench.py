@@ -158,7 +158,7 @@ def run_reference(args, rank, world):
     pb, _k = prob.to_c()
     sm, _k2 = alg.mc_sample._descriptor(D)
     cores = os.cpu_count() or 1
-    n_sample = max(cores * 4, 32)  # bounded sample of the same workload per step
+    n_sample = max(cores * 16, 64)  # bounded sample of the same workload per step (~0.6 s; dynamic schedule over the threads)
     for w in range(args.warmup):
         O.bench_solves(pb, sm, M, L, K, prob.x, cores, cores, seed=w)
     tot = 0.0

@@ -410,12 +410,15 @@ typedef struct bench_job {
     uint64_t seed;
     double* u_out;
     int rc;
+    int* next; /* shared: the next solve nobody has taken yet (dynamic schedule: no thread waits on a static share) */
 } bench_job;
 
 static void* bench_main(void* arg)
 {
     bench_job* j = (bench_job*)arg;
-    for (int i = j->tid; i < j->n_solves; i += j->nthreads) {
+    for (;;) {
+        const int i = __atomic_fetch_add(j->next, 1, __ATOMIC_RELAXED);
+        if (i >= j->n_solves) break;
         hdp_oracle_rng* g = hdp_oracle_rng_xoshiro(j->seed + (uint64_t)i, 0,
                                                    j->sm && j->sm->kind == HDP_SAMPLER_NORMAL);
         double u = 0;
@@ -435,9 +438,10 @@ int hdp_oracle_bench_solves_f64(const hdp_problem* pb, const hdp_sampler* sm, in
     bench_job* jobs = (bench_job*)calloc((size_t)nthreads, sizeof(bench_job));
     pthread_t* th = (pthread_t*)calloc((size_t)nthreads, sizeof(pthread_t));
     struct timespec t0, t1;
+    int next = 0;
     clock_gettime(CLOCK_MONOTONIC, &t0);
     for (int t = 0; t < nthreads; ++t) {
-        jobs[t] = (bench_job){pb, sm, M, L, K, n_solves, nthreads, t, x, seed, u_out, 0};
+        jobs[t] = (bench_job){pb, sm, M, L, K, n_solves, nthreads, t, x, seed, u_out, 0, &next};
         pthread_create(&th[t], NULL, bench_main, &jobs[t]);
     }
     int rc = 0;
