@@ -53,7 +53,7 @@ template <> MlpLaunchers<float> launchers_for<float>(int G)
 // bookkeeping is spread over more coordinate work.
 // Latency regime: a narrow group makes every work unit take longer, so when there are few
 // path-steps per resident lane group (or only a handful of solves, whose trees cut into coarse
-// units) the group is widened until each resident group has about a dozen path-steps to do.
+// units) the group is widened until each resident group has about five path-steps to do.
 // `forced` (cfg->group_size) overrides the rule; results never depend on the width.
 int pick_group(int forced, int nvec, double path_steps_total, int n_solves, double sms)
 {
@@ -72,7 +72,10 @@ int pick_group(int forced, int nvec, double path_steps_total, int n_solves, doub
     while (G < 32 && (nvec + G - 1) / G > cap) G *= 2;
     // (a batch never widens to the point where lanes of a group idle: 2 G <= nvec)
     const int gmax = n_solves < 8 ? nvec : nvec / 2;
-    while (G < 32 && G < gmax && path_steps_total < 12.0 * resident_groups(G)) G *= 2;
+    // (five path-steps per resident lane group: re-measured on the share of one rank of eight of Allen-Cahn d=100, M=8,
+    // L=5 — 148 k path-steps — where the earlier twelve widened to 16 lanes: 0.31 ms against 0.26 with four,
+    // profiles/r2z_fake8_sweep.txt; the batch sizes of profiles/r1k_group_sweep.txt keep their best or second-best width)
+    while (G < 32 && G < gmax && path_steps_total < 5.0 * resident_groups(G)) G *= 2;
     return G;
 }
 
@@ -331,7 +334,10 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
     const size_t dyn_smem = (size_t)block * sizeof(Frame<T>);
     // long rows: three vec-groups per pass, very long rows four (Tune<U>, k_mlp.cuh)
     const int npl_ = (nvec + G - 1) / G;
-    const int long_rows = npl_ >= 48 ? 2 : (npl_ >= 12 ? 1 : 0);
+    int long_rows = npl_ >= 48 ? 2 : (npl_ >= 12 ? 1 : 0);
+#ifdef HDP_PHASE_TRACE
+    if (const char* lr = getenv("HDP_TRACE_LONG_ROWS")) long_rows = atoi(lr); // debugging build only: force the variant
+#endif
     int bps = 0;
     if (um) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, (const void*)um->units, block, dyn_smem) != cudaSuccess) {
