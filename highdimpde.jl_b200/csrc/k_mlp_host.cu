@@ -66,10 +66,14 @@ int pick_group(int forced, int nvec, double path_steps_total, int n_solves, doub
     // lane — are in the throughput regime like a batch: 7.85 ms with one lane per point against 9.29 ms with four)
     // In between (8..64 path-steps per resident lane: the same solve on 8 GPUs, 2.4 M path-steps per rank) rows of
     // up to 32 vec-groups per lane: 1.40 ms with two lanes per point, 1.54 with four, 1.66 with one.
+    // (re-measured on the shares of one rank of 2, 4 and 8, profiles/r2z_fake*_minunit.txt: from 32 path-steps per
+    // resident lane one lane per d=100 point once the cut may go down to four path-steps per unit — 1.19 -> 1.14 ms for
+    // a rank of eight of M=8, L=6 —, and a full warp per point only for rows beyond 32 vec-groups per lane or almost
+    // no work per lane: d=1000 with 16 lanes is 3-8 % faster than with 32 on 2, 4 and 8 ranks)
     const double per_lane = path_steps_total / resident_groups(1);
-    const int cap = n_solves >= 8 || per_lane >= 64.0 ? 64 : (per_lane >= 8.0 ? 32 : 16);
+    const int cap = n_solves >= 8 || per_lane >= 32.0 ? 64 : (per_lane >= 8.0 ? 32 : 16);
     int G = 1;
-    while (G < 32 && (nvec + G - 1) / G > cap) G *= 2;
+    while (G < 32 && (nvec + G - 1) / G > ((G >= 16 && per_lane >= 1.5) ? std::max(cap, 32) : cap)) G *= 2;
     // (a batch never widens to the point where lanes of a group idle: 2 G <= nvec)
     const int gmax = n_solves < 8 ? nvec : nvec / 2;
     // (five path-steps per resident lane group: re-measured on the share of one rank of eight of Allen-Cahn d=100, M=8,
@@ -309,7 +313,10 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
     constexpr int VEC = Tr<T>::VEC;
     const int d = prob->d;
     const int nvec = (d + VEC - 1) / VEC;
-    const double min_unit = 8.0; // smallest work unit (path-steps + half the sampler calls)
+    double min_unit = 8.0; // smallest work unit (path-steps + half the sampler calls)
+#ifdef HDP_PHASE_TRACE
+    if (const char* mu = getenv("HDP_TRACE_MIN_UNIT")) min_unit = atof(mu); // debugging build only
+#endif
     const int sms = h->prop.multiProcessorCount;
     int nranks = h->nccl_comm ? h->nccl_nranks : 1;
     int rank = h->nccl_comm ? h->nccl_rank : 0;
@@ -356,6 +363,14 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
     double target = cfg->target_units > 0 ? (double)cfg->target_units : resident_groups * oversub * nranks;
     const double total_work = tab.W[L] * (double)n_solves;
     double thresh = total_work / target;
+    // A single solve (or a handful) whose wanted cut is finer than the smallest unit: where the coarser cut still gives
+    // every resident lane group a unit, halving the smallest unit balances the groups better (a rank of eight of
+    // Allen-Cahn d=1000, M=8: 0.71 -> 0.64 ms with 16 lanes; of two or four of d=100, M=8, L=5: 8-12 %); where it
+    // does not (fewer units than groups: the time is one unit's), smaller units only add per-unit work.
+    // (units of the coarser cut: ~ total_work / (1.36 * min_unit), measured on the M=8 trees)
+    if (n_solves < 8 && thresh < min_unit && cfg->target_units <= 0 &&
+        total_work / (1.36 * min_unit) >= resident_groups * nranks)
+        min_unit *= 0.5;
     if (thresh < min_unit) thresh = min_unit;
     if (thresh >= tab.W[L]) thresh = tab.W[L]; // one WHOLE unit per solve
     {
