@@ -564,7 +564,6 @@ template <typename T> struct Frame {
 // warp's accesses to one field on 16 distinct bank pairs (two wavefronts for a 64-bit field: the minimum)
 static_assert(sizeof(Frame<double>) % 8 == 0 && (sizeof(Frame<double>) / 8) % 2 == 1, "Frame<double> stride");
 static_assert(sizeof(Frame<float>) % 8 == 0 && (sizeof(Frame<float>) / 8) % 2 == 1, "Frame<float> stride");
-enum { SITE_UPPER = 0, SITE_MINE = 1, SITE_OTHER = 2 };
 enum { CMB_ALL = 0, CMB_PARTIAL = 1, CMB_FINAL = 2 };
 constexpr int kXTail = 8; // xbuf tail: [0..3] 16-bit chunks of the call hash, [4] wall hits, [5..7] spare
 enum { PH_B2 = 0, PH_B4 = 1, PH_V = 2, PH_W = 3 };
@@ -999,7 +998,6 @@ __device__ __forceinline__ T site_term(const MlpParams<T>& P, int si, const T* v
 constexpr int kCmbStage = kMaxL + 1 + 3 * (kMaxL + 1);
 constexpr int kBigNode = 4096;   // units of one node above which several blocks share the sum
 constexpr unsigned long long kExpandSplitBelow = 32768; // (sites x solves) of a geometry pass below which its points are spread over lane groups
-constexpr int kStageBlocks = 64; // blocks per such node
 // STATS = false: a launch that cannot contain the root of a solve that wants an error bar — the 21 doubles of the
 // level statistics then never exist (they cost the kernel 42 registers and a stack frame whoever the node is).
 template <typename T, bool STATS = true>
@@ -1183,6 +1181,63 @@ __device__ __forceinline__ void combine_item(const MlpParams<T>& P, const int32_
     }
 }
 
+// One thread's part (`tid` of `nthreads`) of share `share` of `nshare` of a node's pre-reduction: its units and — with
+// `with_sites`, the crown partial pass of a sharded solve — its sites, summed per level into Bl / Gs (and, for the root
+// of a solve that wants an error bar, the level statistics).  Shared by mlp_prereduce_kernel (a block's threads, then
+// reduced over the block) and the test-only host emulation (one thread).
+template <typename T, bool STATS>
+__device__ __forceinline__ void prereduce_share(const MlpParams<T>& P, const PlanNode& nd, int nidx, int solve, int share, int nshare,
+                                                bool with_sites, int mode, int tid, int nthreads, T* Bl, T& Gs, double* Ns,
+                                                double* Sm, double* Sq)
+{
+    const int nu = nd.unit_end - nd.unit_begin;
+    const double* part = P.partial + (u64)solve * P.n_units;
+    const bool stats = STATS && nidx == 0 && P.lvstat != nullptr;
+    const double* rsq = stats ? P.rootsq + (u64)solve * P.rootsq_stride : nullptr;
+    const int per = (nu + nshare - 1) / nshare;
+    const int u0 = nd.unit_begin + share * per;
+    const int u1 = u0 + per < nd.unit_end ? u0 + per : nd.unit_end;
+    for (int u = u0 + tid; u < u1; u += nthreads) {
+        if (mode == CMB_PARTIAL && !P.unit_mine[u]) continue;
+        const int tag = P.unit_tag[u];
+        const T v = (T)part[u];
+        const int sl = (tag >> 4) == UNIT_G ? P.L : (tag & 15);
+        if ((tag >> 4) == UNIT_G) Gs += v;
+        else {
+#pragma unroll
+            for (int l = 0; l < kMaxL; ++l)
+                if (l == (tag & 15)) Bl[l] += v;
+        }
+        if (stats) {
+            const PlanUnit un = P.units[u];
+#pragma unroll
+            for (int l = 0; l <= kMaxL; ++l)
+                if (l == sl) { Ns[l] += (double)(un.k1 - un.k0); Sm[l] += rsq[2 * u]; Sq[l] += rsq[2 * u + 1]; }
+        }
+    }
+    if (with_sites) { // this share of the node's sites
+        const T* val = P.value + (u64)solve * P.n_nodes;
+        const T* feat = P.feat + (u64)solve * P.n_points;
+        const int ns = nd.site_end - nd.site_begin, sper = (ns + nshare - 1) / nshare;
+        const int s0 = nd.site_begin + share * sper;
+        const int s1 = s0 + sper < nd.site_end ? s0 + sper : nd.site_end;
+        for (int si = s0 + tid; si < s1; si += nthreads) {
+            if (mode != CMB_ALL) {
+                const int cls = P.site_cls[si];
+                if (mode == CMB_PARTIAL ? cls != SITE_MINE : cls != SITE_UPPER) continue;
+            }
+            int l;
+            const T add = site_term<T>(P, si, val, part, feat, &l);
+#pragma unroll
+            for (int q = 0; q < kMaxL; ++q)
+                if (q == l) {
+                    Bl[q] += add;
+                    if (stats) { Ns[q] += 1.0; Sm[q] += (double)add; Sq[q] += (double)add * (double)add; }
+                }
+        }
+    }
+}
+
 // points[solve][0] <- x0 (padded with zeros)
 template <typename T>
 __device__ __forceinline__ void init_item(const MlpParams<T>& P, const T* x0, u64 q)
@@ -1320,12 +1375,7 @@ __global__ void __launch_bounds__(256, 3) mlp_prereduce_kernel(const __grid_cons
     const PlanNode nd = P.nodes[nidx];
     const int nu = nd.unit_end - nd.unit_begin;
     if (!jobs && nu <= kBigNode) return;
-    const double* part = P.partial + (u64)solve * P.n_units;
     const bool stats = STATS && nidx == 0 && P.lvstat != nullptr;
-    const double* rsq = stats ? P.rootsq + (u64)solve * P.rootsq_stride : nullptr;
-    const int per = (nu + nshare - 1) / nshare;
-    const int u0 = nd.unit_begin + share * per;
-    const int u1 = u0 + per < nd.unit_end ? u0 + per : nd.unit_end;
     T Bl[kMaxL];
     T Gs = (T)0;
     double Ns[kMaxL + 1], Sm[kMaxL + 1], Sq[kMaxL + 1];
@@ -1333,45 +1383,8 @@ __global__ void __launch_bounds__(256, 3) mlp_prereduce_kernel(const __grid_cons
     for (int l = 0; l < kMaxL; ++l) Bl[l] = (T)0;
 #pragma unroll
     for (int l = 0; l <= kMaxL; ++l) { Ns[l] = 0.0; Sm[l] = 0.0; Sq[l] = 0.0; }
-    for (int u = u0 + (int)threadIdx.x; u < u1; u += (int)blockDim.x) {
-        if (mode == CMB_PARTIAL && !P.unit_mine[u]) continue;
-        const int tag = P.unit_tag[u];
-        const T v = (T)part[u];
-        const int sl = (tag >> 4) == UNIT_G ? P.L : (tag & 15);
-        if ((tag >> 4) == UNIT_G) Gs += v;
-        else {
-#pragma unroll
-            for (int l = 0; l < kMaxL; ++l)
-                if (l == (tag & 15)) Bl[l] += v;
-        }
-        if (stats) {
-            const PlanUnit un = P.units[u];
-#pragma unroll
-            for (int l = 0; l <= kMaxL; ++l)
-                if (l == sl) { Ns[l] += (double)(un.k1 - un.k0); Sm[l] += rsq[2 * u]; Sq[l] += rsq[2 * u + 1]; }
-        }
-    }
-    if (jobs) { // this share of the node's sites
-        const T* val = P.value + (u64)solve * P.n_nodes;
-        const T* feat = P.feat + (u64)solve * P.n_points;
-        const int ns = nd.site_end - nd.site_begin, sper = (ns + nshare - 1) / nshare;
-        const int s0 = nd.site_begin + share * sper;
-        const int s1 = s0 + sper < nd.site_end ? s0 + sper : nd.site_end;
-        for (int si = s0 + (int)threadIdx.x; si < s1; si += (int)blockDim.x) {
-            if (mode != CMB_ALL) {
-                const int cls = P.site_cls[si];
-                if (mode == CMB_PARTIAL ? cls != SITE_MINE : cls != SITE_UPPER) continue;
-            }
-            int l;
-            const T add = site_term<T>(P, si, val, part, feat, &l);
-#pragma unroll
-            for (int q = 0; q < kMaxL; ++q)
-                if (q == l) {
-                    Bl[q] += add;
-                    if (stats) { Ns[q] += 1.0; Sm[q] += (double)add; Sq[q] += (double)add * (double)add; }
-                }
-        }
-    }
+    prereduce_share<T, STATS>(P, nd, nidx, solve, share, nshare, jobs != nullptr, mode, (int)threadIdx.x, (int)blockDim.x, Bl, Gs, Ns,
+                              Sm, Sq);
     for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
         for (int l = 0; l < kMaxL; ++l) Bl[l] += __shfl_xor_sync(0xffffffffu, Bl[l], o);

@@ -152,25 +152,7 @@ int get_sharding(hdp_context* h, const std::string& plan_key, const MlpPlan& pla
     if ((rc = upload(h, sh->unit_mine, &sh->d_unit_mine)) != HDP_OK) return rc;
     if ((rc = upload(h, sh->site_cls, &sh->d_site_cls)) != HDP_OK) return rc;
     if ((rc = upload(h, sh->node_slot, &sh->d_node_slot)) != HDP_OK) return rc;
-    // shares of the crown partial pass: about two thousand units (a site of this rank counts as sixteen: 1 + K
-    // evaluations of f behind three dependent loads) per block of 256 threads, at most kStageBlocks per node; a
-    // light node (C4: 4312 crown nodes of a few dozen sites) gets none and is walked by its warp of the combine launch
-    sh->crown_job_off.assign(1, 0);
-    for (size_t k = 0; k < sh->crown_nodes.size(); ++k) {
-        const PlanNode& nd = plan.nodes[sh->crown_nodes[k]];
-        const int nu = nd.unit_end - nd.unit_begin;
-        const bool leaf = nu == 1 && nd.site_end == nd.site_begin && (plan.unit_tag[nd.unit_begin] >> 4) == UNIT_WHOLE;
-        int nb = 0;
-        if (!leaf) {
-            long work = nu;
-            for (int si = nd.site_begin; si < nd.site_end; ++si)
-                if (sh->site_cls[si] == SITE_MINE) work += 16;
-            nb = work <= 512 ? 0 : (int)std::min<long>(std::max<long>((work + 2047) / 2048, 1), kStageBlocks);
-        }
-        sh->crown_heavy += nb > 0;
-        for (int b = 0; b < nb; ++b) { sh->crown_jobs.push_back((int32_t)k); sh->crown_jobs.push_back(b); }
-        sh->crown_job_off.push_back((int32_t)(sh->crown_jobs.size() / 2));
-    }
+    mlp_build_crown_jobs(plan, sh.get()); // shares of the crown partial pass
     if ((rc = upload(h, sh->crown_jobs, &sh->d_crown_jobs)) != HDP_OK) return rc;
     if ((rc = upload(h, sh->crown_job_off, &sh->d_crown_job_off)) != HDP_OK) return rc;
     h->shardings[key] = sh;

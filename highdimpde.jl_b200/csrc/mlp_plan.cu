@@ -372,4 +372,27 @@ void mlp_build_sharding(const MlpPlan& plan, int nranks, int rank, MlpSharding* 
     }
 }
 
+void mlp_build_crown_jobs(const MlpPlan& plan, MlpSharding* sh, long light_below, long per_share)
+{
+    sh->crown_jobs.clear();
+    sh->crown_job_off.assign(1, 0);
+    sh->crown_heavy = 0;
+    for (size_t k = 0; k < sh->crown_nodes.size(); ++k) {
+        const PlanNode& nd = plan.nodes[sh->crown_nodes[k]];
+        const int nu = nd.unit_end - nd.unit_begin;
+        const bool leaf = nu == 1 && nd.site_end == nd.site_begin && (plan.unit_tag[nd.unit_begin] >> 4) == UNIT_WHOLE;
+        int nb = 0;
+        if (!leaf) {
+            long work = nu;
+            for (int si = nd.site_begin; si < nd.site_end; ++si)
+                if (sh->site_cls[si] == SITE_MINE) work += 16;
+            nb = work <= light_below ? 0 : (int)std::min<long>(std::max<long>((work + per_share - 1) / per_share, 1), kStageBlocks);
+        }
+        sh->crown_heavy += nb > 0;
+        for (int b = 0; b < nb; ++b) { sh->crown_jobs.push_back((int32_t)k); sh->crown_jobs.push_back(b); }
+        sh->crown_job_off.push_back((int32_t)(sh->crown_jobs.size() / 2));
+    }
+}
+
+
 } // namespace hdp

@@ -111,5 +111,10 @@ struct MlpSharding {
 };
 // own_items: ownership roots per rank to aim for (0: the default, 64; tests lower it to nest explicit sites below a root)
 void mlp_build_sharding(const MlpPlan& plan, int nranks, int rank, MlpSharding* out, double own_items = 0);
+// Shares of the crown partial pass (crown_job_off, crown_jobs, crown_heavy): about `per_share` units per block of
+// 256 threads — a site of this rank counts as sixteen: 1 + K evaluations of f behind three dependent loads —, at most
+// kStageBlocks per node; a node of at most `light_below` such units gets none and is walked by its warp of the
+// combine launch (C4: 4312 crown nodes of a few dozen sites).  (Tests lower both to force shares on small trees.)
+void mlp_build_crown_jobs(const MlpPlan& plan, MlpSharding* sh, long light_below = 512, long per_share = 2048);
 
 } // namespace hdp

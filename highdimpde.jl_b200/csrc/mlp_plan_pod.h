@@ -10,6 +10,10 @@ namespace hdp {
 constexpr int kMaxL = 6; // == HDP_MAX_LEVELS (include/hdpde.h)
 
 enum { UNIT_LEVEL = 0, UNIT_G = 1, UNIT_WHOLE = 2 };
+// class of a site in a sharded solve (MlpSharding::site_cls): replicated above the ownership roots / at or below an
+// ownership root of this rank / of another rank
+enum { SITE_UPPER = 0, SITE_MINE = 1, SITE_OTHER = 2 };
+constexpr int kStageBlocks = 64; // most blocks that share the pre-reduction of one node (mlp_prereduce_kernel)
 
 struct PlanUnit {
     int32_t node;

@@ -24,6 +24,12 @@ MlpSharding::~MlpSharding() {}
 // explicit sites nest below an ownership root on small trees
 static double g_own_items = 0;
 extern "C" void hdp_emu_set_own_items(double v) { g_own_items = v; }
+// shares of the crown partial pass (mlp_build_crown_jobs): the library's values unless a test lowers them to force
+// several shares per node on a small tree
+static long g_job_light = 512, g_job_share = 2048;
+extern "C" void hdp_emu_set_crown_jobs(long light_below, long per_share) { g_job_light = light_below; g_job_share = per_share; }
+static long g_jobs_used = 0; // crown partial passes that went through the shares (tests assert the path was taken)
+extern "C" long hdp_emu_crown_jobs_used(void) { return g_jobs_used; }
 
 // nranks > 1 emulates a solve sharded over several GPUs (MlpSharding).  In one process the ranks run one after
 // the other on private copies of the per-call state, their exchange buffers are summed as the all-reduce would,
@@ -111,6 +117,7 @@ template <typename T> struct EmuSolve {
             S.points_raw.resize(((size_t)n_solves * P.n_points * P.dpad * sizeof(T)) / sizeof(double2) + 2);
             if (nranks > 1) {
                 mlp_build_sharding(plan, nranks, r, &S.sh, g_own_items);
+                mlp_build_crown_jobs(plan, &S.sh, g_job_light, g_job_share);
                 xstride = S.sh.n_slots + 3 * (kMaxL + 1);
                 S.xbuf.assign((size_t)n_solves * xstride + kXTail, 0.0);
             }
@@ -174,7 +181,37 @@ template <typename T> struct EmuSolve {
             for (int dep = plan.max_depth; dep >= 0; --dep)
                 combine_list(S.sh.owned_nodes.data() + S.sh.owned_depth_off[dep],
                              S.sh.owned_depth_off[dep + 1] - S.sh.owned_depth_off[dep], CMB_ALL);
-            combine_list(S.sh.crown_nodes.data(), (int)S.sh.crown_nodes.size(), CMB_PARTIAL);
+            if (S.sh.crown_heavy >= 2) {
+                // the library's crown partial pass by shares (k_mlp_host.cu): every job sums its share of a node's units
+                // and of this rank's sites into a record (mlp_prereduce_kernel: here one thread per block), then the
+                // combine pass adds the records of a node up; light nodes are walked directly
+                const int n_jobs = (int)(S.sh.crown_jobs.size() / 2);
+                std::vector<double> stage((size_t)n_solves * n_jobs * kCmbStage, 0.0);
+                for (int sv = 0; sv < n_solves; ++sv)
+                    for (int j = 0; j < n_jobs; ++j) {
+                        const int k = S.sh.crown_jobs[2 * j], share = S.sh.crown_jobs[2 * j + 1];
+                        const int nshare = S.sh.crown_job_off[k + 1] - S.sh.crown_job_off[k];
+                        const int nidx = S.sh.crown_nodes[k];
+                        T Bl[kMaxL], Gs = (T)0;
+                        double Ns[kMaxL + 1], Sm[kMaxL + 1], Sq[kMaxL + 1];
+                        for (int l = 0; l < kMaxL; ++l) Bl[l] = (T)0;
+                        for (int l = 0; l <= kMaxL; ++l) { Ns[l] = 0.0; Sm[l] = 0.0; Sq[l] = 0.0; }
+                        prereduce_share<T, true>(P, P.nodes[nidx], nidx, sv, share, nshare, true, CMB_PARTIAL, 0, 1, Bl, Gs, Ns, Sm, Sq);
+                        double* q = stage.data() + ((size_t)sv * n_jobs + j) * kCmbStage;
+                        for (int l = 0; l < kMaxL; ++l) q[l] = (double)Bl[l];
+                        q[kMaxL] = (double)Gs;
+                        for (int l = 0; l <= kMaxL; ++l) { q[kMaxL + 1 + 3 * l] = Ns[l]; q[kMaxL + 2 + 3 * l] = Sm[l]; q[kMaxL + 3 + 3 * l] = Sq[l]; }
+                    }
+                P.stage = stage.data();
+                P.stage_off = S.sh.crown_job_off.data();
+                P.stage_jobs = n_jobs;
+                combine_list(S.sh.crown_nodes.data(), (int)S.sh.crown_nodes.size(), CMB_PARTIAL);
+                P.stage = nullptr;
+                P.stage_off = nullptr;
+                P.stage_jobs = 0;
+                ++g_jobs_used;
+            } else
+                combine_list(S.sh.crown_nodes.data(), (int)S.sh.crown_nodes.size(), CMB_PARTIAL);
             S.xbuf[(size_t)n_solves * xstride + 4] = (double)S.ctr[1];
             S.xbuf[(size_t)n_solves * xstride + 5] = (double)S.flags[0]; // (the library reads its flag per rank; here it rides along)
         }

@@ -302,6 +302,45 @@ def test_long_sites_and_nested_ownership_match_the_oracle(H, O, emu):
         emu.hdp_emu_set_own_items(C.c_double(0.0))
 
 
+def test_crown_partial_pass_by_shares_matches_oracle(H, O, emu):
+    """The crown partial pass of a sharded solve by per-node shares (mlp_build_crown_jobs -> prereduce_share ->
+    combine_item over the records; on the GPU: mlp_prereduce_kernel with jobs, then mlp_combine_kernel): the share
+    sizes are lowered so that the crown nodes of a small tree are split over several shares each, for a local and a
+    non-local problem, 2 to 8 emulated ranks, with the error bar.  Same tapes: the oracle's value and wall-hit count;
+    the standard error equals the unsharded solve's."""
+    emu.hdp_emu_set_crown_jobs.argtypes = [C.c_long, C.c_long]
+    emu.hdp_emu_crown_jobs_used.restype = C.c_long
+    dt = np.float64
+    cases = [
+        (H.ParabolicPDEProblem(0.0, 0.7, np.zeros(3), (0.0, 0.5), g=H.ExpSumSq(0.25), f=H.FAllenCahn(1.0), neumann_bc=(-0.5, 0.5)),
+         H.MLP(M=4, L=4, K=3), False),
+        (H.PIDEProblem(0.0, 0.4, np.zeros(2), (0.0, 0.5), H.ExpSumSq(0.25), H.FNLFisher(), neumann_bc=(-0.5, 0.5)),
+         H.MLP(M=3, L=3, K=8, mc_sample=H.UniformSampling(-0.5, 0.5)), True),
+    ]
+    try:
+        for prob, alg, nl in cases:
+            tapes = random_tapes(H, prob, alg, dt, seed=11)
+            uo, info = oracle_solve(H, O, prob, alg, dt, tapes)
+            cn = H.mlp_counts(alg.M, alg.L, alg.K, nonlocal_=nl)
+            target = int((cn["path_steps"] + 0.5 * cn["sampler_calls"]) / 8.0)   # a fine cut: many units per crown node
+            u1, rc1, st1 = emu_solve(H, emu, prob, alg, dt, tapes=tapes, target_units=target, nranks=1, std_err=True)
+            assert rc1 == 0 and rel_err(float(u1[0]), uo) <= 1e-12
+            for light, per_share in ((0, 4), (2, 16), (512, 2048)):
+                emu.hdp_emu_set_crown_jobs(light, per_share)
+                for nranks in (2, 3, 8):
+                    before = emu.hdp_emu_crown_jobs_used()
+                    u, rc, st = emu_solve(H, emu, prob, alg, dt, tapes=tapes, target_units=target, nranks=nranks, std_err=True)
+                    assert rc == 0
+                    assert rel_err(float(u[0]), uo) <= 1e-12, (light, per_share, nranks, float(u[0]), uo)
+                    assert st.bounces == info["bounces"], (light, per_share, nranks)
+                    assert abs(st.std_error - st1.std_error) <= 1e-10 * st1.std_error, (st.std_error, st1.std_error)
+                    assert list(st.level_n) == list(st1.level_n)
+                    if per_share <= 16:   # the path under test was taken (by every emulated rank)
+                        assert emu.hdp_emu_crown_jobs_used() >= before + nranks, (light, per_share, nranks)
+    finally:
+        emu.hdp_emu_set_crown_jobs(512, 2048)
+
+
 def alg_work(H, alg):
     cn = H.mlp_counts(alg.M, alg.L, alg.K, nonlocal_=True)
     return cn["path_steps"] + 0.5 * cn["sampler_calls"]
