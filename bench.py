@@ -16,8 +16,12 @@ configs[2] (C3: B=8192, d=100, N=10, fp32).
 `e2e`    : the same metric through the public API `_ml_picard_batch` (the call `solve` makes):
            host buffers in, host→device copy of x0 and device→host read of u inside the timed
            region, wall clock around each call with a stream sync on both sides.
+`extra.strong` (N > 1): ONE solve sharded over the N ranks by subtree ownership, one exchange of a double per crown
+           node through the library's own kernel over NVLink peer windows (hdp_peer_window_*; ncclAllReduce where
+           no peer path exists), against the same solve on one GPU; max over ranks, best of 5.
 `--impl reference`: the reference's algorithm on the host cores (the C oracle port — Julia is
-           not in this image), every host thread busy with independent serial solves.
+           not in this image), every host thread busy with independent serial solves (dynamic schedule,
+           16 solves per thread and step).
 """
 from __future__ import annotations
 

@@ -18,6 +18,46 @@ def _free_port():
     return p
 
 
+class _FakeHandle:
+    """Stands in for hdpde_b200.Handle in the handshake test: records the calls, fails where told to."""
+
+    def __init__(self, H, rank, fail_export=False, fail_attach=False):
+        self.H, self.rank, self.fail_export, self.fail_attach = H, rank, fail_export, fail_attach
+        self.attached, self.detached, self.seen = None, 0, None
+
+    def peer_window_export(self):
+        if self.fail_export:
+            raise self.H.HdpError(self.H.capi.HDP_ERR_CUDA, "no window")
+        return bytes([self.rank + 1]) * self.H.capi.HDP_PEER_HANDLE_BYTES
+
+    def peer_window_attach(self, handles, nranks, rank):
+        self.seen = (handles, nranks, rank)
+        if self.fail_attach:
+            raise self.H.HdpError(self.H.capi.HDP_ERR_CUDA, "no peer path")
+        self.attached = nranks
+
+    def peer_window_detach(self):
+        self.detached += 1
+        self.attached = None
+
+
+def _peer_window_handshake(rank, world, H, D):
+    nb = H.capi.HDP_PEER_HANDLE_BYTES
+    # every rank fine: attached everywhere, each rank was given all handles in rank order
+    h = _FakeHandle(H, rank)
+    assert D.attach_peer_windows(h) is True
+    assert h.attached == world and h.detached == 0
+    assert h.seen == (b"".join(bytes([r + 1]) * nb for r in range(world)), world, rank)
+    # the last rank cannot map its peers: everyone detaches, including the ranks whose own attach succeeded
+    h = _FakeHandle(H, rank, fail_attach=(rank == world - 1))
+    assert D.attach_peer_windows(h) is False
+    assert h.attached is None and h.detached == 1
+    # rank 0 cannot even export: nobody tries to attach, everyone detaches
+    h = _FakeHandle(H, rank, fail_export=(rank == 0))
+    assert D.attach_peer_windows(h) is False
+    assert h.seen is None and h.attached is None and h.detached == 1
+
+
 def _worker(rank, world, port, q):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -51,6 +91,9 @@ def _worker(rank, world, port, q):
         #    compiled for the host (tests/hostemu): each process runs its rank's geometry, units and local combine,
         #    the exchange buffers are summed by a real all-reduce, each rank finishes the crown.
         _sharded_solve(rank, world, H, D)
+        # 6. the peer-window handshake (dist.attach_peer_windows) is all or nothing: handles gathered in rank order,
+        #    and one rank that cannot export or cannot map a peer makes EVERY rank detach (they then all keep NCCL)
+        _peer_window_handshake(rank, world, H, D)
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))
