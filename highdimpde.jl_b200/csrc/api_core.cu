@@ -142,10 +142,18 @@ extern "C" int hdp_sync(hdp_handle h)
     if (!h) return HDP_ERR_BAD_ARG;
     std::lock_guard<std::mutex> lk(h->mu);
     DeviceGuard g(h->device);
-    int f = 0;
-    HDP_CUDA(h, cudaMemcpyAsync(&f, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    int f[3] = {0, 0, 0}; // [0] start point outside the box, [1] kernel / mode mismatch, [2] peer exchange timed out
+    HDP_CUDA(h, cudaMemcpyAsync(f, h->d_flags, sizeof(f), cudaMemcpyDeviceToHost, h->stream));
     HDP_CUDA(h, cudaStreamSynchronize(h->stream));
-    if (f) {
+    if (f[2]) {
+        cudaMemsetAsync(h->d_flags, 0, sizeof(f), h->stream);
+        return set_err(h, HDP_ERR_NCCL, "an asynchronous sharded solve: a peer did not reach the exchange within 20 s");
+    }
+    if (f[1]) {
+        cudaMemsetAsync(h->d_flags, 0, sizeof(f), h->stream);
+        return set_err(h, HDP_ERR_UNSUPPORTED, "internal: the units kernel launched does not match the mode of the problem");
+    }
+    if (f[0]) {
         cudaMemsetAsync(h->d_flags, 0, sizeof(int), h->stream);
         return set_err(h, HDP_ERR_START_OUTSIDE_DOMAIN, "an asynchronous call found a start point outside the hypercube");
     }
