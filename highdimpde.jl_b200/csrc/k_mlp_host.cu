@@ -652,8 +652,6 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
                                      sh->owned_depth_off[dep + 1] - off, CMB_ALL)) != HDP_OK)
                 return rc;
         }
-        // (the root first and alone: it has thousands of children and takes a block of lanes, the other crown
-        // nodes a few lanes each — one launch sized for the root spent 95 us on 4313 blocks of 512 threads)
         const int n_jobs = (int)(sh->crown_jobs.size() / 2);
         // (one heavy node only — the root of C4, its other 4312 crown nodes are light — gains nothing over root first, rest after)
         if (!um && n_solves <= 65535 && sh->crown_heavy >= 2) {
@@ -686,6 +684,8 @@ int mlp_solve_impl(hdp_handle h, const hdp_problem* prob, const hdp_mlp_cfg* cfg
             h->launches++;
             trace("combine_partial", cnt);
         } else {
+            // (the root first and alone: it has thousands of children and takes a block of lanes, the other crown
+            // nodes a few lanes each — one launch sized for the root spent 95 us on 4313 blocks of 512 threads)
             if ((rc = launch_combine((const int32_t*)sh->d_crown_nodes, sh->crown_nodes.data(), 1, CMB_PARTIAL)) != HDP_OK) return rc;
             if ((rc = launch_combine((const int32_t*)sh->d_crown_nodes + 1, sh->crown_nodes.data() + 1,
                                      (int)sh->crown_nodes.size() - 1, CMB_PARTIAL)) != HDP_OK)
