@@ -316,6 +316,53 @@ extern "C" int hdp_emu_mlp_solve_sharded_f32(const hdp_problem* prob, const hdp_
 {
     return emu_solve<float>(prob, cfg, x0, u_out, stats, nranks);
 }
+// The share table of the crown partial pass (mlp_build_crown_jobs) of one rank, checked structurally:
+// returns 0 when every invariant holds, else the number of the first one that fails.
+// out: [heavy nodes, jobs, light non-leaf nodes, leaves, units covered by shares, sites covered by shares]
+extern "C" int hdp_emu_crown_jobs_check(int M, int L, int K, int nonlocal, double thresh, int nranks, int rank, long light_below,
+                                        long per_share, int64_t out[6])
+{
+    MlpPlan plan;
+    mlp_build_plan(M, L, K, nonlocal != 0, thresh, 0, &plan);
+    MlpSharding sh;
+    mlp_build_sharding(plan, nranks, rank, &sh, g_own_items);
+    mlp_build_crown_jobs(plan, &sh, light_below, per_share);
+    for (int q = 0; q < 6; ++q) out[q] = 0;
+    const size_t nc = sh.crown_nodes.size();
+    if (sh.crown_job_off.size() != nc + 1 || sh.crown_job_off[0] != 0) return 1;
+    if (sh.crown_jobs.size() != 2 * (size_t)sh.crown_job_off[nc]) return 2;
+    out[1] = sh.crown_job_off[nc];
+    for (size_t k = 0; k < nc; ++k) {
+        const PlanNode& nd = plan.nodes[sh.crown_nodes[k]];
+        const int nb = sh.crown_job_off[k + 1] - sh.crown_job_off[k];
+        if (nb < 0 || nb > kStageBlocks) return 3;
+        const int nu = nd.unit_end - nd.unit_begin, ns = nd.site_end - nd.site_begin;
+        const bool leaf = nu == 1 && ns == 0 && (plan.unit_tag[nd.unit_begin] >> 4) == UNIT_WHOLE;
+        if (leaf) { if (nb != 0) return 4; out[3]++; continue; }
+        if (nb == 0) { out[2]++; continue; }
+        out[0]++;
+        // the jobs of node k are (k, 0) .. (k, nb - 1), in order
+        for (int b = 0; b < nb; ++b) {
+            const int j = sh.crown_job_off[k] + b;
+            if (sh.crown_jobs[2 * j] != (int32_t)k || sh.crown_jobs[2 * j + 1] != b) return 5;
+        }
+        // the shares as prereduce_share cuts them tile the node's units and sites exactly once
+        std::vector<int> ucover(nu, 0), scover(ns, 0);
+        for (int b = 0; b < nb; ++b) {
+            const int per = (nu + nb - 1) / nb, u0 = nd.unit_begin + b * per, u1 = std::min(u0 + per, nd.unit_end);
+            for (int u = u0; u < u1; ++u) ucover[u - nd.unit_begin]++;
+            const int sper = (ns + nb - 1) / nb, s0 = nd.site_begin + b * sper, s1 = std::min(s0 + sper, nd.site_end);
+            for (int si = s0; si < s1; ++si) scover[si - nd.site_begin]++;
+        }
+        for (int c : ucover) if (c != 1) return 6;
+        for (int c : scover) if (c != 1) return 7;
+        out[4] += nu;
+        out[5] += ns;
+    }
+    if (sh.crown_heavy != (int)out[0]) return 8;
+    return 0;
+}
+
 // the sharding of a plan, summarised: [n_slots, crown nodes, crown leaves, upper sites, sites at or below an ownership root (all ranks),
 // owned nodes (this rank), units (this rank), 1000 * busiest rank's modelled load / mean load]
 extern "C" void hdp_emu_sharding_summary(int M, int L, int K, int nonlocal, double thresh, int nranks, int rank, int64_t out[8])

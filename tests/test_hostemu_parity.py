@@ -302,6 +302,28 @@ def test_long_sites_and_nested_ownership_match_the_oracle(H, O, emu):
         emu.hdp_emu_set_own_items(C.c_double(0.0))
 
 
+def test_crown_share_table_tiles_every_heavy_node(emu):
+    """mlp_build_crown_jobs: jobs (k, 0..nb-1) in order, leaves and light nodes without jobs, at most 64 shares per
+    node, and the shares — cut as prereduce_share cuts them — cover every unit and every site of a heavy node exactly
+    once.  Trees of the strong-scaling cases (Allen-Cahn M=8, C4) at the library's thresholds and small ones forced."""
+    emu.hdp_emu_crown_jobs_check.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_long, C.c_long,
+                                             C.POINTER(C.c_int64)]
+    out = (C.c_int64 * 6)()
+    heavy_seen = 0
+    big = ((8, 5, 10, 0, 8.0), (4, 5, 10, 1, 16.0))     # the library's thresholds, 8 ranks, one rank each
+    small = ((8, 4, 10, 0, 8.0), (4, 4, 3, 0, 8.0), (3, 3, 8, 1, 20.0))
+    combos = [(t, 8, 512, 2048, (0,)) for t in big]
+    combos += [(t, nr, light, ps, (0, nr - 1)) for t in small for nr in (2, 3, 8) for light, ps in ((512, 2048), (0, 4), (8, 64))]
+    for (M, L, K, nl, thresh), nranks, light, per_share, ranks in combos:
+        for rank in ranks:
+            rc = emu.hdp_emu_crown_jobs_check(M, L, K, nl, thresh, nranks, rank, light, per_share, out)
+            assert rc == 0, (M, L, K, nl, nranks, rank, light, per_share, rc, list(out))
+            heavy_seen += out[0]
+            if out[0]:
+                assert out[1] >= out[0] and out[4] > 0
+    assert heavy_seen > 0
+
+
 def test_crown_partial_pass_by_shares_matches_oracle(H, O, emu):
     """The crown partial pass of a sharded solve by per-node shares (mlp_build_crown_jobs -> prereduce_share ->
     combine_item over the records; on the GPU: mlp_prereduce_kernel with jobs, then mlp_combine_kernel): the share
