@@ -407,14 +407,14 @@ def bench_strong(torch, dist, H, HD, local_rank, rank, world, reps=5):
         # sharded call does, so that the line carries the Monte-Carlo standard error of the value)
         dist.barrier()
         use, stse = H._ml_picard_batch(prob, alg, n_solves=1, seed=seed, handle=hc, std_err=True)
-        assert abs(float(use[0]) - un) <= 1e-13 * abs(un)
-        stn = dict(stn, std_err=stse["std_err"])
+        stn = dict(stn, std_err=stse["std_err"], value_with_std_err_rel_diff=abs(float(use[0]) - un) / abs(un))
         ms1 = HD.min_over_ranks(best1)  # (every rank timed the 1-GPU solve; identical GPUs)
         alln = HD.all_gather_object(un)
         out[name] = {"path_steps": st1["path_steps"], "ms_1gpu": ms1, "ms_sharded": bestn, "speedup": ms1 / bestn,
                      "n_gpus": world, "u_1gpu": u1, "u_sharded": un, "rel_vs_1gpu": abs(un - u1) / abs(u1),
                      "identical_on_all_ranks": all(v == alln[0] for v in alln),
                      "std_err": float(stn["std_err"][0]),
+                     "value_with_std_err_rel_diff": stn["value_with_std_err_rel_diff"],   # the same solve asked for its error bar: 0 expected
                      "units_1gpu": st1["n_units"], "units_sharded": stn["n_units"], "group_1gpu": st1["group_size"],
                      "group_sharded": stn["group_size"], "exchange_bytes": stn["exchange_bytes"],
                      "exchange": stn["exchange_kind"],
